@@ -1,0 +1,701 @@
+// assemble.cu — element kernels + the merge as a deterministic, atomic-free gather.            (compiled --fmad=false)
+//
+// Reference being replaced: the serial element loop + scatter-add
+//   emat = kernel(p0..);  Matrix::merge_for_array_blk(&emat, node2vtx, &mut col2idx)      del-fem-cpu/src/sparse_square.rs:180-214
+//   merge::csrdia / merge::blkcsr                                                          del-fem-cpu/src/merge.rs:3-88
+//   Matrix::merge                                                                          del-fem-ls/src/sparse_square.rs:66-104
+// whose floating-point accumulation order into a given nonzero is "ascending element index".
+//
+// Here: dfb_plan_create inverts the element->nonzero map once per (pattern, mesh): for every nonzero slot (off-diagonal
+// idx, or nnz+row for the separate diagonal) the list of contributions (e,i,j), sorted ascending.  dfb_assemble then runs
+// one thread per slot that walks its list in that order, recomputes the (i,j) block of each element matrix from the
+// vertex coordinates (no 1152 B/tet scratch) and writes the sum once: no atomics, no set_zero pass, bit-reproducible.
+// This translation unit is compiled with --fmad=false and the element formulas are written operation-for-operation like
+// the reference's (no contraction in rustc either), so linear kernels reproduce the serial result bit-for-bit.
+#include "dfb_internal.h"
+#include "reduce.cuh"
+
+static const uint32_t NO_SLOT = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------------------------------------ element formulas
+struct ElemInfo {
+  int n_node, ndim, N;
+};
+__host__ __device__ inline ElemInfo elem_info(int kind) {
+  switch (kind) {
+    case DFB_ELEM_LAPLACE_TRI2: return {3, 2, 1};
+    case DFB_ELEM_COT_LAPLACE_TRI3: return {3, 3, 1};
+    case DFB_ELEM_SOLID_LINEAR_TRI2: return {3, 2, 2};
+    case DFB_ELEM_LAPLACE_TET: return {4, 3, 1};
+    case DFB_ELEM_SOLID_LINEAR_TET: return {4, 3, 3};
+    case DFB_ELEM_NEOHOOKEAN_TET: return {4, 3, 3};
+    case DFB_ELEM_SPRING3: return {2, 3, 3};
+  }
+  return {0, 0, 0};
+}
+
+// del_geo_core::tri2::{area, dldx} (third-party; call sites laplace_tri2.rs:9-10, solid_linear_tri2.rs:28-29)
+__device__ __forceinline__ double tri2_area(const double *p0, const double *p1, const double *p2) {
+  return 0.5 * ((p1[0] - p0[0]) * (p2[1] - p0[1]) - (p2[0] - p0[0]) * (p1[1] - p0[1]));
+}
+__device__ __forceinline__ void tri2_dldx(double (&dldx)[2][3], const double *p0, const double *p1, const double *p2) {
+  const double a = tri2_area(p0, p1, p2);
+  const double t = 1.0 / (2.0 * a);
+  dldx[0][0] = t * (p1[1] - p2[1]);
+  dldx[0][1] = t * (p2[1] - p0[1]);
+  dldx[0][2] = t * (p0[1] - p1[1]);
+  dldx[1][0] = t * (p2[0] - p1[0]);
+  dldx[1][1] = t * (p0[0] - p2[0]);
+  dldx[1][2] = t * (p1[0] - p0[0]);
+}
+
+// tet volume + barycentric gradients g[i][d] = dN_i/dx_d
+__device__ __forceinline__ double tet_vol_grad(double (&g)[4][3], const double *p0, const double *p1, const double *p2,
+                                               const double *p3) {
+  double d1[3], d2[3], d3[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    d1[k] = p1[k] - p0[k];
+    d2[k] = p2[k] - p0[k];
+    d3[k] = p3[k] - p0[k];
+  }
+  const double c1[3] = {d2[1] * d3[2] - d2[2] * d3[1], d2[2] * d3[0] - d2[0] * d3[2], d2[0] * d3[1] - d2[1] * d3[0]};
+  const double c2[3] = {d3[1] * d1[2] - d3[2] * d1[1], d3[2] * d1[0] - d3[0] * d1[2], d3[0] * d1[1] - d3[1] * d1[0]};
+  const double c3[3] = {d1[1] * d2[2] - d1[2] * d2[1], d1[2] * d2[0] - d1[0] * d2[2], d1[0] * d2[1] - d1[1] * d2[0]};
+  const double det = d1[0] * c1[0] + d1[1] * c1[1] + d1[2] * c1[2];
+  const double inv = 1.0 / det;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    g[1][k] = c1[k] * inv;
+    g[2][k] = c2[k] * inv;
+    g[3][k] = c3[k] * inv;
+    g[0][k] = -(g[1][k] + g[2][k] + g[3][k]);
+  }
+  return det / 6.0;
+}
+
+// Per-element precomputation shared by all (i,j) blocks of one element.
+template <int KIND> struct ElemGeo;
+
+template <> struct ElemGeo<DFB_ELEM_LAPLACE_TRI2> {  // laplace_tri2::ddw_  laplace_tri2.rs:3-17
+  static constexpr int NNODE = 3, NDIM = 2, N = 1;
+  double area, dldx[2][3];
+  __device__ void init(const double *const *p, double, double) {
+    area = tri2_area(p[0], p[1], p[2]);
+    tri2_dldx(dldx, p[0], p[1], p[2]);
+  }
+  __device__ void block(int i, int j, double alpha, double, double *e) const {
+    e[0] = alpha * area * (dldx[0][i] * dldx[0][j] + dldx[1][i] * dldx[1][j]);
+  }
+};
+
+template <> struct ElemGeo<DFB_ELEM_COT_LAPLACE_TRI3> {  // tri3::emat_cotangent_laplacian (call site laplace_tri3.rs:18)
+  static constexpr int NNODE = 3, NDIM = 3, N = 1;
+  double cot[3];
+  __device__ void init(const double *const *p, double, double) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double *a = p[k], *b = p[(k + 1) % 3], *c = p[(k + 2) % 3];
+      const double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+      const double v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+      const double cr[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+      const double sn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+      const double cs = u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+      cot[k] = cs / sn;
+    }
+  }
+  __device__ void block(int i, int j, double, double, double *e) const {
+    const int j1 = (i + 1) % 3, k1 = (i + 2) % 3;
+    if (j == i) e[0] = 0.5 * (cot[j1] + cot[k1]);
+    else if (j == j1) e[0] = -0.5 * cot[k1];
+    else e[0] = -0.5 * cot[j1];
+  }
+};
+
+template <> struct ElemGeo<DFB_ELEM_SOLID_LINEAR_TRI2> {  // solid_linear_tri2::emat_tri2  solid_linear_tri2.rs:1-33
+  static constexpr int NNODE = 3, NDIM = 2, N = 2;
+  double w, dldx[2][3];
+  __device__ void init(const double *const *p, double, double) {
+    w = tri2_area(p[0], p[1], p[2]);
+    tri2_dldx(dldx, p[0], p[1], p[2]);
+  }
+  __device__ void block(int i, int j, double lambda, double myu, double *e) const {
+    e[0] = 0.0; e[1] = 0.0; e[2] = 0.0; e[3] = 0.0;
+    e[0] += w * (lambda + myu) * dldx[0][i] * dldx[0][j];
+    e[2] += w * (lambda * dldx[0][i] * dldx[1][j] + myu * dldx[0][j] * dldx[1][i]);
+    e[1] += w * (lambda * dldx[1][i] * dldx[0][j] + myu * dldx[1][j] * dldx[0][i]);
+    e[3] += w * (lambda + myu) * dldx[1][i] * dldx[1][j];
+    const double dtmp1 = w * myu * (dldx[1][i] * dldx[1][j] + dldx[0][i] * dldx[0][j]);
+    e[0] += dtmp1;
+    e[3] += dtmp1;
+  }
+};
+
+template <> struct ElemGeo<DFB_ELEM_LAPLACE_TET> {  // DERIVED from laplace_tri2.rs:12-15
+  static constexpr int NNODE = 4, NDIM = 3, N = 1;
+  double vol, g[4][3];
+  __device__ void init(const double *const *p, double, double) { vol = tet_vol_grad(g, p[0], p[1], p[2], p[3]); }
+  __device__ void block(int i, int j, double alpha, double, double *e) const {
+    e[0] = alpha * vol * (g[i][0] * g[j][0] + g[i][1] * g[j][1] + g[i][2] * g[j][2]);
+  }
+};
+
+template <> struct ElemGeo<DFB_ELEM_SOLID_LINEAR_TET> {  // DERIVED from solid_linear_tri2.rs:11-19, solid_linear_hex.rs:18-25
+  static constexpr int NNODE = 4, NDIM = 3, N = 3;
+  double vol, g[4][3];
+  __device__ void init(const double *const *p, double, double) { vol = tet_vol_grad(g, p[0], p[1], p[2], p[3]); }
+  __device__ void block(int i, int j, double lambda, double myu, double *e) const {
+    double dtmp1 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) e[a + 3 * b] = vol * (lambda * g[i][a] * g[j][b] + myu * g[j][a] * g[i][b]);
+      dtmp1 += g[i][a] * g[j][a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) e[a + 3 * a] += vol * myu * dtmp1;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ plan (index maps)
+// slot of (row r, column vertex cv): last occurrence wins like the reference's col2idx scatter; NO_SLOT if absent
+__device__ __forceinline__ uint32_t find_slot(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
+                                              uint32_t r, uint32_t cv) {
+  uint32_t s = NO_SLOT;
+  for (uint32_t k = row2idx[r]; k < row2idx[r + 1]; ++k)
+    if (idx2col[k] == cv) s = k;
+  return s;
+}
+
+// MODE 0: count contributions per slot; MODE 1: fill contribution lists; MODE 2: write the forward map elem2nz
+template <int MODE>
+__global__ void k_plan_pass(const uint32_t *__restrict__ e2v, uint64_t num_elem, int n_node, int flavour, int convention,
+                            const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col, uint64_t num_rows,
+                            uint64_t nnz, uint32_t *__restrict__ cnt_or_cursor, const uint32_t *__restrict__ nz2ptr,
+                            uint32_t *__restrict__ out, int *err) {
+  const uint64_t total = num_elem * n_node;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t e = q / n_node;
+    const int i = (int)(q - e * n_node);
+    const uint32_t *conn = e2v + e * n_node;
+    const uint32_t r = conn[i];
+    if (r >= num_rows) {  // row owned by another rank: not assembled here
+      if (MODE == 2)
+        for (int j = 0; j < n_node; ++j) out[q * n_node + j] = NO_SLOT;
+      continue;
+    }
+    for (int j = 0; j < n_node; ++j) {
+      const uint32_t cv = conn[j];
+      const bool is_dia = convention == 0 && (flavour == 0 ? (i == j) : (r == cv));
+      uint32_t slot;
+      if (is_dia) slot = (uint32_t)nnz + r;
+      else {
+        slot = find_slot(row2idx, idx2col, r, cv);
+        if (slot == NO_SLOT) {
+          atomicExch(err, 1);
+          if (MODE == 2) out[q * n_node + j] = NO_SLOT;
+          continue;
+        }
+      }
+      if (MODE == 0) atomicAdd(&cnt_or_cursor[slot], 1u);
+      if (MODE == 1) {
+        const uint32_t pos = atomicAdd(&cnt_or_cursor[slot], 1u);
+        out[nz2ptr[slot] + pos] = (uint32_t)(q * n_node + j);  // code = (e*n_node + i)*n_node + j
+      }
+      if (MODE == 2) out[q * n_node + j] = slot;
+    }
+  }
+}
+
+static __global__ void k_sort_contrib(const uint32_t *__restrict__ ptr, uint32_t *__restrict__ items, uint64_t n_lists) {
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_lists; v += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t b = ptr[v], e = ptr[v + 1];
+    for (uint32_t i = b + 1; i < e; ++i) {
+      const uint32_t key = items[i];
+      uint32_t j = i;
+      while (j > b && items[j - 1] > key) {
+        items[j] = items[j - 1];
+        --j;
+      }
+      items[j] = key;
+    }
+  }
+}
+
+DFB_API dfb_status dfb_plan_create(dfb_ctx *ctx, dfb_pattern *pattern, const dfb_mesh *mesh, int32_t flavour, dfb_plan **out) {
+  DFB_REQUIRE(ctx && pattern && mesh && out, "dfb_plan_create: NULL argument");
+  DFB_REQUIRE(flavour == 0 || flavour == 1, "dfb_plan_create: flavour %d not in {0,1}", flavour);
+  DFB_REQUIRE(pattern->num_blk <= mesh->num_vtx, "dfb_plan_create: pattern has more rows than the mesh has vertices");
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  const int n_node = mesh->num_node;
+  const uint64_t num_slots = pattern->nnz + (pattern->convention == 0 ? pattern->num_blk : 0);
+  dfb_plan *p = new dfb_plan();
+  p->ctx = ctx;
+  p->pat = pattern;
+  pattern->refcount += 1;
+  p->num_elem = mesh->num_elem;
+  p->num_node = n_node;
+  p->flavour = flavour;
+  p->num_slots = num_slots;
+  p->num_contrib = 0;
+  p->d_nz2ptr = nullptr;
+  p->d_contrib = nullptr;
+  p->mesh = mesh;
+  uint32_t *d_cursor = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&p->d_nz2ptr, num_slots + 2);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_cursor, num_slots + 2);
+  const int G = ctx->sm_count * 8;
+  if (st == DFB_OK) {
+    cudaMemsetAsync(p->d_nz2ptr, 0, (num_slots + 2) * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(d_cursor, 0, (num_slots + 2) * sizeof(uint32_t), ctx->stream);
+    DFB_LAUNCH(ctx, k_plan_pass<0>, G, 256, 0, mesh->d_elem2vtx, mesh->num_elem, n_node, flavour, pattern->convention,
+               pattern->d_row2idx, pattern->d_idx2col, pattern->num_blk, pattern->nnz, p->d_nz2ptr, (const uint32_t *)nullptr,
+               (uint32_t *)nullptr, ctx->d_errflag + 1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_create: %s", cudaGetErrorString(e));
+  }
+  if (st == DFB_OK)
+    st = dfb_check_error_flag(ctx, 1, DFB_ERR_PATTERN_MISS,
+                              "dfb_plan_create: an element couples two vertices whose (row, col) is not in the pattern "
+                              "(assert_ne!(idx0, usize::MAX))");
+  uint64_t total = 0;
+  if (st == DFB_OK) st = dfb_exclusive_scan_u32(ctx, p->d_nz2ptr, num_slots, &total);
+  if (st == DFB_OK) {
+    p->num_contrib = total;
+    st = dfb_dev_alloc_t(&p->d_contrib, total + 2);
+  }
+  if (st == DFB_OK) {
+    DFB_LAUNCH(ctx, k_plan_pass<1>, G, 256, 0, mesh->d_elem2vtx, mesh->num_elem, n_node, flavour, pattern->convention,
+               pattern->d_row2idx, pattern->d_idx2col, pattern->num_blk, pattern->nnz, d_cursor, p->d_nz2ptr, p->d_contrib,
+               ctx->d_errflag + 1);
+    DFB_LAUNCH(ctx, k_sort_contrib, G, 128, 0, p->d_nz2ptr, p->d_contrib, num_slots);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_create: %s", cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_cursor);
+  if (st != DFB_OK) {
+    dfb_plan_destroy(p);
+    return st;
+  }
+  *out = p;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_plan_destroy(dfb_plan *p) {
+  if (!p) return DFB_OK;
+  cudaStreamSynchronize(p->ctx->stream);
+  cudaFree(p->d_nz2ptr);
+  cudaFree(p->d_contrib);
+  dfb_pattern_destroy(p->pat);
+  delete p;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_plan_sizes(const dfb_plan *p, uint64_t *num_slots, uint64_t *num_contrib) {
+  DFB_REQUIRE(p, "dfb_plan_sizes: NULL argument");
+  if (num_slots) *num_slots = p->num_slots;
+  if (num_contrib) *num_contrib = p->num_contrib;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_plan_download_elem2nz(const dfb_plan *p, uint32_t *elem2nz) {
+  DFB_REQUIRE(p && elem2nz, "dfb_plan_download_elem2nz: NULL argument");
+  dfb_ctx *c = p->ctx;
+  const uint64_t n = p->num_elem * p->num_node * p->num_node;
+  uint32_t *d_out = nullptr;
+  DFB_TRY(dfb_dev_alloc_t(&d_out, n + 2));
+  DFB_LAUNCH(c, k_plan_pass<2>, c->sm_count * 8, 256, 0, p->mesh->d_elem2vtx, p->num_elem, p->num_node, p->flavour,
+             p->pat->convention, p->pat->d_row2idx, p->pat->d_idx2col, p->pat->num_blk, p->pat->nnz, (uint32_t *)nullptr,
+             (const uint32_t *)nullptr, d_out, c->d_errflag + 1);
+  DFB_CHECK_LAUNCH();
+  DFB_CUDA(cudaMemcpyAsync(elem2nz, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_out);
+  DFB_CUDA(cudaMemsetAsync(c->d_errflag + 1, 0, sizeof(int), c->stream));
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused gather-assembly
+template <int KIND>
+__global__ void __launch_bounds__(128) k_assemble_fused(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
+                                                        uint64_t num_slots, uint64_t nnz, const uint32_t *__restrict__ e2v,
+                                                        const double *__restrict__ xyz, double p0, double p1,
+                                                        double *__restrict__ idx2val, double *__restrict__ row2val) {
+  using G = ElemGeo<KIND>;
+  constexpr int NN = G::N * G::N, NNODE = G::NNODE, NDIM = G::NDIM;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+    double acc[NN];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+    const uint32_t cb = nz2ptr[s], ce = nz2ptr[s + 1];
+    for (uint32_t c = cb; c < ce; ++c) {
+      const uint32_t code = contrib[c];
+      const uint32_t e = code / (NNODE * NNODE);
+      const int ij = (int)(code - e * (NNODE * NNODE));
+      const int i = ij / NNODE, j = ij - i * NNODE;
+      const double *p[NNODE];
+      double coords[NNODE][NDIM];
+#pragma unroll
+      for (int n = 0; n < NNODE; ++n) {
+        const uint32_t v = e2v[(uint64_t)e * NNODE + n];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&xyz[(uint64_t)v * NDIM + d]);
+        p[n] = coords[n];
+      }
+      G geo;
+      geo.init(p, p0, p1);
+      double blk[NN];
+      geo.block(i, j, p0, p1, blk);
+#pragma unroll
+      for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+    }
+    double *dst = (s < nnz) ? (idx2val + s * NN) : (row2val + (s - nnz) * NN);
+#pragma unroll
+    for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+  }
+}
+
+DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, double p0, double p1, dfb_bsr *m) {
+  DFB_REQUIRE(plan && mesh && m, "dfb_assemble: NULL argument");
+  const ElemInfo info = elem_info(kind);
+  DFB_REQUIRE(info.n_node != 0, "dfb_assemble: unknown element kind %d", kind);
+  DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble: matrix and plan use different patterns");
+  DFB_REQUIRE(mesh->num_elem == plan->num_elem && mesh->num_node == plan->num_node, "dfb_assemble: mesh does not match the plan");
+  DFB_REQUIRE(mesh->num_node == info.n_node && mesh->ndim == info.ndim, "dfb_assemble: mesh (%d nodes, %d-D) does not fit element kind %d",
+              mesh->num_node, mesh->ndim, kind);
+  DFB_REQUIRE(m->blk_dim == info.N, "dfb_assemble: matrix block dim %d != element block dim %d", m->blk_dim, info.N);
+  dfb_ctx *c = plan->ctx;
+  const uint64_t ns = plan->num_slots;
+  uint64_t g = (ns + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+#define ASM_CASE(K)                                                                                                          \
+  case K:                                                                                                                    \
+    DFB_LAUNCH(c, k_assemble_fused<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz, mesh->d_elem2vtx, \
+               mesh->d_xyz, p0, p1, m->d_idx2val, m->d_row2val);                                                             \
+    break;
+  switch (kind) {
+    ASM_CASE(DFB_ELEM_LAPLACE_TRI2)
+    ASM_CASE(DFB_ELEM_COT_LAPLACE_TRI3)
+    ASM_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
+    ASM_CASE(DFB_ELEM_LAPLACE_TET)
+    ASM_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+    default:
+      return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
+  }
+#undef ASM_CASE
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ two-phase path
+// batched element kernels: one thread per element writes the whole [n_node][n_node][NN] element matrix
+template <int KIND>
+__global__ void __launch_bounds__(128) k_emat_batch(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                    uint64_t num_elem, double p0, double p1, double *__restrict__ emat) {
+  using G = ElemGeo<KIND>;
+  constexpr int NN = G::N * G::N, NNODE = G::NNODE, NDIM = G::NDIM;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    const double *p[NNODE];
+    double coords[NNODE][NDIM];
+#pragma unroll
+    for (int n = 0; n < NNODE; ++n) {
+      const uint32_t v = e2v[e * NNODE + n];
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&xyz[(uint64_t)v * NDIM + d]);
+      p[n] = coords[n];
+    }
+    G geo;
+    geo.init(p, p0, p1);
+    double *out = emat + e * (NNODE * NNODE * NN);
+#pragma unroll
+    for (int i = 0; i < NNODE; ++i)
+#pragma unroll
+      for (int j = 0; j < NNODE; ++j) {
+        double blk[NN];
+        geo.block(i, j, p0, p1, blk);
+#pragma unroll
+        for (int q = 0; q < NN; ++q) out[(i * NNODE + j) * NN + q] = blk[q];
+      }
+  }
+}
+
+// ---- DERIVED tet neo-Hookean: energy density + the reference's chain rule
+// (solid_incompressive_hex.rs:86-148) with 4 nodes, dndx = g, detwei = V. Writes the Hessian already transposed to the
+// column-major block convention of the BSR (a + 3b), the gradient and the energy.
+__device__ __forceinline__ void mat3_det_inv(double &det, double (&inv)[3][3], const double (&c)[3][3]) {
+  const double d = c[0][0] * (c[1][1] * c[2][2] - c[1][2] * c[2][1]) - c[0][1] * (c[1][0] * c[2][2] - c[1][2] * c[2][0]) +
+                   c[0][2] * (c[1][0] * c[2][1] - c[1][1] * c[2][0]);
+  const double t = 1.0 / d;
+  inv[0][0] = t * (c[1][1] * c[2][2] - c[1][2] * c[2][1]);
+  inv[0][1] = t * (c[0][2] * c[2][1] - c[0][1] * c[2][2]);
+  inv[0][2] = t * (c[0][1] * c[1][2] - c[0][2] * c[1][1]);
+  inv[1][0] = t * (c[1][2] * c[2][0] - c[1][0] * c[2][2]);
+  inv[1][1] = t * (c[0][0] * c[2][2] - c[0][2] * c[2][0]);
+  inv[1][2] = t * (c[0][2] * c[1][0] - c[0][0] * c[1][2]);
+  inv[2][0] = t * (c[1][0] * c[2][1] - c[1][1] * c[2][0]);
+  inv[2][1] = t * (c[0][1] * c[2][0] - c[0][0] * c[2][1]);
+  inv[2][2] = t * (c[0][0] * c[1][1] - c[0][1] * c[1][0]);
+  det = d;
+}
+
+__global__ void __launch_bounds__(64) k_neohookean_tet(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                       const double *__restrict__ disp, uint64_t num_elem, double myu,
+                                                       double lambda, double *__restrict__ emat, double *__restrict__ evec,
+                                                       double *__restrict__ w_out) {
+  const int IJ[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {1, 2}, {2, 0}};  // dudx.rs:36
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    double X[4][3], U[4][3];
+    for (int n = 0; n < 4; ++n) {
+      const uint32_t v = e2v[e * 4 + n];
+      for (int d = 0; d < 3; ++d) {
+        X[n][d] = xyz[(uint64_t)v * 3 + d];
+        U[n][d] = disp[(uint64_t)v * 3 + d];
+      }
+    }
+    double g[4][3];
+    const double vol = tet_vol_grad(g, X[0], X[1], X[2], X[3]);
+    double dudx[3][3];  // dndx.rs:2-21
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double t = 0.0;
+        for (int n = 0; n < 4; ++n) t += U[n][i] * g[n][j];
+        dudx[i][j] = t;
+      }
+    double C[3][3], Ci[3][3], detc;  // dudx.rs:17-34
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        double t = dudx[i][j] + dudx[j][i];
+        for (int k = 0; k < 3; ++k) t += dudx[k][i] * dudx[k][j];
+        C[i][j] = t;
+      }
+      C[i][i] += 1.0;
+    }
+    mat3_det_inv(detc, Ci, C);
+    const double lnj = 0.5 * log(detc);
+    const double wr = 0.5 * myu * (C[0][0] + C[1][1] + C[2][2] - 3.0) - myu * lnj + 0.5 * lambda * lnj * lnj;
+    const double sco = 0.5 * lambda * lnj - 0.5 * myu;
+    const double tco = 0.5 * myu - 0.5 * lambda * lnj;
+    double dwrdc[6], ddwrddc[6][6];
+    for (int a = 0; a < 6; ++a) {
+      const int i = IJ[a][0], j = IJ[a][1];
+      dwrdc[a] = ((i == j) ? 0.5 * myu : 0.0) + sco * Ci[i][j];
+      for (int b = 0; b < 6; ++b) {
+        const int k = IJ[b][0], l = IJ[b][1];
+        const double v1 = 0.25 * lambda * Ci[i][j] * Ci[k][l];
+        const double v2 = 0.5 * tco * Ci[i][l] * Ci[j][k];
+        const double v3 = 0.5 * tco * Ci[i][k] * Ci[j][l];
+        ddwrddc[a][b] = v1 + v2 + v3;
+      }
+    }
+    double z[3][3];  // def_grad_tensor dudx.rs:1-14
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) z[i][j] = dudx[i][j];
+      z[i][i] += 1.0;
+    }
+    double dcdu0[4][3][6];
+    for (int n = 0; n < 4; ++n)
+      for (int d = 0; d < 3; ++d) {
+        dcdu0[n][d][0] = g[n][0] * z[d][0];
+        dcdu0[n][d][1] = g[n][1] * z[d][1];
+        dcdu0[n][d][2] = g[n][2] * z[d][2];
+        dcdu0[n][d][3] = g[n][0] * z[d][1] + g[n][1] * z[d][0];
+        dcdu0[n][d][4] = g[n][1] * z[d][2] + g[n][2] * z[d][1];
+        dcdu0[n][d][5] = g[n][2] * z[d][0] + g[n][0] * z[d][2];
+      }
+    const double detwei = vol;
+    if (emat) {
+      double *out = emat + e * 144;
+      for (int ino = 0; ino < 4; ++ino)
+        for (int jno = 0; jno < 4; ++jno) {
+          double blk[9];  // reference convention a*3+b
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+              double dtmp1 = 0.0;
+              for (int gg = 0; gg < 6; ++gg)
+                for (int hh = 0; hh < 6; ++hh) dtmp1 += 2.0 * ddwrddc[gg][hh] * dcdu0[ino][a][gg] * dcdu0[jno][b][hh];
+              blk[a * 3 + b] = 0.0 + 2.0 * detwei * dtmp1;
+            }
+          double dtmp2 = 0.0;
+          dtmp2 += dwrdc[0] * g[ino][0] * g[jno][0];
+          dtmp2 += dwrdc[1] * g[ino][1] * g[jno][1];
+          dtmp2 += dwrdc[2] * g[ino][2] * g[jno][2];
+          dtmp2 += dwrdc[3] * (g[ino][0] * g[jno][1] + g[ino][1] * g[jno][0]);
+          dtmp2 += dwrdc[4] * (g[ino][1] * g[jno][2] + g[ino][2] * g[jno][1]);
+          dtmp2 += dwrdc[5] * (g[ino][2] * g[jno][0] + g[ino][0] * g[jno][2]);
+          for (int a = 0; a < 3; ++a) blk[a * 3 + a] += 2.0 * detwei * dtmp2;
+          // transpose into the column-major BSR convention
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) out[(ino * 4 + jno) * 9 + a + 3 * b] = blk[a * 3 + b];
+        }
+    }
+    if (evec) {
+      for (int n = 0; n < 4; ++n)
+        for (int d = 0; d < 3; ++d) {
+          double dtmp1 = 0.0;
+          for (int gg = 0; gg < 6; ++gg) dtmp1 += dcdu0[n][d][gg] * dwrdc[gg];
+          evec[e * 12 + n * 3 + d] = 0.0 + 2.0 * detwei * dtmp1;
+        }
+    }
+    if (w_out) w_out[e] = 0.0 + wr * detwei;
+  }
+}
+
+DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *mesh, double p0, double p1, const dfb_vec *disp,
+                                  double *emat_dev, double *evec_dev, double *w_dev) {
+  DFB_REQUIRE(ctx && mesh, "dfb_emat_batch: NULL argument");
+  const ElemInfo info = elem_info(kind);
+  DFB_REQUIRE(info.n_node != 0, "dfb_emat_batch: unknown element kind %d", kind);
+  DFB_REQUIRE(mesh->num_node == info.n_node && mesh->ndim == info.ndim, "dfb_emat_batch: mesh does not fit element kind %d", kind);
+  uint64_t g = (mesh->num_elem + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)ctx->sm_count * 16) g = (uint64_t)ctx->sm_count * 16;
+#define EM_CASE(K)                                                                                                        \
+  case K:                                                                                                                 \
+    DFB_REQUIRE(emat_dev, "dfb_emat_batch: emat_dev is NULL");                                                            \
+    DFB_LAUNCH(ctx, k_emat_batch<K>, (unsigned)g, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, emat_dev); \
+    break;
+  switch (kind) {
+    EM_CASE(DFB_ELEM_LAPLACE_TRI2)
+    EM_CASE(DFB_ELEM_COT_LAPLACE_TRI3)
+    EM_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
+    EM_CASE(DFB_ELEM_LAPLACE_TET)
+    EM_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+    case DFB_ELEM_NEOHOOKEAN_TET: {
+      DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
+                  "dfb_emat_batch: neo-Hookean needs a displacement vector covering every mesh vertex");
+      uint64_t g2 = (mesh->num_elem + 63) / 64;
+      if (g2 < 1) g2 = 1;
+      if (g2 > (uint64_t)ctx->sm_count * 32) g2 = (uint64_t)ctx->sm_count * 32;
+      DFB_LAUNCH(ctx, k_neohookean_tet, (unsigned)g2, 64, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, p1,
+                 emat_dev, evec_dev, w_dev);
+      break;
+    }
+    default:
+      return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_emat_batch: kind %d not implemented", kind);
+  }
+#undef EM_CASE
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// gather of precomputed element matrices through the plan (any element kind / user-supplied emat)
+template <int NN>
+__global__ void __launch_bounds__(128) k_assemble_from_emat(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
+                                                            uint64_t num_slots, uint64_t nnz, const double *__restrict__ emat,
+                                                            double *__restrict__ idx2val, double *__restrict__ row2val) {
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+    double acc[NN];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+    for (uint32_t c = nz2ptr[s]; c < nz2ptr[s + 1]; ++c) {
+      const double *b = emat + (uint64_t)contrib[c] * NN;
+#pragma unroll
+      for (int q = 0; q < NN; ++q) acc[q] += b[q];
+    }
+    double *dst = (s < nnz) ? (idx2val + s * NN) : (row2val + (s - nnz) * NN);
+#pragma unroll
+    for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+  }
+}
+
+DFB_API dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev, dfb_bsr *m) {
+  DFB_REQUIRE(plan && emat_dev && m, "dfb_assemble_from_emat: NULL argument");
+  DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble_from_emat: matrix and plan use different patterns");
+  dfb_ctx *c = plan->ctx;
+  const uint64_t ns = plan->num_slots;
+  uint64_t g = (ns + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+#define FE_CASE(NNV)                                                                                                       \
+  case NNV:                                                                                                                \
+    DFB_LAUNCH(c, k_assemble_from_emat<NNV>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz, emat_dev, \
+               m->d_idx2val, m->d_row2val);                                                                                \
+    break;
+  switch (m->blk_dim * m->blk_dim) {
+    FE_CASE(1)
+    FE_CASE(4)
+    FE_CASE(9)
+    FE_CASE(16)
+  }
+#undef FE_CASE
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// gradient gather: dw[row] = sum over the diagonal slot's contributions (e,i,i) of evec[e][i], ascending e
+__global__ void k_gather_evec(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib, uint64_t nnz,
+                              uint64_t num_rows, int n_node, int N, const double *__restrict__ evec, double *__restrict__ out) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (uint32_t c = nz2ptr[nnz + r]; c < nz2ptr[nnz + r + 1]; ++c) {
+      const uint32_t code = contrib[c];
+      const uint32_t ei = code / n_node;  // e*n_node + i
+      for (int d = 0; d < N; ++d) acc[d] += evec[(uint64_t)ei * N + d];
+    }
+    for (int d = 0; d < N; ++d) out[r * N + d] = acc[d];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sum(const double *__restrict__ a, uint64_t n, double *partials, unsigned int *ticket, double *out) {
+  __shared__ double s_buf[32];
+  double acc[1] = {0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc[0] += a[i];
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_buf) && threadIdx.x == 0) out[0] = acc[0];
+}
+
+DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, const dfb_vec *disp, double myu,
+                                               double lambda, dfb_bsr *m, dfb_vec *dw, double *w) {
+  DFB_REQUIRE(plan && mesh && disp && m, "dfb_assemble_neohookean_tet: NULL argument");
+  DFB_REQUIRE(plan->pat->convention == 0 && plan->flavour == 0, "dfb_assemble_neohookean_tet: needs a convention-0 / flavour-0 plan");
+  DFB_REQUIRE(m->blk_dim == 3 && mesh->num_node == 4, "dfb_assemble_neohookean_tet: needs 3x3 blocks on a tet mesh");
+  dfb_ctx *c = plan->ctx;
+  double *d_emat = nullptr, *d_evec = nullptr, *d_w = nullptr;
+  DFB_TRY(dfb_dev_alloc_t(&d_emat, mesh->num_elem * 144));
+  DFB_TRY(dfb_dev_alloc_t(&d_evec, mesh->num_elem * 12));
+  DFB_TRY(dfb_dev_alloc_t(&d_w, mesh->num_elem));
+  dfb_status st = dfb_emat_batch(c, DFB_ELEM_NEOHOOKEAN_TET, mesh, myu, lambda, disp, d_emat, d_evec, d_w);
+  if (st == DFB_OK) st = dfb_assemble_from_emat(plan, d_emat, m);
+  if (st == DFB_OK && dw) {
+    DFB_LAUNCH(c, k_gather_evec, c->sm_count * 8, 128, 0, plan->d_nz2ptr, plan->d_contrib, plan->pat->nnz, plan->pat->num_blk, 4, 3,
+               d_evec, dw->d);
+  }
+  if (st == DFB_OK && w) {
+    uint64_t g = (mesh->num_elem + 1023) / 1024;
+    if (g < 1) g = 1;
+    if (g > 1024) g = 1024;
+    DFB_LAUNCH(c, k_sum, (unsigned)g, 256, 0, d_w, mesh->num_elem, c->d_partials, c->d_ticket + 3, c->d_scratch + 8);
+    cudaMemcpyAsync(c->h_pinned, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (st == DFB_OK && e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_assemble_neohookean_tet: %s", cudaGetErrorString(e));
+  if (st == DFB_OK && w) *w = *(double *)c->h_pinned;
+  cudaFree(d_emat);
+  cudaFree(d_evec);
+  cudaFree(d_w);
+  return st;
+}
+
+// one element on host arrays (tests / API parity with the reference's by-value element functions)
+DFB_API dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2xyz, double p0, double p1, double *emat) {
+  DFB_REQUIRE(ctx && node2xyz && emat, "dfb_emat_one: NULL argument");
+  const ElemInfo info = elem_info(kind);
+  DFB_REQUIRE(info.n_node != 0 && kind != DFB_ELEM_NEOHOOKEAN_TET && kind != DFB_ELEM_SPRING3, "dfb_emat_one: unsupported kind %d", kind);
+  uint32_t conn[4] = {0, 1, 2, 3};
+  dfb_mesh *mesh = nullptr;
+  DFB_TRY(dfb_mesh_create_u32(ctx, conn, 1, info.n_node, node2xyz, info.n_node, info.ndim, &mesh));
+  const size_t n = (size_t)info.n_node * info.n_node * info.N * info.N;
+  double *d_e = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&d_e, n);
+  if (st == DFB_OK) st = dfb_emat_batch(ctx, kind, mesh, p0, p1, nullptr, d_e, nullptr, nullptr);
+  if (st == DFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(emat, d_e, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_emat_one: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_e);
+  dfb_mesh_destroy(mesh);
+  return st;
+}

@@ -1,0 +1,608 @@
+// bsr.cu — sparse_square::Matrix<[T;NN]> on the device (del-fem-cpu/src/sparse_square.rs:75-214, :349-447;
+// del-fem-ls/src/sparse_square.rs:6-164): storage, set_zero, BC (set_fixed_bc :3-55) and mult_vec (:419-447).
+//
+// SpMV design (HBM-bound: 76 B per off-diagonal 3x3 block, 0.24 flop/B — no tensor cores):
+//   variant 0  one thread per block-row, direct global loads (simple; baseline / fallback for huge rows)
+//   variant 1  one warp per tile of 32 consecutive block-rows: the tile's values, column indices and diagonal blocks
+//              are contiguous in memory, so the warp streams them into shared memory with 16-byte cp.async.cg
+//              (L2 evict-first: the matrix is read once per SpMV), then lane r computes row r out of shared memory
+//              while x is gathered from L2.
+//   variant 2  same tiling, but the staging is three TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) issued
+//              by one lane, completion tracked by a per-warp mbarrier: the copy engine streams the matrix, the SM's
+//              LSU only serves the x gather.
+// Persistent warps (grid = #SM x CTAs/SM) walk the tiles with a fixed stride, so the optional fused dot product
+// (p . Ap for CG) is reduced over a fixed grid in a fixed order: bit-reproducible.
+#include "dfb_internal.h"
+#include "reduce.cuh"
+
+// ------------------------------------------------------------------------------------------------ create / IO
+DFB_API dfb_status dfb_bsr_create(dfb_ctx *ctx, dfb_pattern *pattern, int32_t blk_dim, dfb_bsr **out) {
+  DFB_REQUIRE(ctx && pattern && out, "dfb_bsr_create: NULL argument");
+  DFB_REQUIRE(blk_dim >= 1 && blk_dim <= 4, "dfb_bsr_create: blk_dim %d not in 1..4", blk_dim);
+  DFB_REQUIRE(pattern->ctx == ctx, "dfb_bsr_create: pattern belongs to another context");
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  dfb_bsr *m = new dfb_bsr();
+  m->ctx = ctx;
+  m->pat = pattern;
+  pattern->refcount += 1;
+  m->blk_dim = blk_dim;
+  m->d_idx2val = nullptr;
+  m->d_row2val = nullptr;
+  m->d_flag = nullptr;
+  m->flag_cap = 0;
+  m->halo = nullptr;
+  m->int_begin = 0;
+  m->int_end = pattern->num_blk;
+  const uint64_t nn = (uint64_t)blk_dim * blk_dim;
+  dfb_status st = dfb_dev_alloc_t(&m->d_idx2val, pattern->nnz * nn + 64);
+  if (st == DFB_OK && pattern->convention == 0) st = dfb_dev_alloc_t(&m->d_row2val, pattern->num_blk * nn + 64);
+  if (st != DFB_OK) {
+    dfb_bsr_destroy(m);
+    return st;
+  }
+  DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, (pattern->nnz * nn + 64) * sizeof(double), ctx->stream));
+  if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, (pattern->num_blk * nn + 64) * sizeof(double), ctx->stream));
+  *out = m;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
+  if (!m) return DFB_OK;
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->d_idx2val);
+  cudaFree(m->d_row2val);
+  cudaFree(m->d_flag);
+  dfb_pattern_destroy(m->pat);
+  delete m;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_set_zero(dfb_bsr *m) {
+  DFB_REQUIRE(m, "dfb_bsr_set_zero: NULL argument");
+  const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
+  DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, m->pat->nnz * nn * sizeof(double), m->ctx->stream));
+  if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, m->pat->num_blk * nn * sizeof(double), m->ctx->stream));
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2val) {
+  DFB_REQUIRE(m, "dfb_bsr_upload: NULL argument");
+  const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
+  if (idx2val) DFB_CUDA(cudaMemcpyAsync(m->d_idx2val, idx2val, m->pat->nnz * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  if (row2val) {
+    DFB_REQUIRE(m->d_row2val, "dfb_bsr_upload: matrix has no separate diagonal (convention 1)");
+    DFB_CUDA(cudaMemcpyAsync(m->d_row2val, row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  }
+  DFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_download(const dfb_bsr *m, double *row2val, double *idx2val) {
+  DFB_REQUIRE(m, "dfb_bsr_download: NULL argument");
+  const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
+  if (idx2val) DFB_CUDA(cudaMemcpyAsync(idx2val, m->d_idx2val, m->pat->nnz * nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  if (row2val) {
+    DFB_REQUIRE(m->d_row2val, "dfb_bsr_download: matrix has no separate diagonal (convention 1)");
+    DFB_CUDA(cudaMemcpyAsync(row2val, m->d_row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  }
+  DFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BC
+// set_fixed_bc (sparse_square.rs:3-55). The reference's three passes touch disjoint data per block, so they collapse
+// into one row-parallel pass: thread per block-row handles its diagonal block, then every off-diagonal block of the
+// row (row zeroing by its own flags, column zeroing by the column block's flags). Only flagged entries are written.
+template <int N>
+__global__ void k_set_fixed_bc(double val_dia, const int32_t *__restrict__ flag, double *__restrict__ row2val,
+                               double *__restrict__ idx2val, const uint32_t *__restrict__ row2idx,
+                               const uint32_t *__restrict__ idx2col, uint64_t num_blk, int convention) {
+  constexpr int NN = N * N;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    int fi[N];
+    bool any_i = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      fi[d] = flag[i * N + d];
+      any_i |= (fi[d] != 0);
+    }
+    if (convention == 0 && any_i) {
+      double *D = row2val + i * NN;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        if (fi[d] == 0) continue;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          D[d + N * j] = 0.0;
+          D[j + N * d] = 0.0;
+        }
+        D[d + N * d] = val_dia;
+      }
+    }
+    for (uint32_t k = row2idx[i]; k < row2idx[i + 1]; ++k) {
+      const uint32_t c = idx2col[k];
+      double *V = idx2val + (uint64_t)k * NN;
+      if (convention == 1 && c == (uint32_t)i) {
+        // diagonal block stored inside the pattern (blkcsr): same treatment as the separate diagonal
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          if (fi[d] == 0) continue;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            V[d + N * j] = 0.0;
+            V[j + N * d] = 0.0;
+          }
+          V[d + N * d] = val_dia;
+        }
+        continue;
+      }
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        if (fi[d] != 0) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) V[d + N * j] = 0.0;
+        }
+        if (flag[(uint64_t)c * N + d] != 0) {
+#pragma unroll
+          for (int a = 0; a < N; ++a) V[a + N * d] = 0.0;
+        }
+      }
+    }
+  }
+}
+
+DFB_API dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *flag_host) {
+  DFB_REQUIRE(m && flag_host, "dfb_bsr_set_fixed_dof: NULL argument");
+  dfb_ctx *c = m->ctx;
+  const uint64_t n_all = m->pat->num_blk + (m->halo ? (m->halo->recv_ptr.empty() ? 0 : m->halo->recv_ptr.back()) : 0);
+  const uint64_t need = n_all * m->blk_dim;
+  if (m->flag_cap < need) {
+    cudaFree(m->d_flag);
+    m->d_flag = nullptr;
+    DFB_TRY(dfb_dev_alloc_t(&m->d_flag, need));
+    m->flag_cap = need;
+  }
+  DFB_CUDA(cudaMemcpyAsync(m->d_flag, flag_host, need * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  const int grid = c->sm_count * 8;
+  switch (m->blk_dim) {
+    case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 2: DFB_LAUNCH(c, k_set_fixed_bc<2>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 3: DFB_LAUNCH(c, k_set_fixed_bc<3>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 4: DFB_LAUNCH(c, k_set_fixed_bc<4>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+  }
+  DFB_CHECK_LAUNCH();
+  DFB_CUDA(cudaStreamSynchronize(c->stream));  // flag_host is borrowed only for the duration of the call
+  return DFB_OK;
+}
+
+// row2val[i][d + N d] += scale * v[i][d]
+__global__ void k_add_to_diagonal(double *__restrict__ row2val, int N, double scale, const double *__restrict__ v, uint64_t n_dof) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_dof; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = q / N;
+    const int d = (int)(q - i * N);
+    row2val[i * N * N + d + N * d] += scale * v[q];
+  }
+}
+
+DFB_API dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_vec *v) {
+  DFB_REQUIRE(m && v, "dfb_bsr_add_to_diagonal: NULL argument");
+  DFB_REQUIRE(m->d_row2val, "dfb_bsr_add_to_diagonal: convention 1 matrices have no separate diagonal");
+  DFB_REQUIRE(v->n_blk == m->pat->num_blk && v->blk_dim == m->blk_dim, "dfb_bsr_add_to_diagonal: shape mismatch");
+  DFB_LAUNCH(m->ctx, k_add_to_diagonal, m->ctx->sm_count * 8, 256, 0, m->d_row2val, m->blk_dim, scale, v->d, v->len());
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// single-element merge (API-parity shim; merge_for_array_blk / ls merge / csrdia / blkcsr). One thread.
+__global__ void k_merge_one(const double *__restrict__ emat, const uint32_t *__restrict__ node2vtx, int n_node, int NN,
+                            int flavour, int convention, const uint32_t *__restrict__ row2idx,
+                            const uint32_t *__restrict__ idx2col, uint64_t num_blk, double *row2val, double *idx2val, int *err) {
+  for (int in = 0; in < n_node; ++in) {
+    const uint32_t r = node2vtx[in];
+    if (r >= num_blk) {
+      *err = 1;
+      return;
+    }
+    for (int jn = 0; jn < n_node; ++jn) {
+      const uint32_t cvt = node2vtx[jn];
+      const bool is_dia = convention == 0 && (flavour == 0 ? (in == jn) : (r == cvt));
+      double *dst = nullptr;
+      if (is_dia) dst = row2val + (uint64_t)r * NN;
+      else {
+        // last occurrence wins, like the reference's col2idx scatter
+        for (uint32_t k = row2idx[r]; k < row2idx[r + 1]; ++k)
+          if (idx2col[k] == cvt) dst = idx2val + (uint64_t)k * NN;
+        if (!dst) {
+          *err = 1;
+          return;
+        }
+      }
+      const double *e = emat + (in * n_node + jn) * NN;
+      for (int q = 0; q < NN; ++q) dst[q] += e[q];
+    }
+  }
+}
+
+DFB_API dfb_status dfb_bsr_merge_one(dfb_bsr *m, const double *emat, const uint64_t *node2vtx, int32_t n_node, int32_t flavour) {
+  DFB_REQUIRE(m && emat && node2vtx, "dfb_bsr_merge_one: NULL argument");
+  DFB_REQUIRE(n_node >= 1 && n_node <= 8, "dfb_bsr_merge_one: n_node %d not in 1..8", n_node);
+  dfb_ctx *c = m->ctx;
+  const int NN = m->blk_dim * m->blk_dim;
+  double *d_e = nullptr;
+  uint32_t *d_n = nullptr;
+  uint32_t h_n[8];
+  for (int i = 0; i < n_node; ++i) {
+    if (node2vtx[i] >= 0xFFFFFFFFull) return dfb_fail(DFB_ERR_INDEX_OVERFLOW, "dfb_bsr_merge_one: vertex index overflow");
+    h_n[i] = (uint32_t)node2vtx[i];
+  }
+  DFB_TRY(dfb_dev_alloc_t(&d_e, (size_t)n_node * n_node * NN));
+  DFB_TRY(dfb_dev_alloc_t(&d_n, 8));
+  DFB_CUDA(cudaMemcpyAsync(d_e, emat, (size_t)n_node * n_node * NN * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  DFB_CUDA(cudaMemcpyAsync(d_n, h_n, n_node * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  DFB_LAUNCH(c, k_merge_one, 1, 1, 0, d_e, d_n, n_node, NN, flavour, m->pat->convention, m->pat->d_row2idx, m->pat->d_idx2col,
+             m->pat->num_blk, m->d_row2val, m->d_idx2val, c->d_errflag + 1);
+  DFB_CHECK_LAUNCH();
+  dfb_status st = dfb_check_error_flag(c, 1, DFB_ERR_PATTERN_MISS, "dfb_bsr_merge_one: (row, col) of the element is not in the pattern");
+  cudaFree(d_e);
+  cudaFree(d_n);
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------------ SpMV
+struct SpmvArgs {
+  const uint32_t *row2idx;
+  const uint32_t *idx2col;
+  const double *idx2val;
+  const double *row2val;  // nullptr for convention 1
+  const double *x;
+  double *y;
+  double alpha, beta;
+  uint32_t row_begin, row_end;
+  int fuse_dot;        // 0 none, 1 red[0] = sum x.y, 2 red[0] += sum x.y
+  int parity;          // solver-state parity slot (done flag)
+  DfbSolverState *st;  // nullptr outside the solvers
+  double *partials;
+  unsigned int *ticket;
+};
+
+template <int N>
+__device__ __forceinline__ void block_times_vec(double (&s)[N], const double *__restrict__ v, const double (&xv)[N]) {
+#pragma unroll
+  for (int b = 0; b < N; ++b)
+#pragma unroll
+    for (int a = 0; a < N; ++a) s[a] += v[a + N * b] * xv[b];
+}
+
+template <int N>
+__device__ __forceinline__ void load_x(double (&xv)[N], const double *__restrict__ x, uint32_t col) {
+  const double *p = x + (uint64_t)col * N;
+#pragma unroll
+  for (int a = 0; a < N; ++a) xv[a] = __ldg(p + a);
+}
+
+// off-diagonal part of one row; vals/cols may point to shared or global memory
+template <int N>
+__device__ __forceinline__ void row_offdiag(double (&s)[N], const double *vals, const uint32_t *cols, uint32_t kb, uint32_t ke,
+                                            const double *__restrict__ x) {
+  constexpr int NN = N * N;
+#pragma unroll 2
+  for (uint32_t k = kb; k < ke; ++k) {
+    double xv[N];
+    load_x<N>(xv, x, cols[k]);
+    block_times_vec<N>(s, vals + (uint64_t)k * NN, xv);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ double row_finish(const SpmvArgs &a, uint32_t r, double (&s)[N], const double *diag_blk) {
+  double xo[N];
+  load_x<N>(xo, a.x, r);
+  if (diag_blk) block_times_vec<N>(s, diag_blk, xo);
+  double d = 0.0;
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    double yv = a.alpha * s[q];
+    if (a.beta != 0.0) yv += a.beta * a.y[(uint64_t)r * N + q];
+    a.y[(uint64_t)r * N + q] = yv;
+    d += xo[q] * yv;
+  }
+  return d;
+}
+
+__device__ __forceinline__ void spmv_publish_dot(const SpmvArgs &a, double d, double *s_buf) {
+  double acc[1] = {d};
+  if (grid_sum_last_block<1>(acc, a.partials, a.ticket, s_buf) && threadIdx.x == 0) {
+    if (a.fuse_dot == 2) a.st->red[0] += acc[0];
+    else a.st->red[0] = acc[0];
+  }
+}
+
+// ---- variant 0: thread per row
+template <int N>
+__global__ void __launch_bounds__(128) k_spmv_row(const SpmvArgs a) {
+  __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
+  double dot = 0.0;
+  for (uint64_t r = (uint64_t)a.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.row_end;
+       r += (uint64_t)gridDim.x * blockDim.x) {
+    double s[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) s[q] = 0.0;
+    row_offdiag<N>(s, a.idx2val, a.idx2col, a.row2idx[r], a.row2idx[r + 1], a.x);
+    dot += row_finish<N>(a, (uint32_t)r, s, a.row2val ? a.row2val + r * N * N : nullptr);
+  }
+  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
+}
+
+// ---- variants 1/2: warp per 32-row tile, staged through shared memory
+template <int N> struct TileCfg;
+template <> struct TileCfg<1> { static constexpr int CAP = 1536; };
+template <> struct TileCfg<2> { static constexpr int CAP = 768; };
+template <> struct TileCfg<3> { static constexpr int CAP = 480; };
+template <> struct TileCfg<4> { static constexpr int CAP = 272; };
+
+template <int N>
+struct TileSmem {
+  static constexpr int NN = N * N;
+  static constexpr int VAL_BYTES = ((TileCfg<N>::CAP * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int DIA_BYTES = ((32 * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int COL_BYTES = ((TileCfg<N>::CAP * 4 + 16 + 15) / 16) * 16;
+  static constexpr int BAR_BYTES = 16;
+  static constexpr int WARP_BYTES = VAL_BYTES + DIA_BYTES + COL_BYTES + BAR_BYTES;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// warp-cooperative 16-byte cp.async of the 16-byte-aligned superset of [src, src+bytes); returns the byte offset of
+// `src` inside the staged region (0..15). The caller guarantees 16 bytes of slack on both sides of the source.
+__device__ __forceinline__ uint32_t stage_cp_async(uint32_t dst_smem, const void *src, uint32_t bytes, unsigned lane,
+                                                   unsigned long long pol) {
+  const uintptr_t s = (uintptr_t)src;
+  const uint32_t mis = (uint32_t)(s & 15);
+  const char *g = (const char *)(s - mis);
+  const uint32_t total = (mis + bytes + 15u) & ~15u;
+  for (uint32_t off = lane * 16u; off < total; off += 512u) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem + off), "l"(g + off), "l"(pol)
+                 : "memory");
+  }
+  return mis;
+}
+
+// one-lane TMA bulk copy of the aligned superset; same return value
+__device__ __forceinline__ uint32_t stage_bulk(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar_smem,
+                                               unsigned long long pol, uint32_t *tx_bytes) {
+  const uintptr_t s = (uintptr_t)src;
+  const uint32_t mis = (uint32_t)(s & 15);
+  const char *g = (const char *)(s - mis);
+  const uint32_t total = (mis + bytes + 15u) & ~15u;
+  if (total > 0) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+        "l"(g), "r"(total), "r"(bar_smem), "l"(pol)
+        : "memory");
+  }
+  *tx_bytes += total;
+  return mis;
+}
+
+__device__ __forceinline__ uint32_t aligned_total(const void *src, uint32_t bytes) {
+  const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
+  return (mis + bytes + 15u) & ~15u;
+}
+
+template <int N, int VARIANT>
+__global__ void __launch_bounds__(160) k_spmv_tile(const SpmvArgs a) {
+  using S = TileSmem<N>;
+  constexpr int NN = N * N;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
+
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
+  unsigned char *s_val = wbase;
+  unsigned char *s_dia = wbase + S::VAL_BYTES;
+  unsigned char *s_col = wbase + S::VAL_BYTES + S::DIA_BYTES;
+  const uint32_t bar = smem_u32(wbase + S::VAL_BYTES + S::DIA_BYTES + S::COL_BYTES);
+  const unsigned long long pol = policy_evict_first();
+
+  uint32_t phase = 0;
+  if (VARIANT == 2) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+
+  const uint32_t n_rows = a.row_end - a.row_begin;
+  const uint32_t n_tiles = (n_rows + 31u) >> 5;
+  const uint32_t warp_global = blockIdx.x * nw + wid, warp_stride = gridDim.x * nw;
+  double dot = 0.0;
+
+  for (uint32_t t = warp_global; t < n_tiles; t += warp_stride) {
+    const uint32_t r0 = a.row_begin + (t << 5);
+    const uint32_t r1 = min(r0 + 32u, a.row_end);
+    const uint32_t r = r0 + lane;
+    // row pointers: lane L holds row2idx[r0+L]; lane 0 / last give the tile range
+    const uint32_t my_kb = (r <= r1) ? a.row2idx[r] : 0u;
+    const uint32_t k0 = __shfl_sync(0xffffffffu, my_kb, 0);
+    const uint32_t k1 = (r1 - r0 == 32u) ? a.row2idx[r1] : __shfl_sync(0xffffffffu, my_kb, (int)(r1 - r0));
+    const uint32_t my_ke = __shfl_down_sync(0xffffffffu, my_kb, 1);
+    const uint32_t ke = (lane == 31u) ? k1 : my_ke;
+    const uint32_t nb = k1 - k0;
+
+    double s[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) s[q] = 0.0;
+
+    if (nb <= (uint32_t)TileCfg<N>::CAP) {
+      const double *g_val = a.idx2val + (uint64_t)k0 * NN;
+      const uint32_t *g_col = a.idx2col + k0;
+      const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
+      const uint32_t val_bytes = nb * NN * 8u, col_bytes = nb * 4u, dia_bytes = (r1 - r0) * NN * 8u;
+      uint32_t mis_v, mis_c, mis_d = 0;
+      if (VARIANT == 1) {
+        mis_v = stage_cp_async(smem_u32(s_val), g_val, val_bytes, lane, pol);
+        mis_c = stage_cp_async(smem_u32(s_col), g_col, col_bytes, lane, pol);
+        if (g_dia) mis_d = stage_cp_async(smem_u32(s_dia), g_dia, dia_bytes, lane, pol);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      } else {
+        mis_v = (uint32_t)((uintptr_t)g_val & 15);
+        mis_c = (uint32_t)((uintptr_t)g_col & 15);
+        mis_d = g_dia ? (uint32_t)((uintptr_t)g_dia & 15) : 0u;
+        if (lane == 0) {
+          uint32_t tx = aligned_total(g_val, val_bytes) + aligned_total(g_col, col_bytes) + (g_dia ? aligned_total(g_dia, dia_bytes) : 0u);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+          uint32_t dummy = 0;
+          stage_bulk(smem_u32(s_val), g_val, val_bytes, bar, pol, &dummy);
+          stage_bulk(smem_u32(s_col), g_col, col_bytes, bar, pol, &dummy);
+          if (g_dia) stage_bulk(smem_u32(s_dia), g_dia, dia_bytes, bar, pol, &dummy);
+        }
+        // all lanes wait for the transaction bytes to land
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(phase)
+            : "memory");
+        phase ^= 1u;
+      }
+      if (r < r1) {
+        const double *sv = reinterpret_cast<const double *>(s_val + mis_v);
+        const uint32_t *sc = reinterpret_cast<const uint32_t *>(s_col + mis_c);
+        row_offdiag<N>(s, sv, sc, my_kb - k0, ke - k0, a.x);
+        const double *sd = g_dia ? reinterpret_cast<const double *>(s_dia + mis_d) + lane * NN : nullptr;
+        dot += row_finish<N>(a, r, s, sd);
+      }
+      __syncwarp();  // all lanes are done reading the staged tile before the next copy overwrites it
+    } else {
+      // oversized tile (very long rows): compute straight from global memory
+      if (r < r1) {
+        row_offdiag<N>(s, a.idx2val, a.idx2col, my_kb, ke, a.x);
+        dot += row_finish<N>(a, r, s, a.row2val ? a.row2val + (uint64_t)r * NN : nullptr);
+      }
+    }
+  }
+  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
+}
+
+template <int N>
+static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
+  const uint64_t n_rows = a.row_end - a.row_begin;
+  if (n_rows == 0 && !a.fuse_dot) return DFB_OK;
+  int variant = (int)c->spmv_variant;
+  if (variant == 0) {
+    uint64_t g = (n_rows + 127) / 128;
+    if (g < 1) g = 1;
+    const uint64_t cap = (uint64_t)c->sm_count * 16;
+    if (g > cap) g = cap;
+    if (g > DFB_RED_MAX_BLOCKS) g = DFB_RED_MAX_BLOCKS;
+    DFB_LAUNCH_ON(c, strm, k_spmv_row<N>, (unsigned)g, 128, 0, a);
+  } else {
+    const int warps = 5;
+    const size_t smem = (size_t)warps * TileSmem<N>::WARP_BYTES;
+    static bool configured[3][5] = {};
+    auto kern = (variant == 2) ? k_spmv_tile<N, 2> : k_spmv_tile<N, 1>;
+    if (!configured[variant][N]) {
+      DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[variant][N] = true;
+    }
+    uint64_t n_tiles = (n_rows + 31) / 32;
+    uint64_t g = (n_tiles + warps - 1) / warps;
+    if (g < 1) g = 1;
+    const uint64_t per_sm = c->spmv_ctas_per_sm > 0 ? (uint64_t)c->spmv_ctas_per_sm : 1;
+    if (g > (uint64_t)c->sm_count * per_sm) g = (uint64_t)c->sm_count * per_sm;
+    DFB_LAUNCH_ON(c, strm, kern, (unsigned)g, warps * 32, smem, a);
+  }
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// internal launcher shared with the solvers
+dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm) {
+  dfb_ctx *c = m->ctx;
+  SpmvArgs a;
+  a.row2idx = m->pat->d_row2idx;
+  a.idx2col = m->pat->d_idx2col;
+  a.idx2val = m->d_idx2val;
+  a.row2val = m->d_row2val;
+  a.x = x;
+  a.y = y;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.row_begin = (uint32_t)row_begin;
+  a.row_end = (uint32_t)row_end;
+  a.fuse_dot = fuse_dot;
+  a.parity = state_parity < 0 ? 0 : state_parity;
+  a.st = state_parity < 0 ? nullptr : c->d_state;  // solvers pass their parity slot; standalone mult_vec passes -1
+  if (fuse_dot && !a.st) return dfb_fail(DFB_ERR_BAD_ARG, "spmv: fused dot needs the solver state");
+  a.partials = c->d_partials;
+  a.ticket = c->d_ticket + 1;
+  switch (m->blk_dim) {
+    case 1: return spmv_dispatch<1>(c, a, strm);
+    case 2: return spmv_dispatch<2>(c, a, strm);
+    case 3: return spmv_dispatch<3>(c, a, strm);
+    case 4: return spmv_dispatch<4>(c, a, strm);
+  }
+  return dfb_fail(DFB_ERR_UNSUPPORTED, "spmv: blk_dim %d", m->blk_dim);
+}
+
+// y <- alpha*A*x + beta*y  with halo exchange of x (overlapped with the interior rows) when a halo is attached
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity) {
+  dfb_ctx *c = m->ctx;
+  const uint64_t n = m->pat->num_blk;
+  if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream);
+  // comm stream: wait until x is final, exchange ghosts
+  DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
+  DFB_CUDA(cudaStreamWaitEvent(c->stream_comm, c->ev_a, 0));
+  DFB_TRY(dfb_halo_exchange_on(m->halo, x, n, m->blk_dim, c->stream_comm));
+  DFB_CUDA(cudaEventRecord(c->ev_b, c->stream_comm));
+  // interior rows do not read ghosts
+  int mode = fuse_dot;
+  if (m->int_end > m->int_begin) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_begin, m->int_end, mode, parity, c->stream));
+    if (mode == 1) mode = 2;
+  }
+  DFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  if (m->int_begin > 0) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, m->int_begin, mode, parity, c->stream));
+    if (mode == 1) mode = 2;
+  }
+  if (m->int_end < n) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_end, n, mode, parity, c->stream));
+    if (mode == 1) mode = 2;
+  }
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, dfb_vec *x) {
+  DFB_REQUIRE(m && y && x, "dfb_bsr_mult_vec: NULL argument");
+  DFB_REQUIRE(y->n_blk == m->pat->num_blk && x->n_blk == m->pat->num_blk, "dfb_bsr_mult_vec: y/x length != num_blk (assert_eq!(y_vec.len(), self.num_blk))");
+  DFB_REQUIRE(y->blk_dim == m->blk_dim && x->blk_dim == m->blk_dim, "dfb_bsr_mult_vec: vector block dim != matrix block dim");
+  DFB_REQUIRE(x->d != y->d, "dfb_bsr_mult_vec: x and y alias");
+  return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, -1);
+}
+
+DFB_API dfb_status dfb_bsr_set_halo(dfb_bsr *m, dfb_halo *h, uint64_t int_begin, uint64_t int_end) {
+  DFB_REQUIRE(m, "dfb_bsr_set_halo: NULL argument");
+  DFB_REQUIRE(int_begin <= int_end && int_end <= m->pat->num_blk, "dfb_bsr_set_halo: bad interior range");
+  m->halo = h;
+  m->int_begin = int_begin;
+  m->int_end = int_end;
+  return DFB_OK;
+}

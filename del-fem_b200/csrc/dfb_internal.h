@@ -1,0 +1,186 @@
+// dfb_internal.h — shared internals of libdelfem_b200.so (not part of the public ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/delfem_b200.h"
+
+#define DFB_API extern "C" __attribute__((visibility("default")))
+
+void dfb_set_error(const char *fmt, ...);
+dfb_status dfb_fail(dfb_status st, const char *fmt, ...);
+
+#define DFB_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return dfb_fail(DFB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define DFB_TRY(expr)                 \
+  do {                                \
+    dfb_status _s = (expr);           \
+    if (_s != DFB_OK) return _s;      \
+  } while (0)
+
+#define DFB_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return dfb_fail(DFB_ERR_BAD_ARG, __VA_ARGS__);  \
+  } while (0)
+
+// kernel launch bookkeeping: every product kernel launch goes through this so gpu_launches is a real count
+#define DFB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+    (ctx)->launches += 1;                                                                \
+  } while (0)
+#define DFB_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                         \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                            \
+    (ctx)->launches += 1;                                                                \
+  } while (0)
+#define DFB_CHECK_LAUNCH() DFB_CUDA(cudaGetLastError())
+
+static const int DFB_RED_MAX_BLOCKS = 2048;  // upper bound of any reducing grid
+static const int DFB_RED_K = 4;              // max scalars reduced by one kernel
+
+// device-side solver scalars (lives in ctx->d_state). Two-slot fields are indexed by iteration parity so
+// that the slot a kernel reads is never the slot a thread of the same kernel writes.
+struct DfbSolverState {
+  double rho[2];      // r.z (PCG) / r.r (CG)
+  double red[4];      // [0] p.Ap   [1] r.r   [2] r.z   (targets of the block reductions / all-reduce)
+  double inv_rr0;     // 1 / (r0.r0)
+  double rr0;
+  double tol;
+  double eps_sq;
+  int done[2];        // convergence flag (parity slots)
+  int iter;           // completed iterations
+  int err;            // 1: p.Ap < 0 (ls flavour assert)
+  int check_pap;
+  int pad;
+};
+
+struct dfb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;   // main stream
+  cudaStream_t stream_comm = nullptr;  // halo / boundary overlap stream
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+  cudaEvent_t ev_flag[2] = {nullptr, nullptr};
+  uint64_t launches = 0;
+  int sm_count = 148;
+  int64_t l2_bytes = 0;
+  int64_t total_mem = 0;
+  // reductions
+  double *d_partials = nullptr;   // [DFB_RED_MAX_BLOCKS * DFB_RED_K]
+  unsigned int *d_ticket = nullptr;  // [8]
+  DfbSolverState *d_state = nullptr;
+  double *d_hist = nullptr;       // r.r history
+  uint64_t hist_cap = 0;
+  double *d_scratch = nullptr;    // small scalar scratch [64]
+  void *h_pinned = nullptr;       // pinned host scratch (4 KB)
+  int *d_errflag = nullptr;       // generic device error flag [4]
+  // L2 flush buffer
+  void *flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // options
+  int64_t spmv_variant = 1;
+  int64_t iters_per_sync = 16;
+  int64_t use_graph = 0;
+  int64_t assemble_variant = 0;
+  int64_t spmv_ctas_per_sm = 0;  // 0 = auto
+  // multi-GPU
+  void *nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+struct dfb_vec {
+  dfb_ctx *ctx;
+  uint64_t n_blk, n_ghost;
+  int blk_dim;
+  double *d;
+  uint64_t len() const { return n_blk * (uint64_t)blk_dim; }          // owned scalars
+  uint64_t len_all() const { return (n_blk + n_ghost) * (uint64_t)blk_dim; }
+};
+
+struct dfb_mesh {
+  dfb_ctx *ctx;
+  uint64_t num_elem, num_vtx;
+  int num_node, ndim;
+  uint32_t *d_elem2vtx;
+  double *d_xyz;
+};
+
+struct dfb_pattern {
+  dfb_ctx *ctx;
+  uint64_t num_blk;   // rows stored
+  uint64_t nnz;
+  int convention;
+  uint32_t *d_row2idx;  // [num_blk+1]
+  uint32_t *d_idx2col;  // [nnz] (+pad)
+  int refcount;
+};
+
+struct dfb_halo {
+  dfb_ctx *ctx;
+  int n_peers;
+  std::vector<int> peers;
+  std::vector<uint64_t> send_ptr, recv_ptr;
+  uint32_t *d_send_idx;
+  double *d_sendbuf;     // packed, sized for blk_dim up to 4
+  uint64_t n_send;
+  int max_dim;
+};
+
+struct dfb_bsr {
+  dfb_ctx *ctx;
+  dfb_pattern *pat;
+  int blk_dim;
+  double *d_idx2val;  // [nnz * NN] (+pad)
+  double *d_row2val;  // [num_blk * NN] (convention 0)
+  int32_t *d_flag;    // uploaded BC flags (scratch, lazily allocated)
+  uint64_t flag_cap;
+  dfb_halo *halo;
+  uint64_t int_begin, int_end;
+};
+
+struct dfb_plan {
+  dfb_ctx *ctx;
+  dfb_pattern *pat;
+  uint64_t num_elem;
+  int num_node;
+  int flavour;
+  uint64_t num_slots;    // nnz (+ num_blk for convention 0)
+  uint64_t num_contrib;
+  uint32_t *d_nz2ptr;    // [num_slots+1]
+  uint32_t *d_contrib;   // [num_contrib] code = e*nn2 + i*num_node + j
+  const dfb_mesh *mesh;  // borrowed (elem2vtx used to rebuild elem2nz on demand)
+};
+
+struct dfb_precond {
+  dfb_ctx *ctx;
+  int kind;
+  int blk_dim;
+  uint64_t num_blk;
+  double *d_inv;  // jacobi: [num_blk*N] ; block-jacobi: [num_blk*NN] inverse blocks (column-major)
+};
+
+// ---- helpers implemented in ctx.cu
+dfb_status dfb_dev_alloc(void **p, size_t bytes);
+template <typename T>
+static inline dfb_status dfb_dev_alloc_t(T **p, size_t count) {
+  return dfb_dev_alloc((void **)p, count * sizeof(T) + 256);
+}
+dfb_status dfb_check_error_flag(dfb_ctx *ctx, int slot, dfb_status st, const char *what);
+
+// ---- cross-file entry points
+dfb_status dfb_exclusive_scan_u32(dfb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *total_out);
+dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaStream_t strm);
+dfb_status dfb_halo_exchange_on(dfb_halo *h, double *d_vec, uint64_t n_blk, int blk_dim, cudaStream_t strm);
+dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm);
+
+static inline int dfb_div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }

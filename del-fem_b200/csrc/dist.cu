@@ -1,0 +1,176 @@
+// dist.cu — multi-GPU plumbing: one rank (process) per GPU, NCCL over NVLink 5 / NVSwitch.
+//   * SpMV halo: pack kernel -> grouped ncclSend/ncclRecv; the receive lands directly in the ghost tail of the vector
+//   * PCG scalars: ncclAllReduce(sum, fp64, 1..2) on the solver-state buffer, stream-ordered (no host sync)
+// NCCL is resolved lazily with dlopen so that single-GPU users need no NCCL at all (and so that a process that has
+// already loaded PyTorch's bundled libnccl.so.2 shares it).  The reference has no multi-device code.
+#include <dlfcn.h>
+#include <string.h>
+
+#include "dfb_internal.h"
+
+typedef void *nccl_comm_t;
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_GetUniqueId)(nccl_uid_t *);
+typedef int (*fn_CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int);
+typedef int (*fn_CommDestroy)(nccl_comm_t);
+typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_Send)(const void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_Recv)(void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+typedef int (*fn_Group)(void);
+typedef const char *(*fn_ErrStr)(int);
+
+static struct {
+  void *h;
+  fn_GetUniqueId GetUniqueId;
+  fn_CommInitRank CommInitRank;
+  fn_CommDestroy CommDestroy;
+  fn_AllReduce AllReduce;
+  fn_Send Send;
+  fn_Recv Recv;
+  fn_Group GroupStart, GroupEnd;
+  fn_ErrStr GetErrorString;
+} g_nccl = {};
+
+static const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+static dfb_status nccl_load() {
+  if (g_nccl.h) return DFB_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.h; ++i) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.h) return dfb_fail(DFB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                         \
+  g_nccl.field = (decltype(g_nccl.field))dlsym(g_nccl.h, name);                  \
+  if (!g_nccl.field) return dfb_fail(DFB_ERR_NCCL, "libnccl: missing symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return DFB_OK;
+}
+
+#define DFB_NCCL(expr)                                                                                   \
+  do {                                                                                                   \
+    int _r = (expr);                                                                                     \
+    if (_r != 0) return dfb_fail(DFB_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString(_r));       \
+  } while (0)
+
+DFB_API dfb_status dfb_comm_unique_id(uint8_t id_out[128]) {
+  DFB_REQUIRE(id_out, "dfb_comm_unique_id: NULL argument");
+  DFB_TRY(nccl_load());
+  nccl_uid_t uid;
+  DFB_NCCL(g_nccl.GetUniqueId(&uid));
+  memcpy(id_out, uid.internal, 128);
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_ctx_comm_init(dfb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t nranks) {
+  DFB_REQUIRE(ctx && id, "dfb_ctx_comm_init: NULL argument");
+  DFB_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "dfb_ctx_comm_init: bad rank %d / %d", rank, nranks);
+  DFB_TRY(nccl_load());
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  nccl_uid_t uid;
+  memcpy(uid.internal, id, 128);
+  nccl_comm_t comm = nullptr;
+  DFB_NCCL(g_nccl.CommInitRank(&comm, nranks, uid, rank));
+  ctx->nccl_comm = comm;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return DFB_OK;
+}
+
+dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaStream_t strm) {
+  if (ctx->nranks <= 1) return DFB_OK;
+  DFB_REQUIRE(ctx->nccl_comm, "all-reduce requested but the context has no communicator");
+  DFB_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, strm));
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ halo
+__global__ void k_halo_pack(const double *__restrict__ v, const uint32_t *__restrict__ idx, uint64_t n_send, int dim,
+                            double *__restrict__ buf) {
+  const uint64_t total = n_send * dim;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = q / dim;
+    const int d = (int)(q - s * dim);
+    buf[q] = v[(uint64_t)idx[s] * dim + d];
+  }
+}
+
+DFB_API dfb_status dfb_halo_create(dfb_ctx *ctx, int32_t n_peers, const int32_t *peers, const uint64_t *send_ptr,
+                                   const uint32_t *send_idx, const uint64_t *recv_ptr, dfb_halo **out) {
+  DFB_REQUIRE(ctx && out, "dfb_halo_create: NULL argument");
+  DFB_REQUIRE(n_peers >= 0, "dfb_halo_create: n_peers < 0");
+  DFB_REQUIRE(n_peers == 0 || (peers && send_ptr && recv_ptr), "dfb_halo_create: NULL array");
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  dfb_halo *h = new dfb_halo();
+  h->ctx = ctx;
+  h->n_peers = n_peers;
+  h->peers.assign(peers, peers + n_peers);
+  h->send_ptr.assign(1, 0);
+  h->recv_ptr.assign(1, 0);
+  if (n_peers > 0) {
+    h->send_ptr.assign(send_ptr, send_ptr + n_peers + 1);
+    h->recv_ptr.assign(recv_ptr, recv_ptr + n_peers + 1);
+  }
+  h->n_send = h->send_ptr.back();
+  h->max_dim = 4;
+  h->d_send_idx = nullptr;
+  h->d_sendbuf = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&h->d_send_idx, h->n_send + 2);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&h->d_sendbuf, h->n_send * h->max_dim + 2);
+  if (st == DFB_OK && h->n_send > 0) {
+    DFB_REQUIRE(send_idx, "dfb_halo_create: send_idx is NULL");
+    cudaError_t e = cudaMemcpyAsync(h->d_send_idx, send_idx, h->n_send * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_halo_create: %s", cudaGetErrorString(e));
+  }
+  if (st != DFB_OK) {
+    dfb_halo_destroy(h);
+    return st;
+  }
+  *out = h;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_halo_destroy(dfb_halo *h) {
+  if (!h) return DFB_OK;
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaStreamSynchronize(h->ctx->stream_comm);
+  cudaFree(h->d_send_idx);
+  cudaFree(h->d_sendbuf);
+  delete h;
+  return DFB_OK;
+}
+
+dfb_status dfb_halo_exchange_on(dfb_halo *h, double *d_vec, uint64_t n_blk, int blk_dim, cudaStream_t strm) {
+  dfb_ctx *c = h->ctx;
+  if (c->nranks <= 1 || h->n_peers == 0) return DFB_OK;
+  DFB_REQUIRE(c->nccl_comm, "halo exchange requested but the context has no communicator");
+  DFB_REQUIRE(blk_dim <= h->max_dim, "halo exchange: blk_dim too large");
+  if (h->n_send > 0) {
+    int g = dfb_div_up(h->n_send * blk_dim, 256);
+    if (g > c->sm_count * 4) g = c->sm_count * 4;
+    DFB_LAUNCH_ON(c, strm, k_halo_pack, g, 256, 0, d_vec, h->d_send_idx, h->n_send, blk_dim, h->d_sendbuf);
+    DFB_CHECK_LAUNCH();
+  }
+  DFB_NCCL(g_nccl.GroupStart());
+  for (int p = 0; p < h->n_peers; ++p) {
+    const uint64_t ns = h->send_ptr[p + 1] - h->send_ptr[p], nr = h->recv_ptr[p + 1] - h->recv_ptr[p];
+    if (ns) DFB_NCCL(g_nccl.Send(h->d_sendbuf + h->send_ptr[p] * blk_dim, ns * blk_dim, NCCL_FLOAT64, h->peers[p], c->nccl_comm, strm));
+    if (nr) DFB_NCCL(g_nccl.Recv(d_vec + (n_blk + h->recv_ptr[p]) * blk_dim, nr * blk_dim, NCCL_FLOAT64, h->peers[p], c->nccl_comm, strm));
+  }
+  DFB_NCCL(g_nccl.GroupEnd());
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_halo_exchange(dfb_halo *h, dfb_vec *v) {
+  DFB_REQUIRE(h && v, "dfb_halo_exchange: NULL argument");
+  DFB_REQUIRE(v->n_ghost >= h->recv_ptr.back(), "dfb_halo_exchange: vector has fewer ghost blocks than the halo receives");
+  return dfb_halo_exchange_on(h, v->d, v->n_blk, v->blk_dim, h->ctx->stream);
+}

@@ -1,0 +1,458 @@
+// solver.cu — conjugate_gradient (del-fem-cpu/src/sparse_square.rs:218-261, del-fem-ls/src/solver_sparse.rs:5-70) and
+// preconditioned_conjugate_gradient (sparse_square.rs:264-347, solver_sparse.rs:73-175) with Jacobi / block-Jacobi
+// (sparse_ilu.rs:87-219 on an empty off-diagonal pattern).
+//
+// One iteration = three kernels, no host round trip:
+//   K1  q = A p            fused  p.q                       (bsr.cu; deterministic last-block reduction -> red[0])
+//   K2  alpha = rho/p.q;   r -= alpha q;  x += alpha p;     fused  r.r, r.(M^-1 r)  -> red[1], red[2]
+//   K3  beta = r.z/rho;    p = M^-1 r + beta p;             thread 0 records ||r||^2, tests convergence, swaps rho
+// alpha/beta live on the device; the host polls a convergence flag every `iters_per_sync` iterations (one chunk of
+// look-ahead); iterations enqueued past convergence exit at their first instruction, so x, r and the history are
+// exactly those of the reference's early return.  Multi-GPU: red[] is all-reduced between the kernels.
+#include <math.h>
+
+#include <vector>
+
+#include "dfb_internal.h"
+#include "reduce.cuh"
+
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity);
+
+// ------------------------------------------------------------------------------------------------ preconditioner
+template <int N>
+__device__ __forceinline__ bool invert_block(double *inv, const double *a) {
+  // Gauss-Jordan with partial pivoting on a column-major NxN block
+  double m[N][2 * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      m[i][j] = a[i + N * j];
+      m[i][N + j] = (i == j) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    int p = c;
+#pragma unroll
+    for (int r = c + 1; r < N; ++r)
+      if (fabs(m[r][c]) > fabs(m[p][c])) p = r;
+    if (m[p][c] == 0.0) return false;
+    if (p != c) {
+#pragma unroll
+      for (int j = 0; j < 2 * N; ++j) {
+        const double t = m[p][j];
+        m[p][j] = m[c][j];
+        m[c][j] = t;
+      }
+    }
+    const double d = 1.0 / m[c][c];
+#pragma unroll
+    for (int j = 0; j < 2 * N; ++j) m[c][j] *= d;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double f = m[r][c];
+#pragma unroll
+      for (int j = 0; j < 2 * N; ++j) m[r][j] -= f * m[c][j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) inv[i + N * j] = m[i][N + j];
+  return true;
+}
+
+// diagonal block of row i (separate diagonal, or searched inside the pattern for convention 1)
+__device__ __forceinline__ const double *find_diag(uint64_t i, int NN, const double *row2val, const double *idx2val,
+                                                   const uint32_t *row2idx, const uint32_t *idx2col) {
+  if (row2val) return row2val + i * NN;
+  for (uint32_t k = row2idx[i]; k < row2idx[i + 1]; ++k)
+    if (idx2col[k] == (uint32_t)i) return idx2val + (uint64_t)k * NN;
+  return nullptr;
+}
+
+template <int N>
+__global__ void k_precond_update(int kind, uint64_t num_blk, const double *__restrict__ row2val, const double *__restrict__ idx2val,
+                                 const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
+                                 double *__restrict__ inv, int *err) {
+  constexpr int NN = N * N;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double *D = find_diag(i, NN, row2val, idx2val, row2idx, idx2col);
+    if (!D) {
+      atomicExch(err, 1);
+      continue;
+    }
+    if (kind == DFB_PRECOND_JACOBI) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const double v = D[d + N * d];
+        if (v == 0.0) atomicExch(err, 1);
+        inv[i * N + d] = 1.0 / v;
+      }
+    } else {
+      double a[NN], b[NN];
+#pragma unroll
+      for (int q = 0; q < NN; ++q) a[q] = D[q];
+      if (!invert_block<N>(b, a)) {
+        atomicExch(err, 1);
+        continue;
+      }
+#pragma unroll
+      for (int q = 0; q < NN; ++q) inv[i * NN + q] = b[q];
+    }
+  }
+}
+
+DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, dfb_precond **out) {
+  DFB_REQUIRE(ctx && m && out, "dfb_precond_create: NULL argument");
+  DFB_REQUIRE(kind >= DFB_PRECOND_NONE && kind <= DFB_PRECOND_BLOCK_JACOBI, "dfb_precond_create: unknown kind %d", kind);
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  dfb_precond *pc = new dfb_precond();
+  pc->ctx = ctx;
+  pc->kind = kind;
+  pc->blk_dim = m->blk_dim;
+  pc->num_blk = m->pat->num_blk;
+  pc->d_inv = nullptr;
+  if (kind != DFB_PRECOND_NONE) {
+    const uint64_t per = kind == DFB_PRECOND_JACOBI ? (uint64_t)m->blk_dim : (uint64_t)m->blk_dim * m->blk_dim;
+    dfb_status st = dfb_dev_alloc_t(&pc->d_inv, pc->num_blk * per + 8);
+    if (st != DFB_OK) {
+      delete pc;
+      return st;
+    }
+  }
+  *out = pc;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {
+  DFB_REQUIRE(pc && m, "dfb_precond_update: NULL argument");
+  DFB_REQUIRE(pc->num_blk == m->pat->num_blk && pc->blk_dim == m->blk_dim, "dfb_precond_update: shape mismatch");
+  if (pc->kind == DFB_PRECOND_NONE) return DFB_OK;
+  dfb_ctx *c = pc->ctx;
+  const int grid = c->sm_count * 8;
+#define PC_CASE(NV)                                                                                                       \
+  case NV:                                                                                                                \
+    DFB_LAUNCH(c, k_precond_update<NV>, grid, 128, 0, pc->kind, pc->num_blk, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, \
+               m->pat->d_idx2col, pc->d_inv, c->d_errflag + 2);                                                           \
+    break;
+  switch (pc->blk_dim) {
+    PC_CASE(1)
+    PC_CASE(2)
+    PC_CASE(3)
+    PC_CASE(4)
+  }
+#undef PC_CASE
+  DFB_CHECK_LAUNCH();
+  return dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "dfb_precond_update: singular (or missing) diagonal block (try_inverse().unwrap())");
+}
+
+template <int N, int KIND>
+__device__ __forceinline__ void apply_minv(double (&z)[N], const double *__restrict__ inv, uint64_t i, const double (&r)[N]) {
+  if (KIND == DFB_PRECOND_NONE) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) z[d] = r[d];
+  } else if (KIND == DFB_PRECOND_JACOBI) {
+#pragma unroll
+    for (int d = 0; d < N; ++d) z[d] = inv[i * N + d] * r[d];
+  } else {
+    const double *B = inv + i * N * N;
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < N; ++b) s += B[a + N * b] * r[b];
+      z[a] = s;
+    }
+  }
+}
+
+template <int N, int KIND>
+__global__ void k_precond_apply(double *__restrict__ v, const double *__restrict__ inv, uint64_t num_blk) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    double r[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) r[d] = v[i * N + d];
+    apply_minv<N, KIND>(z, inv, i, r);
+#pragma unroll
+    for (int d = 0; d < N; ++d) v[i * N + d] = z[d];
+  }
+}
+
+#define DISPATCH_N_KIND(NV, KV, MACRO) \
+  if (n == NV && kind == KV) { MACRO(NV, KV); }
+#define DISPATCH_ALL(MACRO)                                 \
+  DISPATCH_N_KIND(1, 0, MACRO) DISPATCH_N_KIND(1, 1, MACRO) DISPATCH_N_KIND(1, 2, MACRO) \
+  DISPATCH_N_KIND(2, 0, MACRO) DISPATCH_N_KIND(2, 1, MACRO) DISPATCH_N_KIND(2, 2, MACRO) \
+  DISPATCH_N_KIND(3, 0, MACRO) DISPATCH_N_KIND(3, 1, MACRO) DISPATCH_N_KIND(3, 2, MACRO) \
+  DISPATCH_N_KIND(4, 0, MACRO) DISPATCH_N_KIND(4, 1, MACRO) DISPATCH_N_KIND(4, 2, MACRO)
+
+DFB_API dfb_status dfb_precond_apply(const dfb_precond *pc, dfb_vec *v) {
+  DFB_REQUIRE(pc && v, "dfb_precond_apply: NULL argument");
+  DFB_REQUIRE(v->n_blk == pc->num_blk && v->blk_dim == pc->blk_dim, "dfb_precond_apply: shape mismatch");
+  dfb_ctx *c = pc->ctx;
+  const int n = pc->blk_dim, kind = pc->kind;
+  const int grid = c->sm_count * 8;
+#define APPLY(NV, KV) DFB_LAUNCH(c, (k_precond_apply<NV, KV>), grid, 256, 0, v->d, pc->d_inv, pc->num_blk)
+  DISPATCH_ALL(APPLY)
+#undef APPLY
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_precond_destroy(dfb_precond *pc) {
+  if (!pc) return DFB_OK;
+  cudaStreamSynchronize(pc->ctx->stream);
+  cudaFree(pc->d_inv);
+  delete pc;
+  return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ (P)CG kernels
+// K0: x = 0 ; p = M^-1 r ; red[1] = r.r ; red[2] = r.(M^-1 r)
+template <int N, int KIND>
+__global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, double *__restrict__ x, double *__restrict__ p,
+                                                  const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
+                                                  double *partials, unsigned int *ticket) {
+  __shared__ double s_buf[64];
+  double acc[2] = {0.0, 0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    double rv[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) rv[d] = r[i * N + d];
+    apply_minv<N, KIND>(z, inv, i, rv);
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      x[i * N + d] = 0.0;
+      p[i * N + d] = z[d];
+      acc[0] += rv[d] * rv[d];
+      acc[1] += rv[d] * z[d];
+    }
+  }
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
+    st->red[1] = acc[0];
+    st->red[2] = acc[1];
+  }
+}
+
+// after the (all-reduced) initial dots: set up the state. hist[0] = r0.r0
+__global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol, double eps_sq, int check_pap) {
+  const double rr0 = st->red[1];
+  st->rr0 = rr0;
+  st->inv_rr0 = 1.0 / rr0;
+  st->rho[0] = st->red[2];
+  st->rho[1] = 0.0;
+  st->tol = tol;
+  st->eps_sq = eps_sq;
+  st->done[0] = (rr0 < eps_sq) ? 1 : 0;
+  st->done[1] = st->done[0];
+  st->iter = 0;
+  st->err = 0;
+  st->check_pap = check_pap;
+  hist[0] = rr0;
+}
+
+// K2: alpha = rho / (p.q) ; r -= alpha q ; x += alpha p ; red[1] = r.r ; red[2] = r.(M^-1 r)
+template <int N, int KIND>
+__global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
+                                                    const double *__restrict__ p, const double *__restrict__ inv,
+                                                    uint64_t num_blk, DfbSolverState *st, int parity, double *partials,
+                                                    unsigned int *ticket) {
+  __shared__ double s_buf[64];
+  if (st->done[parity]) return;
+  const double pq = st->red[0];
+  const double alpha = st->rho[parity] / pq;
+  double acc[2] = {0.0, 0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    double rv[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      rv[d] = r[i * N + d] - alpha * q[i * N + d];
+      r[i * N + d] = rv[d];
+      x[i * N + d] += alpha * p[i * N + d];
+    }
+    apply_minv<N, KIND>(z, inv, i, rv);
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      acc[0] += rv[d] * rv[d];
+      acc[1] += rv[d] * z[d];
+    }
+  }
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
+    st->red[1] = acc[0];
+    st->red[2] = acc[1];
+  }
+}
+
+// K3: beta = r.z / rho ; p = M^-1 r + beta p ; thread 0 of block 0: history, convergence, rho swap
+template <int N, int KIND>
+__global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict__ r, double *__restrict__ p,
+                                                       const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
+                                                       int parity, double *hist, uint64_t hist_cap) {
+  if (st->done[parity]) {
+    // converged earlier: propagate the flag into the slot the next iteration reads, change nothing else
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
+    return;
+  }
+  const double rr = st->red[1], rz = st->red[2];
+  const double beta = rz / st->rho[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int it = st->iter + 1;
+    st->iter = it;
+    if ((uint64_t)it < hist_cap) hist[it] = rr;
+    const double conv_ratio = sqrt(rr * st->inv_rr0);
+    int done = (conv_ratio < st->tol) ? 1 : 0;
+    if (st->check_pap && !(st->red[0] >= 0.0)) {
+      st->err = 1;
+      done = 1;
+    }
+    st->done[parity ^ 1] = done;
+    st->rho[parity ^ 1] = rz;
+  }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    double rv[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) rv[d] = r[i * N + d];
+    apply_minv<N, KIND>(z, inv, i, rv);
+#pragma unroll
+    for (int d = 0; d < N; ++d) p[i * N + d] = z[d] + beta * p[i * N + d];
+  }
+}
+
+struct FlagsHost {
+  int done[2];
+  int iter;
+  int err;
+};
+
+static int vec_grid(const dfb_ctx *c, uint64_t num_blk) {
+  uint64_t g = (num_blk + 255) / 256;
+  const uint64_t cap = (uint64_t)c->sm_count * 8;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  if (g > DFB_RED_MAX_BLOCKS) g = DFB_RED_MAX_BLOCKS;
+  return (int)g;
+}
+
+// shared driver. mode 0 = CG history semantics (ratios, k=0 excluded), 1 = PCG (absolute, k=0 included, trailing entry)
+static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, dfb_vec *x, dfb_vec *q, dfb_vec *p, double tol,
+                          uint64_t max_it, double eps_sq, int check_pap, int mode, double *hist_out, uint64_t hist_cap,
+                          uint64_t *n_hist) {
+  dfb_ctx *c = m->ctx;
+  const uint64_t nb = m->pat->num_blk;
+  const int n = m->blk_dim;
+  const int kind = pc ? pc->kind : DFB_PRECOND_NONE;
+  const double *inv = pc ? pc->d_inv : nullptr;
+  for (dfb_vec *v : {r, x, q, p}) {
+    DFB_REQUIRE(v && v->n_blk == nb && v->blk_dim == n, "(p)cg: vector shape != matrix shape (assert_eq!(r_vec.len(), mat.num_blk))");
+    DFB_REQUIRE(v->ctx == c, "(p)cg: vector belongs to another context");
+  }
+  if (pc) DFB_REQUIRE(pc->num_blk == nb && pc->blk_dim == n, "pcg: preconditioner shape != matrix shape");
+  DFB_REQUIRE(max_it < 0x7FFFFFF0ull, "(p)cg: max_it too large");
+  // device history buffer
+  if (c->hist_cap < max_it + 2) {
+    cudaFree(c->d_hist);
+    c->d_hist = nullptr;
+    DFB_TRY(dfb_dev_alloc_t(&c->d_hist, max_it + 2));
+    c->hist_cap = max_it + 2;
+  }
+  const int G = vec_grid(c, nb);
+  DfbSolverState *st = c->d_state;
+
+#define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2)
+  DISPATCH_ALL(INIT)
+#undef INIT
+  DFB_CHECK_LAUNCH();
+  if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 1, 0, st, c->d_hist, tol, eps_sq, check_pap);
+  DFB_CHECK_LAUNCH();
+
+  FlagsHost *hf = (FlagsHost *)c->h_pinned;  // two slots
+  hf[0].done[0] = hf[0].done[1] = hf[1].done[0] = hf[1].done[1] = 0;
+  uint64_t chunk = c->iters_per_sync > 0 ? (uint64_t)c->iters_per_sync : 16;
+  uint64_t enq = 0;  // iterations enqueued
+  int n_chunks = 0;
+  bool finished = false;
+  FlagsHost last = {{0, 0}, 0, 0};
+  while (!finished) {
+    const uint64_t todo = (max_it - enq < chunk) ? (max_it - enq) : chunk;
+    for (uint64_t j = 0; j < todo; ++j) {
+      const int parity = (int)((enq + j) & 1);
+      DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity));
+      if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
+#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2)
+      DISPATCH_ALL(UPD)
+#undef UPD
+      if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap)
+      DISPATCH_ALL(DIR)
+#undef DIR
+    }
+    DFB_CHECK_LAUNCH();
+    enq += todo;
+    const int slot = n_chunks & 1;
+    DFB_CUDA(cudaMemcpyAsync(&hf[slot], &st->done[0], sizeof(FlagsHost), cudaMemcpyDeviceToHost, c->stream));
+    DFB_CUDA(cudaEventRecord(c->ev_flag[slot], c->stream));
+    ++n_chunks;
+    // look at the flags of the PREVIOUS chunk (one chunk of look-ahead keeps the GPU busy)
+    if (n_chunks >= 2) {
+      const int prev = (n_chunks - 2) & 1;
+      DFB_CUDA(cudaEventSynchronize(c->ev_flag[prev]));
+      last = hf[prev];
+      if (last.done[0] || last.done[1]) finished = true;
+    }
+    if (enq >= max_it || todo == 0) {
+      DFB_CUDA(cudaEventSynchronize(c->ev_flag[slot]));
+      last = hf[slot];
+      finished = true;
+    }
+  }
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    const int slot = (n_chunks - 1) & 1;
+    last = hf[slot];
+  }
+  if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
+
+  // history: the device stored ||r_k||^2 for k = 0..iter
+  const uint64_t iters = (uint64_t)last.iter;
+  std::vector<double> rr(iters + 1);
+  DFB_CUDA(cudaMemcpyAsync(rr.data(), c->d_hist, (iters + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  const double rr0 = rr[0];
+  const bool converged = last.done[0] || last.done[1];
+  uint64_t nh = 0;
+  auto push = [&](double v) {
+    if (hist_out && nh < hist_cap) hist_out[nh] = v;
+    ++nh;
+  };
+  if (mode == 0) {
+    // CG: empty history if ||r0||^2 < eps (sparse_square.rs:235); ratios for k>=1
+    if (!(rr0 < eps_sq)) {
+      const double inv0 = 1.0 / rr0;
+      for (uint64_t k = 1; k <= iters; ++k) push(sqrt(rr[k] * inv0));
+    }
+  } else {
+    // PCG: absolute norms incl. k=0 (:291,:321), one trailing entry when max_it is exhausted (:341-345)
+    push(sqrt(rr0));
+    if (!(rr0 < eps_sq)) {
+      for (uint64_t k = 1; k <= iters; ++k) push(sqrt(rr[k]));
+      if (!converged) push(sqrt(rr[iters]));
+    }
+  }
+  if (n_hist) *n_hist = nh;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_cg(const dfb_bsr *m, dfb_vec *r, dfb_vec *u, dfb_vec *ap, dfb_vec *p, double tol, uint64_t max_it,
+                          double eps_sq, int32_t check_pap, double *hist_out, uint64_t hist_cap, uint64_t *n_hist) {
+  DFB_REQUIRE(m, "dfb_cg: matrix is NULL");
+  return run_pcg(m, nullptr, r, u, ap, p, tol, max_it, eps_sq, check_pap, 0, hist_out, hist_cap, n_hist);
+}
+
+DFB_API dfb_status dfb_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, dfb_vec *x, dfb_vec *pr, dfb_vec *p, double tol,
+                           uint64_t max_it, double eps_sq, double *hist_out, uint64_t hist_cap, uint64_t *n_hist) {
+  DFB_REQUIRE(m && pc, "dfb_pcg: NULL argument");
+  return run_pcg(m, pc, r, x, pr, p, tol, max_it, eps_sq, 0, 1, hist_out, hist_cap, n_hist);
+}

@@ -1,0 +1,43 @@
+"""Mirror of del-fem-cpu/src/sparse_ilu.rs for the preconditioners that exist on the device: the ILU code path with an
+empty off-diagonal pattern (= block-Jacobi) and point Jacobi. ILU(0)/ILU(k) with real fill are §8(f) "next"."""
+from __future__ import annotations
+
+import ctypes as C
+
+from ._lib import check, lib
+from .core import PRECOND, Ctx, Vec
+from .sparse_square import Matrix
+
+
+class Preconditioner:
+    def __init__(self, kind="block_jacobi"):
+        self.kind = PRECOND[kind] if isinstance(kind, str) else kind
+        self.h = None
+        self.ctx = None
+
+    def initialize(self, a: Matrix):
+        """initialize_ilu0-like symbolic phase (:28): allocates the inverse-diagonal storage"""
+        self.ctx = a.ctx
+        h = C.c_void_p()
+        check(lib().dfb_precond_create(a.ctx.h, self.kind, a.h, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().dfb_precond_destroy(self.h)
+            self.h = None
+
+
+def copy_value(ilu: Preconditioner, a: Matrix):
+    """copy_value (:87-125) — fused with decompose on the device (the copy is never materialised)"""
+    ilu._src = a
+
+
+def decompose(ilu: Preconditioner):
+    """decompose (:127-181): stores D_i^-1 (raises DfbError(SINGULAR_DIAG) where the reference unwraps None)"""
+    check(lib().dfb_precond_update(ilu.h, ilu._src.h))
+
+
+def solve_preconditioning_vec(vec: Vec, ilu: Preconditioner):
+    """solve_preconditioning_vec (:183-219), in place"""
+    check(lib().dfb_precond_apply(ilu.h, vec.h))
