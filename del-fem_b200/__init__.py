@@ -7,7 +7,7 @@ succeeds without the library, but the first call raises ImportError / DfbError i
 """
 from . import core, elements, linearsystem, sparse_ilu, sparse_square  # noqa: F401
 from ._lib import LIB_PATH, STATUS, DfbError, build, header_symbols, lib  # noqa: F401
-from .core import ELEM, PRECOND, Ctx, Halo, Mesh, Pattern, Plan, Vec  # noqa: F401
+from .core import ELEM, PRECOND, BcFlag, Ctx, Halo, Mesh, Pattern, Plan, Vec  # noqa: F401
 from .sparse_square import Matrix, conjugate_gradient, preconditioned_conjugate_gradient  # noqa: F401
 
 __version__ = "0.1.0"

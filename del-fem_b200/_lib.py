@@ -79,6 +79,14 @@ def lib():
         "dfb_timer_stop": [_vp, C.POINTER(C.c_float)],
         "dfb_flush_l2": [_vp],
         "dfb_device_info": [_vp, C.POINTER(_i32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+        "dfb_host_register": [_vp, _vp, _u64],
+        "dfb_host_unregister": [_vp, _vp],
+        "dfb_profile_spmv": [_vp, C.POINTER(_f64), C.POINTER(_u64), _i32],
+        "dfb_bcflag_create": [_vp, _vp, _u64, _i32, _pp],
+        "dfb_bcflag_destroy": [_vp],
+        "dfb_vec_set_fixed_dof_zero_dev": [_vp, _vp],
+        "dfb_mesh_rotate_vertex_ids": [_vp, _u64],
+        "dfb_bsr_set_fixed_dof_dev": [_vp, _f64, _vp],
         "dfb_vec_create": [_vp, _u64, _u64, _i32, _pp],
         "dfb_vec_destroy": [_vp],
         "dfb_vec_upload": [_vp, _vp],

@@ -71,6 +71,19 @@ class Ctx:
         check(lib().dfb_device_info(self.h, C.byref(sm), C.byref(l2), C.byref(mem)))
         return {"sm_count": sm.value, "l2_bytes": l2.value, "total_mem_bytes": mem.value}
 
+    def host_register(self, a: np.ndarray):
+        """page-lock a numpy buffer (so uploads from it are asynchronous DMA at full PCIe speed)"""
+        check(lib().dfb_host_register(self.h, _ptr(a), a.nbytes))
+
+    def host_unregister(self, a: np.ndarray):
+        check(lib().dfb_host_unregister(self.h, _ptr(a)))
+
+    def profile_spmv(self, reset=False):
+        """(total_ms, count) of the SpMV launches bracketed with CUDA events while option profile_spmv = 1"""
+        ms, n = C.c_double(), C.c_uint64()
+        check(lib().dfb_profile_spmv(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
     def comm_init(self, uid: bytes, rank: int, nranks: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         check(lib().dfb_ctx_comm_init(self.h, buf, rank, nranks))
@@ -139,6 +152,9 @@ class Vec:
             raise DfbError(1, "Vec.set_fixed_dof_zero: flag size mismatch")
         check(lib().dfb_vec_set_fixed_dof_zero(self.h, _ptr(f)))
 
+    def set_fixed_dof_zero_dev(self, flag: "BcFlag"):
+        check(lib().dfb_vec_set_fixed_dof_zero_dev(self.h, flag.h))
+
     def fill_splitmix(self, seed, first_idx, lo, hi):
         check(lib().dfb_vec_fill_splitmix(self.h, int(seed), int(first_idx), float(lo), float(hi)))
 
@@ -148,6 +164,22 @@ class Vec:
     def __del__(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             lib().dfb_vec_destroy(self.h)
+            self.h = None
+
+
+class BcFlag:
+    """device-resident `&[[i32; N]]` Dirichlet flags"""
+
+    def __init__(self, ctx: Ctx, blk2isfix):
+        f = _c(blk2isfix, np.int32)
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib().dfb_bcflag_create(ctx.h, _ptr(f), f.shape[0], f.shape[1], C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            lib().dfb_bcflag_destroy(self.h)
             self.h = None
 
 
@@ -184,6 +216,9 @@ class Mesh:
         hd = C.c_void_p()
         check(lib().dfb_mesh_create_kuhn(ctx.h, nx, ny, nz, float(h), k_begin, k_end, C.byref(hd)))
         return cls(ctx, _handle=hd)
+
+    def rotate_vertex_ids(self, shift):
+        check(lib().dfb_mesh_rotate_vertex_ids(self.h, int(shift)))
 
     def update_xyz(self, vtx2xyz):
         xyz = _c(vtx2xyz, np.float64)

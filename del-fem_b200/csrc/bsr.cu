@@ -151,11 +151,27 @@ __global__ void k_set_fixed_bc(double val_dia, const int32_t *__restrict__ flag,
   }
 }
 
+static dfb_status launch_set_fixed_bc(dfb_bsr *m, double val_dia, const int32_t *d_flag) {
+  dfb_ctx *c = m->ctx;
+  const int grid = c->sm_count * 8;
+  switch (m->blk_dim) {
+    case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 2: DFB_LAUNCH(c, k_set_fixed_bc<2>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 3: DFB_LAUNCH(c, k_set_fixed_bc<3>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+    case 4: DFB_LAUNCH(c, k_set_fixed_bc<4>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
+  }
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+static uint64_t bsr_n_all(const dfb_bsr *m) {
+  return m->pat->num_blk + (m->halo ? (m->halo->recv_ptr.empty() ? 0 : m->halo->recv_ptr.back()) : 0);
+}
+
 DFB_API dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *flag_host) {
   DFB_REQUIRE(m && flag_host, "dfb_bsr_set_fixed_dof: NULL argument");
   dfb_ctx *c = m->ctx;
-  const uint64_t n_all = m->pat->num_blk + (m->halo ? (m->halo->recv_ptr.empty() ? 0 : m->halo->recv_ptr.back()) : 0);
-  const uint64_t need = n_all * m->blk_dim;
+  const uint64_t need = bsr_n_all(m) * m->blk_dim;
   if (m->flag_cap < need) {
     cudaFree(m->d_flag);
     m->d_flag = nullptr;
@@ -163,16 +179,15 @@ DFB_API dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32
     m->flag_cap = need;
   }
   DFB_CUDA(cudaMemcpyAsync(m->d_flag, flag_host, need * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  const int grid = c->sm_count * 8;
-  switch (m->blk_dim) {
-    case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
-    case 2: DFB_LAUNCH(c, k_set_fixed_bc<2>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
-    case 3: DFB_LAUNCH(c, k_set_fixed_bc<3>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
-    case 4: DFB_LAUNCH(c, k_set_fixed_bc<4>, grid, 128, 0, val_dia, m->d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
-  }
-  DFB_CHECK_LAUNCH();
+  DFB_TRY(launch_set_fixed_bc(m, val_dia, m->d_flag));
   DFB_CUDA(cudaStreamSynchronize(c->stream));  // flag_host is borrowed only for the duration of the call
   return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcflag *f) {
+  DFB_REQUIRE(m && f, "dfb_bsr_set_fixed_dof_dev: NULL argument");
+  DFB_REQUIRE(f->blk_dim == m->blk_dim && f->n_blk_all >= bsr_n_all(m), "dfb_bsr_set_fixed_dof_dev: assert_eq!(bc_flag.len(), row2val.len())");
+  return launch_set_fixed_bc(m, val_dia, f->d);
 }
 
 // row2val[i][d + N d] += scale * v[i][d]

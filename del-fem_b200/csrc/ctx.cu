@@ -84,6 +84,7 @@ DFB_API dfb_status dfb_ctx_destroy(dfb_ctx *c) {
   cudaFree(c->d_errflag);
   cudaFree(c->flush_buf);
   cudaFreeHost(c->h_pinned);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_t0);
   cudaEventDestroy(c->ev_t1);
   cudaEventDestroy(c->ev_a);
@@ -116,6 +117,7 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "use_graph")) return &c->use_graph;
   if (!strcmp(key, "assemble_variant")) return &c->assemble_variant;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
+  if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
   return nullptr;
 }
 
@@ -174,6 +176,63 @@ DFB_API dfb_status dfb_device_info(dfb_ctx *c, int32_t *sm_count, int64_t *l2_by
   if (total_mem_bytes) *total_mem_bytes = c->total_mem;
   return DFB_OK;
 }
+
+DFB_API dfb_status dfb_host_register(dfb_ctx *c, void *host, uint64_t bytes) {
+  DFB_REQUIRE(c && host, "dfb_host_register: NULL argument");
+  DFB_CUDA(cudaSetDevice(c->device));
+  DFB_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
+  return DFB_OK;
+}
+DFB_API dfb_status dfb_host_unregister(dfb_ctx *c, void *host) {
+  DFB_REQUIRE(c && host, "dfb_host_unregister: NULL argument");
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  DFB_CUDA(cudaHostUnregister(host));
+  return DFB_OK;
+}
+
+// fold finished event pairs into the running totals (synchronises the stream)
+static dfb_status prof_collect(dfb_ctx *c) {
+  if (c->prof_used == 0) return DFB_OK;
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    float ms = 0.f;
+    DFB_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+    c->prof_ms += ms;
+    c->prof_count += 1;
+  }
+  c->prof_used = 0;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_profile_spmv(dfb_ctx *c, double *total_ms, uint64_t *count, int32_t reset) {
+  DFB_REQUIRE(c, "dfb_profile_spmv: ctx is NULL");
+  DFB_TRY(prof_collect(c));
+  if (total_ms) *total_ms = c->prof_ms;
+  if (count) *count = c->prof_count;
+  if (reset) {
+    c->prof_ms = 0.0;
+    c->prof_count = 0;
+  }
+  return DFB_OK;
+}
+
+// called by the solvers around an SpMV launch; returns false when the per-solve budget of event pairs is used up
+bool dfb_prof_begin(dfb_ctx *c) {
+  if (!c->profile_spmv) return false;
+  if (c->prof_used + 2 > 32768) return false;
+  while (c->prof_ev.size() < c->prof_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return false;
+    c->prof_ev.push_back(e);
+  }
+  cudaEventRecord(c->prof_ev[c->prof_used], c->stream);
+  return true;
+}
+void dfb_prof_end(dfb_ctx *c) {
+  cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream);
+  c->prof_used += 2;
+}
+dfb_status dfb_prof_flush(dfb_ctx *c) { return prof_collect(c); }
 
 DFB_API dfb_status dfb_malloc(dfb_ctx *c, uint64_t bytes, void **dev_ptr) {
   DFB_REQUIRE(c && dev_ptr, "dfb_malloc: NULL argument");

@@ -92,6 +92,12 @@ struct dfb_ctx {
   int64_t use_graph = 0;
   int64_t assemble_variant = 0;
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
+  int64_t profile_spmv = 0;
+  // SpMV profiling (events on the launching stream)
+  std::vector<cudaEvent_t> prof_ev;   // pairs
+  size_t prof_used = 0;
+  double prof_ms = 0.0;
+  uint64_t prof_count = 0;
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -104,6 +110,13 @@ struct dfb_vec {
   double *d;
   uint64_t len() const { return n_blk * (uint64_t)blk_dim; }          // owned scalars
   uint64_t len_all() const { return (n_blk + n_ghost) * (uint64_t)blk_dim; }
+};
+
+struct dfb_bcflag {
+  dfb_ctx *ctx;
+  uint64_t n_blk_all;
+  int blk_dim;
+  int32_t *d;
 };
 
 struct dfb_mesh {

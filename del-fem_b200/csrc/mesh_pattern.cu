@@ -155,6 +155,37 @@ DFB_API dfb_status dfb_mesh_create_kuhn(dfb_ctx *ctx, uint64_t nx, uint64_t ny, 
   return DFB_OK;
 }
 
+__global__ void k_rotate_ids(uint32_t *__restrict__ e2v, uint64_t n_entries, uint32_t shift, uint32_t nv) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_entries; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = e2v[q];
+    e2v[q] = (v >= shift) ? (v - shift) : (v + nv - shift);
+  }
+}
+__global__ void k_rotate_xyz(const double *__restrict__ in, double *__restrict__ out, uint64_t nv, int ndim, uint64_t shift) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nv * ndim; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t v = q / ndim;
+    const int d = (int)(q - v * ndim);
+    const uint64_t nvn = (v >= shift) ? (v - shift) : (v + nv - shift);
+    out[nvn * ndim + d] = in[q];
+  }
+}
+
+DFB_API dfb_status dfb_mesh_rotate_vertex_ids(dfb_mesh *m, uint64_t shift) {
+  DFB_REQUIRE(m, "dfb_mesh_rotate_vertex_ids: NULL argument");
+  DFB_REQUIRE(shift <= m->num_vtx, "dfb_mesh_rotate_vertex_ids: shift > num_vtx");
+  if (shift == 0 || shift == m->num_vtx) return DFB_OK;
+  dfb_ctx *c = m->ctx;
+  double *d_new = nullptr;
+  DFB_TRY(dfb_dev_alloc_t(&d_new, m->num_vtx * m->ndim + 4));
+  DFB_LAUNCH(c, k_rotate_ids, c->sm_count * 8, 256, 0, m->d_elem2vtx, m->num_elem * m->num_node, (uint32_t)shift, (uint32_t)m->num_vtx);
+  DFB_LAUNCH(c, k_rotate_xyz, c->sm_count * 8, 256, 0, m->d_xyz, d_new, m->num_vtx, m->ndim, shift);
+  DFB_CHECK_LAUNCH();
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(m->d_xyz);
+  m->d_xyz = d_new;
+  return DFB_OK;
+}
+
 DFB_API dfb_status dfb_mesh_destroy(dfb_mesh *m) {
   if (!m) return DFB_OK;
   cudaStreamSynchronize(m->ctx->stream);

@@ -17,6 +17,9 @@
 #include "reduce.cuh"
 
 dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity);
+bool dfb_prof_begin(dfb_ctx *c);
+void dfb_prof_end(dfb_ctx *c);
+dfb_status dfb_prof_flush(dfb_ctx *c);
 
 // ------------------------------------------------------------------------------------------------ preconditioner
 template <int N>
@@ -379,7 +382,9 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     const uint64_t todo = (max_it - enq < chunk) ? (max_it - enq) : chunk;
     for (uint64_t j = 0; j < todo; ++j) {
       const int parity = (int)((enq + j) & 1);
+      const bool prof = dfb_prof_begin(c);
       DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity));
+      if (prof) dfb_prof_end(c);
       if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
 #define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2)
       DISPATCH_ALL(UPD)
@@ -413,6 +418,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     const int slot = (n_chunks - 1) & 1;
     last = hf[slot];
   }
+  DFB_TRY(dfb_prof_flush(c));
   if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
 
   // history: the device stored ||r_k||^2 for k = 0..iter

@@ -173,6 +173,47 @@ DFB_API dfb_status dfb_vec_set_fixed_dof_zero(dfb_vec *rhs, const int32_t *flag_
   return DFB_OK;
 }
 
+DFB_API dfb_status dfb_bcflag_create(dfb_ctx *ctx, const int32_t *flag_host, uint64_t n_blk_all, int32_t blk_dim, dfb_bcflag **out) {
+  DFB_REQUIRE(ctx && flag_host && out, "dfb_bcflag_create: NULL argument");
+  DFB_REQUIRE(blk_dim >= 1 && blk_dim <= 4, "dfb_bcflag_create: blk_dim %d not in 1..4", blk_dim);
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  dfb_bcflag *f = new dfb_bcflag();
+  f->ctx = ctx;
+  f->n_blk_all = n_blk_all;
+  f->blk_dim = blk_dim;
+  f->d = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&f->d, n_blk_all * blk_dim + 4);
+  if (st == DFB_OK) {
+    cudaError_t e = cudaMemcpyAsync(f->d, flag_host, n_blk_all * blk_dim * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_bcflag_create: %s", cudaGetErrorString(e));
+  }
+  if (st != DFB_OK) {
+    cudaFree(f->d);
+    delete f;
+    return st;
+  }
+  *out = f;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bcflag_destroy(dfb_bcflag *f) {
+  if (!f) return DFB_OK;
+  cudaStreamSynchronize(f->ctx->stream);
+  cudaFree(f->d);
+  delete f;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_vec_set_fixed_dof_zero_dev(dfb_vec *rhs, const dfb_bcflag *f) {
+  DFB_REQUIRE(rhs && f, "dfb_vec_set_fixed_dof_zero_dev: NULL argument");
+  DFB_REQUIRE(f->blk_dim == rhs->blk_dim && f->n_blk_all >= rhs->n_blk, "dfb_vec_set_fixed_dof_zero_dev: flag shape mismatch");
+  dfb_ctx *c = rhs->ctx;
+  DFB_LAUNCH(c, k_zero_flagged, stream_grid(c, rhs->len(), 4, 256), 256, 0, rhs->d, f->d, rhs->len());
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 // ---- synthetic fill (bit-identical to oracle orc_splitmix_fill)
 __global__ void k_fill_splitmix(double *v, uint64_t n, uint64_t seed, uint64_t first, double lo, double hi) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {

@@ -64,6 +64,10 @@ class Matrix:
             raise DfbError(1, "set_fixed_dof: assert_eq!(bc_flag.len(), row2val.len())")
         check(lib().dfb_bsr_set_fixed_dof(self.h, float(val_dia), _ptr(f)))
 
+    def set_fixed_dof_dev(self, val_dia, flag):
+        """set_fixed_dof with device-resident flags (core.BcFlag): no host traffic"""
+        check(lib().dfb_bsr_set_fixed_dof_dev(self.h, float(val_dia), flag.h))
+
     def mult_vec(self, y_vec: Vec, beta, alpha, x_vec: Vec):
         """Matrix::mult_vec: y <- alpha*A*x + beta*y (:143-171)"""
         check(lib().dfb_bsr_mult_vec(self.h, y_vec.h, float(beta), float(alpha), x_vec.h))

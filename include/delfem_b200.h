@@ -47,6 +47,7 @@ typedef struct dfb_bsr dfb_bsr;
 typedef struct dfb_plan dfb_plan;
 typedef struct dfb_precond dfb_precond;
 typedef struct dfb_halo dfb_halo;
+typedef struct dfb_bcflag dfb_bcflag;
 
 /* element kinds (kernel = reference function it batches) */
 enum {
@@ -84,6 +85,12 @@ dfb_status dfb_timer_start(dfb_ctx *ctx);
 dfb_status dfb_timer_stop(dfb_ctx *ctx, float *elapsed_ms); /* records, synchronises, returns elapsed */
 dfb_status dfb_flush_l2(dfb_ctx *ctx);                      /* overwrites a buffer larger than L2 */
 dfb_status dfb_device_info(dfb_ctx *ctx, int32_t *sm_count, int64_t *l2_bytes, int64_t *total_mem_bytes);
+/* page-lock a caller-owned host buffer so that the uploads/downloads that borrow it are true asynchronous DMA */
+dfb_status dfb_host_register(dfb_ctx *ctx, void *host, uint64_t bytes);
+dfb_status dfb_host_unregister(dfb_ctx *ctx, void *host);
+/* with option "profile_spmv" = 1 the solvers bracket every SpMV launch (first 16384 per solve) with CUDA events on the
+   launching stream; this returns the accumulated device time and launch count since the last reset */
+dfb_status dfb_profile_spmv(dfb_ctx *ctx, double *total_ms, uint64_t *count, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------ vectors
  * `[[T;N]]` slices of the reference (del-fem-cpu/src/slice_of_array.rs:1-47). n_blk rows are "owned"; n_ghost extra
@@ -102,6 +109,10 @@ dfb_status dfb_vec_set_fixed_dof_zero(dfb_vec *rhs, const int32_t *blk2isfix_hos
 /* out[i] = lo + (hi-lo)*splitmix64(seed, first_idx + i) — synthetic inputs for benches, bit-identical to the oracle's */
 dfb_status dfb_vec_fill_splitmix(dfb_vec *v, uint64_t seed, uint64_t first_idx, double lo, double hi);
 double *dfb_vec_device_ptr(dfb_vec *v);
+/* device-resident Dirichlet flags `&[[i32; N]]` (0 = free), so that per-step BC application needs no host traffic */
+dfb_status dfb_bcflag_create(dfb_ctx *ctx, const int32_t *blk2isfix_host, uint64_t n_blk_all, int32_t blk_dim, dfb_bcflag **out);
+dfb_status dfb_bcflag_destroy(dfb_bcflag *f);
+dfb_status dfb_vec_set_fixed_dof_zero_dev(dfb_vec *rhs, const dfb_bcflag *f);
 
 /* ------------------------------------------------------------------------------------------------ mesh
  * device-resident `elem2vtx` (uniform mesh, num_node per element) + `vtx2xyz` — the arguments of the reference's
@@ -114,6 +125,9 @@ dfb_status dfb_mesh_create_u32(dfb_ctx *ctx, const uint32_t *elem2vtx, uint64_t 
    nx*ny*nz grid, spacing h; vertex ids are local: i + nx*(j + ny*(k-k_begin)). */
 dfb_status dfb_mesh_create_kuhn(dfb_ctx *ctx, uint64_t nx, uint64_t ny, uint64_t nz, double h, uint64_t k_begin,
                                 uint64_t k_end, dfb_mesh **out);
+/* renumber vertices: new_id = (id - shift) mod num_vtx (elem2vtx and vtx2xyz are permuted consistently). Used by the
+   slab partition to move a leading ghost plane behind the owned vertices. */
+dfb_status dfb_mesh_rotate_vertex_ids(dfb_mesh *m, uint64_t shift);
 dfb_status dfb_mesh_destroy(dfb_mesh *m);
 dfb_status dfb_mesh_update_xyz(dfb_mesh *m, const double *vtx2xyz);
 dfb_status dfb_mesh_sizes(const dfb_mesh *m, uint64_t *num_elem, int32_t *num_node, uint64_t *num_vtx, int32_t *ndim);
@@ -144,6 +158,7 @@ dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2v
 dfb_status dfb_bsr_download(const dfb_bsr *m, double *row2val, double *idx2val);
 /* Matrix::set_fixed_dof / set_fixed_bc  :129 / :3-55 */
 dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *blk2isfix_host /* (n_blk+n_ghost)*N */);
+dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcflag *f);
 /* Matrix::mult_vec  y <- alpha*A*x + beta*y   :143-171 / MatrixRef::mult_vec :419-447 */
 dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, dfb_vec *x);
 /* row2val[i][d + N d] += scale * v[i][d]  — inertia / damping on the diagonal (rod3_darboux.rs:1219-1226) */
