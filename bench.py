@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--workload", default="S10", help="S1 | S10 | S50 | <vertices per edge>")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "block_jacobi"])
-    ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "2")))
+    ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "4")))
     ap.add_argument("--iters-per-sync", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -515,8 +515,199 @@ __global__ void __launch_bounds__(160) k_spmv_tile(const SpmvArgs a) {
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
+// ---- variants 3/4/5: LPR lanes per row, tiles of 32/LPR rows, two-stage TMA ring per warp.
+// While a warp computes tile i out of one buffer, the bulk copies of tile i+1 are already in flight into the other; the
+// row's blocks are split over LPR lanes (one gather round instead of ~14 dependent ones) and summed with shuffles.
+template <int N, int LPR>
+struct RingSmem {
+  static constexpr int NN = N * N;
+  static constexpr int RPT = 32 / LPR;   // rows per tile
+  static constexpr int CAP = RPT * 16;   // blocks per tile held in shared memory (longer tiles take the direct path)
+  static constexpr int VAL_BYTES = ((CAP * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int COL_BYTES = ((CAP * 4 + 16 + 15) / 16) * 16;
+  static constexpr int DIA_BYTES = ((RPT * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES;
+  static constexpr int WARP_BYTES = 2 * BUF_BYTES + 32;  // + two mbarriers
+  static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
+  static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);  // warps per CTA (one CTA per SM)
+};
+
+// one row (or its share) of the ring kernel; vals/cols/dia point to the staged tile (shared) or to global memory
+template <int N, int LPR>
+__device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const uint32_t *cols, const double *dia,
+                                           uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub) {
+  constexpr int NN = N * N;
+  double s[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) s[q] = 0.0;
+  // this lane's share of the row: blocks kb+sub, kb+sub+LPR, ... four at a time (index loads, then gathers, then FMAs)
+  for (uint32_t k = kb + sub; k < ke; k += 4 * LPR) {
+    uint32_t c[4];
+    double xv[4][N];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t kk = k + u * LPR;
+      c[u] = (kk < ke) ? cols[kk] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], a.x, c[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c[u] != 0xFFFFFFFFu) block_times_vec<N>(s, vals + (uint64_t)(k + u * LPR) * NN, xv[u]);
+    }
+  }
+  // diagonal block: lane `sub` contributes column `sub` (, sub+LPR, ...)
+  if (valid && dia) {
+    for (int cc = sub; cc < N; cc += LPR) {
+      const double xo = __ldg(a.x + (uint64_t)r * N + cc);
+#pragma unroll
+      for (int q = 0; q < N; ++q) s[q] += dia[q + N * cc] * xo;
+    }
+  }
+#pragma unroll
+  for (int off = 1; off < LPR; off <<= 1) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], off);
+  }
+  double d = 0.0;
+  if (valid && sub == 0) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double yv = a.alpha * s[q];
+      if (a.beta != 0.0) yv += a.beta * a.y[(uint64_t)r * N + q];
+      a.y[(uint64_t)r * N + q] = yv;
+      d += __ldg(a.x + (uint64_t)r * N + q) * yv;
+    }
+  }
+  return d;
+}
+
+template <int N, int LPR>
+__global__ void __launch_bounds__(RingSmem<N, LPR>::WARPS * 32) k_spmv_ring(const SpmvArgs a) {
+  using S = RingSmem<N, LPR>;
+  constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
+
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned sub = lane % LPR, rl = lane / LPR;
+  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
+  const uint32_t bar0 = smem_u32(wbase + 2 * S::BUF_BYTES);
+  const unsigned long long pol = policy_evict_first();
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint32_t n_rows = a.row_end - a.row_begin;
+  const uint32_t n_tiles = (n_rows + RPT - 1) / RPT;
+  const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
+
+  // lane 0 issues the three bulk copies of tile t into buffer b (nothing for oversized tiles)
+  auto issue = [&](uint32_t t, uint32_t b) {
+    if (lane != 0) return;
+    const uint32_t r0 = a.row_begin + t * RPT;
+    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
+    const uint32_t nb = k1 - k0;
+    if (nb > (uint32_t)CAP) return;
+    unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+    const uint32_t bar = bar0 + 8 * b;
+    const double *g_val = a.idx2val + (uint64_t)k0 * NN;
+    const uint32_t *g_col = a.idx2col + k0;
+    const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
+    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u;
+    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+    uint32_t dummy = 0;
+    stage_bulk(smem_u32(buf), g_val, vb, bar, pol, &dummy);
+    stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
+    if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
+  };
+
+  if (wg < n_tiles) issue(wg, 0);
+  if (wg + ws < n_tiles) issue(wg + ws, 1);
+  uint32_t phase0 = 0u, phase1 = 0u;
+  double dot = 0.0;
+  uint32_t it = 0;
+  for (uint32_t t = wg; t < n_tiles; t += ws, ++it) {
+    const uint32_t b = it & 1u;
+    const uint32_t r0 = a.row_begin + t * RPT;
+    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
+    const uint32_t nb = k1 - k0;
+    const uint32_t r = r0 + rl;
+    const bool valid = r < r1;
+    const uint32_t kb = valid ? a.row2idx[r] : k0;
+    const uint32_t ke = valid ? a.row2idx[r + 1] : k0;
+    const bool staged = nb <= (uint32_t)CAP;
+    if (staged) {
+      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+      const uint32_t bar = bar0 + 8 * b;
+      const uint32_t ph = b ? phase1 : phase0;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "RING_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra RING_DONE;\n"
+          "bra RING_WAIT;\n"
+          "RING_DONE:\n"
+          "}\n" ::"r"(bar),
+          "r"(ph)
+          : "memory");
+      if (b) phase1 ^= 1u;
+      else phase0 ^= 1u;
+      const double *g_val = a.idx2val + (uint64_t)k0 * NN;
+      const uint32_t *g_col = a.idx2col + k0;
+      const double *sv = reinterpret_cast<const double *>(buf + ((uintptr_t)g_val & 15));
+      const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15));
+      const double *sd = nullptr;
+      if (a.row2val) {
+        const double *g_dia = a.row2val + (uint64_t)r0 * NN;
+        sd = reinterpret_cast<const double *>(buf + S::VAL_BYTES + S::COL_BYTES + ((uintptr_t)g_dia & 15)) + rl * NN;
+      }
+      dot += ring_row<N, LPR>(a, sv, sc, sd, kb - k0, ke - k0, r, valid, sub);
+    } else {
+      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, a.row2val ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub);
+    }
+    __syncwarp();  // every lane is done with buffer b
+    const uint32_t t2 = t + 2 * ws;
+    if (t2 < n_tiles) issue(t2, b);
+  }
+  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
+}
+
+template <int N, int LPR>
+static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
+  using S = RingSmem<N, LPR>;
+  const int warps = S::WARPS;
+  const size_t smem = (size_t)warps * S::WARP_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_ring<N, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const uint64_t n_rows = a.row_end - a.row_begin;
+  const uint64_t n_tiles = (n_rows + S::RPT - 1) / S::RPT;
+  uint64_t g = (n_tiles + warps - 1) / warps;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
+  DFB_LAUNCH_ON(c, strm, (k_spmv_ring<N, LPR>), (unsigned)g, warps * 32, smem, a);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 template <int N>
 static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
+  if (c->spmv_variant == 3) return spmv_launch_ring<N, 2>(c, a, strm);
+  if (c->spmv_variant == 4) return spmv_launch_ring<N, 4>(c, a, strm);
+  if (c->spmv_variant == 5) return spmv_launch_ring<N, 8>(c, a, strm);
   const uint64_t n_rows = a.row_end - a.row_begin;
   if (n_rows == 0 && !a.fuse_dot) return DFB_OK;
   int variant = (int)c->spmv_variant;

@@ -87,7 +87,7 @@ struct dfb_ctx {
   void *flush_buf = nullptr;
   size_t flush_bytes = 0;
   // options
-  int64_t spmv_variant = 1;
+  int64_t spmv_variant = 4;
   int64_t iters_per_sync = 16;
   int64_t use_graph = 0;
   int64_t assemble_variant = 0;
