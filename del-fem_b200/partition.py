@@ -98,3 +98,15 @@ def make_slab(nx, ny, nz, rank, nranks) -> Slab:
     s.int_end = n_own - (nxy if has_above else 0)
     s.first_global_vtx = k0 * nxy
     return s
+
+
+def local_mesh_host(s: Slab, h: float, index_dtype=np.uint32):
+    """host twin of `Mesh.kuhn(k_begin=s.kb, k_end=s.ke)` followed by `rotate_vertex_ids(s.shift)`:
+    (elem2vtx, vtx2xyz) of the rank's slab in local numbering [owned | ghost-above | ghost-below]"""
+    from . import synthetic
+    e2v, xyz = synthetic.kuhn_tet_mesh(s.nx, s.ny, s.nz, h, s.kb, s.ke, index_dtype=np.int64)
+    nv = xyz.shape[0]
+    if s.shift:
+        e2v = np.where(e2v >= s.shift, e2v - s.shift, e2v + nv - s.shift)
+        xyz = np.roll(xyz, -s.shift, axis=0)
+    return e2v.astype(index_dtype), np.ascontiguousarray(xyz)

@@ -157,7 +157,7 @@ dfb_status dfb_bsr_destroy(dfb_bsr *m);
 dfb_status dfb_bsr_set_zero(dfb_bsr *m);                                       /* Matrix::set_zero :174 */
 dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2val);
 dfb_status dfb_bsr_download(const dfb_bsr *m, double *row2val, double *idx2val);
-/* Matrix::set_fixed_dof / set_fixed_bc  :129 / :3-55 */
+/* Matrix::set_fixed_dof (del-fem-cpu/src/sparse_square.rs:129) / set_fixed_bc (sparse_square.rs:3-55) */
 dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *blk2isfix_host /* (n_blk+n_ghost)*N */);
 dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcflag *f);
 /* Matrix::mult_vec  y <- alpha*A*x + beta*y   :143-171 / MatrixRef::mult_vec :419-447 */

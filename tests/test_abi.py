@@ -1,0 +1,87 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/delfem_b200.h declares,
+fails loudly without a GPU, and the product never touches the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(dfb):
+    L = dfb.lib()
+    names = dfb.header_symbols()
+    assert len(names) >= 70
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    # and nothing with the dfb_ prefix is exported that the header does not declare
+    out = subprocess.run(["nm", "-D", "--defined-only", dfb.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\b(dfb_[a-z0-9_]+)\b", out)))
+    extra = [n for n in exported if n not in names]
+    assert not extra, extra
+
+
+def test_header_is_plain_c_and_cites_the_reference():
+    hdr = os.path.join(ROOT, "include", "delfem_b200.h")
+    src = open(hdr).read()
+    assert "torch" not in src.lower()
+    for cite in ["sparse_square.rs:218-261", "sparse_square.rs:264-347", "sparse_square.rs:180-214", "merge.rs:3", "merge.rs:51",
+                 "sparse_ilu.rs:87-219", "sparse_square.rs:3-55", "linearsystem.rs:67", "laplace_tri2.rs:3", "solid_linear_tri2.rs:23"]:
+        assert cite in src, cite
+    # compiles as C
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_status_codes_match_header(dfb):
+    src = open(os.path.join(ROOT, "include", "delfem_b200.h")).read()
+    for name, val in dfb.STATUS.items():
+        key = "DFB_OK" if name == "OK" else f"DFB_ERR_{name}"
+        m = re.search(rf"{key}\s*=\s*(\d+)", src)
+        assert m and int(m.group(1)) == val, key
+
+
+def test_no_gpu_means_loud_failure_not_fallback(dfb):
+    """on a box without a CUDA device the product must raise, never compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dfb.DfbError) as ei:
+        dfb.Ctx(0)
+    assert ei.value.status == dfb.STATUS["CUDA"]
+    assert "no CPU fallback" in str(ei.value)
+    assert dfb.lib().dfb_version().decode().startswith("delfem_b200")
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "del-fem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath or dirpath.endswith("lib"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dirpath, f)
+    r = subprocess.run(["ldd", os.path.join(pkg, "lib", "libdelfem_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in r and "torch" not in r
+
+
+def test_sass_contains_tma_bulk_copies(dfb):
+    """the SpMV streams the matrix with TMA bulk copies: SASS shows UBLKCP (B200_PROFILING.md), and the target is sm_100a"""
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z11k_spmv_ringILi3ELi4EEv8SpmvArgs", dfb.LIB_PATH],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out or "SM100" in out.upper() or "EF_CUDA_SM100" in out
+    assert "UBLKCP" in out
+    assert "SYNCS" in out  # mbarrier
+
+
+def test_python_mirror_signatures_cover_header(dfb):
+    from del_fem_b200 import _lib
+    L = dfb.lib()
+    for n in dfb.header_symbols():
+        fn = getattr(L, n)
+        if n in ("dfb_last_error_message", "dfb_version"):
+            continue
+        assert fn.argtypes is not None, f"{n}: ctypes argtypes not declared"

@@ -1,0 +1,388 @@
+"""CPU tests that PIN the oracle: the reference's own property tests / golden constants re-run against the C++
+restatement.  No GPU needed.  Where the reference has nothing to pin a kernel (tet, neo-Hookean, Jacobi:
+none exist upstream) the mathematical properties of SURVEY appendix B are the definition ("parity unpinned")."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_constants.json")))
+
+
+def csr_from_csrdia(r2i, i2c, rv, iv, n):
+    """scipy matrix of a convention-0 (off-diagonal CSR + separate diagonal) block matrix, blocks column-major"""
+    nb = r2i.size - 1
+    blocks = iv.reshape(-1, n, n).transpose(0, 2, 1)
+    A = sp.bsr_matrix((blocks, i2c.astype(np.int64), r2i.astype(np.int64)), shape=(n * nb, n * nb)).tocsr()
+    D = sp.block_diag([sp.csr_matrix(b.reshape(n, n).T) for b in rv], format="csr")
+    return (A + D).tocsr()
+
+
+# ---------------------------------------------------------------------------------- del-fem-ls smoke pattern
+def test_ls_smoke_pattern(orc):
+    g = GOLD["ls_smoke_pattern"]
+    r2i, i2c = np.array(g["row2idx"], dtype=np.uint64), np.array(g["idx2col"], dtype=np.uint64)
+    rv, iv = np.zeros((4, 1)), np.zeros((10, 1))
+    emat = np.array([1.0, 0.0, 0.0, 1.0]).reshape(2, 2, 1)
+    orc.merge_for_array_blk(emat, np.array([0, 1]), r2i, i2c, rv, iv, flavour=1)
+    assert rv[:, 0].tolist() == [1.0, 1.0, 0.0, 0.0]
+    assert np.all(iv == 0.0)  # the explicit diagonal slots stay zero: the vertex-id test routes them to row2val
+    lhs, rhs = np.zeros((4, 1)), np.zeros((4, 1))
+    orc.mult_vec(lhs, 1.0, 1.0, rhs, r2i, i2c, iv, rv)
+    assert np.all(lhs == 0.0)
+    # blkcsr on the same pattern (diagonal inside the pattern)
+    iv2 = np.zeros((10, 1))
+    orc.merge_blkcsr(np.array([0, 1]), np.array([0, 1]), emat, r2i, i2c, iv2)
+    assert iv2[:, 0].tolist() == [1.0, 0, 0, 1.0, 0, 0, 0, 0, 0, 0]
+
+
+def test_merge_panics_like_the_reference(orc):
+    g = GOLD["ls_smoke_pattern"]
+    r2i, i2c = np.array(g["row2idx"], dtype=np.uint64), np.array(g["idx2col"], dtype=np.uint64)
+    rv, iv = np.zeros((4, 1)), np.zeros((10, 1))
+    with pytest.raises(orc.OraclePanic):  # (0,3) is not in the pattern: assert_ne!(idx0, usize::MAX)
+        orc.merge_for_array_blk(np.ones((2, 2, 1)), np.array([0, 3]), r2i, i2c, rv, iv)
+    with pytest.raises(orc.OraclePanic):  # row out of range: assert!(i_row < num_blk)
+        orc.merge_csrdia(np.array([0, 9]), np.array([0, 9]), np.ones((2, 2, 1)), r2i, i2c, rv.reshape(-1), iv.reshape(-1))
+
+
+# ---------------------------------------------------------------------------------- solid_linear_tri2 end-to-end test
+def unit_square_problem(orc):
+    g = GOLD["tri2_solid_test"]
+    n = int(round(1.0 / g["edge"]))  # structured stand-in for meshing_from_polyloop2(edge 0.07)
+    t2v, xy = orc.grid_tri_mesh(n, disk=False)
+    xy = 0.5 * (xy + 1.0)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble("solid_linear_tri2", 0, t2v, xy, g["lambda"], g["myu"], r2i, i2c)
+    flag = np.zeros((nv, 2), dtype=np.int32)
+    flag[xy[:, 1] < g["fixed_if_y_below"]] = 1
+    u = orc.splitmix_fill(0, 0, 2 * nv, -g["perturbation"], g["perturbation"]).reshape(nv, 2)
+    u[flag != 0] = 0.0
+    return dict(t2v=t2v, xy=xy, nv=nv, r2i=r2i, i2c=i2c, rv=rv, iv=iv, flag=flag, u=u, g=g)
+
+
+def element_energy(orc, t2v, xy, u, lam, mu):
+    eng = 0.0
+    for tri in t2v.astype(np.int64):
+        emat = orc.emat_tri2(lam, mu, *xy[tri]).reshape(3, 3, 2, 2).transpose(0, 1, 3, 2)  # [i][j][a][b]
+        ue = u[tri]
+        e = 0.5 * np.einsum("ia,ijab,jb->", ue, emat, ue)
+        assert e >= -1e-10  # solid_linear_tri2.rs:74
+        eng += e
+    return eng
+
+
+def test_energy_identity(orc):
+    """solid_linear_tri2.rs:164-176: 0.5 u^T A u == sum of element energies (pins merge + mult_vec)"""
+    p = unit_square_problem(orc)
+    au = np.zeros_like(p["u"])
+    orc.mult_vec(au, 0.0, 1.0, p["u"], p["r2i"], p["i2c"], p["iv"], p["rv"])
+    pap = 0.5 * orc.dot(p["u"], au)
+    eng = element_energy(orc, p["t2v"], p["xy"], p["u"], p["g"]["lambda"], p["g"]["myu"])
+    assert abs(pap - eng) < p["g"]["bounds"]["energy_identity_abs"]
+
+
+def test_solver_quality_bounds(orc):
+    """solid_linear_tri2.rs:306-326: CG < 80 its, ILU0-PCG < 36, full-LU PCG history length == 2, dense LU solves"""
+    p = unit_square_problem(orc)
+    g, b = p["g"], p["g"]["bounds"]
+    r2i, i2c, nv = p["r2i"], p["i2c"], p["nv"]
+    rhs = np.zeros_like(p["u"])
+    orc.mult_vec(rhs, 0.0, -1.0, p["u"], r2i, i2c, p["iv"], p["rv"])  # r = -K u  (per-element accumulation upstream)
+    orc.set_fix_dof_to_rhs_vector(rhs, p["flag"])
+    rv, iv = p["rv"].copy(), p["iv"].copy()
+    orc.set_fixed_bc(1.0, p["flag"], rv, iv, r2i, i2c)
+
+    def check(u_sol):
+        r1 = np.zeros_like(u_sol)
+        orc.mult_vec(r1, 0.0, 1.0, u_sol, r2i, i2c, iv, rv)
+        res = np.max(np.linalg.norm(rhs - r1, axis=1))
+        eng = element_energy(orc, p["t2v"], p["xy"], p["u"] + u_sol, g["lambda"], g["myu"])
+        return res, eng
+
+    # CG. The reference asserts "< 80 iterations" on ITS mesh (third-party Delaunay mesher, ChaCha perturbation): neither is
+    # reproducible here and a right-triangle grid is worse conditioned, so that bound is not transferable. What IS pinned:
+    # the oracle's CG is iteration-for-iteration a textbook CG on the same matrix (independent numpy implementation).
+    K = csr_from_csrdia(r2i, i2c, rv, iv, 2)
+    bvec = rhs.reshape(-1)
+    xk, rk = np.zeros_like(bvec), bvec.copy()
+    pk, rr = rk.copy(), rk @ rk
+    rr0, ratios = rr, []
+    for _ in range(300):
+        Ap = K @ pk
+        al = rr / (pk @ Ap)
+        xk += al * pk
+        rk -= al * Ap
+        rn = rk @ rk
+        ratios.append(np.sqrt(rn / rr0))
+        if ratios[-1] < g["cg_tol"]:
+            break
+        pk = rk + (rn / rr) * pk
+        rr = rn
+    r = rhs.copy()
+    u, ap, pp = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    hist = orc.conjugate_gradient(r, u, ap, pp, g["cg_tol"], 300, r2i, i2c, iv, rv)
+    assert abs(len(hist) - len(ratios)) <= 1
+    assert np.allclose(hist[:60], ratios[:60], rtol=1e-6)
+    res, eng = check(u)
+    assert res < b["cg_res_lt"] and eng < 10 * b["cg_energy_lt"], (res, eng, len(hist))
+    r = rhs.copy()  # reference call: tol 1e-5, max 100 -> history is capped at 100 entries
+    hist = orc.conjugate_gradient(r, np.zeros_like(r), np.zeros_like(r), np.zeros_like(r), g["cg_tol"], g["cg_max"], r2i, i2c, iv, rv)
+    assert len(hist) <= g["cg_max"]
+
+    ilu = orc.Ilu("ilu0", 2, r2i, i2c)
+    ilu.copy_value(r2i, i2c, iv, rv)
+    ilu.decompose()
+    r = rhs.copy()
+    x, pr, pp = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    hist = orc.preconditioned_conjugate_gradient(r, x, pr, pp, g["cg_tol"], g["cg_max"], r2i, i2c, iv, rv, ilu)
+    res, eng = check(x)
+    assert res < b["ilu0_res_lt"] and eng < 10 * b["ilu0_energy_lt"] and len(hist) < b["ilu0_iters_lt"], (res, eng, len(hist))
+
+    full = orc.Ilu("full", 2, r2i, i2c)
+    full.copy_value(r2i, i2c, iv, rv)
+    full.decompose()
+    r = rhs.copy()
+    x, pr, pp = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    hist = orc.preconditioned_conjugate_gradient(r, x, pr, pp, g["cg_tol"], g["cg_max"], r2i, i2c, iv, rv, full)
+    assert len(hist) == b["iluinf_hist_len"]
+    res, eng = check(x)
+    assert res < 1e-13 and eng < 1e-25
+    xd = rhs.copy()  # SolverType::DENSE: one application of the full LU
+    full.solve(xd)
+    res, eng = check(xd)
+    assert res < 1e-13 and eng < 1e-25
+    # scipy cross-check of the whole path
+    xs = spla.spsolve(K.tocsc(), rhs.reshape(-1)).reshape(nv, 2)
+    assert np.linalg.norm(xs - xd) / np.linalg.norm(xs) < 1e-10
+
+
+def test_pcg_history_semantics(orc):
+    """A11/A12: CG history = ratios without k=0; PCG = absolute norms with k=0 and a trailing entry at max_it"""
+    p = unit_square_problem(orc)
+    r2i, i2c = p["r2i"], p["i2c"]
+    rhs = np.zeros_like(p["u"])
+    orc.mult_vec(rhs, 0.0, -1.0, p["u"], r2i, i2c, p["iv"], p["rv"])
+    orc.set_fix_dof_to_rhs_vector(rhs, p["flag"])
+    rv, iv = p["rv"].copy(), p["iv"].copy()
+    orc.set_fixed_bc(1.0, p["flag"], rv, iv, r2i, i2c)
+    z = np.zeros_like(rhs)
+    assert len(orc.conjugate_gradient(z.copy(), z.copy(), z.copy(), z.copy(), 1e-5, 10, r2i, i2c, iv, rv)) == 0
+    jac = orc.Ilu("block_jacobi", 2, r2i, i2c)
+    jac.copy_value(r2i, i2c, iv, rv)
+    jac.decompose()
+    h = orc.preconditioned_conjugate_gradient(z.copy(), z.copy(), z.copy(), z.copy(), 1e-5, 10, r2i, i2c, iv, rv, jac)
+    assert len(h) == 1 and h[0] == 0.0
+    r = rhs.copy()
+    h = orc.preconditioned_conjugate_gradient(r, z.copy(), z.copy(), z.copy(), 1e-30, 7, r2i, i2c, iv, rv, jac)
+    assert len(h) == 9 and h[0] == np.sqrt(orc.dot(rhs, rhs)) and h[-1] == h[-2]
+    r = rhs.copy()
+    hc = orc.conjugate_gradient(r, z.copy(), z.copy(), z.copy(), 1e-30, 7, r2i, i2c, iv, rv)
+    assert len(hc) == 7 and hc[0] < 1.0 + 1e-12
+    # block-Jacobi == reference ILU code on an empty pattern: D^-1 applied blockwise
+    v = np.random.default_rng(0).standard_normal(rhs.shape)
+    w = v.copy()
+    jac.solve(w)
+    for i in range(0, p["nv"], 17):
+        assert np.allclose(w[i], np.linalg.solve(rv[i].reshape(2, 2).T, v[i]), rtol=1e-12)
+    pj = orc.Ilu("jacobi", 2, r2i, i2c)
+    pj.copy_value(r2i, i2c, iv, rv)
+    pj.decompose()
+    w = v.copy()
+    pj.solve(w)
+    assert np.allclose(w, v / rv[:, [0, 3]], rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------- Laplacian properties (tests/test_laplace.py:22-30)
+@pytest.mark.parametrize("kind", ["laplace_tri2", "cot_laplace_tri3"])
+def test_laplacian_properties(orc, kind):
+    t2v, xy = orc.grid_tri_mesh(12, disk=True)
+    if kind == "cot_laplace_tri3":
+        xy = np.ascontiguousarray(np.concatenate([xy, np.zeros((xy.shape[0], 1))], axis=1))
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble(kind, 0, t2v, xy, 1.0, 0.0, r2i, i2c)
+    L = csr_from_csrdia(r2i, i2c, rv, iv, 1)
+    assert abs(L - L.T).max() < 1e-10
+    assert np.abs(L @ np.ones(nv)).max() < 1e-10  # reference bound 1e-4 (f32)
+    # convention II (diagonal inside the pattern), as del_fem_numpy/LaplacianMatrix.py:8-20 builds it
+    r2, c2 = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, True)
+    _, iv2 = orc.assemble(kind, 1, t2v, xy, 1.0, 0.0, r2, c2)
+    L2 = sp.csr_matrix((iv2[:, 0], c2.astype(np.int64), r2.astype(np.int64)), shape=(nv, nv))
+    assert abs(L - L2).max() < 1e-13
+    # generalized eigenpair Rayleigh identity with a lumped mass matrix
+    area = np.zeros(nv)
+    for tri in t2v.astype(np.int64):
+        p = xy[tri][:, :2]
+        a = 0.5 * abs((p[1, 0] - p[0, 0]) * (p[2, 1] - p[0, 1]) - (p[2, 0] - p[0, 0]) * (p[1, 1] - p[0, 1]))
+        area[tri] += a / 3.0
+    M = sp.diags(area)
+    w, v = spla.eigsh(L.tocsc(), k=4, M=M.tocsc(), sigma=-0.1)
+    for k in range(4):
+        assert abs(v[:, k] @ (L @ v[:, k]) - w[k] * (v[:, k] @ (M @ v[:, k]))) < 1e-8
+    if kind == "laplace_tri2":  # planar mesh: the cotangent Laplacian equals the P1 Laplacian
+        _, ivc = orc.assemble("cot_laplace_tri3", 0, t2v, np.ascontiguousarray(np.concatenate([xy, np.zeros((nv, 1))], 1)), 0, 0, r2i, i2c)
+        assert np.abs(ivc - iv).max() < 1e-12
+
+
+# ---------------------------------------------------------------------------------- derived tet kernels
+def test_tet_kernel_properties(orc):
+    rng = np.random.default_rng(4)
+    for _ in range(10):
+        p = rng.standard_normal((4, 3))
+        if orc.tet_volume(*p) < 0:
+            p[[1, 2]] = p[[2, 1]]
+        vol = orc.tet_volume(*p)
+        assert abs(vol - np.linalg.det(p[1:] - p[0]) / 6.0) < 1e-14
+        lam, mu = 1.3, 0.7
+        E = orc.emat_tet(lam, mu, *p).reshape(4, 4, 3, 3).transpose(0, 1, 3, 2)  # [i][j][a][b]
+        assert np.allclose(E, E.transpose(1, 0, 3, 2), atol=1e-13)  # E_ij^T = E_ji
+        K = E.transpose(0, 2, 1, 3).reshape(12, 12)
+        for t in np.eye(3):  # rigid translations
+            assert np.abs(K @ np.tile(t, 4)).max() < 1e-12
+        w = rng.standard_normal(3)  # infinitesimal rotation
+        assert np.abs(K @ np.cross(w, p).reshape(-1)).max() < 1e-11
+        eps = rng.standard_normal((3, 3))
+        eps = 0.5 * (eps + eps.T)
+        u = (p @ eps.T).reshape(-1)  # uniform strain patch energy
+        assert abs(0.5 * u @ K @ u - vol * (0.5 * lam * np.trace(eps) ** 2 + mu * np.sum(eps * eps))) < 1e-11
+        assert np.linalg.eigvalsh(0.5 * (K + K.T)).min() > -1e-11
+        Lp = orc.laplace_tet_ddw(2.0, *p)[:, :, 0]
+        assert np.allclose(Lp, Lp.T, atol=1e-14) and np.abs(Lp.sum(axis=1)).max() < 1e-13
+        f = rng.standard_normal(3)  # exact for linear fields: x^T L x = alpha V |grad|^2
+        xlin = p @ f
+        assert abs(xlin @ Lp @ xlin - 2.0 * vol * (f @ f)) < 1e-11
+
+
+def test_kuhn_mesh_and_pattern(orc):
+    n = 7
+    e2v, xyz = orc.kuhn_tet_mesh(n)
+    assert e2v.shape[0] == 6 * (n - 1) ** 3
+    vols = np.array([orc.tet_volume(*xyz[t]) for t in e2v.astype(np.int64)])
+    assert vols.min() > 0 and abs(vols.sum() - 1.0) < 1e-12
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, n ** 3, False)
+    assert i2c.size == 2 * (3 * n * n * (n - 1) + 3 * n * (n - 1) ** 2 + (n - 1) ** 3)
+    assert np.diff(r2i.astype(np.int64)).max() == 14
+    # the per-row column SET is mesh adjacency (the order is first-seen: third-party, parity unpinned)
+    adj = [set() for _ in range(n ** 3)]
+    for t in e2v.astype(np.int64):
+        for a in t:
+            adj[a].update(int(b) for b in t if b != a)
+    for v in range(0, n ** 3, 13):
+        row = i2c[int(r2i[v]):int(r2i[v + 1])].astype(np.int64)
+        assert len(set(row)) == len(row) and set(row) == adj[v]
+    r2, c2 = orc.vtx2vtx_from_uniform_mesh(e2v, 4, n ** 3, True)
+    assert c2.size == i2c.size + n ** 3
+
+
+# ---------------------------------------------------------------------------------- neo-Hookean (FD protocol of the reference)
+def _tet_from_hex_constants():
+    X = np.array(GOLD["hex_node2xyz"]["value"])[[0, 1, 3, 4]]
+    U = np.array(GOLD["hex_node2disp"]["value"])[[0, 1, 3, 4]]
+    return X, U
+
+
+def test_neohookean_density_fd(orc):
+    g = GOLD["fd_eps_tol_density"]
+    ij = GOLD["istdim2ij"]["value"]
+    cv = np.array(GOLD["voigt_c"]["value"])
+
+    def tens(v):
+        return np.array([[v[0], v[3], v[5]], [v[3], v[1], v[4]], [v[5], v[4], v[2]]])  # dudx.rs:38-43
+
+    c0 = tens(cv)
+    w0, dw0, ddw0 = orc.wr_dwrdc_ddwrddc_neohookean(1.0, 10.0, c0)
+    for d in range(6):
+        c1 = c0.copy()
+        c1[ij[d][0], ij[d][1]] += g["eps"]
+        w1, _, _ = orc.wr_dwrdc_ddwrddc_neohookean(1.0, 10.0, c1)
+        assert abs((w1 - w0) / g["eps"] - dw0[d]) < 10 * g["tol_dw"]
+    for d in range(6):  # symmetrised derivative (solid_incompressive_hex.rs:70-82)
+        c1 = c0.copy()
+        c1[ij[d][0], ij[d][1]] += 0.5 * g["eps"]
+        c1[ij[d][1], ij[d][0]] += 0.5 * g["eps"]
+        _, dw1, _ = orc.wr_dwrdc_ddwrddc_neohookean(1.0, 10.0, c1)
+        assert np.abs((dw1 - dw0) / g["eps"] - ddw0[d]).max() < 20 * g["tol_ddw"]
+
+
+def test_neohookean_tet_fd_and_limits(orc):
+    g = GOLD["fd_eps_tol_hex"]
+    X, U = _tet_from_hex_constants()
+    if orc.tet_volume(*X) < 0:
+        X[[1, 2]], U[[1, 2]] = X[[2, 1]], U[[2, 1]]
+    mu, lam = 1.0, 10.0
+    w0, dw0, ddw0 = orc.neohookean_tet_wdwddw(mu, lam, X, U)
+    for i in range(4):
+        for a in range(3):
+            U1 = U.copy()
+            U1[i, a] += g["eps"]
+            w1, dw1, _ = orc.neohookean_tet_wdwddw(mu, lam, X, U1)
+            assert abs((w1 - w0) / g["eps"] - dw0[i, a]) < 20 * g["tol"]
+            num = (dw1 - dw0) / g["eps"]  # [j][b]
+            ana = ddw0[i].reshape(4, 3, 3)[:, a, :]  # ddw[i][j][a*3+b]
+            assert np.abs(num - ana).max() < 50 * g["tol"]
+    # zero state, and the Hessian at u = 0 is the linear-elastic tet matrix with the same (lambda, mu)
+    w, dw, ddw = orc.neohookean_tet_wdwddw(mu, lam, X, np.zeros((4, 3)))
+    assert abs(w) < 1e-14 and np.abs(dw).max() < 1e-13
+    lin = orc.emat_tet(lam, mu, *X).reshape(4, 4, 3, 3).transpose(0, 1, 3, 2).reshape(4, 4, 9)  # a + 3b -> a*3 + b
+    assert np.abs(ddw - lin).max() < 1e-12
+
+
+def test_spring3_fd(orc):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 3))
+    w0, dw0, ddw0 = orc.spring3_wdwddw(1.7, x, 0.8)
+    eps = 1e-6
+    for i in range(2):
+        for a in range(3):
+            x1 = x.copy()
+            x1[i, a] += eps
+            w1, dw1, _ = orc.spring3_wdwddw(1.7, x1, 0.8)
+            assert abs((w1 - w0) / eps - dw0[i, a]) < 1e-5
+            ana = ddw0[i].reshape(2, 3, 3)[:, :, a]  # column-major: entry (b,a) at b + 3a ; symmetric
+            assert np.abs((dw1 - dw0) / eps - ana).max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------- config 1: 2-D Poisson on the disk
+def test_config1_poisson_disk(orc):
+    t2v, xy = orc.grid_tri_mesh(100, disk=True)
+    nv = xy.shape[0]
+    assert nv == 10201 and t2v.shape[0] == 20000
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble("laplace_tri2", 0, t2v, xy, 1.0, 0.0, r2i, i2c)
+    idx = np.arange(nv)
+    i, j = idx % 101, idx // 101
+    flag = ((i == 0) | (i == 100) | (j == 0) | (j == 100)).astype(np.int32).reshape(nv, 1)
+    rhs = np.zeros((nv, 1))
+    for tri in t2v.astype(np.int64):  # lumped f = 1
+        p = xy[tri]
+        a = 0.5 * ((p[1, 0] - p[0, 0]) * (p[2, 1] - p[0, 1]) - (p[2, 0] - p[0, 0]) * (p[1, 1] - p[0, 1]))
+        rhs[tri, 0] += a / 3.0
+    orc.set_fix_dof_to_rhs_vector(rhs, flag)
+    orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+    r = rhs.copy()
+    u, ap, p = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    hist = orc.conjugate_gradient(r, u, ap, p, 1e-10, 2000, r2i, i2c, iv, rv)
+    assert hist[-1] < 1e-10
+    K = csr_from_csrdia(r2i, i2c, rv, iv, 1)
+    us = spla.spsolve(K.tocsc(), rhs[:, 0])
+    assert np.linalg.norm(u[:, 0] - us) / np.linalg.norm(us) < 1e-8
+    # -lap u = 1 on the unit disk, u = 0 on the boundary: u(0) = 1/4
+    assert abs(u[50 + 101 * 50, 0] - 0.25) < 2e-3
+
+
+def test_ls_mult_mat(orc):
+    """del-fem-ls mult_mat (sparse_square.rs:134-164): scalar matrix applied to interleaved components"""
+    t2v, xy = orc.grid_tri_mesh(6)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble("laplace_tri2", 0, t2v, xy, 1.0, 0.0, r2i, i2c)
+    x = np.random.default_rng(0).standard_normal((nv, 3))
+    y = np.ones((nv, 3))
+    orc.ls_mult_mat(y, 0.5, 2.0, x, r2i, i2c, iv.reshape(-1), rv.reshape(-1))
+    L = csr_from_csrdia(r2i, i2c, rv, iv, 1)
+    assert np.allclose(y, 0.5 + 2.0 * (L @ x), atol=1e-12)
