@@ -1,0 +1,54 @@
+"""Device-resident state of BASELINE config 2/5 (3-D linear-elastic Kuhn tet cube, z=0 clamped, rhs = -K u0) for one rank,
+and one pass of the hot path over it. Shared by bench.py and the multi-GPU tests."""
+from __future__ import annotations
+
+
+class Problem:
+    """device-resident state of one rank: mesh slab, pattern, plan, matrix, flags, work vectors"""
+
+    def __init__(self, dfb, ctx, nx, ny, nz, rank, nranks, precond, lam=1.0, mu=1.0):
+        from del_fem_b200 import partition, sparse_ilu
+        self.dfb, self.ctx = dfb, ctx
+        self.lam, self.mu = lam, mu
+        self.h = 1.0 / (nx - 1)
+        self.slab = s = partition.make_slab(nx, ny, nz, rank, nranks)
+        self.mesh = dfb.Mesh.kuhn(ctx, nx, ny, nz, self.h, s.kb, s.ke)
+        self.mesh.rotate_vertex_ids(s.shift)
+        self.pat = dfb.Pattern.from_uniform_mesh(ctx, self.mesh, False, s.n_own)
+        self.plan = dfb.Plan(ctx, self.pat, self.mesh, 0)
+        self.mat = dfb.Matrix(ctx, self.pat, 3)
+        self.halo = None
+        if nranks > 1:
+            self.halo = dfb.Halo(ctx, s.peers, s.send_ptr, s.send_idx, s.recv_ptr)
+            self.mat.set_halo(self.halo, s.int_begin, s.int_end)
+        self.flag_host = s.flags_clamp_z0()
+        self.flag = dfb.BcFlag(ctx, self.flag_host)
+        ng = s.n_ghost
+        self.u0 = dfb.Vec(ctx, s.n_own, 3, ng)
+        self.rhs = dfb.Vec(ctx, s.n_own, 3, ng)
+        self.x = dfb.Vec(ctx, s.n_own, 3, ng)
+        self.q = dfb.Vec(ctx, s.n_own, 3, ng)
+        self.p = dfb.Vec(ctx, s.n_own, 3, ng)
+        self.pc = sparse_ilu.Preconditioner(precond)
+        self.pc.initialize(self.mat)
+        self.n_dof_local = 3 * s.n_own
+        self.hist = None
+
+    def step(self, tol=1e-8, max_it=20000):
+        """one pass of the hot path, everything already resident in HBM. returns (assembly_ms, total_ms, iterations)"""
+        from del_fem_b200 import sparse_ilu
+        dfb, ctx, s = self.dfb, self.ctx, self.slab
+        ctx.timer_start()
+        self.mat.assemble(self.plan, "solid_linear_tet", self.mesh, self.lam, self.mu)
+        asm_ms = ctx.timer_stop()
+        ctx.timer_start()
+        self.u0.fill_splitmix(0, 3 * s.first_global_vtx, -0.1, 0.1)
+        self.u0.set_fixed_dof_zero_dev(self.flag)
+        self.mat.mult_vec(self.rhs, 0.0, -1.0, self.u0)
+        self.rhs.set_fixed_dof_zero_dev(self.flag)
+        self.mat.set_fixed_dof_dev(1.0, self.flag)
+        sparse_ilu.copy_value(self.pc, self.mat)
+        sparse_ilu.decompose(self.pc)
+        self.hist = dfb.preconditioned_conjugate_gradient(self.rhs, self.x, self.q, self.p, tol, max_it, self.mat, self.pc)
+        rest_ms = ctx.timer_stop()
+        return asm_ms, asm_ms + rest_ms, len(self.hist) - 1
