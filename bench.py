@@ -259,7 +259,7 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     spmv_avg_ms = spmv_ms_total / max(spmv_count, 1)
     achieved = b_spmv / (spmv_avg_ms * 1e-3) / 1e9 if spmv_count else None
-    roofline = {"kernel": "k_spmv_tile<3> (3x3-block BSR SpMV + fused p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "k_spmv_ring<3,4> (3x3-block BSR SpMV, TMA ring, fused p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak if achieved else None), "peak_source": peak_src,
                 "frac_of_nominal_8000": (achieved / 8000.0 if achieved else None),
                 "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_avg_ms, "launches_timed": spmv_count,

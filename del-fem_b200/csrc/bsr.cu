@@ -515,10 +515,12 @@ __global__ void __launch_bounds__(160) k_spmv_tile(const SpmvArgs a) {
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-// ---- variants 3/4/5: LPR lanes per row, tiles of 32/LPR rows, two-stage TMA ring per warp.
-// While a warp computes tile i out of one buffer, the bulk copies of tile i+1 are already in flight into the other; the
-// row's blocks are split over LPR lanes (one gather round instead of ~14 dependent ones) and summed with shuffles.
-template <int N, int LPR>
+// ---- variants 3..8: LPR lanes per row, tiles of 32/LPR rows, NST-stage TMA ring per warp.
+// While a warp computes tile i out of one buffer, the bulk copies of tiles i+1..i+NST-1 are already in flight into the
+// others; the row's blocks are split over LPR lanes (one gather round instead of ~14 dependent ones) and summed with
+// shuffles. Row pointers never stall the warp: the tile's row2idx slice rides along as a fourth bulk copy, and the two
+// pointers that size a tile's copies are prefetched into registers NST+1 tiles ahead.
+template <int N, int LPR, int NST>
 struct RingSmem {
   static constexpr int NN = N * N;
   static constexpr int RPT = 32 / LPR;   // rows per tile
@@ -526,8 +528,10 @@ struct RingSmem {
   static constexpr int VAL_BYTES = ((CAP * NN * 8 + 16 + 15) / 16) * 16;
   static constexpr int COL_BYTES = ((CAP * 4 + 16 + 15) / 16) * 16;
   static constexpr int DIA_BYTES = ((RPT * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES;
-  static constexpr int WARP_BYTES = 2 * BUF_BYTES + 32;  // + two mbarriers
+  static constexpr int ROWP_BYTES = (((RPT + 1) * 4 + 16 + 15) / 16) * 16;
+  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES + ROWP_BYTES;
+  static constexpr int BAR_BYTES = ((NST * 8 + 15) / 16) * 16;
+  static constexpr int WARP_BYTES = NST * BUF_BYTES + BAR_BYTES;
   static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
   static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);  // warps per CTA (one CTA per SM)
 };
@@ -535,11 +539,13 @@ struct RingSmem {
 // one row (or its share) of the ring kernel; vals/cols/dia point to the staged tile (shared) or to global memory
 template <int N, int LPR>
 __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const uint32_t *cols, const double *dia,
-                                           uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub) {
+                                           uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub,
+                                           const double (&dcol)[N], double dxo) {
   constexpr int NN = N * N;
   double s[N];
+  // contribution of a diagonal-block column that was fetched straight from global memory (zero otherwise)
 #pragma unroll
-  for (int q = 0; q < N; ++q) s[q] = 0.0;
+  for (int q = 0; q < N; ++q) s[q] = dcol[q] * dxo;
   // this lane's share of the row: blocks kb+sub, kb+sub+LPR, ... four at a time (index loads, then gathers, then FMAs)
   for (uint32_t k = kb + sub; k < ke; k += 4 * LPR) {
     uint32_t c[4];
@@ -584,9 +590,9 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
   return d;
 }
 
-template <int N, int LPR>
-__global__ void __launch_bounds__(RingSmem<N, LPR>::WARPS * 32) k_spmv_ring(const SpmvArgs a) {
-  using S = RingSmem<N, LPR>;
+template <int N, int LPR, int NST, bool RPCOPY, bool PREFETCH, bool DIACOPY>
+__global__ void __launch_bounds__(RingSmem<N, LPR, NST>::WARPS * 32) k_spmv_ring(const SpmvArgs a) {
+  using S = RingSmem<N, LPR, NST>;
   constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
@@ -595,11 +601,11 @@ __global__ void __launch_bounds__(RingSmem<N, LPR>::WARPS * 32) k_spmv_ring(cons
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned sub = lane % LPR, rl = lane / LPR;
   unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
-  const uint32_t bar0 = smem_u32(wbase + 2 * S::BUF_BYTES);
+  const uint32_t bar0 = smem_u32(wbase + NST * S::BUF_BYTES);
   const unsigned long long pol = policy_evict_first();
   if (lane == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+#pragma unroll
+    for (int j = 0; j < NST; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * j) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -608,48 +614,83 @@ __global__ void __launch_bounds__(RingSmem<N, LPR>::WARPS * 32) k_spmv_ring(cons
   const uint32_t n_tiles = (n_rows + RPT - 1) / RPT;
   const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
 
-  // lane 0 issues the three bulk copies of tile t into buffer b (nothing for oversized tiles)
-  auto issue = [&](uint32_t t, uint32_t b) {
-    if (lane != 0) return;
+  struct TilePtr {
+    uint32_t k0, k1;
+  };
+  // first / one-past-last nonzero of tile t (uniform loads, issued early so that nobody waits for them)
+  auto ptrs = [&](uint32_t t) -> TilePtr {
+    TilePtr p = {0u, 0u};
+    if (t < n_tiles) {
+      const uint32_t r0 = a.row_begin + t * RPT;
+      const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+      p.k0 = __ldg(a.row2idx + r0);
+      p.k1 = __ldg(a.row2idx + r1);
+    }
+    return p;
+  };
+  // lane 0 issues the four bulk copies of tile t into buffer b (nothing for oversized tiles)
+  auto issue = [&](uint32_t t, uint32_t b, TilePtr p) {
+    if (lane != 0 || t >= n_tiles) return;
+    if (!PREFETCH) p = ptrs(t);
+    const uint32_t nb = p.k1 - p.k0;
+    if (nb > (uint32_t)CAP) return;
     const uint32_t r0 = a.row_begin + t * RPT;
     const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
-    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
-    const uint32_t nb = k1 - k0;
-    if (nb > (uint32_t)CAP) return;
     unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
     const uint32_t bar = bar0 + 8 * b;
-    const double *g_val = a.idx2val + (uint64_t)k0 * NN;
-    const uint32_t *g_col = a.idx2col + k0;
-    const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
-    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u;
-    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u);
+    const double *g_val = a.idx2val + (uint64_t)p.k0 * NN;
+    const uint32_t *g_col = a.idx2col + p.k0;
+    const double *g_dia = (DIACOPY && a.row2val) ? a.row2val + (uint64_t)r0 * NN : nullptr;
+    const uint32_t *g_rp = a.row2idx + r0;
+    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u, rb = (r1 - r0 + 1u) * 4u;
+    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u) +
+                        (RPCOPY ? aligned_total(g_rp, rb) : 0u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
     uint32_t dummy = 0;
     stage_bulk(smem_u32(buf), g_val, vb, bar, pol, &dummy);
     stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
     if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
+    if (RPCOPY) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES + S::DIA_BYTES), g_rp, rb, bar, pol, &dummy);
   };
 
-  if (wg < n_tiles) issue(wg, 0);
-  if (wg + ws < n_tiles) issue(wg + ws, 1);
-  uint32_t phase0 = 0u, phase1 = 0u;
+  TilePtr q[NST + 1];
+#pragma unroll
+  for (int j = 0; j <= NST; ++j) q[j] = PREFETCH ? ptrs(wg + j * ws) : TilePtr{0u, 0u};
+#pragma unroll
+  for (int j = 0; j < NST; ++j) issue(wg + j * ws, j, q[j]);
+  uint32_t phase_bits = 0u;
   double dot = 0.0;
-  uint32_t it = 0;
-  for (uint32_t t = wg; t < n_tiles; t += ws, ++it) {
-    const uint32_t b = it & 1u;
+  uint32_t b = 0;
+  for (uint32_t t = wg; t < n_tiles; t += ws) {
+    // PREFETCH: pointers of tile t+NST+1 are requested now and consumed at the end of the NEXT iteration
+    const TilePtr qn = PREFETCH ? ptrs(t + (NST + 1) * ws) : TilePtr{0u, 0u};
+    const TilePtr cur = PREFETCH ? q[0] : ptrs(t);
+    const uint32_t k0 = cur.k0, k1 = cur.k1;
     const uint32_t r0 = a.row_begin + t * RPT;
     const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
-    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
     const uint32_t nb = k1 - k0;
     const uint32_t r = r0 + rl;
     const bool valid = r < r1;
-    const uint32_t kb = valid ? a.row2idx[r] : k0;
-    const uint32_t ke = valid ? a.row2idx[r + 1] : k0;
-    const bool staged = nb <= (uint32_t)CAP;
-    if (staged) {
+    // without DIACOPY the diagonal block comes straight from global memory: lane `sub` loads column `sub` of its row's block
+    // (and the matching x entry) BEFORE the barrier wait, so the latency overlaps the wait for the bulk copies
+    double dcol[N], dxo = 0.0;
+#pragma unroll
+    for (int qq = 0; qq < N; ++qq) dcol[qq] = 0.0;
+    if (!DIACOPY && a.row2val && valid && sub < (unsigned)N) {
+      const double *dp = a.row2val + (uint64_t)r * NN + (uint64_t)sub * N;
+#pragma unroll
+      for (int qq = 0; qq < N; ++qq) dcol[qq] = __ldg(dp + qq);
+      dxo = __ldg(a.x + (uint64_t)r * N + sub);
+    }
+    uint32_t gkb = k0, gke = k0;
+    if (!RPCOPY && valid) {  // requested before the barrier wait so that their latency overlaps it
+      gkb = a.row2idx[r];
+      gke = a.row2idx[r + 1];
+    }
+    if (nb <= (uint32_t)CAP) {
       unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
       const uint32_t bar = bar0 + 8 * b;
-      const uint32_t ph = b ? phase1 : phase0;
+      const uint32_t ph = (phase_bits >> b) & 1u;
       asm volatile(
           "{\n"
           ".reg .pred p;\n"
@@ -661,36 +702,45 @@ __global__ void __launch_bounds__(RingSmem<N, LPR>::WARPS * 32) k_spmv_ring(cons
           "}\n" ::"r"(bar),
           "r"(ph)
           : "memory");
-      if (b) phase1 ^= 1u;
-      else phase0 ^= 1u;
+      phase_bits ^= (1u << b);
       const double *g_val = a.idx2val + (uint64_t)k0 * NN;
       const uint32_t *g_col = a.idx2col + k0;
+      const uint32_t *g_rp = a.row2idx + r0;
       const double *sv = reinterpret_cast<const double *>(buf + ((uintptr_t)g_val & 15));
       const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15));
+      const uint32_t *sr = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + S::COL_BYTES + S::DIA_BYTES + ((uintptr_t)g_rp & 15));
       const double *sd = nullptr;
-      if (a.row2val) {
+      if (DIACOPY && a.row2val) {
         const double *g_dia = a.row2val + (uint64_t)r0 * NN;
         sd = reinterpret_cast<const double *>(buf + S::VAL_BYTES + S::COL_BYTES + ((uintptr_t)g_dia & 15)) + rl * NN;
       }
-      dot += ring_row<N, LPR>(a, sv, sc, sd, kb - k0, ke - k0, r, valid, sub);
+      const uint32_t kb = RPCOPY ? (valid ? sr[rl] : k0) : gkb;
+      const uint32_t ke = RPCOPY ? (valid ? sr[rl + 1] : k0) : gke;
+      dot += ring_row<N, LPR>(a, sv, sc, sd, kb - k0, ke - k0, r, valid, sub, dcol, dxo);
     } else {
-      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, a.row2val ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub);
+      const uint32_t kb = valid ? a.row2idx[r] : k0;
+      const uint32_t ke = valid ? a.row2idx[r + 1] : k0;
+      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, (DIACOPY && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
+                              dcol, dxo);
     }
     __syncwarp();  // every lane is done with buffer b
-    const uint32_t t2 = t + 2 * ws;
-    if (t2 < n_tiles) issue(t2, b);
+    issue(t + NST * ws, b, q[NST]);
+#pragma unroll
+    for (int j = 0; j < NST; ++j) q[j] = q[j + 1];
+    q[NST] = qn;
+    b = (b + 1 == NST) ? 0u : b + 1;
   }
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-template <int N, int LPR>
+template <int N, int LPR, int NST, bool RPCOPY, bool PREFETCH, bool DIACOPY>
 static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
-  using S = RingSmem<N, LPR>;
+  using S = RingSmem<N, LPR, NST>;
   const int warps = S::WARPS;
   const size_t smem = (size_t)warps * S::WARP_BYTES;
   static bool configured = false;
   if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_ring<N, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_ring<N, LPR, NST, RPCOPY, PREFETCH, DIACOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const uint64_t n_rows = a.row_end - a.row_begin;
@@ -698,16 +748,23 @@ static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t s
   uint64_t g = (n_tiles + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  DFB_LAUNCH_ON(c, strm, (k_spmv_ring<N, LPR>), (unsigned)g, warps * 32, smem, a);
+  DFB_LAUNCH_ON(c, strm, (k_spmv_ring<N, LPR, NST, RPCOPY, PREFETCH, DIACOPY>), (unsigned)g, warps * 32, smem, a);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
 
 template <int N>
 static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
-  if (c->spmv_variant == 3) return spmv_launch_ring<N, 2>(c, a, strm);
-  if (c->spmv_variant == 4) return spmv_launch_ring<N, 4>(c, a, strm);
-  if (c->spmv_variant == 5) return spmv_launch_ring<N, 8>(c, a, strm);
+  switch (c->spmv_variant) {
+    case 3: return spmv_launch_ring<N, 2, 2, false, false, true>(c, a, strm);
+    case 4: return spmv_launch_ring<N, 4, 2, false, false, true>(c, a, strm);
+    case 5: return spmv_launch_ring<N, 8, 2, false, false, true>(c, a, strm);
+    case 6: return spmv_launch_ring<N, 4, 3, false, false, true>(c, a, strm);
+    case 7: return spmv_launch_ring<N, 4, 2, false, true, true>(c, a, strm);
+    case 8: return spmv_launch_ring<N, 4, 2, true, true, true>(c, a, strm);
+    case 9: return spmv_launch_ring<N, 4, 2, false, false, false>(c, a, strm);  // LPR must be >= N here
+    default: break;
+  }
   const uint64_t n_rows = a.row_end - a.row_begin;
   if (n_rows == 0 && !a.fuse_dot) return DFB_OK;
   int variant = (int)c->spmv_variant;

@@ -191,10 +191,10 @@ DFB_API dfb_status dfb_host_unregister(dfb_ctx *c, void *host) {
 }
 
 // fold finished event pairs into the running totals (synchronises the stream)
-static dfb_status prof_collect(dfb_ctx *c) {
+static dfb_status prof_collect(dfb_ctx *c, size_t max_pairs = (size_t)-1) {
   if (c->prof_used == 0) return DFB_OK;
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+  for (size_t i = 0; i + 1 < c->prof_used && i / 2 < max_pairs; i += 2) {
     float ms = 0.f;
     DFB_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
     c->prof_ms += ms;
@@ -232,7 +232,8 @@ void dfb_prof_end(dfb_ctx *c) {
   cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream);
   c->prof_used += 2;
 }
-dfb_status dfb_prof_flush(dfb_ctx *c) { return prof_collect(c); }
+// the solvers enqueue iterations ahead of the convergence test: only the first `max_pairs` recorded launches did real work
+dfb_status dfb_prof_flush(dfb_ctx *c, size_t max_pairs) { return prof_collect(c, max_pairs); }
 
 DFB_API dfb_status dfb_malloc(dfb_ctx *c, uint64_t bytes, void **dev_ptr) {
   DFB_REQUIRE(c && dev_ptr, "dfb_malloc: NULL argument");

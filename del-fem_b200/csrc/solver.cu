@@ -19,7 +19,7 @@
 dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity);
 bool dfb_prof_begin(dfb_ctx *c);
 void dfb_prof_end(dfb_ctx *c);
-dfb_status dfb_prof_flush(dfb_ctx *c);
+dfb_status dfb_prof_flush(dfb_ctx *c, size_t max_pairs);
 
 // ------------------------------------------------------------------------------------------------ preconditioner
 template <int N>
@@ -418,7 +418,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     const int slot = (n_chunks - 1) & 1;
     last = hf[slot];
   }
-  DFB_TRY(dfb_prof_flush(c));
+  DFB_TRY(dfb_prof_flush(c, (size_t)last.iter));
   if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
 
   // history: the device stored ||r_k||^2 for k = 0..iter

@@ -13,7 +13,7 @@ from helpers import device_elasticity_problem, flags_z0, oracle_elasticity_probl
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 1, 2, 3, 4, 5]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8]  # 9 (diagonal from global) is N<=4/LPR=4 only, covered below
 
 
 # ------------------------------------------------------------------------------------------------ mesh / pattern / plan
