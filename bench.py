@@ -266,6 +266,13 @@ def run_ours(args):
                 "isolated_ms": spmv_iso_ms, "isolated_gbs": (b_spmv / (spmv_iso_ms * 1e-3) / 1e9 if spmv_iso_ms else None),
                 "share_of_step": (spmv_ms_total / sum(step_ms) if spmv_count == it_total and it_total > 0 else None),
                 "traffic": None}
+    try:  # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_spmv_ring_v4_traffic.json")))
+        if world == 1 and args.workload == tr["workload"] and args.spmv_variant == 4:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
 
     # ---- end-to-end through the C ABI from host buffers (N = 1: whole mesh on the host; N > 1: this rank's slab)
     e2e = None

@@ -323,6 +323,101 @@ __global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict_
   }
 }
 
+// ---- flat (element-wise) forms of K2 / K3 for the preconditioners that act per scalar (none, point Jacobi):
+// 128-bit loads/stores over the n_dof scalars instead of 24-byte block rows.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
+                                                         const double *__restrict__ p, const double *__restrict__ inv,
+                                                         uint64_t n, DfbSolverState *st, int parity, double *partials,
+                                                         unsigned int *ticket) {
+  __shared__ double s_buf[64];
+  if (st->done[parity]) return;
+  const double alpha = st->rho[parity] / st->red[0];
+  double acc[2] = {0.0, 0.0};
+  const uint64_t n2 = n >> 1;
+  double2 *r2 = reinterpret_cast<double2 *>(r);
+  double2 *x2 = reinterpret_cast<double2 *>(x);
+  const double2 *q2 = reinterpret_cast<const double2 *>(q);
+  const double2 *p2 = reinterpret_cast<const double2 *>(p);
+  const double2 *i2 = reinterpret_cast<const double2 *>(inv);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 rv = r2[i], xv = x2[i];
+    const double2 qv = q2[i], pv = p2[i];
+    rv.x -= alpha * qv.x;
+    rv.y -= alpha * qv.y;
+    xv.x += alpha * pv.x;
+    xv.y += alpha * pv.y;
+    r2[i] = rv;
+    x2[i] = xv;
+    double zx = rv.x, zy = rv.y;
+    if (KIND == DFB_PRECOND_JACOBI) {
+      const double2 iv = i2[i];
+      zx *= iv.x;
+      zy *= iv.y;
+    }
+    acc[0] += rv.x * rv.x + rv.y * rv.y;
+    acc[1] += rv.x * zx + rv.y * zy;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint64_t i = n - 1;
+    const double rv = r[i] - alpha * q[i];
+    r[i] = rv;
+    x[i] += alpha * p[i];
+    const double z = (KIND == DFB_PRECOND_JACOBI) ? inv[i] * rv : rv;
+    acc[0] += rv * rv;
+    acc[1] += rv * z;
+  }
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
+    st->red[1] = acc[0];
+    st->red[2] = acc[1];
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__restrict__ r, double *__restrict__ p,
+                                                            const double *__restrict__ inv, uint64_t n, DfbSolverState *st,
+                                                            int parity, double *hist, uint64_t hist_cap) {
+  if (st->done[parity]) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
+    return;
+  }
+  const double rr = st->red[1], rz = st->red[2];
+  const double beta = rz / st->rho[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int it = st->iter + 1;
+    st->iter = it;
+    if ((uint64_t)it < hist_cap) hist[it] = rr;
+    const double conv_ratio = sqrt(rr * st->inv_rr0);
+    int done = (conv_ratio < st->tol) ? 1 : 0;
+    if (st->check_pap && !(st->red[0] >= 0.0)) {
+      st->err = 1;
+      done = 1;
+    }
+    st->done[parity ^ 1] = done;
+    st->rho[parity ^ 1] = rz;
+  }
+  const uint64_t n2 = n >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r);
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  const double2 *i2 = reinterpret_cast<const double2 *>(inv);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+    double2 z = r2[i], pv = p2[i];
+    if (KIND == DFB_PRECOND_JACOBI) {
+      const double2 iv = i2[i];
+      z.x *= iv.x;
+      z.y *= iv.y;
+    }
+    pv.x = z.x + beta * pv.x;
+    pv.y = z.y + beta * pv.y;
+    p2[i] = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint64_t i = n - 1;
+    const double z = (KIND == DFB_PRECOND_JACOBI) ? inv[i] * r[i] : r[i];
+    p[i] = z + beta * p[i];
+  }
+}
+
 struct FlagsHost {
   int done[2];
   int iter;
@@ -361,6 +456,8 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     c->hist_cap = max_it + 2;
   }
   const int G = vec_grid(c, nb);
+  const uint64_t nflat = nb * (uint64_t)n;
+  const int GF = vec_grid(c, (nflat + 1) / 2);
   DfbSolverState *st = c->d_state;
 
 #define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2)
@@ -386,13 +483,25 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
       DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity));
       if (prof) dfb_prof_end(c);
       if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
+      if (kind == DFB_PRECOND_BLOCK_JACOBI) {
 #define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2)
-      DISPATCH_ALL(UPD)
+        DISPATCH_ALL(UPD)
 #undef UPD
+      } else if (kind == DFB_PRECOND_JACOBI) {
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2);
+      } else {
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2);
+      }
       if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+      if (kind == DFB_PRECOND_BLOCK_JACOBI) {
 #define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap)
-      DISPATCH_ALL(DIR)
+        DISPATCH_ALL(DIR)
 #undef DIR
+      } else if (kind == DFB_PRECOND_JACOBI) {
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap);
+      } else {
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap);
+      }
     }
     DFB_CHECK_LAUNCH();
     enq += todo;
