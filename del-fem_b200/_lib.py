@@ -96,6 +96,7 @@ def lib():
         "dfb_vec_dot": [_vp, _vp, C.POINTER(_f64)],
         "dfb_vec_add_scaled": [_vp, _f64, _vp],
         "dfb_vec_scale_and_add": [_vp, _f64, _vp],
+        "dfb_vec_scale": [_vp, _f64],
         "dfb_vec_set_fixed_dof_zero": [_vp, _vp],
         "dfb_vec_fill_splitmix": [_vp, _u64, _u64, _f64, _f64],
         "dfb_vec_device_ptr": [_vp],
@@ -129,6 +130,7 @@ def lib():
         "dfb_emat_batch": [_vp, _i32, _vp, _f64, _f64, _vp, _vp, _vp, _vp],
         "dfb_assemble_from_emat": [_vp, _vp, _vp],
         "dfb_assemble_neohookean_tet": [_vp, _vp, _vp, _f64, _f64, _vp, _vp, C.POINTER(_f64)],
+        "dfb_assemble_energy": [_vp, _i32, _vp, _vp, _f64, _f64, _vp, _vp, C.POINTER(_f64)],
         "dfb_emat_one": [_vp, _i32, _vp, _f64, _f64, _vp],
         "dfb_malloc": [_vp, _u64, _pp],
         "dfb_free": [_vp, _vp],

@@ -146,6 +146,9 @@ class Vec:
     def scale_and_add(self, beta, r):
         check(lib().dfb_vec_scale_and_add(self.h, float(beta), r.h))
 
+    def scale(self, s):
+        check(lib().dfb_vec_scale(self.h, float(s)))
+
     def set_fixed_dof_zero(self, blk2isfix):
         f = _c(blk2isfix, np.int32)
         if f.size != self.n_blk * self.blk_dim:

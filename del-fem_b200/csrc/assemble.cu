@@ -543,6 +543,49 @@ __global__ void __launch_bounds__(64) k_neohookean_tet(const uint32_t *__restric
   }
 }
 
+// ---- spring3::wdwddw_squared_length_difference (del-fem-cpu/src/spring3.rs:1-28), batched over the edges of a 2-node mesh.
+// Rest positions = mesh coordinates, deformed positions = rest + disp; rest length = |rest_0 - rest_1|.
+__global__ void __launch_bounds__(128) k_spring3(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                 const double *__restrict__ disp, uint64_t num_elem, double stiffness,
+                                                 double *__restrict__ emat, double *__restrict__ evec, double *__restrict__ w_out) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v0 = e2v[e * 2 + 0], v1 = e2v[e * 2 + 1];
+    double r[3], v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double a0 = xyz[(uint64_t)v0 * 3 + k], a1 = xyz[(uint64_t)v1 * 3 + k];
+      r[k] = a0 - a1;
+      v[k] = (a0 + disp[(uint64_t)v0 * 3 + k]) - (a1 + disp[(uint64_t)v1 * 3 + k]);
+    }
+    const double l0 = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    const double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const double c = l0 - l;
+    if (evec) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        evec[e * 6 + k] = v[k] * (-c * stiffness / l);
+        evec[e * 6 + 3 + k] = v[k] * (c * stiffness / l);
+      }
+    }
+    if (emat) {
+      const double t0 = stiffness * l0 / (l * l * l);
+      const double t1 = stiffness * (l - l0) / l;
+      double *out = emat + e * 36;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const double m = (v[a] * v[b]) * t0 + ((a == b) ? t1 : 0.0);
+          out[0 * 9 + a + 3 * b] = m;
+          out[1 * 9 + a + 3 * b] = -m;
+          out[2 * 9 + a + 3 * b] = -m;
+          out[3 * 9 + a + 3 * b] = m;
+        }
+    }
+    if (w_out) w_out[e] = 0.5 * stiffness * c * c;
+  }
+}
+
 DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *mesh, double p0, double p1, const dfb_vec *disp,
                                   double *emat_dev, double *evec_dev, double *w_dev) {
   DFB_REQUIRE(ctx && mesh, "dfb_emat_batch: NULL argument");
@@ -571,6 +614,12 @@ DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *me
       if (g2 > (uint64_t)ctx->sm_count * 32) g2 = (uint64_t)ctx->sm_count * 32;
       DFB_LAUNCH(ctx, k_neohookean_tet, (unsigned)g2, 64, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, p1,
                  emat_dev, evec_dev, w_dev);
+      break;
+    }
+    case DFB_ELEM_SPRING3: {
+      DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
+                  "dfb_emat_batch: spring3 needs a displacement vector covering every mesh vertex");
+      DFB_LAUNCH(ctx, k_spring3, (unsigned)g, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, emat_dev, evec_dev, w_dev);
       break;
     }
     default:
@@ -646,20 +695,27 @@ __global__ void __launch_bounds__(256) k_sum(const double *__restrict__ a, uint6
   if (grid_sum_last_block<1>(acc, partials, ticket, s_buf) && threadIdx.x == 0) out[0] = acc[0];
 }
 
-DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, const dfb_vec *disp, double myu,
-                                               double lambda, dfb_bsr *m, dfb_vec *dw, double *w) {
-  DFB_REQUIRE(plan && mesh && disp && m, "dfb_assemble_neohookean_tet: NULL argument");
-  DFB_REQUIRE(plan->pat->convention == 0 && plan->flavour == 0, "dfb_assemble_neohookean_tet: needs a convention-0 / flavour-0 plan");
-  DFB_REQUIRE(m->blk_dim == 3 && mesh->num_node == 4, "dfb_assemble_neohookean_tet: needs 3x3 blocks on a tet mesh");
+// energy-model assembly (two-phase): Hessian -> m (deterministic gather), gradient -> dw, energy -> *w.
+// kinds: DFB_ELEM_NEOHOOKEAN_TET (p0 = myu, p1 = lambda), DFB_ELEM_SPRING3 (p0 = stiffness)
+DFB_API dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1,
+                                       dfb_bsr *m, dfb_vec *dw, double *w) {
+  DFB_REQUIRE(plan && mesh && disp && m, "dfb_assemble_energy: NULL argument");
+  DFB_REQUIRE(kind == DFB_ELEM_NEOHOOKEAN_TET || kind == DFB_ELEM_SPRING3, "dfb_assemble_energy: kind %d is not an energy model", kind);
+  const ElemInfo info = elem_info(kind);
+  DFB_REQUIRE(plan->pat->convention == 0 && plan->flavour == 0, "dfb_assemble_energy: needs a convention-0 / flavour-0 plan");
+  DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble_energy: matrix and plan use different patterns");
+  DFB_REQUIRE(m->blk_dim == 3 && mesh->num_node == info.n_node && mesh->ndim == 3, "dfb_assemble_energy: needs 3x3 blocks and a matching mesh");
+  DFB_REQUIRE(mesh->num_elem == plan->num_elem && mesh->num_node == plan->num_node, "dfb_assemble_energy: mesh does not match the plan");
   dfb_ctx *c = plan->ctx;
+  const uint64_t nn = (uint64_t)info.n_node;
   double *d_emat = nullptr, *d_evec = nullptr, *d_w = nullptr;
-  DFB_TRY(dfb_dev_alloc_t(&d_emat, mesh->num_elem * 144));
-  DFB_TRY(dfb_dev_alloc_t(&d_evec, mesh->num_elem * 12));
+  DFB_TRY(dfb_dev_alloc_t(&d_emat, mesh->num_elem * nn * nn * 9));
+  DFB_TRY(dfb_dev_alloc_t(&d_evec, mesh->num_elem * nn * 3));
   DFB_TRY(dfb_dev_alloc_t(&d_w, mesh->num_elem));
-  dfb_status st = dfb_emat_batch(c, DFB_ELEM_NEOHOOKEAN_TET, mesh, myu, lambda, disp, d_emat, d_evec, d_w);
+  dfb_status st = dfb_emat_batch(c, kind, mesh, p0, p1, disp, d_emat, d_evec, d_w);
   if (st == DFB_OK) st = dfb_assemble_from_emat(plan, d_emat, m);
   if (st == DFB_OK && dw) {
-    DFB_LAUNCH(c, k_gather_evec, c->sm_count * 8, 128, 0, plan->d_nz2ptr, plan->d_contrib, plan->pat->nnz, plan->pat->num_blk, 4, 3,
+    DFB_LAUNCH(c, k_gather_evec, c->sm_count * 8, 128, 0, plan->d_nz2ptr, plan->d_contrib, plan->pat->nnz, plan->pat->num_blk, info.n_node, 3,
                d_evec, dw->d);
   }
   if (st == DFB_OK && w) {
@@ -670,12 +726,17 @@ DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *m
     cudaMemcpyAsync(c->h_pinned, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  if (st == DFB_OK && e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_assemble_neohookean_tet: %s", cudaGetErrorString(e));
+  if (st == DFB_OK && e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_assemble_energy: %s", cudaGetErrorString(e));
   if (st == DFB_OK && w) *w = *(double *)c->h_pinned;
   cudaFree(d_emat);
   cudaFree(d_evec);
   cudaFree(d_w);
   return st;
+}
+
+DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, const dfb_vec *disp, double myu,
+                                               double lambda, dfb_bsr *m, dfb_vec *dw, double *w) {
+  return dfb_assemble_energy(plan, DFB_ELEM_NEOHOOKEAN_TET, mesh, disp, myu, lambda, m, dw, w);
 }
 
 // one element on host arrays (tests / API parity with the reference's by-value element functions)

@@ -154,6 +154,19 @@ DFB_API dfb_status dfb_vec_scale_and_add(dfb_vec *p, double beta, const dfb_vec 
   return DFB_OK;
 }
 
+// ---- v *= s
+__global__ void __launch_bounds__(256) k_scale(double *__restrict__ v, double s, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] *= s;
+}
+
+DFB_API dfb_status dfb_vec_scale(dfb_vec *v, double s) {
+  DFB_REQUIRE(v, "dfb_vec_scale: NULL argument");
+  dfb_ctx *c = v->ctx;
+  DFB_LAUNCH(c, k_scale, stream_grid(c, v->len(), 4, 256), 256, 0, v->d, s, v->len());
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 // ---- rhs[d] = 0 where flag
 __global__ void k_zero_flagged(double *__restrict__ v, const int32_t *__restrict__ flag, uint64_t n) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)

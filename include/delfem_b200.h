@@ -105,6 +105,7 @@ dfb_status dfb_vec_copy(dfb_vec *dst, const dfb_vec *src);                /* sli
 dfb_status dfb_vec_dot(const dfb_vec *a, const dfb_vec *b, double *out);  /* slice_of_array::dot       :8  (deterministic tree; all-reduced over ranks) */
 dfb_status dfb_vec_add_scaled(dfb_vec *u, double alpha, const dfb_vec *p);/* add_scaled_vector         :26 */
 dfb_status dfb_vec_scale_and_add(dfb_vec *p, double beta, const dfb_vec *r); /* scale_and_add_vec      :38 */
+dfb_status dfb_vec_scale(dfb_vec *v, double s);                           /* vecn::scale_in_place per block (sparse_square.rs:156) */
 /* set_fix_dof_to_rhs_vector  del-fem-cpu/src/sparse_square.rs:57-70 */
 dfb_status dfb_vec_set_fixed_dof_zero(dfb_vec *rhs, const int32_t *blk2isfix_host /* n_blk*blk_dim */);
 /* out[i] = lo + (hi-lo)*splitmix64(seed, first_idx + i) — synthetic inputs for benches, bit-identical to the oracle's */
@@ -187,6 +188,10 @@ dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev, dfb_bs
 /* neo-Hookean Newton step input: Hessian -> m, gradient -> dw (deterministic gather), energy -> *w */
 dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, const dfb_vec *disp, double myu,
                                        double lambda, dfb_bsr *m, dfb_vec *dw, double *w);
+/* generic energy-model assembly (two-phase): kinds DFB_ELEM_NEOHOOKEAN_TET (p0 = myu, p1 = lambda) and DFB_ELEM_SPRING3 (p0 = stiffness,
+   mesh = edges, rest positions = mesh coordinates; del-fem-cpu/src/spring3.rs:1 merged as in rod3_darboux.rs:775-792) */
+dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1,
+                               dfb_bsr *m, dfb_vec *dw, double *w);
 /* one element on host arrays (tests): node2xyz [n_node][ndim], out emat [n_node][n_node][N*N] */
 dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2xyz, double p0, double p1, double *emat);
 /* device scratch helpers for the two-phase path */

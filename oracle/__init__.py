@@ -247,6 +247,19 @@ def assemble_neohookean_tet(elem2vtx, vtx2xyz, vtx2disp, mu, lam, row2idx, idx2c
     return w.value, dw, row2val, idx2val
 
 
+def assemble_spring3(edge2vtx, vtx2xyz, vtx2disp, stiffness, row2idx, idx2col):
+    """edge loop of wdwddw_hair_system (rod3_darboux.rs:760-793) with 3x3 blocks -> (w, dw, row2val, idx2val)"""
+    e2v = _u64(edge2vtx).reshape(-1, 2)
+    nb = row2idx.size - 1
+    row2val = np.zeros((nb, 9))
+    idx2val = np.zeros((idx2col.size, 9))
+    dw = np.zeros((nb, 3))
+    w = C.c_double(0)
+    _chk(lib().orc_assemble_spring3(_p(e2v), C.c_uint64(e2v.shape[0]), _p(_f64(vtx2xyz)), _p(_f64(vtx2disp)), C.c_double(stiffness),
+                                    _p(row2idx), C.c_uint64(nb), _p(idx2col), _p(row2val), _p(idx2val), _p(dw), C.byref(w)))
+    return w.value, dw, row2val, idx2val
+
+
 def elem2nz(convention, flavour, elem2vtx, n_node, row2idx, idx2col):
     """element -> nonzero slot map implied by the merge routines (diagonal slot = nnz + row for convention 0)"""
     e2v = _u64(elem2vtx).reshape(-1, n_node)

@@ -672,6 +672,36 @@ ORC_API int orc_assemble_neohookean_tet(const usize *elem2vtx, usize num_elem, c
   return ORC_OK;
 }
 
+// mass-spring whole-mesh loop: the edge part of wdwddw_hair_system (del-fem-cpu/src/rod3_darboux.rs:760-793) with 3x3 blocks:
+// per edge spring3::wdwddw_squared_length_difference -> w += , dw[node] += , ddw.merge_for_array_blk. Rest positions = vtx2xyz,
+// deformed = vtx2xyz + vtx2disp, rest length = |rest_0 - rest_1|.
+ORC_API int orc_assemble_spring3(const usize *edge2vtx, usize num_edge, const double *vtx2xyz, const double *vtx2disp,
+                                 double stiffness, const usize *row2idx, usize num_blk, const usize *idx2col, double *row2val,
+                                 double *idx2val, double *dw_out, double *w_out) {
+  std::vector<usize> col2idx(num_blk, USIZE_MAX);
+  double wsum = 0.0;
+  for (usize e = 0; e < num_edge; ++e) {
+    const usize *nv = edge2vtx + e * 2;
+    double def[6], r[3];
+    for (int k = 0; k < 3; ++k) {
+      const double a0 = vtx2xyz[nv[0] * 3 + k], a1 = vtx2xyz[nv[1] * 3 + k];
+      r[k] = a0 - a1;
+      def[k] = a0 + vtx2disp[nv[0] * 3 + k];
+      def[3 + k] = a1 + vtx2disp[nv[1] * 3 + k];
+    }
+    const double l0 = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    double w, dw[6], ddw[36];
+    orc_spring3_wdwddw(stiffness, def, l0, &w, dw, ddw);
+    wsum += w;
+    for (int n = 0; n < 2; ++n)
+      for (int k = 0; k < 3; ++k) dw_out[nv[n] * 3 + k] += dw[n * 3 + k];
+    int rc = orc_merge_for_array_blk(9, 2, nv, ddw, row2idx, num_blk, idx2col, row2val, idx2val, col2idx.data(), 0);
+    if (rc) return rc;
+  }
+  *w_out = wsum;
+  return ORC_OK;
+}
+
 // element -> nonzero index map (the artefact the GPU assembly plan must reproduce bit-exactly):
 // slot of (e,i,j): off-diagonal -> index into idx2val; diagonal (convention 0) -> num_idx + row.
 // flavour as in merge_for_array_blk (0 node-index diagonal test, 1 vertex-id test).

@@ -172,3 +172,51 @@ def test_cg_other_block_sizes(dfb, ctx, orc, n):
         rd = dfb.Vec.from_numpy(ctx, b)
         hd = dfb.preconditioned_conjugate_gradient(rd, ud, apd, pd, 1e-10, 500, mat, pc)
         assert abs(len(hd) - len(ho)) <= 1 and rel_err(ud.download(), xo) < 1e-8
+
+
+def test_config3_mass_spring_cloth_steps_match_oracle(dfb, ctx, orc):
+    """implicit mass-spring steps (spring3 element kernel -> gather -> inertia on the diagonal -> BC -> CG), state for state"""
+    from del_fem_b200.cloth import MassSpringCloth, edges_of_grid_cloth
+    nx, ny = 17, 13
+    edges = edges_of_grid_cloth(nx, ny)
+    gx, gy = np.meshgrid(np.arange(nx) / (nx - 1), np.arange(ny) / (nx - 1))
+    rest = np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(nx * ny)], 1))
+    nv = rest.shape[0]
+    flag = np.zeros((nv, 3), dtype=np.int32)
+    flag[0] = 1
+    flag[nx - 1] = 1  # two pinned corners
+    k, mass, dt = 50.0, 1.0 / nv, 1e-2
+    grav = np.array([0.0, 0.0, -9.8])
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(edges, 2, nv, False)
+    cloth = MassSpringCloth(ctx, edges, rest, flag, k, mass, gravity=grav, pattern=dfb.Pattern(ctx, r2i, i2c, 0))
+    # same pattern when built on the device from the edge mesh
+    r_d, c_d = dfb.Pattern.from_uniform_mesh(ctx, cloth.mesh, False).download()
+    assert np.array_equal(r_d, r2i) and np.array_equal(c_d, i2c)
+    rng = np.random.default_rng(0)
+    disp = 1e-3 * rng.standard_normal((nv, 3))
+    disp[flag != 0] = 0.0
+    vel = np.zeros((nv, 3))
+    cloth.disp.upload(disp)
+    f = mass * np.tile(grav, (nv, 1))
+    for step in range(5):
+        cloth.disp.upload(disp)
+        cloth.vel.upload(vel)
+        w_d, it_d = cloth.step(dt, 1e-8, 1000)
+        # oracle step (rod3_darboux.rs:1174-1263 with spring3 edges)
+        vel[flag != 0] = 0.0
+        x_tmp = disp + dt * vel
+        w_o, dw, rv, iv = orc.assemble_spring3(edges, rest, x_tmp, k, r2i, i2c)
+        g = dw - f
+        rv[:, [0, 4, 8]] += mass / (dt * dt)
+        orc.set_fix_dof_to_rhs_vector(g, flag)
+        orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+        u, ap, p = np.zeros_like(g), np.zeros_like(g), np.zeros_like(g)
+        hist = orc.conjugate_gradient(g, u, ap, p, 1e-8, 1000, r2i, i2c, iv, rv)
+        x_new = x_tmp - u
+        vel = (x_new - disp) / dt
+        disp = x_new
+        assert abs(w_d - w_o) <= 1e-12 * max(1.0, abs(w_o))
+        assert abs(it_d - len(hist)) <= 1
+        assert rel_err(cloth.disp.download(), disp) < 1e-7
+        assert rel_err(cloth.vel.download(), vel) < 1e-5
+    assert disp[:, 2].min() < -1e-4  # the cloth falls
