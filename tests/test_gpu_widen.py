@@ -220,3 +220,52 @@ def test_config3_mass_spring_cloth_steps_match_oracle(dfb, ctx, orc):
         assert rel_err(cloth.disp.download(), disp) < 1e-7
         assert rel_err(cloth.vel.download(), vel) < 1e-5
     assert disp[:, 2].min() < -1e-4  # the cloth falls
+
+
+def test_numpy_shaped_api(dfb, ctx, orc):
+    """del-fem-numpy's flat-array functions + the reference's own Python test (tests/test_laplace.py:22-30)"""
+    from del_fem_b200 import numpy_api as na
+    t2v, xy = orc.grid_tri_mesh(14, disk=True)
+    nv = xy.shape[0]
+    r2, c2 = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, True)
+    for fn, kind, pts in ((na.merge_laplace_to_bsr_for_meshtri2, "laplace_tri2", xy),
+                          (na.merge_laplace_to_bsr_for_meshtri3, "cot_laplace_tri3", np.c_[xy, 0.1 * xy[:, 0] ** 2])):
+        pts = np.ascontiguousarray(pts)
+        idx2val = np.ones(c2.size, dtype=np.float32)  # the merge ADDS into the caller's f32 array
+        fn(t2v, pts, r2, c2, idx2val, ctx=ctx)
+        _, iv = orc.assemble(kind, 1, t2v, pts, 1.0, 0.0, r2, c2)
+        assert np.allclose(idx2val - 1.0, iv[:, 0], rtol=1e-5, atol=1e-5)
+    iv3 = np.zeros((c2.size, 2, 2), dtype=np.float64)
+    na.merge_linear_solid_to_bsr_for_meshtri2(t2v, xy, r2, c2, iv3, ctx=ctx)
+    _, iv = orc.assemble("solid_linear_tri2", 1, t2v, xy, 1.0, 1.0, r2, c2)
+    assert np.array_equal(iv3.reshape(-1, 4), iv)
+    # csrdia flavour
+    r0, c0 = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    pts = np.ascontiguousarray(np.c_[xy, np.zeros(nv)])
+    rv, ivv = np.zeros(nv), np.zeros(c0.size)
+    na.merge_hessian_mesh_laplacian_on_trimesh3(t2v, pts, r0, c0, rv, ivv, ctx=ctx)
+    rvo, ivo = orc.assemble("cot_laplace_tri3", 0, t2v, pts, 0, 0, r0, c0)
+    assert rel_err(rv, rvo[:, 0]) < 1e-13 and rel_err(ivv, ivo[:, 0]) < 1e-13
+    # LaplacianMatrix.from_uniform_mesh + the reference's pytest assertions
+    L = na.LaplacianMatrix.from_uniform_mesh(t2v, xy, ctx=ctx)
+    assert abs(L - L.T).max() < 1e-10
+    assert np.abs(L @ np.ones(nv)).max() < 1e-4
+    # block_sparse_apply_bc / conjugate_gradient with 4x4 blocks (the only size upstream implements)
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((4, 4))
+    S = S @ S.T + 4 * np.eye(4)
+    Lr, Li = orc.assemble("laplace_tri2", 0, t2v, xy, 1.0, 0.0, r0, c0)
+    row2val = ((Lr[:, :1] + 1.0) * S.T.reshape(1, -1)).astype(np.float64)
+    idx2val = (Li[:, :1] * S.T.reshape(1, -1)).astype(np.float64)
+    isfix = (rng.random((nv, 4)) < 0.1).astype(np.int32)
+    rvo, ivo = row2val.copy(), idx2val.copy()
+    orc.set_fixed_bc(1.0, isfix, rvo, ivo, r0, c0)
+    na.block_sparse_apply_bc(1.0, isfix, row2val, idx2val, r0, c0, ctx=ctx)
+    assert np.array_equal(row2val, rvo) and np.array_equal(idx2val, ivo)
+    b = rng.standard_normal((nv, 4))
+    na.block_sparse_set_fixed_bc_to_rhs_vector(isfix, b)
+    r, u, p, ap = b.copy(), np.zeros_like(b), np.zeros_like(b), np.zeros_like(b)
+    hist = na.conjugate_gradient(r, u, p, ap, r0, c0, idx2val, row2val, ctx=ctx)
+    ro, uo, apo, po = b.copy(), np.zeros_like(b), np.zeros_like(b), np.zeros_like(b)
+    ho = orc.conjugate_gradient(ro, uo, apo, po, 1e-5, 1000, r0, c0, ivo, rvo)
+    assert abs(len(hist) - len(ho)) <= 1 and rel_err(u, uo) < 1e-6
