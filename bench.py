@@ -259,7 +259,7 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     spmv_avg_ms = spmv_ms_total / max(spmv_count, 1)
     achieved = b_spmv / (spmv_avg_ms * 1e-3) / 1e9 if spmv_count else None
-    roofline = {"kernel": "k_spmv_ring<3,4> (3x3-block BSR SpMV, TMA ring, fused p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "k_spmv_packed<3> (3x3-block BSR SpMV over the tile-packed mirror, one TMA bulk copy per 8-row tile, fused p.Ap)" if args.spmv_variant == 20 else f"spmv variant {args.spmv_variant}", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": (achieved / peak if achieved else None), "peak_source": peak_src,
                 "frac_of_nominal_8000": (achieved / 8000.0 if achieved else None),
                 "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_avg_ms, "launches_timed": spmv_count,
@@ -267,8 +267,8 @@ def run_ours(args):
                 "share_of_step": (spmv_ms_total / sum(step_ms) if spmv_count == it_total and it_total > 0 else None),
                 "traffic": None}
     try:  # DRAM traffic of the same kernel on the same workload from the committed ncu capture (per launch)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_spmv_ring_v4_traffic.json")))
-        if world == 1 and args.workload == tr["workload"] and args.spmv_variant == 4:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_spmv_packed_traffic.json")))
+        if world == 1 and args.workload == tr["workload"] and args.spmv_variant == 20:
             roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roofline["traffic_source"] = tr["source"]
     except Exception:
@@ -367,7 +367,7 @@ def main():
     ap.add_argument("--workload", default="S10", help="S1 | S10 | S50 | <vertices per edge>")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "block_jacobi"])
-    ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "4")))
+    ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "20")))
     ap.add_argument("--iters-per-sync", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -52,6 +52,8 @@ DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
   cudaFree(m->d_idx2val);
   cudaFree(m->d_row2val);
   cudaFree(m->d_flag);
+  cudaFree(m->d_packed);
+  cudaFree(m->d_tile_off);
   dfb_pattern_destroy(m->pat);
   delete m;
   return DFB_OK;
@@ -59,6 +61,7 @@ DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
 
 DFB_API dfb_status dfb_bsr_set_zero(dfb_bsr *m) {
   DFB_REQUIRE(m, "dfb_bsr_set_zero: NULL argument");
+  m->packed_valid = 0;
   const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
   DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, m->pat->nnz * nn * sizeof(double), m->ctx->stream));
   if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, m->pat->num_blk * nn * sizeof(double), m->ctx->stream));
@@ -67,6 +70,7 @@ DFB_API dfb_status dfb_bsr_set_zero(dfb_bsr *m) {
 
 DFB_API dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2val) {
   DFB_REQUIRE(m, "dfb_bsr_upload: NULL argument");
+  m->packed_valid = 0;
   const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
   if (idx2val) DFB_CUDA(cudaMemcpyAsync(m->d_idx2val, idx2val, m->pat->nnz * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
   if (row2val) {
@@ -153,6 +157,7 @@ __global__ void k_set_fixed_bc(double val_dia, const int32_t *__restrict__ flag,
 
 static dfb_status launch_set_fixed_bc(dfb_bsr *m, double val_dia, const int32_t *d_flag) {
   dfb_ctx *c = m->ctx;
+  m->packed_valid = 0;
   const int grid = c->sm_count * 8;
   switch (m->blk_dim) {
     case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
@@ -202,6 +207,7 @@ __global__ void k_add_to_diagonal(double *__restrict__ row2val, int N, double sc
 DFB_API dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_vec *v) {
   DFB_REQUIRE(m && v, "dfb_bsr_add_to_diagonal: NULL argument");
   DFB_REQUIRE(m->d_row2val, "dfb_bsr_add_to_diagonal: convention 1 matrices have no separate diagonal");
+  m->packed_valid = 0;
   DFB_REQUIRE(v->n_blk == m->pat->num_blk && v->blk_dim == m->blk_dim, "dfb_bsr_add_to_diagonal: shape mismatch");
   DFB_LAUNCH(m->ctx, k_add_to_diagonal, m->ctx->sm_count * 8, 256, 0, m->d_row2val, m->blk_dim, scale, v->d, v->len());
   DFB_CHECK_LAUNCH();
@@ -241,6 +247,7 @@ __global__ void k_merge_one(const double *__restrict__ emat, const uint32_t *__r
 DFB_API dfb_status dfb_bsr_merge_one(dfb_bsr *m, const double *emat, const uint64_t *node2vtx, int32_t n_node, int32_t flavour) {
   DFB_REQUIRE(m && emat && node2vtx, "dfb_bsr_merge_one: NULL argument");
   DFB_REQUIRE(n_node >= 1 && n_node <= 8, "dfb_bsr_merge_one: n_node %d not in 1..8", n_node);
+  m->packed_valid = 0;
   dfb_ctx *c = m->ctx;
   const int NN = m->blk_dim * m->blk_dim;
   double *d_e = nullptr;
@@ -753,6 +760,455 @@ static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t s
   return DFB_OK;
 }
 
+// ---- variants 12/13/14: software-pipelined ring ("pipe").
+// Same tiling as the ring (LPR lanes per row, 32/LPR rows per tile, NST-stage TMA ring per warp), but the x gather of tile
+// i+1 is issued BEFORE the FMAs of tile i: by the time a tile is multiplied its x values sit in registers, so the dependent
+// chain  column index (shared) -> x (L2) -> DFMA  never stalls the warp, and a deeper ring (NST-1 tiles in flight per warp)
+// with fewer resident warps keeps more bytes in flight per SM.
+template <int N, int LPR, int NST>
+struct PipeSmem {
+  static constexpr int NN = N * N;
+  static constexpr int RPT = 32 / LPR;
+  static constexpr int CAP = RPT * 16;
+  static constexpr int VAL_BYTES = ((CAP * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int COL_BYTES = ((CAP * 4 + 16 + 15) / 16) * 16;
+  static constexpr int DIA_BYTES = ((RPT * NN * 8 + 16 + 15) / 16) * 16;
+  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES;
+  static constexpr int BAR_BYTES = ((NST * 8 + 15) / 16) * 16;
+  static constexpr int WARP_BYTES = NST * BUF_BYTES + BAR_BYTES;
+  static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
+  static constexpr int WARPS = WARPS_RAW > 16 ? 16 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
+};
+
+template <int N>
+struct PipePre {      // what a lane holds for a tile whose gathers are in flight
+  uint32_t r, k0, kb, ke;
+  uint32_t c[4];
+  double xv[4][N];
+  double xo;          // x[r][sub] for the diagonal-block column this lane owns
+  bool valid, staged;
+};
+
+template <int N, int LPR, int NST, int ML>
+__global__ void __launch_bounds__(PipeSmem<N, LPR, NST>::WARPS * 32) k_spmv_pipe(const SpmvArgs a) {
+  using S = PipeSmem<N, LPR, NST>;
+  constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
+
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned sub = lane % LPR, rl = lane / LPR;
+  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
+  const uint32_t bar0 = smem_u32(wbase + NST * S::BUF_BYTES);
+  const unsigned long long pol = policy_evict_first();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NST; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * j) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint32_t n_rows = a.row_end - a.row_begin;
+  const uint32_t n_tiles = (n_rows + RPT - 1) / RPT;
+  const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
+
+  // ML == 0: lane 0 issues the three bulk copies. ML > 0: lane 0 posts the expected byte count, then the value range is
+  // split into ML pieces issued by ML different lanes, columns and diagonal by two more lanes (independent TMA requests).
+  auto issue = [&](uint32_t t, uint32_t b) {
+    if (t >= n_tiles) return;
+    if (ML == 0 && lane != 0) return;
+    const uint32_t r0 = a.row_begin + t * RPT;
+    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
+    const uint32_t nb = k1 - k0;
+    if (nb > (uint32_t)CAP) return;
+    unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+    const uint32_t bar = bar0 + 8 * b;
+    const double *g_val = a.idx2val + (uint64_t)k0 * NN;
+    const uint32_t *g_col = a.idx2col + k0;
+    const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
+    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u;
+    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u);
+    uint32_t dummy = 0;
+    if (ML == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+      stage_bulk(smem_u32(buf), g_val, vb, bar, pol, &dummy);
+      stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
+      if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
+    } else {
+      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+      __syncwarp();
+      // aligned superset of the value range, cut into ML pieces on 16-byte boundaries
+      const uintptr_t sv = (uintptr_t)g_val;
+      const uint32_t mis = (uint32_t)(sv & 15);
+      const char *gs = (const char *)(sv - mis);
+      const uint32_t total = (mis + vb + 15u) & ~15u;
+      const uint32_t piece = ((total / ML) + 15u) & ~15u;
+      if (lane < (unsigned)ML) {
+        const uint32_t off = lane * piece;
+        if (off < total) {
+          const uint32_t len = min(piece, total - off);
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                  smem_u32(buf) + off),
+              "l"(gs + off), "r"(len), "r"(bar), "l"(pol)
+              : "memory");
+        }
+      } else if (lane == (unsigned)ML) {
+        stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
+      } else if (lane == (unsigned)ML + 1 && g_dia) {
+        stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
+      }
+    }
+  };
+
+  uint32_t phase_bits = 0u;
+  // wait for tile t in buffer b, then put its column indices and x gathers in flight
+  auto prefetch = [&](uint32_t t, uint32_t b) -> PipePre<N> {
+    PipePre<N> p;
+    const uint32_t r0 = a.row_begin + t * RPT;
+    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
+    p.r = r0 + rl;
+    p.k0 = k0;
+    p.valid = p.r < r1;
+    p.kb = p.valid ? a.row2idx[p.r] : k0;
+    p.ke = p.valid ? a.row2idx[p.r + 1] : k0;
+    p.staged = (k1 - k0) <= (uint32_t)CAP;
+    p.xo = (p.valid && sub < (unsigned)N) ? __ldg(a.x + (uint64_t)p.r * N + sub) : 0.0;
+    const uint32_t *cols = a.idx2col;
+    if (p.staged) {
+      const uint32_t bar = bar0 + 8 * b;
+      const uint32_t ph = (phase_bits >> b) & 1u;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "PIPE_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra PIPE_DONE;\n"
+          "bra PIPE_WAIT;\n"
+          "PIPE_DONE:\n"
+          "}\n" ::"r"(bar),
+          "r"(ph)
+          : "memory");
+      phase_bits ^= (1u << b);
+      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+      const uint32_t *g_col = a.idx2col + k0;
+      cols = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15)) - k0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t kk = p.kb + sub + u * LPR;
+      p.c[u] = (kk < p.ke) ? cols[kk] : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p.c[u] != 0xFFFFFFFFu) load_x<N>(p.xv[u], a.x, p.c[u]);
+    }
+    return p;
+  };
+
+  double dot = 0.0;
+  auto compute = [&](const PipePre<N> &p, uint32_t b) {
+    const double *vals = a.idx2val;
+    const uint32_t *cols = a.idx2col;
+    const double *dia = a.row2val ? a.row2val + (uint64_t)p.r * NN : nullptr;
+    if (p.staged) {
+      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+      const double *g_val = a.idx2val + (uint64_t)p.k0 * NN;
+      const uint32_t *g_col = a.idx2col + p.k0;
+      vals = reinterpret_cast<const double *>(buf + ((uintptr_t)g_val & 15)) - (uint64_t)p.k0 * NN;
+      cols = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15)) - p.k0;
+      if (a.row2val) {
+        const uint32_t r0 = p.r - rl;
+        const double *g_dia = a.row2val + (uint64_t)r0 * NN;
+        dia = reinterpret_cast<const double *>(buf + S::VAL_BYTES + S::COL_BYTES + ((uintptr_t)g_dia & 15)) + rl * NN;
+      }
+    }
+    double s[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) s[q] = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p.c[u] != 0xFFFFFFFFu) block_times_vec<N>(s, vals + (uint64_t)(p.kb + sub + u * LPR) * NN, p.xv[u]);
+    }
+    // rows with more than 4*LPR blocks: remaining rounds, not pipelined
+    for (uint32_t k = p.kb + sub + 4 * LPR; k < p.ke; k += LPR) {
+      double xv[N];
+      load_x<N>(xv, a.x, cols[k]);
+      block_times_vec<N>(s, vals + (uint64_t)k * NN, xv);
+    }
+    if (p.valid && dia && sub < (unsigned)N) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) s[q] += dia[q + N * sub] * p.xo;
+    }
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], off);
+    }
+    if (p.valid && sub == 0) {
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double yv = a.alpha * s[q];
+        if (a.beta != 0.0) yv += a.beta * a.y[(uint64_t)p.r * N + q];
+        a.y[(uint64_t)p.r * N + q] = yv;
+        // x[r][q] sits in lane q of this row's group (xo); fetch it with a shuffle-free reload from L1
+        dot += __ldg(a.x + (uint64_t)p.r * N + q) * yv;
+      }
+    }
+  };
+
+#pragma unroll
+  for (int j = 0; j < NST; ++j) issue(wg + j * ws, j);
+  if (wg < n_tiles) {
+    PipePre<N> cur = prefetch(wg, 0);
+    uint32_t b = 0;
+    for (uint32_t t = wg; t < n_tiles; t += ws) {
+      const uint32_t bn = (b + 1 == NST) ? 0u : b + 1;
+      const uint32_t tn = t + ws;
+      PipePre<N> nxt;
+      const bool has_next = tn < n_tiles;
+      if (has_next) nxt = prefetch(tn, bn);
+      compute(cur, b);
+      __syncwarp();
+      issue(t + NST * ws, b);
+      if (has_next) cur = nxt;
+      b = bn;
+    }
+  }
+  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
+}
+
+template <int N, int LPR, int NST, int ML>
+static dfb_status spmv_launch_pipe(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
+  using S = PipeSmem<N, LPR, NST>;
+  static_assert(LPR >= N, "the diagonal-block columns are spread over the lanes of a row");
+  const int warps = S::WARPS;
+  const size_t smem = (size_t)warps * S::WARP_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_pipe<N, LPR, NST, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const uint64_t n_rows = a.row_end - a.row_begin;
+  const uint64_t n_tiles = (n_rows + S::RPT - 1) / S::RPT;
+  uint64_t g = (n_tiles + warps - 1) / warps;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
+  DFB_LAUNCH_ON(c, strm, (k_spmv_pipe<N, LPR, NST, ML>), (unsigned)g, warps * 32, smem, a);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// ---- variant 20: tile-packed mirror, ONE TMA bulk copy per 8-row tile.
+// Measured on the ring kernels: every additional bulk-copy operation per tile costs ~10 % (the per-SM TMA unit is busy per
+// operation, not only per byte), and row-pointer loads from DRAM sit on every warp's critical path. The packed mirror stores,
+// per tile of 8 block-rows, one contiguous 16-byte-aligned record
+//     [ u32 rowptr_rel[9] + pad : 48 B | u32 cols[nb] (pad 16) | diag 8 x NN f64 | vals nb x NN f64 (pad 16) ]
+// so a tile is fetched by a single cp.async.bulk and everything the compute phase needs (relative row pointers included)
+// arrives with it. The canonical arrays (the reference's AoS layout) stay the storage every other entry point works on;
+// the mirror is rebuilt lazily (one streaming pass, ~2 SpMV-equivalents) after the values change and lives for a whole solve.
+static const int PK_RPT = 8, PK_LPR = 4, PK_HDR = 48;
+
+template <int N>
+struct PackedCfg {
+  static constexpr int NN = N * N;
+  static constexpr int CAP = PK_RPT * 16;
+  static constexpr int BUF_BYTES = PK_HDR + ((CAP * 4 + 15) / 16) * 16 + PK_RPT * NN * 8 + ((CAP * NN * 8 + 15) / 16) * 16;
+  static constexpr int WARP_BYTES = 2 * BUF_BYTES + 16;
+  static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
+  static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
+};
+
+__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia) {
+  const uint32_t bytes = PK_HDR + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
+  return bytes >> 4;
+}
+
+__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia,
+                             uint32_t *__restrict__ tile_units) {
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
+    tile_units[t] = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia);
+  }
+}
+
+// one warp per tile: streams the tile's pieces out of the canonical arrays into its packed record
+__global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
+                                                    const double *__restrict__ idx2val, const double *__restrict__ row2val,
+                                                    uint64_t n_rows, uint64_t n_tiles, int NN, const uint32_t *__restrict__ tile_off,
+                                                    unsigned char *__restrict__ packed) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const int has_dia = row2val != nullptr;
+  for (uint64_t t = warp; t < n_tiles; t += nwarp) {
+    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
+    const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
+    unsigned char *rec = packed + (uint64_t)tile_off[t] * 16;
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(rec);
+    if (lane <= PK_RPT) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
+    if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = 0u;
+    uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
+    const uint32_t ncol_pad = ((nb * 4u + 15u) & ~15u) / 4u;
+    for (uint32_t k = lane; k < ncol_pad; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
+    double *dia = reinterpret_cast<double *>(rec + PK_HDR + ncol_pad * 4u);
+    if (has_dia) {
+      const uint32_t nd = (uint32_t)(r1 - r0) * NN;
+      for (uint32_t q = lane; q < (uint32_t)(PK_RPT * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
+    }
+    double *vals = dia + (has_dia ? PK_RPT * NN : 0);
+    const uint32_t nv = nb * NN, nv_pad = (((nb * NN * 8u) + 15u) & ~15u) / 8u;
+    const double *src = idx2val + (uint64_t)k0 * NN;
+    for (uint32_t q = lane; q < nv_pad; q += 32) vals[q] = (q < nv) ? src[q] : 0.0;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const SpmvArgs a, const unsigned char *__restrict__ packed,
+                                                                         const uint32_t *__restrict__ tile_off, int has_dia) {
+  using S = PackedCfg<N>;
+  constexpr int NN = N * N, RPT = PK_RPT, LPR = PK_LPR;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned sub = lane % LPR, rl = lane / LPR;
+  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
+  const uint32_t bar0 = smem_u32(wbase + 2 * S::BUF_BYTES);
+  const unsigned long long pol = policy_evict_first();
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint32_t t_begin = a.row_begin / RPT, t_end = (a.row_end + RPT - 1) / RPT;
+  const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
+
+  struct Off {
+    uint32_t o0, o1;
+  };
+  auto offs = [&](uint32_t t) -> Off {
+    Off o = {0u, 0u};
+    if (t < t_end) {
+      o.o0 = __ldg(tile_off + t);
+      o.o1 = __ldg(tile_off + t + 1);
+    }
+    return o;
+  };
+  auto issue = [&](uint32_t t, uint32_t b, Off o) {
+    if (lane != 0 || t >= t_end) return;
+    const uint32_t bytes = (o.o1 - o.o0) << 4;
+    if (bytes > (uint32_t)S::BUF_BYTES) return;
+    const uint32_t bar = bar0 + 8 * b;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(wbase + (size_t)b * S::BUF_BYTES)),
+                 "l"(packed + ((uint64_t)o.o0 << 4)), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+  };
+
+  Off q0 = offs(t_begin + wg), q1 = offs(t_begin + wg + ws), q2 = offs(t_begin + wg + 2 * ws);
+  issue(t_begin + wg, 0, q0);
+  issue(t_begin + wg + ws, 1, q1);
+  uint32_t phase0 = 0u, phase1 = 0u, b = 0u;
+  double dot = 0.0;
+  double dzero[N];
+#pragma unroll
+  for (int qq = 0; qq < N; ++qq) dzero[qq] = 0.0;
+  for (uint32_t t = t_begin + wg; t < t_end; t += ws) {
+    const Off qn = offs(t + 3 * ws);  // requested now, used at the end of the next iteration
+    const uint32_t r = t * RPT + rl;
+    const bool valid = r >= a.row_begin && r < a.row_end;
+    const uint32_t bytes = (q0.o1 - q0.o0) << 4;
+    if (bytes <= (uint32_t)S::BUF_BYTES) {
+      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
+      const uint32_t bar = bar0 + 8 * b;
+      const uint32_t ph = b ? phase1 : phase0;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "PK_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra PK_DONE;\n"
+          "bra PK_WAIT;\n"
+          "PK_DONE:\n"
+          "}\n" ::"r"(bar),
+          "r"(ph)
+          : "memory");
+      if (b) phase1 ^= 1u;
+      else phase0 ^= 1u;
+      const uint32_t *hdr = reinterpret_cast<const uint32_t *>(buf);
+      const uint32_t nb = hdr[RPT];
+      const uint32_t kb = hdr[rl], ke = hdr[rl + 1];
+      const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + PK_HDR);
+      const double *sd0 = reinterpret_cast<const double *>(buf + PK_HDR + ((nb * 4u + 15u) & ~15u));
+      const double *sv = sd0 + (has_dia ? RPT * NN : 0);
+      dot += ring_row<N, LPR>(a, sv, sc, has_dia ? sd0 + rl * NN : nullptr, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
+    } else {
+      // oversized tile: straight from the canonical arrays
+      const uint32_t kb = valid ? a.row2idx[r] : 0u, ke = valid ? a.row2idx[r + 1] : 0u;
+      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, (valid && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
+                              dzero, 0.0);
+    }
+    __syncwarp();
+    issue(t + 2 * ws, b, q2);
+    q0 = q1;
+    q1 = q2;
+    q2 = qn;
+    b ^= 1u;
+  }
+  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
+}
+
+// (re)build the packed mirror of m on the stream
+static dfb_status bsr_pack(dfb_bsr *m, cudaStream_t strm) {
+  dfb_ctx *c = m->ctx;
+  const uint64_t n = m->pat->num_blk;
+  const int NN = m->blk_dim * m->blk_dim;
+  const int has_dia = m->d_row2val != nullptr;
+  const uint64_t n_tiles = (n + PK_RPT - 1) / PK_RPT;
+  if (!m->d_tile_off) {
+    // the layout only depends on the pattern: sizes -> scan once
+    DFB_TRY(dfb_dev_alloc_t(&m->d_tile_off, n_tiles + 2));
+    DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, m->d_tile_off);
+    DFB_CHECK_LAUNCH();
+    uint64_t total_units = 0;
+    DFB_TRY(dfb_exclusive_scan_u32(c, m->d_tile_off, n_tiles, &total_units));
+    m->n_tiles = n_tiles;
+    m->packed_cap = total_units * 16 + 256;
+    DFB_TRY(dfb_dev_alloc((void **)&m->d_packed, m->packed_cap));
+  }
+  if (n_tiles > 0) {
+    DFB_LAUNCH_ON(c, strm, k_pack_tiles, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val, n,
+                  n_tiles, NN, m->d_tile_off, m->d_packed);
+    DFB_CHECK_LAUNCH();
+  }
+  m->packed_valid = 1;
+  return DFB_OK;
+}
+
+template <int N>
+static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bsr *m, cudaStream_t strm) {
+  using S = PackedCfg<N>;
+  const int warps = S::WARPS;
+  const size_t smem = (size_t)warps * S::WARP_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const uint64_t t_begin = a.row_begin / PK_RPT, t_end = ((uint64_t)a.row_end + PK_RPT - 1) / PK_RPT;
+  uint64_t g = (t_end - t_begin + warps - 1) / warps;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
+  DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 template <int N>
 static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
   switch (c->spmv_variant) {
@@ -763,6 +1219,12 @@ static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm
     case 7: return spmv_launch_ring<N, 4, 2, false, true, true>(c, a, strm);
     case 8: return spmv_launch_ring<N, 4, 2, true, true, true>(c, a, strm);
     case 9: return spmv_launch_ring<N, 4, 2, false, false, false>(c, a, strm);  // LPR must be >= N here
+    case 12: return spmv_launch_pipe<N, 4, 3, 0>(c, a, strm);
+    case 13: return spmv_launch_pipe<N, 4, 4, 0>(c, a, strm);
+    case 14: return spmv_launch_pipe<N, 4, 2, 0>(c, a, strm);
+    case 15: return spmv_launch_pipe<N, 4, 2, 4>(c, a, strm);
+    case 16: return spmv_launch_pipe<N, 4, 3, 4>(c, a, strm);
+    case 17: return spmv_launch_pipe<N, 4, 4, 4>(c, a, strm);
     default: break;
   }
   const uint64_t n_rows = a.row_end - a.row_begin;
@@ -816,6 +1278,16 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   if (fuse_dot && !a.st) return dfb_fail(DFB_ERR_BAD_ARG, "spmv: fused dot needs the solver state");
   a.partials = c->d_partials;
   a.ticket = c->d_ticket + 1;
+  if (c->spmv_variant == 20) {
+    dfb_bsr *mm = const_cast<dfb_bsr *>(m);
+    if (!mm->packed_valid) DFB_TRY(bsr_pack(mm, strm));
+    switch (m->blk_dim) {
+      case 1: return spmv_launch_packed<1>(c, a, m, strm);
+      case 2: return spmv_launch_packed<2>(c, a, m, strm);
+      case 3: return spmv_launch_packed<3>(c, a, m, strm);
+      case 4: return spmv_launch_packed<4>(c, a, m, strm);
+    }
+  }
   switch (m->blk_dim) {
     case 1: return spmv_dispatch<1>(c, a, strm);
     case 2: return spmv_dispatch<2>(c, a, strm);

@@ -87,7 +87,7 @@ struct dfb_ctx {
   void *flush_buf = nullptr;
   size_t flush_bytes = 0;
   // options
-  int64_t spmv_variant = 4;
+  int64_t spmv_variant = 20;
   int64_t iters_per_sync = 16;
   int64_t use_graph = 0;
   int64_t assemble_variant = 0;
@@ -158,6 +158,12 @@ struct dfb_bsr {
   uint64_t flag_cap;
   dfb_halo *halo;
   uint64_t int_begin, int_end;
+  // tile-packed mirror for the SpMV (built lazily, invalidated by every mutation of the values)
+  unsigned char *d_packed = nullptr;
+  uint32_t *d_tile_off = nullptr;   // [n_tiles + 1], in 16-byte units
+  uint64_t packed_cap = 0;          // bytes allocated
+  uint64_t n_tiles = 0;
+  int packed_valid = 0;
 };
 
 struct dfb_plan {

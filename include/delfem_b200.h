@@ -76,9 +76,9 @@ dfb_status dfb_ctx_destroy(dfb_ctx *ctx);
 dfb_status dfb_ctx_sync(dfb_ctx *ctx);
 /* number of CUDA kernels this ctx has launched so far (graph replays count their kernel nodes) */
 dfb_status dfb_ctx_launch_count(dfb_ctx *ctx, uint64_t *out);
-/* tuning knobs: "spmv_variant" (0 row-per-thread, 1 warp-tile cp.async, 2 warp-tile TMA, 3/4/5 double-buffered TMA ring
-   with 2/4/8 lanes per row; default 4), "iters_per_sync" (PCG iterations between convergence polls), "profile_spmv",
-   "spmv_ctas_per_sm" */
+/* tuning knobs: "spmv_variant" (20 = tile-packed mirror, one TMA bulk copy per 8-row tile [default]; 4 = TMA ring over the
+   canonical arrays, no extra memory; 0 row-per-thread, 1 warp-tile cp.async, 2 warp-tile TMA, 3..17 experiments, see
+   profiles/README.md), "iters_per_sync" (PCG iterations between convergence polls), "profile_spmv" */
 dfb_status dfb_ctx_set_option(dfb_ctx *ctx, const char *key, int64_t value);
 dfb_status dfb_ctx_get_option(dfb_ctx *ctx, const char *key, int64_t *value);
 /* CUDA-event timing on the ctx stream (events are recorded on the stream the kernels are launched on) */

@@ -13,7 +13,7 @@ from helpers import device_elasticity_problem, flags_z0, oracle_elasticity_probl
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8]  # 9 (diagonal from global) is N<=4/LPR=4 only, covered below
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 20]
 
 
 # ------------------------------------------------------------------------------------------------ mesh / pattern / plan
@@ -239,7 +239,7 @@ def test_mult_vec_matches_oracle(dfb, ctx, orc, n, variant):
             mat.mult_vec(yd, beta, alpha, xd)
             assert rel_err(yd.download(), y) < 1e-13
     finally:
-        ctx.set_option("spmv_variant", 4)
+        ctx.set_option("spmv_variant", 20)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -270,7 +270,7 @@ def test_mult_vec_blkcsr_and_ragged_rows(dfb, ctx, orc, variant):
             want = (B @ x.reshape(-1)).reshape(nb, 3)
             assert rel_err(y.download(), want) < 1e-13
     finally:
-        ctx.set_option("spmv_variant", 4)
+        ctx.set_option("spmv_variant", 20)
 
 
 def test_ls_smoke_pattern(dfb, ctx, orc):
@@ -376,7 +376,7 @@ def test_cg_matches_oracle(dfb, ctx, orc, n_mesh, variant):
         # r is overwritten with the final (recursive) residual like the reference
         assert rel_err(rd.download(), prob["rhs"] - ax) < 1e-4
     finally:
-        ctx.set_option("spmv_variant", 4)
+        ctx.set_option("spmv_variant", 20)
 
 
 @pytest.mark.parametrize("kind", ["jacobi", "block_jacobi"])
@@ -510,7 +510,7 @@ def test_full_size_properties(dfb, ctx, orc, size):
         results.append(ya.download())
         s1, s2 = b.dot(ya), a.dot(yb)
         assert abs(s1 - s2) <= 1e-11 * abs(s1)
-    ctx.set_option("spmv_variant", 4)
+    ctx.set_option("spmv_variant", 20)
     assert all(rel_err(r, results[0]) < 1e-14 for r in results[1:])
     # config-2 solve
     flag = synthetic.clamp_flags_z0(n, n, n)
