@@ -190,6 +190,10 @@ def run_ours(args):
         uid = [dfb.Ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
+        if not args.no_peer:  # NVLink peer mailboxes: the PCG scalars are all-reduced inside the PCG kernels, not by NCCL
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_export())
+            ctx.peer_import(handles)
     ctx.set_option("spmv_variant", args.spmv_variant)
     ctx.set_option("iters_per_sync", args.iters_per_sync)
     ctx.set_option("profile_spmv", 1)
@@ -314,7 +318,7 @@ def run_ours(args):
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {nx}x{ny}x{nz}-vertex Kuhn tet cube, {n_dof_total} DoF, linear elasticity (lambda=mu=1), "
                                       f"z=0 clamped, rhs=-K*u0(splitmix seed 0), {args.precond}-PCG to 1e-8",
-                          "partition": f"{world} z-slab(s)", "precond": args.precond, "spmv_variant": args.spmv_variant,
+                          "partition": f"{world} z-slab(s)", "scalar_allreduce": ("nvlink peer mailbox (fused in kernels)" if (world > 1 and not args.no_peer) else ("nccl" if world > 1 else "none")), "precond": args.precond, "spmv_variant": args.spmv_variant,
                           "l2_note": "matrix (3.6 GB/rank at S10) >> 126 MB L2: no flush needed between iterations"},
                "assembly_ms": asm_total / args.steps, "pcg_ms": (total_ms - asm_total) / args.steps, "pcg_iters": iters[0],
                "final_rel_residual": final_rel, "wall_s_timed_region": t_wall,
@@ -369,6 +373,7 @@ def main():
     ap.add_argument("--precond", default="jacobi", choices=["jacobi", "block_jacobi"])
     ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "20")))
     ap.add_argument("--iters-per-sync", type=int, default=32)
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU: use ncclAllReduce for the PCG scalars instead of the peer mailboxes")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -144,6 +144,8 @@ def lib():
         "dfb_pcg": [_vp, _vp, _vp, _vp, _vp, _vp, _f64, _u64, _f64, _vp, _u64, C.POINTER(_u64)],
         "dfb_comm_unique_id": [_vp],
         "dfb_ctx_comm_init": [_vp, _vp, _i32, _i32],
+        "dfb_ctx_peer_export": [_vp, _vp],
+        "dfb_ctx_peer_import": [_vp, _vp, _i32],
         "dfb_halo_create": [_vp, _i32, _vp, _vp, _vp, _vp, _pp],
         "dfb_halo_destroy": [_vp],
         "dfb_halo_exchange": [_vp, _vp],

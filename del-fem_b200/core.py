@@ -89,6 +89,18 @@ class Ctx:
         check(lib().dfb_ctx_comm_init(self.h, buf, rank, nranks))
         self.rank, self.nranks = rank, nranks
 
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's scalar mailbox"""
+        buf = (C.c_uint8 * 64)()
+        check(lib().dfb_ctx_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_import(self, handles):
+        """handles: list of the nranks exported handles, in rank order"""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().dfb_ctx_peer_import(self.h, buf, len(handles)))
+
     @staticmethod
     def comm_unique_id() -> bytes:
         buf = (C.c_uint8 * 128)()

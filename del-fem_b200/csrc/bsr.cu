@@ -285,6 +285,7 @@ struct SpmvArgs {
   DfbSolverState *st;  // nullptr outside the solvers
   double *partials;
   unsigned int *ticket;
+  DfbPeerView pv;      // pv.seq != 0 (and nranks > 1): the launch that completes p.Ap posts it to every peer's mailbox
 };
 
 template <int N>
@@ -336,6 +337,10 @@ __device__ __forceinline__ void spmv_publish_dot(const SpmvArgs &a, double d, do
   if (grid_sum_last_block<1>(acc, a.partials, a.ticket, s_buf) && threadIdx.x == 0) {
     if (a.fuse_dot == 2) a.st->red[0] += acc[0];
     else a.st->red[0] = acc[0];
+    if (a.pv.nranks > 1 && a.pv.seq != 0) {
+      const double total = a.st->red[0];
+      peer_post<1>(a.pv, &total);
+    }
   }
 }
 
@@ -1259,7 +1264,7 @@ static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm
 
 // internal launcher shared with the solvers
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm) {
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq) {
   dfb_ctx *c = m->ctx;
   SpmvArgs a;
   a.row2idx = m->pat->d_row2idx;
@@ -1278,6 +1283,7 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   if (fuse_dot && !a.st) return dfb_fail(DFB_ERR_BAD_ARG, "spmv: fused dot needs the solver state");
   a.partials = c->d_partials;
   a.ticket = c->d_ticket + 1;
+  a.pv = dfb_peer_view(c, post_seq);
   if (c->spmv_variant == 20) {
     dfb_bsr *mm = const_cast<dfb_bsr *>(m);
     if (!mm->packed_valid) DFB_TRY(bsr_pack(mm, strm));
@@ -1298,30 +1304,33 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
 }
 
 // y <- alpha*A*x + beta*y  with halo exchange of x (overlapped with the interior rows) when a halo is attached
-dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity) {
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity,
+                         unsigned long long post_seq) {
   dfb_ctx *c = m->ctx;
   const uint64_t n = m->pat->num_blk;
-  if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream);
+  if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq);
   // comm stream: wait until x is final, exchange ghosts
   DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
   DFB_CUDA(cudaStreamWaitEvent(c->stream_comm, c->ev_a, 0));
   DFB_TRY(dfb_halo_exchange_on(m->halo, x, n, m->blk_dim, c->stream_comm));
   DFB_CUDA(cudaEventRecord(c->ev_b, c->stream_comm));
-  // interior rows do not read ghosts
+  // interior rows do not read ghosts; the launch that completes the fused dot product also posts it to the peers
+  const bool has_lo = m->int_begin > 0, has_hi = m->int_end < n, has_int = m->int_end > m->int_begin;
   int mode = fuse_dot;
-  if (m->int_end > m->int_begin) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_begin, m->int_end, mode, parity, c->stream));
+  if (has_int) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_begin, m->int_end, mode, parity, c->stream, (!has_lo && !has_hi) ? post_seq : 0));
     if (mode == 1) mode = 2;
   }
   DFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-  if (m->int_begin > 0) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, m->int_begin, mode, parity, c->stream));
+  if (has_lo) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, m->int_begin, mode, parity, c->stream, !has_hi ? post_seq : 0));
     if (mode == 1) mode = 2;
   }
-  if (m->int_end < n) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_end, n, mode, parity, c->stream));
+  if (has_hi) {
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_end, n, mode, parity, c->stream, post_seq));
     if (mode == 1) mode = 2;
   }
+  if (!has_int && !has_lo && !has_hi && fuse_dot) DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, 0, fuse_dot, parity, c->stream, post_seq));
   return DFB_OK;
 }
 
@@ -1330,7 +1339,7 @@ DFB_API dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, d
   DFB_REQUIRE(y->n_blk == m->pat->num_blk && x->n_blk == m->pat->num_blk, "dfb_bsr_mult_vec: y/x length != num_blk (assert_eq!(y_vec.len(), self.num_blk))");
   DFB_REQUIRE(y->blk_dim == m->blk_dim && x->blk_dim == m->blk_dim, "dfb_bsr_mult_vec: vector block dim != matrix block dim");
   DFB_REQUIRE(x->d != y->d, "dfb_bsr_mult_vec: x and y alias");
-  return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, -1);
+  return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, -1, 0);
 }
 
 DFB_API dfb_status dfb_bsr_set_halo(dfb_bsr *m, dfb_halo *h, uint64_t int_begin, uint64_t int_end) {

@@ -118,6 +118,7 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "assemble_variant")) return &c->assemble_variant;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
+  if (!strcmp(key, "use_peer_allreduce")) return &c->use_peer_allreduce;
   return nullptr;
 }
 

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/delfem_b200.h"
+#include "peer.cuh"
 
 #define DFB_API extern "C" __attribute__((visibility("default")))
 
@@ -101,7 +102,23 @@ struct dfb_ctx {
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer mailboxes (NVLink P2P scalar all-reduce fused into the PCG kernels)
+  DfbMailbox *d_mbox = nullptr;                 // local, IPC-exported
+  DfbMailbox *peer_mbox[DFB_MAX_RANKS] = {};    // mapped peers (own entry = d_mbox)
+  int peer_enabled = 0;
+  unsigned long long peer_seq = 0;
+  int64_t use_peer_allreduce = 1;               // option: 0 forces NCCL all-reduce even when mailboxes are mapped
 };
+
+// view handed to kernels; seq = 0 disables the exchange for that launch
+static inline DfbPeerView dfb_peer_view(const dfb_ctx *c, unsigned long long seq) {
+  DfbPeerView pv;
+  pv.rank = c->rank;
+  pv.nranks = (c->peer_enabled && c->use_peer_allreduce && c->nranks > 1) ? c->nranks : 1;
+  pv.seq = seq;
+  for (int r = 0; r < DFB_MAX_RANKS; ++r) pv.mbox[r] = c->peer_mbox[r];
+  return pv;
+}
 
 struct dfb_vec {
   dfb_ctx *ctx;
@@ -200,6 +217,6 @@ dfb_status dfb_exclusive_scan_u32(dfb_ctx *ctx, uint32_t *d_data, uint64_t n, ui
 dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaStream_t strm);
 dfb_status dfb_halo_exchange_on(dfb_halo *h, double *d_vec, uint64_t n_blk, int blk_dim, cudaStream_t strm);
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm);
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq = 0);
 
 static inline int dfb_div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }

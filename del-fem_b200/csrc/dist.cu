@@ -91,6 +91,42 @@ dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaSt
   return DFB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ peer mailboxes
+DFB_API dfb_status dfb_ctx_peer_export(dfb_ctx *ctx, uint8_t handle_out[64]) {
+  DFB_REQUIRE(ctx && handle_out, "dfb_ctx_peer_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->d_mbox) {
+    DFB_CUDA(cudaMalloc((void **)&ctx->d_mbox, sizeof(DfbMailbox)));
+    DFB_CUDA(cudaMemset(ctx->d_mbox, 0, sizeof(DfbMailbox)));
+  }
+  cudaIpcMemHandle_t h;
+  DFB_CUDA(cudaIpcGetMemHandle(&h, ctx->d_mbox));
+  memcpy(handle_out, &h, 64);
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_ctx_peer_import(dfb_ctx *ctx, const uint8_t *handles, int32_t nranks) {
+  DFB_REQUIRE(ctx && handles, "dfb_ctx_peer_import: NULL argument");
+  DFB_REQUIRE(nranks == ctx->nranks && nranks <= DFB_MAX_RANKS, "dfb_ctx_peer_import: nranks %d does not match the communicator (%d, max %d)",
+              nranks, ctx->nranks, DFB_MAX_RANKS);
+  DFB_REQUIRE(ctx->d_mbox, "dfb_ctx_peer_import: call dfb_ctx_peer_export first");
+  DFB_CUDA(cudaSetDevice(ctx->device));
+  for (int r = 0; r < nranks; ++r) {
+    if (r == ctx->rank) {
+      ctx->peer_mbox[r] = ctx->d_mbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    void *p = nullptr;
+    DFB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_mbox[r] = (DfbMailbox *)p;
+  }
+  ctx->peer_enabled = 1;
+  return DFB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ halo
 __global__ void k_halo_pack(const double *__restrict__ v, const uint32_t *__restrict__ idx, uint64_t n_send, int dim,
                             double *__restrict__ buf) {

@@ -1,0 +1,72 @@
+// peer.cuh — scalar all-reduce fused into the producing / consuming kernels over NVLink peer memory.
+// Every rank owns a small "mailbox" in its own HBM, IPC-mapped into all peers. The last block of a reducing kernel writes
+// its rank's partial sums straight into every peer's mailbox (plain NVLink stores) and then releases a sequence flag;
+// the consuming kernel's blocks acquire the R flags of their LOCAL mailbox and add the R partials in rank order, so every
+// rank obtains the bit-identical total without a collective launch (NCCL all-reduce: ~2 x 25 us per PCG iteration).
+// Spins are bounded (about 2 s): a lost peer raises an error flag instead of hanging the GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+static const int DFB_MAX_RANKS = 8;
+static const int DFB_MBOX_SLOTS = 4;
+
+struct DfbMailbox {
+  double val[DFB_MBOX_SLOTS][DFB_MAX_RANKS][4];
+  unsigned long long flag[DFB_MBOX_SLOTS][DFB_MAX_RANKS];
+};
+
+struct DfbPeerView {
+  int rank;
+  int nranks;                      // <= 1: peer path disabled
+  unsigned long long seq;          // sequence number of THIS exchange (0: none)
+  DfbMailbox *mbox[DFB_MAX_RANKS];  // mbox[rank] is local
+};
+
+// called by ONE thread: publish K partial sums of this rank to every rank (including itself)
+template <int K>
+__device__ __forceinline__ void peer_post(const DfbPeerView &pv, const double *vals) {
+  const int slot = (int)(pv.seq % DFB_MBOX_SLOTS);
+  for (int r = 0; r < pv.nranks; ++r) {
+    DfbMailbox *mb = pv.mbox[r];
+#pragma unroll
+    for (int k = 0; k < K; ++k) mb->val[slot][pv.rank][k] = vals[k];
+  }
+  for (int r = 0; r < pv.nranks; ++r) {
+    unsigned long long *f = &pv.mbox[r]->flag[slot][pv.rank];
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(pv.seq) : "memory");
+  }
+}
+
+// called by ALL threads of a block (blockDim.x >= nranks): wait for the R partials of exchange pv.seq in the local mailbox
+// and return their sum in rank order (identical on every rank). *err is set to 2 on timeout.
+template <int K>
+__device__ __forceinline__ void peer_gather(const DfbPeerView &pv, double (&out)[K], int *err) {
+  const int slot = (int)(pv.seq % DFB_MBOX_SLOTS);
+  DfbMailbox *mb = pv.mbox[pv.rank];
+  if ((int)threadIdx.x < pv.nranks) {
+    const unsigned long long *f = &mb->flag[slot][threadIdx.x];
+    unsigned long long v = 0;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v == pv.seq) break;
+      if (clock64() - t0 > 4000000000ll) {
+        *err = 2;
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = 0.0;
+  for (int r = 0; r < pv.nranks; ++r) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double v;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(&mb->val[slot][r][k]) : "memory");
+      out[k] += v;
+    }
+  }
+}

@@ -16,7 +16,8 @@
 #include "dfb_internal.h"
 #include "reduce.cuh"
 
-dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity);
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity,
+                         unsigned long long post_seq);
 bool dfb_prof_begin(dfb_ctx *c);
 void dfb_prof_end(dfb_ctx *c);
 dfb_status dfb_prof_flush(dfb_ctx *c, size_t max_pairs);
@@ -217,7 +218,7 @@ DFB_API dfb_status dfb_precond_destroy(dfb_precond *pc) {
 template <int N, int KIND>
 __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, double *__restrict__ x, double *__restrict__ p,
                                                   const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
-                                                  double *partials, unsigned int *ticket) {
+                                                  double *partials, unsigned int *ticket, const DfbPeerView pv_out) {
   __shared__ double s_buf[64];
   double acc[2] = {0.0, 0.0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -236,22 +237,28 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, 
   if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
     st->red[1] = acc[0];
     st->red[2] = acc[1];
+    if (pv_out.nranks > 1 && pv_out.seq != 0) peer_post<2>(pv_out, acc);
   }
 }
 
 // after the (all-reduced) initial dots: set up the state. hist[0] = r0.r0
-__global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol, double eps_sq, int check_pap) {
-  const double rr0 = st->red[1];
+__global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol, double eps_sq, int check_pap,
+                                    const DfbPeerView pv_in) {
+  double g[2] = {st->red[1], st->red[2]};
+  int perr = 0;
+  if (pv_in.nranks > 1 && pv_in.seq != 0) peer_gather<2>(pv_in, g, &perr);
+  if (threadIdx.x != 0) return;
+  const double rr0 = g[0];
   st->rr0 = rr0;
   st->inv_rr0 = 1.0 / rr0;
-  st->rho[0] = st->red[2];
+  st->rho[0] = g[1];
   st->rho[1] = 0.0;
   st->tol = tol;
   st->eps_sq = eps_sq;
   st->done[0] = (rr0 < eps_sq) ? 1 : 0;
   st->done[1] = st->done[0];
   st->iter = 0;
-  st->err = 0;
+  st->err = perr;
   st->check_pap = check_pap;
   hist[0] = rr0;
 }
@@ -261,10 +268,16 @@ template <int N, int KIND>
 __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
                                                     const double *__restrict__ p, const double *__restrict__ inv,
                                                     uint64_t num_blk, DfbSolverState *st, int parity, double *partials,
-                                                    unsigned int *ticket) {
+                                                    unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
   __shared__ double s_buf[64];
   if (st->done[parity]) return;
-  const double pq = st->red[0];
+  double pq = st->red[0];
+  if (pv_in.nranks > 1) {
+    double g[1];
+    peer_gather<1>(pv_in, g, &st->err);
+    pq = g[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->red[0] = pq;
+  }
   const double alpha = st->rho[parity] / pq;
   double acc[2] = {0.0, 0.0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -285,6 +298,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, doub
   if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
     st->red[1] = acc[0];
     st->red[2] = acc[1];
+    if (pv_out.nranks > 1) peer_post<2>(pv_out, acc);
   }
 }
 
@@ -292,13 +306,19 @@ __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, doub
 template <int N, int KIND>
 __global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict__ r, double *__restrict__ p,
                                                        const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
-                                                       int parity, double *hist, uint64_t hist_cap) {
+                                                       int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
   if (st->done[parity]) {
     // converged earlier: propagate the flag into the slot the next iteration reads, change nothing else
     if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
     return;
   }
-  const double rr = st->red[1], rz = st->red[2];
+  double rr = st->red[1], rz = st->red[2];
+  if (pv_in.nranks > 1) {
+    double g[2];
+    peer_gather<2>(pv_in, g, &st->err);
+    rr = g[0];
+    rz = g[1];
+  }
   const double beta = rz / st->rho[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const int it = st->iter + 1;
@@ -329,10 +349,17 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
                                                          const double *__restrict__ p, const double *__restrict__ inv,
                                                          uint64_t n, DfbSolverState *st, int parity, double *partials,
-                                                         unsigned int *ticket) {
+                                                         unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
   __shared__ double s_buf[64];
   if (st->done[parity]) return;
-  const double alpha = st->rho[parity] / st->red[0];
+  double pq = st->red[0];
+  if (pv_in.nranks > 1) {
+    double g[1];
+    peer_gather<1>(pv_in, g, &st->err);
+    pq = g[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->red[0] = pq;
+  }
+  const double alpha = st->rho[parity] / pq;
   double acc[2] = {0.0, 0.0};
   const uint64_t n2 = n >> 1;
   double2 *r2 = reinterpret_cast<double2 *>(r);
@@ -370,18 +397,25 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
   if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
     st->red[1] = acc[0];
     st->red[2] = acc[1];
+    if (pv_out.nranks > 1) peer_post<2>(pv_out, acc);
   }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__restrict__ r, double *__restrict__ p,
                                                             const double *__restrict__ inv, uint64_t n, DfbSolverState *st,
-                                                            int parity, double *hist, uint64_t hist_cap) {
+                                                            int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
   if (st->done[parity]) {
     if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
     return;
   }
-  const double rr = st->red[1], rz = st->red[2];
+  double rr = st->red[1], rz = st->red[2];
+  if (pv_in.nranks > 1) {
+    double g[2];
+    peer_gather<2>(pv_in, g, &st->err);
+    rr = g[0];
+    rz = g[1];
+  }
   const double beta = rz / st->rho[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const int it = st->iter + 1;
@@ -460,12 +494,18 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   const int GF = vec_grid(c, (nflat + 1) / 2);
   DfbSolverState *st = c->d_state;
 
-#define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2)
+  // scalar all-reduces: fused into the kernels through the NVLink peer mailboxes when mapped, NCCL otherwise
+  const bool peer = c->peer_enabled && c->use_peer_allreduce && c->nranks > 1;
+  const bool nccl_red = c->nranks > 1 && !peer;
+  const DfbPeerView pv_none = dfb_peer_view(c, 0);
+  DfbPeerView pv_i = peer ? dfb_peer_view(c, ++c->peer_seq) : pv_none;
+  if (!peer) pv_i.nranks = 1;
+#define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2, pv_i)
   DISPATCH_ALL(INIT)
 #undef INIT
   DFB_CHECK_LAUNCH();
-  if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
-  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 1, 0, st, c->d_hist, tol, eps_sq, check_pap);
+  if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 32, 0, st, c->d_hist, tol, eps_sq, check_pap, pv_i);
   DFB_CHECK_LAUNCH();
 
   FlagsHost *hf = (FlagsHost *)c->h_pinned;  // two slots
@@ -480,27 +520,33 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     for (uint64_t j = 0; j < todo; ++j) {
       const int parity = (int)((enq + j) & 1);
       const bool prof = dfb_prof_begin(c);
-      DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity));
+      DfbPeerView pv_a = pv_none, pv_b = pv_none;  // a: p.Ap (K1 -> K2), b: r.r, r.z (K2 -> K3)
+      pv_a.nranks = pv_b.nranks = 1;
+      if (peer) {
+        pv_a = dfb_peer_view(c, ++c->peer_seq);
+        pv_b = dfb_peer_view(c, ++c->peer_seq);
+      }
+      DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity, peer ? pv_a.seq : 0));
       if (prof) dfb_prof_end(c);
-      if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
+      if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
       if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2)
+#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b)
         DISPATCH_ALL(UPD)
 #undef UPD
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b);
       } else {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b);
       }
-      if (c->nranks > 1) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+      if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
       if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap)
+#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap, pv_b)
         DISPATCH_ALL(DIR)
 #undef DIR
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_b);
       } else {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_b);
       }
     }
     DFB_CHECK_LAUNCH();
@@ -528,6 +574,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     last = hf[slot];
   }
   DFB_TRY(dfb_prof_flush(c, (size_t)last.iter));
+  if (last.err == 2) return dfb_fail(DFB_ERR_NCCL, "(p)cg: peer mailbox all-reduce timed out (a rank is missing or out of step)");
   if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
 
   // history: the device stored ||r_k||^2 for k = 0..iter

@@ -222,6 +222,11 @@ dfb_status dfb_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, dfb_vec 
  * that the distributed assembly + PCG equals the single-domain result. */
 dfb_status dfb_comm_unique_id(uint8_t id_out[128]);
 dfb_status dfb_ctx_comm_init(dfb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* Optional: NVLink peer "mailboxes" (one process per GPU on one node). Each rank exports a 64-byte CUDA IPC handle, all ranks
+   exchange them (any transport) and import the full table; (P)CG then all-reduces its scalars inside its own kernels through peer
+   memory instead of calling ncclAllReduce twice per iteration. Without this call the NCCL path is used. */
+dfb_status dfb_ctx_peer_export(dfb_ctx *ctx, uint8_t handle_out[64]);
+dfb_status dfb_ctx_peer_import(dfb_ctx *ctx, const uint8_t *handles /* nranks x 64 */, int32_t nranks);
 /* halo of a vector: for each peer p, owned blocks send_idx[send_ptr[p]..send_ptr[p+1]) are sent to rank peers[p],
    and ghost blocks [recv_ptr[p], recv_ptr[p+1]) (offsets into the ghost tail) are received from it. */
 dfb_status dfb_halo_create(dfb_ctx *ctx, int32_t n_peers, const int32_t *peers, const uint64_t *send_ptr,

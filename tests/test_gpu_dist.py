@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, out_dir, variant):
+def _worker(rank, world, port, shape, out_dir, variant, use_peer):
     import sys
     sys.path.insert(0, ROOT)
     import torch
@@ -35,6 +35,10 @@ def _worker(rank, world, port, shape, out_dir, variant):
     uid = [dfb.Ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
+    if use_peer:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export())
+        ctx.peer_import(handles)
     ctx.set_option("spmv_variant", variant)
     nx, ny, nz = shape
     prob = Problem(dfb, ctx, nx, ny, nz, rank, world, "jacobi")
@@ -51,15 +55,16 @@ def _worker(rank, world, port, shape, out_dir, variant):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("variant", [0, 4])
+@pytest.mark.parametrize("use_peer", [False, True])
+@pytest.mark.parametrize("variant", [0, 4, 20])
 @pytest.mark.parametrize("shape", [(9, 8, 20)])
-def test_two_gpu_pcg_equals_single_gpu(tmp_path, dfb, shape, variant):
+def test_two_gpu_pcg_equals_single_gpu(tmp_path, dfb, shape, variant, use_peer):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path), variant), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path), variant, use_peer), nprocs=world, join=True)
     from del_fem_b200.workload import Problem
     ctx = dfb.Ctx(0)
     ctx.set_option("spmv_variant", variant)
