@@ -288,6 +288,7 @@ DFB_API dfb_status dfb_plan_destroy(dfb_plan *p) {
   cudaStreamSynchronize(p->ctx->stream);
   cudaFree(p->d_nz2ptr);
   cudaFree(p->d_contrib);
+  cudaFree(p->d_geo);
   dfb_pattern_destroy(p->pat);
   delete p;
   return DFB_OK;
@@ -357,6 +358,177 @@ __global__ void __launch_bounds__(128) k_assemble_fused(const uint32_t *__restri
   }
 }
 
+// ---- node records: the per-(element, node) quarter of the element geometry, one aligned 32-byte sector each, so that a
+// contribution (e,i,j) needs exactly two sectors (two pairs of 128-bit loads). The block formulas repeat ElemGeo<KIND>::block
+// operation for operation (bit-identical results).
+struct __align__(32) NodeRec {
+  double v[4];
+};
+
+template <int KIND> struct NodeOps;  // make(geo, i) -> NodeRec ; block(ri, rj, p0, p1, e)
+
+template <> struct NodeOps<DFB_ELEM_LAPLACE_TRI2> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_LAPLACE_TRI2> &g, int i) { return {{g.dldx[0][i], g.dldx[1][i], g.area, 0.0}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double alpha, double, double *e) {
+    e[0] = alpha * a.v[2] * (a.v[0] * b.v[0] + a.v[1] * b.v[1]);
+  }
+};
+template <> struct NodeOps<DFB_ELEM_SOLID_LINEAR_TRI2> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_SOLID_LINEAR_TRI2> &g, int i) { return {{g.dldx[0][i], g.dldx[1][i], g.w, 0.0}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double lambda, double myu, double *e) {
+    const double w = a.v[2];
+    e[0] = 0.0; e[1] = 0.0; e[2] = 0.0; e[3] = 0.0;
+    e[0] += w * (lambda + myu) * a.v[0] * b.v[0];
+    e[2] += w * (lambda * a.v[0] * b.v[1] + myu * b.v[0] * a.v[1]);
+    e[1] += w * (lambda * a.v[1] * b.v[0] + myu * b.v[1] * a.v[0]);
+    e[3] += w * (lambda + myu) * a.v[1] * b.v[1];
+    const double dtmp1 = w * myu * (a.v[1] * b.v[1] + a.v[0] * b.v[0]);
+    e[0] += dtmp1;
+    e[3] += dtmp1;
+  }
+};
+template <> struct NodeOps<DFB_ELEM_LAPLACE_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_LAPLACE_TET> &g, int i) { return {{g.g[i][0], g.g[i][1], g.g[i][2], g.vol}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double alpha, double, double *e) {
+    e[0] = alpha * a.v[3] * (a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]);
+  }
+};
+template <> struct NodeOps<DFB_ELEM_SOLID_LINEAR_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_SOLID_LINEAR_TET> &g, int i) { return {{g.g[i][0], g.g[i][1], g.g[i][2], g.vol}}; }
+  __device__ static void block(const NodeRec &ri, const NodeRec &rj, double lambda, double myu, double *e) {
+    const double vol = ri.v[3];
+    double dtmp1 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) e[a + 3 * b] = vol * (lambda * ri.v[a] * rj.v[b] + myu * rj.v[a] * ri.v[b]);
+      dtmp1 += ri.v[a] * rj.v[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) e[a + 3 * a] += vol * myu * dtmp1;
+  }
+};
+template <> struct NodeOps<DFB_ELEM_COT_LAPLACE_TRI3> {
+  static constexpr bool OK = false;  // the cotangent block of (i,j) needs the angle at the THIRD corner: stays on the ElemGeo path
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_COT_LAPLACE_TRI3> &, int) { return {{0, 0, 0, 0}}; }
+  __device__ static void block(const NodeRec &, const NodeRec &, double, double, double *) {}
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_node_recs(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz, uint64_t num_elem,
+                                                   double p0, double p1, NodeRec *__restrict__ recs) {
+  using G = ElemGeo<KIND>;
+  constexpr int NNODE = G::NNODE, NDIM = G::NDIM;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    const double *p[NNODE];
+    double coords[NNODE][NDIM];
+#pragma unroll
+    for (int n = 0; n < NNODE; ++n) {
+      const uint32_t v = e2v[e * NNODE + n];
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&xyz[(uint64_t)v * NDIM + d]);
+      p[n] = coords[n];
+    }
+    G g;
+    g.init(p, p0, p1);
+#pragma unroll
+    for (int n = 0; n < NNODE; ++n) {
+      const NodeRec r = NodeOps<KIND>::make(g, n);
+      double4 *dst = reinterpret_cast<double4 *>(&recs[e * NNODE + n]);
+      dst[0] = make_double4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_assemble_recs(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
+                                                       uint64_t num_slots, uint64_t nnz, const NodeRec *__restrict__ recs, double p0,
+                                                       double p1, double *__restrict__ idx2val, double *__restrict__ row2val) {
+  using G = ElemGeo<KIND>;
+  constexpr int NN = G::N * G::N, NNODE = G::NNODE;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+    double acc[NN];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+    const uint32_t cb = nz2ptr[s], ce = nz2ptr[s + 1];
+    for (uint32_t c = cb; c < ce; ++c) {
+      const uint32_t code = contrib[c];          // (e*NNODE + i)*NNODE + j
+      const uint32_t ei = code / NNODE;          // e*NNODE + i
+      const uint32_t j = code - ei * NNODE;
+      const uint32_t ej = (ei / NNODE) * NNODE + j;
+      const double2 *pa = reinterpret_cast<const double2 *>(&recs[ei]);
+      const double2 *pb = reinterpret_cast<const double2 *>(&recs[ej]);
+      const double2 a0 = __ldg(pa), a1 = __ldg(pa + 1), b0 = __ldg(pb), b1 = __ldg(pb + 1);
+      const NodeRec ra = {{a0.x, a0.y, a1.x, a1.y}}, rb = {{b0.x, b0.y, b1.x, b1.y}};
+      double blk[NN];
+      NodeOps<KIND>::block(ra, rb, p0, p1, blk);
+#pragma unroll
+      for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+    }
+    // (a 4-way unrolled variant with all loads hoisted measured no faster: ncu shows the kernel bound by L1 sector throughput
+    //  (86 %), not by latency: 2 record sectors + ~1 list sector per contribution and 4x-amplified 72-byte strided stores)
+    double *dst = (s < nnz) ? (idx2val + s * NN) : (row2val + (s - nnz) * NN);
+#pragma unroll
+    for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+  }
+}
+
+// ---- default fused path in two kernels: (1) one thread per element evaluates the element geometry ONCE (tet: volume + 4 barycentric
+// gradients = 104 B) into a scratch array; (2) one thread per nonzero slot walks its contribution list and forms only the (i,j)
+// block from that record. Same arithmetic, same order => same bits as the single-kernel variant, but the per-contribution cost
+// drops from (16 B connectivity + 96 B coordinates + ~110 flop geometry) to (56 B + ~45 flop).
+template <int KIND>
+__global__ void __launch_bounds__(128) k_elem_geo(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz, uint64_t num_elem,
+                                                  double p0, double p1, ElemGeo<KIND> *__restrict__ geo) {
+  using G = ElemGeo<KIND>;
+  constexpr int NNODE = G::NNODE, NDIM = G::NDIM;
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    const double *p[NNODE];
+    double coords[NNODE][NDIM];
+#pragma unroll
+    for (int n = 0; n < NNODE; ++n) {
+      const uint32_t v = e2v[e * NNODE + n];
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&xyz[(uint64_t)v * NDIM + d]);
+      p[n] = coords[n];
+    }
+    G g;
+    g.init(p, p0, p1);
+    geo[e] = g;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_assemble_geo(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
+                                                      uint64_t num_slots, uint64_t nnz, const ElemGeo<KIND> *__restrict__ geo, double p0,
+                                                      double p1, double *__restrict__ idx2val, double *__restrict__ row2val) {
+  using G = ElemGeo<KIND>;
+  constexpr int NN = G::N * G::N, NNODE = G::NNODE;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+    double acc[NN];
+#pragma unroll
+    for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+    const uint32_t cb = nz2ptr[s], ce = nz2ptr[s + 1];
+    for (uint32_t c = cb; c < ce; ++c) {
+      const uint32_t code = contrib[c];
+      const uint32_t e = code / (NNODE * NNODE);
+      const int ij = (int)(code - e * (NNODE * NNODE));
+      const int i = ij / NNODE, j = ij - i * NNODE;
+      double blk[NN];
+      geo[e].block(i, j, p0, p1, blk);
+#pragma unroll
+      for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+    }
+    double *dst = (s < nnz) ? (idx2val + s * NN) : (row2val + (s - nnz) * NN);
+#pragma unroll
+    for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+  }
+}
+
 DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, double p0, double p1, dfb_bsr *m) {
   DFB_REQUIRE(plan && mesh && m, "dfb_assemble: NULL argument");
   const ElemInfo info = elem_info(kind);
@@ -372,6 +544,69 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
   uint64_t g = (ns + 127) / 128;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+  if (c->assemble_variant == 0 && kind != DFB_ELEM_COT_LAPLACE_TRI3) {
+    // node-record path: 32-byte record per (element, node), two aligned sectors per contribution
+    uint64_t ge = (mesh->num_elem + 127) / 128;
+    if (ge < 1) ge = 1;
+    if (ge > (uint64_t)c->sm_count * 16) ge = (uint64_t)c->sm_count * 16;
+    const uint64_t need = mesh->num_elem * info.n_node * sizeof(NodeRec) + 256;
+    if (plan->geo_cap < need) {
+      cudaFree(plan->d_geo);
+      plan->d_geo = nullptr;
+      plan->geo_cap = 0;
+      DFB_TRY(dfb_dev_alloc(&plan->d_geo, need));
+      plan->geo_cap = need;
+    }
+#define REC_CASE(K)                                                                                                                   \
+  case K:                                                                                                                             \
+    DFB_LAUNCH(c, k_node_recs<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (NodeRec *)plan->d_geo); \
+    DFB_LAUNCH(c, k_assemble_recs<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                       \
+               (const NodeRec *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                                     \
+    break;
+    switch (kind) {
+      REC_CASE(DFB_ELEM_LAPLACE_TRI2)
+      REC_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
+      REC_CASE(DFB_ELEM_LAPLACE_TET)
+      REC_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+      default:
+        return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
+    }
+#undef REC_CASE
+    DFB_CHECK_LAUNCH();
+    return DFB_OK;
+  }
+  if (c->assemble_variant == 0 || c->assemble_variant == 2) {
+    uint64_t ge = (mesh->num_elem + 127) / 128;
+    if (ge < 1) ge = 1;
+    if (ge > (uint64_t)c->sm_count * 16) ge = (uint64_t)c->sm_count * 16;
+#define GEO_CASE(K)                                                                                                            \
+  case K: {                                                                                                                    \
+    const uint64_t need = mesh->num_elem * sizeof(ElemGeo<K>) + 256;                                                           \
+    if (plan->geo_cap < need) {                                                                                                \
+      cudaFree(plan->d_geo);                                                                                                   \
+      plan->d_geo = nullptr;                                                                                                   \
+      plan->geo_cap = 0;                                                                                                       \
+      DFB_TRY(dfb_dev_alloc(&plan->d_geo, need));                                                                              \
+      plan->geo_cap = need;                                                                                                    \
+    }                                                                                                                          \
+    DFB_LAUNCH(c, k_elem_geo<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (ElemGeo<K> *)plan->d_geo); \
+    DFB_LAUNCH(c, k_assemble_geo<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                \
+               (const ElemGeo<K> *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                           \
+    break;                                                                                                                     \
+  }
+    switch (kind) {
+      GEO_CASE(DFB_ELEM_LAPLACE_TRI2)
+      GEO_CASE(DFB_ELEM_COT_LAPLACE_TRI3)
+      GEO_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
+      GEO_CASE(DFB_ELEM_LAPLACE_TET)
+      GEO_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+      default:
+        return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
+    }
+#undef GEO_CASE
+    DFB_CHECK_LAUNCH();
+    return DFB_OK;
+  }
 #define ASM_CASE(K)                                                                                                          \
   case K:                                                                                                                    \
     DFB_LAUNCH(c, k_assemble_fused<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz, mesh->d_elem2vtx, \

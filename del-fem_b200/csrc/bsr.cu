@@ -765,248 +765,6 @@ static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t s
   return DFB_OK;
 }
 
-// ---- variants 12/13/14: software-pipelined ring ("pipe").
-// Same tiling as the ring (LPR lanes per row, 32/LPR rows per tile, NST-stage TMA ring per warp), but the x gather of tile
-// i+1 is issued BEFORE the FMAs of tile i: by the time a tile is multiplied its x values sit in registers, so the dependent
-// chain  column index (shared) -> x (L2) -> DFMA  never stalls the warp, and a deeper ring (NST-1 tiles in flight per warp)
-// with fewer resident warps keeps more bytes in flight per SM.
-template <int N, int LPR, int NST>
-struct PipeSmem {
-  static constexpr int NN = N * N;
-  static constexpr int RPT = 32 / LPR;
-  static constexpr int CAP = RPT * 16;
-  static constexpr int VAL_BYTES = ((CAP * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int COL_BYTES = ((CAP * 4 + 16 + 15) / 16) * 16;
-  static constexpr int DIA_BYTES = ((RPT * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES;
-  static constexpr int BAR_BYTES = ((NST * 8 + 15) / 16) * 16;
-  static constexpr int WARP_BYTES = NST * BUF_BYTES + BAR_BYTES;
-  static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
-  static constexpr int WARPS = WARPS_RAW > 16 ? 16 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
-};
-
-template <int N>
-struct PipePre {      // what a lane holds for a tile whose gathers are in flight
-  uint32_t r, k0, kb, ke;
-  uint32_t c[4];
-  double xv[4][N];
-  double xo;          // x[r][sub] for the diagonal-block column this lane owns
-  bool valid, staged;
-};
-
-template <int N, int LPR, int NST, int ML>
-__global__ void __launch_bounds__(PipeSmem<N, LPR, NST>::WARPS * 32) k_spmv_pipe(const SpmvArgs a) {
-  using S = PipeSmem<N, LPR, NST>;
-  constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
-
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const unsigned sub = lane % LPR, rl = lane / LPR;
-  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
-  const uint32_t bar0 = smem_u32(wbase + NST * S::BUF_BYTES);
-  const unsigned long long pol = policy_evict_first();
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < NST; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * j) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-
-  const uint32_t n_rows = a.row_end - a.row_begin;
-  const uint32_t n_tiles = (n_rows + RPT - 1) / RPT;
-  const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
-
-  // ML == 0: lane 0 issues the three bulk copies. ML > 0: lane 0 posts the expected byte count, then the value range is
-  // split into ML pieces issued by ML different lanes, columns and diagonal by two more lanes (independent TMA requests).
-  auto issue = [&](uint32_t t, uint32_t b) {
-    if (t >= n_tiles) return;
-    if (ML == 0 && lane != 0) return;
-    const uint32_t r0 = a.row_begin + t * RPT;
-    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
-    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
-    const uint32_t nb = k1 - k0;
-    if (nb > (uint32_t)CAP) return;
-    unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
-    const uint32_t bar = bar0 + 8 * b;
-    const double *g_val = a.idx2val + (uint64_t)k0 * NN;
-    const uint32_t *g_col = a.idx2col + k0;
-    const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
-    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u;
-    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u);
-    uint32_t dummy = 0;
-    if (ML == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-      stage_bulk(smem_u32(buf), g_val, vb, bar, pol, &dummy);
-      stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
-      if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
-    } else {
-      if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-      __syncwarp();
-      // aligned superset of the value range, cut into ML pieces on 16-byte boundaries
-      const uintptr_t sv = (uintptr_t)g_val;
-      const uint32_t mis = (uint32_t)(sv & 15);
-      const char *gs = (const char *)(sv - mis);
-      const uint32_t total = (mis + vb + 15u) & ~15u;
-      const uint32_t piece = ((total / ML) + 15u) & ~15u;
-      if (lane < (unsigned)ML) {
-        const uint32_t off = lane * piece;
-        if (off < total) {
-          const uint32_t len = min(piece, total - off);
-          asm volatile(
-              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                  smem_u32(buf) + off),
-              "l"(gs + off), "r"(len), "r"(bar), "l"(pol)
-              : "memory");
-        }
-      } else if (lane == (unsigned)ML) {
-        stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
-      } else if (lane == (unsigned)ML + 1 && g_dia) {
-        stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
-      }
-    }
-  };
-
-  uint32_t phase_bits = 0u;
-  // wait for tile t in buffer b, then put its column indices and x gathers in flight
-  auto prefetch = [&](uint32_t t, uint32_t b) -> PipePre<N> {
-    PipePre<N> p;
-    const uint32_t r0 = a.row_begin + t * RPT;
-    const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
-    const uint32_t k0 = a.row2idx[r0], k1 = a.row2idx[r1];
-    p.r = r0 + rl;
-    p.k0 = k0;
-    p.valid = p.r < r1;
-    p.kb = p.valid ? a.row2idx[p.r] : k0;
-    p.ke = p.valid ? a.row2idx[p.r + 1] : k0;
-    p.staged = (k1 - k0) <= (uint32_t)CAP;
-    p.xo = (p.valid && sub < (unsigned)N) ? __ldg(a.x + (uint64_t)p.r * N + sub) : 0.0;
-    const uint32_t *cols = a.idx2col;
-    if (p.staged) {
-      const uint32_t bar = bar0 + 8 * b;
-      const uint32_t ph = (phase_bits >> b) & 1u;
-      asm volatile(
-          "{\n"
-          ".reg .pred p;\n"
-          "PIPE_WAIT:\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-          "@p bra PIPE_DONE;\n"
-          "bra PIPE_WAIT;\n"
-          "PIPE_DONE:\n"
-          "}\n" ::"r"(bar),
-          "r"(ph)
-          : "memory");
-      phase_bits ^= (1u << b);
-      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
-      const uint32_t *g_col = a.idx2col + k0;
-      cols = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15)) - k0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t kk = p.kb + sub + u * LPR;
-      p.c[u] = (kk < p.ke) ? cols[kk] : 0xFFFFFFFFu;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (p.c[u] != 0xFFFFFFFFu) load_x<N>(p.xv[u], a.x, p.c[u]);
-    }
-    return p;
-  };
-
-  double dot = 0.0;
-  auto compute = [&](const PipePre<N> &p, uint32_t b) {
-    const double *vals = a.idx2val;
-    const uint32_t *cols = a.idx2col;
-    const double *dia = a.row2val ? a.row2val + (uint64_t)p.r * NN : nullptr;
-    if (p.staged) {
-      unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
-      const double *g_val = a.idx2val + (uint64_t)p.k0 * NN;
-      const uint32_t *g_col = a.idx2col + p.k0;
-      vals = reinterpret_cast<const double *>(buf + ((uintptr_t)g_val & 15)) - (uint64_t)p.k0 * NN;
-      cols = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15)) - p.k0;
-      if (a.row2val) {
-        const uint32_t r0 = p.r - rl;
-        const double *g_dia = a.row2val + (uint64_t)r0 * NN;
-        dia = reinterpret_cast<const double *>(buf + S::VAL_BYTES + S::COL_BYTES + ((uintptr_t)g_dia & 15)) + rl * NN;
-      }
-    }
-    double s[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) s[q] = 0.0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (p.c[u] != 0xFFFFFFFFu) block_times_vec<N>(s, vals + (uint64_t)(p.kb + sub + u * LPR) * NN, p.xv[u]);
-    }
-    // rows with more than 4*LPR blocks: remaining rounds, not pipelined
-    for (uint32_t k = p.kb + sub + 4 * LPR; k < p.ke; k += LPR) {
-      double xv[N];
-      load_x<N>(xv, a.x, cols[k]);
-      block_times_vec<N>(s, vals + (uint64_t)k * NN, xv);
-    }
-    if (p.valid && dia && sub < (unsigned)N) {
-#pragma unroll
-      for (int q = 0; q < N; ++q) s[q] += dia[q + N * sub] * p.xo;
-    }
-#pragma unroll
-    for (int off = 1; off < LPR; off <<= 1) {
-#pragma unroll
-      for (int q = 0; q < N; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], off);
-    }
-    if (p.valid && sub == 0) {
-#pragma unroll
-      for (int q = 0; q < N; ++q) {
-        double yv = a.alpha * s[q];
-        if (a.beta != 0.0) yv += a.beta * a.y[(uint64_t)p.r * N + q];
-        a.y[(uint64_t)p.r * N + q] = yv;
-        // x[r][q] sits in lane q of this row's group (xo); fetch it with a shuffle-free reload from L1
-        dot += __ldg(a.x + (uint64_t)p.r * N + q) * yv;
-      }
-    }
-  };
-
-#pragma unroll
-  for (int j = 0; j < NST; ++j) issue(wg + j * ws, j);
-  if (wg < n_tiles) {
-    PipePre<N> cur = prefetch(wg, 0);
-    uint32_t b = 0;
-    for (uint32_t t = wg; t < n_tiles; t += ws) {
-      const uint32_t bn = (b + 1 == NST) ? 0u : b + 1;
-      const uint32_t tn = t + ws;
-      PipePre<N> nxt;
-      const bool has_next = tn < n_tiles;
-      if (has_next) nxt = prefetch(tn, bn);
-      compute(cur, b);
-      __syncwarp();
-      issue(t + NST * ws, b);
-      if (has_next) cur = nxt;
-      b = bn;
-    }
-  }
-  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
-}
-
-template <int N, int LPR, int NST, int ML>
-static dfb_status spmv_launch_pipe(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
-  using S = PipeSmem<N, LPR, NST>;
-  static_assert(LPR >= N, "the diagonal-block columns are spread over the lanes of a row");
-  const int warps = S::WARPS;
-  const size_t smem = (size_t)warps * S::WARP_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_pipe<N, LPR, NST, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  const uint64_t n_rows = a.row_end - a.row_begin;
-  const uint64_t n_tiles = (n_rows + S::RPT - 1) / S::RPT;
-  uint64_t g = (n_tiles + warps - 1) / warps;
-  if (g < 1) g = 1;
-  if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  DFB_LAUNCH_ON(c, strm, (k_spmv_pipe<N, LPR, NST, ML>), (unsigned)g, warps * 32, smem, a);
-  DFB_CHECK_LAUNCH();
-  return DFB_OK;
-}
-
 // ---- variant 20: tile-packed mirror, ONE TMA bulk copy per 8-row tile.
 // Measured on the ring kernels: every additional bulk-copy operation per tile costs ~10 % (the per-SM TMA unit is busy per
 // operation, not only per byte), and row-pointer loads from DRAM sit on every warp's critical path. The packed mirror stores,
@@ -1221,15 +979,8 @@ static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm
     case 4: return spmv_launch_ring<N, 4, 2, false, false, true>(c, a, strm);
     case 5: return spmv_launch_ring<N, 8, 2, false, false, true>(c, a, strm);
     case 6: return spmv_launch_ring<N, 4, 3, false, false, true>(c, a, strm);
-    case 7: return spmv_launch_ring<N, 4, 2, false, true, true>(c, a, strm);
-    case 8: return spmv_launch_ring<N, 4, 2, true, true, true>(c, a, strm);
-    case 9: return spmv_launch_ring<N, 4, 2, false, false, false>(c, a, strm);  // LPR must be >= N here
-    case 12: return spmv_launch_pipe<N, 4, 3, 0>(c, a, strm);
-    case 13: return spmv_launch_pipe<N, 4, 4, 0>(c, a, strm);
-    case 14: return spmv_launch_pipe<N, 4, 2, 0>(c, a, strm);
-    case 15: return spmv_launch_pipe<N, 4, 2, 4>(c, a, strm);
-    case 16: return spmv_launch_pipe<N, 4, 3, 4>(c, a, strm);
-    case 17: return spmv_launch_pipe<N, 4, 4, 4>(c, a, strm);
+    // (the row-pointer-prefetch / row-pointer-copy / diagonal-from-global / gather-pipelined / multi-lane-issue experiments
+    //  of profiles/README.md were all slower and have been removed from the build; the template flags remain for reference)
     default: break;
   }
   const uint64_t n_rows = a.row_end - a.row_begin;

@@ -194,6 +194,8 @@ struct dfb_plan {
   uint32_t *d_nz2ptr;    // [num_slots+1]
   uint32_t *d_contrib;   // [num_contrib] code = e*nn2 + i*num_node + j
   const dfb_mesh *mesh;  // borrowed (elem2vtx used to rebuild elem2nz on demand)
+  void *d_geo = nullptr;   // per-element geometry scratch of the two-kernel fused assembly (lazily allocated)
+  uint64_t geo_cap = 0;
 };
 
 struct dfb_precond {

@@ -1,0 +1,39 @@
+"""times the fused assembly variants on one resident problem and checks they produce identical bits"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import _bootstrap
+
+dfb = _bootstrap.load()
+from del_fem_b200 import synthetic
+
+n = synthetic.SIZES.get(sys.argv[1], None) or int(sys.argv[1])
+ctx = dfb.Ctx(0)
+mesh = dfb.Mesh.kuhn(ctx, n)
+ctx.timer_start()
+pat = dfb.Pattern.from_uniform_mesh(ctx, mesh, False)
+t_pat = ctx.timer_stop()
+ctx.timer_start()
+plan = dfb.Plan(ctx, pat, mesh, 0)
+t_plan = ctx.timer_stop()
+print(f"pattern {t_pat:.2f} ms, plan {t_plan:.2f} ms, {mesh.num_elem} tets, {plan.num_slots} slots")
+mat = dfb.Matrix(ctx, pat, 3)
+ref = None
+bytes_alg = 16 * mesh.num_elem + 24 * mesh.num_vtx + 72 * plan.num_slots + 64 * mesh.num_elem + 4 * (plan.num_slots + 1)
+for variant in (1, 2, 0):
+    ctx.set_option("assemble_variant", variant)
+    mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
+    best = 1e9
+    for _ in range(5):
+        ctx.timer_start()
+        mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
+        best = min(best, ctx.timer_stop())
+    rv, iv = mat.download()
+    h = (float(np.abs(rv).sum()), float(np.abs(iv).sum()))
+    same = ref is None or (np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1]))
+    if ref is None:
+        ref = (rv, iv)
+    print(f"assemble_variant {variant}: {best:.3f} ms  {mesh.num_elem / best / 1e6:.2f} G tets/s  {bytes_alg / best / 1e6:.0f} GB/s algorithmic  identical_bits={same} checksum={h}")
