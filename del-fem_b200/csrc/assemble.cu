@@ -274,7 +274,7 @@ DFB_API dfb_status dfb_plan_create(dfb_ctx *ctx, dfb_pattern *pattern, const dfb
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_create: %s", cudaGetErrorString(e));
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_cursor);
+  dfb_dev_free(d_cursor);
   if (st != DFB_OK) {
     dfb_plan_destroy(p);
     return st;
@@ -286,9 +286,9 @@ DFB_API dfb_status dfb_plan_create(dfb_ctx *ctx, dfb_pattern *pattern, const dfb
 DFB_API dfb_status dfb_plan_destroy(dfb_plan *p) {
   if (!p) return DFB_OK;
   cudaStreamSynchronize(p->ctx->stream);
-  cudaFree(p->d_nz2ptr);
-  cudaFree(p->d_contrib);
-  cudaFree(p->d_geo);
+  dfb_dev_free(p->d_nz2ptr);
+  dfb_dev_free(p->d_contrib);
+  dfb_dev_free(p->d_geo);
   dfb_pattern_destroy(p->pat);
   delete p;
   return DFB_OK;
@@ -313,7 +313,7 @@ DFB_API dfb_status dfb_plan_download_elem2nz(const dfb_plan *p, uint32_t *elem2n
   DFB_CHECK_LAUNCH();
   DFB_CUDA(cudaMemcpyAsync(elem2nz, d_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_out);
+  dfb_dev_free(d_out);
   DFB_CUDA(cudaMemsetAsync(c->d_errflag + 1, 0, sizeof(int), c->stream));
   return DFB_OK;
 }
@@ -551,7 +551,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     if (ge > (uint64_t)c->sm_count * 16) ge = (uint64_t)c->sm_count * 16;
     const uint64_t need = mesh->num_elem * info.n_node * sizeof(NodeRec) + 256;
     if (plan->geo_cap < need) {
-      cudaFree(plan->d_geo);
+      dfb_dev_free(plan->d_geo);
       plan->d_geo = nullptr;
       plan->geo_cap = 0;
       DFB_TRY(dfb_dev_alloc(&plan->d_geo, need));
@@ -583,7 +583,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
   case K: {                                                                                                                    \
     const uint64_t need = mesh->num_elem * sizeof(ElemGeo<K>) + 256;                                                           \
     if (plan->geo_cap < need) {                                                                                                \
-      cudaFree(plan->d_geo);                                                                                                   \
+      dfb_dev_free(plan->d_geo);                                                                                                   \
       plan->d_geo = nullptr;                                                                                                   \
       plan->geo_cap = 0;                                                                                                       \
       DFB_TRY(dfb_dev_alloc(&plan->d_geo, need));                                                                              \
@@ -965,9 +965,9 @@ DFB_API dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_m
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (st == DFB_OK && e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_assemble_energy: %s", cudaGetErrorString(e));
   if (st == DFB_OK && w) *w = *(double *)c->h_pinned;
-  cudaFree(d_emat);
-  cudaFree(d_evec);
-  cudaFree(d_w);
+  dfb_dev_free(d_emat);
+  dfb_dev_free(d_evec);
+  dfb_dev_free(d_w);
   return st;
 }
 
@@ -993,7 +993,7 @@ DFB_API dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2x
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_emat_one: %s", cudaGetErrorString(e));
   }
-  cudaFree(d_e);
+  dfb_dev_free(d_e);
   dfb_mesh_destroy(mesh);
   return st;
 }

@@ -49,11 +49,11 @@ DFB_API dfb_status dfb_bsr_create(dfb_ctx *ctx, dfb_pattern *pattern, int32_t bl
 DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
   if (!m) return DFB_OK;
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->d_idx2val);
-  cudaFree(m->d_row2val);
-  cudaFree(m->d_flag);
-  cudaFree(m->d_packed);
-  cudaFree(m->d_tile_off);
+  dfb_dev_free(m->d_idx2val);
+  dfb_dev_free(m->d_row2val);
+  dfb_dev_free(m->d_flag);
+  dfb_dev_free(m->d_packed);
+  dfb_dev_free(m->d_tile_off);
   dfb_pattern_destroy(m->pat);
   delete m;
   return DFB_OK;
@@ -178,7 +178,7 @@ DFB_API dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32
   dfb_ctx *c = m->ctx;
   const uint64_t need = bsr_n_all(m) * m->blk_dim;
   if (m->flag_cap < need) {
-    cudaFree(m->d_flag);
+    dfb_dev_free(m->d_flag);
     m->d_flag = nullptr;
     DFB_TRY(dfb_dev_alloc_t(&m->d_flag, need));
     m->flag_cap = need;
@@ -265,8 +265,8 @@ DFB_API dfb_status dfb_bsr_merge_one(dfb_bsr *m, const double *emat, const uint6
              m->pat->num_blk, m->d_row2val, m->d_idx2val, c->d_errflag + 1);
   DFB_CHECK_LAUNCH();
   dfb_status st = dfb_check_error_flag(c, 1, DFB_ERR_PATTERN_MISS, "dfb_bsr_merge_one: (row, col) of the element is not in the pattern");
-  cudaFree(d_e);
-  cudaFree(d_n);
+  dfb_dev_free(d_e);
+  dfb_dev_free(d_n);
   return st;
 }
 

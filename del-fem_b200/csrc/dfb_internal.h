@@ -208,6 +208,7 @@ struct dfb_precond {
 
 // ---- helpers implemented in ctx.cu
 dfb_status dfb_dev_alloc(void **p, size_t bytes);
+void dfb_dev_free(void *p);
 template <typename T>
 static inline dfb_status dfb_dev_alloc_t(T **p, size_t count) {
   return dfb_dev_alloc((void **)p, count * sizeof(T) + 256);

@@ -178,8 +178,8 @@ DFB_API dfb_status dfb_halo_destroy(dfb_halo *h) {
   if (!h) return DFB_OK;
   cudaStreamSynchronize(h->ctx->stream);
   cudaStreamSynchronize(h->ctx->stream_comm);
-  cudaFree(h->d_send_idx);
-  cudaFree(h->d_sendbuf);
+  dfb_dev_free(h->d_send_idx);
+  dfb_dev_free(h->d_sendbuf);
   delete h;
   return DFB_OK;
 }

@@ -34,7 +34,7 @@ static dfb_status upload_narrow(dfb_ctx *c, const uint64_t *host, uint64_t n, ui
   DFB_LAUNCH(c, k_narrow_u64, c->sm_count * 8, 256, 0, d_tmp, d_out, n, (unsigned long long)limit, c->d_errflag + 0);
   DFB_CHECK_LAUNCH();
   dfb_status st = dfb_check_error_flag(c, 0, DFB_ERR_BAD_ARG, what);
-  cudaFree(d_tmp);
+  dfb_dev_free(d_tmp);
   return st;
 }
 
@@ -56,7 +56,7 @@ static dfb_status mesh_alloc(dfb_ctx *ctx, uint64_t num_elem, int num_node, uint
   dfb_status st = dfb_dev_alloc_t(&m->d_elem2vtx, num_elem * num_node + 4);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&m->d_xyz, num_vtx * ndim + 4);
   if (st != DFB_OK) {
-    cudaFree(m->d_elem2vtx);
+    dfb_dev_free(m->d_elem2vtx);
     delete m;
     return st;
   }
@@ -181,7 +181,7 @@ DFB_API dfb_status dfb_mesh_rotate_vertex_ids(dfb_mesh *m, uint64_t shift) {
   DFB_LAUNCH(c, k_rotate_xyz, c->sm_count * 8, 256, 0, m->d_xyz, d_new, m->num_vtx, m->ndim, shift);
   DFB_CHECK_LAUNCH();
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(m->d_xyz);
+  dfb_dev_free(m->d_xyz);
   m->d_xyz = d_new;
   return DFB_OK;
 }
@@ -189,8 +189,8 @@ DFB_API dfb_status dfb_mesh_rotate_vertex_ids(dfb_mesh *m, uint64_t shift) {
 DFB_API dfb_status dfb_mesh_destroy(dfb_mesh *m) {
   if (!m) return DFB_OK;
   cudaStreamSynchronize(m->ctx->stream);
-  cudaFree(m->d_elem2vtx);
-  cudaFree(m->d_xyz);
+  dfb_dev_free(m->d_elem2vtx);
+  dfb_dev_free(m->d_xyz);
   delete m;
   return DFB_OK;
 }
@@ -219,7 +219,7 @@ static dfb_status download_widen(dfb_ctx *c, const uint32_t *d_in, uint64_t n, u
   DFB_CHECK_LAUNCH();
   DFB_CUDA(cudaMemcpyAsync(host, d_tmp, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_tmp);
+  dfb_dev_free(d_tmp);
   return DFB_OK;
 }
 
@@ -256,7 +256,7 @@ static dfb_status pattern_alloc(dfb_ctx *ctx, uint64_t num_blk, uint64_t nnz, in
   dfb_status st = dfb_dev_alloc_t(&p->d_row2idx, num_blk + 2);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&p->d_idx2col, nnz + 8);
   if (st != DFB_OK) {
-    cudaFree(p->d_row2idx);
+    dfb_dev_free(p->d_row2idx);
     delete p;
     return st;
   }
@@ -316,8 +316,8 @@ DFB_API dfb_status dfb_pattern_destroy(dfb_pattern *p) {
   if (!p) return DFB_OK;
   if (--p->refcount > 0) return DFB_OK;
   cudaStreamSynchronize(p->ctx->stream);
-  cudaFree(p->d_row2idx);
-  cudaFree(p->d_idx2col);
+  dfb_dev_free(p->d_row2idx);
+  dfb_dev_free(p->d_idx2col);
   delete p;
   return DFB_OK;
 }
@@ -446,11 +446,11 @@ DFB_API dfb_status dfb_pattern_from_uniform_mesh(dfb_ctx *ctx, const dfb_mesh *m
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_pattern_from_uniform_mesh: %s", cudaGetErrorString(e));
   }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_ptr);
-  cudaFree(d_cur);
-  cudaFree(d_v2e);
-  cudaFree(d_scratch);
-  cudaFree(d_row2idx);
+  dfb_dev_free(d_ptr);
+  dfb_dev_free(d_cur);
+  dfb_dev_free(d_v2e);
+  dfb_dev_free(d_scratch);
+  dfb_dev_free(d_row2idx);
   if (st != DFB_OK) {
     if (p) dfb_pattern_destroy(p);
     return st;

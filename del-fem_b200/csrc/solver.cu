@@ -208,7 +208,7 @@ DFB_API dfb_status dfb_precond_apply(const dfb_precond *pc, dfb_vec *v) {
 DFB_API dfb_status dfb_precond_destroy(dfb_precond *pc) {
   if (!pc) return DFB_OK;
   cudaStreamSynchronize(pc->ctx->stream);
-  cudaFree(pc->d_inv);
+  dfb_dev_free(pc->d_inv);
   delete pc;
   return DFB_OK;
 }
@@ -484,7 +484,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   DFB_REQUIRE(max_it < 0x7FFFFFF0ull, "(p)cg: max_it too large");
   // device history buffer
   if (c->hist_cap < max_it + 2) {
-    cudaFree(c->d_hist);
+    dfb_dev_free(c->d_hist);
     c->d_hist = nullptr;
     DFB_TRY(dfb_dev_alloc_t(&c->d_hist, max_it + 2));
     c->hist_cap = max_it + 2;

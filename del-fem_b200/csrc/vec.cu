@@ -35,7 +35,7 @@ DFB_API dfb_status dfb_vec_create(dfb_ctx *ctx, uint64_t n_blk, uint64_t n_ghost
 DFB_API dfb_status dfb_vec_destroy(dfb_vec *v) {
   if (!v) return DFB_OK;
   cudaStreamSynchronize(v->ctx->stream);
-  cudaFree(v->d);
+  dfb_dev_free(v->d);
   delete v;
   return DFB_OK;
 }
@@ -182,7 +182,7 @@ DFB_API dfb_status dfb_vec_set_fixed_dof_zero(dfb_vec *rhs, const int32_t *flag_
   DFB_LAUNCH(c, k_zero_flagged, stream_grid(c, rhs->len(), 4, 256), 256, 0, rhs->d, d_flag, rhs->len());
   DFB_CHECK_LAUNCH();
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  cudaFree(d_flag);
+  dfb_dev_free(d_flag);
   return DFB_OK;
 }
 
@@ -202,7 +202,7 @@ DFB_API dfb_status dfb_bcflag_create(dfb_ctx *ctx, const int32_t *flag_host, uin
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_bcflag_create: %s", cudaGetErrorString(e));
   }
   if (st != DFB_OK) {
-    cudaFree(f->d);
+    dfb_dev_free(f->d);
     delete f;
     return st;
   }
@@ -213,7 +213,7 @@ DFB_API dfb_status dfb_bcflag_create(dfb_ctx *ctx, const int32_t *flag_host, uin
 DFB_API dfb_status dfb_bcflag_destroy(dfb_bcflag *f) {
   if (!f) return DFB_OK;
   cudaStreamSynchronize(f->ctx->stream);
-  cudaFree(f->d);
+  dfb_dev_free(f->d);
   delete f;
   return DFB_OK;
 }
