@@ -334,13 +334,13 @@ __device__ __forceinline__ double row_finish(const SpmvArgs &a, uint32_t r, doub
 
 __device__ __forceinline__ void spmv_publish_dot(const SpmvArgs &a, double d, double *s_buf) {
   double acc[1] = {d};
-  if (grid_sum_last_block<1>(acc, a.partials, a.ticket, s_buf) && threadIdx.x == 0) {
-    if (a.fuse_dot == 2) a.st->red[0] += acc[0];
-    else a.st->red[0] = acc[0];
-    if (a.pv.nranks > 1 && a.pv.seq != 0) {
-      const double total = a.st->red[0];
-      peer_post<1>(a.pv, &total);
+  if (grid_sum_last_block<1>(acc, a.partials, a.ticket, s_buf)) {  // true for every thread of the last block
+    if (threadIdx.x == 0) {
+      if (a.fuse_dot == 2) a.st->red[0] += acc[0];
+      else a.st->red[0] = acc[0];
+      s_buf[0] = a.st->red[0];
     }
+    if (a.pv.nranks > 1 && a.pv.seq != 0) peer_post_block<1>(a.pv, s_buf);
   }
 }
 

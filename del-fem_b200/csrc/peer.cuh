@@ -27,14 +27,33 @@ struct DfbPeerView {
 template <int K>
 __device__ __forceinline__ void peer_post(const DfbPeerView &pv, const double *vals) {
   const int slot = (int)(pv.seq % DFB_MBOX_SLOTS);
+  // all values to all peers (fire-and-forget NVLink stores), ONE system fence, then the flags
   for (int r = 0; r < pv.nranks; ++r) {
-    DfbMailbox *mb = pv.mbox[r];
+    volatile double *dst = pv.mbox[r]->val[slot][pv.rank];
 #pragma unroll
-    for (int k = 0; k < K; ++k) mb->val[slot][pv.rank][k] = vals[k];
+    for (int k = 0; k < K; ++k) dst[k] = vals[k];
   }
+  __threadfence_system();
   for (int r = 0; r < pv.nranks; ++r) {
-    unsigned long long *f = &pv.mbox[r]->flag[slot][pv.rank];
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(pv.seq) : "memory");
+    volatile unsigned long long *f = &pv.mbox[r]->flag[slot][pv.rank];
+    *f = pv.seq;
+  }
+}
+
+// parallel form: called by ALL threads of the (last) block after thread 0 left the K totals in shared memory `vals`;
+// thread r serves peer r, so the NVLink round trips of the R peers overlap instead of queueing behind one thread
+template <int K>
+__device__ __forceinline__ void peer_post_block(const DfbPeerView &pv, const double *vals) {
+  __syncthreads();
+  const int r = (int)threadIdx.x;
+  if (r < pv.nranks) {
+    const int slot = (int)(pv.seq % DFB_MBOX_SLOTS);
+    volatile double *dst = pv.mbox[r]->val[slot][pv.rank];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[k] = vals[k];
+    __threadfence_system();
+    volatile unsigned long long *f = &pv.mbox[r]->flag[slot][pv.rank];
+    *f = pv.seq;
   }
 }
 
@@ -49,14 +68,14 @@ __device__ __forceinline__ void peer_gather(const DfbPeerView &pv, double (&out)
     unsigned long long v = 0;
     const long long t0 = clock64();
     for (;;) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");  // local HBM: L2 is the coherence point
       if (v == pv.seq) break;
       if (clock64() - t0 > 4000000000ll) {
         *err = 2;
         break;
       }
-      __nanosleep(64);
     }
+    __threadfence_system();  // acquire: the values below were written before the flag
   }
   __syncthreads();
 #pragma unroll
@@ -65,7 +84,7 @@ __device__ __forceinline__ void peer_gather(const DfbPeerView &pv, double (&out)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       double v;
-      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(&mb->val[slot][r][k]) : "memory");
+      asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(&mb->val[slot][r][k]) : "memory");
       out[k] += v;
     }
   }

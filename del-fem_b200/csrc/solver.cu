@@ -234,10 +234,14 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, 
       acc[1] += rv[d] * z[d];
     }
   }
-  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
-    st->red[1] = acc[0];
-    st->red[2] = acc[1];
-    if (pv_out.nranks > 1 && pv_out.seq != 0) peer_post<2>(pv_out, acc);
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf)) {
+    if (threadIdx.x == 0) {
+      st->red[1] = acc[0];
+      st->red[2] = acc[1];
+      s_buf[0] = acc[0];
+      s_buf[1] = acc[1];
+    }
+    if (pv_out.nranks > 1 && pv_out.seq != 0) peer_post_block<2>(pv_out, s_buf);
   }
 }
 
@@ -295,10 +299,14 @@ __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, doub
       acc[1] += rv[d] * z[d];
     }
   }
-  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
-    st->red[1] = acc[0];
-    st->red[2] = acc[1];
-    if (pv_out.nranks > 1) peer_post<2>(pv_out, acc);
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf)) {
+    if (threadIdx.x == 0) {
+      st->red[1] = acc[0];
+      st->red[2] = acc[1];
+      s_buf[0] = acc[0];
+      s_buf[1] = acc[1];
+    }
+    if (pv_out.nranks > 1) peer_post_block<2>(pv_out, s_buf);
   }
 }
 
@@ -394,10 +402,14 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
     acc[0] += rv * rv;
     acc[1] += rv * z;
   }
-  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf) && threadIdx.x == 0) {
-    st->red[1] = acc[0];
-    st->red[2] = acc[1];
-    if (pv_out.nranks > 1) peer_post<2>(pv_out, acc);
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_buf)) {
+    if (threadIdx.x == 0) {
+      st->red[1] = acc[0];
+      st->red[2] = acc[1];
+      s_buf[0] = acc[0];
+      s_buf[1] = acc[1];
+    }
+    if (pv_out.nranks > 1) peer_post_block<2>(pv_out, s_buf);
   }
 }
 
@@ -452,6 +464,22 @@ __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__rest
   }
 }
 
+// One warp collects the R partial sums of exchange pv.seq from the LOCAL mailbox and stores the rank-ordered total where the
+// single-GPU kernels expect it. (Letting every block of the consumer kernel spin on the mailbox line was measured slower than
+// NCCL: ~10^4 spinning threads starve the incoming NVLink write.)
+template <int K>
+__global__ void k_peer_gather(const DfbPeerView pv, DfbSolverState *st, int first, int parity) {
+  if (parity >= 0 && st->done[parity]) return;  // converged: the producer did not post either
+  double g[K];
+  int err = 0;
+  peer_gather<K>(pv, g, &err);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) st->red[first + k] = g[k];
+    if (err) st->err = 2;
+  }
+}
+
 struct FlagsHost {
   int done[2];
   int iter;
@@ -498,6 +526,8 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   const bool peer = c->peer_enabled && c->use_peer_allreduce && c->nranks > 1;
   const bool nccl_red = c->nranks > 1 && !peer;
   const DfbPeerView pv_none = dfb_peer_view(c, 0);
+  DfbPeerView pv_off = pv_none;  // consumers read st->red[] (filled by k_peer_gather / NCCL / the local reduction)
+  pv_off.nranks = 1;
   DfbPeerView pv_i = peer ? dfb_peer_view(c, ++c->peer_seq) : pv_none;
   if (!peer) pv_i.nranks = 1;
 #define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2, pv_i)
@@ -505,7 +535,8 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
 #undef INIT
   DFB_CHECK_LAUNCH();
   if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
-  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 32, 0, st, c->d_hist, tol, eps_sq, check_pap, pv_i);
+  if (peer) DFB_LAUNCH(c, k_peer_gather<2>, 1, 32, 0, pv_i, st, 1, -1);
+  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 32, 0, st, c->d_hist, tol, eps_sq, check_pap, pv_off);
   DFB_CHECK_LAUNCH();
 
   FlagsHost *hf = (FlagsHost *)c->h_pinned;  // two slots
@@ -529,24 +560,26 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
       DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity, peer ? pv_a.seq : 0));
       if (prof) dfb_prof_end(c);
       if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
+      if (peer) DFB_LAUNCH(c, k_peer_gather<1>, 1, 32, 0, pv_a, st, 0, parity);
       if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b)
+#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b)
         DISPATCH_ALL(UPD)
 #undef UPD
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       } else {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_a, pv_b);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       }
       if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+      if (peer) DFB_LAUNCH(c, k_peer_gather<2>, 1, 32, 0, pv_b, st, 1, parity);
       if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap, pv_b)
+#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap, pv_off)
         DISPATCH_ALL(DIR)
 #undef DIR
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_b);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       } else {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_b);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       }
     }
     DFB_CHECK_LAUNCH();
