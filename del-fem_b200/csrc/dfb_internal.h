@@ -198,13 +198,23 @@ struct dfb_plan {
   uint64_t geo_cap = 0;
 };
 
+struct DfbIlu;
 struct dfb_precond {
   dfb_ctx *ctx;
   int kind;
   int blk_dim;
   uint64_t num_blk;
-  double *d_inv;  // jacobi: [num_blk*N] ; block-jacobi: [num_blk*NN] inverse blocks (column-major)
+  double *d_inv;  // jacobi: [num_blk*N] ; block-jacobi / ilu0: [num_blk*NN] inverse (pivot) blocks (column-major)
+  DfbIlu *ilu = nullptr;        // kind == DFB_PRECOND_ILU0
+  dfb_pattern *pat = nullptr;   // pattern of the matrix the ILU was built for
 };
+// ilu.cu
+dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, DfbIlu **out);
+void dfb_ilu_destroy(DfbIlu *s);
+dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia_out);
+dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec);
+double *dfb_ilu_z(DfbIlu *s);
+dfb_status dfb_ilu_dot(dfb_ctx *c, const double *a, const double *b, uint64_t n, double *d_out);
 
 // ---- helpers implemented in ctx.cu
 dfb_status dfb_dev_alloc(void **p, size_t bytes);

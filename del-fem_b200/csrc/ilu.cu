@@ -1,0 +1,376 @@
+// ilu.cu — ILU(0) preconditioner of the reference on the device (compiled --fmad=false so that the factorisation rounds like
+// the reference's).  Restates del-fem-cpu/src/sparse_ilu.rs:
+//   initialize_ilu0 :28-56   symbolic phase: per-row sorted copy of the pattern, row2idx_dia = first strictly-upper entry
+//   copy_value      :87-125  scatter A's off-diagonals through a column map, copy the diagonal blocks
+//   decompose       :127-181 IKJ incomplete factorisation; stores D_i^-1 and scales the strictly-upper part of row i by it
+//   solve_preconditioning_vec :183-219  forward sweep (L, then multiply by the stored inverse), backward sweep (U)
+// The reference runs all of it serially. Here rows are grouped into dependency LEVELS (level_f(i) = 1 + max level_f(k) over the
+// strictly-lower columns k of row i; level_b likewise over the strictly-upper columns, from the last row up): rows of one level
+// are independent, each row is processed by ONE thread with exactly the reference's loop order, so the factors and the sweeps
+// are deterministic and reproduce the serial arithmetic. One launch per level (S10 Kuhn cube: 448 forward + 448 backward
+// levels), which makes this preconditioner latency-bound on a GPU — it exists for fidelity with the reference's own PCG
+// (ILU(0) is what `solid_linear_tri2.rs:239-256` and `linearsystem::Solver` use), not for speed; Jacobi is the fast path.
+#include <algorithm>
+#include <vector>
+
+#include "dfb_internal.h"
+#include "reduce.cuh"
+
+struct DfbIlu {
+  uint32_t *d_col = nullptr;      // sorted columns [nnz]
+  uint32_t *d_a2ilu = nullptr;    // position of A's k-th entry inside the sorted row [nnz]
+  uint32_t *d_dia = nullptr;      // row2idx_dia [n]
+  uint32_t *d_rows_f = nullptr;   // rows ordered by forward level [n]
+  uint32_t *d_rows_b = nullptr;   // rows ordered by backward level [n]
+  std::vector<uint32_t> lev_f, lev_b;  // level pointers into d_rows_f / d_rows_b (host)
+  double *d_val = nullptr;        // factor values [nnz*NN]
+  double *d_z = nullptr;          // explicit preconditioned residual for PCG [n*N]
+};
+
+template <int N>
+__device__ __forceinline__ void mat_mul(double *c, const double *a, const double *b) {  // matn_col_major::mult_mat_col_major
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = s + a[i + N * k] * b[k + N * j];
+      c[i + N * j] = s;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void mat_vec(double *y, const double *a, const double *x) {  // matn_col_major::mult_vec
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = s + a[i + N * j] * x[j];
+    y[i] = s;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ bool mat_inverse(double *inv, const double *a) {  // try_inverse: Gauss-Jordan, partial pivoting
+  double m[N][2 * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      m[i][j] = a[i + N * j];
+      m[i][N + j] = (i == j) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    int p = c;
+#pragma unroll
+    for (int r = c + 1; r < N; ++r)
+      if (fabs(m[r][c]) > fabs(m[p][c])) p = r;
+    if (m[p][c] == 0.0) return false;
+    if (p != c) {
+#pragma unroll
+      for (int j = 0; j < 2 * N; ++j) {
+        const double t = m[p][j];
+        m[p][j] = m[c][j];
+        m[c][j] = t;
+      }
+    }
+    const double d = 1.0 / m[c][c];
+#pragma unroll
+    for (int j = 0; j < 2 * N; ++j) m[c][j] *= d;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      if (r == c) continue;
+      const double f = m[r][c];
+      if (f == 0.0) continue;
+#pragma unroll
+      for (int j = 0; j < 2 * N; ++j) m[r][j] -= f * m[c][j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) inv[i + N * j] = m[i][N + j];
+  return true;
+}
+
+// copy_value: ilu.idx2val[a2ilu[k]] = a.idx2val[k]; ilu.row2val = a.row2val
+__global__ void k_ilu_copy(const double *__restrict__ a_val, const double *__restrict__ a_dia, const uint32_t *__restrict__ a2ilu,
+                           uint64_t nnz, uint64_t n, int NN, double *__restrict__ val, double *__restrict__ dia) {
+  const uint64_t total = (nnz + n) * NN;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t blk = q / NN;
+    const int e = (int)(q - blk * NN);
+    if (blk < nnz) val[(uint64_t)a2ilu[blk] * NN + e] = a_val[q];
+    else dia[(blk - nnz) * NN + e] = a_dia[(blk - nnz) * NN + e];
+  }
+}
+
+// decompose, one level: rows[first..last)
+template <int N>
+__global__ void k_ilu_decompose_level(const uint32_t *__restrict__ rows, uint32_t first, uint32_t last, const uint32_t *__restrict__ r2i,
+                                      const uint32_t *__restrict__ col, const uint32_t *__restrict__ diap, double *__restrict__ val,
+                                      double *__restrict__ dia, int *err) {
+  constexpr int NN = N * N;
+  for (uint32_t q = first + blockIdx.x * blockDim.x + threadIdx.x; q < last; q += gridDim.x * blockDim.x) {
+    const uint32_t i = rows[q];
+    const uint32_t rb = r2i[i], re = r2i[i + 1], rd = diap[i];
+    for (uint32_t ik = rb; ik < rd; ++ik) {
+      const uint32_t k = col[ik];
+      double ikv[NN];
+#pragma unroll
+      for (int e = 0; e < NN; ++e) ikv[e] = val[(uint64_t)ik * NN + e];
+      for (uint32_t kj = diap[k]; kj < r2i[k + 1]; ++kj) {
+        const uint32_t j = col[kj];
+        double ikkj[NN];
+        mat_mul<N>(ikkj, ikv, val + (uint64_t)kj * NN);
+        if (j != i) {
+          // col2idx[j] of the reference: position of column j in (sorted) row i, if present
+          uint32_t lo = rb, hi = re;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (col[mid] < j) lo = mid + 1;
+            else hi = mid;
+          }
+          if (lo == re || col[lo] != j) continue;
+#pragma unroll
+          for (int e = 0; e < NN; ++e) val[(uint64_t)lo * NN + e] -= ikkj[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < NN; ++e) dia[(uint64_t)i * NN + e] -= ikkj[e];
+        }
+      }
+    }
+    double inv[NN], d[NN];
+#pragma unroll
+    for (int e = 0; e < NN; ++e) d[e] = dia[(uint64_t)i * NN + e];
+    if (!mat_inverse<N>(inv, d)) {
+      atomicExch(err, 1);
+      continue;
+    }
+#pragma unroll
+    for (int e = 0; e < NN; ++e) dia[(uint64_t)i * NN + e] = inv[e];
+    for (uint32_t ij = rd; ij < re; ++ij) {
+      double t[NN];
+      mat_mul<N>(t, inv, val + (uint64_t)ij * NN);
+#pragma unroll
+      for (int e = 0; e < NN; ++e) val[(uint64_t)ij * NN + e] = t[e];
+    }
+  }
+}
+
+// forward sweep, one level: t = v_i - sum_{j<i} L_ij v_j ; v_i = D_i^-1 t
+template <int N>
+__global__ void k_ilu_forward_level(const uint32_t *__restrict__ rows, uint32_t first, uint32_t last, const uint32_t *__restrict__ r2i,
+                                    const uint32_t *__restrict__ col, const uint32_t *__restrict__ diap, const double *__restrict__ val,
+                                    const double *__restrict__ dia, double *__restrict__ vec) {
+  constexpr int NN = N * N;
+  for (uint32_t q = first + blockIdx.x * blockDim.x + threadIdx.x; q < last; q += gridDim.x * blockDim.x) {
+    const uint32_t i = rows[q];
+    double t[N], v[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) t[d] = vec[(uint64_t)i * N + d];
+    for (uint32_t k = r2i[i]; k < diap[i]; ++k) {
+      mat_vec<N>(v, val + (uint64_t)k * NN, vec + (uint64_t)col[k] * N);
+#pragma unroll
+      for (int d = 0; d < N; ++d) t[d] -= v[d];
+    }
+    mat_vec<N>(v, dia + (uint64_t)i * NN, t);
+#pragma unroll
+    for (int d = 0; d < N; ++d) vec[(uint64_t)i * N + d] = v[d];
+  }
+}
+
+// backward sweep, one level: v_i -= sum_{j>i} U_ij v_j
+template <int N>
+__global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t first, uint32_t last, const uint32_t *__restrict__ r2i,
+                                     const uint32_t *__restrict__ col, const uint32_t *__restrict__ diap, const double *__restrict__ val,
+                                     double *__restrict__ vec) {
+  constexpr int NN = N * N;
+  for (uint32_t q = first + blockIdx.x * blockDim.x + threadIdx.x; q < last; q += gridDim.x * blockDim.x) {
+    const uint32_t i = rows[q];
+    double t[N], v[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) t[d] = vec[(uint64_t)i * N + d];
+    for (uint32_t k = diap[i]; k < r2i[i + 1]; ++k) {
+      mat_vec<N>(v, val + (uint64_t)k * NN, vec + (uint64_t)col[k] * N);
+#pragma unroll
+      for (int d = 0; d < N; ++d) t[d] -= v[d];
+    }
+#pragma unroll
+    for (int d = 0; d < N; ++d) vec[(uint64_t)i * N + d] = t[d];
+  }
+}
+
+// red_out[0] = a . b  (deterministic)
+__global__ void __launch_bounds__(256) k_ilu_dot(const double *__restrict__ a, const double *__restrict__ b, uint64_t n, double *partials,
+                                                 unsigned int *ticket, double *out) {
+  __shared__ double s_buf[32];
+  double acc[1] = {0.0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc[0] += a[i] * b[i];
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_buf) && threadIdx.x == 0) out[0] = acc[0];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+void dfb_ilu_destroy(DfbIlu *s) {
+  if (!s) return;
+  dfb_dev_free(s->d_col);
+  dfb_dev_free(s->d_a2ilu);
+  dfb_dev_free(s->d_dia);
+  dfb_dev_free(s->d_rows_f);
+  dfb_dev_free(s->d_rows_b);
+  dfb_dev_free(s->d_val);
+  dfb_dev_free(s->d_z);
+  delete s;
+}
+
+// initialize_ilu0 (:28-56) + level schedule
+dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, DfbIlu **out) {
+  DFB_REQUIRE(m->pat->convention == 0, "ilu0: needs the csrdia convention (separate diagonal)");
+  DFB_REQUIRE(c->nranks <= 1, "ilu0: single-GPU only (a distributed ILU would be a different preconditioner)");
+  const uint64_t n = m->pat->num_blk, nnz = m->pat->nnz;
+  const int N = m->blk_dim, NN = N * N;
+  std::vector<uint32_t> r2i(n + 1), col(nnz);
+  DFB_CUDA(cudaMemcpyAsync(r2i.data(), m->pat->d_row2idx, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (nnz) DFB_CUDA(cudaMemcpyAsync(col.data(), m->pat->d_idx2col, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  DFB_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<uint32_t> scol(nnz), a2ilu(nnz), dia(n), lf(n, 0), lb(n, 0);
+  std::vector<std::pair<uint32_t, uint32_t>> tmp;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t b = r2i[i], e = r2i[i + 1];
+    tmp.clear();
+    for (uint32_t k = b; k < e; ++k) {
+      if (col[k] == i) return dfb_fail(DFB_ERR_BAD_ARG, "ilu0: the pattern must not contain the diagonal (assert!(j_col < i_row) sparse_ilu.rs:199)");
+      tmp.emplace_back(col[k], k);
+    }
+    std::sort(tmp.begin(), tmp.end());
+    dia[i] = e;
+    for (uint32_t q = 0; q < tmp.size(); ++q) {
+      scol[b + q] = tmp[q].first;
+      a2ilu[tmp[q].second] = b + q;
+      if (dia[i] == e && tmp[q].first > i) dia[i] = b + q;
+    }
+  }
+  uint32_t max_f = 0, max_b = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t l = 0;
+    for (uint32_t k = r2i[i]; k < dia[i]; ++k) l = std::max(l, lf[scol[k]] + 1);
+    lf[i] = l;
+    max_f = std::max(max_f, l);
+  }
+  for (uint64_t ii = n; ii-- > 0;) {
+    uint32_t l = 0;
+    for (uint32_t k = dia[ii]; k < r2i[ii + 1]; ++k) l = std::max(l, lb[scol[k]] + 1);
+    lb[ii] = l;
+    max_b = std::max(max_b, l);
+  }
+  auto order = [&](const std::vector<uint32_t> &lev, uint32_t nlev, std::vector<uint32_t> &ptr, std::vector<uint32_t> &rows) {
+    ptr.assign(nlev + 2, 0);
+    for (uint64_t i = 0; i < n; ++i) ptr[lev[i] + 1] += 1;
+    for (uint32_t l = 0; l <= nlev; ++l) ptr[l + 1] += ptr[l];
+    rows.resize(n);
+    std::vector<uint32_t> cur(ptr.begin(), ptr.end() - 1);
+    for (uint64_t i = 0; i < n; ++i) rows[cur[lev[i]]++] = (uint32_t)i;  // ascending row index inside a level
+  };
+  DfbIlu *s = new DfbIlu();
+  std::vector<uint32_t> rows_f, rows_b;
+  order(lf, max_f, s->lev_f, rows_f);
+  order(lb, max_b, s->lev_b, rows_b);
+  s->lev_f.resize(n ? max_f + 2 : 1);
+  s->lev_b.resize(n ? max_b + 2 : 1);
+  dfb_status st = DFB_OK;
+  auto up = [&](uint32_t **d, const std::vector<uint32_t> &h) {
+    if (st != DFB_OK) return;
+    st = dfb_dev_alloc_t(d, h.size() + 2);
+    if (st == DFB_OK && !h.empty()) {
+      cudaError_t e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu0: %s", cudaGetErrorString(e));
+    }
+  };
+  up(&s->d_col, scol);
+  up(&s->d_a2ilu, a2ilu);
+  up(&s->d_dia, dia);
+  up(&s->d_rows_f, rows_f);
+  up(&s->d_rows_b, rows_b);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_val, nnz * NN + 8);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_z, n * N + 8);
+  if (st == DFB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu0: upload failed");
+  if (st != DFB_OK) {
+    dfb_ilu_destroy(s);
+    return st;
+  }
+  *out = s;
+  return DFB_OK;
+}
+
+static int level_grid(uint32_t count) {
+  int g = (int)((count + 127) / 128);
+  return g < 1 ? 1 : (g > 1184 ? 1184 : g);
+}
+
+// copy_value + decompose
+dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia_out) {
+  const uint64_t n = m->pat->num_blk, nnz = m->pat->nnz;
+  const int N = m->blk_dim, NN = N * N;
+  DFB_LAUNCH(c, k_ilu_copy, c->sm_count * 8, 256, 0, m->d_idx2val, m->d_row2val, s->d_a2ilu, nnz, n, NN, s->d_val, d_dia_out);
+  const uint32_t nlev = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1;
+  for (uint32_t l = 0; l < nlev; ++l) {
+    const uint32_t a = s->lev_f[l], b = s->lev_f[l + 1];
+    if (a == b) continue;
+#define DEC(NV)                                                                                                                     \
+  case NV:                                                                                                                          \
+    DFB_LAUNCH(c, k_ilu_decompose_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, m->pat->d_row2idx, s->d_col, s->d_dia, s->d_val, \
+               d_dia_out, c->d_errflag + 2);                                                                                        \
+    break;
+    switch (N) {
+      DEC(1) DEC(2) DEC(3) DEC(4)
+    }
+#undef DEC
+  }
+  DFB_CHECK_LAUNCH();
+  return dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "ilu0 decompose: singular pivot block (try_inverse().unwrap())");
+}
+
+// solve_preconditioning_vec, in place
+dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec) {
+  const uint32_t nf = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1, nb = s->lev_b.empty() ? 0 : (uint32_t)s->lev_b.size() - 1;
+  for (uint32_t l = 0; l < nf; ++l) {
+    const uint32_t a = s->lev_f[l], b = s->lev_f[l + 1];
+    if (a == b) continue;
+#define FWD(NV)                                                                                                                      \
+  case NV:                                                                                                                           \
+    DFB_LAUNCH(c, k_ilu_forward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, pat->d_row2idx, s->d_col, s->d_dia, s->d_val, d_dia, \
+               d_vec);                                                                                                               \
+    break;
+    switch (N) {
+      FWD(1) FWD(2) FWD(3) FWD(4)
+    }
+#undef FWD
+  }
+  for (uint32_t l = 0; l < nb; ++l) {
+    const uint32_t a = s->lev_b[l], b = s->lev_b[l + 1];
+    if (a == b) continue;
+#define BWD(NV)                                                                                                                       \
+  case NV:                                                                                                                            \
+    DFB_LAUNCH(c, k_ilu_backward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_b, a, b, pat->d_row2idx, s->d_col, s->d_dia, s->d_val, d_vec); \
+    break;
+    switch (N) {
+      BWD(1) BWD(2) BWD(3) BWD(4)
+    }
+#undef BWD
+  }
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+double *dfb_ilu_z(DfbIlu *s) { return s->d_z; }
+
+dfb_status dfb_ilu_dot(dfb_ctx *c, const double *a, const double *b, uint64_t n, double *d_out) {
+  uint64_t g = (n + 1023) / 1024;
+  if (g < 1) g = 1;
+  if (g > 1184) g = 1184;
+  DFB_LAUNCH(c, k_ilu_dot, (unsigned)g, 256, 0, a, b, n, c->d_partials, c->d_ticket + 4, d_out);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}

@@ -110,7 +110,7 @@ __global__ void k_precond_update(int kind, uint64_t num_blk, const double *__res
 
 DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, dfb_precond **out) {
   DFB_REQUIRE(ctx && m && out, "dfb_precond_create: NULL argument");
-  DFB_REQUIRE(kind >= DFB_PRECOND_NONE && kind <= DFB_PRECOND_BLOCK_JACOBI, "dfb_precond_create: unknown kind %d", kind);
+  DFB_REQUIRE(kind >= DFB_PRECOND_NONE && kind <= DFB_PRECOND_ILU0, "dfb_precond_create: unknown kind %d", kind);
   DFB_CUDA(cudaSetDevice(ctx->device));
   dfb_precond *pc = new dfb_precond();
   pc->ctx = ctx;
@@ -121,7 +121,15 @@ DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr 
   if (kind != DFB_PRECOND_NONE) {
     const uint64_t per = kind == DFB_PRECOND_JACOBI ? (uint64_t)m->blk_dim : (uint64_t)m->blk_dim * m->blk_dim;
     dfb_status st = dfb_dev_alloc_t(&pc->d_inv, pc->num_blk * per + 8);
+    if (st == DFB_OK && kind == DFB_PRECOND_ILU0) {
+      st = dfb_ilu_create(ctx, m, &pc->ilu);
+      if (st == DFB_OK) {
+        pc->pat = m->pat;
+        m->pat->refcount += 1;
+      }
+    }
     if (st != DFB_OK) {
+      dfb_dev_free(pc->d_inv);
       delete pc;
       return st;
     }
@@ -135,6 +143,10 @@ DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {
   DFB_REQUIRE(pc->num_blk == m->pat->num_blk && pc->blk_dim == m->blk_dim, "dfb_precond_update: shape mismatch");
   if (pc->kind == DFB_PRECOND_NONE) return DFB_OK;
   dfb_ctx *c = pc->ctx;
+  if (pc->kind == DFB_PRECOND_ILU0) {
+    DFB_REQUIRE(pc->pat == m->pat, "dfb_precond_update: the ILU(0) was initialised for another pattern");
+    return dfb_ilu_update(c, pc->ilu, m, pc->d_inv);
+  }
   const int grid = c->sm_count * 8;
 #define PC_CASE(NV)                                                                                                       \
   case NV:                                                                                                                \
@@ -160,6 +172,10 @@ __device__ __forceinline__ void apply_minv(double (&z)[N], const double *__restr
   } else if (KIND == DFB_PRECOND_JACOBI) {
 #pragma unroll
     for (int d = 0; d < N; ++d) z[d] = inv[i * N + d] * r[d];
+  } else if (KIND == DFB_PRECOND_ILU0) {
+    // explicit z: `inv` points at the vector M^-1 r computed beforehand by the triangular sweeps
+#pragma unroll
+    for (int d = 0; d < N; ++d) z[d] = inv[i * N + d];
   } else {
     const double *B = inv + i * N * N;
 #pragma unroll
@@ -197,6 +213,7 @@ DFB_API dfb_status dfb_precond_apply(const dfb_precond *pc, dfb_vec *v) {
   DFB_REQUIRE(v->n_blk == pc->num_blk && v->blk_dim == pc->blk_dim, "dfb_precond_apply: shape mismatch");
   dfb_ctx *c = pc->ctx;
   const int n = pc->blk_dim, kind = pc->kind;
+  if (kind == DFB_PRECOND_ILU0) return dfb_ilu_apply(c, pc->ilu, pc->pat, n, pc->d_inv, v->d);
   const int grid = c->sm_count * 8;
 #define APPLY(NV, KV) DFB_LAUNCH(c, (k_precond_apply<NV, KV>), grid, 256, 0, v->d, pc->d_inv, pc->num_blk)
   DISPATCH_ALL(APPLY)
@@ -209,6 +226,8 @@ DFB_API dfb_status dfb_precond_destroy(dfb_precond *pc) {
   if (!pc) return DFB_OK;
   cudaStreamSynchronize(pc->ctx->stream);
   dfb_dev_free(pc->d_inv);
+  dfb_ilu_destroy(pc->ilu);
+  if (pc->pat) dfb_pattern_destroy(pc->pat);
   delete pc;
   return DFB_OK;
 }
@@ -504,6 +523,10 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   const int n = m->blk_dim;
   const int kind = pc ? pc->kind : DFB_PRECOND_NONE;
   const double *inv = pc ? pc->d_inv : nullptr;
+  const bool ilu = kind == DFB_PRECOND_ILU0;
+  double *zbuf = ilu ? dfb_ilu_z(pc->ilu) : nullptr;
+  if (ilu) DFB_REQUIRE(pc->pat == m->pat, "pcg: the ILU(0) preconditioner belongs to another pattern");
+  if (ilu) DFB_REQUIRE(c->nranks <= 1, "pcg: ILU(0) is single-GPU only");
   for (dfb_vec *v : {r, x, q, p}) {
     DFB_REQUIRE(v && v->n_blk == nb && v->blk_dim == n, "(p)cg: vector shape != matrix shape (assert_eq!(r_vec.len(), mat.num_blk))");
     DFB_REQUIRE(v->ctx == c, "(p)cg: vector belongs to another context");
@@ -530,6 +553,15 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   pv_off.nranks = 1;
   DfbPeerView pv_i = peer ? dfb_peer_view(c, ++c->peer_seq) : pv_none;
   if (!peer) pv_i.nranks = 1;
+  if (ilu) {
+    // z = M^-1 r by the level-scheduled sweeps, then the generic init with z taken as given
+    DFB_CUDA(cudaMemcpyAsync(zbuf, r->d, nb * (uint64_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    DFB_TRY(dfb_ilu_apply(c, pc->ilu, pc->pat, n, pc->d_inv, zbuf));
+#define INITZ(NV) \
+  if (n == NV) DFB_LAUNCH(c, (k_pcg_init<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, x->d, p->d, zbuf, nb, st, c->d_partials, c->d_ticket + 2, pv_i);
+    INITZ(1) INITZ(2) INITZ(3) INITZ(4)
+#undef INITZ
+  }
 #define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2, pv_i)
   DISPATCH_ALL(INIT)
 #undef INIT
@@ -570,6 +602,12 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
       } else {
         DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       }
+      if (ilu) {
+        // the update kernel ran with M = I (r.r in red[1]); now z = M^-1 r explicitly and r.z -> red[2]
+        DFB_CUDA(cudaMemcpyAsync(zbuf, r->d, nflat * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        DFB_TRY(dfb_ilu_apply(c, pc->ilu, pc->pat, n, pc->d_inv, zbuf));
+        DFB_TRY(dfb_ilu_dot(c, r->d, zbuf, nflat, &st->red[2]));
+      }
       if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
       if (peer) DFB_LAUNCH(c, k_peer_gather<2>, 1, 32, 0, pv_b, st, 1, parity);
       if (kind == DFB_PRECOND_BLOCK_JACOBI) {
@@ -578,6 +616,11 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
 #undef DIR
       } else if (kind == DFB_PRECOND_JACOBI) {
         DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
+      } else if (ilu) {
+#define DIRZ(NV) \
+  if (n == NV) DFB_LAUNCH(c, (k_pcg_direction<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, p->d, zbuf, nb, st, parity, c->d_hist, c->hist_cap, pv_off);
+        DIRZ(1) DIRZ(2) DIRZ(3) DIRZ(4)
+#undef DIRZ
       } else {
         DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       }

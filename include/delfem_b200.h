@@ -64,8 +64,10 @@ enum {
 enum {
   DFB_PRECOND_NONE = 0,
   DFB_PRECOND_JACOBI = 1,       /* DERIVED: z[i][d] = r[i][d] / D[i][d + N d]                                             */
-  DFB_PRECOND_BLOCK_JACOBI = 2  /* sparse_ilu::{copy_value,decompose,solve_preconditioning_vec} with an empty off-diagonal
+  DFB_PRECOND_BLOCK_JACOBI = 2, /* sparse_ilu::{copy_value,decompose,solve_preconditioning_vec} with an empty off-diagonal
                                    pattern  del-fem-cpu/src/sparse_ilu.rs:87-219                                           */
+  DFB_PRECOND_ILU0 = 3          /* the reference's own preconditioner: initialize_ilu0 :28, copy_value :87, decompose :127,
+                                   solve_preconditioning_vec :183 — level-scheduled on the device, one GPU only             */
 };
 
 /* ------------------------------------------------------------------------------------------------ context */

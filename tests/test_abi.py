@@ -89,3 +89,13 @@ def test_python_mirror_signatures_cover_header(dfb):
         if n in ("dfb_last_error_message", "dfb_version"):
             continue
         assert fn.argtypes is not None, f"{n}: ctypes argtypes not declared"
+
+
+def test_cpp_mirror_compiles():
+    """the header-only C++ mirror and its test program compile and link against the C-ABI library (no GPU needed to build)"""
+    import tempfile
+    lib_dir = os.path.join(ROOT, "del-fem_b200", "lib")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_solid_linear_tri2.cpp"), "-o",
+                            os.path.join(d, "t"), "-L" + lib_dir, "-ldelfem_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
