@@ -104,34 +104,41 @@ def kuhn_counts(nx, ny, nz):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def e2e_step(dfb, ctx, host, precond, tol=1e-8, max_it=20000):
+def e2e_step(dfb, ctx, host, precond, tol=1e-8, max_it=20000, slab=None):
     """the same step through the reference-facing C-ABI calls starting from HOST (page-locked) buffers: usize connectivity,
-    coordinates, usize pattern, flags, u0 in; solution out. Returns (wall seconds, iterations, h2d bytes, d2h bytes)."""
+    coordinates, pattern, flags, u0 in; solution out. Returns (wall seconds, iterations, h2d bytes, d2h bytes).
+    With `slab` (multi-GPU) the host buffers are this rank's slab in local numbering and the halo description is attached."""
     from del_fem_b200 import sparse_ilu
     t0 = time.perf_counter()
     mesh = dfb.Mesh(ctx, host["e2v"], host["xyz"])                      # H2D: usize elem2vtx + f64 coordinates
-    pat = dfb.Pattern(ctx, host["r2i"], host["i2c"], 0)                 # H2D: usize row2idx / idx2col
+    pat = dfb.Pattern(ctx, host["r2i"], host["i2c"], 0)                 # H2D: row2idx / idx2col (usize; u32 for slabs: ghost columns)
     plan = dfb.Plan(ctx, pat, mesh, 0)
     mat = dfb.Matrix(ctx, pat, 3)                                       # Matrix::from_vtx2vtx
+    n_own = pat.num_blk
+    n_ghost = 0
+    halo = None
+    if slab is not None and slab.nranks > 1:
+        halo = dfb.Halo(ctx, slab.peers, slab.send_ptr, slab.send_idx, slab.recv_ptr)
+        mat.set_halo(halo, slab.int_begin, slab.int_end)
+        n_ghost = slab.n_ghost
     mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)             # element loop + merge
-    nv = host["xyz"].shape[0]
-    u0 = dfb.Vec(ctx, nv, 3, 0, host["u0"])                             # H2D
-    rhs = dfb.Vec(ctx, nv, 3)
+    u0 = dfb.Vec(ctx, n_own, 3, n_ghost, host["u0"])                    # H2D
+    rhs = dfb.Vec(ctx, n_own, 3, n_ghost)
     mat.mult_vec(rhs, 0.0, -1.0, u0)
-    rhs.set_fixed_dof_zero(host["flag"])                                # H2D flags
+    rhs.set_fixed_dof_zero(host["flag"][:n_own])                        # H2D flags
     mat.set_fixed_dof(1.0, host["flag"])                                # H2D flags
     pc = sparse_ilu.Preconditioner(precond)
     pc.initialize(mat)
     sparse_ilu.copy_value(pc, mat)
     sparse_ilu.decompose(pc)
-    x, q, p = dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3)
+    x, q, p = dfb.Vec(ctx, n_own, 3, n_ghost), dfb.Vec(ctx, n_own, 3, n_ghost), dfb.Vec(ctx, n_own, 3, n_ghost)
     hist = dfb.preconditioned_conjugate_gradient(rhs, x, q, p, tol, max_it, mat, pc)
     check = dfb.lib().dfb_vec_download(x.h, host["x_out"].ctypes.data)  # D2H solution into the pinned buffer
     assert check == 0
     dt = time.perf_counter() - t0
     h2d = host["e2v"].nbytes + host["xyz"].nbytes + host["r2i"].nbytes + host["i2c"].nbytes + host["u0"].nbytes + 2 * host["flag"].nbytes
     d2h = host["x_out"].nbytes + 8 * len(hist)
-    del mesh, pat, plan, mat, u0, rhs, pc, x, q, p
+    del mesh, pat, plan, mat, u0, rhs, pc, x, q, p, halo
     return dt, len(hist) - 1, h2d, d2h
 
 
@@ -281,21 +288,37 @@ def run_ours(args):
     # ---- end-to-end through the C ABI from host buffers (N = 1: whole mesh on the host; N > 1: this rank's slab)
     e2e = None
     cpu = None
-    if world == 1 and not args.no_e2e:
-        e2v, xyz = synthetic.kuhn_tet_mesh(nx, ny, nz, prob.h, index_dtype=np.uint64)
-        r2i, i2c = prob.pat.download()
+    if not args.no_e2e:
+        from del_fem_b200 import partition
+        slab = prob.slab
+        if world == 1:
+            e2v, xyz = synthetic.kuhn_tet_mesh(nx, ny, nz, prob.h, index_dtype=np.uint64)
+            r2i, i2c = prob.pat.download()                      # usize arrays, as a Rust caller holds them
+        else:
+            e2v, xyz = partition.local_mesh_host(slab, prob.h, index_dtype=np.uint64)
+            r2i, i2c = (a.astype(np.uint32) for a in prob.pat.download())  # local ids incl. ghost columns
+        n_own = slab.n_own
         host = {"e2v": e2v, "xyz": xyz, "r2i": r2i, "i2c": i2c, "flag": prob.flag_host,
-                "u0": None, "x_out": np.empty((nx * ny * nz, 3))}
-        u0 = synthetic.splitmix_uniform(0, 0, 3 * nx * ny * nz, -0.1, 0.1).reshape(-1, 3)
-        u0[prob.flag_host != 0] = 0.0
+                "u0": None, "x_out": np.empty((n_own, 3))}
+        u0 = synthetic.splitmix_uniform(0, 3 * slab.first_global_vtx, 3 * n_own, -0.1, 0.1).reshape(-1, 3)
+        u0[prob.flag_host[:n_own] != 0] = 0.0
         host["u0"] = u0
         del prob  # free the resident copy so both fit comfortably
         for k in ("e2v", "xyz", "r2i", "i2c", "flag", "u0", "x_out"):
             ctx.host_register(host[k])
-        e2e_step(dfb, ctx, host, args.precond)  # warm-up
+        barrier()
+        e2e_step(dfb, ctx, host, args.precond, slab=slab)  # warm-up
         ts, its = [], []
         for _ in range(max(1, min(args.steps, 3))):
-            dt, it, h2d, d2h = e2e_step(dfb, ctx, host, args.precond)
+            barrier()
+            dt, it, h2d, d2h = e2e_step(dfb, ctx, host, args.precond, slab=slab)
+            if dist is not None:  # wall time of the slowest rank, bytes summed over ranks
+                import torch
+                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                b = torch.tensor([float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(b)
+                dt, h2d, d2h = float(t[0]), float(b[0]), float(b[1])
             ts.append(dt)
             its.append(it)
         e2e_val = n_dof_total * sum(its) / sum(ts) / 1e6
