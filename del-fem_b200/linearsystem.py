@@ -9,7 +9,8 @@ from .core import Ctx, Pattern, Vec
 
 class Solver:
     def __init__(self, ctx: Ctx = None, blk_dim: int = 1, precond="jacobi"):
-        """Solver::new (:33): tol 1e-5, 100 iterations"""
+        """Solver::new (:33): tol 1e-5, 100 iterations. precond: "jacobi" (fast GPU path, default), "block_jacobi", or "ilu0"
+        (what the reference's Solver::initialize sets up, :53)"""
         self.ctx = ctx or Ctx.default()
         self.blk_dim = blk_dim
         self.sparse = None
