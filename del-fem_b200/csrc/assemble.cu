@@ -30,6 +30,8 @@ __host__ __device__ inline ElemInfo elem_info(int kind) {
     case DFB_ELEM_SOLID_LINEAR_TET: return {4, 3, 3};
     case DFB_ELEM_NEOHOOKEAN_TET: return {4, 3, 3};
     case DFB_ELEM_SPRING3: return {2, 3, 3};
+    case DFB_ELEM_STVK_TRI3: return {3, 3, 3};
+    case DFB_ELEM_BENDING_QUAD: return {4, 3, 3};
   }
   return {0, 0, 0};
 }
@@ -822,6 +824,196 @@ __global__ void __launch_bounds__(128) k_spring3(const uint32_t *__restrict__ e2
   }
 }
 
+__device__ __forceinline__ void cross3(double *o, const double *a, const double *b) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ---- stvk_tri3::wdwddw_ (del-fem-cpu/src/stvk_tri3.rs:152-330), batched over the triangles of a 3-D surface mesh.
+// St.Venant-Kirchhoff membrane: rest = mesh coordinates, deformed = rest + disp, p0 = lambda, p1 = myu.
+// The 16 material terms of :282-313 are summed in the reference's order; the dN factors there are -1/0/+1, so each term is
+// +-((gd[p][a] * E[x][y]) * gd[q][b]) exactly or vanishes — the signs are resolved at compile time instead of multiplied.
+// Blocks are written transposed (reference index a*3+b -> BSR a+3b).
+struct StvkTerm {
+  int p, r, x, y, q, s;
+};
+__global__ void __launch_bounds__(64) k_stvk_tri3(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                  const double *__restrict__ disp, uint64_t num_elem, double lambda, double myu,
+                                                  double *__restrict__ emat, double *__restrict__ evec, double *__restrict__ w_out) {
+  constexpr int dN[3][2] = {{-1, -1}, {1, 0}, {0, 1}};
+  constexpr StvkTerm T[16] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 1, 1, 1}, {0, 0, 0, 2, 0, 1}, {0, 0, 0, 2, 1, 0},
+                              {1, 1, 1, 0, 0, 0}, {1, 1, 1, 1, 1, 1}, {1, 1, 1, 2, 0, 1}, {1, 1, 1, 2, 1, 0},
+                              {0, 1, 2, 0, 0, 0}, {0, 1, 2, 1, 1, 1}, {0, 1, 2, 2, 0, 1}, {0, 1, 2, 2, 1, 0},
+                              {1, 0, 2, 0, 0, 0}, {1, 0, 2, 1, 1, 1}, {1, 0, 2, 2, 0, 1}, {1, 0, 2, 2, 1, 0}};
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    double P[3][3], Q[3][3];
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+      const uint64_t v = e2v[e * 3 + n];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        P[n][k] = xyz[v * 3 + k];
+        Q[n][k] = P[n][k] + disp[v * 3 + k];
+      }
+    }
+    double gd0[3][3], nrm[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      gd0[0][k] = P[1][k] - P[0][k];
+      gd0[1][k] = P[2][k] - P[0][k];
+    }
+    cross3(nrm, gd0[0], gd0[1]);
+    const double area0 = sqrt(dot3(nrm, nrm)) * 0.5;
+    {
+      const double inv = 0.5 / area0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gd0[2][k] = nrm[k] * inv;
+    }
+    double gu0[2][3];
+    cross3(gu0[0], gd0[1], gd0[2]);
+    {
+      const double inv = 1.0 / dot3(gu0[0], gd0[0]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gu0[0][k] *= inv;
+    }
+    cross3(gu0[1], gd0[2], gd0[0]);
+    {
+      const double inv = 1.0 / dot3(gu0[1], gd0[1]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gu0[1][k] *= inv;
+    }
+    double gd[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      gd[0][k] = Q[1][k] - Q[0][k];
+      gd[1][k] = Q[2][k] - Q[0][k];
+    }
+    const double gl[3] = {0.5 * (dot3(gd[0], gd[0]) - dot3(gd0[0], gd0[0])), 0.5 * (dot3(gd[1], gd[1]) - dot3(gd0[1], gd0[1])),
+                          1.0 * (dot3(gd[0], gd[1]) - dot3(gd0[0], gd0[1]))};
+    const double g[3] = {dot3(gu0[0], gu0[0]), dot3(gu0[1], gu0[1]), dot3(gu0[1], gu0[0])};
+    const double E[3][3] = {
+        {lambda * g[0] * g[0] + 2.0 * myu * (g[0] * g[0]), lambda * g[0] * g[1] + 2.0 * myu * (g[2] * g[2]),
+         lambda * g[0] * g[2] + 2.0 * myu * (g[0] * g[2])},
+        {lambda * g[1] * g[0] + 2.0 * myu * (g[2] * g[2]), lambda * g[1] * g[1] + 2.0 * myu * (g[1] * g[1]),
+         lambda * g[1] * g[2] + 2.0 * myu * (g[2] * g[1])},
+        {lambda * g[2] * g[0] + 2.0 * myu * (g[0] * g[2]), lambda * g[2] * g[1] + 2.0 * myu * (g[2] * g[1]),
+         lambda * g[2] * g[2] + 1.0 * myu * (g[0] * g[1] + g[2] * g[2])}};
+    double S[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) S[s] = E[s][0] * gl[0] + E[s][1] * gl[1] + E[s][2] * gl[2];
+    if (w_out) w_out[e] = 0.5 * area0 * (gl[0] * S[0] + gl[1] * S[1] + gl[2] * S[2]);
+    if (evec) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          evec[e * 9 + i * 3 + a] = area0 * (S[0] * gd[0][a] * (double)dN[i][0] + S[2] * gd[0][a] * (double)dN[i][1] +
+                                             S[2] * gd[1][a] * (double)dN[i][0] + S[1] * gd[1][a] * (double)dN[i][1]);
+    }
+    if (emat) {
+      double *out = emat + e * 81;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double M[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) M[k] = (gd[T[k].p][a] * E[T[k].x][T[k].y]) * gd[T[k].q][b];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              double t = 0.0;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int sg = dN[i][T[k].r] * dN[j][T[k].s];
+                if (sg > 0) t += M[k];
+                if (sg < 0) t -= M[k];
+              }
+              t *= area0;
+              if (a == b)
+                t += area0 * (S[0] * (double)dN[i][0] * (double)dN[j][0] + S[2] * (double)dN[i][0] * (double)dN[j][1] +
+                              S[2] * (double)dN[i][1] * (double)dN[j][0] + S[1] * (double)dN[i][1] * (double)dN[j][1]);
+              out[(i * 3 + j) * 9 + a + 3 * b] = t;
+            }
+        }
+    }
+  }
+}
+
+// ---- quadratic bending hinge: energy p0/2 |w|^2 of the hinge vector w = sum_n k_n x_n of quadratic_bending::wdw
+// (del-fem-cpu/src/quadratic_bending.rs:1-43; the energy/Hessian is DERIVED: w is linear in x, so H_ij = p0 k_i k_j I_3).
+// Element = 4-node hinge (0,1 = wing vertices, 2-3 = shared edge; triangles (0,2,3) and (1,3,2)).
+__device__ __forceinline__ double tri3_area(const double *a, const double *b, const double *c) {
+  double u[3], v[3], n[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    u[k] = b[k] - a[k];
+    v[k] = c[k] - a[k];
+  }
+  cross3(n, u, v);
+  return sqrt(dot3(n, n)) * 0.5;
+}
+__global__ void __launch_bounds__(128) k_bending_quad(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                      const double *__restrict__ disp, uint64_t num_elem, double stiffness,
+                                                      double *__restrict__ emat, double *__restrict__ evec, double *__restrict__ w_out) {
+  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
+    double P[4][3], Q[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const uint64_t v = e2v[e * 4 + n];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        P[n][k] = xyz[v * 3 + k];
+        Q[n][k] = P[n][k] + disp[v * 3 + k];
+      }
+    }
+    const double area0 = tri3_area(P[0], P[2], P[3]);
+    const double area1 = tri3_area(P[1], P[3], P[2]);
+    double e23[3], e02[3], e03[3], e12[3], e13[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      e23[k] = P[3][k] - P[2][k];
+      e02[k] = P[2][k] - P[0][k];
+      e03[k] = P[3][k] - P[0][k];
+      e12[k] = P[2][k] - P[1][k];
+      e13[k] = P[3][k] - P[1][k];
+    }
+    const double len = sqrt(dot3(e23, e23));
+    const double h0 = 2.0 * area0 / len;
+    const double h1 = 2.0 * area1 / len;
+    const double cot023 = -dot3(e02, e23) / h0;
+    const double cot032 = dot3(e03, e23) / h0;
+    const double cot123 = -dot3(e12, e23) / h1;
+    const double cot132 = dot3(e13, e23) / h1;
+    const double tmp0 = sqrt(3.0) / (sqrt(area0 + area1) * len);
+    const double k[4] = {(-cot023 - cot032) * tmp0, (-cot123 - cot132) * tmp0, (cot032 + cot132) * tmp0, (cot023 + cot123) * tmp0};
+    double c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) c[d] = k[0] * Q[0][d] + k[1] * Q[1][d] + k[2] * Q[2][d] + k[3] * Q[3][d];
+    if (w_out) w_out[e] = 0.5 * stiffness * (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    if (evec) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) evec[e * 12 + n * 3 + d] = (stiffness * k[n]) * c[d];
+    }
+    if (emat) {
+      double *out = emat + e * 144;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double v = (stiffness * k[i]) * k[j];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) out[(i * 4 + j) * 9 + q] = (q == 0 || q == 4 || q == 8) ? v : 0.0;
+        }
+    }
+  }
+}
+
 DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *mesh, double p0, double p1, const dfb_vec *disp,
                                   double *emat_dev, double *evec_dev, double *w_dev) {
   DFB_REQUIRE(ctx && mesh, "dfb_emat_batch: NULL argument");
@@ -856,6 +1048,23 @@ DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *me
       DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
                   "dfb_emat_batch: spring3 needs a displacement vector covering every mesh vertex");
       DFB_LAUNCH(ctx, k_spring3, (unsigned)g, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, emat_dev, evec_dev, w_dev);
+      break;
+    }
+    case DFB_ELEM_STVK_TRI3: {
+      DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
+                  "dfb_emat_batch: stvk_tri3 needs a displacement vector covering every mesh vertex");
+      uint64_t g2 = (mesh->num_elem + 63) / 64;
+      if (g2 < 1) g2 = 1;
+      if (g2 > (uint64_t)ctx->sm_count * 32) g2 = (uint64_t)ctx->sm_count * 32;
+      DFB_LAUNCH(ctx, k_stvk_tri3, (unsigned)g2, 64, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, p1, emat_dev, evec_dev,
+                 w_dev);
+      break;
+    }
+    case DFB_ELEM_BENDING_QUAD: {
+      DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
+                  "dfb_emat_batch: bending_quad needs a displacement vector covering every mesh vertex");
+      DFB_LAUNCH(ctx, k_bending_quad, (unsigned)g, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, disp->d, mesh->num_elem, p0, emat_dev, evec_dev,
+                 w_dev);
       break;
     }
     default:
@@ -933,11 +1142,13 @@ __global__ void __launch_bounds__(256) k_sum(const double *__restrict__ a, uint6
 }
 
 // energy-model assembly (two-phase): Hessian -> m (deterministic gather), gradient -> dw, energy -> *w.
-// kinds: DFB_ELEM_NEOHOOKEAN_TET (p0 = myu, p1 = lambda), DFB_ELEM_SPRING3 (p0 = stiffness)
+// kinds: DFB_ELEM_NEOHOOKEAN_TET (p0 = myu, p1 = lambda), DFB_ELEM_SPRING3 (p0 = stiffness), DFB_ELEM_STVK_TRI3 (p0 = lambda,
+// p1 = myu), DFB_ELEM_BENDING_QUAD (p0 = stiffness)
 DFB_API dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1,
                                        dfb_bsr *m, dfb_vec *dw, double *w) {
   DFB_REQUIRE(plan && mesh && disp && m, "dfb_assemble_energy: NULL argument");
-  DFB_REQUIRE(kind == DFB_ELEM_NEOHOOKEAN_TET || kind == DFB_ELEM_SPRING3, "dfb_assemble_energy: kind %d is not an energy model", kind);
+  DFB_REQUIRE(kind == DFB_ELEM_NEOHOOKEAN_TET || kind == DFB_ELEM_SPRING3 || kind == DFB_ELEM_STVK_TRI3 || kind == DFB_ELEM_BENDING_QUAD,
+              "dfb_assemble_energy: kind %d is not an energy model", kind);
   const ElemInfo info = elem_info(kind);
   DFB_REQUIRE(plan->pat->convention == 0 && plan->flavour == 0, "dfb_assemble_energy: needs a convention-0 / flavour-0 plan");
   DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble_energy: matrix and plan use different patterns");
@@ -980,7 +1191,7 @@ DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *m
 DFB_API dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2xyz, double p0, double p1, double *emat) {
   DFB_REQUIRE(ctx && node2xyz && emat, "dfb_emat_one: NULL argument");
   const ElemInfo info = elem_info(kind);
-  DFB_REQUIRE(info.n_node != 0 && kind != DFB_ELEM_NEOHOOKEAN_TET && kind != DFB_ELEM_SPRING3, "dfb_emat_one: unsupported kind %d", kind);
+  DFB_REQUIRE(info.n_node != 0 && kind <= DFB_ELEM_SOLID_LINEAR_TET, "dfb_emat_one: unsupported kind %d", kind);
   uint32_t conn[4] = {0, 1, 2, 3};
   dfb_mesh *mesh = nullptr;
   DFB_TRY(dfb_mesh_create_u32(ctx, conn, 1, info.n_node, node2xyz, info.n_node, info.ndim, &mesh));

@@ -214,6 +214,23 @@ DFB_API dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_v
   return DFB_OK;
 }
 
+// values of m += alpha * values of other (same pattern object): sums matrices assembled from different element families
+__global__ void k_axpy_values(double *__restrict__ y, double alpha, const double *__restrict__ x, uint64_t n) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) y[q] += alpha * x[q];
+}
+
+DFB_API dfb_status dfb_bsr_add_scaled(dfb_bsr *m, double alpha, const dfb_bsr *other) {
+  DFB_REQUIRE(m && other, "dfb_bsr_add_scaled: NULL argument");
+  DFB_REQUIRE(m->pat == other->pat && m->blk_dim == other->blk_dim, "dfb_bsr_add_scaled: matrices must share pattern and block size");
+  m->packed_valid = 0;
+  const uint64_t NN = (uint64_t)m->blk_dim * m->blk_dim;
+  const uint64_t n_off = m->pat->nnz * NN;
+  if (n_off) DFB_LAUNCH(m->ctx, k_axpy_values, m->ctx->sm_count * 8, 256, 0, m->d_idx2val, alpha, other->d_idx2val, n_off);
+  if (m->d_row2val) DFB_LAUNCH(m->ctx, k_axpy_values, m->ctx->sm_count * 8, 256, 0, m->d_row2val, alpha, other->d_row2val, m->pat->num_blk * NN);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 // single-element merge (API-parity shim; merge_for_array_blk / ls merge / csrdia / blkcsr). One thread.
 __global__ void k_merge_one(const double *__restrict__ emat, const uint32_t *__restrict__ node2vtx, int n_node, int NN,
                             int flavour, int convention, const uint32_t *__restrict__ row2idx,

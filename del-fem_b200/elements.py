@@ -82,7 +82,8 @@ def assemble_neohookean_tet(plan, mesh: Mesh, disp: Vec, myu, lam, mat, dw: Vec 
 
 
 def assemble_energy(plan, kind, mesh: Mesh, disp: Vec, p0, p1, mat, dw: Vec = None):
-    """generic energy-model assembly: Hessian -> mat, gradient -> dw, returns the energy (neohookean_tet | spring3)"""
+    """generic energy-model assembly: Hessian -> mat, gradient -> dw, returns the energy
+    (neohookean_tet | spring3 | stvk_tri3 | bending_quad)"""
     k = ELEM[kind] if isinstance(kind, str) else kind
     w = C.c_double()
     check(lib().dfb_assemble_energy(plan.h, k, mesh.h, disp.h, float(p0), float(p1), mat.h, dw.h if dw is not None else None, C.byref(w)))

@@ -83,6 +83,10 @@ class Matrix:
     def add_to_diagonal(self, scale, v: Vec):
         check(lib().dfb_bsr_add_to_diagonal(self.h, float(scale), v.h))
 
+    def add_scaled(self, alpha, other: "Matrix"):
+        """values(self) += alpha * values(other); both matrices must have been created on the same Pattern"""
+        check(lib().dfb_bsr_add_scaled(self.h, float(alpha), other.h))
+
     def set_halo(self, halo, int_begin, int_end):
         check(lib().dfb_bsr_set_halo(self.h, halo.h if halo is not None else None, int_begin, int_end))
         self.halo = halo

@@ -57,7 +57,9 @@ enum {
   DFB_ELEM_LAPLACE_TET = 3,       /* DERIVED from laplace_tri2.rs:12-15                                            N=1, 4 nodes, xyz */
   DFB_ELEM_SOLID_LINEAR_TET = 4,  /* DERIVED from solid_linear_tri2.rs:11-19 + solid_linear_hex.rs:18-25           N=3, 4 nodes, xyz */
   DFB_ELEM_NEOHOOKEAN_TET = 5,    /* DERIVED from solid_incompressive_hex.rs:86-148 (chain rule), 4 nodes          N=3, 4 nodes, xyz */
-  DFB_ELEM_SPRING3 = 6            /* spring3::wdwddw_squared_length_difference  del-fem-cpu/src/spring3.rs:1       N=3, 2 nodes, xyz */
+  DFB_ELEM_SPRING3 = 6,           /* spring3::wdwddw_squared_length_difference  del-fem-cpu/src/spring3.rs:1       N=3, 2 nodes, xyz */
+  DFB_ELEM_STVK_TRI3 = 7,         /* stvk_tri3::wdwddw_                     del-fem-cpu/src/stvk_tri3.rs:152       N=3, 3 nodes, xyz */
+  DFB_ELEM_BENDING_QUAD = 8       /* energy k/2 |w|^2 DERIVED from quadratic_bending::wdw  quadratic_bending.rs:1  N=3, 4 nodes, xyz */
 };
 
 /* preconditioner kinds */
@@ -167,6 +169,9 @@ dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcfla
 dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, dfb_vec *x);
 /* row2val[i][d + N d] += scale * v[i][d]  — inertia / damping on the diagonal (rod3_darboux.rs:1219-1226) */
 dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_vec *v);
+/* values(m) += alpha * values(other); both on the SAME pattern handle. Sums Hessians of different element families (the reference
+   merges them into one matrix in one loop nest, rod3_darboux.rs:760-850) */
+dfb_status dfb_bsr_add_scaled(dfb_bsr *m, double alpha, const dfb_bsr *other);
 /* single-element merge shims (API parity with the reference's per-element calls; one tiny launch each):
    merge_for_array_blk sparse_square.rs:180-214 (flavour 0) / ls merge :66-104 (flavour 1) / csrdia merge.rs:3 /
    blkcsr merge.rs:51 (chosen by the pattern's convention). emat is [n_node][n_node][N*N] on the host. */
@@ -191,7 +196,9 @@ dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev, dfb_bs
 dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, const dfb_vec *disp, double myu,
                                        double lambda, dfb_bsr *m, dfb_vec *dw, double *w);
 /* generic energy-model assembly (two-phase): kinds DFB_ELEM_NEOHOOKEAN_TET (p0 = myu, p1 = lambda) and DFB_ELEM_SPRING3 (p0 = stiffness,
-   mesh = edges, rest positions = mesh coordinates; del-fem-cpu/src/spring3.rs:1 merged as in rod3_darboux.rs:775-792) */
+   mesh = edges, rest positions = mesh coordinates; del-fem-cpu/src/spring3.rs:1 merged as in rod3_darboux.rs:775-792),
+   DFB_ELEM_STVK_TRI3 (p0 = lambda, p1 = myu, mesh = surface triangles; stvk_tri3.rs:152-330) and DFB_ELEM_BENDING_QUAD
+   (p0 = stiffness, mesh = 4-node hinges (wing, wing, edge, edge); quadratic_bending.rs:1-43) */
 dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1,
                                dfb_bsr *m, dfb_vec *dw, double *w);
 /* one element on host arrays (tests): node2xyz [n_node][ndim], out emat [n_node][n_node][N*N] */

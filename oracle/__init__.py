@@ -138,6 +138,41 @@ def spring3_wdwddw(stiffness, node2xyz_def, edge_length_ini):
     return w.value, dw, ddw
 
 
+def stvk_tri3_wdw(p_ini, p_def):
+    """del-fem-cpu/src/stvk_tri3.rs:9-98 -> (w[3], dw[3][3][3] = dw[strain][node][dim])"""
+    w = np.zeros(3)
+    dw = np.zeros((3, 3, 3))
+    lib().orc_stvk_tri3_wdw(_p(_f64(p_ini)), _p(_f64(p_def)), _p(w), _p(dw))
+    return w, dw
+
+
+def stvk_tri3_wdwddw(p0, p1, lam, myu):
+    """del-fem-cpu/src/stvk_tri3.rs:152-330 -> (w, dw[3][3], ddw[3][3][9] with idim*3+jdim)"""
+    w = C.c_double(0)
+    dw = np.zeros((3, 3))
+    ddw = np.zeros((3, 3, 9))
+    lib().orc_stvk_tri3_wdwddw(_p(_f64(p0)), _p(_f64(p1)), C.c_double(lam), C.c_double(myu), C.byref(w), _p(dw), _p(ddw))
+    return w.value, dw, ddw
+
+
+def quadratic_bending_wdw(p_ini, p_def):
+    """del-fem-cpu/src/quadratic_bending.rs:1-43 -> (w[3], dwdp[3][4][3], k[4])"""
+    w = np.zeros(3)
+    dwdp = np.zeros((3, 4, 3))
+    k = np.zeros(4)
+    lib().orc_quadratic_bending_wdw(_p(_f64(p_ini)), _p(_f64(p_def)), _p(w), _p(dwdp), _p(k))
+    return w, dwdp, k
+
+
+def quadratic_bending_wdwddw(stiffness, p_ini, p_def):
+    """DERIVED energy stiffness/2 |w|^2 of quadratic_bending.rs:1-43 -> (w, dw[4][3], ddw[4][4][9] column-major)"""
+    w = C.c_double(0)
+    dw = np.zeros((4, 3))
+    ddw = np.zeros((4, 4, 9))
+    lib().orc_quadratic_bending_wdwddw(C.c_double(stiffness), _p(_f64(p_ini)), _p(_f64(p_def)), C.byref(w), _p(dw), _p(ddw))
+    return w.value, dw, ddw
+
+
 # ---------------------------------------------------------------- meshes / pattern
 def kuhn_tet_mesh(nx, ny=None, nz=None, h=None):
     """SURVEY B.6 synthetic mesh: (elem2vtx [ne,4] u64, vtx2xyz [nv,3])"""
@@ -257,6 +292,22 @@ def assemble_spring3(edge2vtx, vtx2xyz, vtx2disp, stiffness, row2idx, idx2col):
     w = C.c_double(0)
     _chk(lib().orc_assemble_spring3(_p(e2v), C.c_uint64(e2v.shape[0]), _p(_f64(vtx2xyz)), _p(_f64(vtx2disp)), C.c_double(stiffness),
                                     _p(row2idx), C.c_uint64(nb), _p(idx2col), _p(row2val), _p(idx2val), _p(dw), C.byref(w)))
+    return w.value, dw, row2val, idx2val
+
+
+def assemble_cloth(kind, elem2vtx, vtx2xyz, vtx2disp, p0, p1, row2idx, idx2col):
+    """kind "stvk_tri3" (p0 = lambda, p1 = myu; stvk_tri3.rs:152) or "bending_quad" (p0 = stiffness; DERIVED from
+    quadratic_bending.rs:1) whole-mesh loop -> (w, dw, row2val, idx2val)"""
+    kid = {"stvk_tri3": 0, "bending_quad": 1}[kind]
+    e2v = _u64(elem2vtx).reshape(-1, 3 if kid == 0 else 4)
+    nb = row2idx.size - 1
+    row2val = np.zeros((nb, 9))
+    idx2val = np.zeros((idx2col.size, 9))
+    dw = np.zeros((nb, 3))
+    w = C.c_double(0)
+    _chk(lib().orc_assemble_cloth(C.c_int(kid), _p(e2v), C.c_uint64(e2v.shape[0]), _p(_f64(vtx2xyz)), _p(_f64(vtx2disp)),
+                                  C.c_double(p0), C.c_double(p1), _p(row2idx), C.c_uint64(nb), _p(idx2col), _p(row2val),
+                                  _p(idx2val), _p(dw), C.byref(w)))
     return w.value, dw, row2val, idx2val
 
 

@@ -386,6 +386,185 @@ ORC_API void orc_spring3_wdwddw(double stiffness, const double *node2xyz_def /*[
   *w = 0.5 * stiffness * c * c;
 }
 
+static inline void orc_cross3(double *o, const double *a, const double *b) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline double orc_dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// stvk_tri3::wdw   del-fem-cpu/src/stvk_tri3.rs:9-98 — 2-D Green-Lagrange strain of a triangle (rest shape in the plane)
+// and its derivative w.r.t. the deformed corner positions.  out: w[3], dw[3][3][3] = dw[strain][node][dim].
+// del_geo_core::vec3::{cross,norm,scale,normalize} restated from their definitions (source unseen).
+ORC_API void orc_stvk_tri3_wdw(const double *p_ini /*[3][2]*/, const double *p_def /*[3][3]*/, double *w, double *dw) {
+  const double gd0_x[3] = {p_ini[2] - p_ini[0], p_ini[3] - p_ini[1], 0.0};
+  const double gd0_y[3] = {p_ini[4] - p_ini[0], p_ini[5] - p_ini[1], 0.0};
+  double gd0_z[3];
+  orc_cross3(gd0_z, gd0_x, gd0_y);
+  const double area0 = std::sqrt(orc_dot3(gd0_z, gd0_z)) * 0.5;
+  const double sc = 1.0 / (area0 * 2.0);
+  for (int k = 0; k < 3; ++k) gd0_z[k] *= sc;
+  double gu0_x[3], gu0_y[3];
+  orc_cross3(gu0_x, gd0_y, gd0_z);
+  {
+    const double il = 1.0 / std::sqrt(orc_dot3(gu0_x, gu0_x));
+    for (int k = 0; k < 3; ++k) gu0_x[k] *= il;
+  }
+  orc_cross3(gu0_y, gd0_z, gd0_x);
+  {
+    const double il = 1.0 / std::sqrt(orc_dot3(gu0_y, gu0_y));
+    for (int k = 0; k < 3; ++k) gu0_y[k] *= il;
+  }
+  const double gd1_x[3] = {p_def[3] - p_def[0], p_def[4] - p_def[1], p_def[5] - p_def[2]};
+  const double gd1_y[3] = {p_def[6] - p_def[0], p_def[7] - p_def[1], p_def[8] - p_def[2]};
+  const double gl[3] = {0.5 * (orc_dot3(gd1_x, gd1_x) - orc_dot3(gd0_x, gd0_x)),
+                        0.5 * (orc_dot3(gd1_y, gd1_y) - orc_dot3(gd0_y, gd0_y)),
+                        orc_dot3(gd1_x, gd1_y) - orc_dot3(gd0_x, gd0_y)};
+  const double gg[3][3] = {
+      {gu0_x[0] * gu0_x[0], gu0_y[0] * gu0_y[0], gu0_x[0] * gu0_y[0]},
+      {gu0_x[1] * gu0_x[1], gu0_y[1] * gu0_y[1], gu0_x[1] * gu0_y[1]},
+      {2.0 * gu0_x[0] * gu0_x[1], 2.0 * gu0_y[0] * gu0_y[1], gu0_x[0] * gu0_y[1] + gu0_x[1] * gu0_y[0]}};
+  for (int s = 0; s < 3; ++s) {
+    w[s] = gl[0] * gg[s][0] + gl[1] * gg[s][1] + gl[2] * gg[s][2];
+    const double ab[3][2] = {{-(gg[s][0] + gg[s][2]), -(gg[s][1] + gg[s][2])}, {gg[s][0], gg[s][2]}, {gg[s][2], gg[s][1]}};
+    for (int n = 0; n < 3; ++n)
+      for (int d = 0; d < 3; ++d) dw[(s * 3 + n) * 3 + d] = ab[n][0] * gd1_x[d] + ab[n][1] * gd1_y[d];
+  }
+}
+
+// stvk_tri3::wdwddw_   del-fem-cpu/src/stvk_tri3.rs:152-330 — St.Venant-Kirchhoff membrane energy of a 3-D triangle,
+// gradient dw[3][3] and Hessian ddw[3][3][9] with the reference's index  ddw[ino][jno][idim*3 + jdim].
+// del_geo_core::tri3::unit_normal_area (source unseen) = (n/|n|, |n|/2) with n = (p1-p0) x (p2-p0).
+ORC_API void orc_stvk_tri3_wdwddw(const double *p0 /*[3][3] rest*/, const double *p1 /*[3][3] deformed*/, double lambda, double myu,
+                                  double *w, double *dw, double *ddw) {
+  double gd0[3][3];
+  for (int k = 0; k < 3; ++k) {
+    gd0[0][k] = p0[3 + k] - p0[k];
+    gd0[1][k] = p0[6 + k] - p0[k];
+  }
+  double nrm[3];
+  orc_cross3(nrm, gd0[0], gd0[1]);
+  const double area0 = std::sqrt(orc_dot3(nrm, nrm)) * 0.5;
+  {
+    const double inv = 0.5 / area0;
+    for (int k = 0; k < 3; ++k) gd0[2][k] = nrm[k] * inv;
+  }
+  double gu0[2][3];
+  orc_cross3(gu0[0], gd0[1], gd0[2]);
+  {
+    const double inv = 1.0 / orc_dot3(gu0[0], gd0[0]);
+    for (int k = 0; k < 3; ++k) gu0[0][k] *= inv;
+  }
+  orc_cross3(gu0[1], gd0[2], gd0[0]);
+  {
+    const double inv = 1.0 / orc_dot3(gu0[1], gd0[1]);
+    for (int k = 0; k < 3; ++k) gu0[1][k] *= inv;
+  }
+  double gd[2][3];
+  for (int k = 0; k < 3; ++k) {
+    gd[0][k] = p1[3 + k] - p1[k];
+    gd[1][k] = p1[6 + k] - p1[k];
+  }
+  const double gl[3] = {0.5 * (orc_dot3(gd[0], gd[0]) - orc_dot3(gd0[0], gd0[0])),
+                        0.5 * (orc_dot3(gd[1], gd[1]) - orc_dot3(gd0[1], gd0[1])),
+                        1.0 * (orc_dot3(gd[0], gd[1]) - orc_dot3(gd0[0], gd0[1]))};
+  const double g[3] = {orc_dot3(gu0[0], gu0[0]), orc_dot3(gu0[1], gu0[1]), orc_dot3(gu0[1], gu0[0])};
+  const double E[3][3] = {
+      {lambda * g[0] * g[0] + 2.0 * myu * (g[0] * g[0]), lambda * g[0] * g[1] + 2.0 * myu * (g[2] * g[2]),
+       lambda * g[0] * g[2] + 2.0 * myu * (g[0] * g[2])},
+      {lambda * g[1] * g[0] + 2.0 * myu * (g[2] * g[2]), lambda * g[1] * g[1] + 2.0 * myu * (g[1] * g[1]),
+       lambda * g[1] * g[2] + 2.0 * myu * (g[2] * g[1])},
+      {lambda * g[2] * g[0] + 2.0 * myu * (g[0] * g[2]), lambda * g[2] * g[1] + 2.0 * myu * (g[2] * g[1]),
+       lambda * g[2] * g[2] + 1.0 * myu * (g[0] * g[1] + g[2] * g[2])}};
+  double S[3];
+  for (int s = 0; s < 3; ++s) S[s] = E[s][0] * gl[0] + E[s][1] * gl[1] + E[s][2] * gl[2];
+  *w = 0.5 * area0 * (gl[0] * S[0] + gl[1] * S[1] + gl[2] * S[2]);
+  static const double dN[3][2] = {{-1.0, -1.0}, {1.0, 0.0}, {0.0, 1.0}};
+  for (int i = 0; i < 3; ++i)
+    for (int a = 0; a < 3; ++a)
+      dw[i * 3 + a] = area0 * (S[0] * gd[0][a] * dN[i][0] + S[2] * gd[0][a] * dN[i][1] + S[2] * gd[1][a] * dN[i][0] +
+                               S[1] * gd[1][a] * dN[i][1]);
+  // the 16 material terms of :282-313 in their order: (row edge p, row dN column r, E entry, col edge q, col dN column s)
+  static const int T[16][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 1, 1, 1}, {0, 0, 0, 2, 0, 1}, {0, 0, 0, 2, 1, 0},
+                               {1, 1, 1, 0, 0, 0}, {1, 1, 1, 1, 1, 1}, {1, 1, 1, 2, 0, 1}, {1, 1, 1, 2, 1, 0},
+                               {0, 1, 2, 0, 0, 0}, {0, 1, 2, 1, 1, 1}, {0, 1, 2, 2, 0, 1}, {0, 1, 2, 2, 1, 0},
+                               {1, 0, 2, 0, 0, 0}, {1, 0, 2, 1, 1, 1}, {1, 0, 2, 2, 0, 1}, {1, 0, 2, 2, 1, 0}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          double t = 0.0;
+          for (int k = 0; k < 16; ++k) t += gd[T[k][0]][a] * dN[i][T[k][1]] * E[T[k][2]][T[k][3]] * gd[T[k][4]][b] * dN[j][T[k][5]];
+          ddw[(i * 3 + j) * 9 + a * 3 + b] = t * area0;
+        }
+      const double t1 = area0 * (S[0] * dN[i][0] * dN[j][0] + S[2] * dN[i][0] * dN[j][1] + S[2] * dN[i][1] * dN[j][0] +
+                                 S[1] * dN[i][1] * dN[j][1]);
+      ddw[(i * 3 + j) * 9 + 0] += t1;
+      ddw[(i * 3 + j) * 9 + 4] += t1;
+      ddw[(i * 3 + j) * 9 + 8] += t1;
+    }
+}
+
+// quadratic_bending::wdw   del-fem-cpu/src/quadratic_bending.rs:1-43 — hinge "bending vector" w[3] = sum_n k_n p_def[n] of the two
+// triangles (0,2,3),(1,3,2) sharing edge 2-3, and dwdp[3][4][3] (= k_n on the diagonal).  Also returns k[4].
+// del_geo_core::tri3::area = |(b-a)x(c-a)|/2, edge::length = |b-a| (source unseen).
+ORC_API void orc_quadratic_bending_wdw(const double *p_ini /*[4][3]*/, const double *p_def /*[4][3]*/, double *w, double *dwdp,
+                                       double *k_out) {
+  auto sub = [](double *o, const double *a, const double *b) {
+    for (int k = 0; k < 3; ++k) o[k] = a[k] - b[k];
+  };
+  auto tri_area = [&](const double *a, const double *b, const double *c) {
+    double u[3], v[3], n[3];
+    sub(u, b, a);
+    sub(v, c, a);
+    orc_cross3(n, u, v);
+    return std::sqrt(orc_dot3(n, n)) * 0.5;
+  };
+  const double *q0 = p_ini, *q1 = p_ini + 3, *q2 = p_ini + 6, *q3 = p_ini + 9;
+  const double area0 = tri_area(q0, q2, q3);
+  const double area1 = tri_area(q1, q3, q2);
+  double e23[3], e02[3], e03[3], e12[3], e13[3];
+  sub(e23, q3, q2);
+  sub(e02, q2, q0);
+  sub(e03, q3, q0);
+  sub(e12, q2, q1);
+  sub(e13, q3, q1);
+  const double len = std::sqrt(orc_dot3(e23, e23));
+  const double h0 = 2.0 * area0 / len;
+  const double h1 = 2.0 * area1 / len;
+  const double cot023 = -orc_dot3(e02, e23) / h0;
+  const double cot032 = orc_dot3(e03, e23) / h0;
+  const double cot123 = -orc_dot3(e12, e23) / h1;
+  const double cot132 = orc_dot3(e13, e23) / h1;
+  const double tmp0 = std::sqrt(3.0) / (std::sqrt(area0 + area1) * len);
+  const double k[4] = {(-cot023 - cot032) * tmp0, (-cot123 - cot132) * tmp0, (cot032 + cot132) * tmp0, (cot023 + cot123) * tmp0};
+  for (int d = 0; d < 3; ++d) w[d] = k[0] * p_def[d] + k[1] * p_def[3 + d] + k[2] * p_def[6 + d] + k[3] * p_def[9 + d];
+  if (dwdp) {
+    for (int q = 0; q < 36; ++q) dwdp[q] = 0.0;
+    for (int d = 0; d < 3; ++d)
+      for (int n = 0; n < 4; ++n) dwdp[(d * 4 + n) * 3 + d] = k[n];
+  }
+  if (k_out)
+    for (int n = 0; n < 4; ++n) k_out[n] = k[n];
+}
+
+// DERIVED (not in the reference): energy W = stiffness/2 |w|^2 of the hinge vector above.  w is linear in p_def, so the
+// Hessian block (i,j) is exactly stiffness k_i k_j I_3 and the gradient stiffness k_i w.  "parity unpinned".
+ORC_API void orc_quadratic_bending_wdwddw(double stiffness, const double *p_ini, const double *p_def, double *w, double *dw,
+                                          double *ddw /*[4][4][9]*/) {
+  double c[3], k[4];
+  orc_quadratic_bending_wdw(p_ini, p_def, c, nullptr, k);
+  *w = 0.5 * stiffness * (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  for (int n = 0; n < 4; ++n)
+    for (int d = 0; d < 3; ++d) dw[n * 3 + d] = (stiffness * k[n]) * c[d];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const double v = (stiffness * k[i]) * k[j];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) ddw[(i * 4 + j) * 9 + a + 3 * b] = (a == b) ? v : 0.0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // synthetic meshes — test/bench inputs, not part of the reference
 // ---------------------------------------------------------------------------------------------
@@ -696,6 +875,43 @@ ORC_API int orc_assemble_spring3(const usize *edge2vtx, usize num_edge, const do
     for (int n = 0; n < 2; ++n)
       for (int k = 0; k < 3; ++k) dw_out[nv[n] * 3 + k] += dw[n * 3 + k];
     int rc = orc_merge_for_array_blk(9, 2, nv, ddw, row2idx, num_blk, idx2col, row2val, idx2val, col2idx.data(), 0);
+    if (rc) return rc;
+  }
+  *w_out = wsum;
+  return ORC_OK;
+}
+
+// cloth membrane / hinge whole-mesh loops (the "remaining element kernels" of SURVEY §8(f)-4; same loop shape as above):
+// kind 0: stvk_tri3::wdwddw_ per triangle (p0 = lambda, p1 = myu), Hessian transposed a*3+b -> a+3b when merged;
+// kind 1: DERIVED quadratic-bending energy per hinge quad (p0 = stiffness).
+// Rest positions = vtx2xyz, deformed = vtx2xyz + vtx2disp.
+ORC_API int orc_assemble_cloth(int kind, const usize *elem2vtx, usize num_elem, const double *vtx2xyz, const double *vtx2disp,
+                               double p0, double p1, const usize *row2idx, usize num_blk, const usize *idx2col, double *row2val,
+                               double *idx2val, double *dw_out, double *w_out) {
+  if (kind != 0 && kind != 1) return ORC_PANIC;
+  const int nn = kind == 0 ? 3 : 4;
+  std::vector<usize> col2idx(num_blk, USIZE_MAX);
+  double wsum = 0.0;
+  for (usize e = 0; e < num_elem; ++e) {
+    const usize *nv = elem2vtx + e * nn;
+    double rest[12], def[12], w, dw[12], ddw[144], emat[144];
+    for (int n = 0; n < nn; ++n)
+      for (int k = 0; k < 3; ++k) {
+        rest[n * 3 + k] = vtx2xyz[nv[n] * 3 + k];
+        def[n * 3 + k] = vtx2xyz[nv[n] * 3 + k] + vtx2disp[nv[n] * 3 + k];
+      }
+    if (kind == 0) {
+      orc_stvk_tri3_wdwddw(rest, def, p0, p1, &w, dw, ddw);
+      for (int ij = 0; ij < 9; ++ij)
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) emat[ij * 9 + a + 3 * b] = ddw[ij * 9 + a * 3 + b];
+    } else {
+      orc_quadratic_bending_wdwddw(p0, rest, def, &w, dw, emat);
+    }
+    wsum += w;
+    for (int n = 0; n < nn; ++n)
+      for (int k = 0; k < 3; ++k) dw_out[nv[n] * 3 + k] += dw[n * 3 + k];
+    int rc = orc_merge_for_array_blk(9, nn, nv, emat, row2idx, num_blk, idx2col, row2val, idx2val, col2idx.data(), 0);
     if (rc) return rc;
   }
   *w_out = wsum;

@@ -222,6 +222,100 @@ def test_config3_mass_spring_cloth_steps_match_oracle(dfb, ctx, orc):
     assert disp[:, 2].min() < -1e-4  # the cloth falls
 
 
+def _grid_cloth(nx, ny):
+    gx, gy = np.meshgrid(np.arange(nx) / (nx - 1), np.arange(ny) / (nx - 1))
+    return np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(nx * ny)], 1))
+
+
+@pytest.mark.parametrize("kind", ["stvk_tri3", "bending_quad"])
+def test_cloth_element_families_match_oracle(dfb, ctx, orc, kind):
+    """stvk_tri3::wdwddw_ (stvk_tri3.rs:152-330) and the quadratic-bending hinge energy (quadratic_bending.rs:1-43), batched:
+    element matrices, merged Hessian, gathered gradient and energy against the oracle's per-element loop"""
+    from del_fem_b200 import elements
+    from del_fem_b200.cloth import hinges_of_tri_mesh, tris_of_grid_cloth
+    nx, ny = 19, 14
+    rest = _grid_cloth(nx, ny)
+    nv = rest.shape[0]
+    tris = tris_of_grid_cloth(nx, ny)
+    e2v, nn, p0, p1 = (tris, 3, 1.3, 1.9) if kind == "stvk_tri3" else (hinges_of_tri_mesh(tris), 4, 0.7, 0.0)
+    if kind == "bending_quad":
+        assert e2v.shape[0] == (nx - 1) * ny + nx * (ny - 1) + (nx - 1) * (ny - 1) - 2 * (nx - 1) - 2 * (ny - 1)  # interior edges
+    rng = np.random.default_rng(5)
+    disp = 0.03 * rng.standard_normal((nv, 3))
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, nn, nv, False)
+    w_o, dw_o, rv_o, iv_o = orc.assemble_cloth(kind, e2v, rest, disp, p0, p1, r2i, i2c)
+    mesh = dfb.Mesh(ctx, e2v, rest)
+    pat = dfb.Pattern(ctx, r2i, i2c, 0)
+    plan = dfb.Plan(ctx, pat, mesh, 0)
+    mat = dfb.Matrix(ctx, pat, 3)
+    d = dfb.Vec.from_numpy(ctx, disp)
+    g = dfb.Vec(ctx, nv, 3)
+    w_d = elements.assemble_energy(plan, kind, mesh, d, p0, p1, mat, g)
+    rv_d, iv_d = mat.download()
+    scale = max(np.abs(rv_o).max(), np.abs(iv_o).max())
+    assert np.abs(rv_d - rv_o).max() <= 1e-12 * scale and np.abs(iv_d - iv_o).max() <= 1e-12 * scale
+    assert np.abs(g.download() - dw_o).max() <= 1e-12 * max(1.0, np.abs(dw_o).max())
+    assert abs(w_d - w_o) <= 1e-12 * max(1.0, abs(w_o))
+    # one element through the batch entry point against the reference-layout element function
+    nvs = np.asarray(e2v[7], dtype=np.int64)
+    emat, evec, wv = elements.emat_batch(ctx, kind, mesh, p0, p1, d, want_evec=True, want_w=True)
+    if kind == "stvk_tri3":
+        we, dwe, ddwe = orc.stvk_tri3_wdwddw(rest[nvs], rest[nvs] + disp[nvs], p0, p1)
+        ref = ddwe.reshape(3, 3, 3, 3).transpose(0, 1, 3, 2).reshape(3, 3, 9)  # a*3+b -> a+3b
+    else:
+        we, dwe, ref = orc.quadratic_bending_wdwddw(p0, rest[nvs], rest[nvs] + disp[nvs])
+    assert np.abs(emat[7] - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(evec[7] - dwe).max() <= 1e-13 * max(1.0, np.abs(dwe).max())
+    assert abs(wv[7] - we) <= 1e-13 * max(1.0, abs(we))
+
+
+def test_stvk_cloth_steps_match_oracle(dfb, ctx, orc):
+    """config 3 with the StVK alternative: membrane + bending merged on one pattern, implicit steps state for state"""
+    from del_fem_b200.cloth import StVKCloth, hinges_of_tri_mesh, tris_of_grid_cloth
+    nx, ny = 15, 11
+    rest = _grid_cloth(nx, ny)
+    nv = rest.shape[0]
+    tris = tris_of_grid_cloth(nx, ny)
+    quads = hinges_of_tri_mesh(tris)
+    flag = np.zeros((nv, 3), dtype=np.int32)
+    flag[0] = 1
+    flag[nx - 1] = 1
+    lam, myu, kb, mass, dt = 20.0, 30.0, 1e-3, 1.0 / nv, 1e-2
+    grav = np.array([0.0, 0.0, -9.8])
+    cloth = StVKCloth(ctx, tris, rest, flag, lam, myu, kb, mass, gravity=grav)
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(quads, 4, nv, False)
+    r_d, c_d = cloth.pat.download()
+    assert np.array_equal(r_d, r2i) and np.array_equal(c_d, i2c)
+    rng = np.random.default_rng(2)
+    disp = 1e-3 * rng.standard_normal((nv, 3))
+    disp[flag != 0] = 0.0
+    vel = np.zeros((nv, 3))
+    f = mass * np.tile(grav, (nv, 1))
+    for step in range(4):
+        cloth.disp.upload(disp)
+        cloth.vel.upload(vel)
+        w_d, it_d = cloth.step(dt, 1e-8, 2000)
+        vel[flag != 0] = 0.0
+        x_tmp = disp + dt * vel
+        w_m, dw_m, rv, iv = orc.assemble_cloth("stvk_tri3", tris, rest, x_tmp, lam, myu, r2i, i2c)
+        w_b, dw_b, rv_b, iv_b = orc.assemble_cloth("bending_quad", quads, rest, x_tmp, kb, 0.0, r2i, i2c)
+        rv, iv = rv + rv_b, iv + iv_b
+        g = (dw_m + dw_b) - f
+        rv[:, [0, 4, 8]] += mass / (dt * dt)
+        orc.set_fix_dof_to_rhs_vector(g, flag)
+        orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+        u, ap, p = np.zeros_like(g), np.zeros_like(g), np.zeros_like(g)
+        hist = orc.conjugate_gradient(g, u, ap, p, 1e-8, 2000, r2i, i2c, iv, rv)
+        x_new = x_tmp - u
+        vel = (x_new - disp) / dt
+        disp = x_new
+        assert abs(w_d - (w_m + w_b)) <= 1e-11 * max(1.0, abs(w_m + w_b))
+        assert abs(it_d - len(hist)) <= 2
+        assert rel_err(cloth.disp.download(), disp) < 1e-6
+        assert rel_err(cloth.vel.download(), vel) < 1e-4
+    assert disp[:, 2].min() < -1e-4
+
+
 def test_numpy_shaped_api(dfb, ctx, orc):
     """del-fem-numpy's flat-array functions + the reference's own Python test (tests/test_laplace.py:22-30)"""
     from del_fem_b200 import numpy_api as na

@@ -347,6 +347,115 @@ def test_spring3_fd(orc):
             assert np.abs((dw1 - dw0) / eps - ana).max() < 1e-5
 
 
+# ---------------------------------------------------------------------------------- cloth elements (SURVEY §8(c) golden vectors)
+def test_stvk_tri3_strain_fd(orc):
+    """stvk_tri3.rs:121-141: FD of the 2-D Green-Lagrange strain, the reference's triangle, eps 1e-6, tol 1e-5"""
+    p_ini = np.array([[0.1, 0.2], [0.2, 0.1], [0.3, 0.4]])
+    p0 = np.array([[0.31, 0.04, 0.38], [0.13, 0.13, 0.07], [0.03, 0.42, 0.35]])
+    w0, dw = orc.stvk_tri3_wdw(p_ini, p0)
+    eps = 1.0e-6
+    for i_no in range(3):
+        for i_dim in range(3):
+            p1 = p0.copy()
+            p1[i_no, i_dim] += eps
+            w1, _ = orc.stvk_tri3_wdw(p_ini, p1)
+            assert np.abs(dw[:, i_no, i_dim] - (w1 - w0) / eps).max() < 1.0e-5
+
+
+STVK_TRIS = [
+    ([[1.2, 2.1, 3.4], [3.5, 5.2, 4.3], [3.4, 4.8, 2.4]], [[3.1, 2.2, 1.5], [4.3, 3.6, 2.0], [5.2, 4.5, 3.4]]),
+    ([[3.1, 5.0, 1.3], [2.0, 1.8, 3.4], [5.6, 2.4, 3.3]], [[2.5, 1.0, 3.2], [0.3, 4.6, 1.2], [3.2, 5.5, 1.4]]),
+]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_stvk_tri3_wdwddw_fd(orc, case):
+    """stvk_tri3.rs:333-362 test_wdwddw_cst: lambda 1.3, myu 1.9, eps 1e-5, tol 1e-4, the reference's two triangles"""
+    lam, myu = 1.3, 1.9
+    pos0, pos1 = (np.array(a) for a in STVK_TRIS[case])
+    w0, dw0, ddw0 = orc.stvk_tri3_wdwddw(pos0, pos1, lam, myu)
+    eps = 1.0e-5
+    for ino in range(3):
+        for idim in range(3):
+            pa = pos1.copy()
+            pa[ino, idim] += eps
+            w1, dw1, _ = orc.stvk_tri3_wdwddw(pos0, pa, lam, myu)
+            assert abs((w1 - w0) / eps - dw0[ino, idim]) < 1.0e-4
+            num = (dw1 - dw0) / eps  # [jno][jdim]
+            ana = ddw0[:, ino, :].reshape(3, 3, 3)[:, :, idim]  # ddw[jno][ino][jdim*3 + idim]
+            assert np.abs(num - ana).max() < 1.0e-4
+    # rigid motion of the rest triangle: zero energy and gradient; Hessian is symmetric as a 9x9 matrix
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    w, dw, _ = orc.stvk_tri3_wdwddw(pos0, pos0 @ R.T + 0.3, lam, myu)
+    assert abs(w) < 1e-12 and np.abs(dw).max() < 1e-11
+    H = ddw0.reshape(3, 3, 3, 3).transpose(0, 2, 1, 3).reshape(9, 9)
+    assert np.abs(H - H.T).max() < 1e-12 * np.abs(H).max()
+
+
+def test_quadratic_bending_fd(orc):
+    """quadratic_bending.rs:45-79: the reference's hinge quad, eps 1e-5, tol 1e-6; plus the derived energy's FD"""
+    p_ini = np.array([[0.1, 0.2, 0.3], [0.2, 0.1, 0.5], [0.3, 0.4, 0.3], [0.5, 0.2, 0.4]])
+    p0 = np.array([[0.11, 0.04, 0.38], [0.22, 0.13, 0.07], [0.03, 0.42, 0.35], [0.54, 0.01, 0.46]])
+    c0, dcdp, k = orc.quadratic_bending_wdw(p_ini, p0)
+    eps = 1.0e-5
+    for i_no in range(4):
+        for i_dim in range(3):
+            p1 = p0.copy()
+            p1[i_no, i_dim] += eps
+            c1, _, _ = orc.quadratic_bending_wdw(p_ini, p1)
+            assert np.abs(dcdp[:, i_no, i_dim] - (c1 - c0) / eps).max() < 1.0e-6
+    assert abs(k.sum()) < 1e-12  # translation invariance of the hinge vector
+    w0, dw0, ddw0 = orc.quadratic_bending_wdwddw(2.5, p_ini, p0)
+    assert abs(w0 - 0.5 * 2.5 * (c0 @ c0)) < 1e-14
+    for i_no in range(4):
+        for i_dim in range(3):
+            p1 = p0.copy()
+            p1[i_no, i_dim] += eps
+            w1, dw1, _ = orc.quadratic_bending_wdwddw(2.5, p_ini, p1)
+            assert abs((w1 - w0) / eps - dw0[i_no, i_dim]) < 1e-3 * max(1.0, abs(dw0[i_no, i_dim]))
+            ana = ddw0[:, i_no, :].reshape(4, 3, 3)[:, :, i_dim]  # block (j,i), entry (b, a) at b + 3a
+            assert np.abs((dw1 - dw0) / eps - ana).max() < 1e-6 * max(1.0, np.abs(ana).max())
+
+
+def test_assemble_cloth_matches_dense(orc):
+    """whole-mesh StVK / hinge loops: merged matrix == dense sum of element Hessians; gradient == sum of element gradients"""
+    from del_fem_b200.cloth import hinges_of_tri_mesh
+    t2v, xy = orc.grid_tri_mesh(5)
+    nv = xy.shape[0]
+    xyz = np.concatenate([xy, np.zeros((nv, 1))], axis=1)
+    rng = np.random.default_rng(3)
+    disp = 0.05 * rng.standard_normal((nv, 3))
+    quads = hinges_of_tri_mesh(t2v)
+    for kind, e2v, nn, p0, p1 in (("stvk_tri3", t2v, 3, 1.3, 1.9), ("bending_quad", quads, 4, 0.7, 0.0)):
+        r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, nn, nv, False)
+        w, dw, rv, iv = orc.assemble_cloth(kind, e2v, xyz, disp, p0, p1, r2i, i2c)
+        K = np.zeros((nv, 3, nv, 3))
+        g = np.zeros((nv, 3))
+        wsum = 0.0
+        for nvs in np.asarray(e2v, dtype=np.int64):
+            rest, dfm = xyz[nvs], xyz[nvs] + disp[nvs]
+            if kind == "stvk_tri3":
+                we, dwe, ddwe = orc.stvk_tri3_wdwddw(rest, dfm, p0, p1)
+                blk = ddwe.reshape(3, 3, 3, 3)  # [i][j][a][b]
+            else:
+                we, dwe, ddwe = orc.quadratic_bending_wdwddw(p0, rest, dfm)
+                blk = ddwe.reshape(4, 4, 3, 3).transpose(0, 1, 3, 2)  # a + 3b -> [a][b]
+            wsum += we
+            g[nvs] += dwe
+            for i in range(nn):
+                for j in range(nn):
+                    K[nvs[i], :, nvs[j], :] += blk[i, j]
+        assert abs(w - wsum) < 1e-12 * max(1.0, abs(wsum))
+        assert np.abs(dw - g).max() < 1e-12 * max(1.0, np.abs(g).max())
+        D = np.zeros_like(K)
+        for r in range(nv):
+            D[r, :, r, :] = rv[r].reshape(3, 3).T  # column-major a + 3b
+            for q in range(r2i[r], r2i[r + 1]):
+                D[r, :, int(i2c[q]), :] = iv[q].reshape(3, 3).T
+        assert np.abs(D - K).max() < 1e-12 * np.abs(K).max()
+
+
 # ---------------------------------------------------------------------------------- config 1: 2-D Poisson on the disk
 def test_config1_poisson_disk(orc):
     t2v, xy = orc.grid_tri_mesh(100, disk=True)
