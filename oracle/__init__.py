@@ -41,6 +41,7 @@ def lib():
         _lib.orc_vtx2vtx_from_uniform_mesh.restype = C.c_uint64
         _lib.orc_conjugate_gradient.restype = C.c_int64
         _lib.orc_preconditioned_conjugate_gradient.restype = C.c_int64
+        _lib.orc_pcg_jacobi3_mt.restype = C.c_int64
         _lib.orc_ilu_new.restype = C.c_void_p
         _lib.orc_ilu_row2val.restype = C.POINTER(C.c_double)
         _lib.orc_version.restype = C.c_char_p
@@ -413,3 +414,11 @@ def preconditioned_conjugate_gradient(r, x, pr, p, tol, max_it, row2idx, idx2col
         C.c_uint64(row2idx.size - 1), _p(idx2col), _p(idx2val), _p(row2val), ilu.h,
         C.c_double(EPS_CPU if flavour == "cpu" else EPS_LS), _p(hist))
     return hist[:nh].copy()
+
+
+def pcg_jacobi3_mt(nthreads, r, x, pr, p, tol, max_it, row2idx, idx2col, idx2val, row2val, eps_sq=0.0):
+    """BASELINE-TIMING AID: row-parallel (std::thread) Jacobi-PCG, 3x3 blocks, A12 history semantics"""
+    hist = np.zeros(max_it + 2)
+    nh = lib().orc_pcg_jacobi3_mt(C.c_int(nthreads), _p(r), _p(x), _p(pr), _p(p), C.c_double(tol), C.c_uint64(max_it), _p(row2idx),
+                                  C.c_uint64(row2idx.size - 1), _p(idx2col), _p(idx2val), _p(row2val), C.c_double(eps_sq), _p(hist))
+    return hist[:nh]

@@ -23,6 +23,7 @@
 // (entry (a,b) of an NxN block at a + N*b) exactly as `del_geo_core::matn_col_major`.
 // =============================================================================================
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cmath>
 #include <cstdint>
@@ -30,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <thread>
 #include <vector>
 
 typedef uint64_t usize;
@@ -1294,6 +1296,138 @@ ORC_API int64_t orc_preconditioned_conjugate_gradient(usize n, double *r, double
   }
   hist[nh++] = std::sqrt(dot_n(n, r, r, num_blk));
   return (int64_t)nh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BASELINE-TIMING AID (not a restatement): the same Jacobi-PCG (A12 history semantics) with the rows split over `nthreads`
+// std::threads — what a maintainer would get from a row-parallel (rayon-style) version of the reference loop.  The reference
+// itself is single-threaded on this path; bench.py reports this beside the faithful 1-thread number.  Dots are summed per
+// thread then over threads in thread order, so results differ from the strict left fold in the last bits.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SpinBarrier {
+  std::atomic<int> count{0};
+  std::atomic<int> gen{0};
+  int n;
+  explicit SpinBarrier(int n_) : n(n_) {}
+  void wait() {
+    const int g = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+      count.store(0, std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (gen.load(std::memory_order_acquire) == g)
+        if (++spins > 2000) std::this_thread::yield();
+    }
+  }
+};
+}  // namespace
+
+ORC_API int64_t orc_pcg_jacobi3_mt(int nthreads, double *r, double *x, double *pr, double *p, double tol, usize max_it,
+                                   const usize *row2idx, usize num_blk, const usize *idx2col, const double *idx2val,
+                                   const double *row2val, double eps_sq, double *hist) {
+  if (nthreads < 1) nthreads = 1;
+  const int T = nthreads;
+  // row ranges balanced by the number of blocks
+  std::vector<usize> rb(T + 1, num_blk);
+  rb[0] = 0;
+  {
+    const usize total = row2idx[num_blk] + num_blk;
+    usize i = 0;
+    for (int t = 1; t < T; ++t) {
+      const usize target = total / T * t;
+      while (i < num_blk && row2idx[i] + i < target) ++i;
+      rb[t] = i;
+    }
+  }
+  std::vector<double> part(3 * (size_t)T * 8, 0.0);  // padded: one cache line per (thread, slot)
+  std::vector<double> dinv(num_blk * 3);
+  SpinBarrier bar(T);
+  std::atomic<int64_t> nh_out{0};
+  auto worker = [&](int t) {
+    const usize r0 = rb[t], r1 = rb[t + 1];
+    auto reduce = [&](int slot, double v) {
+      part[((size_t)slot * T + t) * 8] = v;
+      bar.wait();
+      double s = 0.0;
+      for (int q = 0; q < T; ++q) s += part[((size_t)slot * T + q) * 8];
+      return s;
+    };
+    int64_t nh = 0;
+    double a0 = 0.0, a1 = 0.0;
+    for (usize i = r0; i < r1; ++i)
+      for (int d = 0; d < 3; ++d) {
+        const usize q = i * 3 + d;
+        dinv[q] = 1.0 / row2val[i * 9 + d + 3 * d];
+        x[q] = 0.0;
+        a0 += r[q] * r[q];
+        pr[q] = dinv[q] * r[q];
+        p[q] = pr[q];
+        a1 += r[q] * pr[q];
+      }
+    const double sq0 = reduce(0, a0);
+    double rpr = reduce(1, a1);
+    if (t == 0) hist[nh] = std::sqrt(sq0);
+    ++nh;
+    if (sq0 < eps_sq) {
+      if (t == 0) nh_out = nh;
+      return;
+    }
+    const double inv0 = 1.0 / sq0;
+    for (usize it = 0; it < max_it; ++it) {
+      double pap_t = 0.0;
+      for (usize i = r0; i < r1; ++i) {
+        double y[3] = {0.0, 0.0, 0.0};
+        for (usize k = row2idx[i]; k < row2idx[i + 1]; ++k) {
+          const double *b = idx2val + k * 9;
+          const double *xv = p + idx2col[k] * 3;
+          for (int a = 0; a < 3; ++a) y[a] += b[a] * xv[0] + b[a + 3] * xv[1] + b[a + 6] * xv[2];
+        }
+        const double *b = row2val + i * 9;
+        const double *xv = p + i * 3;
+        for (int a = 0; a < 3; ++a) {
+          y[a] += b[a] * xv[0] + b[a + 3] * xv[1] + b[a + 6] * xv[2];
+          pr[i * 3 + a] = y[a];
+          pap_t += xv[a] * y[a];
+        }
+      }
+      const double pap = reduce(2, pap_t);
+      const double alpha = rpr / pap;
+      double rr_t = 0.0, rz_t = 0.0;
+      for (usize q = r0 * 3; q < r1 * 3; ++q) {
+        r[q] -= alpha * pr[q];
+        x[q] += alpha * p[q];
+        rr_t += r[q] * r[q];
+        pr[q] = dinv[q] * r[q];
+        rz_t += r[q] * pr[q];
+      }
+      const double rr = reduce(0, rr_t);
+      const double rz = reduce(1, rz_t);
+      if (t == 0) hist[nh] = std::sqrt(rr);
+      ++nh;
+      if (std::sqrt(rr * inv0) < tol) {
+        if (t == 0) nh_out = nh;
+        return;
+      }
+      const double beta = rz / rpr;
+      rpr = rz;
+      for (usize q = r0 * 3; q < r1 * 3; ++q) p[q] = pr[q] + beta * p[q];
+      bar.wait();  // p complete before the next SpMV reads it
+    }
+    double rr_t = 0.0;
+    for (usize q = r0 * 3; q < r1 * 3; ++q) rr_t += r[q] * r[q];
+    const double rr = reduce(0, rr_t);
+    if (t == 0) {
+      hist[nh] = std::sqrt(rr);
+      nh_out = nh + 1;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto &q : th) q.join();
+  return nh_out.load();
 }
 
 ORC_API const char *orc_version(void) { return "delfem-oracle 0.1 (restates del-fem 0.1.9 hot path)"; }

@@ -495,3 +495,31 @@ def test_ls_mult_mat(orc):
     orc.ls_mult_mat(y, 0.5, 2.0, x, r2i, i2c, iv.reshape(-1), rv.reshape(-1))
     L = csr_from_csrdia(r2i, i2c, rv, iv, 1)
     assert np.allclose(y, 0.5 + 2.0 * (L @ x), atol=1e-12)
+
+
+def test_threaded_baseline_pcg_agrees_with_the_oracle_pcg(orc):
+    """bench.py's row-parallel CPU baseline (orc_pcg_jacobi3_mt) is the same iteration as the A12 restatement with Jacobi"""
+    nx = 10
+    e2v, xyz = orc.kuhn_tet_mesh(nx)
+    nv = xyz.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rv, iv = orc.assemble("solid_linear_tet", 0, e2v, xyz, 1.0, 1.0, r2i, i2c)
+    flag = np.zeros((nv, 3), dtype=np.int32)
+    flag[: nx * nx] = 1
+    u0 = orc.splitmix_fill(0, 0, 3 * nv, -0.1, 0.1).reshape(nv, 3)
+    u0[flag != 0] = 0.0
+    rhs = np.zeros((nv, 3))
+    orc.mult_vec(rhs, 0.0, -1.0, u0, r2i, i2c, iv, rv)
+    orc.set_fix_dof_to_rhs_vector(rhs, flag)
+    orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+    ilu = orc.Ilu("jacobi", 3, r2i, i2c)
+    ilu.copy_value(r2i, i2c, iv, rv)
+    ilu.decompose()
+    r, x, pr, p = rhs.copy(), np.zeros_like(rhs), np.zeros_like(rhs), np.zeros_like(rhs)
+    h1 = orc.preconditioned_conjugate_gradient(r, x, pr, p, 1e-8, 1000, r2i, i2c, iv, rv, ilu)
+    for nt in (1, 3):
+        r2, x2, pr2, p2 = rhs.copy(), np.zeros_like(rhs), np.zeros_like(rhs), np.zeros_like(rhs)
+        h2 = orc.pcg_jacobi3_mt(nt, r2, x2, pr2, p2, 1e-8, 1000, r2i, i2c, iv, rv)
+        assert len(h2) == len(h1)
+        assert np.abs(h2 - h1).max() <= 1e-9 * h1[0]
+        assert np.abs(x2 - x).max() <= 1e-9 * np.abs(x).max()
