@@ -132,6 +132,7 @@ def lib():
         "dfb_assemble_from_emat": [_vp, _vp, _vp],
         "dfb_assemble_neohookean_tet": [_vp, _vp, _vp, _f64, _f64, _vp, _vp, C.POINTER(_f64)],
         "dfb_assemble_energy": [_vp, _i32, _vp, _vp, _f64, _f64, _vp, _vp, C.POINTER(_f64)],
+        "dfb_lumped_mass": [_vp, _vp, _f64, _vp],
         "dfb_emat_one": [_vp, _i32, _vp, _f64, _f64, _vp],
         "dfb_malloc": [_vp, _u64, _pp],
         "dfb_free": [_vp, _vp],

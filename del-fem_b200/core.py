@@ -8,8 +8,8 @@ import numpy as np
 from ._lib import DfbError, check, lib
 
 ELEM = {"laplace_tri2": 0, "cot_laplace_tri3": 1, "solid_linear_tri2": 2, "laplace_tet": 3, "solid_linear_tet": 4,
-        "neohookean_tet": 5, "spring3": 6, "stvk_tri3": 7, "bending_quad": 8}
-ELEM_INFO = {0: (3, 2, 1), 1: (3, 3, 1), 2: (3, 2, 2), 3: (4, 3, 1), 4: (4, 3, 3), 5: (4, 3, 3), 6: (2, 3, 3), 7: (3, 3, 3), 8: (4, 3, 3)}
+        "neohookean_tet": 5, "spring3": 6, "stvk_tri3": 7, "bending_quad": 8, "mass_tet": 9}
+ELEM_INFO = {0: (3, 2, 1), 1: (3, 3, 1), 2: (3, 2, 2), 3: (4, 3, 1), 4: (4, 3, 3), 5: (4, 3, 3), 6: (2, 3, 3), 7: (3, 3, 3), 8: (4, 3, 3), 9: (4, 3, 3)}
 PRECOND = {"none": 0, "jacobi": 1, "block_jacobi": 2, "ilu0": 3}
 
 

@@ -32,6 +32,7 @@ __host__ __device__ inline ElemInfo elem_info(int kind) {
     case DFB_ELEM_SPRING3: return {2, 3, 3};
     case DFB_ELEM_STVK_TRI3: return {3, 3, 3};
     case DFB_ELEM_BENDING_QUAD: return {4, 3, 3};
+    case DFB_ELEM_MASS_TET: return {4, 3, 3};
   }
   return {0, 0, 0};
 }
@@ -156,6 +157,20 @@ template <> struct ElemGeo<DFB_ELEM_SOLID_LINEAR_TET> {  // DERIVED
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) e[a + 3 * a] += vol * myu * dtmp1;
+  }
+};
+
+template <> struct ElemGeo<DFB_ELEM_MASS_TET> {  // DERIVED (SURVEY A9'): consistent tet mass rho V / 20 (1 + delta_ij) I_3
+  static constexpr int NNODE = 4, NDIM = 3, N = 3;
+  double vol;
+  __device__ void init(const double *const *p, double, double) {
+    double g[4][3];
+    vol = tet_vol_grad(g, p[0], p[1], p[2], p[3]);
+  }
+  __device__ void block(int i, int j, double rho, double, double *e) const {
+    const double v = rho * vol / 20.0 * (i == j ? 2.0 : 1.0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) e[q] = (q == 0 || q == 4 || q == 8) ? v : 0.0;
   }
 };
 
@@ -414,6 +429,15 @@ template <> struct NodeOps<DFB_ELEM_SOLID_LINEAR_TET> {
     for (int a = 0; a < 3; ++a) e[a + 3 * a] += vol * myu * dtmp1;
   }
 };
+template <> struct NodeOps<DFB_ELEM_MASS_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_MASS_TET> &g, int i) { return {{(double)i, 0.0, 0.0, g.vol}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double rho, double, double *e) {
+    const double v = rho * a.v[3] / 20.0 * (a.v[0] == b.v[0] ? 2.0 : 1.0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) e[q] = (q == 0 || q == 4 || q == 8) ? v : 0.0;
+  }
+};
 template <> struct NodeOps<DFB_ELEM_COT_LAPLACE_TRI3> {
   static constexpr bool OK = false;  // the cotangent block of (i,j) needs the angle at the THIRD corner: stays on the ElemGeo path
   __device__ static NodeRec make(const ElemGeo<DFB_ELEM_COT_LAPLACE_TRI3> &, int) { return {{0, 0, 0, 0}}; }
@@ -570,6 +594,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
       REC_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
       REC_CASE(DFB_ELEM_LAPLACE_TET)
       REC_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+      REC_CASE(DFB_ELEM_MASS_TET)
       default:
         return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
     }
@@ -602,6 +627,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
       GEO_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
       GEO_CASE(DFB_ELEM_LAPLACE_TET)
       GEO_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+      GEO_CASE(DFB_ELEM_MASS_TET)
       default:
         return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
     }
@@ -620,6 +646,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     ASM_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
     ASM_CASE(DFB_ELEM_LAPLACE_TET)
     ASM_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+    ASM_CASE(DFB_ELEM_MASS_TET)
     default:
       return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
   }
@@ -1034,6 +1061,7 @@ DFB_API dfb_status dfb_emat_batch(dfb_ctx *ctx, int32_t kind, const dfb_mesh *me
     EM_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
     EM_CASE(DFB_ELEM_LAPLACE_TET)
     EM_CASE(DFB_ELEM_SOLID_LINEAR_TET)
+    EM_CASE(DFB_ELEM_MASS_TET)
     case DFB_ELEM_NEOHOOKEAN_TET: {
       DFB_REQUIRE(disp && disp->blk_dim == 3 && disp->n_blk + disp->n_ghost >= mesh->num_vtx,
                   "dfb_emat_batch: neo-Hookean needs a displacement vector covering every mesh vertex");
@@ -1187,11 +1215,75 @@ DFB_API dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *m
   return dfb_assemble_energy(plan, DFB_ELEM_NEOHOOKEAN_TET, mesh, disp, myu, lambda, m, dw, w);
 }
 
+// ---- lumped mass (DERIVED, SURVEY A9'; loop shape of mitc_tri3::mass_lumped_plate_bending, mitc_tri3.rs:321-331): every node of an
+// element receives measure / n_node * rho.  Deterministic gather: row r walks the contribution list of its DIAGONAL slot, whose
+// entries (e, i, i) are in ascending element order — the same order as the reference-style serial loop, hence the same bits.
+template <int NNODE, int NDIM>
+__global__ void __launch_bounds__(128) k_lumped_mass(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib, uint64_t nnz,
+                                                     uint64_t num_rows, const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                     double rho, int N, double *__restrict__ out) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (uint32_t c = nz2ptr[nnz + r]; c < nz2ptr[nnz + r + 1]; ++c) {
+      const uint64_t e = contrib[c] / (NNODE * NNODE);
+      double P[NNODE][NDIM];
+#pragma unroll
+      for (int n = 0; n < NNODE; ++n) {
+        const uint64_t v = e2v[e * NNODE + n];
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) P[n][d] = __ldg(&xyz[v * NDIM + d]);
+      }
+      double meas;
+      if constexpr (NNODE == 3 && NDIM == 2) {
+        meas = tri2_area(P[0], P[1], P[2]);
+      } else if constexpr (NNODE == 3 && NDIM == 3) {
+        const double u[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
+        const double v[3] = {P[2][0] - P[0][0], P[2][1] - P[0][1], P[2][2] - P[0][2]};
+        const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        meas = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * 0.5;
+      } else {
+        double g[4][3];
+        meas = tet_vol_grad(g, P[0], P[1], P[2], P[3]);
+      }
+      acc += meas / (double)NNODE * rho;
+    }
+    for (int d = 0; d < N; ++d) out[r * N + d] = acc;
+  }
+}
+
+DFB_API dfb_status dfb_lumped_mass(dfb_plan *plan, const dfb_mesh *mesh, double rho, dfb_vec *out) {
+  DFB_REQUIRE(plan && mesh && out, "dfb_lumped_mass: NULL argument");
+  DFB_REQUIRE(plan->pat->convention == 0 && plan->flavour == 0, "dfb_lumped_mass: needs a convention-0 / flavour-0 plan");
+  DFB_REQUIRE(mesh->num_elem == plan->num_elem && mesh->num_node == plan->num_node, "dfb_lumped_mass: mesh does not match the plan");
+  DFB_REQUIRE(out->n_blk == plan->pat->num_blk, "dfb_lumped_mass: vector has %llu blocks, pattern %llu", (unsigned long long)out->n_blk,
+              (unsigned long long)plan->pat->num_blk);
+  dfb_ctx *c = plan->ctx;
+  const uint64_t nr = plan->pat->num_blk;
+  uint64_t g = (nr + 127) / 128;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+#define LM_CASE(NNODE, NDIM)                                                                                                          \
+  DFB_LAUNCH(c, (k_lumped_mass<NNODE, NDIM>), (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, plan->pat->nnz, nr, mesh->d_elem2vtx, \
+             mesh->d_xyz, rho, out->blk_dim, out->d)
+  if (mesh->num_node == 3 && mesh->ndim == 2) {
+    LM_CASE(3, 2);
+  } else if (mesh->num_node == 3 && mesh->ndim == 3) {
+    LM_CASE(3, 3);
+  } else if (mesh->num_node == 4 && mesh->ndim == 3) {
+    LM_CASE(4, 3);
+  } else {
+    return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_lumped_mass: %d-node elements in %d-D are not supported", mesh->num_node, mesh->ndim);
+  }
+#undef LM_CASE
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 // one element on host arrays (tests / API parity with the reference's by-value element functions)
 DFB_API dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2xyz, double p0, double p1, double *emat) {
   DFB_REQUIRE(ctx && node2xyz && emat, "dfb_emat_one: NULL argument");
   const ElemInfo info = elem_info(kind);
-  DFB_REQUIRE(info.n_node != 0 && kind <= DFB_ELEM_SOLID_LINEAR_TET, "dfb_emat_one: unsupported kind %d", kind);
+  DFB_REQUIRE(info.n_node != 0 && (kind <= DFB_ELEM_SOLID_LINEAR_TET || kind == DFB_ELEM_MASS_TET), "dfb_emat_one: unsupported kind %d", kind);
   uint32_t conn[4] = {0, 1, 2, 3};
   dfb_mesh *mesh = nullptr;
   DFB_TRY(dfb_mesh_create_u32(ctx, conn, 1, info.n_node, node2xyz, info.n_node, info.ndim, &mesh));

@@ -88,3 +88,9 @@ def assemble_energy(plan, kind, mesh: Mesh, disp: Vec, p0, p1, mat, dw: Vec = No
     w = C.c_double()
     check(lib().dfb_assemble_energy(plan.h, k, mesh.h, disp.h, float(p0), float(p1), mat.h, dw.h if dw is not None else None, C.byref(w)))
     return w.value
+
+
+def lumped_mass(plan, mesh: Mesh, rho, out: Vec):
+    """out[v][:] = sum over elements at v of measure / n_node * rho (DERIVED A9'; loop shape of mitc_tri3.rs:304-332)"""
+    check(lib().dfb_lumped_mass(plan.h, mesh.h, float(rho), out.h))
+    return out

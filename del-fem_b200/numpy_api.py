@@ -99,3 +99,41 @@ class LaplacianMatrix:
         else:
             merge_laplace_to_bsr_for_meshtri3(elem2vtx, xyz, row2idx, idx2col, idx2val, ctx)
         return scipy.sparse.csr_matrix((idx2val, idx2col.astype(np.int64), row2idx.astype(np.int64)))
+
+
+class MassMatrix:
+    """del_fem_numpy/MassMatrix.py:3-10 — diagonal (lumped) mass: del_msh_numpy TriMesh.vtx2area (area / 3 per corner) repeated ndim
+    times, as a scipy dia_matrix.  Evaluated by dfb_lumped_mass (rho = 1); also accepts tet meshes (volume / 4 per corner)."""
+
+    @staticmethod
+    def from_uniform_mesh(elem2vtx, vtx2xyz, ndim=1, ctx=None):
+        import scipy.sparse
+        from . import elements
+        ctx = ctx or Ctx.default()
+        xyz = np.ascontiguousarray(vtx2xyz, dtype=np.float64)
+        mesh = Mesh(ctx, np.ascontiguousarray(elem2vtx, dtype=np.uint64), xyz)
+        pat = Pattern.from_uniform_mesh(ctx, mesh, False)
+        plan = Plan(ctx, pat, mesh, 0)
+        out = Vec(ctx, xyz.shape[0], 1)
+        elements.lumped_mass(plan, mesh, 1.0, out)
+        vtx2area = out.download().ravel()
+        n = xyz.shape[0] * ndim
+        return scipy.sparse.dia_matrix((vtx2area.repeat(ndim).reshape(1, -1), np.array([0])), shape=(n, n))
+
+
+class LinearSolid:
+    """del_fem_numpy/LinearSolid.py:3-12 (upstream imports a name that does not exist, `merge_linear_solid_to_csr_for_meshtri2`;
+    the function that exists is `merge_linear_solid_to_bsr_for_meshtri2`, linear_solid.rs:17 — that is the one used here)"""
+
+    @staticmethod
+    def stiffness_matrix_from_uniform_mesh(tri2vtx, vtx2xy, ctx=None):
+        import scipy.sparse
+        ctx = ctx or Ctx.default()
+        xy = np.ascontiguousarray(vtx2xy, dtype=np.float64)
+        mesh = Mesh(ctx, np.ascontiguousarray(tri2vtx, dtype=np.uint64), xy)
+        row2idx, idx2col = Pattern.from_uniform_mesh(ctx, mesh, True).download()
+        idx2val = np.zeros((idx2col.shape[0], 2, 2), dtype=np.float64)
+        merge_linear_solid_to_bsr_for_meshtri2(tri2vtx, xy, row2idx, idx2col, idx2val, ctx)
+        # blocks are column-major (a + 2 b, solid_linear_tri2.rs:11-19); scipy's bsr blocks are row-major [a][b]
+        blocks = idx2val.reshape(-1, 2, 2).transpose(0, 2, 1)
+        return scipy.sparse.bsr_matrix((blocks, idx2col.astype(np.int64), row2idx.astype(np.int64)))

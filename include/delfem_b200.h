@@ -59,7 +59,8 @@ enum {
   DFB_ELEM_NEOHOOKEAN_TET = 5,    /* DERIVED from solid_incompressive_hex.rs:86-148 (chain rule), 4 nodes          N=3, 4 nodes, xyz */
   DFB_ELEM_SPRING3 = 6,           /* spring3::wdwddw_squared_length_difference  del-fem-cpu/src/spring3.rs:1       N=3, 2 nodes, xyz */
   DFB_ELEM_STVK_TRI3 = 7,         /* stvk_tri3::wdwddw_                     del-fem-cpu/src/stvk_tri3.rs:152       N=3, 3 nodes, xyz */
-  DFB_ELEM_BENDING_QUAD = 8       /* energy k/2 |w|^2 DERIVED from quadratic_bending::wdw  quadratic_bending.rs:1  N=3, 4 nodes, xyz */
+  DFB_ELEM_BENDING_QUAD = 8,      /* energy k/2 |w|^2 DERIVED from quadratic_bending::wdw  quadratic_bending.rs:1  N=3, 4 nodes, xyz */
+  DFB_ELEM_MASS_TET = 9           /* DERIVED consistent mass rho V/20 (1+delta_ij) I3 (lumped precedent mitc_tri3.rs:304) N=3, 4 nodes */
 };
 
 /* preconditioner kinds */
@@ -201,6 +202,9 @@ dfb_status dfb_assemble_neohookean_tet(dfb_plan *plan, const dfb_mesh *mesh, con
    (p0 = stiffness, mesh = 4-node hinges (wing, wing, edge, edge); quadratic_bending.rs:1-43) */
 dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1,
                                dfb_bsr *m, dfb_vec *dw, double *w);
+/* lumped mass: out[v][0..N) = sum over elements at v of measure / n_node * rho (tri2 area, tri3 area, tet volume); deterministic
+   gather in ascending element order. DERIVED; loop shape of mitc_tri3::mass_lumped_plate_bending, del-fem-cpu/src/mitc_tri3.rs:304-332 */
+dfb_status dfb_lumped_mass(dfb_plan *plan, const dfb_mesh *mesh, double rho, dfb_vec *out);
 /* one element on host arrays (tests): node2xyz [n_node][ndim], out emat [n_node][n_node][N*N] */
 dfb_status dfb_emat_one(dfb_ctx *ctx, int32_t kind, const double *node2xyz, double p0, double p1, double *emat);
 /* device scratch helpers for the two-phase path */

@@ -174,6 +174,33 @@ def quadratic_bending_wdwddw(stiffness, p_ini, p_def):
     return w.value, dw, ddw
 
 
+def emat_mass_tet(rho, p0, p1, p2, p3):
+    """A9' DERIVED consistent tet mass rho V / 20 (1 + delta_ij) I_3 -> [4][4][9]"""
+    e = np.zeros((4, 4, 9))
+    lib().orc_emat_mass_tet(C.c_double(rho), _p(_f64(p0)), _p(_f64(p1)), _p(_f64(p2)), _p(_f64(p3)), _p(e))
+    return e
+
+
+def mass_lumped_plate_bending(tri2vtx, vtx2xy, thick, rho):
+    """del-fem-cpu/src/mitc_tri3.rs:304-332 -> vtx2mass [nv, 3]"""
+    t2v = _u64(tri2vtx).reshape(-1, 3)
+    xy = _f64(vtx2xy).reshape(-1, 2)
+    out = np.zeros((xy.shape[0], 3))
+    lib().orc_mass_lumped_plate_bending(_p(t2v), C.c_uint64(t2v.shape[0]), _p(xy), C.c_uint64(xy.shape[0]), C.c_double(thick),
+                                        C.c_double(rho), _p(out))
+    return out
+
+
+def lumped_mass(elem2vtx, n_node, vtx2xyz, ndim, rho):
+    """A9' DERIVED lumped mass (measure / n_node * rho per element node), loop shape of mitc_tri3.rs:321-331 -> [nv]"""
+    e2v = _u64(elem2vtx).reshape(-1, n_node)
+    xyz = _f64(vtx2xyz).reshape(-1, ndim)
+    out = np.zeros(xyz.shape[0])
+    _chk(lib().orc_lumped_mass(_p(e2v), C.c_uint64(e2v.shape[0]), C.c_uint64(n_node), _p(xyz), C.c_uint64(xyz.shape[0]),
+                               C.c_uint64(ndim), C.c_double(rho), _p(out)))
+    return out
+
+
 # ---------------------------------------------------------------- meshes / pattern
 def kuhn_tet_mesh(nx, ny=None, nz=None, h=None):
     """SURVEY B.6 synthetic mesh: (elem2vtx [ne,4] u64, vtx2xyz [nv,3])"""
@@ -249,9 +276,9 @@ def merge_for_array_blk(emat, node2vtx, row2idx, idx2col, row2val, idx2val, merg
                                        C.c_uint64(nb), _p(idx2col), _p(row2val), _p(idx2val), _p(buf), C.c_int(flavour)))
 
 
-KIND = {"laplace_tri2": 0, "cot_laplace_tri3": 1, "solid_linear_tri2": 2, "laplace_tet": 3, "solid_linear_tet": 4}
+KIND = {"laplace_tri2": 0, "cot_laplace_tri3": 1, "solid_linear_tri2": 2, "laplace_tet": 3, "solid_linear_tet": 4, "mass_tet": 9}
 KIND_INFO = {  # kind -> (n_node, ndim_x, blk_dim N)
-    0: (3, 2, 1), 1: (3, 3, 1), 2: (3, 2, 2), 3: (4, 3, 1), 4: (4, 3, 3)}
+    0: (3, 2, 1), 1: (3, 3, 1), 2: (3, 2, 2), 3: (4, 3, 1), 4: (4, 3, 3), 9: (4, 3, 3)}
 
 
 def assemble(kind, convention, elem2vtx, vtx2xyz, p0, p1, row2idx, idx2col):

@@ -236,6 +236,60 @@ ORC_API double orc_tet_volume(const double *p0, const double *p1, const double *
   return tet_vol_grad(g, p0, p1, p2, p3);
 }
 
+// A9' (DERIVED) consistent tet mass: block (i,j) = rho V / 20 (1 + delta_ij) I_3, column-major 3x3 blocks.  "parity unpinned".
+ORC_API void orc_emat_mass_tet(double rho, const double *p0, const double *p1, const double *p2, const double *p3, double *emat) {
+  const double vol = orc_tet_volume(p0, p1, p2, p3);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const double v = rho * vol / 20.0 * (i == j ? 2.0 : 1.0);
+      double *e = emat + (i * 4 + j) * 9;
+      for (int q = 0; q < 9; ++q) e[q] = (q == 0 || q == 4 || q == 8) ? v : 0.0;
+    }
+}
+
+// mitc_tri3::mass_lumped_plate_bending   del-fem-cpu/src/mitc_tri3.rs:304-332 (3 dofs per vertex: w, theta_x, theta_y)
+ORC_API void orc_mass_lumped_plate_bending(const usize *tri2vtx, usize num_tri, const double *vtx2xy, usize num_vtx, double thick,
+                                           double rho, double *vtx2mass) {
+  for (usize q = 0; q < num_vtx * 3; ++q) vtx2mass[q] = 0.0;
+  for (usize t = 0; t < num_tri; ++t) {
+    const usize *nv = tri2vtx + t * 3;
+    const double a012 = tri2_area(vtx2xy + nv[0] * 2, vtx2xy + nv[1] * 2, vtx2xy + nv[2] * 2);
+    const double m0 = a012 / 3.0 * rho * thick;
+    const double m1 = a012 / 3.0 * rho * thick * thick * thick / 12.0;
+    for (int n = 0; n < 3; ++n) {
+      vtx2mass[nv[n] * 3] += m0;
+      vtx2mass[nv[n] * 3 + 1] += m1;
+      vtx2mass[nv[n] * 3 + 2] += m1;
+    }
+  }
+}
+
+// A9' (DERIVED) lumped mass of a uniform mesh, same loop shape as mass_lumped_plate_bending (:321-331): every node of an element
+// receives measure / n_node * rho.  measure: tri2 area (n_node 3, ndim 2), tri3 area (3, 3), tet volume (4, 3).
+ORC_API int orc_lumped_mass(const usize *elem2vtx, usize num_elem, usize n_node, const double *vtx2xyz, usize num_vtx, usize ndim,
+                            double rho, double *vtx2mass) {
+  for (usize q = 0; q < num_vtx; ++q) vtx2mass[q] = 0.0;
+  for (usize e = 0; e < num_elem; ++e) {
+    const usize *nv = elem2vtx + e * n_node;
+    double meas;
+    if (n_node == 3 && ndim == 2) {
+      meas = tri2_area(vtx2xyz + nv[0] * 2, vtx2xyz + nv[1] * 2, vtx2xyz + nv[2] * 2);
+    } else if (n_node == 3 && ndim == 3) {
+      const double *a = vtx2xyz + nv[0] * 3, *b = vtx2xyz + nv[1] * 3, *c = vtx2xyz + nv[2] * 3;
+      const double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, v[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+      const double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+      meas = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) * 0.5;
+    } else if (n_node == 4 && ndim == 3) {
+      meas = orc_tet_volume(vtx2xyz + nv[0] * 3, vtx2xyz + nv[1] * 3, vtx2xyz + nv[2] * 3, vtx2xyz + nv[3] * 3);
+    } else {
+      return ORC_PANIC;
+    }
+    const double m0 = meas / (double)n_node * rho;
+    for (usize n = 0; n < n_node; ++n) vtx2mass[nv[n]] += m0;
+  }
+  return ORC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // A15' (DERIVED) tet neo-Hookean  W = mu/2 (trC - 3) - mu ln J + lambda/2 (ln J)^2   
 // energy density + chain rule of solid_incompressive_hex.rs:86-148 with NNODE=4, dndx=g, detwei=V.
@@ -779,7 +833,7 @@ ORC_API int orc_merge_for_array_blk(usize nn, usize n_node, const usize *node2vt
 // whole-mesh assembly loops (caller loops of the reference: solid_linear_tri2.rs:144-161, laplace_tri3.rs:13-29,
 // del-fem-numpy/src/{laplacian.rs:71-103, linear_solid.rs:17-51}); elements in ascending order.
 // kind: 0 tri2 laplace (N=1), 1 tri3 cot-laplace (N=1), 2 tri2 linear solid (N=2),
-//       3 tet laplace (N=1), 4 tet linear solid (N=3)
+//       3 tet laplace (N=1), 4 tet linear solid (N=3), 9 consistent tet mass (N=3, p0 = rho; numbered like DFB_ELEM_MASS_TET)
 // convention: 0 = csrdia (row2val + idx2val), 1 = blkcsr (diag inside idx2val; row2val ignored)
 // ---------------------------------------------------------------------------------------------
 ORC_API int orc_assemble(int kind, int convention, const usize *elem2vtx, usize num_elem, const double *vtx2xyz,
@@ -793,6 +847,7 @@ ORC_API int orc_assemble(int kind, int convention, const usize *elem2vtx, usize 
     case 2: n_node = 3; ndim_x = 2; nn = 4; break;
     case 3: n_node = 4; ndim_x = 3; nn = 1; break;
     case 4: n_node = 4; ndim_x = 3; nn = 9; break;
+    case 9: n_node = 4; ndim_x = 3; nn = 9; break;
     default: return ORC_PANIC;
   }
   double emat[16 * 9];
@@ -809,6 +864,7 @@ ORC_API int orc_assemble(int kind, int convention, const usize *elem2vtx, usize 
       case 2: orc_emat_tri2(p0, p1, p[0], p[1], p[2], emat); break;
       case 3: orc_laplace_tet_ddw(p0, p[0], p[1], p[2], p[3], emat); break;
       case 4: orc_emat_tet(p0, p1, p[0], p[1], p[2], p[3], emat); break;
+      case 9: orc_emat_mass_tet(p0, p[0], p[1], p[2], p[3], emat); break;
     }
     int rc;
     if (convention == 1) {

@@ -316,6 +316,44 @@ def test_stvk_cloth_steps_match_oracle(dfb, ctx, orc):
     assert disp[:, 2].min() < -1e-4
 
 
+def test_mass_matches_oracle(dfb, ctx, orc):
+    """A9' (DERIVED): consistent tet mass through every assembly variant and the lumped mass gather, bit for bit"""
+    from del_fem_b200 import elements
+    from del_fem_b200 import numpy_api as na
+    e2v, xyz = orc.kuhn_tet_mesh(9, 7, 8, 0.2)
+    xyz = xyz + 0.02 * np.random.default_rng(0).standard_normal(xyz.shape)
+    nv = xyz.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rv_o, iv_o = orc.assemble("mass_tet", 0, e2v, xyz, 2.5, 0.0, r2i, i2c)
+    mesh = dfb.Mesh(ctx, e2v, xyz)
+    pat = dfb.Pattern(ctx, r2i, i2c, 0)
+    plan = dfb.Plan(ctx, pat, mesh, 0)
+    mat = dfb.Matrix(ctx, pat, 3)
+    for variant in (0, 1, 2):
+        ctx.set_option("assemble_variant", variant)
+        mat.set_zero()
+        mat.assemble(plan, "mass_tet", mesh, 2.5, 0.0)
+        rv, iv = mat.download()
+        assert np.array_equal(rv, rv_o) and np.array_equal(iv, iv_o), f"assembly variant {variant}"
+    ctx.set_option("assemble_variant", 0)
+    for n in (1, 3):
+        out = dfb.Vec(ctx, nv, n)
+        elements.lumped_mass(plan, mesh, 2.5, out)
+        got = out.download()
+        want = orc.lumped_mass(e2v, 4, xyz, 3, 2.5)
+        assert np.array_equal(got, np.repeat(want[:, None], n, axis=1))
+    # triangles in 2-D and 3-D + the del_fem_numpy MassMatrix wrapper (MassMatrix.py:3-10)
+    t2v, xy = orc.grid_tri_mesh(12, disk=True)
+    for pts, nd in ((xy, 2), (np.ascontiguousarray(np.c_[xy, 0.2 * xy[:, 1] ** 2]), 3)):
+        M = na.MassMatrix.from_uniform_mesh(t2v, pts, ndim=2, ctx=ctx)
+        want = orc.lumped_mass(t2v, 3, pts, nd, 1.0)
+        assert np.array_equal(M.diagonal(), want.repeat(2))
+    K = na.LinearSolid.stiffness_matrix_from_uniform_mesh(t2v, xy, ctx=ctx)
+    assert abs(K - K.T).max() < 1e-12
+    rigid = np.tile([1.0, -2.0], xy.shape[0])
+    assert np.abs(K @ rigid).max() < 1e-12
+
+
 def test_numpy_shaped_api(dfb, ctx, orc):
     """del-fem-numpy's flat-array functions + the reference's own Python test (tests/test_laplace.py:22-30)"""
     from del_fem_b200 import numpy_api as na

@@ -456,6 +456,36 @@ def test_assemble_cloth_matches_dense(orc):
         assert np.abs(D - K).max() < 1e-12 * np.abs(K).max()
 
 
+# ---------------------------------------------------------------------------------- A9' mass
+def test_mass_kernels(orc):
+    """lumped mass sums to rho * measure, the consistent tet mass has the lumped mass as its row sum, and the plate-bending
+    lumped mass (mitc_tri3.rs:304-332) is (A/3 rho t, A/3 rho t^3/12, A/3 rho t^3/12) per corner"""
+    e2v, xyz = orc.kuhn_tet_mesh(5, 4, 6, 0.25)
+    nv = xyz.shape[0]
+    m = orc.lumped_mass(e2v, 4, xyz, 3, 2.5)
+    assert abs(m.sum() - 2.5 * (4 * 0.25) * (3 * 0.25) * (5 * 0.25)) < 1e-12
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rv, iv = orc.assemble("mass_tet", 0, e2v, xyz, 2.5, 0.0, r2i, i2c)
+    rows = rv[:, 0].copy()
+    for r in range(nv):
+        rows[r] += iv[r2i[r]:r2i[r + 1], 0].sum()
+    assert np.abs(rows - m).max() < 1e-14
+    assert np.abs(rv[:, [1, 2, 3, 5, 6, 7]]).max() == 0.0 and np.array_equal(rv[:, 0], rv[:, 4]) and np.array_equal(rv[:, 0], rv[:, 8])
+    em = orc.emat_mass_tet(3.0, *xyz[e2v[0].astype(np.int64)])
+    vol = orc.tet_volume(*xyz[e2v[0].astype(np.int64)])
+    assert abs(em[:, :, 0].sum() - 3.0 * vol) < 1e-15 and abs(em[1, 1, 4] - 2 * em[1, 2, 4]) < 1e-18
+    t2v, xy = orc.grid_tri_mesh(6)
+    ma = orc.lumped_mass(t2v, 3, xy, 2, 1.0)
+    assert abs(ma.sum() - 4.0) < 1e-12  # the square [-1, 1]^2
+    xyz3 = np.c_[xy, 0.3 * xy[:, 0]]
+    m3 = orc.lumped_mass(t2v, 3, xyz3, 3, 1.0)
+    assert abs(m3.sum() - 4.0 * np.sqrt(1 + 0.09)) < 1e-12
+    thick, rho = 0.05, 7.0
+    mp = orc.mass_lumped_plate_bending(t2v, xy, thick, rho)
+    assert np.allclose(mp[:, 0], ma * rho * thick, rtol=1e-14) and np.allclose(mp[:, 1], ma * rho * thick ** 3 / 12, rtol=1e-14)
+    assert np.array_equal(mp[:, 1], mp[:, 2])
+
+
 # ---------------------------------------------------------------------------------- config 1: 2-D Poisson on the disk
 def test_config1_poisson_disk(orc):
     t2v, xy = orc.grid_tri_mesh(100, disk=True)
