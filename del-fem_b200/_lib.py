@@ -151,6 +151,7 @@ def lib():
         "dfb_halo_create": [_vp, _i32, _vp, _vp, _vp, _vp, _pp],
         "dfb_halo_destroy": [_vp],
         "dfb_halo_exchange": [_vp, _vp],
+        "dfb_halo_set_remote": [_vp, _vp],
         "dfb_bsr_set_halo": [_vp, _vp, _u64, _u64],
     }
     for name, argtypes in sig.items():

@@ -337,6 +337,11 @@ class Halo:
     def exchange(self, v: Vec):
         check(lib().dfb_halo_exchange(self.h, v.h))
 
+    def set_remote(self, remote_off):
+        """remote_off[p]: where (in blocks) this rank's packet lands in peer p's ghost tail -> enables the NVLink peer push in (P)CG"""
+        ro = _c(remote_off, np.uint64)
+        check(lib().dfb_halo_set_remote(self.h, _ptr(ro)))
+
     def __del__(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             lib().dfb_halo_destroy(self.h)

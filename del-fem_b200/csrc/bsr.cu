@@ -303,6 +303,7 @@ struct SpmvArgs {
   double *partials;
   unsigned int *ticket;
   DfbPeerView pv;      // pv.seq != 0 (and nranks > 1): the launch that completes p.Ap posts it to every peer's mailbox
+  DfbHaloWait hw;      // hw.xg != nullptr: ghost columns come from the peer landing zone (variant 20 inside the solvers)
 };
 
 template <int N>
@@ -586,7 +587,7 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], a.x, c[u]);
+      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], c[u] >= a.hw.n_own ? a.hw.xg : a.x, c[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -866,13 +867,27 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   __syncwarp();
   const uint32_t t_begin = a.row_begin / RPT, t_end = (a.row_end + RPT - 1) / RPT;
   const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
+  // Tiles are visited in a virtual order v = t_begin + wg, + ws, ...: with a peer halo the interior tiles come first and the
+  // tiles that read ghost columns ([t_begin, t_lo) and [t_hi, t_end)) last, so the neighbours' pushes have normally landed by
+  // the time a warp reaches them; without a halo the mapping is the identity.
+  const bool halo = a.hw.xg != nullptr;
+  const uint32_t t_lo = halo ? min(max(a.hw.tile_lo_end, t_begin), t_end) : t_begin;
+  const uint32_t t_hi = halo ? min(max(a.hw.tile_hi_begin, t_lo), t_end) : t_end;
+  const uint32_t n_int = t_hi - t_lo;
+  auto tile_of = [&](uint32_t v) -> uint32_t {   // v and the result are absolute tile indices in [t_begin, t_end)
+    if (!halo || v >= t_hi) return v;
+    const uint32_t k = v - t_begin;
+    return k < n_int ? t_lo + k : t_begin + (k - n_int);
+  };
+  bool waited = !halo;
 
   struct Off {
     uint32_t o0, o1;
   };
-  auto offs = [&](uint32_t t) -> Off {
+  auto offs = [&](uint32_t v) -> Off {
     Off o = {0u, 0u};
-    if (t < t_end) {
+    if (v < t_end) {
+      const uint32_t t = tile_of(v);
       o.o0 = __ldg(tile_off + t);
       o.o1 = __ldg(tile_off + t + 1);
     }
@@ -898,8 +913,17 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   double dzero[N];
 #pragma unroll
   for (int qq = 0; qq < N; ++qq) dzero[qq] = 0.0;
-  for (uint32_t t = t_begin + wg; t < t_end; t += ws) {
-    const Off qn = offs(t + 3 * ws);  // requested now, used at the end of the next iteration
+  for (uint32_t v = t_begin + wg; v < t_end; v += ws) {
+    const Off qn = offs(v + 3 * ws);  // requested now, used at the end of the next iteration
+    const uint32_t t = tile_of(v);
+    if (!waited && (t < t_lo || t >= t_hi)) {
+      // first boundary tile of this warp: the ghost values must have landed (all neighbours, see peer.cuh)
+      int ok = 1;
+      if (lane == 0) ok = halo_wait(a.hw) ? 1 : 0;
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      if (!ok && lane == 0 && a.st) a.st->err = 2;
+      waited = true;
+    }
     const uint32_t r = t * RPT + rl;
     const bool valid = r >= a.row_begin && r < a.row_end;
     const uint32_t bytes = (q0.o1 - q0.o0) << 4;
@@ -934,7 +958,7 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
                               dzero, 0.0);
     }
     __syncwarp();
-    issue(t + 2 * ws, b, q2);
+    issue(v + 2 * ws, b, q2);
     q0 = q1;
     q1 = q2;
     q2 = qn;
@@ -1032,7 +1056,8 @@ static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm
 
 // internal launcher shared with the solvers
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq) {
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq,
+                           const DfbHaloWait *hw) {
   dfb_ctx *c = m->ctx;
   SpmvArgs a;
   a.row2idx = m->pat->d_row2idx;
@@ -1052,6 +1077,17 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   a.partials = c->d_partials;
   a.ticket = c->d_ticket + 1;
   a.pv = dfb_peer_view(c, post_seq);
+  if (hw) {
+    a.hw = *hw;
+  } else {
+    a.hw.xg = nullptr;
+    a.hw.n_own = 0xFFFFFFFFu;
+    a.hw.wait_mask = 0;
+    a.hw.seq = 0;
+    a.hw.halo_flag = nullptr;
+    a.hw.tile_lo_end = 0;
+    a.hw.tile_hi_begin = 0xFFFFFFFFu;
+  }
   if (c->spmv_variant == 20) {
     dfb_bsr *mm = const_cast<dfb_bsr *>(m);
     if (!mm->packed_valid) DFB_TRY(bsr_pack(mm, strm));
@@ -1077,6 +1113,17 @@ dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha,
   dfb_ctx *c = m->ctx;
   const uint64_t n = m->pat->num_blk;
   if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq);
+  if (post_seq != 0 && c->spmv_variant == 20 && dfb_halo_peer_usable(m->halo, m->blk_dim)) {
+    // peer push (inside the solvers, where the scalar all-reduces order consecutive exchanges): one pack-and-push launch, then
+    // ONE SpMV launch over all rows whose boundary tiles wait for the neighbours' flags
+    DfbHaloWait hw;
+    DFB_TRY(dfb_halo_push(m->halo, x, m->blk_dim, parity, c->stream, &hw));
+    hw.n_own = (uint32_t)n;
+    hw.xg = hw.xg - n * (uint64_t)m->blk_dim;
+    hw.tile_lo_end = (uint32_t)((m->int_begin + PK_RPT - 1) / PK_RPT);
+    hw.tile_hi_begin = (uint32_t)(m->int_end / PK_RPT);
+    return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq, &hw);
+  }
   // comm stream: wait until x is final, exchange ghosts
   DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
   DFB_CUDA(cudaStreamWaitEvent(c->stream_comm, c->ev_a, 0));

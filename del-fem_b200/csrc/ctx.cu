@@ -151,6 +151,8 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
   if (!strcmp(key, "use_peer_allreduce")) return &c->use_peer_allreduce;
+  if (!strcmp(key, "use_peer_halo")) return &c->use_peer_halo;
+  if (!strcmp(key, "peer_halo_bytes")) return &c->peer_halo_bytes;
   return nullptr;
 }
 

@@ -108,7 +108,16 @@ struct dfb_ctx {
   int peer_enabled = 0;
   unsigned long long peer_seq = 0;
   int64_t use_peer_allreduce = 1;               // option: 0 forces NCCL all-reduce even when mailboxes are mapped
+  // peer halo push (ghost values stored straight into the neighbours' landing zones over NVLink; PCG only)
+  int64_t use_peer_halo = 1;                    // option: 0 forces the NCCL send/recv halo
+  int64_t peer_halo_bytes = 8ll << 20;          // option (before dfb_ctx_peer_export): landing-zone bytes per parity buffer
+  uint64_t landing_bytes = 0;                   // what the exported allocation actually holds per parity buffer
+  unsigned long long halo_seq = 0;
 };
+
+static inline double *dfb_peer_landing(const dfb_ctx *c, int r, int parity) {
+  return (double *)((unsigned char *)c->peer_mbox[r] + sizeof(DfbMailbox) + (size_t)parity * c->landing_bytes);
+}
 
 // view handed to kernels; seq = 0 disables the exchange for that launch
 static inline DfbPeerView dfb_peer_view(const dfb_ctx *c, unsigned long long seq) {
@@ -163,6 +172,17 @@ struct dfb_halo {
   double *d_sendbuf;     // packed, sized for blk_dim up to 4
   uint64_t n_send;
   int max_dim;
+  // peer push (dfb_halo_set_remote): where this rank's packets land in each peer's ghost tail (in blocks)
+  std::vector<uint64_t> remote_off;
+  int peer_ready = 0;
+};
+struct DfbHaloPush {   // kernel argument of the pack-and-push launch
+  int n_peers;
+  int rank;
+  unsigned long long seq;
+  uint64_t send_ptr[DFB_MAX_RANKS + 1];
+  double *dst[DFB_MAX_RANKS];                 // peer landing zone (this parity) + remote offset, in doubles
+  unsigned long long *flag[DFB_MAX_RANKS];    // &peer_mbox[peer]->halo_flag[rank]
 };
 
 struct dfb_bsr {
@@ -229,7 +249,10 @@ dfb_status dfb_check_error_flag(dfb_ctx *ctx, int slot, dfb_status st, const cha
 dfb_status dfb_exclusive_scan_u32(dfb_ctx *ctx, uint32_t *d_data, uint64_t n, uint64_t *total_out);
 dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaStream_t strm);
 dfb_status dfb_halo_exchange_on(dfb_halo *h, double *d_vec, uint64_t n_blk, int blk_dim, cudaStream_t strm);
+bool dfb_halo_peer_usable(const dfb_halo *h, int blk_dim);
+dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, int state_parity, cudaStream_t strm, DfbHaloWait *wait_out);
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq = 0);
+                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq = 0,
+                           const DfbHaloWait *hw = nullptr);
 
 static inline int dfb_div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }

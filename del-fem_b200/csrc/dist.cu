@@ -97,7 +97,9 @@ DFB_API dfb_status dfb_ctx_peer_export(dfb_ctx *ctx, uint8_t handle_out[64]) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   DFB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->d_mbox) {
-    DFB_CUDA(cudaMalloc((void **)&ctx->d_mbox, sizeof(DfbMailbox)));
+    // one IPC allocation: [mailbox | landing zone parity 0 | landing zone parity 1]
+    ctx->landing_bytes = ctx->peer_halo_bytes > 0 ? (((uint64_t)ctx->peer_halo_bytes + 127) & ~127ull) : 0;
+    DFB_CUDA(cudaMalloc((void **)&ctx->d_mbox, sizeof(DfbMailbox) + 2 * ctx->landing_bytes));
     DFB_CUDA(cudaMemset(ctx->d_mbox, 0, sizeof(DfbMailbox)));
   }
   cudaIpcMemHandle_t h;
@@ -128,6 +130,32 @@ DFB_API dfb_status dfb_ctx_peer_import(dfb_ctx *ctx, const uint8_t *handles, int
 }
 
 // ------------------------------------------------------------------------------------------------ halo
+// Peer push: the boundary entries of the vector are stored straight into the neighbours' landing zones over NVLink; the last
+// block to finish fences and then raises this rank's flag in every neighbour's mailbox.  The matching wait lives in the
+// boundary tiles of the neighbour's SpMV (bsr.cu), so a ghost exchange costs one small launch and no collective.
+__global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ v, const uint32_t *__restrict__ idx, int dim,
+                                                    const DfbHaloPush hp, const DfbSolverState *st, int parity, unsigned int *ticket) {
+  if (st && st->done[parity]) return;
+  __shared__ bool s_last;
+  const uint64_t total = hp.send_ptr[hp.n_peers] * (uint64_t)dim;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = q / dim;
+    const int d = (int)(q - s * dim);
+    int p = 0;
+    while (p + 1 < hp.n_peers && s >= hp.send_ptr[p + 1]) ++p;
+    hp.dst[p][(s - hp.send_ptr[p]) * dim + d] = v[(uint64_t)idx[s] * dim + d];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < hp.n_peers) {
+    __threadfence_system();
+    volatile unsigned long long *f = hp.flag[threadIdx.x];
+    *f = hp.seq;
+  }
+}
+
 __global__ void k_halo_pack(const double *__restrict__ v, const uint32_t *__restrict__ idx, uint64_t n_send, int dim,
                             double *__restrict__ buf) {
   const uint64_t total = n_send * dim;
@@ -171,6 +199,57 @@ DFB_API dfb_status dfb_halo_create(dfb_ctx *ctx, int32_t n_peers, const int32_t 
     return st;
   }
   *out = h;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_halo_set_remote(dfb_halo *h, const uint64_t *remote_off) {
+  DFB_REQUIRE(h, "dfb_halo_set_remote: NULL argument");
+  DFB_REQUIRE(h->n_peers == 0 || remote_off, "dfb_halo_set_remote: NULL array");
+  DFB_REQUIRE(h->n_peers <= DFB_MAX_RANKS, "dfb_halo_set_remote: more than %d peers", DFB_MAX_RANKS);
+  h->remote_off.assign(remote_off, remote_off + h->n_peers);
+  h->peer_ready = 1;
+  return DFB_OK;
+}
+
+// the push path needs mapped peers, remote offsets, and landing zones large enough for what is sent AND received
+bool dfb_halo_peer_usable(const dfb_halo *h, int blk_dim) {
+  const dfb_ctx *c = h->ctx;
+  if (!h->peer_ready || !c->peer_enabled || !c->use_peer_halo || c->nranks <= 1 || c->landing_bytes == 0) return false;
+  const uint64_t cap_blk = c->landing_bytes / ((uint64_t)blk_dim * sizeof(double));
+  if (h->recv_ptr.back() > cap_blk) return false;
+  for (int p = 0; p < h->n_peers; ++p)
+    if (h->remote_off[p] + (h->send_ptr[p + 1] - h->send_ptr[p]) > cap_blk) return false;
+  return true;
+}
+
+dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, int state_parity, cudaStream_t strm, DfbHaloWait *wait_out) {
+  dfb_ctx *c = h->ctx;
+  const unsigned long long seq = ++c->halo_seq;
+  const int par = (int)(seq & 1ull);
+  DfbHaloPush hp;
+  hp.n_peers = h->n_peers;
+  hp.rank = c->rank;
+  hp.seq = seq;
+  uint32_t mask = 0;
+  for (int p = 0; p <= h->n_peers; ++p) hp.send_ptr[p] = h->send_ptr[p];
+  for (int p = 0; p < h->n_peers; ++p) {
+    const int pr = h->peers[p];
+    hp.dst[p] = dfb_peer_landing(c, pr, par) + h->remote_off[p] * (uint64_t)blk_dim;
+    hp.flag[p] = &c->peer_mbox[pr]->halo_flag[c->rank];
+    if (h->recv_ptr[p + 1] > h->recv_ptr[p]) mask |= 1u << pr;
+  }
+  if (h->n_peers > 0) {
+    int g = dfb_div_up(h->n_send * blk_dim, 256);
+    if (g < 1) g = 1;
+    if (g > c->sm_count * 2) g = c->sm_count * 2;
+    DFB_LAUNCH_ON(c, strm, k_halo_push, g, 256, 0, d_vec, h->d_send_idx, blk_dim, hp, state_parity < 0 ? nullptr : c->d_state,
+                  state_parity < 0 ? 0 : state_parity, c->d_ticket + 5);
+    DFB_CHECK_LAUNCH();
+  }
+  wait_out->seq = seq;
+  wait_out->wait_mask = mask;
+  wait_out->halo_flag = c->d_mbox->halo_flag;
+  wait_out->xg = dfb_peer_landing(c, c->rank, par);  // the caller subtracts n_own * N
   return DFB_OK;
 }
 

@@ -14,7 +14,39 @@ static const int DFB_MBOX_SLOTS = 4;
 struct DfbMailbox {
   double val[DFB_MBOX_SLOTS][DFB_MAX_RANKS][4];
   unsigned long long flag[DFB_MBOX_SLOTS][DFB_MAX_RANKS];
+  // halo push: peer r stores the sequence number of the ghost exchange it has completed INTO THIS rank's landing zone
+  unsigned long long halo_flag[DFB_MAX_RANKS];
+  unsigned long long pad[8];
+  // the landing zone (2 parity buffers of ctx->peer_halo_bytes each) follows the struct in the same IPC allocation
 };
+static_assert(sizeof(DfbMailbox) % 128 == 0, "landing zone must start on a 128-byte boundary");
+
+// receiver side of the halo push, handed to the SpMV: ghost columns (>= n_own) are read from the landing zone once every
+// peer in `wait_mask` has posted `seq`
+struct DfbHaloWait {
+  const double *xg;                      // landing base pre-offset by -n_own*N (so xg + col*N addresses ghost `col`); nullptr: off
+  uint32_t n_own;
+  uint32_t wait_mask;                    // bit r: wait for halo_flag[r]
+  unsigned long long seq;
+  const unsigned long long *halo_flag;   // LOCAL mailbox flags
+  uint32_t tile_lo_end, tile_hi_begin;   // tiles [0, tile_lo_end) and [tile_hi_begin, ...) hold boundary rows: processed last
+};
+
+// called by one lane; returns false on timeout
+__device__ __forceinline__ bool halo_wait(const DfbHaloWait &hw) {
+  const long long t0 = clock64();
+  for (int r = 0; r < DFB_MAX_RANKS; ++r) {
+    if (!((hw.wait_mask >> r) & 1u)) continue;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(hw.halo_flag + r) : "memory");
+      if (v >= hw.seq) break;
+      if (clock64() - t0 > 4000000000ll) return false;
+    }
+  }
+  __threadfence_system();
+  return true;
+}
 
 struct DfbPeerView {
   int rank;

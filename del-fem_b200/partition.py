@@ -41,6 +41,7 @@ class Slab:
     send_ptr: np.ndarray = None
     send_idx: np.ndarray = None
     recv_ptr: np.ndarray = None
+    remote_off: np.ndarray = None   # per peer: offset (blocks) of this rank's packet in that peer's ghost tail
     int_begin: int = 0
     int_end: int = 0
     first_global_vtx: int = 0
@@ -77,21 +78,24 @@ def make_slab(nx, ny, nz, rank, nranks) -> Slab:
     n_own = (k1 - k0) * nxy
     n_ghost = (int(has_below) + int(has_above)) * nxy
     s = Slab(nx, ny, nz, rank, nranks, k0, k1, kb, ke, n_own, n_ghost, shift=(nxy if has_below else 0))
-    peers, send_ptr, send_idx, recv_ptr = [], [0], [], [0]
+    peers, send_ptr, send_idx, recv_ptr, remote_off = [], [0], [], [0], []
     # ghost tail order is [above | below]; peers listed in the same order so recv ranges are contiguous
     if has_above:
         peers.append(rank + 1)
         send_idx.append(np.arange(n_own - nxy, n_own, dtype=np.uint32))  # my last owned plane
         send_ptr.append(send_ptr[-1] + nxy)
         recv_ptr.append(recv_ptr[-1] + nxy)
+        remote_off.append(nxy if rank + 1 < nranks - 1 else 0)  # I am its ghost-BELOW plane: behind its ghost-above plane, if any
     if has_below:
         peers.append(rank - 1)
         send_idx.append(np.arange(0, nxy, dtype=np.uint32))  # my first owned plane
         send_ptr.append(send_ptr[-1] + nxy)
         recv_ptr.append(recv_ptr[-1] + nxy)
+        remote_off.append(0)  # I am its ghost-ABOVE plane: first in its ghost tail
     s.peers = peers
     s.send_ptr = np.array(send_ptr, dtype=np.uint64)
     s.recv_ptr = np.array(recv_ptr, dtype=np.uint64)
+    s.remote_off = np.array(remote_off, dtype=np.uint64)
     s.send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.uint32)
     # rows of the first / last owned plane reference ghosts; everything in between is interior
     s.int_begin = nxy if has_below else 0

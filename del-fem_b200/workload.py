@@ -20,6 +20,7 @@ class Problem:
         self.halo = None
         if nranks > 1:
             self.halo = dfb.Halo(ctx, s.peers, s.send_ptr, s.send_idx, s.recv_ptr)
+            self.halo.set_remote(s.remote_off)  # enables the NVLink peer push when the ctx has mapped peers
             self.mat.set_halo(self.halo, s.int_begin, s.int_end)
         self.flag_host = s.flags_clamp_z0()
         self.flag = dfb.BcFlag(ctx, self.flag_host)

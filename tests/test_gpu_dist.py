@@ -20,6 +20,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, shape, out_dir, variant, use_peer):
+    # use_peer: 0 = NCCL all-reduce + NCCL halo, 1 = peer mailbox all-reduce + NCCL halo, 2 = peer mailbox + peer halo push
     import sys
     sys.path.insert(0, ROOT)
     import torch
@@ -40,6 +41,7 @@ def _worker(rank, world, port, shape, out_dir, variant, use_peer):
         dist.all_gather_object(handles, ctx.peer_export())
         ctx.peer_import(handles)
     ctx.set_option("spmv_variant", variant)
+    ctx.set_option("use_peer_halo", 1 if use_peer == 2 else 0)
     nx, ny, nz = shape
     prob = Problem(dfb, ctx, nx, ny, nz, rank, world, "jacobi")
     asm_ms, tot_ms, iters = prob.step(max_it=5000)
@@ -55,7 +57,7 @@ def _worker(rank, world, port, shape, out_dir, variant, use_peer):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_peer", [False, True])
+@pytest.mark.parametrize("use_peer", [0, 1, 2])
 @pytest.mark.parametrize("variant", [0, 4, 20])
 @pytest.mark.parametrize("shape", [(9, 8, 20)])
 def test_two_gpu_pcg_equals_single_gpu(tmp_path, dfb, shape, variant, use_peer):

@@ -160,3 +160,20 @@ def test_distributed_pcg_equals_single_domain(tmp_path, orc, world, shape):
         assert abs(len(d["hist"]) - len(hist)) <= 1
     assert seen.all()
     assert np.linalg.norm(xs - x) / np.linalg.norm(x) < 1e-7
+
+
+def test_remote_offsets_match_the_receivers_ghost_ranges():
+    """peer push: remote_off[p] on the sender must be the receiver's recv_ptr entry for the sender, and sizes must agree"""
+    from del_fem_b200 import partition
+    for nranks in (2, 3, 5, 8):
+        slabs = [partition.make_slab(5, 4, 23, r, nranks) for r in range(nranks)]
+        for s in slabs:
+            for p, peer in enumerate(s.peers):
+                t = slabs[peer]
+                q = t.peers.index(s.rank)
+                assert int(s.remote_off[p]) == int(t.recv_ptr[q])
+                assert int(s.send_ptr[p + 1] - s.send_ptr[p]) == int(t.recv_ptr[q + 1] - t.recv_ptr[q])
+                # and the packet is the receiver's ghost copy of exactly those global vertices
+                g_send = s.local_to_global()[s.send_idx[int(s.send_ptr[p]):int(s.send_ptr[p + 1])]]
+                g_recv = t.local_to_global()[t.n_own + int(t.recv_ptr[q]): t.n_own + int(t.recv_ptr[q + 1])]
+                assert np.array_equal(g_send, g_recv)
