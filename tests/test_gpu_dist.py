@@ -59,13 +59,15 @@ def _worker(rank, world, port, shape, out_dir, variant, use_peer):
 
 @pytest.mark.parametrize("use_peer", [0, 1, 2])
 @pytest.mark.parametrize("variant", [0, 4, 20])
-@pytest.mark.parametrize("shape", [(9, 8, 20)])
-def test_two_gpu_pcg_equals_single_gpu(tmp_path, dfb, shape, variant, use_peer):
+@pytest.mark.parametrize("world,shape", [(2, (9, 8, 20)), (4, (9, 8, 23))])
+def test_multi_gpu_pcg_equals_single_gpu(tmp_path, dfb, world, shape, variant, use_peer):
+    """world = 4 has middle ranks with two neighbours (both landing ranges, two flags to wait for)"""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if world > 2 and variant != 20:
+        pytest.skip("the 4-GPU case only runs the default SpMV variant")
     import torch.multiprocessing as mp
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path), variant, use_peer), nprocs=world, join=True)
     from del_fem_b200.workload import Problem
     ctx = dfb.Ctx(0)
