@@ -53,3 +53,48 @@ class Problem:
         self.hist = dfb.preconditioned_conjugate_gradient(self.rhs, self.x, self.q, self.p, tol, max_it, self.mat, self.pc)
         rest_ms = ctx.timer_stop()
         return asm_ms, asm_ms + rest_ms, len(self.hist) - 1
+
+
+class GeneralProblem:
+    """one rank of a vertex-partitioned solve on ANY uniform mesh (partition.partition_general): local mesh in the numbering
+    [interior owned | boundary owned | ghosts], matrix rows = owned vertices, halo + peer push attached when nranks > 1.
+    `flags` / `rhs` / `u` are given and returned in GLOBAL vertex order on every rank (host-side convenience for tests and examples)."""
+
+    def __init__(self, dfb, ctx, elem2vtx, vtx2xyz, rank, nranks, kind="solid_linear_tet", p0=1.0, p1=1.0, precond="jacobi"):
+        import numpy as np
+        from del_fem_b200 import partition, sparse_ilu
+        from del_fem_b200.core import ELEM, ELEM_INFO
+        self.dfb, self.ctx, self.kind, self.p0, self.p1 = dfb, ctx, kind, p0, p1
+        self.blk_dim = ELEM_INFO[ELEM[kind]][2]
+        xyz = np.ascontiguousarray(vtx2xyz, dtype=np.float64)
+        self.part = s = partition.partition_general(elem2vtx, xyz.shape[0], nranks, rank)
+        self.mesh = dfb.Mesh(ctx, np.ascontiguousarray(s.elem2vtx, dtype=np.uint32), np.ascontiguousarray(xyz[s.local2global]))
+        self.pat = dfb.Pattern.from_uniform_mesh(ctx, self.mesh, False, s.n_own)
+        self.plan = dfb.Plan(ctx, self.pat, self.mesh, 0)
+        self.mat = dfb.Matrix(ctx, self.pat, self.blk_dim)
+        self.halo = None
+        if nranks > 1:
+            self.halo = dfb.Halo(ctx, s.peers, s.send_ptr, s.send_idx, s.recv_ptr)
+            self.halo.set_remote(s.remote_off)
+            self.mat.set_halo(self.halo, s.int_begin, s.int_end)
+        self.pc = sparse_ilu.Preconditioner(precond)
+        self.pc.initialize(self.mat)
+        self.hist = None
+
+    def solve(self, flags_global, rhs_global, tol=1e-8, max_it=20000):
+        """assemble -> Dirichlet rows/columns -> Jacobi-PCG; returns this rank's owned solution and their global vertex ids"""
+        import numpy as np
+        from del_fem_b200 import sparse_ilu
+        dfb, ctx, s, n = self.dfb, self.ctx, self.part, self.blk_dim
+        l2g = s.local2global
+        flag = dfb.BcFlag(ctx, np.ascontiguousarray(np.asarray(flags_global, dtype=np.int32).reshape(-1, n)[l2g]))
+        self.mat.assemble(self.plan, self.kind, self.mesh, self.p0, self.p1)
+        rhs = dfb.Vec(ctx, s.n_own, n, s.n_ghost,
+                      np.ascontiguousarray(np.asarray(rhs_global, dtype=np.float64).reshape(-1, n)[l2g[: s.n_own]]))
+        rhs.set_fixed_dof_zero_dev(flag)
+        self.mat.set_fixed_dof_dev(1.0, flag)
+        sparse_ilu.copy_value(self.pc, self.mat)
+        sparse_ilu.decompose(self.pc)
+        x, q, p = (dfb.Vec(ctx, s.n_own, n, s.n_ghost) for _ in range(3))
+        self.hist = dfb.preconditioned_conjugate_gradient(rhs, x, q, p, tol, max_it, self.mat, self.pc)
+        return x.download(), l2g[: s.n_own]

@@ -90,3 +90,74 @@ def test_multi_gpu_pcg_equals_single_gpu(tmp_path, dfb, world, shape, variant, u
         assert abs(len(d["hist"]) - len(ref.hist)) <= 1
         assert d["hist"][-1] / d["hist"][0] < 1e-8
     assert np.linalg.norm(xs - x_ref) / np.linalg.norm(x_ref) < 1e-7
+
+
+def _general_worker(rank, world, port, shape, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import _bootstrap
+    dfb = _bootstrap.load()
+    from del_fem_b200.workload import GeneralProblem
+    from test_partition_gloo import _shuffled_rcm_mesh
+    import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = dfb.Ctx(rank)
+    uid = [dfb.Ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export())
+    ctx.peer_import(handles)
+    e2v, xyz = _shuffled_rcm_mesh(orc, shape)
+    flags, rhs = _general_rhs(xyz)
+    prob = GeneralProblem(dfb, ctx, e2v, xyz, rank, world)
+    x, g = prob.solve(flags, rhs, max_it=5000)
+    np.savez(os.path.join(out_dir, f"g{rank}.npz"), x=x, g=g, hist=prob.hist)
+    ctx.sync()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _general_rhs(xyz):
+    nv = xyz.shape[0]
+    flags = np.zeros((nv, 3), dtype=np.int32)
+    flags[xyz[:, 2] == 0.0] = 1
+    rhs = np.zeros((nv, 3))
+    rhs[:, 2] = -1e-3 * (1.0 + xyz[:, 0])
+    rhs[:, 0] = 2e-4 * np.sin(7.0 * xyz[:, 1])
+    return flags, rhs
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_general_partition_multi_gpu_equals_single_gpu(tmp_path, dfb, orc, world):
+    """unstructured numbering (shuffled, then RCM) partitioned by contiguous vertex ranges: distributed PCG == single-GPU PCG"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_partition_gloo import _shuffled_rcm_mesh
+    from del_fem_b200.workload import GeneralProblem
+    shape = (9, 8, 21)
+    mp.spawn(_general_worker, args=(world, _free_port(), shape, str(tmp_path)), nprocs=world, join=True)
+    e2v, xyz = _shuffled_rcm_mesh(orc, shape)
+    flags, rhs = _general_rhs(xyz)
+    ctx = dfb.Ctx(0)
+    ref = GeneralProblem(dfb, ctx, e2v, xyz, 0, 1)
+    x_ref, g_ref = ref.solve(flags, rhs, max_it=5000)
+    xs = np.zeros_like(x_ref)
+    xs_ref = np.zeros_like(x_ref)
+    xs_ref[g_ref] = x_ref
+    for rk in range(world):
+        d = np.load(os.path.join(str(tmp_path), f"g{rk}.npz"))
+        xs[d["g"]] = d["x"]
+        assert abs(len(d["hist"]) - len(ref.hist)) <= 1
+        assert d["hist"][-1] / d["hist"][0] < 1e-8
+    assert np.linalg.norm(xs - xs_ref) / np.linalg.norm(xs_ref) < 1e-7

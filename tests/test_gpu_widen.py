@@ -480,3 +480,32 @@ def test_ilu0_matches_oracle(dfb, ctx, orc, case):
     with pytest.raises(dfb.DfbError) as ei:
         pb.initialize(bad)
     assert ei.value.status == dfb.STATUS["BAD_ARG"]
+
+
+def test_general_problem_single_rank_matches_oracle(dfb, ctx, orc):
+    """GeneralProblem (partition_general with one rank) on a shuffled + RCM-renumbered mesh: same PCG as the oracle"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_partition_gloo import _shuffled_rcm_mesh
+    from del_fem_b200.workload import GeneralProblem
+    e2v, xyz = _shuffled_rcm_mesh(orc, (8, 7, 9))
+    nv = xyz.shape[0]
+    flags = np.zeros((nv, 3), dtype=np.int32)
+    flags[xyz[:, 2] == 0.0] = 1
+    rhs = np.zeros((nv, 3))
+    rhs[:, 2] = -1e-3 * (1.0 + xyz[:, 0])
+    prob = GeneralProblem(dfb, ctx, e2v, xyz, 0, 1)
+    x, g = prob.solve(flags, rhs, max_it=5000)
+    assert np.array_equal(g, np.arange(nv))
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rv, iv = orc.assemble("solid_linear_tet", 0, e2v, xyz, 1.0, 1.0, r2i, i2c)
+    b = rhs.copy()
+    orc.set_fix_dof_to_rhs_vector(b, flags)
+    orc.set_fixed_bc(1.0, flags, rv, iv, r2i, i2c)
+    ilu = orc.Ilu("jacobi", 3, r2i, i2c)
+    ilu.copy_value(r2i, i2c, iv, rv)
+    ilu.decompose()
+    xo, pr, p = np.zeros_like(b), np.zeros_like(b), np.zeros_like(b)
+    ho = orc.preconditioned_conjugate_gradient(b, xo, pr, p, 1e-8, 5000, r2i, i2c, iv, rv, ilu)
+    assert abs(len(prob.hist) - len(ho)) <= 1
+    assert rel_err(x, xo) < 1e-7

@@ -177,3 +177,45 @@ def test_remote_offsets_match_the_receivers_ghost_ranges():
                 g_send = s.local_to_global()[s.send_idx[int(s.send_ptr[p]):int(s.send_ptr[p + 1])]]
                 g_recv = t.local_to_global()[t.n_own + int(t.recv_ptr[q]): t.n_own + int(t.recv_ptr[q + 1])]
                 assert np.array_equal(g_send, g_recv)
+
+
+def _shuffled_rcm_mesh(orc, shape, seed=0):
+    from del_fem_b200 import partition
+    e2v, xyz = orc.kuhn_tet_mesh(*shape, 1.0 / (shape[0] - 1))
+    nv = xyz.shape[0]
+    shuf = np.random.default_rng(seed).permutation(nv)
+    e1, x1, _ = partition.renumber_mesh(e2v, xyz, shuf)          # destroy the structured numbering ...
+    e2, x2, _ = partition.renumber_mesh(e1, x1, partition.rcm_order(e1, nv))  # ... and recover locality with RCM
+    return e2, x2
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+def test_general_partition_description(orc, nranks):
+    """partition_general on an unstructured numbering: packets match the receivers' ghost ranges, interior rows read no ghost,
+    and the owned rows of the local oracle assembly equal the global assembly bit for bit"""
+    from del_fem_b200 import partition
+    e2v, xyz = _shuffled_rcm_mesh(orc, (6, 5, 8))
+    nv = xyz.shape[0]
+    r2i_g, i2c_g = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rv_g, iv_g = orc.assemble("solid_linear_tet", 0, e2v, xyz, 1.0, 1.0, r2i_g, i2c_g)
+    parts = [partition.partition_general(e2v, nv, nranks, r) for r in range(nranks)]
+    assert sum(s.n_own for s in parts) == nv
+    for s in parts:
+        for p, q in enumerate(s.peers):
+            t = parts[q]
+            k = t.peers.index(s.rank)
+            assert int(s.remote_off[p]) == int(t.recv_ptr[k])
+            gs = s.local2global[s.send_idx[int(s.send_ptr[p]):int(s.send_ptr[p + 1])]]
+            gr = t.local2global[t.n_own + int(t.recv_ptr[k]): t.n_own + int(t.recv_ptr[k + 1])]
+            assert np.array_equal(gs, gr)
+        nloc = s.n_own + s.n_ghost
+        r2i, i2c = orc.vtx2vtx_from_uniform_mesh(s.elem2vtx, 4, nloc, False)
+        for r in range(s.int_begin, s.int_end):
+            assert (i2c[r2i[r]:r2i[r + 1]] < s.n_own).all()
+        rv, iv = orc.assemble("solid_linear_tet", 0, s.elem2vtx, xyz[s.local2global], 1.0, 1.0, r2i, i2c)
+        g = s.local2global
+        for r in (0, s.n_own // 2, s.n_own - 1):
+            gr_ = int(g[r])
+            assert np.array_equal(rv[r], rv_g[gr_])
+            assert np.array_equal(g[i2c[r2i[r]:r2i[r + 1]].astype(np.int64)], i2c_g[r2i_g[gr_]:r2i_g[gr_ + 1]].astype(np.int64))
+            assert np.array_equal(iv[r2i[r]:r2i[r + 1]], iv_g[r2i_g[gr_]:r2i_g[gr_ + 1]])
