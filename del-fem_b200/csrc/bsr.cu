@@ -853,7 +853,6 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   constexpr int NN = N * N, RPT = PK_RPT, LPR = PK_LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned sub = lane % LPR, rl = lane / LPR;
   unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
@@ -865,6 +864,8 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  dfb_pdl_wait();  // everything above is independent of the predecessor kernel
+  if (a.st && a.st->done[a.parity]) return;
   const uint32_t t_begin = a.row_begin / RPT, t_end = (a.row_end + RPT - 1) / RPT;
   const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
   // Tiles are visited in a virtual order v = t_begin + wg, + ws, ...: with a peer halo the interior tiles come first and the
@@ -1008,7 +1009,9 @@ static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bs
   uint64_t g = (t_end - t_begin + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+  // inside the solvers (a.st set) the launch is a programmatic dependent of the previous iteration's direction kernel
+  DFB_LAUNCH_PDL(c, strm, (a.st != nullptr && c->use_pdl != 0), (k_spmv_packed<N>), (unsigned)g, warps * 32, smem, a,
+                 (const unsigned char *)m->d_packed, (const uint32_t *)m->d_tile_off, (int)(m->d_row2val != nullptr));
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }

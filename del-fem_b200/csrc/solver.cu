@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
                                                          uint64_t n, DfbSolverState *st, int parity, double *partials,
                                                          unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
   __shared__ double s_buf[64];
+  dfb_pdl_wait();
   if (st->done[parity]) return;
   double pq = st->red[0];
   if (pv_in.nranks > 1) {
@@ -436,6 +437,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__restrict__ r, double *__restrict__ p,
                                                             const double *__restrict__ inv, uint64_t n, DfbSolverState *st,
                                                             int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
+  dfb_pdl_wait();
   if (st->done[parity]) {
     if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
     return;
@@ -548,6 +550,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   // scalar all-reduces: fused into the kernels through the NVLink peer mailboxes when mapped, NCCL otherwise
   const bool peer = c->peer_enabled && c->use_peer_allreduce && c->nranks > 1;
   const bool nccl_red = c->nranks > 1 && !peer;
+  const bool pdl = c->use_pdl != 0;
   const DfbPeerView pv_none = dfb_peer_view(c, 0);
   DfbPeerView pv_off = pv_none;  // consumers read st->red[] (filled by k_peer_gather / NCCL / the local reduction)
   pv_off.nranks = 1;
@@ -582,7 +585,8 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     const uint64_t todo = (max_it - enq < chunk) ? (max_it - enq) : chunk;
     for (uint64_t j = 0; j < todo; ++j) {
       const int parity = (int)((enq + j) & 1);
-      const bool prof = dfb_prof_begin(c);
+      // profile_spmv = K: bracket every K-th SpMV with events (K = 1: all of them)
+      const bool prof = (c->profile_spmv > 0 && (enq + j) % (uint64_t)c->profile_spmv == 0) ? dfb_prof_begin(c) : false;
       DfbPeerView pv_a = pv_none, pv_b = pv_none;  // a: p.Ap (K1 -> K2), b: r.r, r.z (K2 -> K3)
       pv_a.nranks = pv_b.nranks = 1;
       if (peer) {
@@ -598,9 +602,9 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
         DISPATCH_ALL(UPD)
 #undef UPD
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
+        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       } else {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
+        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       }
       if (ilu) {
         // the update kernel ran with M = I (r.r in red[1]); now z = M^-1 r explicitly and r.z -> red[2]
@@ -615,14 +619,14 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
         DISPATCH_ALL(DIR)
 #undef DIR
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
+        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       } else if (ilu) {
 #define DIRZ(NV) \
   if (n == NV) DFB_LAUNCH(c, (k_pcg_direction<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, p->d, zbuf, nb, st, parity, c->d_hist, c->hist_cap, pv_off);
         DIRZ(1) DIRZ(2) DIRZ(3) DIRZ(4)
 #undef DIRZ
       } else {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
+        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       }
     }
     DFB_CHECK_LAUNCH();
@@ -649,7 +653,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     const int slot = (n_chunks - 1) & 1;
     last = hf[slot];
   }
-  DFB_TRY(dfb_prof_flush(c, (size_t)last.iter));
+  DFB_TRY(dfb_prof_flush(c, c->profile_spmv > 0 ? ((size_t)last.iter + (size_t)c->profile_spmv - 1) / (size_t)c->profile_spmv : 0));
   if (last.err == 2) return dfb_fail(DFB_ERR_NCCL, "(p)cg: peer mailbox all-reduce timed out (a rank is missing or out of step)");
   if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
 
