@@ -965,6 +965,7 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
     q2 = qn;
     b ^= 1u;
   }
+  dfb_pdl_trigger();
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 

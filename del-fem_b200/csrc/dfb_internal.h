@@ -69,10 +69,10 @@ static inline cudaError_t dfb_launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 
   } while (0)
 #ifdef __CUDACC__
 // wait for the predecessor grid (no-op for a normally launched kernel), then let the successor start its own launch
-__device__ __forceinline__ void dfb_pdl_wait() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+__device__ __forceinline__ void dfb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// called once the CTA's streaming loop is over: the successor's CTAs take the SM as this kernel's CTAs retire (triggering at
+// the top instead was measured SLOWER: resident-but-waiting CTAs of the successor take registers/shared memory from this kernel)
+__device__ __forceinline__ void dfb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 #define DFB_CHECK_LAUNCH() DFB_CUDA(cudaGetLastError())
 
@@ -125,7 +125,7 @@ struct dfb_ctx {
   int64_t assemble_variant = 0;
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
-  int64_t use_pdl = 1;           // programmatic dependent launch of the PCG iteration kernels
+  int64_t use_pdl = 0;           // programmatic dependent launch of the PCG iteration kernels: measured 1 % SLOWER (profiles/README.md)
   // SpMV profiling (events on the launching stream)
   std::vector<cudaEvent_t> prof_ev;   // pairs
   size_t prof_used = 0;

@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
     acc[0] += rv * rv;
     acc[1] += rv * z;
   }
+  dfb_pdl_trigger();
   if (grid_sum_last_block<2>(acc, partials, ticket, s_buf)) {
     if (threadIdx.x == 0) {
       st->red[1] = acc[0];
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__rest
     pv.y = z.y + beta * pv.y;
     p2[i] = pv;
   }
+  dfb_pdl_trigger();
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const uint64_t i = n - 1;
     const double z = (KIND == DFB_PRECOND_JACOBI) ? inv[i] * r[i] : r[i];
