@@ -99,3 +99,20 @@ def test_cpp_mirror_compiles():
         r = subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_solid_linear_tri2.cpp"), "-o",
                             os.path.join(d, "t"), "-L" + lib_dir, "-ldelfem_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_rust_sys_crate_is_in_sync_with_the_header():
+    """rust/delfem-b200-sys/src/lib.rs (the binding a del-fem maintainer adds) is generated from the header:
+    every exported function and constant must be declared, and the committed file must be what the generator produces now"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"])
+    assert r.returncode == 0, "run `python tools/gen_rust_sys.py` and commit rust/delfem-b200-sys/src/lib.rs"
+    import re
+    hdr = open(os.path.join(root, "include", "delfem_b200.h")).read()
+    rs = open(os.path.join(root, "rust", "delfem-b200-sys", "src", "lib.rs")).read()
+    names = set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)))
+    assert len(names) > 80
+    for n in names:
+        assert re.search(r"pub fn %s\(" % n, rs), n
