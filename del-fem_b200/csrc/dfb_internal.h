@@ -248,6 +248,9 @@ struct dfb_plan {
   const dfb_mesh *mesh;  // borrowed (elem2vtx used to rebuild elem2nz on demand)
   void *d_geo = nullptr;   // per-element geometry scratch of the two-kernel fused assembly (lazily allocated)
   uint64_t geo_cap = 0;
+  // row-tile assembly (variant 3): for every (row, element-node) pair the tile-relative slots of its n_node blocks, one byte each
+  uint32_t *d_pair_slots = nullptr;
+  int pairs_state = 0;     // 0 not built yet, 1 usable, -1 not applicable (convention/flavour, oversized tile, degenerate element)
 };
 
 struct DfbIlu;

@@ -122,9 +122,13 @@ def _mesh_for(orc, kind, rng):
     return t2v, np.ascontiguousarray(xy), 3
 
 
+@pytest.mark.parametrize("asm_variant", [0, 3])
 @pytest.mark.parametrize("convention", [0, 1])
 @pytest.mark.parametrize("kind,p0,p1", KINDS)
-def test_fused_assembly_matches_oracle(dfb, ctx, orc, kind, p0, p1, convention):
+def test_fused_assembly_matches_oracle(dfb, ctx, orc, kind, p0, p1, convention, asm_variant):
+    """asm_variant 0: slot-centric gather over node records; 3: row-tile gather in shared memory (falls back to 0 where it does
+    not apply: convention 1, the cotangent kernel)"""
+    ctx.set_option("assemble_variant", asm_variant)
     rng = np.random.default_rng(3)
     e2v, xyz, n_node = _mesh_for(orc, kind, rng)
     nv = xyz.shape[0]
@@ -158,6 +162,7 @@ def test_fused_assembly_matches_oracle(dfb, ctx, orc, kind, p0, p1, convention):
     assert np.array_equal(iv2, iv_d)
     if convention == 0:
         assert np.array_equal(rv2, rv_d)
+    ctx.set_option("assemble_variant", 0)
 
 
 def test_assembly_is_run_to_run_deterministic(dfb, ctx, orc):

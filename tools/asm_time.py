@@ -23,7 +23,7 @@ print(f"pattern {t_pat:.2f} ms, plan {t_plan:.2f} ms, {mesh.num_elem} tets, {pla
 mat = dfb.Matrix(ctx, pat, 3)
 ref = None
 bytes_alg = 16 * mesh.num_elem + 24 * mesh.num_vtx + 72 * plan.num_slots + 64 * mesh.num_elem + 4 * (plan.num_slots + 1)
-for variant in (1, 2, 0):
+for variant in (1, 2, 0, 3):
     ctx.set_option("assemble_variant", variant)
     mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
     best = 1e9
@@ -37,3 +37,23 @@ for variant in (1, 2, 0):
     if ref is None:
         ref = (rv, iv)
     print(f"assemble_variant {variant}: {best:.3f} ms  {mesh.num_elem / best / 1e6:.2f} G tets/s  {bytes_alg / best / 1e6:.0f} GB/s algorithmic  identical_bits={same} checksum={h}")
+
+# two-phase path (element matrices in HBM -> gather): slot-centric vs row-tile
+from del_fem_b200 import elements  # noqa: E402
+if n <= 110:
+    d = dfb.Vec(ctx, mesh.num_vtx, 3)
+    d.fill_splitmix(0, 0, -1e-3, 1e-3)
+    g = dfb.Vec(ctx, mesh.num_vtx, 3)
+    ref = None
+    for variant in (0, 3):
+        ctx.set_option("assemble_variant", variant)
+        elements.assemble_energy(plan, "neohookean_tet", mesh, d, 1.0, 10.0, mat, g)
+        best = 1e9
+        for _ in range(3):
+            ctx.timer_start()
+            elements.assemble_energy(plan, "neohookean_tet", mesh, d, 1.0, 10.0, mat, g)
+            best = min(best, ctx.timer_stop())
+        rv, iv = mat.download()
+        same = ref is None or (np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1]))
+        ref = ref or (rv, iv)
+        print(f"neo-Hookean energy assembly, variant {variant}: {best:.3f} ms identical_bits={same}")
