@@ -580,35 +580,57 @@ static dfb_status plan_build_pairs(dfb_plan *plan) {
   return DFB_OK;
 }
 
-// block sources for k_assemble_rows: get() is called by the 4 lanes of a row group together (it shuffles)
+// block sources for k_assemble_rows. load() fetches what lane j contributes to pair (e, i) — issued U pairs ahead of its use —
+// and block() turns it into block (i, j); block() is called by the 4 lanes of a row group together (SrcRecs shuffles record i).
 template <int KIND>
 struct SrcRecs {
-  static constexpr int NNODE = ElemGeo<KIND>::NNODE, N = ElemGeo<KIND>::N;
+  static constexpr int NNODE = ElemGeo<KIND>::NNODE, N = ElemGeo<KIND>::N, U = 2;
+  struct Pre {
+    double v[4];
+  };
   const NodeRec *recs;
   double p0, p1;
-  __device__ __forceinline__ void get(uint32_t e, uint32_t i, unsigned j, bool on, double *blk) const {
-    NodeRec rb = {{0.0, 0.0, 0.0, 0.0}};
+  __device__ __forceinline__ Pre load(uint32_t e, uint32_t, unsigned j, bool on) const {
+    Pre r = {{0.0, 0.0, 0.0, 0.0}};
     if (on) {
       const double2 *pb = reinterpret_cast<const double2 *>(&recs[(uint64_t)e * NNODE + j]);
       const double2 b0 = __ldg(pb), b1 = __ldg(pb + 1);
-      rb = {{b0.x, b0.y, b1.x, b1.y}};
+      r = {{b0.x, b0.y, b1.x, b1.y}};
     }
+    return r;
+  }
+  __device__ __forceinline__ void block(const Pre &pre, uint32_t i, bool on, double *blk) const {
     const int src = (int)((threadIdx.x & 31u & ~3u) + i);
-    NodeRec ra;
+    NodeRec ra, rb;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ra.v[k] = __shfl_sync(0xffffffffu, rb.v[k], src);
+    for (int k = 0; k < 4; ++k) {
+      rb.v[k] = pre.v[k];
+      ra.v[k] = __shfl_sync(0xffffffffu, pre.v[k], src);
+    }
     if (on) NodeOps<KIND>::block(ra, rb, p0, p1, blk);
   }
 };
 template <int NNODE_, int N_>
 struct SrcEmat {  // precomputed element matrices [e][i][j][N*N] (two-phase path: energy models, user-supplied emat)
-  static constexpr int NNODE = NNODE_, N = N_;
+  static constexpr int NNODE = NNODE_, N = N_, U = 1;
+  struct Pre {
+    double v[N_ * N_];
+  };
   const double *emat;
-  __device__ __forceinline__ void get(uint32_t e, uint32_t i, unsigned j, bool on, double *blk) const {
-    if (!on) return;
-    const double *b = emat + (((uint64_t)e * NNODE + i) * NNODE + j) * (N * N);
+  __device__ __forceinline__ Pre load(uint32_t e, uint32_t i, unsigned j, bool on) const {
+    Pre r;
 #pragma unroll
-    for (int q = 0; q < N * N; ++q) blk[q] = __ldg(b + q);
+    for (int q = 0; q < N * N; ++q) r.v[q] = 0.0;
+    if (on) {
+      const double *b = emat + (((uint64_t)e * NNODE + i) * NNODE + j) * (N * N);
+#pragma unroll
+      for (int q = 0; q < N * N; ++q) r.v[q] = __ldg(b + q);
+    }
+    return r;
+  }
+  __device__ __forceinline__ void block(const Pre &pre, uint32_t, bool, double *blk) const {
+#pragma unroll
+    for (int q = 0; q < N * N; ++q) blk[q] = pre.v[q];
   }
 };
 
@@ -618,10 +640,12 @@ __global__ void __launch_bounds__(AR_WARPS * 32) k_assemble_rows(const Src src, 
                                                                  const uint32_t *__restrict__ pair_slots,
                                                                  const uint32_t *__restrict__ row2idx, uint64_t nnz, uint64_t num_rows,
                                                                  double *__restrict__ idx2val, double *__restrict__ row2val) {
-  constexpr int NN = Src::N * Src::N, NNODE = Src::NNODE;
+  constexpr int NN = Src::N * Src::N, NNODE = Src::NNODE, U = Src::U;
+  using Pre = typename Src::Pre;
   extern __shared__ double ar_smem[];
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned g = lane >> 2, j = lane & 3;
+  const bool jon = j < (unsigned)NNODE;
   double *acc = ar_smem + (size_t)wid * (AR_TILE_CAP + AR_RPT) * NN;
   double *dia = acc + (size_t)AR_TILE_CAP * NN;
   const uint32_t pair_base = nz2ptr[nnz];
@@ -630,28 +654,59 @@ __global__ void __launch_bounds__(AR_WARPS * 32) k_assemble_rows(const Src src, 
     const uint64_t r0 = tile * AR_RPT, r1 = min(r0 + (uint64_t)AR_RPT, num_rows), r = r0 + g;
     const bool valid = r < r1;
     const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
+    const uint32_t cb = valid ? nz2ptr[nnz + r] : 0u, n = valid ? nz2ptr[nnz + r + 1] - cb : 0u;
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
+    // software pipeline over chunks of U pairs: indices two chunks ahead, records one chunk ahead of the accumulation
+    uint32_t codeA[U], psA[U], codeB[U], psB[U];
+    Pre preA[U];
+    auto load_idx = [&](uint32_t t, uint32_t &code, uint32_t &ps) {
+      code = 0u;
+      ps = 0u;
+      if (t < n) {
+        code = __ldg(contrib + cb + t);
+        ps = __ldg(pair_slots + (cb + t - pair_base));
+      }
+    };
+    auto load_pre = [&](uint32_t t, uint32_t code) -> Pre {
+      const uint32_t ei = code / NNODE, e = ei / NNODE, i = ei - e * NNODE;
+      return src.load(e, i, j, jon && t < n);
+    };
+#pragma unroll
+    for (int u = 0; u < U; ++u) load_idx(u, codeA[u], psA[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) load_idx(U + u, codeB[u], psB[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) preA[u] = load_pre(u, codeA[u]);
     for (uint32_t q = lane; q < nb * NN; q += 32) acc[q] = 0.0;
     for (uint32_t q = lane; q < AR_RPT * NN; q += 32) dia[q] = 0.0;
     __syncwarp();
-    const uint32_t cb = valid ? nz2ptr[nnz + r] : 0u, n = valid ? nz2ptr[nnz + r + 1] - cb : 0u;
-    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-    uint32_t code_n = (0 < n) ? __ldg(contrib + cb) : 0u, ps_n = (0 < n) ? __ldg(pair_slots + (cb - pair_base)) : 0u;
-    for (uint32_t t = 0; t < nmax; ++t) {
-      const bool active = t < n;
-      const uint32_t code = code_n, ps = ps_n;
-      if (t + 1 < n) {  // next pair's indices are in flight while this pair's records are fetched
-        code_n = __ldg(contrib + cb + t + 1);
-        ps_n = __ldg(pair_slots + (cb + t + 1 - pair_base));
-      }
-      const uint32_t ei = code / NNODE, e = ei / NNODE, i = ei - e * NNODE;
-      const bool on = active && j < (unsigned)NNODE;
-      double blk[NN];
-      src.get(e, i, j, on, blk);
-      if (on) {
-        const uint32_t rel = (ps >> (8 * j)) & 0xFFu;
-        double *dst = (rel == 0xFFu) ? dia + g * NN : acc + (size_t)rel * NN;
+    for (uint32_t t0 = 0; t0 < nmax; t0 += U) {
+      Pre preB[U];
+      uint32_t codeC[U], psC[U];
 #pragma unroll
-        for (int q = 0; q < NN; ++q) dst[q] += blk[q];
+      for (int u = 0; u < U; ++u) preB[u] = load_pre(t0 + U + u, codeB[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) load_idx(t0 + 2 * U + u, codeC[u], psC[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ei = codeA[u] / NNODE, i = ei % NNODE;
+        const bool on = jon && (t0 + u) < n;
+        double blk[NN];
+        src.block(preA[u], i, on, blk);
+        if (on) {
+          const uint32_t rel = (psA[u] >> (8 * j)) & 0xFFu;
+          double *dst = (rel == 0xFFu) ? dia + g * NN : acc + (size_t)rel * NN;
+#pragma unroll
+          for (int q = 0; q < NN; ++q) dst[q] += blk[q];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        preA[u] = preB[u];
+        codeA[u] = codeB[u];
+        psA[u] = psB[u];
+        codeB[u] = codeC[u];
+        psB[u] = psC[u];
       }
     }
     __syncwarp();
@@ -769,7 +824,10 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
   case K:                                                                                                                             \
     DFB_LAUNCH(c, k_node_recs<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (NodeRec *)plan->d_geo); \
     if (rows_path) {                                                                                                                  \
-      SrcRecs<K> src = {(const NodeRec *)plan->d_geo, p0, p1};                                                                        \
+      SrcRecs<K> src;                                                                                                                 \
+      src.recs = (const NodeRec *)plan->d_geo;                                                                                        \
+      src.p0 = p0;                                                                                                                    \
+      src.p1 = p1;                                                                        \
       DFB_TRY(launch_assemble_rows(plan, src, m));                                                                                    \
     } else {                                                                                                                          \
       DFB_LAUNCH(c, k_assemble_recs<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                     \
@@ -1321,7 +1379,8 @@ DFB_API dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev
     if (plan->pairs_state == 1) {
 #define FE_ROWS(NNODE, NV)                                     \
   if (plan->num_node == NNODE && m->blk_dim == NV) {           \
-    SrcEmat<NNODE, NV> src = {emat_dev};                       \
+    SrcEmat<NNODE, NV> src;                                    \
+    src.emat = emat_dev;                                       \
     return launch_assemble_rows(plan, src, m);                 \
   }
       FE_ROWS(2, 1) FE_ROWS(2, 2) FE_ROWS(2, 3) FE_ROWS(3, 1) FE_ROWS(3, 2) FE_ROWS(3, 3) FE_ROWS(4, 1) FE_ROWS(4, 2) FE_ROWS(4, 3)
