@@ -228,7 +228,6 @@ def run_ours(args):
     ctx.set_option("use_peer_halo", 0 if args.no_peer_halo else 1)
     ctx.set_option("iters_per_sync", args.iters_per_sync)
     ctx.set_option("use_pdl", 1 if args.pdl else 0)
-    ctx.set_option("spmv_col16", 0 if args.no_col16 else 1)
     ctx.set_option("profile_spmv", args.profile_every)
     n = synthetic.SIZES.get(args.workload) or int(args.workload)
     nx = ny = n
@@ -431,7 +430,6 @@ def main():
     ap.add_argument("--no-peer-halo", action="store_true", help="multi-GPU: exchange ghosts with ncclSend/ncclRecv instead of the NVLink peer push")
     ap.add_argument("--profile-every", type=int, default=8, help="bracket every K-th SpMV launch of the timed PCG loops with CUDA events (roofline.achieved); 0 = off")
     ap.add_argument("--pdl", action="store_true", help="launch the PCG iteration kernels as programmatic dependent launches (measured ~1 %% slower)")
-    ap.add_argument("--no-col16", action="store_true", help="packed SpMV mirror: 32-bit columns in every tile (default: 16-bit offsets where a tile's column range fits)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

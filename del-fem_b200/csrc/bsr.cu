@@ -567,10 +567,10 @@ struct RingSmem {
 };
 
 // one row (or its share) of the ring kernel; vals/cols/dia point to the staged tile (shared) or to global memory
-template <int N, int LPR, typename CT = uint32_t>
-__device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const CT *cols, const double *dia,
+template <int N, int LPR>
+__device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const uint32_t *cols, const double *dia,
                                            uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub,
-                                           const double (&dcol)[N], double dxo, uint32_t cbase = 0u) {
+                                           const double (&dcol)[N], double dxo) {
   constexpr int NN = N * N;
   double s[N];
   // contribution of a diagonal-block column that was fetched straight from global memory (zero otherwise)
@@ -583,7 +583,7 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint32_t kk = k + u * LPR;
-      c[u] = (kk < ke) ? cbase + (uint32_t)cols[kk] : 0xFFFFFFFFu;
+      c[u] = (kk < ke) ? cols[kk] : 0xFFFFFFFFu;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -803,40 +803,24 @@ struct PackedCfg {
   static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
 };
 
-// header words: [0..8] row pointers relative to the tile, [9] column base, [10] column width (0: u32 columns, 1: u16 offsets
-// from the base — chosen per tile when the tile's column range fits 16 bits, which saves 2 of the 76 bytes per block)
-__host__ __device__ inline uint32_t pk_col_bytes(uint32_t nb, uint32_t c16) { return ((nb * (c16 ? 2u : 4u)) + 15u) & ~15u; }
-__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia, uint32_t c16) {
-  const uint32_t bytes = PK_HDR + pk_col_bytes(nb, c16) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
+__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia) {
+  const uint32_t bytes = PK_HDR + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
   return bytes >> 4;
 }
-__device__ __forceinline__ void pk_col_range(const uint32_t *__restrict__ idx2col, uint32_t k0, uint32_t nb, uint32_t &cmin, uint32_t &c16) {
-  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-  for (uint32_t k = 0; k < nb; ++k) {
-    const uint32_t c = idx2col[k0 + k];
-    lo = min(lo, c);
-    hi = max(hi, c);
-  }
-  cmin = nb ? lo : 0u;
-  c16 = (nb == 0 || hi - lo < 65536u) ? 1u : 0u;
-}
 
-__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col, uint64_t n_rows, uint64_t n_tiles,
-                             int NN, int has_dia, int allow_c16, uint32_t *__restrict__ tile_units) {
+__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia,
+                             uint32_t *__restrict__ tile_units) {
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
-    const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
-    uint32_t cmin = 0u, c16 = 0u;
-    if (allow_c16) pk_col_range(idx2col, k0, nb, cmin, c16);
-    tile_units[t] = pk_tile_units(nb, NN, has_dia, c16);
+    tile_units[t] = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia);
   }
 }
 
 // one warp per tile: streams the tile's pieces out of the canonical arrays into its packed record
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
                                                     const double *__restrict__ idx2val, const double *__restrict__ row2val,
-                                                    uint64_t n_rows, uint64_t n_tiles, int NN, int allow_c16,
-                                                    const uint32_t *__restrict__ tile_off, unsigned char *__restrict__ packed) {
+                                                    uint64_t n_rows, uint64_t n_tiles, int NN, const uint32_t *__restrict__ tile_off,
+                                                    unsigned char *__restrict__ packed) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   const int has_dia = row2val != nullptr;
@@ -845,28 +829,12 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__
     const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
     unsigned char *rec = packed + (uint64_t)tile_off[t] * 16;
     uint32_t *hdr = reinterpret_cast<uint32_t *>(rec);
-    // column width of this tile: the unit count of the record says which layout k_pack_sizes chose
-    const uint32_t c16 = (allow_c16 && (tile_off[t + 1] - tile_off[t]) == pk_tile_units(nb, NN, has_dia, 1u) &&
-                          pk_tile_units(nb, NN, has_dia, 1u) != pk_tile_units(nb, NN, has_dia, 0u)) ? 1u : 0u;
-    uint32_t cmin = 0u;
-    if (c16) {
-      uint32_t lo = 0xFFFFFFFFu;
-      for (uint32_t k = lane; k < nb; k += 32) lo = min(lo, idx2col[k0 + k]);
-#pragma unroll
-      for (int off = 16; off; off >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-      cmin = lo;
-    }
     if (lane <= PK_RPT) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
-    if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = (lane == PK_RPT + 1) ? cmin : ((lane == PK_RPT + 2) ? c16 : 0u);
-    const uint32_t colb = pk_col_bytes(nb, c16);
-    if (c16) {
-      uint16_t *cols = reinterpret_cast<uint16_t *>(rec + PK_HDR);
-      for (uint32_t k = lane; k < colb / 2u; k += 32) cols[k] = (k < nb) ? (uint16_t)(idx2col[k0 + k] - cmin) : (uint16_t)0;
-    } else {
-      uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
-      for (uint32_t k = lane; k < colb / 4u; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
-    }
-    double *dia = reinterpret_cast<double *>(rec + PK_HDR + colb);
+    if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = 0u;
+    uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
+    const uint32_t ncol_pad = ((nb * 4u + 15u) & ~15u) / 4u;
+    for (uint32_t k = lane; k < ncol_pad; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
+    double *dia = reinterpret_cast<double *>(rec + PK_HDR + ncol_pad * 4u);
     if (has_dia) {
       const uint32_t nd = (uint32_t)(r1 - r0) * NN;
       for (uint32_t q = lane; q < (uint32_t)(PK_RPT * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
@@ -978,17 +946,12 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
       if (b) phase1 ^= 1u;
       else phase0 ^= 1u;
       const uint32_t *hdr = reinterpret_cast<const uint32_t *>(buf);
-      const uint32_t nb = hdr[RPT], cbase = hdr[RPT + 1], c16 = hdr[RPT + 2];
+      const uint32_t nb = hdr[RPT];
       const uint32_t kb = hdr[rl], ke = hdr[rl + 1];
-      const double *sd0 = reinterpret_cast<const double *>(buf + PK_HDR + pk_col_bytes(nb, c16));
+      const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + PK_HDR);
+      const double *sd0 = reinterpret_cast<const double *>(buf + PK_HDR + ((nb * 4u + 15u) & ~15u));
       const double *sv = sd0 + (has_dia ? RPT * NN : 0);
-      if (c16) {
-        dot += ring_row<N, LPR, uint16_t>(a, sv, reinterpret_cast<const uint16_t *>(buf + PK_HDR), has_dia ? sd0 + rl * NN : nullptr,
-                                          valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0, cbase);
-      } else {
-        dot += ring_row<N, LPR>(a, sv, reinterpret_cast<const uint32_t *>(buf + PK_HDR), has_dia ? sd0 + rl * NN : nullptr,
-                                valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
-      }
+      dot += ring_row<N, LPR>(a, sv, sc, has_dia ? sd0 + rl * NN : nullptr, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
     } else {
       // oversized tile: straight from the canonical arrays
       const uint32_t kb = valid ? a.row2idx[r] : 0u, ke = valid ? a.row2idx[r + 1] : 0u;
@@ -1016,9 +979,7 @@ static dfb_status bsr_pack(dfb_bsr *m, cudaStream_t strm) {
   if (!m->d_tile_off) {
     // the layout only depends on the pattern: sizes -> scan once
     DFB_TRY(dfb_dev_alloc_t(&m->d_tile_off, n_tiles + 2));
-    DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, n, n_tiles, NN, has_dia,
-               (int)(c->spmv_col16 != 0), m->d_tile_off);
-    m->packed_c16 = c->spmv_col16 != 0;
+    DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, m->d_tile_off);
     DFB_CHECK_LAUNCH();
     uint64_t total_units = 0;
     DFB_TRY(dfb_exclusive_scan_u32(c, m->d_tile_off, n_tiles, &total_units));
@@ -1028,7 +989,7 @@ static dfb_status bsr_pack(dfb_bsr *m, cudaStream_t strm) {
   }
   if (n_tiles > 0) {
     DFB_LAUNCH_ON(c, strm, k_pack_tiles, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val, n,
-                  n_tiles, NN, m->packed_c16, m->d_tile_off, m->d_packed);
+                  n_tiles, NN, m->d_tile_off, m->d_packed);
     DFB_CHECK_LAUNCH();
   }
   m->packed_valid = 1;

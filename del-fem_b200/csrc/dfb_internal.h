@@ -125,7 +125,6 @@ struct dfb_ctx {
   int64_t assemble_variant = 0;
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
-  int64_t spmv_col16 = 1;        // packed SpMV mirror: 16-bit column offsets in tiles whose column range fits (else 32-bit)
   int64_t use_pdl = 0;           // programmatic dependent launch of the PCG iteration kernels: measured 1 % SLOWER (profiles/README.md)
   // SpMV profiling (events on the launching stream)
   std::vector<cudaEvent_t> prof_ev;   // pairs
@@ -234,7 +233,6 @@ struct dfb_bsr {
   uint64_t packed_cap = 0;          // bytes allocated
   uint64_t n_tiles = 0;
   int packed_valid = 0;
-  int packed_c16 = 0;               // the layout was sized with 16-bit column offsets allowed (per-tile choice)
 };
 
 struct dfb_plan {

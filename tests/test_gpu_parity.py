@@ -278,44 +278,6 @@ def test_mult_vec_blkcsr_and_ragged_rows(dfb, ctx, orc, variant):
         ctx.set_option("spmv_variant", 20)
 
 
-@pytest.mark.parametrize("col16", [0, 1])
-@pytest.mark.parametrize("n", [1, 3])
-def test_packed_spmv_column_width_modes(dfb, ctx, orc, n, col16):
-    """packed mirror (variant 20): tiles whose column range fits 16 bits store u16 offsets from a per-tile base, the others u32.
-    A 200 000-row banded pattern with a few far-away columns exercises both layouts in one matrix; `spmv_col16` = 0 forces u32."""
-    import scipy.sparse as sp
-    rng = np.random.default_rng(11)
-    nb = 200_000
-    rows = np.repeat(np.arange(nb), 5)
-    cols = np.clip(rows + rng.integers(-300, 301, rows.size), 0, nb - 1)
-    far = rng.random(rows.size) < 0.001          # a few entries far from the diagonal: their tiles need 32-bit columns
-    cols[far] = rng.integers(0, nb, int(far.sum()))
-    A = sp.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(nb, nb))
-    A.sum_duplicates()
-    A.sort_indices()
-    r2i, i2c = A.indptr.astype(np.uint64), A.indices.astype(np.uint64)
-    iv = rng.standard_normal((i2c.size, n * n))
-    x = rng.standard_normal((nb, n))
-    ctx.set_option("spmv_variant", 20)
-    ctx.set_option("spmv_col16", col16)
-    try:
-        pat = dfb.Pattern(ctx, r2i, i2c, 1)
-        mat = dfb.Matrix(ctx, pat, n)
-        mat.upload(None, iv)
-        y = dfb.Vec(ctx, nb, n)
-        mat.mult_vec(y, 0.0, 1.0, dfb.Vec.from_numpy(ctx, x))
-        blocks = iv.reshape(-1, n, n).transpose(0, 2, 1)
-        B = sp.bsr_matrix((blocks, A.indices, A.indptr), shape=(n * nb, n * nb))
-        want = (B @ x.reshape(-1)).reshape(nb, n)
-        assert rel_err(y.download(), want) < 1e-13
-        # values change, layout stays: the re-pack must reproduce the same column encoding
-        mat.upload(None, 2.0 * iv)
-        mat.mult_vec(y, 0.0, 1.0, dfb.Vec.from_numpy(ctx, x))
-        assert rel_err(y.download(), 2.0 * want) < 1e-13
-    finally:
-        ctx.set_option("spmv_col16", 1)
-
-
 def test_ls_smoke_pattern(dfb, ctx, orc):
     """del-fem-ls/src/sparse_square.rs:166-184: 4-row pattern with explicit diagonal slots, merge + mult_vec"""
     colind = np.array([0, 2, 5, 8, 10], dtype=np.uint64)
