@@ -227,7 +227,6 @@ def run_ours(args):
     ctx.set_option("spmv_variant", args.spmv_variant)
     ctx.set_option("use_peer_halo", 0 if args.no_peer_halo else 1)
     ctx.set_option("iters_per_sync", args.iters_per_sync)
-    ctx.set_option("use_pdl", 1 if args.pdl else 0)
     ctx.set_option("profile_spmv", args.profile_every)
     n = synthetic.SIZES.get(args.workload) or int(args.workload)
     nx = ny = n
@@ -429,7 +428,6 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="multi-GPU: use ncclAllReduce for the PCG scalars instead of the peer mailboxes")
     ap.add_argument("--no-peer-halo", action="store_true", help="multi-GPU: exchange ghosts with ncclSend/ncclRecv instead of the NVLink peer push")
     ap.add_argument("--profile-every", type=int, default=8, help="bracket every K-th SpMV launch of the timed PCG loops with CUDA events (roofline.achieved); 0 = off")
-    ap.add_argument("--pdl", action="store_true", help="launch the PCG iteration kernels as programmatic dependent launches (measured ~1 %% slower)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -567,7 +567,7 @@ struct RingSmem {
 };
 
 // one row (or its share) of the ring kernel; vals/cols/dia point to the staged tile (shared) or to global memory
-template <int N, int LPR>
+template <int N, int LPR, bool HALO = false>
 __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const uint32_t *cols, const double *dia,
                                            uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub,
                                            const double (&dcol)[N], double dxo) {
@@ -587,7 +587,7 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], c[u] >= a.hw.n_own ? a.hw.xg : a.x, c[u]);
+      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], (HALO && c[u] >= a.hw.n_own) ? a.hw.xg : a.x, c[u]);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -846,13 +846,17 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__
   }
 }
 
-template <int N>
+// HALO = false is the single-domain kernel; HALO = true adds the peer-halo logic (ghost columns from the landing zone, interior
+// tiles first, bounded wait before the first boundary tile). The two are separate instantiations because the extra address
+// select and tile mapping in the hot loop cost the single-domain kernel 14 % when they were compiled in unconditionally.
+template <int N, bool HALO>
 __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const SpmvArgs a, const unsigned char *__restrict__ packed,
                                                                          const uint32_t *__restrict__ tile_off, int has_dia) {
   using S = PackedCfg<N>;
   constexpr int NN = N * N, RPT = PK_RPT, LPR = PK_LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
+  if (a.st && a.st->done[a.parity]) return;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned sub = lane % LPR, rl = lane / LPR;
   unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
@@ -864,23 +868,20 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  dfb_pdl_wait();  // everything above is independent of the predecessor kernel
-  if (a.st && a.st->done[a.parity]) return;
   const uint32_t t_begin = a.row_begin / RPT, t_end = (a.row_end + RPT - 1) / RPT;
   const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
   // Tiles are visited in a virtual order v = t_begin + wg, + ws, ...: with a peer halo the interior tiles come first and the
   // tiles that read ghost columns ([t_begin, t_lo) and [t_hi, t_end)) last, so the neighbours' pushes have normally landed by
   // the time a warp reaches them; without a halo the mapping is the identity.
-  const bool halo = a.hw.xg != nullptr;
-  const uint32_t t_lo = halo ? min(max(a.hw.tile_lo_end, t_begin), t_end) : t_begin;
-  const uint32_t t_hi = halo ? min(max(a.hw.tile_hi_begin, t_lo), t_end) : t_end;
+  const uint32_t t_lo = HALO ? min(max(a.hw.tile_lo_end, t_begin), t_end) : t_begin;
+  const uint32_t t_hi = HALO ? min(max(a.hw.tile_hi_begin, t_lo), t_end) : t_end;
   const uint32_t n_int = t_hi - t_lo;
   auto tile_of = [&](uint32_t v) -> uint32_t {   // v and the result are absolute tile indices in [t_begin, t_end)
-    if (!halo || v >= t_hi) return v;
+    if (!HALO || v >= t_hi) return v;
     const uint32_t k = v - t_begin;
     return k < n_int ? t_lo + k : t_begin + (k - n_int);
   };
-  bool waited = !halo;
+  bool waited = !HALO;
 
   struct Off {
     uint32_t o0, o1;
@@ -917,7 +918,7 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   for (uint32_t v = t_begin + wg; v < t_end; v += ws) {
     const Off qn = offs(v + 3 * ws);  // requested now, used at the end of the next iteration
     const uint32_t t = tile_of(v);
-    if (!waited && (t < t_lo || t >= t_hi)) {
+    if (HALO && !waited && (t < t_lo || t >= t_hi)) {
       // first boundary tile of this warp: the ghost values must have landed (all neighbours, see peer.cuh)
       int ok = 1;
       if (lane == 0) ok = halo_wait(a.hw) ? 1 : 0;
@@ -951,11 +952,11 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
       const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + PK_HDR);
       const double *sd0 = reinterpret_cast<const double *>(buf + PK_HDR + ((nb * 4u + 15u) & ~15u));
       const double *sv = sd0 + (has_dia ? RPT * NN : 0);
-      dot += ring_row<N, LPR>(a, sv, sc, has_dia ? sd0 + rl * NN : nullptr, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
+      dot += ring_row<N, LPR, HALO>(a, sv, sc, has_dia ? sd0 + rl * NN : nullptr, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
     } else {
       // oversized tile: straight from the canonical arrays
       const uint32_t kb = valid ? a.row2idx[r] : 0u, ke = valid ? a.row2idx[r + 1] : 0u;
-      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, (valid && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
+      dot += ring_row<N, LPR, HALO>(a, a.idx2val, a.idx2col, (valid && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
                               dzero, 0.0);
     }
     __syncwarp();
@@ -965,7 +966,6 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
     q2 = qn;
     b ^= 1u;
   }
-  dfb_pdl_trigger();
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
@@ -1003,16 +1003,23 @@ static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bs
   const size_t smem = (size_t)warps * S::WARP_BYTES;
   static bool configured = false;
   if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const uint64_t t_begin = a.row_begin / PK_RPT, t_end = ((uint64_t)a.row_end + PK_RPT - 1) / PK_RPT;
   uint64_t g = (t_end - t_begin + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  // inside the solvers (a.st set) the launch is a programmatic dependent of the previous iteration's direction kernel
-  DFB_LAUNCH_PDL(c, strm, (a.st != nullptr && c->use_pdl != 0), (k_spmv_packed<N>), (unsigned)g, warps * 32, smem, a,
-                 (const unsigned char *)m->d_packed, (const uint32_t *)m->d_tile_off, (int)(m->d_row2val != nullptr));
+  if (a.hw.xg != nullptr) {
+    static bool configured_h = false;
+    if (!configured_h) {
+      DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_h = true;
+    }
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+  } else {
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+  }
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }

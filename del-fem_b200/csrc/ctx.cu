@@ -147,7 +147,6 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "spmv_variant")) return &c->spmv_variant;
   if (!strcmp(key, "iters_per_sync")) return &c->iters_per_sync;
   if (!strcmp(key, "use_graph")) return &c->use_graph;
-  if (!strcmp(key, "use_pdl")) return &c->use_pdl;
   if (!strcmp(key, "assemble_variant")) return &c->assemble_variant;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;

@@ -43,37 +43,6 @@ dfb_status dfb_fail(dfb_status st, const char *fmt, ...);
     kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                            \
     (ctx)->launches += 1;                                                                \
   } while (0)
-// Programmatic dependent launch (sm_90+): a kernel launched with `pdl` may become resident while its predecessor in the stream
-// drains; it MUST execute dfb_pdl_wait() before touching anything the predecessor reads or writes. Used for the three kernels
-// of the PCG iteration, whose launch latency otherwise sits between dependent kernels ~3 times per iteration.
-template <typename... KArgs, typename... Args>
-static inline cudaError_t dfb_launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, bool pdl,
-                                        Args &&...args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = strm;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-#define DFB_LAUNCH_PDL(ctx, strm, pdl, kernel, grid, block, smem, ...)                                    \
-  do {                                                                                                    \
-    cudaError_t _le = dfb_launch_ex(kernel, dim3(grid), dim3(block), (smem), (strm), (pdl), __VA_ARGS__); \
-    if (_le != cudaSuccess) return dfb_fail(DFB_ERR_CUDA, "launch failed: %s", cudaGetErrorString(_le));  \
-    (ctx)->launches += 1;                                                                                 \
-  } while (0)
-#ifdef __CUDACC__
-// wait for the predecessor grid (no-op for a normally launched kernel), then let the successor start its own launch
-__device__ __forceinline__ void dfb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-// called once the CTA's streaming loop is over: the successor's CTAs take the SM as this kernel's CTAs retire (triggering at
-// the top instead was measured SLOWER: resident-but-waiting CTAs of the successor take registers/shared memory from this kernel)
-__device__ __forceinline__ void dfb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-#endif
 #define DFB_CHECK_LAUNCH() DFB_CUDA(cudaGetLastError())
 
 static const int DFB_RED_MAX_BLOCKS = 2048;  // upper bound of any reducing grid
@@ -125,7 +94,6 @@ struct dfb_ctx {
   int64_t assemble_variant = 0;
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
-  int64_t use_pdl = 0;           // programmatic dependent launch of the PCG iteration kernels: measured 1 % SLOWER (profiles/README.md)
   // SpMV profiling (events on the launching stream)
   std::vector<cudaEvent_t> prof_ev;   // pairs
   size_t prof_used = 0;

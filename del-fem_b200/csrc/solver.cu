@@ -378,7 +378,6 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
                                                          uint64_t n, DfbSolverState *st, int parity, double *partials,
                                                          unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
   __shared__ double s_buf[64];
-  dfb_pdl_wait();
   if (st->done[parity]) return;
   double pq = st->red[0];
   if (pv_in.nranks > 1) {
@@ -422,7 +421,6 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
     acc[0] += rv * rv;
     acc[1] += rv * z;
   }
-  dfb_pdl_trigger();
   if (grid_sum_last_block<2>(acc, partials, ticket, s_buf)) {
     if (threadIdx.x == 0) {
       st->red[1] = acc[0];
@@ -438,7 +436,6 @@ template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__restrict__ r, double *__restrict__ p,
                                                             const double *__restrict__ inv, uint64_t n, DfbSolverState *st,
                                                             int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
-  dfb_pdl_wait();
   if (st->done[parity]) {
     if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
     return;
@@ -479,7 +476,6 @@ __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__rest
     pv.y = z.y + beta * pv.y;
     p2[i] = pv;
   }
-  dfb_pdl_trigger();
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const uint64_t i = n - 1;
     const double z = (KIND == DFB_PRECOND_JACOBI) ? inv[i] * r[i] : r[i];
@@ -552,7 +548,6 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   // scalar all-reduces: fused into the kernels through the NVLink peer mailboxes when mapped, NCCL otherwise
   const bool peer = c->peer_enabled && c->use_peer_allreduce && c->nranks > 1;
   const bool nccl_red = c->nranks > 1 && !peer;
-  const bool pdl = c->use_pdl != 0;
   const DfbPeerView pv_none = dfb_peer_view(c, 0);
   DfbPeerView pv_off = pv_none;  // consumers read st->red[] (filled by k_peer_gather / NCCL / the local reduction)
   pv_off.nranks = 1;
@@ -604,9 +599,9 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
         DISPATCH_ALL(UPD)
 #undef UPD
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       } else {
-        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
+        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
       }
       if (ilu) {
         // the update kernel ran with M = I (r.r in red[1]); now z = M^-1 r explicitly and r.z -> red[2]
@@ -621,14 +616,14 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
         DISPATCH_ALL(DIR)
 #undef DIR
       } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       } else if (ilu) {
 #define DIRZ(NV) \
   if (n == NV) DFB_LAUNCH(c, (k_pcg_direction<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, p->d, zbuf, nb, st, parity, c->d_hist, c->hist_cap, pv_off);
         DIRZ(1) DIRZ(2) DIRZ(3) DIRZ(4)
 #undef DIRZ
       } else {
-        DFB_LAUNCH_PDL(c, c->stream, pdl, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
+        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
       }
     }
     DFB_CHECK_LAUNCH();
