@@ -225,7 +225,7 @@ def run_ours(args):
             dist.all_gather_object(handles, ctx.peer_export())
             ctx.peer_import(handles)
     ctx.set_option("spmv_variant", args.spmv_variant)
-    ctx.set_option("use_peer_halo", 0 if args.no_peer_halo else 1)
+    ctx.set_option("use_peer_halo", 1 if args.peer_halo else 0)
     ctx.set_option("iters_per_sync", args.iters_per_sync)
     ctx.set_option("profile_spmv", args.profile_every)
     n = synthetic.SIZES.get(args.workload) or int(args.workload)
@@ -368,7 +368,7 @@ def run_ours(args):
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {nx}x{ny}x{nz}-vertex Kuhn tet cube, {n_dof_total} DoF, linear elasticity (lambda=mu=1), "
                                       f"z=0 clamped, rhs=-K*u0(splitmix seed 0), {args.precond}-PCG to 1e-8",
-                          "partition": f"{world} z-slab(s)", "scalar_allreduce": ("nvlink peer mailbox (fused in kernels)" if (world > 1 and not args.no_peer) else ("nccl" if world > 1 else "none")), "halo": ("nvlink peer push (pack kernel stores into the neighbours' landing zones; boundary SpMV tiles wait on flags)" if (world > 1 and not args.no_peer and not args.no_peer_halo and args.spmv_variant == 20) else ("nccl send/recv" if world > 1 else "none")), "precond": args.precond, "spmv_variant": args.spmv_variant,
+                          "partition": f"{world} z-slab(s)", "scalar_allreduce": ("nvlink peer mailbox (fused in kernels)" if (world > 1 and not args.no_peer) else ("nccl" if world > 1 else "none")), "halo": ("nvlink peer push (pack kernel stores into the neighbours' landing zones; boundary SpMV tiles wait on flags)" if (world > 1 and not args.no_peer and args.peer_halo and args.spmv_variant == 20) else ("nccl send/recv" if world > 1 else "none")), "precond": args.precond, "spmv_variant": args.spmv_variant,
                           "l2_note": "matrix (3.6 GB/rank at S10) >> 126 MB L2: no flush needed between iterations"},
                "assembly_ms": asm_total / args.steps, "pcg_ms": (total_ms - asm_total) / args.steps, "pcg_iters": iters[0],
                "final_rel_residual": final_rel, "wall_s_timed_region": t_wall,
@@ -426,7 +426,7 @@ def main():
     ap.add_argument("--spmv-variant", type=int, default=int(os.environ.get("DFB_SPMV_VARIANT", "20")))
     ap.add_argument("--iters-per-sync", type=int, default=32)
     ap.add_argument("--no-peer", action="store_true", help="multi-GPU: use ncclAllReduce for the PCG scalars instead of the peer mailboxes")
-    ap.add_argument("--no-peer-halo", action="store_true", help="multi-GPU: exchange ghosts with ncclSend/ncclRecv instead of the NVLink peer push")
+    ap.add_argument("--peer-halo", action="store_true", help="multi-GPU: exchange ghosts by the NVLink peer push instead of ncclSend/ncclRecv (experimental: measured slower)")
     ap.add_argument("--profile-every", type=int, default=8, help="bracket every K-th SpMV launch of the timed PCG loops with CUDA events (roofline.achieved); 0 = off")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
