@@ -1127,13 +1127,20 @@ dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha,
   if (post_seq != 0 && c->spmv_variant == 20 && dfb_halo_peer_usable(m->halo, m->blk_dim)) {
     // peer push (inside the solvers, where the scalar all-reduces order consecutive exchanges): one pack-and-push launch, then
     // ONE SpMV launch over all rows whose boundary tiles wait for the neighbours' flags
+    // This rank's SpMV does not depend on its OWN push (it reads what the neighbours pushed), so the push runs on the comm
+    // stream beside the SpMV; the main stream only rejoins it before anything may overwrite x again.
     DfbHaloWait hw;
-    DFB_TRY(dfb_halo_push(m->halo, x, m->blk_dim, parity, c->stream, &hw));
+    DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    DFB_CUDA(cudaStreamWaitEvent(c->stream_comm, c->ev_a, 0));
+    DFB_TRY(dfb_halo_push(m->halo, x, m->blk_dim, parity, c->stream_comm, &hw));
+    DFB_CUDA(cudaEventRecord(c->ev_b, c->stream_comm));
     hw.n_own = (uint32_t)n;
     hw.xg = hw.xg - n * (uint64_t)m->blk_dim;
     hw.tile_lo_end = (uint32_t)((m->int_begin + PK_RPT - 1) / PK_RPT);
     hw.tile_hi_begin = (uint32_t)(m->int_end / PK_RPT);
-    return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq, &hw);
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq, &hw));
+    DFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+    return DFB_OK;
   }
   // comm stream: wait until x is final, exchange ghosts
   DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
