@@ -139,6 +139,7 @@ def lib():
         "dfb_memcpy_d2h": [_vp, _vp, _vp, _u64],
         "dfb_memcpy_h2d": [_vp, _vp, _vp, _u64],
         "dfb_precond_create": [_vp, _i32, _vp, _pp],
+        "dfb_precond_create_iluk": [_vp, _vp, _u64, _pp],
         "dfb_precond_update": [_vp, _vp],
         "dfb_precond_apply": [_vp, _vp],
         "dfb_precond_destroy": [_vp],

@@ -232,7 +232,7 @@ struct dfb_precond {
   dfb_pattern *pat = nullptr;   // pattern of the matrix the ILU was built for
 };
 // ilu.cu
-dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, DfbIlu **out);
+dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIlu **out);
 void dfb_ilu_destroy(DfbIlu *s);
 dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia_out);
 dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec);

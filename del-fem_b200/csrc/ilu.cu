@@ -11,14 +11,18 @@
 // levels), which makes this preconditioner latency-bound on a GPU — it exists for fidelity with the reference's own PCG
 // (ILU(0) is what `solid_linear_tri2.rs:239-256` and `linearsystem::Solver` use), not for speed; Jacobi is the fast path.
 #include <algorithm>
+#include <map>
+#include <set>
 #include <vector>
 
 #include "dfb_internal.h"
 #include "reduce.cuh"
 
 struct DfbIlu {
+  uint32_t *d_r2i = nullptr;      // row pointers of the ILU pattern [n+1] (== A's for ILU(0), larger rows with fill for ILU(k))
+  uint64_t nnz = 0;               // entries of the ILU pattern
   uint32_t *d_col = nullptr;      // sorted columns [nnz]
-  uint32_t *d_a2ilu = nullptr;    // position of A's k-th entry inside the sorted row [nnz]
+  uint32_t *d_a2ilu = nullptr;    // position of A's k-th entry inside the ILU arrays [nnz of A]
   uint32_t *d_dia = nullptr;      // row2idx_dia [n]
   uint32_t *d_rows_f = nullptr;   // rows ordered by forward level [n]
   uint32_t *d_rows_b = nullptr;   // rows ordered by backward level [n]
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(256) k_ilu_dot(const double *__restrict__ a, c
 // ------------------------------------------------------------------------------------------------ host side
 void dfb_ilu_destroy(DfbIlu *s) {
   if (!s) return;
+  dfb_dev_free(s->d_r2i);
   dfb_dev_free(s->d_col);
   dfb_dev_free(s->d_a2ilu);
   dfb_dev_free(s->d_dia);
@@ -225,31 +230,88 @@ void dfb_ilu_destroy(DfbIlu *s) {
   delete s;
 }
 
-// initialize_ilu0 (:28-56) + level schedule
-dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, DfbIlu **out) {
-  DFB_REQUIRE(m->pat->convention == 0, "ilu0: needs the csrdia convention (separate diagonal)");
-  DFB_REQUIRE(c->nranks <= 1, "ilu0: single-GPU only (a distributed ILU would be a different preconditioner)");
-  const uint64_t n = m->pat->num_blk, nnz = m->pat->nnz;
+// initialize_ilu0 (:28-56) / initialize_iluk (:58-64, symbolic_iluk :221-312) + level schedule
+dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIlu **out) {
+  DFB_REQUIRE(m->pat->convention == 0, "ilu: needs the csrdia convention (separate diagonal)");
+  DFB_REQUIRE(c->nranks <= 1, "ilu: single-GPU only (a distributed ILU would be a different preconditioner)");
+  const uint64_t n = m->pat->num_blk, nnz_a = m->pat->nnz;
   const int N = m->blk_dim, NN = N * N;
-  std::vector<uint32_t> r2i(n + 1), col(nnz);
-  DFB_CUDA(cudaMemcpyAsync(r2i.data(), m->pat->d_row2idx, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (nnz) DFB_CUDA(cudaMemcpyAsync(col.data(), m->pat->d_idx2col, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint32_t> a_r2i(n + 1), a_col(nnz_a);
+  DFB_CUDA(cudaMemcpyAsync(a_r2i.data(), m->pat->d_row2idx, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (nnz_a) DFB_CUDA(cudaMemcpyAsync(a_col.data(), m->pat->d_idx2col, nnz_a * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  std::vector<uint32_t> scol(nnz), a2ilu(nnz), dia(n), lf(n, 0), lb(n, 0);
-  std::vector<std::pair<uint32_t, uint32_t>> tmp;
-  for (uint64_t i = 0; i < n; ++i) {
-    const uint32_t b = r2i[i], e = r2i[i + 1];
-    tmp.clear();
-    for (uint32_t k = b; k < e; ++k) {
-      if (col[k] == i) return dfb_fail(DFB_ERR_BAD_ARG, "ilu0: the pattern must not contain the diagonal (assert!(j_col < i_row) sparse_ilu.rs:199)");
-      tmp.emplace_back(col[k], k);
+  for (uint64_t i = 0; i < n; ++i)
+    for (uint32_t k = a_r2i[i]; k < a_r2i[i + 1]; ++k)
+      if (a_col[k] == i) return dfb_fail(DFB_ERR_BAD_ARG, "ilu: the pattern must not contain the diagonal (assert!(j_col < i_row) sparse_ilu.rs:199)");
+  // ---- symbolic phase: r2i / scol (sorted columns per row) / dia (first strictly-upper entry)
+  std::vector<uint32_t> r2i(n + 1, 0), scol, dia(n);
+  if (lev_fill == 0) {
+    r2i = a_r2i;
+    scol = a_col;
+    for (uint64_t i = 0; i < n; ++i) std::sort(scol.begin() + r2i[i], scol.begin() + r2i[i + 1]);
+  } else {
+    // level of fill: row i = A's columns at level 0, then for each strictly-lower column k (ascending) the strictly-upper part
+    // of the finished row k, entries (k,j) with level <= lev_fill - 1 reached through (i,k) with level <= lev_fill - 1, at level
+    // max + 1 (minimum over paths). Worklist and row are ordered containers, as the reference's BTreeSet / BTreeMap.
+    std::vector<uint32_t> lev;
+    scol.reserve(nnz_a * 2);
+    lev.reserve(nnz_a * 2);
+    std::map<uint32_t, uint64_t> row;
+    std::set<uint32_t> todo;
+    for (uint64_t i = 0; i < n; ++i) {
+      row.clear();
+      todo.clear();
+      for (uint32_t k = a_r2i[i]; k < a_r2i[i + 1]; ++k) {
+        row[a_col[k]] = 0;
+        if (a_col[k] < i) todo.insert(a_col[k]);
+      }
+      while (!todo.empty()) {
+        const uint32_t k = *todo.begin();
+        todo.erase(todo.begin());
+        const uint64_t lik = row[k];
+        if (lik + 1 > lev_fill) continue;
+        for (uint32_t kj = dia[k]; kj < r2i[k + 1]; ++kj) {
+          const uint64_t lkj = lev[kj];
+          if (lkj + 1 > lev_fill) continue;
+          const uint32_t j = scol[kj];
+          if (j == i) continue;
+          const uint64_t l = std::max(lik, lkj) + 1;
+          if (j < i) todo.insert(j);
+          auto it = row.find(j);
+          if (it == row.end()) row[j] = l;
+          else if (l < it->second) it->second = l;
+        }
+      }
+      if (scol.size() + row.size() > 0xFFFFFFF0ull) return dfb_fail(DFB_ERR_INDEX_OVERFLOW, "iluk: fill exceeds the u32 index range");
+      for (const auto &cl : row) {
+        scol.push_back(cl.first);
+        lev.push_back((uint32_t)std::min<uint64_t>(cl.second, 0xFFFFFFFFull));
+      }
+      r2i[i + 1] = (uint32_t)scol.size();
+      dia[i] = r2i[i + 1];
+      for (uint32_t q = r2i[i]; q < r2i[i + 1]; ++q)
+        if (scol[q] > i) {
+          dia[i] = q;
+          break;
+        }
     }
-    std::sort(tmp.begin(), tmp.end());
-    dia[i] = e;
-    for (uint32_t q = 0; q < tmp.size(); ++q) {
-      scol[b + q] = tmp[q].first;
-      a2ilu[tmp[q].second] = b + q;
-      if (dia[i] == e && tmp[q].first > i) dia[i] = b + q;
+  }
+  const uint64_t nnz = scol.size();
+  std::vector<uint32_t> a2ilu(nnz_a), lf(n, 0), lb(n, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    const auto rb = scol.begin() + r2i[i], re = scol.begin() + r2i[i + 1];
+    if (lev_fill == 0) {
+      dia[i] = r2i[i + 1];
+      for (uint32_t q = r2i[i]; q < r2i[i + 1]; ++q)
+        if (scol[q] > i) {
+          dia[i] = q;
+          break;
+        }
+    }
+    for (uint32_t k = a_r2i[i]; k < a_r2i[i + 1]; ++k) {
+      const auto it = std::lower_bound(rb, re, a_col[k]);  // copy_value's col2idx: A's entry must exist in the ILU row
+      if (it == re || *it != a_col[k]) return dfb_fail(DFB_ERR_PATTERN_MISS, "ilu copy_value: entry outside the ILU pattern (panic!() sparse_ilu.rs:115)");
+      a2ilu[k] = (uint32_t)(it - scol.begin());
     }
   }
   uint32_t max_f = 0, max_b = 0;
@@ -285,9 +347,11 @@ dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, DfbIlu **out) {
     st = dfb_dev_alloc_t(d, h.size() + 2);
     if (st == DFB_OK && !h.empty()) {
       cudaError_t e = cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
-      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu0: %s", cudaGetErrorString(e));
+      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu: %s", cudaGetErrorString(e));
     }
   };
+  s->nnz = nnz;
+  up(&s->d_r2i, r2i);
   up(&s->d_col, scol);
   up(&s->d_a2ilu, a2ilu);
   up(&s->d_dia, dia);
@@ -313,6 +377,7 @@ static int level_grid(uint32_t count) {
 dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia_out) {
   const uint64_t n = m->pat->num_blk, nnz = m->pat->nnz;
   const int N = m->blk_dim, NN = N * N;
+  if (s->nnz != nnz) DFB_CUDA(cudaMemsetAsync(s->d_val, 0, s->nnz * NN * sizeof(double), c->stream));  // fill entries start at zero
   DFB_LAUNCH(c, k_ilu_copy, c->sm_count * 8, 256, 0, m->d_idx2val, m->d_row2val, s->d_a2ilu, nnz, n, NN, s->d_val, d_dia_out);
   const uint32_t nlev = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1;
   for (uint32_t l = 0; l < nlev; ++l) {
@@ -320,7 +385,7 @@ dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia
     if (a == b) continue;
 #define DEC(NV)                                                                                                                     \
   case NV:                                                                                                                          \
-    DFB_LAUNCH(c, k_ilu_decompose_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, m->pat->d_row2idx, s->d_col, s->d_dia, s->d_val, \
+    DFB_LAUNCH(c, k_ilu_decompose_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, s->d_r2i, s->d_col, s->d_dia, s->d_val, \
                d_dia_out, c->d_errflag + 2);                                                                                        \
     break;
     switch (N) {
@@ -340,7 +405,7 @@ dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, in
     if (a == b) continue;
 #define FWD(NV)                                                                                                                      \
   case NV:                                                                                                                           \
-    DFB_LAUNCH(c, k_ilu_forward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, pat->d_row2idx, s->d_col, s->d_dia, s->d_val, d_dia, \
+    DFB_LAUNCH(c, k_ilu_forward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_f, a, b, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, \
                d_vec);                                                                                                               \
     break;
     switch (N) {
@@ -353,7 +418,7 @@ dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, in
     if (a == b) continue;
 #define BWD(NV)                                                                                                                       \
   case NV:                                                                                                                            \
-    DFB_LAUNCH(c, k_ilu_backward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_b, a, b, pat->d_row2idx, s->d_col, s->d_dia, s->d_val, d_vec); \
+    DFB_LAUNCH(c, k_ilu_backward_level<NV>, level_grid(b - a), 128, 0, s->d_rows_b, a, b, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_vec); \
     break;
     switch (N) {
       BWD(1) BWD(2) BWD(3) BWD(4)

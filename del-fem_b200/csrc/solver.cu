@@ -108,7 +108,7 @@ __global__ void k_precond_update(int kind, uint64_t num_blk, const double *__res
   }
 }
 
-DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, dfb_precond **out) {
+static dfb_status precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, uint64_t lev_fill, dfb_precond **out) {
   DFB_REQUIRE(ctx && m && out, "dfb_precond_create: NULL argument");
   DFB_REQUIRE(kind >= DFB_PRECOND_NONE && kind <= DFB_PRECOND_ILU0, "dfb_precond_create: unknown kind %d", kind);
   DFB_CUDA(cudaSetDevice(ctx->device));
@@ -122,7 +122,7 @@ DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr 
     const uint64_t per = kind == DFB_PRECOND_JACOBI ? (uint64_t)m->blk_dim : (uint64_t)m->blk_dim * m->blk_dim;
     dfb_status st = dfb_dev_alloc_t(&pc->d_inv, pc->num_blk * per + 8);
     if (st == DFB_OK && kind == DFB_PRECOND_ILU0) {
-      st = dfb_ilu_create(ctx, m, &pc->ilu);
+      st = dfb_ilu_create(ctx, m, lev_fill, &pc->ilu);
       if (st == DFB_OK) {
         pc->pat = m->pat;
         m->pat->refcount += 1;
@@ -136,6 +136,15 @@ DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr 
   }
   *out = pc;
   return DFB_OK;
+}
+
+DFB_API dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, dfb_precond **out) {
+  return precond_create(ctx, kind, m, 0, out);
+}
+
+// initialize_iluk (sparse_ilu.rs:58-64): the ILU preconditioner on the level-of-fill pattern; lev_fill = 0 is ILU(0)
+DFB_API dfb_status dfb_precond_create_iluk(dfb_ctx *ctx, const dfb_bsr *m, uint64_t lev_fill, dfb_precond **out) {
+  return precond_create(ctx, DFB_PRECOND_ILU0, m, lev_fill, out);
 }
 
 DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {

@@ -1,5 +1,5 @@
-"""Mirror of del-fem-cpu/src/sparse_ilu.rs for the preconditioners that exist on the device: the ILU code path with an
-empty off-diagonal pattern (= block-Jacobi) and point Jacobi. ILU(0)/ILU(k) with real fill are §8(f) "next"."""
+"""Mirror of del-fem-cpu/src/sparse_ilu.rs: ILU(0) (`initialize_ilu0`), ILU(k) (`initialize_iluk`, level of fill), the same code
+path with an empty off-diagonal pattern (= block-Jacobi) and point Jacobi (DERIVED)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -20,6 +20,19 @@ class Preconditioner:
         self.ctx = a.ctx
         h = C.c_void_p()
         check(lib().dfb_precond_create(a.ctx.h, self.kind, a.h, C.byref(h)))
+        self.h = h
+
+    def initialize_ilu0(self, a: Matrix):
+        """Preconditioner::initialize_ilu0 (:28-56)"""
+        self.kind = PRECOND["ilu0"]
+        self.initialize(a)
+
+    def initialize_iluk(self, a: Matrix, lev_fill: int):
+        """Preconditioner::initialize_iluk (:58-64): level-of-fill pattern from symbolic_iluk (:221-312)"""
+        self.kind = PRECOND["ilu0"]
+        self.ctx = a.ctx
+        h = C.c_void_p()
+        check(lib().dfb_precond_create_iluk(a.ctx.h, a.h, int(lev_fill), C.byref(h)))
         self.h = h
 
     def __del__(self):

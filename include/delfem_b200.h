@@ -215,6 +215,9 @@ dfb_status dfb_memcpy_h2d(dfb_ctx *ctx, void *dev, const void *host, uint64_t by
 
 /* ------------------------------------------------------------------------------------------------ solvers */
 dfb_status dfb_precond_create(dfb_ctx *ctx, int32_t kind, const dfb_bsr *m, dfb_precond **out);
+/* Preconditioner::initialize_iluk  del-fem-cpu/src/sparse_ilu.rs:58-64 (symbolic_iluk :221-312): ILU on the level-of-fill pattern;
+   lev_fill = 0 is DFB_PRECOND_ILU0, a very large lev_fill the complete LU (linearsystem.rs:55). Single GPU, level-scheduled. */
+dfb_status dfb_precond_create_iluk(dfb_ctx *ctx, const dfb_bsr *m, uint64_t lev_fill, dfb_precond **out);
 /* copy_value + decompose  (del-fem-cpu/src/sparse_ilu.rs:87-181; Solver::end_merge del-fem-ls/src/linearsystem.rs:67) */
 dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m);
 /* solve_preconditioning_vec  sparse_ilu.rs:183-219 (in place) */

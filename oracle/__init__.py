@@ -42,6 +42,7 @@ def lib():
         _lib.orc_conjugate_gradient.restype = C.c_int64
         _lib.orc_preconditioned_conjugate_gradient.restype = C.c_int64
         _lib.orc_pcg_jacobi3_mt.restype = C.c_int64
+        _lib.orc_symbolic_iluk.restype = C.c_uint64
         _lib.orc_ilu_new.restype = C.c_void_p
         _lib.orc_ilu_row2val.restype = C.POINTER(C.c_double)
         _lib.orc_version.restype = C.c_char_p
@@ -404,12 +405,13 @@ def conjugate_gradient(r, u, ap, p, tol, max_it, row2idx, idx2col, idx2val, row2
 
 
 class Ilu:
-    """del-fem-cpu/src/sparse_ilu.rs Preconditioner. mode: 'ilu0' | 'full' | 'block_jacobi' | 'jacobi'"""
+    """del-fem-cpu/src/sparse_ilu.rs Preconditioner. mode: 'ilu0' | 'full' | 'block_jacobi' | 'jacobi' | ('iluk', lev_fill)"""
     MODES = {"ilu0": 0, "full": 1, "block_jacobi": 2, "jacobi": 3}
 
     def __init__(self, mode, n, row2idx, idx2col):
         self.n = n
-        self.h = C.c_void_p(lib().orc_ilu_new(C.c_int(self.MODES[mode]), C.c_uint64(n), _p(row2idx),
+        code = 4 + int(mode[1]) if isinstance(mode, tuple) else self.MODES[mode]
+        self.h = C.c_void_p(lib().orc_ilu_new(C.c_int(code), C.c_uint64(n), _p(row2idx),
                                               C.c_uint64(row2idx.size - 1), _p(idx2col)))
         self.num_blk = row2idx.size - 1
 
@@ -430,6 +432,20 @@ class Ilu:
         if getattr(self, "h", None):
             lib().orc_ilu_free(self.h)
             self.h = None
+
+
+def symbolic_iluk(row2idx, idx2col, lev_fill):
+    """del-fem-cpu/src/sparse_ilu.rs:221-312 -> (row2idx, idx2col, row2idx_dia) of the level-of-fill pattern"""
+    n = row2idx.size - 1
+    r = np.zeros(n + 1, dtype=U64)
+    d = np.zeros(n, dtype=U64)
+    cap = max(int(idx2col.size) * 4, 16)
+    while True:
+        c = np.zeros(cap, dtype=U64)
+        need = int(lib().orc_symbolic_iluk(_p(row2idx), _p(idx2col), C.c_uint64(n), C.c_uint64(lev_fill), _p(r), _p(c), C.c_uint64(cap), _p(d)))
+        if need <= cap:
+            return r, c[:need].copy(), d
+        cap = need
 
 
 def preconditioned_conjugate_gradient(r, x, pr, p, tol, max_it, row2idx, idx2col, idx2val, row2val, ilu, flavour="cpu"):

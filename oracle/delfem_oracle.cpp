@@ -31,6 +31,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <set>
 #include <thread>
 #include <vector>
 
@@ -1165,8 +1167,68 @@ static void ilu_set_dia(OrcIlu *s) {
   }
 }
 
+// symbolic_iluk   del-fem-cpu/src/sparse_ilu.rs:221-312 — level-of-fill pattern: row i starts from A's (sorted) columns at
+// level 0; for every strictly-lower column k taken in ascending order (std BTreeSet), the strictly-upper part of the already
+// finished row k whose level allows it (lev_ik + 1 <= lev_fill and lev_kj + 1 <= lev_fill) is merged in with level
+// max(lev_ik, lev_kj) + 1 (minimum over all paths); the diagonal is never stored.
+static void symbolic_iluk(const usize *a_row2idx, const usize *a_idx2col, usize num_row, usize lev_fill, std::vector<usize> &row2idx,
+                          std::vector<usize> &idx2col, std::vector<usize> &row2idx_dia) {
+  row2idx.assign(num_row + 1, 0);
+  row2idx_dia.assign(num_row, 0);
+  std::vector<usize> col, lev;  // idx2collev
+  for (usize i = 0; i < num_row; ++i) {
+    std::map<usize, usize> col2lev;
+    std::set<usize> que;
+    for (usize k = a_row2idx[i]; k < a_row2idx[i + 1]; ++k) {
+      col2lev[a_idx2col[k]] = 0;  // BTreeMap::insert overwrites: duplicates collapse
+      if (a_idx2col[k] < i) que.insert(a_idx2col[k]);
+    }
+    while (!que.empty()) {
+      const usize k = *que.begin();
+      que.erase(que.begin());
+      const usize ik_lev = col2lev[k];
+      if (ik_lev + 1 > lev_fill) continue;
+      for (usize kj = row2idx_dia[k]; kj < row2idx[k + 1]; ++kj) {
+        const usize kj_lev = lev[kj];
+        if (kj_lev + 1 > lev_fill) continue;
+        const usize j = col[kj];
+        if (j == i) continue;
+        const usize mx = ik_lev > kj_lev ? ik_lev : kj_lev;
+        if (j < i) que.insert(j);
+        auto it = col2lev.find(j);
+        if (it == col2lev.end()) col2lev[j] = mx + 1;
+        else if (mx + 1 < it->second) it->second = mx + 1;
+      }
+    }
+    for (auto &cl : col2lev) {
+      col.push_back(cl.first);
+      lev.push_back(cl.second);
+    }
+    row2idx[i + 1] = row2idx[i] + col2lev.size();
+    row2idx_dia[i] = row2idx[i + 1];
+    for (usize q = row2idx[i]; q < row2idx[i + 1]; ++q)
+      if (col[q] > i) {
+        row2idx_dia[i] = q;
+        break;
+      }
+  }
+  idx2col = col;
+}
+
+// the pattern alone, for tests and for the device side's own symbolic phase to be compared with
+ORC_API usize orc_symbolic_iluk(const usize *a_row2idx, const usize *a_idx2col, usize num_row, usize lev_fill, usize *row2idx_out,
+                                usize *idx2col_out, usize cap, usize *row2idx_dia_out) {
+  std::vector<usize> r, c, d;
+  symbolic_iluk(a_row2idx, a_idx2col, num_row, lev_fill, r, c, d);
+  std::copy(r.begin(), r.end(), row2idx_out);
+  if (row2idx_dia_out) std::copy(d.begin(), d.end(), row2idx_dia_out);
+  if (c.size() <= cap) std::copy(c.begin(), c.end(), idx2col_out);
+  return c.size();
+}
+
 // mode 0: initialize_ilu0 (:28-56)   mode 1: initialize_full (:66-84)
 // mode 2: empty off-diagonal pattern = block-Jacobi   mode 3: point (scalar) Jacobi (DERIVED)
+// mode 4 + k: initialize_iluk (:58-64) with lev_fill = k
 ORC_API OrcIlu *orc_ilu_new(int mode, usize n, const usize *row2idx, usize num_blk, const usize *idx2col) {
   OrcIlu *s = new OrcIlu();
   s->n = n;
@@ -1184,6 +1246,9 @@ ORC_API OrcIlu *orc_ilu_new(int mode, usize n, const usize *row2idx, usize num_b
       for (usize j = 0; j < i; ++j) s->idx2col[i * (num_blk - 1) + j] = j;
       for (usize j = i + 1; j < num_blk; ++j) s->idx2col[i * (num_blk - 1) + j - 1] = j;
     }
+  } else if (mode >= 4) {
+    std::vector<usize> dia;
+    symbolic_iluk(row2idx, idx2col, num_blk, (usize)(mode - 4), s->row2idx, s->idx2col, dia);
   } else {
     s->row2idx.assign(num_blk + 1, 0);
   }

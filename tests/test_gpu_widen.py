@@ -509,3 +509,51 @@ def test_general_problem_single_rank_matches_oracle(dfb, ctx, orc):
     ho = orc.preconditioned_conjugate_gradient(b, xo, pr, p, 1e-8, 5000, r2i, i2c, iv, rv, ilu)
     assert abs(len(prob.hist) - len(ho)) <= 1
     assert rel_err(x, xo) < 1e-7
+
+
+@pytest.mark.parametrize("lev_fill", [0, 1, 3, 10000])
+def test_iluk_matches_oracle(dfb, ctx, orc, lev_fill):
+    """Preconditioner::initialize_iluk (sparse_ilu.rs:58-64, symbolic_iluk :221-312) on the device: same factors as the oracle's
+    serial ILU(k) applied to a random vector, same PCG history; lev_fill = 10000 (linearsystem.rs:55) is the complete LU, so PCG
+    returns after one step with the reference's history length 2 (solid_linear_tri2.rs:318-321)."""
+    from del_fem_b200 import sparse_ilu
+    import test_oracle_pins as T
+    p = T.unit_square_problem(orc)
+    r2i, i2c, nv = p["r2i"], p["i2c"], p["nv"]
+    rhs_h = np.zeros_like(p["u"])
+    orc.mult_vec(rhs_h, 0.0, -1.0, p["u"], r2i, i2c, p["iv"], p["rv"])
+    orc.set_fix_dof_to_rhs_vector(rhs_h, p["flag"])
+    rv, iv = p["rv"].copy(), p["iv"].copy()
+    orc.set_fixed_bc(1.0, p["flag"], rv, iv, r2i, i2c)
+    mat = dfb.Matrix.from_vtx2vtx(r2i, i2c, 2, ctx=ctx)
+    mat.upload(rv, iv)
+    ilu_o = orc.Ilu(("iluk", lev_fill), 2, r2i, i2c)
+    ilu_o.copy_value(r2i, i2c, iv, rv)
+    ilu_o.decompose()
+    pc = sparse_ilu.Preconditioner("ilu0")
+    pc.initialize_iluk(mat, lev_fill)
+    sparse_ilu.copy_value(pc, mat)
+    sparse_ilu.decompose(pc)
+    v = np.random.default_rng(3).standard_normal((nv, 2))
+    want = v.copy()
+    ilu_o.solve(want)
+    vd = dfb.Vec.from_numpy(ctx, v)
+    sparse_ilu.solve_preconditioning_vec(vd, pc)
+    assert rel_err(vd.download(), want) < 1e-12
+    ro = rhs_h.copy()
+    xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+    hist_o = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, 1e-5, 100, r2i, i2c, iv, rv, ilu_o)
+    rd = dfb.Vec.from_numpy(ctx, rhs_h)
+    xd, prd, pd = dfb.Vec(ctx, nv, 2), dfb.Vec(ctx, nv, 2), dfb.Vec(ctx, nv, 2)
+    hist_d = dfb.preconditioned_conjugate_gradient(rd, xd, prd, pd, 1e-5, 100, mat, pc)
+    assert abs(len(hist_d) - len(hist_o)) <= 1, (len(hist_d), len(hist_o))
+    assert rel_err(xd.download(), xo) < 1e-5
+    if lev_fill == 10000:
+        assert len(hist_d) == 2
+    # a second update (values changed) reuses the symbolic phase: fill entries must be re-zeroed
+    mat.upload(2.0 * rv, 2.0 * iv)
+    sparse_ilu.copy_value(pc, mat)
+    sparse_ilu.decompose(pc)
+    vd.upload(v)
+    sparse_ilu.solve_preconditioning_vec(vd, pc)
+    assert rel_err(vd.download(), 0.5 * want) < 1e-12

@@ -553,3 +553,64 @@ def test_threaded_baseline_pcg_agrees_with_the_oracle_pcg(orc):
         assert len(h2) == len(h1)
         assert np.abs(h2 - h1).max() <= 1e-9 * h1[0]
         assert np.abs(x2 - x).max() <= 1e-9 * np.abs(x).max()
+
+
+def test_symbolic_iluk_and_iluk_preconditioner(orc):
+    """sparse_ilu.rs:221-312: level-of-fill pattern. ILU(k=0) is the ILU(0) pattern (sorted columns); a huge k (the commented-out
+    `initialize_iluk(&sparse, 10000)` of linearsystem.rs:55) reproduces the fill of an exact LU, so one PCG step solves the system;
+    fill grows and PCG iterations shrink monotonically with k."""
+    import scipy.sparse as sp
+    t2v, xy = orc.grid_tri_mesh(10)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble("solid_linear_tri2", 0, t2v, xy, 1.0, 1.0, r2i, i2c)
+    flag = np.zeros((nv, 2), dtype=np.int32)
+    flag[xy[:, 1] == xy[:, 1].min()] = 1
+    rng = np.random.default_rng(0)
+    rhs = rng.standard_normal((nv, 2))
+    orc.set_fix_dof_to_rhs_vector(rhs, flag)
+    orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+    # k = 0: same column sets as A, sorted
+    r0, c0, d0 = orc.symbolic_iluk(r2i, i2c, 0)
+    assert np.array_equal(r0, r2i)
+    for i in range(nv):
+        assert np.array_equal(c0[r0[i]:r0[i + 1]], np.sort(i2c[r2i[i]:r2i[i + 1]]))
+        up = c0[r0[i]:r0[i + 1]] > i
+        assert d0[i] == (r0[i] + int(np.argmax(up)) if up.any() else r0[i + 1])
+    # exact symbolic LU fill (dense boolean elimination) == ILU(k -> infinity)
+    A = np.zeros((nv, nv), dtype=bool)
+    for i in range(nv):
+        A[i, i2c[r2i[i]:r2i[i + 1]].astype(np.int64)] = True
+        A[i, i] = True
+    F = A.copy()
+    for k in range(nv):
+        rows = np.nonzero(F[k + 1:, k])[0] + k + 1
+        F[np.ix_(rows, np.nonzero(F[k, k + 1:])[0] + k + 1)] = True
+    rinf, cinf, _ = orc.symbolic_iluk(r2i, i2c, 10000)
+    for i in (0, 1, nv // 3, nv // 2, nv - 2, nv - 1):
+        want = np.nonzero(F[i])[0]
+        assert np.array_equal(cinf[rinf[i]:rinf[i + 1]].astype(np.int64), want[want != i])
+    sizes, iters = [], []
+    for k in (0, 1, 2, 4, 10000):
+        ilu = orc.Ilu(("iluk", k), 2, r2i, i2c)
+        ilu.copy_value(r2i, i2c, iv, rv)
+        ilu.decompose()
+        r = rhs.copy()
+        x, pr, pp = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+        hist = orc.preconditioned_conjugate_gradient(r, x, pr, pp, 1e-10, 200, r2i, i2c, iv, rv, ilu)
+        y = np.zeros_like(x)
+        orc.mult_vec(y, 0.0, 1.0, x, r2i, i2c, iv, rv)
+        assert np.abs(y - rhs).max() < 1e-7
+        sizes.append(int(orc.symbolic_iluk(r2i, i2c, k)[1].size))
+        iters.append(len(hist))
+    assert sizes == sorted(sizes) and sizes[0] == i2c.size and sizes[-1] > 3 * sizes[0]
+    assert iters == sorted(iters, reverse=True) and iters[-1] == 2, iters
+    # ILU(0) through the k = 0 path is the ILU(0) preconditioner bit for bit
+    a, b = orc.Ilu("ilu0", 2, r2i, i2c), orc.Ilu(("iluk", 0), 2, r2i, i2c)
+    for s in (a, b):
+        s.copy_value(r2i, i2c, iv, rv)
+        s.decompose()
+    v1, v2 = rhs.copy(), rhs.copy()
+    a.solve(v1)
+    b.solve(v2)
+    assert np.array_equal(v1, v2)
