@@ -120,6 +120,7 @@ def lib():
         "dfb_bsr_download": [_vp, _vp, _vp],
         "dfb_bsr_set_fixed_dof": [_vp, _f64, _vp],
         "dfb_bsr_mult_vec": [_vp, _vp, _f64, _f64, _vp],
+        "dfb_bsr_mult_mat": [_vp, _vp, _f64, _f64, _vp],
         "dfb_bsr_add_to_diagonal": [_vp, _f64, _vp],
         "dfb_bsr_add_scaled": [_vp, _f64, _vp],
         "dfb_bsr_merge_one": [_vp, _vp, _vp, _i32, _i32],

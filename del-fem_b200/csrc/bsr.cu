@@ -1175,6 +1175,41 @@ DFB_API dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, d
   return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, -1, 0);
 }
 
+// del-fem-ls mult_mat (del-fem-ls/src/sparse_square.rs:134-164): a SCALAR matrix applied to num_dim interleaved components,
+// y[i][d] <- beta y[i][d] + sum_j (alpha a_ij) x[j][d] + (alpha d_i) x[i][d], terms in the reference's order (off-diagonals in
+// storage order, diagonal last). One thread per (row, component); off the hot path (ARAP-style uses), kept simple.
+__global__ void k_mult_mat_scalar(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col, const double *__restrict__ idx2val,
+                                  const double *__restrict__ row2val, uint64_t num_rows, int nd, double beta, double alpha,
+                                  const double *__restrict__ x, double *__restrict__ y) {
+  const uint64_t total = num_rows * (uint64_t)nd;
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = q / nd;
+    const int d = (int)(q - i * nd);
+    double acc = y[q] * beta;
+    for (uint32_t k = row2idx[i]; k < row2idx[i + 1]; ++k) acc += alpha * idx2val[k] * x[(uint64_t)idx2col[k] * nd + d];
+    if (row2val) acc += alpha * row2val[i] * x[q];
+    y[q] = acc;
+  }
+}
+
+DFB_API dfb_status dfb_bsr_mult_mat(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, const dfb_vec *x) {
+  DFB_REQUIRE(m && y && x, "dfb_bsr_mult_mat: NULL argument");
+  DFB_REQUIRE(m->blk_dim == 1, "dfb_bsr_mult_mat: the matrix must be scalar (blk_dim 1), got %d", m->blk_dim);
+  DFB_REQUIRE(y->n_blk == m->pat->num_blk && x->n_blk == m->pat->num_blk && x->blk_dim == y->blk_dim,
+              "dfb_bsr_mult_mat: assert_eq!(y_mat.len(), x_mat.len()) / num_dim * num_row");
+  DFB_REQUIRE(x->d != y->d, "dfb_bsr_mult_mat: x and y alias");
+  DFB_REQUIRE(!m->halo, "dfb_bsr_mult_mat: not available for distributed matrices");
+  dfb_ctx *c = m->ctx;
+  const uint64_t total = m->pat->num_blk * (uint64_t)x->blk_dim;
+  uint64_t g = (total + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+  DFB_LAUNCH(c, k_mult_mat_scalar, (unsigned)g, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val, m->pat->num_blk,
+             x->blk_dim, beta, alpha, x->d, y->d);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
 DFB_API dfb_status dfb_bsr_set_halo(dfb_bsr *m, dfb_halo *h, uint64_t int_begin, uint64_t int_end) {
   DFB_REQUIRE(m, "dfb_bsr_set_halo: NULL argument");
   DFB_REQUIRE(int_begin <= int_end && int_end <= m->pat->num_blk, "dfb_bsr_set_halo: bad interior range");

@@ -72,6 +72,10 @@ class Matrix:
         """Matrix::mult_vec: y <- alpha*A*x + beta*y (:143-171)"""
         check(lib().dfb_bsr_mult_vec(self.h, y_vec.h, float(beta), float(alpha), x_vec.h))
 
+    def mult_mat(self, y_mat: Vec, beta, alpha, x_mat: Vec):
+        """del-fem-ls mult_mat (del-fem-ls/src/sparse_square.rs:134-164): scalar matrix times num_dim interleaved components"""
+        check(lib().dfb_bsr_mult_mat(self.h, y_mat.h, float(beta), float(alpha), x_mat.h))
+
     def merge_for_array_blk(self, emat, node2vtx, col2idx=None, flavour=0):
         """Matrix::merge_for_array_blk (:180-214). `col2idx` is accepted for signature parity and ignored."""
         e = _c(emat, np.float64)

@@ -168,6 +168,9 @@ dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *blk2
 dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcflag *f);
 /* Matrix::mult_vec  y <- alpha*A*x + beta*y   :143-171 / MatrixRef::mult_vec :419-447 */
 dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, dfb_vec *x);
+/* del-fem-ls mult_mat  del-fem-ls/src/sparse_square.rs:134-164: scalar matrix (blk_dim 1) applied to the num_dim = x->blk_dim interleaved
+   components of x: y <- alpha*A*x + beta*y per component */
+dfb_status dfb_bsr_mult_mat(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, const dfb_vec *x);
 /* row2val[i][d + N d] += scale * v[i][d]  — inertia / damping on the diagonal (rod3_darboux.rs:1219-1226) */
 dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_vec *v);
 /* values(m) += alpha * values(other); both on the SAME pattern handle. Sums Hessians of different element families (the reference

@@ -557,3 +557,24 @@ def test_iluk_matches_oracle(dfb, ctx, orc, lev_fill):
     vd.upload(v)
     sparse_ilu.solve_preconditioning_vec(vd, pc)
     assert rel_err(vd.download(), 0.5 * want) < 1e-12
+
+
+@pytest.mark.parametrize("nd", [1, 3, 4])
+def test_ls_mult_mat_matches_oracle(dfb, ctx, orc, nd):
+    """del-fem-ls mult_mat (del-fem-ls/src/sparse_square.rs:134-164): scalar Laplacian applied to nd interleaved components"""
+    t2v, xy = orc.grid_tri_mesh(13, disk=True)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv, iv = orc.assemble("laplace_tri2", 0, t2v, xy, 1.3, 0.0, r2i, i2c)
+    rng = np.random.default_rng(4)
+    x, y0 = rng.standard_normal((nv, nd)), rng.standard_normal((nv, nd))
+    mat = dfb.Matrix.from_vtx2vtx(r2i, i2c, 1, ctx=ctx)
+    mat.upload(rv, iv)
+    for alpha, beta in [(1.0, 0.0), (2.0, 0.5), (-0.3, 1.0)]:
+        want = y0.copy()
+        orc.ls_mult_mat(want, beta, alpha, x, r2i, i2c, iv.reshape(-1), rv.reshape(-1))
+        yd = dfb.Vec.from_numpy(ctx, y0)
+        mat.mult_mat(yd, beta, alpha, dfb.Vec.from_numpy(ctx, x))
+        assert rel_err(yd.download(), want) < 1e-13
+    with pytest.raises(dfb.DfbError):
+        dfb.Matrix.from_vtx2vtx(r2i, i2c, 2, ctx=ctx).mult_mat(dfb.Vec(ctx, nv, 2), 0.0, 1.0, dfb.Vec(ctx, nv, 2))
