@@ -121,6 +121,10 @@ class Matrix {
   void mult_vec(DevVec<N> &y_vec, double beta, double alpha, DevVec<N> &x_vec) const {
     check(dfb_bsr_mult_vec(h_, y_vec.get(), beta, alpha, x_vec.get()));
   }
+  // values(self) += alpha * values(other): sums Hessians of element families assembled on the same pattern
+  void add_scaled(double alpha, const Matrix &other) { check(dfb_bsr_add_scaled(h_, alpha, other.h_)); }
+  // inertia / damping on the diagonal (rod3_darboux.rs:1219-1226)
+  void add_to_diagonal(double scale, const DevVec<N> &v) { check(dfb_bsr_add_to_diagonal(h_, scale, v.get())); }
   void download(std::vector<std::array<double, NN>> &row2val, std::vector<std::array<double, NN>> &idx2val) const {
     uint64_t nb, nnz;
     int32_t conv;
@@ -165,11 +169,21 @@ class Preconditioner {
  public:
   explicit Preconditioner(int kind = DFB_PRECOND_BLOCK_JACOBI) : kind_(kind) {}
   ~Preconditioner() { if (h_) dfb_precond_destroy(h_); }
-  void initialize(const Ctx &ctx, const sparse_square::Matrix<N> &a) { check(dfb_precond_create(ctx.get(), kind_, a.get(), &h_)); }
+  void initialize(const Ctx &ctx, const sparse_square::Matrix<N> &a) { reset(); check(dfb_precond_create(ctx.get(), kind_, a.get(), &h_)); }
+  // Preconditioner::initialize_ilu0 (:28-56) / initialize_iluk (:58-64): the reference's own preconditioners, level-scheduled
+  void initialize_ilu0(const Ctx &ctx, const sparse_square::Matrix<N> &a) { reset(); check(dfb_precond_create(ctx.get(), DFB_PRECOND_ILU0, a.get(), &h_)); }
+  void initialize_iluk(const Ctx &ctx, const sparse_square::Matrix<N> &a, std::size_t lev_fill) {
+    reset();
+    check(dfb_precond_create_iluk(ctx.get(), a.get(), lev_fill, &h_));
+  }
   dfb_precond *get() const { return h_; }
   const sparse_square::Matrix<N> *src = nullptr;
 
  private:
+  void reset() {
+    if (h_) dfb_precond_destroy(h_);
+    h_ = nullptr;
+  }
   int kind_;
   dfb_precond *h_ = nullptr;
 };

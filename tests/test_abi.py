@@ -116,3 +116,34 @@ def test_rust_sys_crate_is_in_sync_with_the_header():
     assert len(names) > 80
     for n in names:
         assert re.search(r"pub fn %s\(" % n, rs), n
+
+
+def test_cpp_mirror_compiles_against_the_header():
+    """del-fem_b200/cpp/delfem_b200.hpp is header-only over the C ABI: every template it offers must at least compile and
+    instantiate (g++ -fsyntax-only, no CUDA, no GPU); the end-to-end run is a GPU test (tests/cpp/test_solid_linear_tri2.cpp)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = r'''
+#include "delfem_b200.hpp"
+using namespace delfem_b200;
+template class sparse_square::Matrix<1>;
+template class sparse_square::Matrix<3>;
+template class sparse_ilu::Preconditioner<2>;
+template class sparse_ilu::Preconditioner<3>;
+void use(const Ctx &ctx, sparse_square::Matrix<3> &m, sparse_square::Matrix<3> &m2, DevVec<3> &v) {
+  sparse_ilu::Preconditioner<3> pc(DFB_PRECOND_JACOBI);
+  pc.initialize(ctx, m);
+  pc.initialize_ilu0(ctx, m);
+  pc.initialize_iluk(ctx, m, 2);
+  m.add_scaled(0.5, m2);
+  m.add_to_diagonal(2.0, v);
+  sparse_ilu::copy_value(pc, m);
+  sparse_ilu::decompose(pc);
+  sparse_ilu::solve_preconditioning_vec(v, pc);
+  auto h = sparse_square::preconditioned_conjugate_gradient(v, v, v, v, 1e-5, 10, m, pc);
+  auto g = sparse_square::conjugate_gradient(v, v, v, v, 1e-5, 10, m);
+  (void)h; (void)g;
+}
+'''
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(root, "include"), "-I",
+                        os.path.join(root, "del-fem_b200", "cpp"), "-x", "c++", "-"], input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]

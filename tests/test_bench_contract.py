@@ -1,0 +1,38 @@
+"""bench.py contract checks that need no GPU: the reference arm (`--impl reference`) prints exactly one JSON line with the keys
+the driver reads, on a tiny workload; under a multi-rank launch only rank 0 prints."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "12", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, env=env, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return [ln for ln in r.stdout.decode().splitlines() if ln.strip().startswith("{")]
+
+
+def test_reference_arm_json_line():
+    lines = _run()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "MDoF*iter/s" and d["higher_is_better"] is True
+    for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["value"] > 0 and d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["single_thread_value"] > 0 and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
