@@ -91,3 +91,177 @@ pub fn conjugate_gradient<const N: usize, const NN: usize>(r_vec: &mut DevVec<N>
     hist.truncate(n as usize);
     hist
 }
+
+/// `set_fix_dof_to_rhs_vector` (del-fem-cpu/src/sparse_square.rs:57-70)
+pub fn set_fix_dof_to_rhs_vector<const N: usize>(blk2rhs: &mut DevVec<N>, blk2isfix: &[[i32; N]]) {
+    assert_eq!(blk2isfix.len(), blk2rhs.len);
+    check(unsafe { sys::dfb_vec_set_fixed_dof_zero(blk2rhs.h, blk2isfix.as_ptr() as *const i32) });
+}
+
+impl<const N: usize> DevVec<N> {
+    /// zero vector of `num_blk` blocks (the reference's `vec![[0.; N]; num_blk]`)
+    pub fn zeros(ctx: &Ctx, num_blk: usize) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::dfb_vec_create(ctx.0, num_blk as u64, 0, N as i32, &mut h) });
+        check(unsafe { sys::dfb_vec_set_zero(h) });
+        DevVec { h, len: num_blk }
+    }
+}
+
+/// Element kinds of the batched assembly (`dfb_assemble`): each replaces one per-element function of the reference.
+#[derive(Clone, Copy)]
+pub enum ElemKind {
+    LaplaceTri2 = sys::DFB_ELEM_LAPLACE_TRI2 as isize,          // laplace_tri2::ddw_            laplace_tri2.rs:3
+    CotLaplaceTri3 = sys::DFB_ELEM_COT_LAPLACE_TRI3 as isize,   // tri3::emat_cotangent_laplacian laplace_tri3.rs:18
+    SolidLinearTri2 = sys::DFB_ELEM_SOLID_LINEAR_TRI2 as isize, // solid_linear_tri2::emat_tri2   solid_linear_tri2.rs:23
+    LaplaceTet = sys::DFB_ELEM_LAPLACE_TET as isize,
+    SolidLinearTet = sys::DFB_ELEM_SOLID_LINEAR_TET as isize,
+    MassTet = sys::DFB_ELEM_MASS_TET as isize,
+}
+
+/// A uniform mesh resident on the device: `elem2vtx` (flat, `NNODE` per element) and `vtx2xyz` (flat, `NDIM` per vertex).
+pub struct Mesh { h: *mut sys::dfb_mesh }
+impl Mesh {
+    pub fn new(ctx: &Ctx, elem2vtx: &[usize], num_node: usize, vtx2xyz: &[f64], num_dim: usize) -> Self {
+        assert_eq!(elem2vtx.len() % num_node, 0);
+        assert_eq!(vtx2xyz.len() % num_dim, 0);
+        let mut h = std::ptr::null_mut();
+        check(unsafe {
+            sys::dfb_mesh_create(ctx.0, elem2vtx.as_ptr(), (elem2vtx.len() / num_node) as u64, num_node as i32, vtx2xyz.as_ptr(),
+                                 (vtx2xyz.len() / num_dim) as u64, num_dim as i32, &mut h)
+        });
+        Mesh { h }
+    }
+}
+impl Drop for Mesh {
+    fn drop(&mut self) { unsafe { sys::dfb_mesh_destroy(self.h) }; }
+}
+
+/// The element -> nonzero map of (pattern, mesh), inverted once: what the reference recomputes per element with `col2idx`.
+pub struct Plan { h: *mut sys::dfb_plan }
+impl Plan {
+    pub fn new<const N: usize, const NN: usize>(ctx: &Ctx, mat: &Matrix<N, NN>, mesh: &Mesh) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::dfb_plan_create(ctx.0, mat.pat, mesh.h, 0, &mut h) });
+        Plan { h }
+    }
+}
+impl Drop for Plan {
+    fn drop(&mut self) { unsafe { sys::dfb_plan_destroy(self.h) }; }
+}
+
+impl<const N: usize, const NN: usize> Matrix<N, NN> {
+    /// The whole `for node2vtx in elem2vtx.chunks(NNODE) { emat = ...; merge_for_array_blk(..) }` loop
+    /// (solid_linear_tri2.rs:144-161) as one deterministic gather on the device. Overwrites the values (no `set_zero` needed).
+    pub fn assemble(&mut self, plan: &Plan, kind: ElemKind, mesh: &Mesh, p0: f64, p1: f64) {
+        check(unsafe { sys::dfb_assemble(plan.h, kind as i32, mesh.h, p0, p1, self.h) });
+    }
+    /// inertia / damping on the diagonal: `row2val[i][d + N d] += scale * v[i][d]` (rod3_darboux.rs:1219-1226)
+    pub fn add_to_diagonal(&mut self, scale: f64, v: &DevVec<N>) {
+        check(unsafe { sys::dfb_bsr_add_to_diagonal(self.h, scale, v.h) });
+    }
+}
+
+/// `sparse_ilu::Preconditioner<[f64; NN]>` (del-fem-cpu/src/sparse_ilu.rs) on the device.
+pub mod sparse_ilu {
+    use super::*;
+    pub struct Preconditioner<const N: usize, const NN: usize> {
+        pub(crate) h: *mut sys::dfb_precond,
+        src: *const sys::dfb_bsr,
+    }
+    impl<const N: usize, const NN: usize> Preconditioner<N, NN> {
+        pub fn new() -> Self { Preconditioner { h: std::ptr::null_mut(), src: std::ptr::null() } }
+        fn reset(&mut self) {
+            if !self.h.is_null() { unsafe { sys::dfb_precond_destroy(self.h) }; }
+            self.h = std::ptr::null_mut();
+        }
+        /// `initialize_ilu0` (:28-56)
+        pub fn initialize_ilu0(&mut self, ctx: &Ctx, a: &Matrix<N, NN>) {
+            self.reset();
+            check(unsafe { sys::dfb_precond_create(ctx.0, sys::DFB_PRECOND_ILU0, a.h, &mut self.h) });
+        }
+        /// `initialize_iluk` (:58-64)
+        pub fn initialize_iluk(&mut self, ctx: &Ctx, a: &Matrix<N, NN>, lev_fill: usize) {
+            self.reset();
+            check(unsafe { sys::dfb_precond_create_iluk(ctx.0, a.h, lev_fill as u64, &mut self.h) });
+        }
+        /// point Jacobi — the fast preconditioner on the GPU (no reference counterpart; the ILU code with an empty pattern
+        /// is block-Jacobi: `DFB_PRECOND_BLOCK_JACOBI`)
+        pub fn initialize_jacobi(&mut self, ctx: &Ctx, a: &Matrix<N, NN>) {
+            self.reset();
+            check(unsafe { sys::dfb_precond_create(ctx.0, sys::DFB_PRECOND_JACOBI, a.h, &mut self.h) });
+        }
+    }
+    impl<const N: usize, const NN: usize> Drop for Preconditioner<N, NN> {
+        fn drop(&mut self) { self.reset(); }
+    }
+    /// `copy_value` (:87-125) — recorded here, performed together with `decompose` on the device
+    pub fn copy_value<const N: usize, const NN: usize>(ilu: &mut Preconditioner<N, NN>, a: &Matrix<N, NN>) { ilu.src = a.h; }
+    /// `decompose` (:127-181); a singular pivot block panics like `try_inverse().unwrap()`
+    pub fn decompose<const N: usize, const NN: usize>(ilu: &mut Preconditioner<N, NN>) {
+        assert!(!ilu.src.is_null(), "decompose: call copy_value first");
+        check(unsafe { sys::dfb_precond_update(ilu.h, ilu.src) });
+    }
+    /// `solve_preconditioning_vec` (:183-219), in place
+    pub fn solve_preconditioning_vec<const N: usize, const NN: usize>(vec: &mut DevVec<N>, ilu: &Preconditioner<N, NN>) {
+        check(unsafe { sys::dfb_precond_apply(ilu.h, vec.h) });
+    }
+}
+
+/// `preconditioned_conjugate_gradient` (del-fem-cpu/src/sparse_square.rs:264-347, any N): history of absolute residual norms
+/// including k = 0, one trailing entry when `max_nitr` is exhausted.
+pub fn preconditioned_conjugate_gradient<const N: usize, const NN: usize>(
+    r_vec: &mut DevVec<N>, x_vec: &mut DevVec<N>, pr_vec: &mut DevVec<N>, p_vec: &mut DevVec<N>, conv_ratio_tol: f64, max_nitr: usize,
+    mat: &Matrix<N, NN>, ilu: &sparse_ilu::Preconditioner<N, NN>) -> Vec<f64> {
+    let mut hist = vec![0f64; max_nitr + 3];
+    let mut n: u64 = 0;
+    check(unsafe { sys::dfb_pcg(mat.h, ilu.h, r_vec.h, x_vec.h, pr_vec.h, p_vec.h, conv_ratio_tol, max_nitr as u64, f64::EPSILON,
+                                hist.as_mut_ptr(), hist.len() as u64, &mut n) });
+    hist.truncate(n as usize);
+    hist
+}
+
+/// `del_fem_ls::linearsystem::Solver` (del-fem-ls/src/linearsystem.rs:8-112) for block size N: same lifecycle
+/// (`initialize` -> `begin_merge` -> merges -> `end_merge` -> `solve_cg` / `solve_pcg`), same defaults (tol 1e-5, 100 iterations).
+pub struct Solver<const N: usize, const NN: usize> {
+    pub sparse: Matrix<N, NN>,
+    pub ilu: sparse_ilu::Preconditioner<N, NN>,
+    pub r_vec: DevVec<N>,
+    pub u_vec: DevVec<N>,
+    ap_vec: DevVec<N>,
+    p_vec: DevVec<N>,
+    pub conv: Vec<f64>,
+    pub conv_ratio_tol: f64,
+    pub max_num_iteration: usize,
+}
+impl<const N: usize, const NN: usize> Solver<N, NN> {
+    /// `Solver::new` + `initialize(colind, rowptr)` (:33-57)
+    pub fn initialize(ctx: &Ctx, colind: &[usize], rowptr: &[usize]) -> Self {
+        let sparse = Matrix::<N, NN>::from_vtx2vtx(ctx, colind, rowptr);
+        let nblk = sparse.num_blk;
+        let mut ilu = sparse_ilu::Preconditioner::new();
+        ilu.initialize_ilu0(ctx, &sparse);
+        Solver { sparse, ilu, r_vec: DevVec::zeros(ctx, nblk), u_vec: DevVec::zeros(ctx, nblk), ap_vec: DevVec::zeros(ctx, nblk),
+                 p_vec: DevVec::zeros(ctx, nblk), conv: Vec::new(), conv_ratio_tol: 1.0e-5, max_num_iteration: 100 }
+    }
+    /// `begin_merge` (:59-62)
+    pub fn begin_merge(&mut self) {
+        self.sparse.set_zero();
+        check(unsafe { sys::dfb_vec_set_zero(self.r_vec.h) });
+    }
+    /// `end_merge` (:64-68): copy_value + decompose
+    pub fn end_merge(&mut self) {
+        sparse_ilu::copy_value(&mut self.ilu, &self.sparse);
+        sparse_ilu::decompose(&mut self.ilu);
+    }
+    /// `solve_cg` (:70-82)
+    pub fn solve_cg(&mut self) {
+        self.conv = conjugate_gradient(&mut self.r_vec, &mut self.u_vec, &mut self.ap_vec, &mut self.p_vec, self.conv_ratio_tol,
+                                       self.max_num_iteration, &self.sparse);
+    }
+    /// `solve_pcg` (:84-96)
+    pub fn solve_pcg(&mut self) {
+        self.conv = preconditioned_conjugate_gradient(&mut self.r_vec, &mut self.u_vec, &mut self.ap_vec, &mut self.p_vec,
+                                                      self.conv_ratio_tol, self.max_num_iteration, &self.sparse, &self.ilu);
+    }
+}
