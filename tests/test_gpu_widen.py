@@ -578,3 +578,84 @@ def test_ls_mult_mat_matches_oracle(dfb, ctx, orc, nd):
         assert rel_err(yd.download(), want) < 1e-13
     with pytest.raises(dfb.DfbError):
         dfb.Matrix.from_vtx2vtx(r2i, i2c, 2, ctx=ctx).mult_mat(dfb.Vec(ctx, nv, 2), 0.0, 1.0, dfb.Vec(ctx, nv, 2))
+
+
+# ------------------------------------------------------------------------------------------------ configs 3 and 4 at full size
+def test_config4_full_size_neohookean_beam_newton(dfb, ctx, orc):
+    """BASELINE config 4 at full size (16 x 16 x 256 cells = 74 273 vertices, 393 216 tets, mu = 1, lambda = 10,
+    x-min face clamped, gravity ramp) through size-independent properties: every PCG converges, the Newton out-of-balance force
+    drops by >= 1e6 within each load step, the total potential decreases, the tangent is symmetric, clamped dofs stay put."""
+    from del_fem_b200 import elements as el
+    from del_fem_b200.newton import NeoHookeanTetNewton
+    nx, ny, nz, h = 257, 17, 17, 1.0 / 16.0
+    mesh = dfb.Mesh.kuhn(ctx, nx, ny, nz, h)
+    nv = mesh.num_vtx
+    assert nv == 74273 and mesh.num_elem == 393216
+    flag = np.zeros((nv, 3), dtype=np.int32)
+    flag[np.arange(nv) % nx == 0] = 1                       # vertex id = i + nx (j + ny k): the face i = 0
+    nt = NeoHookeanTetNewton(ctx, mesh, flag, 1.0, 10.0)
+    mass = dfb.Vec(ctx, nv, 3)
+    el.lumped_mass(nt.plan, mesh, 1.0, mass)                 # rho V / 4 per corner
+    m = mass.download()
+    assert abs(m[:, 0].sum() - 16.0) < 1e-9                  # beam volume 16 x 1 x 1
+    f = np.zeros((nv, 3))
+    f[:, 2] = -1.0e-5 * m[:, 0]                              # tip deflection of a few percent of the length at full load
+    nt.set_load(f)
+    pot = [0.0]
+    for s in (0.5, 1.0):
+        g0 = None
+        for _ in range(12):
+            w, gn, its = nt.step(s, pcg_tol=1e-9, pcg_max=50000)
+            assert its < 50000
+            g0 = gn if g0 is None else g0
+            if gn < 1e-6 * g0:
+                break
+        assert gn < 1e-6 * g0, (s, gn, g0)
+        u = nt.u.download()
+        w_now = el.assemble_neohookean_tet(nt.plan, mesh, nt.u, 1.0, 10.0, nt.mat, nt.g)
+        pot.append(w_now - s * float((f * u).sum()))
+    assert pot[2] < pot[1] < pot[0]                          # W - s f.u decreases along the ramp (u is a minimiser for each s)
+    assert np.abs(u[flag != 0]).max() == 0.0
+    assert u[:, 2].min() < -0.01 and np.isfinite(u).all()
+    # tangent symmetry at the deformed state: a.(H b) == b.(H a)
+    a, b, ya, yb = (dfb.Vec(ctx, nv, 3) for _ in range(4))
+    a.fill_splitmix(1, 0, -1, 1)
+    b.fill_splitmix(2, 0, -1, 1)
+    nt.mat.mult_vec(ya, 0.0, 1.0, a)
+    nt.mat.mult_vec(yb, 0.0, 1.0, b)
+    s1, s2 = b.dot(ya), a.dot(yb)
+    assert abs(s1 - s2) <= 1e-10 * max(abs(s1), abs(s2))
+
+
+def test_config3_full_size_mass_spring_cloth(dfb, ctx, orc):
+    """BASELINE config 3 at full size (2048 x 2048 grid = 4 194 304 vertices, spring3 edges k = 1, lumped mass / dt^2
+    on the diagonal with dt = 1e-2 and rho = 1, two corners pinned, gravity, 10 steps of reassembly + CG to 1e-5): every CG
+    converges, pinned corners stay, the cloth falls, the state stays finite and the step is run-to-run reproducible."""
+    from del_fem_b200.cloth import MassSpringCloth, edges_of_grid_cloth
+    n = 2048
+    edges = edges_of_grid_cloth(n, n)
+    assert edges.shape[0] == 2 * n * (n - 1) + (n - 1) ** 2
+    gx, gy = np.meshgrid(np.arange(n) / (n - 1), np.arange(n) / (n - 1))
+    rest = np.ascontiguousarray(np.stack([gx.ravel(), gy.ravel(), np.zeros(n * n)], 1))
+    nv = n * n
+    flag = np.zeros((nv, 3), dtype=np.int32)
+    flag[0] = 1
+    flag[n - 1] = 1
+    dt, mass = 1e-2, 1.0 / nv                                  # rho = 1 over the unit square, lumped
+    cloth = MassSpringCloth(ctx, edges, rest, flag, 1.0, mass, gravity=(0.0, 0.0, -9.8))
+    assert cloth.pat.nnz == 2 * edges.shape[0]
+    its = []
+    for step in range(10):
+        w, it = cloth.step(dt, 1e-5, 3000)
+        assert it < 3000 and np.isfinite(w) and w >= 0.0
+        its.append(it)
+    x = cloth.disp.download()
+    assert np.isfinite(x).all()
+    assert np.abs(x[0]).max() == 0.0 and np.abs(x[n - 1]).max() == 0.0
+    assert x[:, 2].min() < -1e-3 and x[:, 2].max() < 1e-6      # falls, nothing rises
+    assert np.abs(x).max() < 0.1                               # g t^2 / 2 = 0.049 after 0.1 s bounds the free fall
+    # reproducibility: the same 10 steps from the same state give the same bits (deterministic assembly and reductions)
+    cloth2 = MassSpringCloth(ctx, edges, rest, flag, 1.0, mass, gravity=(0.0, 0.0, -9.8), pattern=cloth.pat)
+    for step in range(10):
+        cloth2.step(dt, 1e-5, 3000)
+    assert np.array_equal(cloth2.disp.download(), x)
