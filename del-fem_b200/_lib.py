@@ -121,6 +121,7 @@ def lib():
         "dfb_bsr_set_fixed_dof": [_vp, _f64, _vp],
         "dfb_bsr_mult_vec": [_vp, _vp, _f64, _f64, _vp],
         "dfb_bsr_mult_mat": [_vp, _vp, _f64, _f64, _vp],
+        "dfb_bsr_mult_square_matrices": [_vp, _vp, _pp, _pp],
         "dfb_bsr_add_to_diagonal": [_vp, _f64, _vp],
         "dfb_bsr_add_scaled": [_vp, _f64, _vp],
         "dfb_bsr_merge_one": [_vp, _vp, _vp, _i32, _i32],

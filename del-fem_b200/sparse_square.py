@@ -72,6 +72,16 @@ class Matrix:
         """Matrix::mult_vec: y <- alpha*A*x + beta*y (:143-171)"""
         check(lib().dfb_bsr_mult_vec(self.h, y_vec.h, float(beta), float(alpha), x_vec.h))
 
+    def mult_square_matrices(self, other: "Matrix") -> "Matrix":
+        """del-fem-ls mult_square_matrices (sparse_matrix_multiplication.rs:109-188): self * other for scalar matrices of the
+        separate-diagonal convention; returns a new Matrix on a new Pattern (columns in the reference's discovery order)"""
+        hp, hm = C.c_void_p(), C.c_void_p()
+        check(lib().dfb_bsr_mult_square_matrices(self.h, other.h, C.byref(hp), C.byref(hm)))
+        out = Matrix.__new__(Matrix)
+        out.ctx, out.pattern, out.blk_dim = self.ctx, Pattern(self.ctx, _handle=hp), 1
+        out.num_blk, out.h, out.halo = out.pattern.num_blk, hm, None
+        return out
+
     def mult_mat(self, y_mat: Vec, beta, alpha, x_mat: Vec):
         """del-fem-ls mult_mat (del-fem-ls/src/sparse_square.rs:134-164): scalar matrix times num_dim interleaved components"""
         check(lib().dfb_bsr_mult_mat(self.h, y_mat.h, float(beta), float(alpha), x_mat.h))

@@ -168,6 +168,10 @@ dfb_status dfb_bsr_set_fixed_dof(dfb_bsr *m, double val_dia, const int32_t *blk2
 dfb_status dfb_bsr_set_fixed_dof_dev(dfb_bsr *m, double val_dia, const dfb_bcflag *f);
 /* Matrix::mult_vec  y <- alpha*A*x + beta*y   :143-171 / MatrixRef::mult_vec :419-447 */
 dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, dfb_vec *x);
+/* mult_square_matrices  del-fem-ls/src/sparse_matrix_multiplication.rs:109-188 (pattern: symbolic_multiplication :7-107, discovery order,
+   diagonal kept apart): C = M0 * M1 for scalar (blk_dim 1) matrices of the separate-diagonal convention. Creates the pattern and the
+   matrix of C; the caller destroys both (matrix first). */
+dfb_status dfb_bsr_mult_square_matrices(const dfb_bsr *m0, const dfb_bsr *m1, dfb_pattern **out_pattern, dfb_bsr **out);
 /* del-fem-ls mult_mat  del-fem-ls/src/sparse_square.rs:134-164: scalar matrix (blk_dim 1) applied to the num_dim = x->blk_dim interleaved
    components of x: y <- alpha*A*x + beta*y per component */
 dfb_status dfb_bsr_mult_mat(const dfb_bsr *m, dfb_vec *y, double beta, double alpha, const dfb_vec *x);

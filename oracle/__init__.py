@@ -43,6 +43,7 @@ def lib():
         _lib.orc_preconditioned_conjugate_gradient.restype = C.c_int64
         _lib.orc_pcg_jacobi3_mt.restype = C.c_int64
         _lib.orc_symbolic_iluk.restype = C.c_uint64
+        _lib.orc_mult_square_matrices.restype = C.c_uint64
         _lib.orc_ilu_new.restype = C.c_void_p
         _lib.orc_ilu_row2val.restype = C.POINTER(C.c_double)
         _lib.orc_version.restype = C.c_char_p
@@ -465,3 +466,18 @@ def pcg_jacobi3_mt(nthreads, r, x, pr, p, tol, max_it, row2idx, idx2col, idx2val
     nh = lib().orc_pcg_jacobi3_mt(C.c_int(nthreads), _p(r), _p(x), _p(pr), _p(p), C.c_double(tol), C.c_uint64(max_it), _p(row2idx),
                                   C.c_uint64(row2idx.size - 1), _p(idx2col), _p(idx2val), _p(row2val), C.c_double(eps_sq), _p(hist))
     return hist[:nh]
+
+
+def mult_square_matrices(r0, c0, v0, d0, r1, c1, v1, d1):
+    """del-fem-ls/src/sparse_matrix_multiplication.rs:109-188: C = M0 * M1 (scalar csrdia) -> (row2idx, idx2col, idx2val, row2val)"""
+    n = r0.size - 1
+    v0, d0, v1, d1 = (_f64(a).reshape(-1) for a in (v0, d0, v1, d1))
+    r = np.zeros(n + 1, dtype=U64)
+    nnz = int(lib().orc_mult_square_matrices(C.c_uint64(n), _p(r0), _p(c0), _p(v0), _p(d0), _p(r1), _p(c1), _p(v1), _p(d1), _p(r),
+                                             None, None, None))
+    c = np.zeros(nnz, dtype=U64)
+    iv = np.zeros(nnz)
+    rv = np.zeros(n)
+    lib().orc_mult_square_matrices(C.c_uint64(n), _p(r0), _p(c0), _p(v0), _p(d0), _p(r1), _p(c1), _p(v1), _p(d1), _p(r), _p(c), _p(iv),
+                                   _p(rv))
+    return r, c, iv, rv

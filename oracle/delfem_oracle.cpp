@@ -1551,4 +1551,84 @@ ORC_API int64_t orc_pcg_jacobi3_mt(int nthreads, double *r, double *x, double *p
   return nh_out.load();
 }
 
+// ---------------------------------------------------------------------------------------------
+// del-fem-ls sparse_matrix_multiplication.rs
+// symbolic_multiplication :7-107 — pattern of C = A * B in discovery order; *_is_square: the matrix has an (unlisted) diagonal,
+// c_is_square: the diagonal of C is kept out of the pattern.
+// ---------------------------------------------------------------------------------------------
+static void symbolic_multiplication(const usize *a_r2i, const usize *a_i2c, usize nrow_a, bool a_sq, const usize *b_r2i,
+                                    const usize *b_i2c, bool b_sq, usize b_ncol, bool c_sq, std::vector<usize> &c_r2i,
+                                    std::vector<usize> &c_i2c) {
+  c_r2i.assign(nrow_a + 1, 0);
+  std::vector<usize> flag(b_ncol, USIZE_MAX);
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      for (usize i = 0; i < nrow_a; ++i) c_r2i[i + 1] += c_r2i[i];
+      c_i2c.assign(c_r2i[nrow_a], 0);
+      std::fill(flag.begin(), flag.end(), USIZE_MAX);
+    }
+    // pass 1 advances c_r2i[i] while filling and shifts it back afterwards (:62-106)
+    for (usize i = 0; i < nrow_a; ++i) {
+      auto add = [&](usize j) {
+        if (flag[j] == i || (j == i && c_sq)) return;
+        if (pass == 0) {
+          c_r2i[i + 1] += 1;
+        } else {
+          c_i2c[c_r2i[i]] = j;
+          c_r2i[i] += 1;
+        }
+        flag[j] = i;
+      };
+      for (usize ka = a_r2i[i]; ka < a_r2i[i + 1]; ++ka) {
+        const usize k = a_i2c[ka];
+        for (usize kb = b_r2i[k]; kb < b_r2i[k + 1]; ++kb) add(b_i2c[kb]);
+        if (b_sq) add(k);
+      }
+      if (a_sq) {
+        for (usize kb = b_r2i[i]; kb < b_r2i[i + 1]; ++kb) add(b_i2c[kb]);
+        if (b_sq) add(i);
+      }
+    }
+  }
+  for (usize i = nrow_a; i-- > 1;) c_r2i[i] = c_r2i[i - 1];
+  c_r2i[0] = 0;
+}
+
+// mult_square_matrices :109-188 — C = M0 * M1 for scalar "CSR + separate diagonal" matrices. Two calls: c_idx2col == NULL
+// returns the number of off-diagonal entries (and fills c_row2idx), the second fills everything.
+ORC_API usize orc_mult_square_matrices(usize num_blk, const usize *r0, const usize *c0, const double *v0, const double *d0,
+                                       const usize *r1, const usize *c1, const double *v1, const double *d1, usize *c_row2idx,
+                                       usize *c_idx2col, double *c_idx2val, double *c_row2val) {
+  std::vector<usize> r2i, i2c;
+  symbolic_multiplication(r0, c0, num_blk, true, r1, c1, true, num_blk, true, r2i, i2c);
+  std::copy(r2i.begin(), r2i.end(), c_row2idx);
+  if (!c_idx2col) return i2c.size();
+  std::copy(i2c.begin(), i2c.end(), c_idx2col);
+  std::vector<double> iv(i2c.size(), 0.0), rv(num_blk, 0.0);
+  std::vector<usize> col2idx(num_blk, USIZE_MAX);
+  for (usize i = 0; i < num_blk; ++i) {
+    for (usize q = r2i[i]; q < r2i[i + 1]; ++q) col2idx[i2c[q]] = q;
+    for (usize k0 = r0[i]; k0 < r0[i + 1]; ++k0) {
+      const usize k = c0[k0];
+      for (usize k1 = r1[k]; k1 < r1[k + 1]; ++k1) {
+        const usize j = c1[k1];
+        if (i == j) rv[i] += v0[k0] * v1[k1];
+        else iv[col2idx[j]] += v0[k0] * v1[k1];
+      }
+      if (i == k) rv[i] += v0[k0] * d1[k];
+      else iv[col2idx[k]] += v0[k0] * d1[k];
+    }
+    for (usize k1 = r1[i]; k1 < r1[i + 1]; ++k1) {
+      const usize j = c1[k1];
+      if (i == j) rv[i] += d0[i] * v1[k1];
+      else iv[col2idx[j]] += d0[i] * v1[k1];
+    }
+    rv[i] += d0[i] * d1[i];
+    for (usize q = r2i[i]; q < r2i[i + 1]; ++q) col2idx[i2c[q]] = USIZE_MAX;
+  }
+  std::copy(iv.begin(), iv.end(), c_idx2val);
+  std::copy(rv.begin(), rv.end(), c_row2val);
+  return i2c.size();
+}
+
 ORC_API const char *orc_version(void) { return "delfem-oracle 0.1 (restates del-fem 0.1.9 hot path)"; }

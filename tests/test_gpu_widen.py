@@ -663,3 +663,32 @@ def test_config3_full_size_mass_spring_cloth(dfb, ctx, orc):
     for step in range(10):
         cloth2.step(dt, 1e-5, 3000)
     assert np.array_equal(cloth2.disp.download(), x)
+
+
+def test_ls_mult_square_matrices_matches_oracle(dfb, ctx, orc):
+    """del-fem-ls mult_square_matrices (sparse_matrix_multiplication.rs:109-188): pattern of the product in the reference's
+    discovery order and its values, bit for bit against the oracle; (A*A)x == A(Ax) closes the loop on the device"""
+    t2v, xy = orc.grid_tri_mesh(17, disk=True)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv0, iv0 = orc.assemble("laplace_tri2", 0, t2v, xy, 1.0, 0.0, r2i, i2c)
+    rng = np.random.default_rng(1)
+    rv1, iv1 = rng.standard_normal(rv0.shape), rng.standard_normal(iv0.shape)
+    a = dfb.Matrix.from_vtx2vtx(r2i, i2c, 1, ctx=ctx)
+    a.upload(rv0, iv0)
+    b = dfb.Matrix.from_vtx2vtx(r2i, i2c, 1, ctx=ctx)
+    b.upload(rv1, iv1)
+    cm = a.mult_square_matrices(b)
+    r_o, c_o, iv_o, rv_o = orc.mult_square_matrices(r2i, i2c, iv0, rv0, r2i, i2c, iv1, rv1)
+    r_d, c_d = cm.pattern.download()
+    rv_d, iv_d = cm.download()
+    assert np.array_equal(r_d, r_o) and np.array_equal(c_d, c_o)
+    assert np.array_equal(iv_d[:, 0], iv_o) and np.array_equal(rv_d[:, 0], rv_o)
+    x = rng.standard_normal((nv, 1))
+    xd, t, y1, y2 = dfb.Vec.from_numpy(ctx, x), dfb.Vec(ctx, nv, 1), dfb.Vec(ctx, nv, 1), dfb.Vec(ctx, nv, 1)
+    b.mult_vec(t, 0.0, 1.0, xd)
+    a.mult_vec(y1, 0.0, 1.0, t)
+    cm.mult_vec(y2, 0.0, 1.0, xd)
+    assert rel_err(y2.download(), y1.download()) < 1e-12
+    with pytest.raises(dfb.DfbError):
+        dfb.Matrix.from_vtx2vtx(r2i, i2c, 3, ctx=ctx).mult_square_matrices(b)

@@ -614,3 +614,29 @@ def test_symbolic_iluk_and_iluk_preconditioner(orc):
     a.solve(v1)
     b.solve(v2)
     assert np.array_equal(v1, v2)
+
+
+def test_mult_square_matrices(orc):
+    """del-fem-ls sparse_matrix_multiplication.rs:109-188: C = M0 * M1 of two scalar csrdia matrices equals the scipy product;
+    the pattern is the set of structurally reachable columns (diagonal kept apart), in discovery order"""
+    t2v, xy = orc.grid_tri_mesh(7, disk=True)
+    nv = xy.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v, 3, nv, False)
+    rv0, iv0 = orc.assemble("laplace_tri2", 0, t2v, xy, 1.0, 0.0, r2i, i2c)
+    rng = np.random.default_rng(1)
+    rv1, iv1 = rng.standard_normal(rv0.shape), rng.standard_normal(iv0.shape)  # M1: same pattern, non-symmetric values
+    A = csr_from_csrdia(r2i, i2c, rv0, iv0, 1)
+    B = csr_from_csrdia(r2i, i2c, rv1, iv1, 1)
+    r, c, iv, rv = orc.mult_square_matrices(r2i, i2c, iv0, rv0, r2i, i2c, iv1, rv1)
+    Cm = csr_from_csrdia(r, c, rv.reshape(-1, 1), iv.reshape(-1, 1), 1)
+    want = (A @ B).toarray()
+    assert np.abs(Cm.toarray() - want).max() < 1e-12 * np.abs(want).max()
+    S = ((abs(A) > 0).astype(int) @ (abs(B) > 0).astype(int)).toarray() > 0   # structural product (no cancellation)
+    for i in (0, 3, nv // 2, nv - 1):
+        cols = c[r[i]:r[i + 1]].astype(np.int64)
+        assert len(set(cols)) == cols.size and i not in cols
+        assert set(cols) == set(np.nonzero(S[i])[0]) - {i}
+        # discovery order: first the columns reached through A's first off-diagonal entry k (B's row k, then k itself), ...
+        k = int(i2c[r2i[i]])
+        first = [int(j) for j in i2c[r2i[k]:r2i[k + 1]] if int(j) != i] + [k]
+        assert list(cols[: len(first)]) == first
