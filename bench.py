@@ -36,6 +36,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class StdoutGuard:
+    """While active, anything written to file descriptor 1 goes to stderr (NCCL prints its version banner on stdout when the
+    first communicator is created); emit() writes one line to the real stdout, so the run prints exactly ONE line there."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def close(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """samples nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)"""
@@ -202,6 +221,7 @@ def cpu_baseline(nx, iters_for_extrapolation, budget_iters=20, elem_fraction=1.0
 
 
 def run_ours(args):
+    guard = StdoutGuard()
     import _bootstrap
     dfb = _bootstrap.load()
     from del_fem_b200 import synthetic
@@ -375,10 +395,11 @@ def run_ours(args):
                "elements_per_s_assembly": ne_l * world / (asm_total / args.steps * 1e-3),
                "spmv_gbs": achieved, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
                "cpu_baseline": cpu}
-        print(json.dumps(out), flush=True)
+        guard.emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    guard.close()
 
 
 def run_reference(args):

@@ -36,3 +36,21 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_print_nothing():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_stdout_guard_keeps_stdout_to_one_line():
+    """bench.py's StdoutGuard: noise written to fd 1 by native code (NCCL's version banner) must not reach stdout"""
+    code = (
+        "import os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "g = bench.StdoutGuard()\n"
+        "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n')\n"
+        "print('python noise')\n"
+        "g.emit('{\"ok\": 1}')\n"
+        "g.close()\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, cwd=ROOT, timeout=120)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stdout.decode() == '{"ok": 1}\n'
+    assert b"NCCL version" in r.stderr and b"python noise" in r.stderr
