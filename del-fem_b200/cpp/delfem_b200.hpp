@@ -79,6 +79,26 @@ template <int N> void add_scaled_vector(DevVec<N> &u, double alpha, const DevVec
 template <int N> void scale_and_add_vec(DevVec<N> &p, double beta, const DevVec<N> &r) { check(dfb_vec_scale_and_add(p.get(), beta, r.get())); }
 }  // namespace slice_of_array
 
+// A uniform mesh on the device (flat elem2vtx with NNODE vertices per element, flat coordinates with NDIM per vertex) and the
+// element -> nonzero map of (pattern, mesh): together they replace the reference's per-element loop
+// `for node2vtx in elem2vtx.chunks(NNODE) { emat = ...; merge_for_array_blk(&emat, node2vtx, &mut col2idx) }` (solid_linear_tri2.rs:144-161).
+class Mesh {
+ public:
+  Mesh(const Ctx &ctx, const std::vector<std::size_t> &elem2vtx, int num_node, const std::vector<double> &vtx2xyz, int num_dim) {
+    static_assert(sizeof(std::size_t) == sizeof(uint64_t), "usize must be 64-bit");
+    if (elem2vtx.size() % num_node != 0 || vtx2xyz.size() % num_dim != 0) throw Panic(DFB_ERR_BAD_ARG, "Mesh: array lengths");
+    check(dfb_mesh_create(ctx.get(), reinterpret_cast<const uint64_t *>(elem2vtx.data()), elem2vtx.size() / num_node, num_node,
+                          vtx2xyz.data(), vtx2xyz.size() / num_dim, num_dim, &h_));
+  }
+  ~Mesh() { dfb_mesh_destroy(h_); }
+  Mesh(const Mesh &) = delete;
+  Mesh &operator=(const Mesh &) = delete;
+  dfb_mesh *get() const { return h_; }
+
+ private:
+  dfb_mesh *h_ = nullptr;
+};
+
 namespace sparse_square {
 
 // sparse_square::Matrix<[f64; N*N]>  (sparse_square.rs:75-214)
@@ -99,9 +119,14 @@ class Matrix {
     check(dfb_bsr_create(ctx.get(), m.pat_, N, &m.h_));
     return m;
   }
-  Matrix(Matrix &&o) noexcept : num_blk(o.num_blk), pat_(o.pat_), h_(o.h_) { o.pat_ = nullptr; o.h_ = nullptr; }
+  Matrix(Matrix &&o) noexcept : num_blk(o.num_blk), pat_(o.pat_), h_(o.h_), plan_(o.plan_), plan_mesh_(o.plan_mesh_) {
+    o.pat_ = nullptr;
+    o.h_ = nullptr;
+    o.plan_ = nullptr;
+  }
   Matrix(const Matrix &) = delete;
   ~Matrix() {
+    if (plan_) dfb_plan_destroy(plan_);
     if (h_) dfb_bsr_destroy(h_);
     if (pat_) dfb_pattern_destroy(pat_);
   }
@@ -120,6 +145,17 @@ class Matrix {
   // mult_vec (:143-171): y <- alpha*A*x + beta*y
   void mult_vec(DevVec<N> &y_vec, double beta, double alpha, DevVec<N> &x_vec) const {
     check(dfb_bsr_mult_vec(h_, y_vec.get(), beta, alpha, x_vec.get()));
+  }
+  // the whole element loop as one deterministic gather (kind = DFB_ELEM_*, e.g. DFB_ELEM_SOLID_LINEAR_TRI2 with p0 = lambda, p1 = myu);
+  // the plan (element -> nonzero map) is built on first use for this mesh and kept
+  void assemble(const Ctx &ctx, const Mesh &mesh, int kind, double p0, double p1) {
+    if (!plan_ || plan_mesh_ != mesh.get()) {
+      if (plan_) dfb_plan_destroy(plan_);
+      plan_ = nullptr;
+      check(dfb_plan_create(ctx.get(), pat_, mesh.get(), 0, &plan_));
+      plan_mesh_ = mesh.get();
+    }
+    check(dfb_assemble(plan_, kind, mesh.get(), p0, p1, h_));
   }
   // values(self) += alpha * values(other): sums Hessians of element families assembled on the same pattern
   void add_scaled(double alpha, const Matrix &other) { check(dfb_bsr_add_scaled(h_, alpha, other.h_)); }
@@ -140,6 +176,8 @@ class Matrix {
   Matrix() = default;
   dfb_pattern *pat_ = nullptr;
   dfb_bsr *h_ = nullptr;
+  dfb_plan *plan_ = nullptr;
+  const dfb_mesh *plan_mesh_ = nullptr;
 };
 
 // set_fix_dof_to_rhs_vector (:57-70)

@@ -136,6 +136,8 @@ void use(const Ctx &ctx, sparse_square::Matrix<3> &m, sparse_square::Matrix<3> &
   pc.initialize_iluk(ctx, m, 2);
   m.add_scaled(0.5, m2);
   m.add_to_diagonal(2.0, v);
+  Mesh mesh(ctx, std::vector<std::size_t>{0, 1, 2, 3}, 4, std::vector<double>(12, 0.0), 3);
+  m.assemble(ctx, mesh, DFB_ELEM_SOLID_LINEAR_TET, 1.0, 1.0);
   sparse_ilu::copy_value(pc, m);
   sparse_ilu::decompose(pc);
   sparse_ilu::solve_preconditioning_vec(v, pc);
