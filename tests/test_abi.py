@@ -72,13 +72,18 @@ def test_sass_contains_tma_bulk_copies(dfb):
     """the SpMV streams the matrix with TMA bulk copies: SASS shows UBLKCP (B200_PROFILING.md), and the target is sm_100a"""
     out = subprocess.run(["cuobjdump", "-sass", dfb.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    # isolate the SASS of the shipped SpMV kernel (k_spmv_ring<3, 4, 2, ...>)
     funcs = out.split("Function : ")
-    ring = [f for f in funcs if f.startswith("_Z11k_spmv_ringILi3ELi4ELi2E")]
-    assert ring, "k_spmv_ring<3,4,2,...> not found in the library"
-    out = ring[0]
-    assert "UBLKCP" in out
-    assert "SYNCS" in out  # mbarrier
+    # the shipped default k_spmv_packed<3, false> (variant 20): exactly one bulk-copy site per tile buffer stage + the prologue,
+    # no halo logic (the separate <3, true> instantiation carries the flag loads), and the ring kernel of variant 4
+    for prefix in ("_Z13k_spmv_packedILi3ELb0EE", "_Z13k_spmv_packedILi3ELb1EE", "_Z11k_spmv_ringILi3ELi4ELi2E"):
+        k = [f for f in funcs if f.startswith(prefix)]
+        assert k, f"{prefix} not found in the library"
+        assert "UBLKCP" in k[0], prefix
+        assert "SYNCS" in k[0], prefix  # mbarrier
+    plain = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb0EE")][0]
+    halo = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb1EE")][0]
+    assert "LDG.E.64.STRONG.SYS" not in plain and "LDG.E.64.STRONG.SYS" in halo  # only the halo kernel polls peer flags
+    assert plain.count("DFMA") == halo.count("DFMA")          # same arithmetic in both
 
 
 def test_python_mirror_signatures_cover_header(dfb):
