@@ -42,6 +42,7 @@ def header_symbols():
 
 
 _lib = None
+_HANDLE_GETTERS = ("dfb_bsr_pattern", "dfb_solver_sparse", "dfb_solver_ilu", "dfb_solver_r_vec", "dfb_solver_u_vec", "dfb_solver_ap_vec", "dfb_solver_p_vec")
 
 _vp = C.c_void_p
 _u64 = C.c_uint64
@@ -66,6 +67,9 @@ def lib():
     for name in header_symbols():
         fn = getattr(L, name)
         if name in ("dfb_last_error_message", "dfb_version", "dfb_vec_device_ptr"):
+            continue
+        if name in _HANDLE_GETTERS:
+            fn.restype = C.c_void_p
             continue
         fn.restype = C.c_int32
     sig = {
@@ -156,6 +160,26 @@ def lib():
         "dfb_halo_exchange": [_vp, _vp],
         "dfb_halo_set_remote": [_vp, _vp],
         "dfb_bsr_set_halo": [_vp, _vp, _u64, _u64],
+        "dfb_bsr_pattern": [_vp],
+        "dfb_ctx_last_history_sq": [_vp, _vp, _u64, C.POINTER(_u64)],
+        "dfb_solver_new": [_vp, _i32, _pp],
+        "dfb_solver_initialize": [_vp, _vp, _u64, _vp, _u64],
+        "dfb_solver_set_preconditioner": [_vp, _i32, _u64],
+        "dfb_solver_begin_merge": [_vp],
+        "dfb_solver_end_merge": [_vp],
+        "dfb_solver_solve_cg": [_vp],
+        "dfb_solver_solve_pcg": [_vp],
+        "dfb_solver_clone": [_vp, _pp],
+        "dfb_solver_destroy": [_vp],
+        "dfb_solver_sparse": [_vp],
+        "dfb_solver_ilu": [_vp],
+        "dfb_solver_r_vec": [_vp],
+        "dfb_solver_u_vec": [_vp],
+        "dfb_solver_ap_vec": [_vp],
+        "dfb_solver_p_vec": [_vp],
+        "dfb_solver_set_params": [_vp, _f64, _u64],
+        "dfb_solver_get_params": [_vp, C.POINTER(_f64), C.POINTER(_u64)],
+        "dfb_solver_conv": [_vp, _vp, _u64, C.POINTER(_u64)],
     }
     for name, argtypes in sig.items():
         getattr(L, name).argtypes = argtypes

@@ -116,8 +116,12 @@ class Ctx:
 class Vec:
     """device `[[f64; N]]` (slice_of_array.rs)"""
 
-    def __init__(self, ctx: Ctx, n_blk: int, blk_dim: int, n_ghost: int = 0, data=None):
+    def __init__(self, ctx: Ctx, n_blk: int, blk_dim: int, n_ghost: int = 0, data=None, _borrow=None):
         self.ctx, self.n_blk, self.blk_dim, self.n_ghost = ctx, int(n_blk), int(blk_dim), int(n_ghost)
+        self._owned = _borrow is None
+        if _borrow is not None:  # a handle owned by another object (linearsystem.Solver's vectors)
+            self.h = C.c_void_p(_borrow)
+            return
         h = C.c_void_p()
         check(lib().dfb_vec_create(ctx.h, self.n_blk, self.n_ghost, self.blk_dim, C.byref(h)))
         self.h = h
@@ -177,9 +181,9 @@ class Vec:
         return lib().dfb_vec_device_ptr(self.h)
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owned", True):
             lib().dfb_vec_destroy(self.h)
-            self.h = None
+        self.h = None
 
 
 class BcFlag:
@@ -256,8 +260,9 @@ class Mesh:
 class Pattern:
     """row2idx / idx2col on the device. convention 0 = csrdia, 1 = blkcsr"""
 
-    def __init__(self, ctx: Ctx, row2idx=None, idx2col=None, convention=0, _handle=None):
+    def __init__(self, ctx: Ctx, row2idx=None, idx2col=None, convention=0, _handle=None, _owned=True):
         self.ctx = ctx
+        self._owned = _owned
         if _handle is not None:
             self.h = _handle
         else:
@@ -293,9 +298,9 @@ class Pattern:
         return r, c
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owned", True):
             lib().dfb_pattern_destroy(self.h)
-            self.h = None
+        self.h = None
 
 
 class Plan:

@@ -245,4 +245,51 @@ std::vector<double> preconditioned_conjugate_gradient(DevVec<N> &r_vec, DevVec<N
 }
 }  // namespace sparse_square
 
+namespace linearsystem {
+// del_fem_ls::linearsystem::Solver (del-fem-ls/src/linearsystem.rs:8-112) over dfb_solver_*: same lifecycle (initialize ->
+// begin_merge -> merges / BCs on sparse() and r_vec() -> end_merge -> solve_cg / solve_pcg), same defaults (1e-5f, 100, ILU(0)),
+// clone() resets max_num_iteration to 100 like :109. sparse() .. p_vec() are the reference's pub fields as BORROWED C handles.
+template <int N>
+class Solver {
+ public:
+  explicit Solver(const Ctx &ctx) { check(dfb_solver_new(ctx.get(), N, &h_)); }  // Solver::new :33
+  Solver(Solver &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  Solver(const Solver &) = delete;
+  ~Solver() { if (h_) dfb_solver_destroy(h_); }
+  // initialize(colind, rowptr) :48 — first array = row pointer, second = column indices (the reference's names are swapped)
+  void initialize(const std::vector<std::size_t> &colind, const std::vector<std::size_t> &rowptr) {
+    check(dfb_solver_initialize(h_, reinterpret_cast<const uint64_t *>(colind.data()), colind.size(),
+                                reinterpret_cast<const uint64_t *>(rowptr.data()), rowptr.size()));
+  }
+  void begin_merge() { check(dfb_solver_begin_merge(h_)); }  // :60
+  void end_merge() { check(dfb_solver_end_merge(h_)); }      // :67
+  void solve_cg() { check(dfb_solver_solve_cg(h_)); }        // :73
+  void solve_pcg() { check(dfb_solver_solve_pcg(h_)); }      // :85
+  Solver clone() const {                                      // :96
+    Solver t;
+    check(dfb_solver_clone(h_, &t.h_));
+    return t;
+  }
+  dfb_bsr *sparse() const { return dfb_solver_sparse(h_); }
+  dfb_precond *ilu() const { return dfb_solver_ilu(h_); }
+  dfb_vec *r_vec() const { return dfb_solver_r_vec(h_); }
+  dfb_vec *u_vec() const { return dfb_solver_u_vec(h_); }
+  std::vector<double> conv() const {
+    uint64_t n = 0;
+    check(dfb_solver_conv(h_, nullptr, 0, &n));
+    std::vector<double> out(n);
+    check(dfb_solver_conv(h_, out.data(), n, &n));
+    return out;
+  }
+  double conv_ratio_tol() const { double t; uint64_t m; check(dfb_solver_get_params(h_, &t, &m)); return t; }
+  std::size_t max_num_iteration() const { double t; uint64_t m; check(dfb_solver_get_params(h_, &t, &m)); return m; }
+  void set_params(double conv_ratio_tol, std::size_t max_num_iteration) { check(dfb_solver_set_params(h_, conv_ratio_tol, max_num_iteration)); }
+  dfb_solver *get() const { return h_; }
+
+ private:
+  Solver() = default;
+  dfb_solver *h_ = nullptr;
+};
+}  // namespace linearsystem
+
 }  // namespace delfem_b200

@@ -2,16 +2,12 @@
 // del-fem-ls/src/sparse_square.rs:6-164): storage, set_zero, BC (set_fixed_bc :3-55) and mult_vec (:419-447).
 //
 // SpMV design (HBM-bound: 76 B per off-diagonal 3x3 block, 0.24 flop/B — no tensor cores):
-//   variant 0  one thread per block-row, direct global loads (simple; baseline / fallback for huge rows)
-//   variant 1  one warp per tile of 32 consecutive block-rows: the tile's values, column indices and diagonal blocks
-//              are contiguous in memory, so the warp streams them into shared memory with 16-byte cp.async.cg
-//              (L2 evict-first: the matrix is read once per SpMV), then lane r computes row r out of shared memory
-//              while x is gathered from L2.
-//   variant 2  same tiling, but the staging is three TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) issued
-//              by one lane, completion tracked by a per-warp mbarrier: the copy engine streams the matrix, the SM's
-//              LSU only serves the x gather.
-// Persistent warps (grid = #SM x CTAs/SM) walk the tiles with a fixed stride, so the optional fused dot product
-// (p . Ap for CG) is reduced over a fixed grid in a fixed order: bit-reproducible.
+//   variant 0   one thread per block-row, direct global loads (simple; reference point and fallback)
+//   variant 4   4 lanes per row, 8-row tiles, two-stage TMA ring per warp over the canonical arrays (no extra memory)
+//   variant 20  [default] the same compute phase over a tile-packed mirror of the matrix: ONE TMA bulk copy per tile
+// Persistent warps (grid = #SM) walk the tiles with a fixed stride, so the optional fused dot product (p . Ap for CG) is
+// reduced over a fixed grid in a fixed order: bit-reproducible.  (The superseded experiments — warp-tile cp.async / TMA staging,
+// 2/8 lanes per row, 3-stage rings, row-pointer copies and prefetch — are recorded in profiles/README.md, not compiled.)
 #include "dfb_internal.h"
 #include "reduce.cuh"
 
@@ -58,6 +54,8 @@ DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
   delete m;
   return DFB_OK;
 }
+
+DFB_API dfb_pattern *dfb_bsr_pattern(const dfb_bsr *m) { return m ? m->pat : nullptr; }
 
 DFB_API dfb_status dfb_bsr_set_zero(dfb_bsr *m) {
   DFB_REQUIRE(m, "dfb_bsr_set_zero: NULL argument");
@@ -298,12 +296,11 @@ struct SpmvArgs {
   double alpha, beta;
   uint32_t row_begin, row_end;
   int fuse_dot;        // 0 none, 1 red[0] = sum x.y, 2 red[0] += sum x.y
-  int parity;          // solver-state parity slot (done flag)
-  DfbSolverState *st;  // nullptr outside the solvers
+  DfbSolverState *st;  // nullptr outside the solvers; inside, the launch reads iteration / stop flag / exchange ids from it
   double *partials;
   unsigned int *ticket;
-  DfbPeerView pv;      // pv.seq != 0 (and nranks > 1): the launch that completes p.Ap posts it to every peer's mailbox
-  DfbHaloWait hw;      // hw.xg != nullptr: ghost columns come from the peer landing zone (variant 20 inside the solvers)
+  DfbPeerView pv;      // pv.post (and nranks > 1): the launch that completes p.Ap posts it to every peer's mailbox
+  DfbHaloWait hw;      // hw.xg[0] != nullptr: ghost columns come from the peer landing zone (variant 20 inside the solvers)
 };
 
 template <int N>
@@ -319,6 +316,13 @@ __device__ __forceinline__ void load_x(double (&xv)[N], const double *__restrict
   const double *p = x + (uint64_t)col * N;
 #pragma unroll
   for (int a = 0; a < N; ++a) xv[a] = __ldg(p + a);
+}
+
+template <int N>
+__device__ __forceinline__ void load_x_coherent(double (&xv)[N], const double *x, uint32_t col) {
+  const double *p = x + (uint64_t)col * N;
+#pragma unroll
+  for (int a = 0; a < N; ++a) xv[a] = __ldcg(p + a);
 }
 
 // off-diagonal part of one row; vals/cols may point to shared or global memory
@@ -358,7 +362,7 @@ __device__ __forceinline__ void spmv_publish_dot(const SpmvArgs &a, double d, do
       else a.st->red[0] = acc[0];
       s_buf[0] = a.st->red[0];
     }
-    if (a.pv.nranks > 1 && a.pv.seq != 0) peer_post_block<1>(a.pv, s_buf);
+    if (a.pv.nranks > 1 && a.pv.post) peer_post_block<1>(a.pv, dfb_xid_pq(a.st->xbase, a.st->iter), s_buf);
   }
 }
 
@@ -366,7 +370,7 @@ __device__ __forceinline__ void spmv_publish_dot(const SpmvArgs &a, double d, do
 template <int N>
 __global__ void __launch_bounds__(128) k_spmv_row(const SpmvArgs a) {
   __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
+  if (a.st && a.st->done[a.st->iter & 1]) return;
   double dot = 0.0;
   for (uint64_t r = (uint64_t)a.row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.row_end;
        r += (uint64_t)gridDim.x * blockDim.x) {
@@ -379,23 +383,7 @@ __global__ void __launch_bounds__(128) k_spmv_row(const SpmvArgs a) {
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-// ---- variants 1/2: warp per 32-row tile, staged through shared memory
-template <int N> struct TileCfg;
-template <> struct TileCfg<1> { static constexpr int CAP = 1536; };
-template <> struct TileCfg<2> { static constexpr int CAP = 768; };
-template <> struct TileCfg<3> { static constexpr int CAP = 480; };
-template <> struct TileCfg<4> { static constexpr int CAP = 272; };
-
-template <int N>
-struct TileSmem {
-  static constexpr int NN = N * N;
-  static constexpr int VAL_BYTES = ((TileCfg<N>::CAP * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int DIA_BYTES = ((32 * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int COL_BYTES = ((TileCfg<N>::CAP * 4 + 16 + 15) / 16) * 16;
-  static constexpr int BAR_BYTES = 16;
-  static constexpr int WARP_BYTES = VAL_BYTES + DIA_BYTES + COL_BYTES + BAR_BYTES;
-};
-
+// ---- shared-memory / TMA helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ unsigned long long policy_evict_first() {
@@ -404,24 +392,10 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   return pol;
 }
 
-// warp-cooperative 16-byte cp.async of the 16-byte-aligned superset of [src, src+bytes); returns the byte offset of
-// `src` inside the staged region (0..15). The caller guarantees 16 bytes of slack on both sides of the source.
-__device__ __forceinline__ uint32_t stage_cp_async(uint32_t dst_smem, const void *src, uint32_t bytes, unsigned lane,
-                                                   unsigned long long pol) {
-  const uintptr_t s = (uintptr_t)src;
-  const uint32_t mis = (uint32_t)(s & 15);
-  const char *g = (const char *)(s - mis);
-  const uint32_t total = (mis + bytes + 15u) & ~15u;
-  for (uint32_t off = lane * 16u; off < total; off += 512u) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem + off), "l"(g + off), "l"(pol)
-                 : "memory");
-  }
-  return mis;
-}
-
-// one-lane TMA bulk copy of the aligned superset; same return value
-__device__ __forceinline__ uint32_t stage_bulk(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar_smem,
-                                               unsigned long long pol, uint32_t *tx_bytes) {
+// one-lane TMA bulk copy of the 16-byte-aligned superset of [src, src+bytes) (the caller guarantees 16 bytes of slack on both
+// sides of the source); the data starts (uintptr_t)src & 15 bytes into the staged region
+__device__ __forceinline__ void stage_bulk(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar_smem,
+                                           unsigned long long pol) {
   const uintptr_t s = (uintptr_t)src;
   const uint32_t mis = (uint32_t)(s & 15);
   const char *g = (const char *)(s - mis);
@@ -432,8 +406,6 @@ __device__ __forceinline__ uint32_t stage_bulk(uint32_t dst_smem, const void *sr
         "l"(g), "r"(total), "r"(bar_smem), "l"(pol)
         : "memory");
   }
-  *tx_bytes += total;
-  return mis;
 }
 
 __device__ __forceinline__ uint32_t aligned_total(const void *src, uint32_t bytes) {
@@ -441,125 +413,20 @@ __device__ __forceinline__ uint32_t aligned_total(const void *src, uint32_t byte
   return (mis + bytes + 15u) & ~15u;
 }
 
-template <int N, int VARIANT>
-__global__ void __launch_bounds__(160) k_spmv_tile(const SpmvArgs a) {
-  using S = TileSmem<N>;
-  constexpr int NN = N * N;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
-
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
-  unsigned char *s_val = wbase;
-  unsigned char *s_dia = wbase + S::VAL_BYTES;
-  unsigned char *s_col = wbase + S::VAL_BYTES + S::DIA_BYTES;
-  const uint32_t bar = smem_u32(wbase + S::VAL_BYTES + S::DIA_BYTES + S::COL_BYTES);
-  const unsigned long long pol = policy_evict_first();
-
-  uint32_t phase = 0;
-  if (VARIANT == 2) {
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-  }
-
-  const uint32_t n_rows = a.row_end - a.row_begin;
-  const uint32_t n_tiles = (n_rows + 31u) >> 5;
-  const uint32_t warp_global = blockIdx.x * nw + wid, warp_stride = gridDim.x * nw;
-  double dot = 0.0;
-
-  for (uint32_t t = warp_global; t < n_tiles; t += warp_stride) {
-    const uint32_t r0 = a.row_begin + (t << 5);
-    const uint32_t r1 = min(r0 + 32u, a.row_end);
-    const uint32_t r = r0 + lane;
-    // row pointers: lane L holds row2idx[r0+L]; lane 0 / last give the tile range
-    const uint32_t my_kb = (r <= r1) ? a.row2idx[r] : 0u;
-    const uint32_t k0 = __shfl_sync(0xffffffffu, my_kb, 0);
-    const uint32_t k1 = (r1 - r0 == 32u) ? a.row2idx[r1] : __shfl_sync(0xffffffffu, my_kb, (int)(r1 - r0));
-    const uint32_t my_ke = __shfl_down_sync(0xffffffffu, my_kb, 1);
-    const uint32_t ke = (lane == 31u) ? k1 : my_ke;
-    const uint32_t nb = k1 - k0;
-
-    double s[N];
-#pragma unroll
-    for (int q = 0; q < N; ++q) s[q] = 0.0;
-
-    if (nb <= (uint32_t)TileCfg<N>::CAP) {
-      const double *g_val = a.idx2val + (uint64_t)k0 * NN;
-      const uint32_t *g_col = a.idx2col + k0;
-      const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
-      const uint32_t val_bytes = nb * NN * 8u, col_bytes = nb * 4u, dia_bytes = (r1 - r0) * NN * 8u;
-      uint32_t mis_v, mis_c, mis_d = 0;
-      if (VARIANT == 1) {
-        mis_v = stage_cp_async(smem_u32(s_val), g_val, val_bytes, lane, pol);
-        mis_c = stage_cp_async(smem_u32(s_col), g_col, col_bytes, lane, pol);
-        if (g_dia) mis_d = stage_cp_async(smem_u32(s_dia), g_dia, dia_bytes, lane, pol);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-      } else {
-        mis_v = (uint32_t)((uintptr_t)g_val & 15);
-        mis_c = (uint32_t)((uintptr_t)g_col & 15);
-        mis_d = g_dia ? (uint32_t)((uintptr_t)g_dia & 15) : 0u;
-        if (lane == 0) {
-          uint32_t tx = aligned_total(g_val, val_bytes) + aligned_total(g_col, col_bytes) + (g_dia ? aligned_total(g_dia, dia_bytes) : 0u);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-          uint32_t dummy = 0;
-          stage_bulk(smem_u32(s_val), g_val, val_bytes, bar, pol, &dummy);
-          stage_bulk(smem_u32(s_col), g_col, col_bytes, bar, pol, &dummy);
-          if (g_dia) stage_bulk(smem_u32(s_dia), g_dia, dia_bytes, bar, pol, &dummy);
-        }
-        // all lanes wait for the transaction bytes to land
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "WAIT_LOOP:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra WAIT_DONE;\n"
-            "bra WAIT_LOOP;\n"
-            "WAIT_DONE:\n"
-            "}\n" ::"r"(bar),
-            "r"(phase)
-            : "memory");
-        phase ^= 1u;
-      }
-      if (r < r1) {
-        const double *sv = reinterpret_cast<const double *>(s_val + mis_v);
-        const uint32_t *sc = reinterpret_cast<const uint32_t *>(s_col + mis_c);
-        row_offdiag<N>(s, sv, sc, my_kb - k0, ke - k0, a.x);
-        const double *sd = g_dia ? reinterpret_cast<const double *>(s_dia + mis_d) + lane * NN : nullptr;
-        dot += row_finish<N>(a, r, s, sd);
-      }
-      __syncwarp();  // all lanes are done reading the staged tile before the next copy overwrites it
-    } else {
-      // oversized tile (very long rows): compute straight from global memory
-      if (r < r1) {
-        row_offdiag<N>(s, a.idx2val, a.idx2col, my_kb, ke, a.x);
-        dot += row_finish<N>(a, r, s, a.row2val ? a.row2val + (uint64_t)r * NN : nullptr);
-      }
-    }
-  }
-  if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
-}
-
-// ---- variants 3..8: LPR lanes per row, tiles of 32/LPR rows, NST-stage TMA ring per warp.
-// While a warp computes tile i out of one buffer, the bulk copies of tiles i+1..i+NST-1 are already in flight into the
-// others; the row's blocks are split over LPR lanes (one gather round instead of ~14 dependent ones) and summed with
-// shuffles. Row pointers never stall the warp: the tile's row2idx slice rides along as a fourth bulk copy, and the two
-// pointers that size a tile's copies are prefetched into registers NST+1 tiles ahead.
-template <int N, int LPR, int NST>
+// ---- variant 4: 4 lanes per row, tiles of 8 rows, two-stage TMA ring per warp over the CANONICAL arrays (no extra memory).
+// While a warp computes tile i out of one buffer, the bulk copies of tile i+1 are already in flight into the other; the row's
+// blocks are split over 4 lanes (one gather round instead of ~14 dependent ones) and summed with shuffles. Three bulk copies
+// per tile (values, column indices, diagonal blocks); the row pointers are plain loads issued before the barrier wait.
+template <int N>
 struct RingSmem {
   static constexpr int NN = N * N;
+  static constexpr int LPR = 4, NST = 2;
   static constexpr int RPT = 32 / LPR;   // rows per tile
   static constexpr int CAP = RPT * 16;   // blocks per tile held in shared memory (longer tiles take the direct path)
   static constexpr int VAL_BYTES = ((CAP * NN * 8 + 16 + 15) / 16) * 16;
   static constexpr int COL_BYTES = ((CAP * 4 + 16 + 15) / 16) * 16;
   static constexpr int DIA_BYTES = ((RPT * NN * 8 + 16 + 15) / 16) * 16;
-  static constexpr int ROWP_BYTES = (((RPT + 1) * 4 + 16 + 15) / 16) * 16;
-  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES + ROWP_BYTES;
+  static constexpr int BUF_BYTES = VAL_BYTES + COL_BYTES + DIA_BYTES;
   static constexpr int BAR_BYTES = ((NST * 8 + 15) / 16) * 16;
   static constexpr int WARP_BYTES = NST * BUF_BYTES + BAR_BYTES;
   static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
@@ -570,12 +437,11 @@ struct RingSmem {
 template <int N, int LPR, bool HALO = false>
 __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals, const uint32_t *cols, const double *dia,
                                            uint32_t kb, uint32_t ke, uint32_t r, bool valid, unsigned sub,
-                                           const double (&dcol)[N], double dxo) {
+                                           const double *xg = nullptr) {
   constexpr int NN = N * N;
   double s[N];
-  // contribution of a diagonal-block column that was fetched straight from global memory (zero otherwise)
 #pragma unroll
-  for (int q = 0; q < N; ++q) s[q] = dcol[q] * dxo;
+  for (int q = 0; q < N; ++q) s[q] = 0.0;
   // this lane's share of the row: blocks kb+sub, kb+sub+LPR, ... four at a time (index loads, then gathers, then FMAs)
   for (uint32_t k = kb + sub; k < ke; k += 4 * LPR) {
     uint32_t c[4];
@@ -587,7 +453,12 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (c[u] != 0xFFFFFFFFu) load_x<N>(xv[u], (HALO && c[u] >= a.hw.n_own) ? a.hw.xg : a.x, c[u]);
+      if (c[u] != 0xFFFFFFFFu) {
+        // ghost columns live in the landing zone the neighbours write WHILE this kernel runs: read them with L2-coherent loads
+        // (ld.global.cg), never through the non-coherent path; owned x is read-only for the kernel's lifetime (__ldg)
+        if (HALO && c[u] >= a.hw.n_own) load_x_coherent<N>(xv[u], xg, c[u]);
+        else load_x<N>(xv[u], a.x, c[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -620,13 +491,13 @@ __device__ __forceinline__ double ring_row(const SpmvArgs &a, const double *vals
   return d;
 }
 
-template <int N, int LPR, int NST, bool RPCOPY, bool PREFETCH, bool DIACOPY>
-__global__ void __launch_bounds__(RingSmem<N, LPR, NST>::WARPS * 32) k_spmv_ring(const SpmvArgs a) {
-  using S = RingSmem<N, LPR, NST>;
-  constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP;
+template <int N>
+__global__ void __launch_bounds__(RingSmem<N>::WARPS * 32) k_spmv_ring(const SpmvArgs a) {
+  using S = RingSmem<N>;
+  constexpr int NN = N * N, RPT = S::RPT, CAP = S::CAP, LPR = S::LPR, NST = S::NST;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
+  if (a.st && a.st->done[a.st->iter & 1]) return;
 
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned sub = lane % LPR, rl = lane / LPR;
@@ -644,78 +515,42 @@ __global__ void __launch_bounds__(RingSmem<N, LPR, NST>::WARPS * 32) k_spmv_ring
   const uint32_t n_tiles = (n_rows + RPT - 1) / RPT;
   const uint32_t wg = blockIdx.x * nw + wid, ws = gridDim.x * nw;
 
-  struct TilePtr {
-    uint32_t k0, k1;
-  };
-  // first / one-past-last nonzero of tile t (uniform loads, issued early so that nobody waits for them)
-  auto ptrs = [&](uint32_t t) -> TilePtr {
-    TilePtr p = {0u, 0u};
-    if (t < n_tiles) {
-      const uint32_t r0 = a.row_begin + t * RPT;
-      const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
-      p.k0 = __ldg(a.row2idx + r0);
-      p.k1 = __ldg(a.row2idx + r1);
-    }
-    return p;
-  };
-  // lane 0 issues the four bulk copies of tile t into buffer b (nothing for oversized tiles)
-  auto issue = [&](uint32_t t, uint32_t b, TilePtr p) {
+  // lane 0 issues the three bulk copies of tile t into buffer b (nothing for oversized tiles)
+  auto issue = [&](uint32_t t, uint32_t b) {
     if (lane != 0 || t >= n_tiles) return;
-    if (!PREFETCH) p = ptrs(t);
-    const uint32_t nb = p.k1 - p.k0;
-    if (nb > (uint32_t)CAP) return;
     const uint32_t r0 = a.row_begin + t * RPT;
     const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = __ldg(a.row2idx + r0), nb = __ldg(a.row2idx + r1) - k0;
+    if (nb > (uint32_t)CAP) return;
     unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
     const uint32_t bar = bar0 + 8 * b;
-    const double *g_val = a.idx2val + (uint64_t)p.k0 * NN;
-    const uint32_t *g_col = a.idx2col + p.k0;
-    const double *g_dia = (DIACOPY && a.row2val) ? a.row2val + (uint64_t)r0 * NN : nullptr;
-    const uint32_t *g_rp = a.row2idx + r0;
-    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u, rb = (r1 - r0 + 1u) * 4u;
-    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u) +
-                        (RPCOPY ? aligned_total(g_rp, rb) : 0u);
+    const double *g_val = a.idx2val + (uint64_t)k0 * NN;
+    const uint32_t *g_col = a.idx2col + k0;
+    const double *g_dia = a.row2val ? a.row2val + (uint64_t)r0 * NN : nullptr;
+    const uint32_t vb = nb * NN * 8u, cb = nb * 4u, db = (r1 - r0) * NN * 8u;
+    const uint32_t tx = aligned_total(g_val, vb) + aligned_total(g_col, cb) + (g_dia ? aligned_total(g_dia, db) : 0u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-    uint32_t dummy = 0;
-    stage_bulk(smem_u32(buf), g_val, vb, bar, pol, &dummy);
-    stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol, &dummy);
-    if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol, &dummy);
-    if (RPCOPY) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES + S::DIA_BYTES), g_rp, rb, bar, pol, &dummy);
+    stage_bulk(smem_u32(buf), g_val, vb, bar, pol);
+    stage_bulk(smem_u32(buf + S::VAL_BYTES), g_col, cb, bar, pol);
+    if (g_dia) stage_bulk(smem_u32(buf + S::VAL_BYTES + S::COL_BYTES), g_dia, db, bar, pol);
   };
 
-  TilePtr q[NST + 1];
 #pragma unroll
-  for (int j = 0; j <= NST; ++j) q[j] = PREFETCH ? ptrs(wg + j * ws) : TilePtr{0u, 0u};
-#pragma unroll
-  for (int j = 0; j < NST; ++j) issue(wg + j * ws, j, q[j]);
+  for (int j = 0; j < NST; ++j) issue(wg + j * ws, j);
   uint32_t phase_bits = 0u;
   double dot = 0.0;
   uint32_t b = 0;
   for (uint32_t t = wg; t < n_tiles; t += ws) {
-    // PREFETCH: pointers of tile t+NST+1 are requested now and consumed at the end of the NEXT iteration
-    const TilePtr qn = PREFETCH ? ptrs(t + (NST + 1) * ws) : TilePtr{0u, 0u};
-    const TilePtr cur = PREFETCH ? q[0] : ptrs(t);
-    const uint32_t k0 = cur.k0, k1 = cur.k1;
     const uint32_t r0 = a.row_begin + t * RPT;
     const uint32_t r1 = min(r0 + (uint32_t)RPT, a.row_end);
+    const uint32_t k0 = __ldg(a.row2idx + r0), k1 = __ldg(a.row2idx + r1);
     const uint32_t nb = k1 - k0;
     const uint32_t r = r0 + rl;
     const bool valid = r < r1;
-    // without DIACOPY the diagonal block comes straight from global memory: lane `sub` loads column `sub` of its row's block
-    // (and the matching x entry) BEFORE the barrier wait, so the latency overlaps the wait for the bulk copies
-    double dcol[N], dxo = 0.0;
-#pragma unroll
-    for (int qq = 0; qq < N; ++qq) dcol[qq] = 0.0;
-    if (!DIACOPY && a.row2val && valid && sub < (unsigned)N) {
-      const double *dp = a.row2val + (uint64_t)r * NN + (uint64_t)sub * N;
-#pragma unroll
-      for (int qq = 0; qq < N; ++qq) dcol[qq] = __ldg(dp + qq);
-      dxo = __ldg(a.x + (uint64_t)r * N + sub);
-    }
-    uint32_t gkb = k0, gke = k0;
-    if (!RPCOPY && valid) {  // requested before the barrier wait so that their latency overlaps it
-      gkb = a.row2idx[r];
-      gke = a.row2idx[r + 1];
+    uint32_t kb = k0, ke = k0;
+    if (valid) {  // requested before the barrier wait so that their latency overlaps it
+      kb = a.row2idx[r];
+      ke = a.row2idx[r + 1];
     }
     if (nb <= (uint32_t)CAP) {
       unsigned char *buf = wbase + (size_t)b * S::BUF_BYTES;
@@ -735,50 +570,38 @@ __global__ void __launch_bounds__(RingSmem<N, LPR, NST>::WARPS * 32) k_spmv_ring
       phase_bits ^= (1u << b);
       const double *g_val = a.idx2val + (uint64_t)k0 * NN;
       const uint32_t *g_col = a.idx2col + k0;
-      const uint32_t *g_rp = a.row2idx + r0;
       const double *sv = reinterpret_cast<const double *>(buf + ((uintptr_t)g_val & 15));
       const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + ((uintptr_t)g_col & 15));
-      const uint32_t *sr = reinterpret_cast<const uint32_t *>(buf + S::VAL_BYTES + S::COL_BYTES + S::DIA_BYTES + ((uintptr_t)g_rp & 15));
       const double *sd = nullptr;
-      if (DIACOPY && a.row2val) {
+      if (a.row2val) {
         const double *g_dia = a.row2val + (uint64_t)r0 * NN;
         sd = reinterpret_cast<const double *>(buf + S::VAL_BYTES + S::COL_BYTES + ((uintptr_t)g_dia & 15)) + rl * NN;
       }
-      const uint32_t kb = RPCOPY ? (valid ? sr[rl] : k0) : gkb;
-      const uint32_t ke = RPCOPY ? (valid ? sr[rl + 1] : k0) : gke;
-      dot += ring_row<N, LPR>(a, sv, sc, sd, kb - k0, ke - k0, r, valid, sub, dcol, dxo);
+      dot += ring_row<N, LPR>(a, sv, sc, sd, kb - k0, ke - k0, r, valid, sub);
     } else {
-      const uint32_t kb = valid ? a.row2idx[r] : k0;
-      const uint32_t ke = valid ? a.row2idx[r + 1] : k0;
-      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, (DIACOPY && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
-                              dcol, dxo);
+      dot += ring_row<N, LPR>(a, a.idx2val, a.idx2col, a.row2val ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub);
     }
     __syncwarp();  // every lane is done with buffer b
-    issue(t + NST * ws, b, q[NST]);
-#pragma unroll
-    for (int j = 0; j < NST; ++j) q[j] = q[j + 1];
-    q[NST] = qn;
+    issue(t + NST * ws, b);
     b = (b + 1 == NST) ? 0u : b + 1;
   }
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-template <int N, int LPR, int NST, bool RPCOPY, bool PREFETCH, bool DIACOPY>
+template <int N>
 static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
-  using S = RingSmem<N, LPR, NST>;
+  using S = RingSmem<N>;
   const int warps = S::WARPS;
   const size_t smem = (size_t)warps * S::WARP_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_ring<N, LPR, NST, RPCOPY, PREFETCH, DIACOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  // the dynamic shared-memory opt-in is a per-device function attribute: set it on every launch (cheap) instead of caching a
+  // process-global flag that a second context on another device would wrongly inherit
+  DFB_CUDA(cudaFuncSetAttribute(k_spmv_ring<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint64_t n_rows = a.row_end - a.row_begin;
   const uint64_t n_tiles = (n_rows + S::RPT - 1) / S::RPT;
   uint64_t g = (n_tiles + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  DFB_LAUNCH_ON(c, strm, (k_spmv_ring<N, LPR, NST, RPCOPY, PREFETCH, DIACOPY>), (unsigned)g, warps * 32, smem, a);
+  DFB_LAUNCH_ON(c, strm, (k_spmv_ring<N>), (unsigned)g, warps * 32, smem, a);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -847,8 +670,8 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__
 }
 
 // HALO = false is the single-domain kernel; HALO = true adds the peer-halo logic (ghost columns from the landing zone, interior
-// tiles first, bounded wait before the first boundary tile). The two are separate instantiations because the extra address
-// select and tile mapping in the hot loop cost the single-domain kernel 14 % when they were compiled in unconditionally.
+// tiles first, bounded wait before the first boundary tile; only inside the solvers: needs a.st). The two are separate
+// instantiations because the tile mapping in the hot loop cost the single-domain kernel when it was compiled in unconditionally.
 template <int N, bool HALO>
 __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const SpmvArgs a, const unsigned char *__restrict__ packed,
                                                                          const uint32_t *__restrict__ tile_off, int has_dia) {
@@ -856,7 +679,7 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   constexpr int NN = N * N, RPT = PK_RPT, LPR = PK_LPR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
-  if (a.st && a.st->done[a.parity]) return;
+  if (a.st && a.st->done[a.st->iter & 1]) return;
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned sub = lane % LPR, rl = lane / LPR;
   unsigned char *wbase = smem_raw + (size_t)wid * S::WARP_BYTES;
@@ -882,6 +705,9 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
     return k < n_int ? t_lo + k : t_begin + (k - n_int);
   };
   bool waited = !HALO;
+  // exchange id of the ghost values this launch multiplies, and the landing-zone parity buffer that holds them
+  const unsigned long long hseq = HALO ? dfb_hid(a.st->hbase, a.st->iter) : 0ull;
+  const double *xg = HALO ? a.hw.xg[hseq & 1ull] : nullptr;
 
   struct Off {
     uint32_t o0, o1;
@@ -912,18 +738,19 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   issue(t_begin + wg + ws, 1, q1);
   uint32_t phase0 = 0u, phase1 = 0u, b = 0u;
   double dot = 0.0;
-  double dzero[N];
-#pragma unroll
-  for (int qq = 0; qq < N; ++qq) dzero[qq] = 0.0;
   for (uint32_t v = t_begin + wg; v < t_end; v += ws) {
     const Off qn = offs(v + 3 * ws);  // requested now, used at the end of the next iteration
     const uint32_t t = tile_of(v);
-    if (HALO && !waited && (t < t_lo || t >= t_hi)) {
+    // boundary tiles (the only ones that read ghost columns) take their own copy of the row code, so that the interior tiles run
+    // exactly the single-domain instruction stream (the address select per gather measured 6-14 % when every tile paid for it)
+    const bool bnd = HALO && (t < t_lo || t >= t_hi);
+    if (HALO && bnd && !waited) {
       // first boundary tile of this warp: the ghost values must have landed (all neighbours, see peer.cuh)
       int ok = 1;
-      if (lane == 0) ok = halo_wait(a.hw) ? 1 : 0;
+      if (lane == 0) ok = halo_wait(a.hw, hseq) ? 1 : 0;
       ok = __shfl_sync(0xffffffffu, ok, 0);
-      if (!ok && lane == 0 && a.st) a.st->err = 2;
+      __syncwarp();  // memory ordering: lane 0's acquire covers the whole warp's ghost loads
+      if (!ok && lane == 0) a.st->err = 2;
       waited = true;
     }
     const uint32_t r = t * RPT + rl;
@@ -952,12 +779,15 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
       const uint32_t *sc = reinterpret_cast<const uint32_t *>(buf + PK_HDR);
       const double *sd0 = reinterpret_cast<const double *>(buf + PK_HDR + ((nb * 4u + 15u) & ~15u));
       const double *sv = sd0 + (has_dia ? RPT * NN : 0);
-      dot += ring_row<N, LPR, HALO>(a, sv, sc, has_dia ? sd0 + rl * NN : nullptr, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, dzero, 0.0);
+      const double *sd = has_dia ? sd0 + rl * NN : nullptr;
+      if (HALO && bnd) dot += ring_row<N, LPR, true>(a, sv, sc, sd, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub, xg);
+      else dot += ring_row<N, LPR, false>(a, sv, sc, sd, valid ? kb : 0u, valid ? ke : 0u, r, valid, sub);
     } else {
       // oversized tile: straight from the canonical arrays
       const uint32_t kb = valid ? a.row2idx[r] : 0u, ke = valid ? a.row2idx[r + 1] : 0u;
-      dot += ring_row<N, LPR, HALO>(a, a.idx2val, a.idx2col, (valid && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr, kb, ke, r, valid, sub,
-                              dzero, 0.0);
+      const double *gd = (valid && a.row2val) ? a.row2val + (uint64_t)r * NN : nullptr;
+      if (HALO && bnd) dot += ring_row<N, LPR, true>(a, a.idx2val, a.idx2col, gd, kb, ke, r, valid, sub, xg);
+      else dot += ring_row<N, LPR, false>(a, a.idx2val, a.idx2col, gd, kb, ke, r, valid, sub);
     }
     __syncwarp();
     issue(v + 2 * ws, b, q2);
@@ -1001,23 +831,15 @@ static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bs
   using S = PackedCfg<N>;
   const int warps = S::WARPS;
   const size_t smem = (size_t)warps * S::WARP_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   const uint64_t t_begin = a.row_begin / PK_RPT, t_end = ((uint64_t)a.row_end + PK_RPT - 1) / PK_RPT;
   uint64_t g = (t_end - t_begin + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
-  if (a.hw.xg != nullptr) {
-    static bool configured_h = false;
-    if (!configured_h) {
-      DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_h = true;
-    }
+  if (a.hw.xg[0] != nullptr) {
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
   } else {
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
   }
   DFB_CHECK_LAUNCH();
@@ -1026,49 +848,23 @@ static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bs
 
 template <int N>
 static dfb_status spmv_dispatch(dfb_ctx *c, const SpmvArgs &a, cudaStream_t strm) {
-  switch (c->spmv_variant) {
-    case 3: return spmv_launch_ring<N, 2, 2, false, false, true>(c, a, strm);
-    case 4: return spmv_launch_ring<N, 4, 2, false, false, true>(c, a, strm);
-    case 5: return spmv_launch_ring<N, 8, 2, false, false, true>(c, a, strm);
-    case 6: return spmv_launch_ring<N, 4, 3, false, false, true>(c, a, strm);
-    // (the row-pointer-prefetch / row-pointer-copy / diagonal-from-global / gather-pipelined / multi-lane-issue experiments
-    //  of profiles/README.md were all slower and have been removed from the build; the template flags remain for reference)
-    default: break;
-  }
+  if (c->spmv_variant == 4) return spmv_launch_ring<N>(c, a, strm);
+  if (c->spmv_variant != 0) return dfb_fail(DFB_ERR_BAD_ARG, "spmv_variant %lld: only 0 (row per thread), 4 (TMA ring) and 20 (packed) exist", (long long)c->spmv_variant);
   const uint64_t n_rows = a.row_end - a.row_begin;
   if (n_rows == 0 && !a.fuse_dot) return DFB_OK;
-  int variant = (int)c->spmv_variant;
-  if (variant == 0) {
-    uint64_t g = (n_rows + 127) / 128;
-    if (g < 1) g = 1;
-    const uint64_t cap = (uint64_t)c->sm_count * 16;
-    if (g > cap) g = cap;
-    if (g > DFB_RED_MAX_BLOCKS) g = DFB_RED_MAX_BLOCKS;
-    DFB_LAUNCH_ON(c, strm, k_spmv_row<N>, (unsigned)g, 128, 0, a);
-  } else {
-    const int warps = 5;
-    const size_t smem = (size_t)warps * TileSmem<N>::WARP_BYTES;
-    static bool configured[3][5] = {};
-    auto kern = (variant == 2) ? k_spmv_tile<N, 2> : k_spmv_tile<N, 1>;
-    if (!configured[variant][N]) {
-      DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[variant][N] = true;
-    }
-    uint64_t n_tiles = (n_rows + 31) / 32;
-    uint64_t g = (n_tiles + warps - 1) / warps;
-    if (g < 1) g = 1;
-    const uint64_t per_sm = c->spmv_ctas_per_sm > 0 ? (uint64_t)c->spmv_ctas_per_sm : 1;
-    if (g > (uint64_t)c->sm_count * per_sm) g = (uint64_t)c->sm_count * per_sm;
-    DFB_LAUNCH_ON(c, strm, kern, (unsigned)g, warps * 32, smem, a);
-  }
+  uint64_t g = (n_rows + 127) / 128;
+  if (g < 1) g = 1;
+  const uint64_t cap = (uint64_t)c->sm_count * 16;
+  if (g > cap) g = cap;
+  if (g > DFB_RED_MAX_BLOCKS) g = DFB_RED_MAX_BLOCKS;
+  DFB_LAUNCH_ON(c, strm, k_spmv_row<N>, (unsigned)g, 128, 0, a);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
 
 // internal launcher shared with the solvers
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq,
-                           const DfbHaloWait *hw) {
+                           uint64_t row_end, int fuse_dot, int in_solver, cudaStream_t strm, int post, const DfbHaloWait *hw) {
   dfb_ctx *c = m->ctx;
   SpmvArgs a;
   a.row2idx = m->pat->d_row2idx;
@@ -1082,19 +878,17 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   a.row_begin = (uint32_t)row_begin;
   a.row_end = (uint32_t)row_end;
   a.fuse_dot = fuse_dot;
-  a.parity = state_parity < 0 ? 0 : state_parity;
-  a.st = state_parity < 0 ? nullptr : c->d_state;  // solvers pass their parity slot; standalone mult_vec passes -1
-  if (fuse_dot && !a.st) return dfb_fail(DFB_ERR_BAD_ARG, "spmv: fused dot needs the solver state");
+  a.st = in_solver ? c->d_state : nullptr;  // standalone mult_vec: no solver state
+  if ((fuse_dot || hw) && !a.st) return dfb_fail(DFB_ERR_BAD_ARG, "spmv: fused dot / peer halo need the solver state");
   a.partials = c->d_partials;
   a.ticket = c->d_ticket + 1;
-  a.pv = dfb_peer_view(c, post_seq);
+  a.pv = dfb_peer_view(c, post);
   if (hw) {
     a.hw = *hw;
   } else {
-    a.hw.xg = nullptr;
+    a.hw.xg[0] = a.hw.xg[1] = nullptr;
     a.hw.n_own = 0xFFFFFFFFu;
     a.hw.wait_mask = 0;
-    a.hw.seq = 0;
     a.hw.halo_flag = nullptr;
     a.hw.tile_lo_end = 0;
     a.hw.tile_hi_begin = 0xFFFFFFFFu;
@@ -1118,29 +912,36 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   return dfb_fail(DFB_ERR_UNSUPPORTED, "spmv: blk_dim %d", m->blk_dim);
 }
 
-// y <- alpha*A*x + beta*y  with halo exchange of x (overlapped with the interior rows) when a halo is attached
-dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity,
-                         unsigned long long post_seq) {
+// the packed mirror must exist before a chunk of iterations is captured into a CUDA graph (the pack allocates on first use)
+dfb_status dfb_bsr_ensure_packed(const dfb_bsr *m) {
+  dfb_bsr *mm = const_cast<dfb_bsr *>(m);
+  if (m->ctx->spmv_variant == 20 && !mm->packed_valid) DFB_TRY(bsr_pack(mm, m->ctx->stream));
+  return DFB_OK;
+}
+
+static uint64_t halo_recv_total(const dfb_bsr *m) { return (m->halo && !m->halo->recv_ptr.empty()) ? m->halo->recv_ptr.back() : 0; }
+
+// true when (P)CG exchanges the ghosts of its direction vector by the NVLink peer push (one SpMV launch over all rows, boundary
+// tiles wait for the neighbours' flags) instead of ncclSend/ncclRecv on the second stream
+bool dfb_spmv_uses_peer_halo(const dfb_bsr *m) {
+  const dfb_ctx *c = m->ctx;
+  return m->halo && c->nranks > 1 && c->spmv_variant == 20 && c->peer_enabled && c->use_peer_allreduce &&
+         dfb_halo_peer_usable(m->halo, m->blk_dim);
+}
+
+// y <- alpha*A*x + beta*y  with halo exchange of x when a halo is attached.
+//   in_solver + peer halo: the producer of x has already pushed its boundary entries (dfb_halo_push); ONE launch over all rows
+//   otherwise: pack + ncclSend/ncclRecv on the comm stream, overlapped with the interior rows; boundary rows follow the event
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int in_solver, int post) {
   dfb_ctx *c = m->ctx;
   const uint64_t n = m->pat->num_blk;
-  if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq);
-  if (post_seq != 0 && c->spmv_variant == 20 && dfb_halo_peer_usable(m->halo, m->blk_dim)) {
-    // peer push (inside the solvers, where the scalar all-reduces order consecutive exchanges): one pack-and-push launch, then
-    // ONE SpMV launch over all rows whose boundary tiles wait for the neighbours' flags
-    // This rank's SpMV does not depend on its OWN push (it reads what the neighbours pushed), so the push runs on the comm
-    // stream beside the SpMV; the main stream only rejoins it before anything may overwrite x again.
+  if (!m->halo || c->nranks <= 1) return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, in_solver, c->stream, post);
+  if (in_solver && dfb_spmv_uses_peer_halo(m)) {
     DfbHaloWait hw;
-    DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
-    DFB_CUDA(cudaStreamWaitEvent(c->stream_comm, c->ev_a, 0));
-    DFB_TRY(dfb_halo_push(m->halo, x, m->blk_dim, parity, c->stream_comm, &hw));
-    DFB_CUDA(cudaEventRecord(c->ev_b, c->stream_comm));
-    hw.n_own = (uint32_t)n;
-    hw.xg = hw.xg - n * (uint64_t)m->blk_dim;
+    dfb_halo_wait_view(m->halo, m->blk_dim, n, &hw);
     hw.tile_lo_end = (uint32_t)((m->int_begin + PK_RPT - 1) / PK_RPT);
     hw.tile_hi_begin = (uint32_t)(m->int_end / PK_RPT);
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, parity, c->stream, post_seq, &hw));
-    DFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-    return DFB_OK;
+    return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, in_solver, c->stream, post, &hw);
   }
   // comm stream: wait until x is final, exchange ghosts
   DFB_CUDA(cudaEventRecord(c->ev_a, c->stream));
@@ -1151,19 +952,19 @@ dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha,
   const bool has_lo = m->int_begin > 0, has_hi = m->int_end < n, has_int = m->int_end > m->int_begin;
   int mode = fuse_dot;
   if (has_int) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_begin, m->int_end, mode, parity, c->stream, (!has_lo && !has_hi) ? post_seq : 0));
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_begin, m->int_end, mode, in_solver, c->stream, (!has_lo && !has_hi) ? post : 0));
     if (mode == 1) mode = 2;
   }
   DFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
   if (has_lo) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, m->int_begin, mode, parity, c->stream, !has_hi ? post_seq : 0));
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, m->int_begin, mode, in_solver, c->stream, !has_hi ? post : 0));
     if (mode == 1) mode = 2;
   }
   if (has_hi) {
-    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_end, n, mode, parity, c->stream, post_seq));
+    DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, m->int_end, n, mode, in_solver, c->stream, post));
     if (mode == 1) mode = 2;
   }
-  if (!has_int && !has_lo && !has_hi && fuse_dot) DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, 0, fuse_dot, parity, c->stream, post_seq));
+  if (!has_int && !has_lo && !has_hi && fuse_dot) DFB_TRY(dfb_spmv_launch(m, y, beta, alpha, x, 0, 0, fuse_dot, in_solver, c->stream, post));
   return DFB_OK;
 }
 
@@ -1172,7 +973,10 @@ DFB_API dfb_status dfb_bsr_mult_vec(const dfb_bsr *m, dfb_vec *y, double beta, d
   DFB_REQUIRE(y->n_blk == m->pat->num_blk && x->n_blk == m->pat->num_blk, "dfb_bsr_mult_vec: y/x length != num_blk (assert_eq!(y_vec.len(), self.num_blk))");
   DFB_REQUIRE(y->blk_dim == m->blk_dim && x->blk_dim == m->blk_dim, "dfb_bsr_mult_vec: vector block dim != matrix block dim");
   DFB_REQUIRE(x->d != y->d, "dfb_bsr_mult_vec: x and y alias");
-  return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, -1, 0);
+  if (m->halo && m->ctx->nranks > 1)
+    DFB_REQUIRE(x->n_ghost >= halo_recv_total(m), "dfb_bsr_mult_vec: the matrix has a halo of %llu ghost blocks but x was created with n_ghost = %llu",
+                (unsigned long long)halo_recv_total(m), (unsigned long long)x->n_ghost);
+  return dfb_spmv_full(m, y->d, beta, alpha, x->d, 0, 0, 0);
 }
 
 // del-fem-ls mult_mat (del-fem-ls/src/sparse_square.rs:134-164): a SCALAR matrix applied to num_dim interleaved components,
@@ -1210,9 +1014,30 @@ DFB_API dfb_status dfb_bsr_mult_mat(const dfb_bsr *m, dfb_vec *y, double beta, d
   return DFB_OK;
 }
 
+__global__ void k_max_u32(const uint32_t *__restrict__ a, uint64_t n, unsigned int *out) {
+  unsigned int m = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, a[i]);
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 DFB_API dfb_status dfb_bsr_set_halo(dfb_bsr *m, dfb_halo *h, uint64_t int_begin, uint64_t int_end) {
   DFB_REQUIRE(m, "dfb_bsr_set_halo: NULL argument");
   DFB_REQUIRE(int_begin <= int_end && int_end <= m->pat->num_blk, "dfb_bsr_set_halo: bad interior range");
+  if (h && m->pat->nnz > 0) {
+    // every column the local rows reference must be an owned row or one of the ghosts the halo receives
+    dfb_ctx *c = m->ctx;
+    unsigned int *d_max = (unsigned int *)(c->d_scratch + 16);
+    DFB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), c->stream));
+    DFB_LAUNCH(c, k_max_u32, c->sm_count * 4, 256, 0, m->pat->d_idx2col, m->pat->nnz, d_max);
+    DFB_CHECK_LAUNCH();
+    unsigned int h_max = 0;
+    DFB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    DFB_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t n_all = m->pat->num_blk + (h->recv_ptr.empty() ? 0 : h->recv_ptr.back());
+    DFB_REQUIRE((uint64_t)h_max < n_all, "dfb_bsr_set_halo: the pattern references column %u but the matrix has only %llu owned rows + %llu ghosts",
+                h_max, (unsigned long long)m->pat->num_blk, (unsigned long long)(n_all - m->pat->num_blk));
+  }
   m->halo = h;
   m->int_begin = int_begin;
   m->int_end = int_end;

@@ -5,6 +5,9 @@
 
 #include "dfb_internal.h"
 
+void dfb_comm_teardown(dfb_ctx *ctx);      // dist.cu
+void dfb_graph_cache_destroy(dfb_ctx *ctx);  // solver.cu
+
 static thread_local char g_err[1024] = "";
 
 void dfb_set_error(const char *fmt, ...) {
@@ -56,8 +59,12 @@ dfb_status dfb_dev_alloc(void **p, size_t bytes) {
   return DFB_OK;
 }
 
+static uint64_t g_free_epoch = 0;
+uint64_t dfb_free_epoch() { return g_free_epoch; }
+
 void dfb_dev_free(void *p) {
   if (!p) return;
+  g_free_epoch += 1;
   cudaStream_t s;
   if (alloc_stream(&s) != DFB_OK) return;
   cudaDeviceSynchronize();  // like cudaFree: nobody is still using the buffer
@@ -108,6 +115,9 @@ DFB_API dfb_status dfb_ctx_destroy(dfb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream_comm);
+  dfb_graph_cache_destroy(c);
+  dfb_comm_teardown(c);
+  if (c->h_poll) cudaFreeHost(c->h_poll);
   dfb_dev_free(c->d_partials);
   dfb_dev_free(c->d_ticket);
   dfb_dev_free(c->d_state);

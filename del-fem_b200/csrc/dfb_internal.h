@@ -48,8 +48,11 @@ dfb_status dfb_fail(dfb_status st, const char *fmt, ...);
 static const int DFB_RED_MAX_BLOCKS = 2048;  // upper bound of any reducing grid
 static const int DFB_RED_K = 4;              // max scalars reduced by one kernel
 
-// device-side solver scalars (lives in ctx->d_state). Two-slot fields are indexed by iteration parity so
-// that the slot a kernel reads is never the slot a thread of the same kernel writes.
+// device-side solver state (lives in ctx->d_state).  The iteration kernels take NO per-iteration host arguments: the iteration
+// index, its parity and the exchange ids of the peer all-reduces / halo pushes are derived from this struct on the device, so
+// that a chunk of iterations is a CUDA graph of identical nodes that can be replayed.  Two-slot fields are indexed by iteration
+// parity so that the slot a kernel reads is never the slot a thread of the same kernel writes; for the same reason `iter` is
+// written by the direction kernel only and `iter_dir` (what the direction kernel reads) by the update kernel only.
 struct DfbSolverState {
   double rho[2];      // r.z (PCG) / r.r (CG)
   double red[4];      // [0] p.Ap   [1] r.r   [2] r.z   (targets of the block reductions / all-reduce)
@@ -57,12 +60,22 @@ struct DfbSolverState {
   double rr0;
   double tol;
   double eps_sq;
-  int done[2];        // convergence flag (parity slots)
+  unsigned long long xbase, hbase;          // exchange-id bases of the running solve (scalar mailboxes / halo flags)
+  unsigned long long xseq_next, hseq_next;  // first unused ids; persist across solves (identical on every rank: SPMD)
+  unsigned long long gflag[2];              // local "total is in red[]" flags of the folded all-reduce: [0] p.Ap, [1] r.r/r.z
+  int done[2];        // stop flag (parity slots): converged, max_it reached, or error
   int iter;           // completed iterations
-  int err;            // 1: p.Ap < 0 (ls flavour assert)
+  int iter_dir;
+  int err;            // 1: p.Ap < 0 (ls flavour assert)   2: peer exchange timed out
   int check_pap;
-  int pad;
+  int converged;      // the stop was the convergence test (not max_it)
+  int max_it;
 };
+// exchange ids: init posts xbase+1; iteration i posts p.Ap as xbase+2+2i and {r.r, r.z} as xbase+3+2i; the halo of the direction
+// that iteration i multiplies is push hbase+1+i (landing-zone parity buffer = id & 1)
+__host__ __device__ inline unsigned long long dfb_xid_pq(unsigned long long xbase, int it) { return xbase + 2ull + 2ull * (unsigned long long)it; }
+__host__ __device__ inline unsigned long long dfb_xid_rr(unsigned long long xbase, int it) { return xbase + 3ull + 2ull * (unsigned long long)it; }
+__host__ __device__ inline unsigned long long dfb_hid(unsigned long long hbase, int it) { return hbase + 1ull + (unsigned long long)it; }
 
 struct dfb_ctx {
   int device = 0;
@@ -79,8 +92,11 @@ struct dfb_ctx {
   double *d_partials = nullptr;   // [DFB_RED_MAX_BLOCKS * DFB_RED_K]
   unsigned int *d_ticket = nullptr;  // [8]
   DfbSolverState *d_state = nullptr;
-  double *d_hist = nullptr;       // r.r history
+  double *d_hist = nullptr;       // ring of the last hist_cap values of ||r_k||^2 (entry k at k % hist_cap), drained per chunk
   uint64_t hist_cap = 0;
+  void *h_poll = nullptr;         // pinned: 2 slots of [DfbSolverState | ring snapshot]
+  size_t h_poll_slot = 0;         // bytes per slot
+  std::vector<double> last_hist;  // ||r_k||^2, k = 0..iter of the last solve (host copy)
   double *d_scratch = nullptr;    // small scalar scratch [64]
   void *h_pinned = nullptr;       // pinned host scratch (4 KB)
   int *d_errflag = nullptr;       // generic device error flag [4]
@@ -90,7 +106,8 @@ struct dfb_ctx {
   // options
   int64_t spmv_variant = 20;
   int64_t iters_per_sync = 16;
-  int64_t use_graph = 0;
+  int64_t use_graph = 1;          // (P)CG: replay chunks of iterations as a CUDA graph (0: plain launches)
+  struct DfbGraphCache *graph = nullptr;
   int64_t assemble_variant = 0;
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
@@ -106,25 +123,23 @@ struct dfb_ctx {
   DfbMailbox *d_mbox = nullptr;                 // local, IPC-exported
   DfbMailbox *peer_mbox[DFB_MAX_RANKS] = {};    // mapped peers (own entry = d_mbox)
   int peer_enabled = 0;
-  unsigned long long peer_seq = 0;
   int64_t use_peer_allreduce = 1;               // option: 0 forces NCCL all-reduce even when mailboxes are mapped
   // peer halo push (ghost values stored straight into the neighbours' landing zones over NVLink; PCG only)
   int64_t use_peer_halo = 0;                    // option: 1 = ghost exchange by peer push inside (P)CG (measured slower than NCCL, see profiles/README.md)
   int64_t peer_halo_bytes = 8ll << 20;          // option (before dfb_ctx_peer_export): landing-zone bytes per parity buffer
   uint64_t landing_bytes = 0;                   // what the exported allocation actually holds per parity buffer
-  unsigned long long halo_seq = 0;
 };
 
 static inline double *dfb_peer_landing(const dfb_ctx *c, int r, int parity) {
   return (double *)((unsigned char *)c->peer_mbox[r] + sizeof(DfbMailbox) + (size_t)parity * c->landing_bytes);
 }
 
-// view handed to kernels; seq = 0 disables the exchange for that launch
-static inline DfbPeerView dfb_peer_view(const dfb_ctx *c, unsigned long long seq) {
+// view handed to kernels; post = 0: the launch does not publish its reduction to the peers
+static inline DfbPeerView dfb_peer_view(const dfb_ctx *c, int post) {
   DfbPeerView pv;
   pv.rank = c->rank;
   pv.nranks = (c->peer_enabled && c->use_peer_allreduce && c->nranks > 1) ? c->nranks : 1;
-  pv.seq = seq;
+  pv.post = post;
   for (int r = 0; r < DFB_MAX_RANKS; ++r) pv.mbox[r] = c->peer_mbox[r];
   return pv;
 }
@@ -179,9 +194,9 @@ struct dfb_halo {
 struct DfbHaloPush {   // kernel argument of the pack-and-push launch
   int n_peers;
   int rank;
-  unsigned long long seq;
+  uint64_t parity_stride;                     // doubles between the two parity buffers of a landing zone
   uint64_t send_ptr[DFB_MAX_RANKS + 1];
-  double *dst[DFB_MAX_RANKS];                 // peer landing zone (this parity) + remote offset, in doubles
+  double *dst[DFB_MAX_RANKS];                 // peer landing zone (parity 0) + remote offset, in doubles
   unsigned long long *flag[DFB_MAX_RANKS];    // &peer_mbox[peer]->halo_flag[rank]
 };
 
@@ -242,6 +257,7 @@ dfb_status dfb_ilu_dot(dfb_ctx *c, const double *a, const double *b, uint64_t n,
 // ---- helpers implemented in ctx.cu
 dfb_status dfb_dev_alloc(void **p, size_t bytes);
 void dfb_dev_free(void *p);
+uint64_t dfb_free_epoch();  // number of dfb_dev_free calls so far: cached graphs bake raw device pointers and must not outlive them
 template <typename T>
 static inline dfb_status dfb_dev_alloc_t(T **p, size_t count) {
   return dfb_dev_alloc((void **)p, count * sizeof(T) + 256);
@@ -253,9 +269,12 @@ dfb_status dfb_exclusive_scan_u32(dfb_ctx *ctx, uint32_t *d_data, uint64_t n, ui
 dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaStream_t strm);
 dfb_status dfb_halo_exchange_on(dfb_halo *h, double *d_vec, uint64_t n_blk, int blk_dim, cudaStream_t strm);
 bool dfb_halo_peer_usable(const dfb_halo *h, int blk_dim);
-dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, int state_parity, cudaStream_t strm, DfbHaloWait *wait_out);
+dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, cudaStream_t strm);
+void dfb_halo_wait_view(const dfb_halo *h, int blk_dim, uint64_t n_own, DfbHaloWait *wait_out);
+// in_solver: the launch belongs to a (P)CG iteration (reads iteration / stop flag / exchange ids from ctx->d_state)
 dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alpha, const double *x, uint64_t row_begin,
-                           uint64_t row_end, int fuse_dot, int state_parity, cudaStream_t strm, unsigned long long post_seq = 0,
+                           uint64_t row_end, int fuse_dot, int in_solver, cudaStream_t strm, int post = 0,
                            const DfbHaloWait *hw = nullptr);
+dfb_status dfb_bsr_ensure_packed(const dfb_bsr *m);
 
 static inline int dfb_div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }

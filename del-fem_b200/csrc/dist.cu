@@ -91,6 +91,19 @@ dfb_status dfb_nccl_allreduce_sum(dfb_ctx *ctx, double *d_buf, int count, cudaSt
   return DFB_OK;
 }
 
+// called by dfb_ctx_destroy: unmap the peers' mailboxes, free the own one, destroy the communicator
+void dfb_comm_teardown(dfb_ctx *ctx) {
+  for (int r = 0; r < DFB_MAX_RANKS; ++r) {
+    if (ctx->peer_mbox[r] && ctx->peer_mbox[r] != ctx->d_mbox) cudaIpcCloseMemHandle(ctx->peer_mbox[r]);
+    ctx->peer_mbox[r] = nullptr;
+  }
+  ctx->peer_enabled = 0;
+  if (ctx->d_mbox) cudaFree(ctx->d_mbox);
+  ctx->d_mbox = nullptr;
+  if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+}
+
 // ------------------------------------------------------------------------------------------------ peer mailboxes
 DFB_API dfb_status dfb_ctx_peer_export(dfb_ctx *ctx, uint8_t handle_out[64]) {
   DFB_REQUIRE(ctx && handle_out, "dfb_ctx_peer_export: NULL argument");
@@ -134,8 +147,12 @@ DFB_API dfb_status dfb_ctx_peer_import(dfb_ctx *ctx, const uint8_t *handles, int
 // block to finish fences and then raises this rank's flag in every neighbour's mailbox.  The matching wait lives in the
 // boundary tiles of the neighbour's SpMV (bsr.cu), so a ghost exchange costs one small launch and no collective.
 __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ v, const uint32_t *__restrict__ idx, int dim,
-                                                    const DfbHaloPush hp, const DfbSolverState *st, int parity, unsigned int *ticket) {
-  if (st && st->done[parity]) return;
+                                                    const DfbHaloPush hp, const DfbSolverState *st, unsigned int *ticket) {
+  // runs after the kernel that produced v (init: iteration 0's direction; the direction kernel of iteration i-1: st->iter == i)
+  const int it = st->iter;
+  if (st->done[it & 1]) return;
+  const unsigned long long seq = dfb_hid(st->hbase, it);
+  const uint64_t par_off = (seq & 1ull) ? hp.parity_stride : 0;
   __shared__ bool s_last;
   const uint64_t total = hp.send_ptr[hp.n_peers] * (uint64_t)dim;
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (uint64_t)gridDim.x * blockDim.x) {
@@ -143,7 +160,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ v,
     const int d = (int)(q - s * dim);
     int p = 0;
     while (p + 1 < hp.n_peers && s >= hp.send_ptr[p + 1]) ++p;
-    hp.dst[p][(s - hp.send_ptr[p]) * dim + d] = v[(uint64_t)idx[s] * dim + d];
+    hp.dst[p][par_off + (s - hp.send_ptr[p]) * dim + d] = v[(uint64_t)idx[s] * dim + d];
   }
   __threadfence_system();
   __syncthreads();
@@ -152,7 +169,7 @@ __global__ void __launch_bounds__(256) k_halo_push(const double *__restrict__ v,
   if (s_last && (int)threadIdx.x < hp.n_peers) {
     __threadfence_system();
     volatile unsigned long long *f = hp.flag[threadIdx.x];
-    *f = hp.seq;
+    *f = seq;
   }
 }
 
@@ -188,8 +205,8 @@ DFB_API dfb_status dfb_halo_create(dfb_ctx *ctx, int32_t n_peers, const int32_t 
   h->d_sendbuf = nullptr;
   dfb_status st = dfb_dev_alloc_t(&h->d_send_idx, h->n_send + 2);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&h->d_sendbuf, h->n_send * h->max_dim + 2);
+  if (st == DFB_OK && h->n_send > 0 && !send_idx) st = dfb_fail(DFB_ERR_BAD_ARG, "dfb_halo_create: send_idx is NULL");
   if (st == DFB_OK && h->n_send > 0) {
-    DFB_REQUIRE(send_idx, "dfb_halo_create: send_idx is NULL");
     cudaError_t e = cudaMemcpyAsync(h->d_send_idx, send_idx, h->n_send * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_halo_create: %s", cudaGetErrorString(e));
@@ -222,35 +239,40 @@ bool dfb_halo_peer_usable(const dfb_halo *h, int blk_dim) {
   return true;
 }
 
-dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, int state_parity, cudaStream_t strm, DfbHaloWait *wait_out) {
+// push the boundary entries of d_vec into the neighbours' landing zones; exchange id and parity buffer come from the solver state
+dfb_status dfb_halo_push(dfb_halo *h, const double *d_vec, int blk_dim, cudaStream_t strm) {
   dfb_ctx *c = h->ctx;
-  const unsigned long long seq = ++c->halo_seq;
-  const int par = (int)(seq & 1ull);
+  if (h->n_peers == 0) return DFB_OK;
   DfbHaloPush hp;
   hp.n_peers = h->n_peers;
   hp.rank = c->rank;
-  hp.seq = seq;
-  uint32_t mask = 0;
+  hp.parity_stride = c->landing_bytes / sizeof(double);
   for (int p = 0; p <= h->n_peers; ++p) hp.send_ptr[p] = h->send_ptr[p];
   for (int p = 0; p < h->n_peers; ++p) {
     const int pr = h->peers[p];
-    hp.dst[p] = dfb_peer_landing(c, pr, par) + h->remote_off[p] * (uint64_t)blk_dim;
+    hp.dst[p] = dfb_peer_landing(c, pr, 0) + h->remote_off[p] * (uint64_t)blk_dim;
     hp.flag[p] = &c->peer_mbox[pr]->halo_flag[c->rank];
-    if (h->recv_ptr[p + 1] > h->recv_ptr[p]) mask |= 1u << pr;
   }
-  if (h->n_peers > 0) {
-    int g = dfb_div_up(h->n_send * blk_dim, 256);
-    if (g < 1) g = 1;
-    if (g > c->sm_count * 2) g = c->sm_count * 2;
-    DFB_LAUNCH_ON(c, strm, k_halo_push, g, 256, 0, d_vec, h->d_send_idx, blk_dim, hp, state_parity < 0 ? nullptr : c->d_state,
-                  state_parity < 0 ? 0 : state_parity, c->d_ticket + 5);
-    DFB_CHECK_LAUNCH();
-  }
-  wait_out->seq = seq;
-  wait_out->wait_mask = mask;
-  wait_out->halo_flag = c->d_mbox->halo_flag;
-  wait_out->xg = dfb_peer_landing(c, c->rank, par);  // the caller subtracts n_own * N
+  int g = dfb_div_up(h->n_send * blk_dim, 256);
+  if (g < 1) g = 1;
+  if (g > c->sm_count * 2) g = c->sm_count * 2;
+  DFB_LAUNCH_ON(c, strm, k_halo_push, g, 256, 0, d_vec, h->d_send_idx, blk_dim, hp, c->d_state, c->d_ticket + 5);
+  DFB_CHECK_LAUNCH();
   return DFB_OK;
+}
+
+// receiver side: where the neighbours' pushes land on THIS rank and whose flags to wait for
+void dfb_halo_wait_view(const dfb_halo *h, int blk_dim, uint64_t n_own, DfbHaloWait *w) {
+  const dfb_ctx *c = h->ctx;
+  uint32_t mask = 0;
+  for (int p = 0; p < h->n_peers; ++p)
+    if (h->recv_ptr[p + 1] > h->recv_ptr[p]) mask |= 1u << h->peers[p];
+  w->wait_mask = mask;
+  w->halo_flag = c->d_mbox->halo_flag;
+  w->n_own = (uint32_t)n_own;
+  for (int par = 0; par < 2; ++par) w->xg[par] = dfb_peer_landing(c, c->rank, par) - n_own * (uint64_t)blk_dim;
+  w->tile_lo_end = 0;
+  w->tile_hi_begin = 0xFFFFFFFFu;
 }
 
 DFB_API dfb_status dfb_halo_destroy(dfb_halo *h) {

@@ -431,6 +431,13 @@ dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, in
 
 double *dfb_ilu_z(DfbIlu *s) { return s->d_z; }
 
+// factor values of src -> dst (both built for the same pattern and level of fill): Solver::clone copies the decomposed ILU
+dfb_status dfb_ilu_copy_values(dfb_ctx *c, DfbIlu *dst, const DfbIlu *src, int NN) {
+  DFB_REQUIRE(dst && src && dst->nnz == src->nnz, "ilu copy: the two factorisations have different patterns");
+  DFB_CUDA(cudaMemcpyAsync(dst->d_val, src->d_val, src->nnz * (uint64_t)NN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  return DFB_OK;
+}
+
 dfb_status dfb_ilu_dot(dfb_ctx *c, const double *a, const double *b, uint64_t n, double *d_out) {
   uint64_t g = (n + 1023) / 1024;
   if (g < 1) g = 1;

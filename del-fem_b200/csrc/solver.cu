@@ -2,22 +2,28 @@
 // preconditioned_conjugate_gradient (sparse_square.rs:264-347, solver_sparse.rs:73-175) with Jacobi / block-Jacobi
 // (sparse_ilu.rs:87-219 on an empty off-diagonal pattern).
 //
-// One iteration = three kernels, no host round trip:
+// One iteration = three kernels, no host round trip and NO per-iteration host arguments:
 //   K1  q = A p            fused  p.q                       (bsr.cu; deterministic last-block reduction -> red[0])
 //   K2  alpha = rho/p.q;   r -= alpha q;  x += alpha p;     fused  r.r, r.(M^-1 r)  -> red[1], red[2]
 //   K3  beta = r.z/rho;    p = M^-1 r + beta p;             thread 0 records ||r||^2, tests convergence, swaps rho
-// alpha/beta live on the device; the host polls a convergence flag every `iters_per_sync` iterations (one chunk of
-// look-ahead); iterations enqueued past convergence exit at their first instruction, so x, r and the history are
-// exactly those of the reference's early return.  Multi-GPU: red[] is all-reduced between the kernels.
+// alpha/beta, the iteration index, its parity and the exchange ids of the multi-GPU steps live in the device-side solver state
+// (dfb_internal.h), so every iteration is the SAME three launches: a chunk of `iters_per_sync` iterations is captured once
+// into a CUDA graph and replayed; the host only polls a stop flag per chunk (one chunk of look-ahead).  Iterations enqueued past
+// convergence / max_it exit at their first instruction, so x, r and the history are exactly those of the reference's early
+// return.  Multi-GPU: the two scalar all-reduces are fused into these kernels over NVLink peer memory (peer.cuh: the last
+// block of the producer posts, the first block of the consumer gathers and releases a local flag), and the direction vector's
+// boundary entries are pushed into the neighbours' landing zones right after K3 (the next K1's boundary tiles wait for the
+// neighbours' flags) — no collective launch in the loop; NCCL (all-reduce + send/recv on a second stream) is the fallback.
 #include <math.h>
+#include <string.h>
 
 #include <vector>
 
 #include "dfb_internal.h"
 #include "reduce.cuh"
 
-dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int parity,
-                         unsigned long long post_seq);
+dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha, double *x, int fuse_dot, int in_solver, int post);
+bool dfb_spmv_uses_peer_halo(const dfb_bsr *m);
 bool dfb_prof_begin(dfb_ctx *c);
 void dfb_prof_end(dfb_ctx *c);
 dfb_status dfb_prof_flush(dfb_ctx *c, size_t max_pairs);
@@ -242,11 +248,11 @@ DFB_API dfb_status dfb_precond_destroy(dfb_precond *pc) {
 }
 
 // ------------------------------------------------------------------------------------------------ (P)CG kernels
-// K0: x = 0 ; p = M^-1 r ; red[1] = r.r ; red[2] = r.(M^-1 r)
+// K0: x = 0 ; p = M^-1 r ; red[1] = r.r ; red[2] = r.(M^-1 r).  Posts them to the peers as exchange xseq_next + 1.
 template <int N, int KIND>
 __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, double *__restrict__ x, double *__restrict__ p,
                                                   const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
-                                                  double *partials, unsigned int *ticket, const DfbPeerView pv_out) {
+                                                  double *partials, unsigned int *ticket, const DfbPeerView pv) {
   __shared__ double s_buf[64];
   double acc[2] = {0.0, 0.0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -269,16 +275,18 @@ __global__ void __launch_bounds__(256) k_pcg_init(const double *__restrict__ r, 
       s_buf[0] = acc[0];
       s_buf[1] = acc[1];
     }
-    if (pv_out.nranks > 1 && pv_out.seq != 0) peer_post_block<2>(pv_out, s_buf);
+    if (pv.nranks > 1 && pv.post) peer_post_block<2>(pv, st->xseq_next + 1ull, s_buf);
   }
 }
 
-// after the (all-reduced) initial dots: set up the state. hist[0] = r0.r0
-__global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol, double eps_sq, int check_pap,
-                                    const DfbPeerView pv_in) {
+// after the (all-reduced) initial dots: set up the state of this solve (one block). The ring entry 0 holds r0.r0.
+__global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol, double eps_sq, int check_pap, int max_it,
+                                    const DfbPeerView pv) {
   double g[2] = {st->red[1], st->red[2]};
   int perr = 0;
-  if (pv_in.nranks > 1 && pv_in.seq != 0) peer_gather<2>(pv_in, g, &perr);
+  const unsigned long long xb = st->xseq_next, hb = st->hseq_next;
+  if (pv.nranks > 1 && pv.post) peer_gather<2>(pv, xb + 1ull, g, &perr);
+  __syncthreads();
   if (threadIdx.x != 0) return;
   const double rr0 = g[0];
   st->rr0 = rr0;
@@ -287,30 +295,59 @@ __global__ void k_pcg_init_finalize(DfbSolverState *st, double *hist, double tol
   st->rho[1] = 0.0;
   st->tol = tol;
   st->eps_sq = eps_sq;
-  st->done[0] = (rr0 < eps_sq) ? 1 : 0;
+  st->xbase = xb;
+  st->hbase = hb;
+  st->done[0] = (rr0 < eps_sq || max_it <= 0) ? 1 : 0;
   st->done[1] = st->done[0];
   st->iter = 0;
-  st->err = perr;
+  st->iter_dir = 0;
+  st->err = perr ? 2 : 0;
   st->check_pap = check_pap;
+  st->converged = (rr0 < eps_sq) ? 1 : 0;
+  st->max_it = max_it;
   hist[0] = rr0;
+}
+
+// after the last chunk: retire the exchange ids this solve used (k completed iterations: 1 + 2k scalar exchanges, 1 + k pushes)
+__global__ void k_pcg_end(DfbSolverState *st) {
+  st->xseq_next = st->xbase + 2ull + 2ull * (unsigned long long)st->iter;
+  st->hseq_next = st->hbase + 2ull + (unsigned long long)st->iter;
+}
+
+// what K2 needs before touching the vectors: iteration index, stop flag, (all-reduced) p.q
+struct IterHead {
+  int it, parity;
+  bool stop;
+  double pq;
+};
+__device__ __forceinline__ IterHead update_head(DfbSolverState *st, const DfbPeerView &pv, unsigned int *gticket) {
+  IterHead h;
+  h.it = st->iter;
+  h.parity = h.it & 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->iter_dir = h.it;  // the direction kernel reads its iteration index from here
+  h.stop = st->done[h.parity] != 0;
+  h.pq = 0.0;
+  if (h.stop) return h;
+  if (pv.nranks > 1) {
+    double g[1];
+    peer_gather_grid<1>(pv, dfb_xid_pq(st->xbase, h.it), &st->red[0], &st->gflag[0], gticket, &st->err, g);
+    h.pq = g[0];
+  } else {
+    h.pq = st->red[0];
+  }
+  return h;
 }
 
 // K2: alpha = rho / (p.q) ; r -= alpha q ; x += alpha p ; red[1] = r.r ; red[2] = r.(M^-1 r)
 template <int N, int KIND>
 __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
                                                     const double *__restrict__ p, const double *__restrict__ inv,
-                                                    uint64_t num_blk, DfbSolverState *st, int parity, double *partials,
-                                                    unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
+                                                    uint64_t num_blk, DfbSolverState *st, double *partials, unsigned int *ticket,
+                                                    unsigned int *gticket, const DfbPeerView pv) {
   __shared__ double s_buf[64];
-  if (st->done[parity]) return;
-  double pq = st->red[0];
-  if (pv_in.nranks > 1) {
-    double g[1];
-    peer_gather<1>(pv_in, g, &st->err);
-    pq = g[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->red[0] = pq;
-  }
-  const double alpha = st->rho[parity] / pq;
+  const IterHead h = update_head(st, pv, gticket);
+  if (h.stop) return;
+  const double alpha = st->rho[h.parity] / h.pq;
   double acc[2] = {0.0, 0.0};
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
     double rv[N], z[N];
@@ -334,41 +371,64 @@ __global__ void __launch_bounds__(256) k_pcg_update(double *__restrict__ r, doub
       s_buf[0] = acc[0];
       s_buf[1] = acc[1];
     }
-    if (pv_out.nranks > 1) peer_post_block<2>(pv_out, s_buf);
+    if (pv.nranks > 1 && pv.post) peer_post_block<2>(pv, dfb_xid_rr(st->xbase, h.it), s_buf);
   }
 }
 
-// K3: beta = r.z / rho ; p = M^-1 r + beta p ; thread 0 of block 0: history, convergence, rho swap
-template <int N, int KIND>
-__global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict__ r, double *__restrict__ p,
-                                                       const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
-                                                       int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
-  if (st->done[parity]) {
-    // converged earlier: propagate the flag into the slot the next iteration reads, change nothing else
+// what K3 needs: iteration index (from iter_dir), stop flag, (all-reduced) r.r / r.z; thread 0 of block 0 does the bookkeeping
+struct DirHead {
+  bool stop;
+  double beta;
+};
+__device__ __forceinline__ DirHead direction_head(DfbSolverState *st, double *hist, uint64_t hist_ring, const DfbPeerView &pv,
+                                                  unsigned int *gticket, bool gather) {
+  DirHead h;
+  const int it = st->iter_dir, parity = it & 1;
+  h.stop = st->done[parity] != 0;
+  h.beta = 0.0;
+  if (h.stop) {
+    // stopped earlier: propagate the flag into the slot the next iteration reads, change nothing else
     if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
-    return;
+    return h;
   }
   double rr = st->red[1], rz = st->red[2];
-  if (pv_in.nranks > 1) {
+  if (pv.nranks > 1 && gather) {
     double g[2];
-    peer_gather<2>(pv_in, g, &st->err);
+    peer_gather_grid<2>(pv, dfb_xid_rr(st->xbase, it), &st->red[1], &st->gflag[1], gticket, &st->err, g);
     rr = g[0];
     rz = g[1];
   }
-  const double beta = rz / st->rho[parity];
+  h.beta = rz / st->rho[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int it = st->iter + 1;
-    st->iter = it;
-    if ((uint64_t)it < hist_cap) hist[it] = rr;
+    const int k = it + 1;
+    st->iter = k;
+    hist[(uint64_t)k % hist_ring] = rr;
     const double conv_ratio = sqrt(rr * st->inv_rr0);
-    int done = (conv_ratio < st->tol) ? 1 : 0;
+    int stop = 0;
+    if (conv_ratio < st->tol) {
+      st->converged = 1;
+      stop = 1;
+    }
     if (st->check_pap && !(st->red[0] >= 0.0)) {
       st->err = 1;
-      done = 1;
+      stop = 1;
     }
-    st->done[parity ^ 1] = done;
+    if (k >= st->max_it) stop = 1;
+    st->done[parity ^ 1] = stop;
     st->rho[parity ^ 1] = rz;
   }
+  return h;
+}
+
+// K3: beta = r.z / rho ; p = M^-1 r + beta p
+template <int N, int KIND>
+__global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict__ r, double *__restrict__ p,
+                                                       const double *__restrict__ inv, uint64_t num_blk, DfbSolverState *st,
+                                                       double *hist, uint64_t hist_ring, unsigned int *gticket, const DfbPeerView pv,
+                                                       int gather) {
+  const DirHead h = direction_head(st, hist, hist_ring, pv, gticket, gather != 0);
+  if (h.stop) return;
+  const double beta = h.beta;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
     double rv[N], z[N];
 #pragma unroll
@@ -384,18 +444,12 @@ __global__ void __launch_bounds__(256) k_pcg_direction(const double *__restrict_
 template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r, double *__restrict__ x, const double *__restrict__ q,
                                                          const double *__restrict__ p, const double *__restrict__ inv,
-                                                         uint64_t n, DfbSolverState *st, int parity, double *partials,
-                                                         unsigned int *ticket, const DfbPeerView pv_in, const DfbPeerView pv_out) {
+                                                         uint64_t n, DfbSolverState *st, double *partials, unsigned int *ticket,
+                                                         unsigned int *gticket, const DfbPeerView pv) {
   __shared__ double s_buf[64];
-  if (st->done[parity]) return;
-  double pq = st->red[0];
-  if (pv_in.nranks > 1) {
-    double g[1];
-    peer_gather<1>(pv_in, g, &st->err);
-    pq = g[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->red[0] = pq;
-  }
-  const double alpha = st->rho[parity] / pq;
+  const IterHead h = update_head(st, pv, gticket);
+  if (h.stop) return;
+  const double alpha = st->rho[h.parity] / h.pq;
   double acc[2] = {0.0, 0.0};
   const uint64_t n2 = n >> 1;
   double2 *r2 = reinterpret_cast<double2 *>(r);
@@ -405,11 +459,11 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
   const double2 *i2 = reinterpret_cast<const double2 *>(inv);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
     double2 rv = r2[i], xv = x2[i];
-    const double2 qv = q2[i], pv = p2[i];
+    const double2 qv = q2[i], pv2 = p2[i];
     rv.x -= alpha * qv.x;
     rv.y -= alpha * qv.y;
-    xv.x += alpha * pv.x;
-    xv.y += alpha * pv.y;
+    xv.x += alpha * pv2.x;
+    xv.y += alpha * pv2.y;
     r2[i] = rv;
     x2[i] = xv;
     double zx = rv.x, zy = rv.y;
@@ -437,53 +491,32 @@ __global__ void __launch_bounds__(256) k_pcg_update_flat(double *__restrict__ r,
       s_buf[0] = acc[0];
       s_buf[1] = acc[1];
     }
-    if (pv_out.nranks > 1) peer_post_block<2>(pv_out, s_buf);
+    if (pv.nranks > 1 && pv.post) peer_post_block<2>(pv, dfb_xid_rr(st->xbase, h.it), s_buf);
   }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__restrict__ r, double *__restrict__ p,
                                                             const double *__restrict__ inv, uint64_t n, DfbSolverState *st,
-                                                            int parity, double *hist, uint64_t hist_cap, const DfbPeerView pv_in) {
-  if (st->done[parity]) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->done[parity ^ 1] = 1;
-    return;
-  }
-  double rr = st->red[1], rz = st->red[2];
-  if (pv_in.nranks > 1) {
-    double g[2];
-    peer_gather<2>(pv_in, g, &st->err);
-    rr = g[0];
-    rz = g[1];
-  }
-  const double beta = rz / st->rho[parity];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int it = st->iter + 1;
-    st->iter = it;
-    if ((uint64_t)it < hist_cap) hist[it] = rr;
-    const double conv_ratio = sqrt(rr * st->inv_rr0);
-    int done = (conv_ratio < st->tol) ? 1 : 0;
-    if (st->check_pap && !(st->red[0] >= 0.0)) {
-      st->err = 1;
-      done = 1;
-    }
-    st->done[parity ^ 1] = done;
-    st->rho[parity ^ 1] = rz;
-  }
+                                                            double *hist, uint64_t hist_ring, unsigned int *gticket,
+                                                            const DfbPeerView pv) {
+  const DirHead h = direction_head(st, hist, hist_ring, pv, gticket, true);
+  if (h.stop) return;
+  const double beta = h.beta;
   const uint64_t n2 = n >> 1;
   const double2 *r2 = reinterpret_cast<const double2 *>(r);
   double2 *p2 = reinterpret_cast<double2 *>(p);
   const double2 *i2 = reinterpret_cast<const double2 *>(inv);
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
-    double2 z = r2[i], pv = p2[i];
+    double2 z = r2[i], pv2 = p2[i];
     if (KIND == DFB_PRECOND_JACOBI) {
       const double2 iv = i2[i];
       z.x *= iv.x;
       z.y *= iv.y;
     }
-    pv.x = z.x + beta * pv.x;
-    pv.y = z.y + beta * pv.y;
-    p2[i] = pv;
+    pv2.x = z.x + beta * pv2.x;
+    pv2.y = z.y + beta * pv2.y;
+    p2[i] = pv2;
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const uint64_t i = n - 1;
@@ -492,28 +525,6 @@ __global__ void __launch_bounds__(256) k_pcg_direction_flat(const double *__rest
   }
 }
 
-// One warp collects the R partial sums of exchange pv.seq from the LOCAL mailbox and stores the rank-ordered total where the
-// single-GPU kernels expect it. (Letting every block of the consumer kernel spin on the mailbox line was measured slower than
-// NCCL: ~10^4 spinning threads starve the incoming NVLink write.)
-template <int K>
-__global__ void k_peer_gather(const DfbPeerView pv, DfbSolverState *st, int first, int parity) {
-  if (parity >= 0 && st->done[parity]) return;  // converged: the producer did not post either
-  double g[K];
-  int err = 0;
-  peer_gather<K>(pv, g, &err);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) st->red[first + k] = g[k];
-    if (err) st->err = 2;
-  }
-}
-
-struct FlagsHost {
-  int done[2];
-  int iter;
-  int err;
-};
-
 static int vec_grid(const dfb_ctx *c, uint64_t num_blk) {
   uint64_t g = (num_blk + 255) / 256;
   const uint64_t cap = (uint64_t)c->sm_count * 8;
@@ -521,6 +532,126 @@ static int vec_grid(const dfb_ctx *c, uint64_t num_blk) {
   if (g > cap) g = cap;
   if (g > DFB_RED_MAX_BLOCKS) g = DFB_RED_MAX_BLOCKS;
   return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+// everything one iteration's launches depend on; also the key of the cached chunk graph
+struct IterPlan {
+  const dfb_bsr *m;
+  const dfb_precond *pc;
+  double *r, *x, *q, *p;
+  const double *inv;
+  double *zbuf;
+  uint64_t nb, nflat;
+  int n, kind, G, GF;
+  int peer, nccl_red, peer_halo;
+  int64_t spmv_variant, chunk;
+  uint64_t hist_ring;
+  const void *packed;  // the packed mirror the SpMV nodes were captured with
+  const void *hist;
+  uint64_t epoch;      // dfb_free_epoch() at capture time (any device free since then invalidates the graph)
+};
+
+struct DfbGraphCache {
+  IterPlan key;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t nodes = 0;  // kernel launches one replay stands for
+};
+
+void dfb_graph_cache_destroy(dfb_ctx *c) {
+  if (!c->graph) return;
+  if (c->graph->exec) cudaGraphExecDestroy(c->graph->exec);
+  delete c->graph;
+  c->graph = nullptr;
+}
+
+// enqueue ONE iteration on c->stream (plain launch or under stream capture: identical arguments every time)
+static dfb_status enqueue_iteration(dfb_ctx *c, const IterPlan &P, bool profile) {
+  DfbSolverState *st = c->d_state;
+  const DfbPeerView pv = dfb_peer_view(c, 1);
+  DfbPeerView pv_local = pv;   // consumers that read st->red[] as it is (single GPU, or after ncclAllReduce)
+  pv_local.nranks = 1;
+  const DfbPeerView &pvk = P.peer ? pv : pv_local;
+  const int n = P.n, kind = P.kind;
+  const bool ilu = kind == DFB_PRECOND_ILU0;
+  const bool prof = profile ? dfb_prof_begin(c) : false;
+  DFB_TRY(dfb_spmv_full(P.m, P.q, 0.0, 1.0, P.p, 1, 1, P.peer));
+  if (prof) dfb_prof_end(c);
+  if (P.nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
+  unsigned int *tk = c->d_ticket + 2, *gt_u = c->d_ticket + 6, *gt_d = c->d_ticket + 7;
+  if (kind == DFB_PRECOND_BLOCK_JACOBI) {
+#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), P.G, 256, 0, P.r, P.x, P.q, P.p, P.inv, P.nb, st, c->d_partials, tk, gt_u, pvk)
+    DISPATCH_ALL(UPD)
+#undef UPD
+  } else if (kind == DFB_PRECOND_JACOBI) {
+    DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, P.GF, 256, 0, P.r, P.x, P.q, P.p, P.inv, P.nflat, st, c->d_partials, tk, gt_u, pvk);
+  } else {
+    DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, P.GF, 256, 0, P.r, P.x, P.q, P.p, P.inv, P.nflat, st, c->d_partials, tk, gt_u, pvk);
+  }
+  if (ilu) {
+    // the update kernel ran with M = I (r.r in red[1]); now z = M^-1 r explicitly and r.z -> red[2]
+    DFB_CUDA(cudaMemcpyAsync(P.zbuf, P.r, P.nflat * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    DFB_TRY(dfb_ilu_apply(c, P.pc->ilu, P.pc->pat, n, P.pc->d_inv, P.zbuf));
+    DFB_TRY(dfb_ilu_dot(c, P.r, P.zbuf, P.nflat, &st->red[2]));
+  }
+  if (P.nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+  if (kind == DFB_PRECOND_BLOCK_JACOBI) {
+#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), P.G, 256, 0, P.r, P.p, P.inv, P.nb, st, c->d_hist, P.hist_ring, gt_d, pvk, 1)
+    DISPATCH_ALL(DIR)
+#undef DIR
+  } else if (kind == DFB_PRECOND_JACOBI) {
+    DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, P.GF, 256, 0, P.r, P.p, P.inv, P.nflat, st, c->d_hist, P.hist_ring, gt_d, pvk);
+  } else if (ilu) {
+#define DIRZ(NV) \
+  if (n == NV) DFB_LAUNCH(c, (k_pcg_direction<NV, DFB_PRECOND_ILU0>), P.G, 256, 0, P.r, P.p, P.zbuf, P.nb, st, c->d_hist, P.hist_ring, gt_d, pv_local, 0);
+    DIRZ(1) DIRZ(2) DIRZ(3) DIRZ(4)
+#undef DIRZ
+  } else {
+    DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, P.GF, 256, 0, P.r, P.p, P.inv, P.nflat, st, c->d_hist, P.hist_ring, gt_d, pvk);
+  }
+  // the boundary entries of the new direction go straight into the neighbours' landing zones
+  if (P.peer_halo) DFB_TRY(dfb_halo_push(P.m->halo, P.p, n, c->stream));
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+// capture `chunk` iterations into a graph (cached per ctx, keyed by every pointer / size baked into the nodes)
+static dfb_status chunk_graph(dfb_ctx *c, const IterPlan &P, DfbGraphCache **out) {
+  *out = nullptr;
+  if (c->graph && c->graph->exec && memcmp(&c->graph->key, &P, sizeof(IterPlan)) == 0) {
+    *out = c->graph;
+    return DFB_OK;
+  }
+  dfb_graph_cache_destroy(c);
+  const uint64_t launches0 = c->launches;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return DFB_OK;  // caller falls back to plain launches
+  }
+  dfb_status st = DFB_OK;
+  for (int64_t j = 0; j < P.chunk && st == DFB_OK; ++j) st = enqueue_iteration(c, P, false);
+  const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  const uint64_t nodes = c->launches - launches0;
+  c->launches = launches0;  // capturing launched nothing
+  if (st != DFB_OK || e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return DFB_OK;
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    return DFB_OK;
+  }
+  cudaGraphDestroy(graph);
+  c->graph = new DfbGraphCache();
+  c->graph->key = P;
+  c->graph->exec = exec;
+  c->graph->nodes = nodes;
+  *out = c->graph;
+  return DFB_OK;
 }
 
 // shared driver. mode 0 = CG history semantics (ratios, k=0 excluded), 1 = PCG (absolute, k=0 included, trailing entry)
@@ -540,136 +671,157 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
     DFB_REQUIRE(v && v->n_blk == nb && v->blk_dim == n, "(p)cg: vector shape != matrix shape (assert_eq!(r_vec.len(), mat.num_blk))");
     DFB_REQUIRE(v->ctx == c, "(p)cg: vector belongs to another context");
   }
+  if (m->halo && c->nranks > 1) {
+    const uint64_t need = m->halo->recv_ptr.empty() ? 0 : m->halo->recv_ptr.back();
+    DFB_REQUIRE(p->n_ghost >= need, "(p)cg: the matrix has a halo of %llu ghost blocks: create p_vec with n_ghost >= that (it has %llu)",
+                (unsigned long long)need, (unsigned long long)p->n_ghost);
+  }
   if (pc) DFB_REQUIRE(pc->num_blk == nb && pc->blk_dim == n, "pcg: preconditioner shape != matrix shape");
   DFB_REQUIRE(max_it < 0x7FFFFFF0ull, "(p)cg: max_it too large");
-  // device history buffer
-  if (c->hist_cap < max_it + 2) {
+  DFB_CUDA(cudaSetDevice(c->device));
+
+  IterPlan P;
+  memset(&P, 0, sizeof(P));
+  P.m = m;
+  P.pc = pc;
+  P.r = r->d;
+  P.x = x->d;
+  P.q = q->d;
+  P.p = p->d;
+  P.inv = inv;
+  P.zbuf = zbuf;
+  P.nb = nb;
+  P.nflat = nb * (uint64_t)n;
+  P.n = n;
+  P.kind = kind;
+  P.G = vec_grid(c, nb);
+  P.GF = vec_grid(c, (P.nflat + 1) / 2);
+  // scalar all-reduces: fused into the kernels through the NVLink peer mailboxes when mapped, NCCL otherwise
+  P.peer = (c->peer_enabled && c->use_peer_allreduce && c->nranks > 1) ? 1 : 0;
+  P.nccl_red = (c->nranks > 1 && !P.peer) ? 1 : 0;
+  P.peer_halo = (P.peer && dfb_spmv_uses_peer_halo(m)) ? 1 : 0;
+  P.spmv_variant = c->spmv_variant;
+  P.chunk = c->iters_per_sync > 0 ? c->iters_per_sync : 16;
+  if (P.chunk > 256) P.chunk = 256;
+  // ring of ||r_k||^2: the host drains it after every chunk, so 2 chunks + the plain head iteration always fit
+  P.hist_ring = (uint64_t)(2 * P.chunk + 4);
+  if (c->hist_cap < P.hist_ring) {
     dfb_dev_free(c->d_hist);
     c->d_hist = nullptr;
-    DFB_TRY(dfb_dev_alloc_t(&c->d_hist, max_it + 2));
-    c->hist_cap = max_it + 2;
+    c->hist_cap = 0;
+    DFB_TRY(dfb_dev_alloc_t(&c->d_hist, P.hist_ring));
+    c->hist_cap = P.hist_ring;
   }
-  const int G = vec_grid(c, nb);
-  const uint64_t nflat = nb * (uint64_t)n;
-  const int GF = vec_grid(c, (nflat + 1) / 2);
+  const size_t slot_bytes = ((sizeof(DfbSolverState) + 15) & ~(size_t)15) + P.hist_ring * sizeof(double);
+  if (c->h_poll_slot < slot_bytes) {
+    if (c->h_poll) cudaFreeHost(c->h_poll);
+    c->h_poll = nullptr;
+    c->h_poll_slot = 0;
+    DFB_CUDA(cudaMallocHost(&c->h_poll, 2 * slot_bytes));
+    c->h_poll_slot = slot_bytes;
+  }
+  DFB_TRY(dfb_bsr_ensure_packed(m));
+  P.packed = m->d_packed;
+  P.hist = c->d_hist;
+  P.epoch = dfb_free_epoch();
   DfbSolverState *st = c->d_state;
+  const DfbPeerView pv = dfb_peer_view(c, P.peer);
+  DfbPeerView pv_i = pv;
+  if (!P.peer) pv_i.nranks = 1;
 
-  // scalar all-reduces: fused into the kernels through the NVLink peer mailboxes when mapped, NCCL otherwise
-  const bool peer = c->peer_enabled && c->use_peer_allreduce && c->nranks > 1;
-  const bool nccl_red = c->nranks > 1 && !peer;
-  const DfbPeerView pv_none = dfb_peer_view(c, 0);
-  DfbPeerView pv_off = pv_none;  // consumers read st->red[] (filled by k_peer_gather / NCCL / the local reduction)
-  pv_off.nranks = 1;
-  DfbPeerView pv_i = peer ? dfb_peer_view(c, ++c->peer_seq) : pv_none;
-  if (!peer) pv_i.nranks = 1;
   if (ilu) {
     // z = M^-1 r by the level-scheduled sweeps, then the generic init with z taken as given
-    DFB_CUDA(cudaMemcpyAsync(zbuf, r->d, nb * (uint64_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    DFB_CUDA(cudaMemcpyAsync(zbuf, r->d, P.nflat * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     DFB_TRY(dfb_ilu_apply(c, pc->ilu, pc->pat, n, pc->d_inv, zbuf));
 #define INITZ(NV) \
-  if (n == NV) DFB_LAUNCH(c, (k_pcg_init<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, x->d, p->d, zbuf, nb, st, c->d_partials, c->d_ticket + 2, pv_i);
+  if (n == NV) DFB_LAUNCH(c, (k_pcg_init<NV, DFB_PRECOND_ILU0>), P.G, 256, 0, r->d, x->d, p->d, zbuf, nb, st, c->d_partials, c->d_ticket + 2, pv_i);
     INITZ(1) INITZ(2) INITZ(3) INITZ(4)
 #undef INITZ
   }
-#define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2, pv_i)
+#define INIT(NV, KV) DFB_LAUNCH(c, (k_pcg_init<NV, KV>), P.G, 256, 0, r->d, x->d, p->d, inv, nb, st, c->d_partials, c->d_ticket + 2, pv_i)
   DISPATCH_ALL(INIT)
 #undef INIT
   DFB_CHECK_LAUNCH();
-  if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
-  if (peer) DFB_LAUNCH(c, k_peer_gather<2>, 1, 32, 0, pv_i, st, 1, -1);
-  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 32, 0, st, c->d_hist, tol, eps_sq, check_pap, pv_off);
+  if (P.nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
+  DFB_LAUNCH(c, k_pcg_init_finalize, 1, 32, 0, st, c->d_hist, tol, eps_sq, check_pap, (int)max_it, pv_i);
   DFB_CHECK_LAUNCH();
+  if (P.peer_halo) DFB_TRY(dfb_halo_push(m->halo, p->d, n, c->stream));  // ghosts of the first direction
 
-  FlagsHost *hf = (FlagsHost *)c->h_pinned;  // two slots
-  hf[0].done[0] = hf[0].done[1] = hf[1].done[0] = hf[1].done[1] = 0;
-  uint64_t chunk = c->iters_per_sync > 0 ? (uint64_t)c->iters_per_sync : 16;
-  uint64_t enq = 0;  // iterations enqueued
+  // ---- chunks: [one plain iteration (bracketed with events when profiling)] + [graph replay of `chunk` iterations]
+  std::vector<double> &rr = c->last_hist;
+  rr.assign(1, 0.0);
+  const bool use_graph = c->use_graph != 0 && !ilu;  // an ILU sweep is ~900 launches: far too many nodes per iteration
+  DfbGraphCache *gc = nullptr;
+  bool graph_tried = false;
+  DfbSolverState last;
+  memset(&last, 0, sizeof(last));
+  uint64_t enq = 0;
   int n_chunks = 0;
-  bool finished = false;
-  FlagsHost last = {{0, 0}, 0, 0};
+  uint64_t drained = 0;  // history entries 1..drained are in rr
+  auto drain = [&](int slot) {
+    const unsigned char *base = (const unsigned char *)c->h_poll + (size_t)slot * c->h_poll_slot;
+    memcpy(&last, base, sizeof(DfbSolverState));
+    const double *ring = (const double *)(base + ((sizeof(DfbSolverState) + 15) & ~(size_t)15));
+    rr[0] = last.rr0;
+    for (uint64_t k = drained + 1; k <= (uint64_t)last.iter; ++k) rr.push_back(ring[k % P.hist_ring]);
+    drained = (uint64_t)last.iter;
+  };
+  bool finished = max_it == 0;
   while (!finished) {
-    const uint64_t todo = (max_it - enq < chunk) ? (max_it - enq) : chunk;
-    for (uint64_t j = 0; j < todo; ++j) {
-      const int parity = (int)((enq + j) & 1);
-      // profile_spmv = K: bracket every K-th SpMV with events (K = 1: all of them)
-      const bool prof = (c->profile_spmv > 0 && (enq + j) % (uint64_t)c->profile_spmv == 0) ? dfb_prof_begin(c) : false;
-      DfbPeerView pv_a = pv_none, pv_b = pv_none;  // a: p.Ap (K1 -> K2), b: r.r, r.z (K2 -> K3)
-      pv_a.nranks = pv_b.nranks = 1;
-      if (peer) {
-        pv_a = dfb_peer_view(c, ++c->peer_seq);
-        pv_b = dfb_peer_view(c, ++c->peer_seq);
-      }
-      DFB_TRY(dfb_spmv_full(m, q->d, 0.0, 1.0, p->d, 1, parity, peer ? pv_a.seq : 0));
-      if (prof) dfb_prof_end(c);
-      if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[0], 1, c->stream));
-      if (peer) DFB_LAUNCH(c, k_peer_gather<1>, 1, 32, 0, pv_a, st, 0, parity);
-      if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define UPD(NV, KV) DFB_LAUNCH(c, (k_pcg_update<NV, KV>), G, 256, 0, r->d, x->d, q->d, p->d, inv, nb, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b)
-        DISPATCH_ALL(UPD)
-#undef UPD
-      } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
-      } else {
-        DFB_LAUNCH(c, k_pcg_update_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, x->d, q->d, p->d, inv, nflat, st, parity, c->d_partials, c->d_ticket + 2, pv_off, pv_b);
-      }
-      if (ilu) {
-        // the update kernel ran with M = I (r.r in red[1]); now z = M^-1 r explicitly and r.z -> red[2]
-        DFB_CUDA(cudaMemcpyAsync(zbuf, r->d, nflat * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        DFB_TRY(dfb_ilu_apply(c, pc->ilu, pc->pat, n, pc->d_inv, zbuf));
-        DFB_TRY(dfb_ilu_dot(c, r->d, zbuf, nflat, &st->red[2]));
-      }
-      if (nccl_red) DFB_TRY(dfb_nccl_allreduce_sum(c, &st->red[1], 2, c->stream));
-      if (peer) DFB_LAUNCH(c, k_peer_gather<2>, 1, 32, 0, pv_b, st, 1, parity);
-      if (kind == DFB_PRECOND_BLOCK_JACOBI) {
-#define DIR(NV, KV) DFB_LAUNCH(c, (k_pcg_direction<NV, KV>), G, 256, 0, r->d, p->d, inv, nb, st, parity, c->d_hist, c->hist_cap, pv_off)
-        DISPATCH_ALL(DIR)
-#undef DIR
-      } else if (kind == DFB_PRECOND_JACOBI) {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_JACOBI>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
-      } else if (ilu) {
-#define DIRZ(NV) \
-  if (n == NV) DFB_LAUNCH(c, (k_pcg_direction<NV, DFB_PRECOND_ILU0>), G, 256, 0, r->d, p->d, zbuf, nb, st, parity, c->d_hist, c->hist_cap, pv_off);
-        DIRZ(1) DIRZ(2) DIRZ(3) DIRZ(4)
-#undef DIRZ
-      } else {
-        DFB_LAUNCH(c, k_pcg_direction_flat<DFB_PRECOND_NONE>, GF, 256, 0, r->d, p->d, inv, nflat, st, parity, c->d_hist, c->hist_cap, pv_off);
-      }
+    const bool head = (n_chunks == 0) || c->profile_spmv > 0 || !use_graph;
+    if (head) {
+      DFB_TRY(enqueue_iteration(c, P, c->profile_spmv > 0));
+      enq += 1;
     }
-    DFB_CHECK_LAUNCH();
-    enq += todo;
+    if (use_graph && !graph_tried) {
+      // captured AFTER the first plain iteration (function attributes set, NCCL connections up, mirror packed)
+      graph_tried = true;
+      DFB_TRY(chunk_graph(c, P, &gc));
+    }
+    if (use_graph && gc) {
+      DFB_CUDA(cudaGraphLaunch(gc->exec, c->stream));
+      c->launches += gc->nodes;
+      enq += (uint64_t)P.chunk;
+    } else {
+      for (int64_t j = head ? 1 : 0; j < P.chunk; ++j) DFB_TRY(enqueue_iteration(c, P, false));
+      enq += (uint64_t)(P.chunk - (head ? 1 : 0));
+    }
     const int slot = n_chunks & 1;
-    DFB_CUDA(cudaMemcpyAsync(&hf[slot], &st->done[0], sizeof(FlagsHost), cudaMemcpyDeviceToHost, c->stream));
+    unsigned char *hs = (unsigned char *)c->h_poll + (size_t)slot * c->h_poll_slot;
+    DFB_CUDA(cudaMemcpyAsync(hs, st, sizeof(DfbSolverState), cudaMemcpyDeviceToHost, c->stream));
+    DFB_CUDA(cudaMemcpyAsync(hs + ((sizeof(DfbSolverState) + 15) & ~(size_t)15), c->d_hist, P.hist_ring * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
     DFB_CUDA(cudaEventRecord(c->ev_flag[slot], c->stream));
     ++n_chunks;
-    // look at the flags of the PREVIOUS chunk (one chunk of look-ahead keeps the GPU busy)
+    // look at the state after the PREVIOUS chunk (one chunk of look-ahead keeps the GPU busy)
     if (n_chunks >= 2) {
       const int prev = (n_chunks - 2) & 1;
       DFB_CUDA(cudaEventSynchronize(c->ev_flag[prev]));
-      last = hf[prev];
+      drain(prev);
       if (last.done[0] || last.done[1]) finished = true;
     }
-    if (enq >= max_it || todo == 0) {
-      DFB_CUDA(cudaEventSynchronize(c->ev_flag[slot]));
-      last = hf[slot];
-      finished = true;
-    }
+    if (enq >= max_it + (uint64_t)P.chunk) finished = true;  // the device stops at max_it by itself; this only ends the enqueueing
   }
+  DFB_LAUNCH(c, k_pcg_end, 1, 1, 0, st);
+  DFB_CHECK_LAUNCH();
   DFB_CUDA(cudaStreamSynchronize(c->stream));
-  {
-    const int slot = (n_chunks - 1) & 1;
-    last = hf[slot];
+  if (n_chunks > 0) {
+    if (n_chunks >= 2 && !(last.done[0] || last.done[1])) drain((n_chunks - 2) & 1);
+    drain((n_chunks - 1) & 1);
+  } else {
+    DFB_CUDA(cudaMemcpyAsync(c->h_poll, st, sizeof(DfbSolverState), cudaMemcpyDeviceToHost, c->stream));
+    DFB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(&last, c->h_poll, sizeof(DfbSolverState));
+    rr[0] = last.rr0;
   }
-  DFB_TRY(dfb_prof_flush(c, c->profile_spmv > 0 ? ((size_t)last.iter + (size_t)c->profile_spmv - 1) / (size_t)c->profile_spmv : 0));
-  if (last.err == 2) return dfb_fail(DFB_ERR_NCCL, "(p)cg: peer mailbox all-reduce timed out (a rank is missing or out of step)");
+  DFB_TRY(dfb_prof_flush(c, c->profile_spmv > 0 ? (size_t)((last.iter + P.chunk) / (P.chunk + 1)) : 0));
+  if (last.err == 2) return dfb_fail(DFB_ERR_NCCL, "(p)cg: peer exchange timed out (a rank is missing or out of step)");
   if (last.err) return dfb_fail(DFB_ERR_NOT_POSITIVE, "cg: p.Ap < 0 (assert!(pap >= T::zero()))");
 
-  // history: the device stored ||r_k||^2 for k = 0..iter
+  // history: rr[k] = ||r_k||^2 for k = 0..iter
   const uint64_t iters = (uint64_t)last.iter;
-  std::vector<double> rr(iters + 1);
-  DFB_CUDA(cudaMemcpyAsync(rr.data(), c->d_hist, (iters + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  DFB_CUDA(cudaStreamSynchronize(c->stream));
   const double rr0 = rr[0];
-  const bool converged = last.done[0] || last.done[1];
+  const bool converged = last.converged != 0;
   uint64_t nh = 0;
   auto push = [&](double v) {
     if (hist_out && nh < hist_cap) hist_out[nh] = v;
@@ -703,4 +855,14 @@ DFB_API dfb_status dfb_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, 
                            uint64_t max_it, double eps_sq, double *hist_out, uint64_t hist_cap, uint64_t *n_hist) {
   DFB_REQUIRE(m && pc, "dfb_pcg: NULL argument");
   return run_pcg(m, pc, r, x, pr, p, tol, max_it, eps_sq, 0, 1, hist_out, hist_cap, n_hist);
+}
+
+// ||r_k||^2 (k = 0..iterations) of the last (P)CG solve on this ctx, kept on the host: lets a caller size its history buffer from
+// the returned length instead of from max_it
+DFB_API dfb_status dfb_ctx_last_history_sq(dfb_ctx *c, double *out, uint64_t cap, uint64_t *n) {
+  DFB_REQUIRE(c && n, "dfb_ctx_last_history_sq: NULL argument");
+  *n = c->last_hist.size();
+  if (out)
+    for (uint64_t k = 0; k < cap && k < c->last_hist.size(); ++k) out[k] = c->last_hist[k];
+  return DFB_OK;
 }

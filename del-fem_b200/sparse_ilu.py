@@ -10,10 +10,13 @@ from .sparse_square import Matrix
 
 
 class Preconditioner:
-    def __init__(self, kind="block_jacobi"):
+    def __init__(self, kind="block_jacobi", _borrow=None, _ctx=None):
         self.kind = PRECOND[kind] if isinstance(kind, str) else kind
         self.h = None
         self.ctx = None
+        self._owned = _borrow is None
+        if _borrow is not None:  # a handle owned by another object (linearsystem.Solver.ilu)
+            self.h, self.ctx = C.c_void_p(_borrow), _ctx
 
     def initialize(self, a: Matrix):
         """initialize_ilu0-like symbolic phase (:28): allocates the inverse-diagonal storage"""
@@ -36,9 +39,9 @@ class Preconditioner:
         self.h = h
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owned", True):
             lib().dfb_precond_destroy(self.h)
-            self.h = None
+        self.h = None
 
 
 def copy_value(ilu: Preconditioner, a: Matrix):

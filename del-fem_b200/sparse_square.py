@@ -20,13 +20,17 @@ class Matrix:
 
     `row2idx`/`idx2col` live in `self.pattern`; `idx2val`/`row2val` are device buffers (download() to read)."""
 
-    def __init__(self, ctx: Ctx, pattern: Pattern, blk_dim: int):
+    def __init__(self, ctx: Ctx, pattern: Pattern, blk_dim: int, _borrow=None):
         self.ctx, self.pattern, self.blk_dim = ctx, pattern, int(blk_dim)
         self.num_blk = pattern.num_blk
+        self.halo = None
+        self._owned = _borrow is None
+        if _borrow is not None:  # a handle owned by another object (linearsystem.Solver.sparse)
+            self.h = C.c_void_p(_borrow)
+            return
         h = C.c_void_p()
         check(lib().dfb_bsr_create(ctx.h, pattern.h, self.blk_dim, C.byref(h)))
         self.h = h
-        self.halo = None
 
     @classmethod
     def from_vtx2vtx(cls, vtx2idx, idx2vtx, blk_dim, ctx: Ctx = None, convention=0):
@@ -120,9 +124,9 @@ class Matrix:
         return self
 
     def __del__(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and getattr(self, "_owned", True):
             lib().dfb_bsr_destroy(self.h)
-            self.h = None
+        self.h = None
 
 
 def set_fix_dof_to_rhs_vector(blk2rhs: Vec, blk2isfix):
@@ -130,15 +134,32 @@ def set_fix_dof_to_rhs_vector(blk2rhs: Vec, blk2isfix):
     blk2rhs.set_fixed_dof_zero(blk2isfix)
 
 
+_HIST_FIRST_GUESS = 4096
+
+
+def _history_from_sq(ctx, n_hist, pcg):
+    """history longer than the first-guess buffer: rebuild it from the library's host copy of ||r_k||^2 (k = 0..iterations)"""
+    n = C.c_uint64()
+    check(lib().dfb_ctx_last_history_sq(ctx.h, None, 0, C.byref(n)))
+    sq = np.zeros(n.value)
+    check(lib().dfb_ctx_last_history_sq(ctx.h, _ptr(sq), sq.size, C.byref(n)))
+    if pcg:
+        h = np.sqrt(sq)
+        return np.concatenate([h, h[-1:]])[:n_hist] if n_hist == sq.size + 1 else h[:n_hist]
+    return np.sqrt(sq[1:] * (1.0 / sq[0]))[:n_hist]
+
+
 def conjugate_gradient(r_vec: Vec, u_vec: Vec, ap_vec: Vec, p_vec: Vec, conv_ratio_tol, max_iteration, mat: Matrix,
                        flavour="cpu"):
     """sparse_square::conjugate_gradient (:218-261; flavour 'ls' = del-fem-ls/src/solver_sparse.rs:5-70).
     Returns the convergence history (||r_k||/||r_0||, k>=1) as a numpy array."""
-    hist = np.zeros(int(max_iteration) + 2)
+    hist = np.zeros(min(int(max_iteration) + 2, _HIST_FIRST_GUESS))
     n = C.c_uint64()
     check(lib().dfb_cg(mat.h, r_vec.h, u_vec.h, ap_vec.h, p_vec.h, float(conv_ratio_tol), int(max_iteration),
                        EPS_CPU if flavour == "cpu" else EPS_LS, 0 if flavour == "cpu" else 1, _ptr(hist), hist.size,
                        C.byref(n)))
+    if n.value > hist.size:
+        return _history_from_sq(mat.ctx, n.value, False)
     return hist[:n.value].copy()
 
 
@@ -146,8 +167,10 @@ def preconditioned_conjugate_gradient(r_vec: Vec, x_vec: Vec, pr_vec: Vec, p_vec
                                       mat: Matrix, ilu, flavour="cpu"):
     """sparse_square::preconditioned_conjugate_gradient (:264-347) generalised to N with a (block-)Jacobi
     `sparse_ilu.Preconditioner`. History = absolute ||r_k|| incl. k=0 (+1 trailing entry when max_nitr is exhausted)."""
-    hist = np.zeros(int(max_nitr) + 3)
+    hist = np.zeros(min(int(max_nitr) + 3, _HIST_FIRST_GUESS))
     n = C.c_uint64()
     check(lib().dfb_pcg(mat.h, ilu.h, r_vec.h, x_vec.h, pr_vec.h, p_vec.h, float(conv_ratio_tol), int(max_nitr),
                         EPS_CPU if flavour == "cpu" else EPS_LS, _ptr(hist), hist.size, C.byref(n)))
+    if n.value > hist.size:
+        return _history_from_sq(mat.ctx, n.value, True)
     return hist[:n.value].copy()

@@ -48,6 +48,7 @@ typedef struct dfb_plan dfb_plan;
 typedef struct dfb_precond dfb_precond;
 typedef struct dfb_halo dfb_halo;
 typedef struct dfb_bcflag dfb_bcflag;
+typedef struct dfb_solver dfb_solver;
 
 /* element kinds (kernel = reference function it batches) */
 enum {
@@ -82,8 +83,9 @@ dfb_status dfb_ctx_sync(dfb_ctx *ctx);
 /* number of CUDA kernels this ctx has launched so far (graph replays count their kernel nodes) */
 dfb_status dfb_ctx_launch_count(dfb_ctx *ctx, uint64_t *out);
 /* tuning knobs: "spmv_variant" (20 = tile-packed mirror, one TMA bulk copy per 8-row tile [default]; 4 = TMA ring over the
-   canonical arrays, no extra memory; 0 row-per-thread, 1 warp-tile cp.async, 2 warp-tile TMA, 3..17 experiments, see
-   profiles/README.md), "iters_per_sync" (PCG iterations between convergence polls), "profile_spmv" */
+   canonical arrays, no extra memory; 0 = row per thread), "iters_per_sync" (PCG iterations per chunk = per CUDA-graph replay and
+   per convergence poll), "use_graph" (1 [default]: replay chunks as a CUDA graph), "profile_spmv", "assemble_variant",
+   "use_peer_allreduce", "use_peer_halo", "peer_halo_bytes" */
 dfb_status dfb_ctx_set_option(dfb_ctx *ctx, const char *key, int64_t value);
 dfb_status dfb_ctx_get_option(dfb_ctx *ctx, const char *key, int64_t *value);
 /* CUDA-event timing on the ctx stream (events are recorded on the stream the kernels are launched on) */
@@ -160,6 +162,7 @@ dfb_status dfb_pattern_download(const dfb_pattern *p, uint64_t *row2idx, uint64_
  * sparse_square::Matrix<[T;NN]> (del-fem-cpu/src/sparse_square.rs:75-214) and del-fem-ls Matrix<MAT>. */
 dfb_status dfb_bsr_create(dfb_ctx *ctx, dfb_pattern *pattern, int32_t blk_dim, dfb_bsr **out);
 dfb_status dfb_bsr_destroy(dfb_bsr *m);
+dfb_pattern *dfb_bsr_pattern(const dfb_bsr *m); /* borrowed: the row2idx / idx2col the matrix was created on (pub fields :76-78) */
 dfb_status dfb_bsr_set_zero(dfb_bsr *m);                                       /* Matrix::set_zero :174 */
 dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2val);
 dfb_status dfb_bsr_download(const dfb_bsr *m, double *row2val, double *idx2val);
@@ -239,6 +242,40 @@ dfb_status dfb_cg(const dfb_bsr *m, dfb_vec *r, dfb_vec *u, dfb_vec *ap, dfb_vec
    del-fem-ls/src/solver_sparse.rs:73-175.  History = absolute ||r_k|| incl. k=0, +1 trailing entry if max_it exhausted. */
 dfb_status dfb_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, dfb_vec *x, dfb_vec *pr, dfb_vec *p, double tol,
                    uint64_t max_it, double eps_sq, double *hist_out, uint64_t hist_cap, uint64_t *n_hist);
+
+/* ------------------------------------------------------------------------------------------------ linearsystem::Solver
+ * del-fem-ls/src/linearsystem.rs:8-112, one entry point per method. The solver owns sparse / ilu / r_vec / u_vec / ap_vec / p_vec /
+ * conv / conv_ratio_tol (1e-5f) / max_num_iteration (100); the accessors return BORROWED handles (valid until the next
+ * dfb_solver_initialize / dfb_solver_destroy) on which the caller merges and applies BCs between begin_merge and end_merge, exactly
+ * as reference code works on `solver.sparse` and `solver.r_vec`. Generalised from scalar T to blk_dim 1..4. */
+dfb_status dfb_solver_new(dfb_ctx *ctx, int32_t blk_dim, dfb_solver **out);               /* Solver::new         :33 */
+/* Solver::initialize(colind, rowptr) :48 — the reference's parameter NAMES are swapped relative to their meaning: `colind` is the
+   row-pointer array (colind_len = num_blk + 1), `rowptr` the column indices. Sets up ILU(0) like :53 (initialize_ilu0). */
+dfb_status dfb_solver_initialize(dfb_solver *s, const uint64_t *colind, uint64_t colind_len, const uint64_t *rowptr, uint64_t rowptr_len);
+/* the alternatives the reference keeps commented out at :50,:54-56 (ILU(k): kind = DFB_PRECOND_ILU0 with lev_fill > 0) and the
+   DERIVED Jacobi kinds; takes effect immediately if the solver is initialised, else at dfb_solver_initialize */
+dfb_status dfb_solver_set_preconditioner(dfb_solver *s, int32_t kind, uint64_t lev_fill);
+dfb_status dfb_solver_begin_merge(dfb_solver *s);                                          /* Solver::begin_merge :60 */
+dfb_status dfb_solver_end_merge(dfb_solver *s);                                            /* Solver::end_merge   :67 */
+dfb_status dfb_solver_solve_cg(dfb_solver *s);   /* Solver::solve_cg :73  (del-fem-ls/src/solver_sparse.rs:5-70; DFB_ERR_NOT_POSITIVE = assert!(pap >= 0)) */
+dfb_status dfb_solver_solve_pcg(dfb_solver *s);  /* Solver::solve_pcg :85 (solver_sparse.rs:73-175 with self.ilu) */
+/* Solver::clone :96-111 — deep copy of every field (decomposed ILU values included), max_num_iteration RESET to 100 like :109 */
+dfb_status dfb_solver_clone(const dfb_solver *s, dfb_solver **out);
+dfb_status dfb_solver_destroy(dfb_solver *s);
+dfb_bsr *dfb_solver_sparse(dfb_solver *s);       /* pub sparse :9  */
+dfb_precond *dfb_solver_ilu(dfb_solver *s);      /* pub ilu    :10 */
+dfb_vec *dfb_solver_r_vec(dfb_solver *s);        /* pub r_vec  :12 */
+dfb_vec *dfb_solver_u_vec(dfb_solver *s);        /* pub u_vec  :13 */
+dfb_vec *dfb_solver_ap_vec(dfb_solver *s);       /* pub ap_vec :17 */
+dfb_vec *dfb_solver_p_vec(dfb_solver *s);        /* pub p_vec  :18 */
+dfb_status dfb_solver_set_params(dfb_solver *s, double conv_ratio_tol, uint64_t max_num_iteration); /* pub conv_ratio_tol :15, max_num_iteration :16 */
+dfb_status dfb_solver_get_params(const dfb_solver *s, double *conv_ratio_tol, uint64_t *max_num_iteration);
+dfb_status dfb_solver_conv(const dfb_solver *s, double *out, uint64_t cap, uint64_t *n);   /* pub conv :14 (*n = conv.len()) */
+
+/* ||r_k||^2 for k = 0..iterations of the LAST dfb_cg / dfb_pcg on this ctx (host copy kept by the library; the device only holds a
+   ring of the last two chunks). *n = iterations + 1 even if it exceeds cap. Lets a caller size its history buffer from the actual
+   iteration count instead of from max_it (the reference's Vec grows per iteration, sparse_square.rs:254). */
+dfb_status dfb_ctx_last_history_sq(dfb_ctx *ctx, double *out, uint64_t cap, uint64_t *n);
 
 /* ------------------------------------------------------------------------------------------------ multi-GPU
  * Vertex-partitioned subdomains, one rank (process) per GPU.  No reference precedent: the contract is

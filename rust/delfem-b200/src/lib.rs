@@ -221,47 +221,51 @@ pub fn preconditioned_conjugate_gradient<const N: usize, const NN: usize>(
     hist
 }
 
-/// `del_fem_ls::linearsystem::Solver` (del-fem-ls/src/linearsystem.rs:8-112) for block size N: same lifecycle
-/// (`initialize` -> `begin_merge` -> merges -> `end_merge` -> `solve_cg` / `solve_pcg`), same defaults (tol 1e-5, 100 iterations).
-pub struct Solver<const N: usize, const NN: usize> {
-    pub sparse: Matrix<N, NN>,
-    pub ilu: sparse_ilu::Preconditioner<N, NN>,
-    pub r_vec: DevVec<N>,
-    pub u_vec: DevVec<N>,
-    ap_vec: DevVec<N>,
-    p_vec: DevVec<N>,
-    pub conv: Vec<f64>,
-    pub conv_ratio_tol: f64,
-    pub max_num_iteration: usize,
+/// `del_fem_ls::linearsystem::Solver` (del-fem-ls/src/linearsystem.rs:8-112) for block size N over `dfb_solver_*`: same
+/// lifecycle (`initialize` -> `begin_merge` -> merges -> `end_merge` -> `solve_cg` / `solve_pcg`), same defaults (tol 1e-5f32,
+/// 100 iterations, ILU(0) set up by `initialize` as :53), `clone` resets `max_num_iteration` to 100 as :109 does.
+/// `sparse()`, `r_vec()`, `u_vec()`, `ilu()` are the reference's pub fields as handles BORROWED from the solver.
+pub struct Solver<const N: usize> { h: *mut sys::dfb_solver, pub conv: Vec<f64> }
+impl<const N: usize> Solver<N> {
+    /// `Solver::new` (:33)
+    pub fn new(ctx: &Ctx) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::dfb_solver_new(ctx.0, N as i32, &mut h) });
+        Solver { h, conv: Vec::new() }
+    }
+    /// `initialize(colind, rowptr)` (:48): first slice = row pointer, second = column indices (names swapped upstream)
+    pub fn initialize(&mut self, colind: &[usize], rowptr: &[usize]) {
+        check(unsafe { sys::dfb_solver_initialize(self.h, colind.as_ptr() as *const u64, colind.len() as u64,
+                                                  rowptr.as_ptr() as *const u64, rowptr.len() as u64) });
+    }
+    pub fn begin_merge(&mut self) { check(unsafe { sys::dfb_solver_begin_merge(self.h) }); }   // :60
+    pub fn end_merge(&mut self) { check(unsafe { sys::dfb_solver_end_merge(self.h) }); }       // :67
+    pub fn solve_cg(&mut self) { check(unsafe { sys::dfb_solver_solve_cg(self.h) }); self.fetch_conv(); }    // :73
+    pub fn solve_pcg(&mut self) { check(unsafe { sys::dfb_solver_solve_pcg(self.h) }); self.fetch_conv(); }  // :85
+    pub fn sparse(&self) -> *mut sys::dfb_bsr { unsafe { sys::dfb_solver_sparse(self.h) } }
+    pub fn ilu(&self) -> *mut sys::dfb_precond { unsafe { sys::dfb_solver_ilu(self.h) } }
+    pub fn r_vec(&self) -> *mut sys::dfb_vec { unsafe { sys::dfb_solver_r_vec(self.h) } }
+    pub fn u_vec(&self) -> *mut sys::dfb_vec { unsafe { sys::dfb_solver_u_vec(self.h) } }
+    pub fn set_params(&mut self, conv_ratio_tol: f64, max_num_iteration: usize) {
+        check(unsafe { sys::dfb_solver_set_params(self.h, conv_ratio_tol, max_num_iteration as u64) });
+    }
+    fn fetch_conv(&mut self) {
+        let mut n = 0u64;
+        check(unsafe { sys::dfb_solver_conv(self.h, std::ptr::null_mut(), 0, &mut n) });
+        self.conv = vec![0.0; n as usize];
+        check(unsafe { sys::dfb_solver_conv(self.h, self.conv.as_mut_ptr(), n, &mut n) });
+    }
 }
-impl<const N: usize, const NN: usize> Solver<N, NN> {
-    /// `Solver::new` + `initialize(colind, rowptr)` (:33-57)
-    pub fn initialize(ctx: &Ctx, colind: &[usize], rowptr: &[usize]) -> Self {
-        let sparse = Matrix::<N, NN>::from_vtx2vtx(ctx, colind, rowptr);
-        let nblk = sparse.num_blk;
-        let mut ilu = sparse_ilu::Preconditioner::new();
-        ilu.initialize_ilu0(ctx, &sparse);
-        Solver { sparse, ilu, r_vec: DevVec::zeros(ctx, nblk), u_vec: DevVec::zeros(ctx, nblk), ap_vec: DevVec::zeros(ctx, nblk),
-                 p_vec: DevVec::zeros(ctx, nblk), conv: Vec::new(), conv_ratio_tol: 1.0e-5, max_num_iteration: 100 }
+impl<const N: usize> Clone for Solver<N> {
+    /// `Solver::clone` (:96-111)
+    fn clone(&self) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::dfb_solver_clone(self.h, &mut h) });
+        let mut t = Solver { h, conv: Vec::new() };
+        t.fetch_conv();
+        t
     }
-    /// `begin_merge` (:59-62)
-    pub fn begin_merge(&mut self) {
-        self.sparse.set_zero();
-        check(unsafe { sys::dfb_vec_set_zero(self.r_vec.h) });
-    }
-    /// `end_merge` (:64-68): copy_value + decompose
-    pub fn end_merge(&mut self) {
-        sparse_ilu::copy_value(&mut self.ilu, &self.sparse);
-        sparse_ilu::decompose(&mut self.ilu);
-    }
-    /// `solve_cg` (:70-82)
-    pub fn solve_cg(&mut self) {
-        self.conv = conjugate_gradient(&mut self.r_vec, &mut self.u_vec, &mut self.ap_vec, &mut self.p_vec, self.conv_ratio_tol,
-                                       self.max_num_iteration, &self.sparse);
-    }
-    /// `solve_pcg` (:84-96)
-    pub fn solve_pcg(&mut self) {
-        self.conv = preconditioned_conjugate_gradient(&mut self.r_vec, &mut self.u_vec, &mut self.ap_vec, &mut self.p_vec,
-                                                      self.conv_ratio_tol, self.max_num_iteration, &self.sparse, &self.ilu);
-    }
+}
+impl<const N: usize> Drop for Solver<N> {
+    fn drop(&mut self) { unsafe { sys::dfb_solver_destroy(self.h) }; }
 }

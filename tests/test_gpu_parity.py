@@ -13,7 +13,7 @@ from helpers import device_elasticity_problem, flags_z0, oracle_elasticity_probl
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 20]
+VARIANTS = [0, 4, 20]
 
 
 # ------------------------------------------------------------------------------------------------ mesh / pattern / plan

@@ -692,3 +692,96 @@ def test_ls_mult_square_matrices_matches_oracle(dfb, ctx, orc):
     assert rel_err(y2.download(), y1.download()) < 1e-12
     with pytest.raises(dfb.DfbError):
         dfb.Matrix.from_vtx2vtx(r2i, i2c, 3, ctx=ctx).mult_square_matrices(b)
+
+
+def test_linearsystem_solver_facade_through_c_abi(dfb, ctx, orc):
+    """A14: `linearsystem::Solver` (del-fem-ls/src/linearsystem.rs:33-112) through dfb_solver_*: the reference's solid_linear_tri2
+    flow (solid_linear_tri2.rs:207-303) — initialize -> begin_merge -> merge on `sparse` / rhs on `r_vec` -> BCs -> end_merge ->
+    solve_cg / solve_pcg — with the reference's defaults (1e-5 as f32, 100 iterations, ILU(0) from `initialize` :53), its bounds
+    (ILU(0)-PCG < 36 history entries, :314-317), history identical to the oracle's ls-flavoured solvers, and `clone` (:96-111)
+    resetting max_num_iteration to 100 while copying everything else (decomposed ILU included)."""
+    import test_oracle_pins as T
+    from del_fem_b200 import linearsystem
+    p = T.unit_square_problem(orc)
+    g = p["g"]
+    r2i, i2c, nv = p["r2i"], p["i2c"], p["nv"]
+    rhs = np.zeros_like(p["u"])
+    orc.mult_vec(rhs, 0.0, -1.0, p["u"], r2i, i2c, p["iv"], p["rv"])
+    orc.set_fix_dof_to_rhs_vector(rhs, p["flag"])
+    rv, iv = p["rv"].copy(), p["iv"].copy()
+    orc.set_fixed_bc(1.0, p["flag"], rv, iv, r2i, i2c)
+
+    s = linearsystem.Solver(ctx, blk_dim=2)
+    assert s.conv_ratio_tol == float(np.float32(1.0e-5)) and s.max_num_iteration == 100 and s.sparse is None
+    s.initialize(r2i, i2c)                       # (colind, rowptr): positional meaning = (row pointer, column indices)
+    assert s.sparse.num_blk == nv and s.sparse.pattern.nnz == i2c.size
+    mesh = dfb.Mesh(ctx, p["t2v"], p["xy"])
+    plan = dfb.Plan(ctx, s.sparse.pattern, mesh, 0)
+
+    def merge_and_bc():
+        s.begin_merge()
+        rv0, iv0 = s.sparse.download()
+        assert not rv0.any() and not iv0.any() and not s.r_vec.download().any()
+        s.sparse.assemble(plan, "solid_linear_tri2", mesh, g["lambda"], g["myu"])   # the element loop + merge on solver.sparse
+        s.r_vec.upload(rhs)
+        s.sparse.set_fixed_dof(1.0, p["flag"])
+        s.end_merge()
+
+    merge_and_bc()
+    rv_d, iv_d = s.sparse.download()
+    assert np.array_equal(rv_d, rv) and np.array_equal(iv_d, iv)
+    # solve_cg == the oracle's ls flavour (eps 1e-20, assert pap >= 0), same history
+    s.solve_cg()
+    ro = rhs.copy()
+    uo, apo, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+    hist_o = orc.conjugate_gradient(ro, uo, apo, po, s.conv_ratio_tol, 100, r2i, i2c, iv, rv, flavour="ls")
+    assert abs(len(s.conv) - len(hist_o)) <= 1 and len(s.conv) <= 100
+    m = min(len(s.conv), len(hist_o)) // 2
+    assert np.allclose(s.conv[:m], hist_o[:m], rtol=1e-6)
+    if len(hist_o) < 100:
+        assert rel_err(s.u_vec.download(), uo) < 1e-4
+    # solve_pcg with the ILU(0) `initialize` set up; reference bound < 36
+    merge_and_bc()
+    s.solve_pcg()
+    ilu_o = orc.Ilu("ilu0", 2, r2i, i2c)
+    ilu_o.copy_value(r2i, i2c, iv, rv)
+    ilu_o.decompose()
+    ro = rhs.copy()
+    xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+    hist_p = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, s.conv_ratio_tol, 100, r2i, i2c, iv, rv, ilu_o, flavour="ls")
+    assert len(s.conv) < g["bounds"]["ilu0_iters_lt"]
+    assert abs(len(s.conv) - len(hist_p)) <= 1
+    assert np.allclose(s.conv[: len(s.conv) // 2], hist_p[: len(s.conv) // 2], rtol=1e-6)
+    u_pcg = s.u_vec.download()
+    assert rel_err(u_pcg, xo) < 1e-5
+    # clone: everything copied, max_num_iteration reset to 100 (:109)
+    s.max_num_iteration = 57
+    s.conv_ratio_tol = 1e-7
+    c = s.clone()
+    assert c.max_num_iteration == 100 and c.conv_ratio_tol == 1e-7 and s.max_num_iteration == 57
+    assert np.array_equal(c.conv, s.conv)
+    rv_c, iv_c = c.sparse.download()
+    assert np.array_equal(rv_c, rv) and np.array_equal(iv_c, iv)
+    assert np.array_equal(c.u_vec.download(), u_pcg)
+    c.r_vec.upload(rhs)
+    c.conv_ratio_tol = s.conv_ratio_tol = float(np.float32(1.0e-5))
+    c.solve_pcg()                                # uses the CLONED decomposed ILU: no end_merge on the clone
+    s.max_num_iteration = 100
+    s.r_vec.upload(rhs)
+    s.solve_pcg()
+    assert np.array_equal(c.conv, s.conv) and np.array_equal(c.u_vec.download(), s.u_vec.download())
+    # the commented-out alternative at :55 (initialize_iluk with a huge level = complete LU): history length 2 (solid_linear_tri2.rs:318-321)
+    s.set_preconditioner("ilu0", 10000)
+    merge_and_bc()
+    s.solve_pcg()
+    assert len(s.conv) == 2
+    # solve_pcg before end_merge is an error, not garbage
+    t = linearsystem.Solver(ctx, blk_dim=1)
+    t.initialize(np.array([0, 1, 3, 4], dtype=np.uint64), np.array([1, 0, 2, 1], dtype=np.uint64))
+    with pytest.raises(dfb.DfbError):
+        t.solve_pcg()
+    # del-fem-ls's own 4-row smoke pattern (sparse_square.rs:169-170) carries explicit diagonal columns: Matrix accepts it, but
+    # Solver::initialize runs initialize_ilu0, whose assert (sparse_ilu.rs:199) rejects it — same here
+    with pytest.raises(dfb.DfbError) as ei:
+        t.initialize(np.array([0, 2, 5, 8, 10], dtype=np.uint64), np.array([0, 1, 0, 1, 2, 1, 2, 3, 2, 3], dtype=np.uint64))
+    assert ei.value.status == dfb.STATUS["BAD_ARG"]
