@@ -161,6 +161,8 @@ def lib():
         "dfb_halo_set_remote": [_vp, _vp],
         "dfb_bsr_set_halo": [_vp, _vp, _u64, _u64],
         "dfb_bsr_pattern": [_vp],
+        "dfb_bsr_pack": [_vp],
+        "dfb_ctx_phase_times": [_vp, _vp, _vp, _i32],
         "dfb_ctx_last_history_sq": [_vp, _vp, _u64, C.POINTER(_u64)],
         "dfb_solver_new": [_vp, _i32, _pp],
         "dfb_solver_initialize": [_vp, _vp, _u64, _vp, _u64],

@@ -69,24 +69,42 @@ class MassSpringCloth:
         self.g, self.u, self.ap, self.p = (Vec(ctx, nv, 3) for _ in range(4))
         self.log = []
 
-    def step(self, dt, conv_ratio=1e-5, max_it=1000):
-        """one implicit-Euler step; returns (energy at the predictor, CG iterations)"""
+    def step(self, dt, conv_ratio=1e-5, max_it=1000, timing=None):
+        """one implicit-Euler step; returns (energy at the predictor, CG iterations). `timing` (dict) accumulates device ms per
+        phase (CUDA events on the ctx stream, one synchronisation per phase): assemble / diag_bc / pack / cg / update"""
+        ctx = self.ctx
+
+        def lap(key):
+            if timing is not None:
+                timing[key] = timing.get(key, 0.0) + ctx.timer_stop()
+                ctx.timer_start()
+
+        if timing is not None:
+            ctx.timer_start()
         # x_tmp = x + dt v on free dofs (fixed dofs keep v = 0)
         self.vel.set_fixed_dof_zero_dev(self.flag)
         self.disp_tmp.copy_from(self.disp)
         self.disp_tmp.add_scaled(dt, self.vel)
+        lap("update")
         w = elements.assemble_energy(self.plan, "spring3", self.mesh, self.disp_tmp, self.k, 0.0, self.mat, self.g)
+        lap("assemble")
         self.g.add_scaled(-1.0, self.f)                               # dW - f
         self.mat.add_to_diagonal(1.0 / (dt * dt), self.mass)          # inertia (:1219-1226)
         self.g.set_fixed_dof_zero_dev(self.flag)                      # set_fix_dof_to_rhs_vector (:1228)
         self.mat.set_fixed_dof_dev(1.0, self.flag)                    # set_fixed_dof (:1229)
+        lap("diag_bc")
+        if timing is not None:
+            self.mat.pack()
+            lap("pack")
         hist = sparse_square.conjugate_gradient(self.g, self.u, self.ap, self.p, conv_ratio, max_it, self.mat)  # (:1235)
+        lap("cg")
         self.disp_tmp.add_scaled(-1.0, self.u)                        # update_solution (x_tmp -= u)
         # v = (x_tmp - x) / dt ; x = x_tmp
         self.vel.copy_from(self.disp_tmp)
         self.vel.add_scaled(-1.0, self.disp)
         self.vel.scale(1.0 / dt)
         self.disp.copy_from(self.disp_tmp)
+        lap("update")
         self.log.append((w, len(hist)))
         return w, len(hist)
 

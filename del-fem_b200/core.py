@@ -84,6 +84,15 @@ class Ctx:
         check(lib().dfb_profile_spmv(self.h, C.byref(ms), C.byref(n), 1 if reset else 0))
         return ms.value, n.value
 
+    PHASES = ("elem", "gather", "grad", "pack", "tile", "bc", "precond", "unused")
+
+    def phase_times(self, reset=False):
+        """{phase: (total_ms, count)} of the library's own assembly / setup launches while option profile_phases = 1"""
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.uint64)
+        check(lib().dfb_ctx_phase_times(self.h, _ptr(ms), _ptr(cnt), 1 if reset else 0))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PHASES)}
+
     def comm_init(self, uid: bytes, rank: int, nranks: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         check(lib().dfb_ctx_comm_init(self.h, buf, rank, nranks))

@@ -822,7 +822,10 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     }
 #define REC_CASE(K)                                                                                                                   \
   case K:                                                                                                                             \
+    dfb_phase_begin(c, DFB_PH_ELEM);                                                                                                  \
     DFB_LAUNCH(c, k_node_recs<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (NodeRec *)plan->d_geo); \
+    dfb_phase_end(c);                                                                                                                 \
+    dfb_phase_begin(c, DFB_PH_GATHER);                                                                                                \
     if (rows_path) {                                                                                                                  \
       SrcRecs<K> src;                                                                                                                 \
       src.recs = (const NodeRec *)plan->d_geo;                                                                                        \
@@ -833,6 +836,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
       DFB_LAUNCH(c, k_assemble_recs<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                     \
                  (const NodeRec *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                                   \
     }                                                                                                                                 \
+    dfb_phase_end(c);                                                                                                                 \
     break;
     switch (kind) {
       REC_CASE(DFB_ELEM_LAPLACE_TRI2)
@@ -1444,11 +1448,20 @@ DFB_API dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_m
   dfb_ctx *c = plan->ctx;
   const uint64_t nn = (uint64_t)info.n_node;
   double *d_emat = nullptr, *d_evec = nullptr, *d_w = nullptr;
-  DFB_TRY(dfb_dev_alloc_t(&d_emat, mesh->num_elem * nn * nn * 9));
-  DFB_TRY(dfb_dev_alloc_t(&d_evec, mesh->num_elem * nn * 3));
-  DFB_TRY(dfb_dev_alloc_t(&d_w, mesh->num_elem));
-  dfb_status st = dfb_emat_batch(c, kind, mesh, p0, p1, disp, d_emat, d_evec, d_w);
-  if (st == DFB_OK) st = dfb_assemble_from_emat(plan, d_emat, m);
+  dfb_status st = dfb_dev_alloc_t(&d_emat, mesh->num_elem * nn * nn * 9);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_evec, mesh->num_elem * nn * 3);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_w, mesh->num_elem);
+  if (st == DFB_OK) {
+    dfb_phase_begin(c, DFB_PH_ELEM);
+    st = dfb_emat_batch(c, kind, mesh, p0, p1, disp, d_emat, d_evec, d_w);
+    dfb_phase_end(c);
+  }
+  if (st == DFB_OK) {
+    dfb_phase_begin(c, DFB_PH_GATHER);
+    st = dfb_assemble_from_emat(plan, d_emat, m);
+    dfb_phase_end(c);
+  }
+  dfb_phase_begin(c, DFB_PH_GRAD);
   if (st == DFB_OK && dw) {
     DFB_LAUNCH(c, k_gather_evec, c->sm_count * 8, 128, 0, plan->d_nz2ptr, plan->d_contrib, plan->pat->nnz, plan->pat->num_blk, info.n_node, 3,
                d_evec, dw->d);
@@ -1460,6 +1473,7 @@ DFB_API dfb_status dfb_assemble_energy(dfb_plan *plan, int32_t kind, const dfb_m
     DFB_LAUNCH(c, k_sum, (unsigned)g, 256, 0, d_w, mesh->num_elem, c->d_partials, c->d_ticket + 3, c->d_scratch + 8);
     cudaMemcpyAsync(c->h_pinned, c->d_scratch + 8, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   }
+  dfb_phase_end(c);
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (st == DFB_OK && e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_assemble_energy: %s", cudaGetErrorString(e));
   if (st == DFB_OK && w) *w = *(double *)c->h_pinned;

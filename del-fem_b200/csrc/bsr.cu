@@ -157,12 +157,14 @@ static dfb_status launch_set_fixed_bc(dfb_bsr *m, double val_dia, const int32_t 
   dfb_ctx *c = m->ctx;
   m->packed_valid = 0;
   const int grid = c->sm_count * 8;
+  dfb_phase_begin(c, DFB_PH_BC);
   switch (m->blk_dim) {
     case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
     case 2: DFB_LAUNCH(c, k_set_fixed_bc<2>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
     case 3: DFB_LAUNCH(c, k_set_fixed_bc<3>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
     case 4: DFB_LAUNCH(c, k_set_fixed_bc<4>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
   }
+  dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -818,8 +820,10 @@ static dfb_status bsr_pack(dfb_bsr *m, cudaStream_t strm) {
     DFB_TRY(dfb_dev_alloc((void **)&m->d_packed, m->packed_cap));
   }
   if (n_tiles > 0) {
+    dfb_phase_begin(c, DFB_PH_PACK, strm);
     DFB_LAUNCH_ON(c, strm, k_pack_tiles, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val, n,
                   n_tiles, NN, m->d_tile_off, m->d_packed);
+    dfb_phase_end(c, strm);
     DFB_CHECK_LAUNCH();
   }
   m->packed_valid = 1;
@@ -917,6 +921,11 @@ dfb_status dfb_bsr_ensure_packed(const dfb_bsr *m) {
   dfb_bsr *mm = const_cast<dfb_bsr *>(m);
   if (m->ctx->spmv_variant == 20 && !mm->packed_valid) DFB_TRY(bsr_pack(mm, m->ctx->stream));
   return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_pack(dfb_bsr *m) {
+  DFB_REQUIRE(m, "dfb_bsr_pack: NULL argument");
+  return dfb_bsr_ensure_packed(m);
 }
 
 static uint64_t halo_recv_total(const dfb_bsr *m) { return (m->halo && !m->halo->recv_ptr.empty()) ? m->halo->recv_ptr.back() : 0; }

@@ -127,6 +127,7 @@ DFB_API dfb_status dfb_ctx_destroy(dfb_ctx *c) {
   dfb_dev_free(c->flush_buf);
   cudaFreeHost(c->h_pinned);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->phase_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_t0);
   cudaEventDestroy(c->ev_t1);
   cudaEventDestroy(c->ev_a);
@@ -160,6 +161,7 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "assemble_variant")) return &c->assemble_variant;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
+  if (!strcmp(key, "profile_phases")) return &c->profile_phases;
   if (!strcmp(key, "use_peer_allreduce")) return &c->use_peer_allreduce;
   if (!strcmp(key, "use_peer_halo")) return &c->use_peer_halo;
   if (!strcmp(key, "peer_halo_bytes")) return &c->peer_halo_bytes;
@@ -279,6 +281,50 @@ void dfb_prof_end(dfb_ctx *c) {
 }
 // the solvers enqueue iterations ahead of the convergence test: only the first `max_pairs` recorded launches did real work
 dfb_status dfb_prof_flush(dfb_ctx *c, size_t max_pairs) { return prof_collect(c, max_pairs); }
+
+// ---- phase profiler: dfb_phase_begin/_end bracket a group of launches with events when option "profile_phases" is set
+void dfb_phase_begin(dfb_ctx *c, int id, cudaStream_t strm) {
+  if (!c->profile_phases) return;
+  if (c->phase_used + 2 > 65536) return;
+  while (c->phase_ev.size() < c->phase_used + 2) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c->phase_ev.push_back(e);
+  }
+  if (c->phase_id.size() < c->phase_ev.size() / 2) c->phase_id.resize(c->phase_ev.size() / 2, 0);
+  c->phase_id[c->phase_used / 2] = id;
+  cudaEventRecord(c->phase_ev[c->phase_used], strm ? strm : c->stream);
+  c->phase_used += 1;
+}
+void dfb_phase_end(dfb_ctx *c, cudaStream_t strm) {
+  if (!c->profile_phases || (c->phase_used & 1) == 0) return;
+  cudaEventRecord(c->phase_ev[c->phase_used], strm ? strm : c->stream);
+  c->phase_used += 1;
+}
+
+DFB_API dfb_status dfb_ctx_phase_times(dfb_ctx *c, double *ms_out, uint64_t *count_out, int32_t reset) {
+  DFB_REQUIRE(c, "dfb_ctx_phase_times: ctx is NULL");
+  if (c->phase_used) {
+    DFB_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->phase_used; i += 2) {
+      float ms = 0.f;
+      DFB_CUDA(cudaEventElapsedTime(&ms, c->phase_ev[i], c->phase_ev[i + 1]));
+      const int id = c->phase_id[i / 2];
+      c->phase_ms[id] += ms;
+      c->phase_count[id] += 1;
+    }
+    c->phase_used = 0;
+  }
+  for (int k = 0; k < DFB_N_PHASES; ++k) {
+    if (ms_out) ms_out[k] = c->phase_ms[k];
+    if (count_out) count_out[k] = c->phase_count[k];
+    if (reset) {
+      c->phase_ms[k] = 0.0;
+      c->phase_count[k] = 0;
+    }
+  }
+  return DFB_OK;
+}
 
 DFB_API dfb_status dfb_malloc(dfb_ctx *c, uint64_t bytes, void **dev_ptr) {
   DFB_REQUIRE(c && dev_ptr, "dfb_malloc: NULL argument");

@@ -77,6 +77,19 @@ __host__ __device__ inline unsigned long long dfb_xid_pq(unsigned long long xbas
 __host__ __device__ inline unsigned long long dfb_xid_rr(unsigned long long xbase, int it) { return xbase + 3ull + 2ull * (unsigned long long)it; }
 __host__ __device__ inline unsigned long long dfb_hid(unsigned long long hbase, int it) { return hbase + 1ull + (unsigned long long)it; }
 
+// phases of the assembly / setup path that the library can time itself (CUDA events around its own launches)
+enum { DFB_PH_ELEM = 0,      // element kernels (two-phase path: dfb_emat_batch / node records)
+       DFB_PH_GATHER = 1,    // merge: gather of element matrices / node records into the matrix values
+       DFB_PH_GRAD = 2,      // gradient gather + energy sum of the energy models
+       DFB_PH_PACK = 3,      // (re)build of the tile-packed SpMV mirror
+       DFB_PH_TILE = 4,      // fused row-tile assembly (element kernel + merge in one launch)
+       DFB_PH_BC = 5,        // Dirichlet rows/columns
+       DFB_PH_PRECOND = 6,   // preconditioner update
+       DFB_N_PHASES = 8 };
+struct dfb_ctx;
+void dfb_phase_begin(dfb_ctx *c, int id, cudaStream_t strm = nullptr);
+void dfb_phase_end(dfb_ctx *c, cudaStream_t strm = nullptr);
+
 struct dfb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;   // main stream
@@ -116,6 +129,13 @@ struct dfb_ctx {
   size_t prof_used = 0;
   double prof_ms = 0.0;
   uint64_t prof_count = 0;
+  // phase profiling (option "profile_phases"): event pairs per phase id on the launching stream, folded lazily
+  int64_t profile_phases = 0;
+  std::vector<cudaEvent_t> phase_ev;   // pairs
+  std::vector<int> phase_id;           // one per pair
+  size_t phase_used = 0;               // events used
+  double phase_ms[DFB_N_PHASES] = {};
+  uint64_t phase_count[DFB_N_PHASES] = {};
   // multi-GPU
   void *nccl_comm = nullptr;
   int rank = 0, nranks = 1;

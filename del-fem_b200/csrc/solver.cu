@@ -163,6 +163,7 @@ DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {
     return dfb_ilu_update(c, pc->ilu, m, pc->d_inv);
   }
   const int grid = c->sm_count * 8;
+  dfb_phase_begin(c, DFB_PH_PRECOND);
 #define PC_CASE(NV)                                                                                                       \
   case NV:                                                                                                                \
     DFB_LAUNCH(c, k_precond_update<NV>, grid, 128, 0, pc->kind, pc->num_blk, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, \
@@ -175,6 +176,7 @@ DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {
     PC_CASE(4)
   }
 #undef PC_CASE
+  dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "dfb_precond_update: singular (or missing) diagonal block (try_inverse().unwrap())");
 }

@@ -31,17 +31,35 @@ class NeoHookeanTetNewton:
     def set_load(self, f_host):
         self.f.upload(f_host)
 
-    def step(self, load_scale=1.0, pcg_tol=1e-8, pcg_max=5000):
-        """one Newton iteration; returns (energy W, ||dW - s f|| over free dofs, PCG iterations)"""
+    def step(self, load_scale=1.0, pcg_tol=1e-8, pcg_max=5000, timing=None):
+        """one Newton iteration; returns (energy W, ||dW - s f|| over free dofs, PCG iterations). `timing` (dict) accumulates
+        device ms per phase (CUDA events on the ctx stream): assemble / rhs_bc / precond / pack / pcg / update"""
+        ctx = self.ctx
+
+        def lap(key):
+            if timing is not None:
+                timing[key] = timing.get(key, 0.0) + ctx.timer_stop()
+                ctx.timer_start()
+
+        if timing is not None:
+            ctx.timer_start()
         w = elements.assemble_neohookean_tet(self.plan, self.mesh, self.u, self.myu, self.lam, self.mat, self.g)
+        lap("assemble")
         self.g.add_scaled(-float(load_scale), self.f)          # g = dW - s f
         self.g.set_fixed_dof_zero_dev(self.flag)               # set_fix_dof_to_rhs_vector
         gnorm = float(np.sqrt(self.g.dot(self.g)))
         self.mat.set_fixed_dof_dev(1.0, self.flag)              # set_fixed_dof::<3>(1.0, ...)
+        lap("rhs_bc")
         sparse_ilu.copy_value(self.pc, self.mat)
         sparse_ilu.decompose(self.pc)
+        lap("precond")
+        if timing is not None:
+            self.mat.pack()
+            lap("pack")
         hist = sparse_square.preconditioned_conjugate_gradient(self.g, self.du, self.q, self.p, pcg_tol, pcg_max, self.mat, self.pc)
+        lap("pcg")
         self.u.add_scaled(-1.0, self.du)                        # u <- u - du
+        lap("update")
         self.log.append((w, gnorm, len(hist) - 1))
         return w, gnorm, len(hist) - 1
 

@@ -98,6 +98,10 @@ class Matrix:
             raise DfbError(1, "merge_for_array_blk: emat shape mismatch")
         check(lib().dfb_bsr_merge_one(self.h, _ptr(e), _ptr(n), n.size, flavour))
 
+    def pack(self):
+        """build the SpMV mirror of the current values now (otherwise the first SpMV after a value change does it)"""
+        check(lib().dfb_bsr_pack(self.h))
+
     def add_to_diagonal(self, scale, v: Vec):
         check(lib().dfb_bsr_add_to_diagonal(self.h, float(scale), v.h))
 

@@ -99,6 +99,12 @@ dfb_status dfb_host_unregister(dfb_ctx *ctx, void *host);
 /* with option "profile_spmv" = 1 the solvers bracket every SpMV launch (first 16384 per solve) with CUDA events on the
    launching stream; this returns the accumulated device time and launch count since the last reset */
 dfb_status dfb_profile_spmv(dfb_ctx *ctx, double *total_ms, uint64_t *count, int32_t reset);
+/* with option "profile_phases" = 1 the library brackets its own assembly / setup launches with CUDA events per phase:
+   [0] element kernels (two-phase path)  [1] merge gather  [2] gradient gather + energy sum  [3] SpMV-mirror pack
+   [4] fused row-tile assembly  [5] Dirichlet BC  [6] preconditioner update  [7] unused.  ms_out / count_out: 8 entries each. */
+dfb_status dfb_ctx_phase_times(dfb_ctx *ctx, double *ms_out, uint64_t *count_out, int32_t reset);
+/* build the SpMV mirror of the current values now (otherwise the first SpMV after a value change does it) */
+dfb_status dfb_bsr_pack(dfb_bsr *m);
 
 /* ------------------------------------------------------------------------------------------------ vectors
  * `[[T;N]]` slices of the reference (del-fem-cpu/src/slice_of_array.rs:1-47). n_blk rows are "owned"; n_ghost extra

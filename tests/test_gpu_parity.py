@@ -282,17 +282,16 @@ def test_ls_smoke_pattern(dfb, ctx, orc):
     """del-fem-ls/src/sparse_square.rs:166-184: 4-row pattern with explicit diagonal slots, merge + mult_vec"""
     colind = np.array([0, 2, 5, 8, 10], dtype=np.uint64)
     rowptr = np.array([0, 1, 0, 1, 2, 1, 2, 3, 2, 3], dtype=np.uint64)
-    s = dfb.linearsystem.Solver(ctx, blk_dim=1)
-    s.initialize(colind, rowptr)
-    s.begin_merge()
+    sparse = dfb.Matrix.from_vtx2vtx(colind, rowptr, 1, ctx=ctx)   # Matrix::new + symbolic_initialization (:168-171)
+    sparse.set_zero()
     emat = np.array([1.0, 0.0, 0.0, 1.0]).reshape(2, 2, 1)
-    s.sparse.merge_for_array_blk(emat, np.array([0, 1]), None, flavour=1)
-    rv, iv = s.sparse.download()
+    sparse.merge_for_array_blk(emat, np.array([0, 1]), None, flavour=1)
+    rv, iv = sparse.download()
     rv_o, iv_o = np.zeros((4, 1)), np.zeros((10, 1))
     orc.merge_for_array_blk(emat, np.array([0, 1]), colind, rowptr, rv_o, iv_o, flavour=1)
     assert np.array_equal(rv, rv_o) and np.array_equal(iv, iv_o)
     lhs = dfb.Vec(ctx, 4, 1)
-    s.sparse.mult_vec(lhs, 1.0, 1.0, dfb.Vec(ctx, 4, 1))
+    sparse.mult_vec(lhs, 1.0, 1.0, dfb.Vec(ctx, 4, 1))
     assert np.array_equal(lhs.download(), np.zeros((4, 1)))
 
 
@@ -540,3 +539,48 @@ def test_full_size_properties(dfb, ctx, orc, size):
     assert np.sqrt(pr.dot(pr)) / hist[0] < 2e-8
     x.add_scaled(1.0, u0)
     assert np.sqrt(x.dot(x)) / np.sqrt(u0.dot(u0)) < 1e-4  # forward error ~ cond(A) * 1e-8
+
+
+def test_config2_full_size_matches_oracle(dfb, ctx, orc):
+    """BASELINE config 2 AT ITS REAL SIZE (S1 = 70^3 vertices, 1 029 000 DoF) against the oracle, not only through properties:
+    pattern and assembled values bit-exact vs `orc.assemble` (the serial element loop + merge_for_array_blk, sparse_square.rs:180-214),
+    constrained matrix and rhs bit-exact, Jacobi-PCG iteration count equal (+-1) to the oracle's SERIAL PCG (the loop of
+    sparse_square.rs:264-347, generalised to 3x3 blocks), which is also the count bench.py's CPU arms use for S1, and the solution
+    within 1e-6.  The oracle side costs ~45 s of one host core (861 iterations x ~50 ms)."""
+    import bench
+    from helpers import device_elasticity_problem, oracle_elasticity_problem
+    from del_fem_b200 import sparse_ilu
+    n = 70
+    prob = oracle_elasticity_problem(orc, n)
+    dev = device_elasticity_problem(dfb, ctx, prob, pattern_on_device=True)
+    r2i, i2c = dev["pat"].download()
+    assert np.array_equal(r2i, prob["r2i"]) and np.array_equal(i2c, prob["i2c"])
+    rv, iv = dev["mat"].download()
+    assert np.array_equal(rv, prob["rv0"]) and np.array_equal(iv, prob["iv0"])           # assembled values, before BC
+    mat, nv = dev["mat"], prob["nv"]
+    assert np.array_equal(dev["rhs"].download(), prob["rhs"])                           # rhs = -K u0, fixed dofs zeroed
+    mat.set_fixed_dof(1.0, prob["flag"])
+    rv, iv = mat.download()
+    assert np.array_equal(rv, prob["rv"]) and np.array_equal(iv, prob["iv"])            # after set_fixed_bc
+    pc = sparse_ilu.Preconditioner("jacobi")
+    pc.initialize(mat)
+    sparse_ilu.copy_value(pc, mat)
+    sparse_ilu.decompose(pc)
+    x, pr, p = dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3)
+    hist = dfb.preconditioned_conjugate_gradient(dev["rhs"], x, pr, p, 1e-8, 20000, mat, pc)
+    ilu = orc.Ilu("jacobi", 3, prob["r2i"], prob["i2c"])
+    ilu.copy_value(prob["r2i"], prob["i2c"], prob["iv"], prob["rv"])
+    ilu.decompose()
+    ro = prob["rhs"].copy()
+    xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+    hist_o = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, 1e-8, 20000, prob["r2i"], prob["i2c"], prob["iv"], prob["rv"], ilu)
+    it_gpu, it_cpu = len(hist) - 1, len(hist_o) - 1
+    assert abs(it_gpu - it_cpu) <= 1, (it_gpu, it_cpu)
+    assert it_cpu == bench.EXPECTED_ITERS[n], (it_cpu, bench.EXPECTED_ITERS[n])
+    m = min(len(hist), len(hist_o)) // 2
+    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-6)
+    assert rel_err(x.download(), xo) < 1e-6
+    ax = np.zeros_like(xo)
+    xs = x.download()
+    orc.mult_vec(ax, 0.0, 1.0, xs, prob["r2i"], prob["i2c"], prob["iv"], prob["rv"])     # true residual on the oracle side
+    assert np.linalg.norm(prob["rhs"] - ax) / np.linalg.norm(prob["rhs"]) < 2e-8
