@@ -799,7 +799,7 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
   DFB_REQUIRE(mesh->num_node == info.n_node && mesh->ndim == info.ndim, "dfb_assemble: mesh (%d nodes, %d-D) does not fit element kind %d",
               mesh->num_node, mesh->ndim, kind);
   DFB_REQUIRE(m->blk_dim == info.N, "dfb_assemble: matrix block dim %d != element block dim %d", m->blk_dim, info.N);
-  m->packed_valid = 0;
+  DFB_TRY(dfb_bsr_canon_overwrite(m));  // every value is about to be rewritten in the canonical arrays
   dfb_ctx *c = plan->ctx;
   const uint64_t ns = plan->num_slots;
   uint64_t g = (ns + 127) / 128;
@@ -1375,7 +1375,7 @@ __global__ void __launch_bounds__(128) k_assemble_from_emat(const uint32_t *__re
 DFB_API dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev, dfb_bsr *m) {
   DFB_REQUIRE(plan && emat_dev && m, "dfb_assemble_from_emat: NULL argument");
   DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble_from_emat: matrix and plan use different patterns");
-  m->packed_valid = 0;
+  DFB_TRY(dfb_bsr_canon_overwrite(m));  // every value is about to be rewritten in the canonical arrays
   dfb_ctx *c = plan->ctx;
   if (c->assemble_variant == 3) {
     // row-tile gather: each (row, element-node) pair reads n_node consecutive blocks of the element matrix

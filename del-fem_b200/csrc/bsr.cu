@@ -11,7 +11,9 @@
 #include "dfb_internal.h"
 #include "reduce.cuh"
 
-// ------------------------------------------------------------------------------------------------ create / IO
+// ------------------------------------------------------------------------------------------------ create / layouts / IO
+static inline bool bsr_has_dia(const dfb_bsr *m) { return m->pat->convention == 0; }
+
 DFB_API dfb_status dfb_bsr_create(dfb_ctx *ctx, dfb_pattern *pattern, int32_t blk_dim, dfb_bsr **out) {
   DFB_REQUIRE(ctx && pattern && out, "dfb_bsr_create: NULL argument");
   DFB_REQUIRE(blk_dim >= 1 && blk_dim <= 4, "dfb_bsr_create: blk_dim %d not in 1..4", blk_dim);
@@ -22,22 +24,9 @@ DFB_API dfb_status dfb_bsr_create(dfb_ctx *ctx, dfb_pattern *pattern, int32_t bl
   m->pat = pattern;
   pattern->refcount += 1;
   m->blk_dim = blk_dim;
-  m->d_idx2val = nullptr;
-  m->d_row2val = nullptr;
-  m->d_flag = nullptr;
-  m->flag_cap = 0;
-  m->halo = nullptr;
   m->int_begin = 0;
   m->int_end = pattern->num_blk;
-  const uint64_t nn = (uint64_t)blk_dim * blk_dim;
-  dfb_status st = dfb_dev_alloc_t(&m->d_idx2val, pattern->nnz * nn + 64);
-  if (st == DFB_OK && pattern->convention == 0) st = dfb_dev_alloc_t(&m->d_row2val, pattern->num_blk * nn + 64);
-  if (st != DFB_OK) {
-    dfb_bsr_destroy(m);
-    return st;
-  }
-  DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, (pattern->nnz * nn + 64) * sizeof(double), ctx->stream));
-  if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, (pattern->num_blk * nn + 64) * sizeof(double), ctx->stream));
+  // no values are allocated yet: the matrix is "all zero" until something writes it (see dfb_internal.h)
   *out = m;
   return DFB_OK;
 }
@@ -57,36 +46,229 @@ DFB_API dfb_status dfb_bsr_destroy(dfb_bsr *m) {
 
 DFB_API dfb_pattern *dfb_bsr_pattern(const dfb_bsr *m) { return m ? m->pat : nullptr; }
 
+// ---- the tile-packed layout: per tile of 8 block-rows one contiguous 16-byte-aligned record
+//     [ u32 rowptr_rel[9] + pad : 48 B | u32 cols[nb] (pad 16) | diag 8 x NN f64 | vals nb x NN f64 (pad 16) ]
+// so the SpMV fetches a tile with a single cp.async.bulk and everything its compute phase needs arrives with it.
+static const int PK_RPT = DFB_PK_RPT, PK_HDR = DFB_PK_HDR;
+
+__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia) {
+  const uint32_t bytes = PK_HDR + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
+  return bytes >> 4;
+}
+
+__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia,
+                             uint32_t *__restrict__ tile_units, unsigned int *max_units) {
+  unsigned int mx = 0;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
+    const uint32_t u = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia);
+    tile_units[t] = u;
+    mx = max(mx, u);
+  }
+  for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_units, mx);
+}
+
+// one warp per tile. STRUCT: header + column indices (pattern only, written once); VALUES: pack the canonical arrays into the
+// record; UNPACK: the reverse
+enum { PK_STRUCT = 1, PK_VALUES = 2, PK_UNPACK = 4 };
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
+                                                    double *__restrict__ idx2val, double *__restrict__ row2val, uint64_t n_rows,
+                                                    uint64_t n_tiles, int NN, int has_dia, const uint32_t *__restrict__ tile_off,
+                                                    unsigned char *__restrict__ packed) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp; t < n_tiles; t += nwarp) {
+    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
+    const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
+    unsigned char *rec = packed + (uint64_t)tile_off[t] * 16;
+    const uint32_t ncol_pad = ((nb * 4u + 15u) & ~15u) / 4u;
+    if (MODE & PK_STRUCT) {
+      uint32_t *hdr = reinterpret_cast<uint32_t *>(rec);
+      if (lane <= PK_RPT) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
+      if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = 0u;
+      uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
+      for (uint32_t k = lane; k < ncol_pad; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
+    }
+    double *dia = reinterpret_cast<double *>(rec + PK_HDR + ncol_pad * 4u);
+    double *vals = dia + (has_dia ? PK_RPT * NN : 0);
+    const uint32_t nv = nb * NN, nv_pad = (((nb * NN * 8u) + 15u) & ~15u) / 8u;
+    const uint32_t nd = (uint32_t)(r1 - r0) * NN;
+    if (MODE & PK_VALUES) {
+      if (has_dia)
+        for (uint32_t q = lane; q < (uint32_t)(PK_RPT * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
+      const double *src = idx2val + (uint64_t)k0 * NN;
+      for (uint32_t q = lane; q < nv_pad; q += 32) vals[q] = (q < nv) ? src[q] : 0.0;
+    }
+    if (MODE & PK_UNPACK) {
+      if (has_dia)
+        for (uint32_t q = lane; q < nd; q += 32) row2val[r0 * NN + q] = dia[q];
+      double *dst = idx2val + (uint64_t)k0 * NN;
+      for (uint32_t q = lane; q < nv; q += 32) dst[q] = vals[q];
+    }
+  }
+}
+
+template <int N> struct PackedCfg;
+static uint32_t packed_buf_bytes(int N);  // the SpMV's per-stage shared-memory buffer (defined with the kernel)
+
+// allocate the packed records and write their pattern-only part (once per matrix); all value bytes start as zero
+static dfb_status bsr_packed_structure(dfb_bsr *m) {
+  if (m->packed_ok >= 0) return DFB_OK;
+  dfb_ctx *c = m->ctx;
+  const uint64_t n = m->pat->num_blk;
+  const int NN = m->blk_dim * m->blk_dim, has_dia = bsr_has_dia(m);
+  const uint64_t n_tiles = (n + PK_RPT - 1) / PK_RPT;
+  DFB_TRY(dfb_dev_alloc_t(&m->d_tile_off, n_tiles + 2));
+  unsigned int *d_max = (unsigned int *)(c->d_scratch + 18);
+  DFB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), c->stream));
+  DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, m->d_tile_off, d_max);
+  DFB_CHECK_LAUNCH();
+  unsigned int h_max = 0;
+  DFB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  uint64_t total_units = 0;
+  DFB_TRY(dfb_exclusive_scan_u32(c, m->d_tile_off, n_tiles, &total_units));  // synchronises: h_max is valid afterwards
+  m->n_tiles = n_tiles;
+  m->packed_cap = total_units * 16 + 256;
+  DFB_TRY(dfb_dev_alloc((void **)&m->d_packed, m->packed_cap));
+  DFB_CUDA(cudaMemsetAsync(m->d_packed, 0, m->packed_cap, c->stream));
+  if (n_tiles > 0) {
+    DFB_LAUNCH(c, k_pack_tiles<PK_STRUCT>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, (double *)nullptr, (double *)nullptr, n,
+               n_tiles, NN, has_dia, m->d_tile_off, m->d_packed);
+    DFB_CHECK_LAUNCH();
+  }
+  m->packed_ok = ((uint64_t)h_max * 16 <= packed_buf_bytes(m->blk_dim)) ? 1 : 0;
+  return DFB_OK;
+}
+
+static dfb_status bsr_canon_alloc(dfb_bsr *m, bool zero) {
+  const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
+  const bool fresh = !m->d_idx2val;
+  if (!m->d_idx2val) DFB_TRY(dfb_dev_alloc_t(&m->d_idx2val, m->pat->nnz * nn + 64));
+  if (bsr_has_dia(m) && !m->d_row2val) DFB_TRY(dfb_dev_alloc_t(&m->d_row2val, m->pat->num_blk * nn + 64));
+  if (zero || fresh) {
+    DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, (m->pat->nnz * nn + 64) * sizeof(double), m->ctx->stream));
+    if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, (m->pat->num_blk * nn + 64) * sizeof(double), m->ctx->stream));
+  }
+  return DFB_OK;
+}
+
+bool dfb_bsr_packed_native(const dfb_bsr *m) {
+  if (m->ctx->spmv_variant != 20) return false;
+  dfb_bsr *mm = const_cast<dfb_bsr *>(m);
+  if (mm->packed_ok < 0 && bsr_packed_structure(mm) != DFB_OK) return false;
+  return mm->packed_ok == 1;
+}
+
+PackedView dfb_bsr_packed_view(const dfb_bsr *m) {
+  PackedView v;
+  v.base = m->d_packed;
+  v.tile_off = m->d_tile_off;
+  v.NN = m->blk_dim * m->blk_dim;
+  v.has_dia = bsr_has_dia(m) ? 1 : 0;
+  return v;
+}
+
+dfb_status dfb_bsr_canon_read(const dfb_bsr *cm) {
+  dfb_bsr *m = const_cast<dfb_bsr *>(cm);
+  if (m->canon_valid) return DFB_OK;
+  dfb_ctx *c = m->ctx;
+  if (!m->packed_valid) {  // all-zero matrix
+    DFB_TRY(bsr_canon_alloc(m, true));
+  } else {
+    DFB_TRY(bsr_canon_alloc(m, false));
+    if (m->n_tiles > 0) {
+      DFB_LAUNCH(c, k_pack_tiles<PK_UNPACK>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val,
+                 m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->d_tile_off, m->d_packed);
+      DFB_CHECK_LAUNCH();
+    }
+  }
+  m->canon_valid = 1;
+  return DFB_OK;
+}
+
+dfb_status dfb_bsr_canon_write(dfb_bsr *m) {
+  DFB_TRY(dfb_bsr_canon_read(m));
+  m->packed_valid = 0;
+  return DFB_OK;
+}
+
+dfb_status dfb_bsr_canon_overwrite(dfb_bsr *m) {
+  DFB_TRY(bsr_canon_alloc(m, false));
+  m->canon_valid = 1;
+  m->packed_valid = 0;
+  return DFB_OK;
+}
+
+dfb_status dfb_bsr_packed_overwrite(dfb_bsr *m) {
+  DFB_TRY(bsr_packed_structure(m));
+  m->packed_valid = 1;
+  m->canon_valid = 0;
+  return DFB_OK;
+}
+
+// packed records hold the current values (packing the canonical arrays / zero-filling on demand)
+dfb_status dfb_bsr_ensure_packed(const dfb_bsr *cm) {
+  dfb_bsr *m = const_cast<dfb_bsr *>(cm);
+  if (m->packed_valid) return DFB_OK;
+  dfb_ctx *c = m->ctx;
+  DFB_TRY(bsr_packed_structure(m));
+  if (!m->canon_valid) {
+    // all-zero matrix: clear the value part of every record (structure is kept)
+    DFB_TRY(bsr_canon_alloc(m, true));
+    m->canon_valid = 1;
+  }
+  if (m->n_tiles > 0) {
+    dfb_phase_begin(c, DFB_PH_PACK);
+    DFB_LAUNCH(c, k_pack_tiles<PK_VALUES>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val,
+               m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->d_tile_off, m->d_packed);
+    dfb_phase_end(c);
+    DFB_CHECK_LAUNCH();
+  }
+  m->packed_valid = 1;
+  return DFB_OK;
+}
+
+dfb_status dfb_bsr_packed_modify(dfb_bsr *m) {
+  DFB_TRY(dfb_bsr_ensure_packed(m));
+  m->canon_valid = 0;
+  return DFB_OK;
+}
+
+DFB_API dfb_status dfb_bsr_pack(dfb_bsr *m) {
+  DFB_REQUIRE(m, "dfb_bsr_pack: NULL argument");
+  if (m->ctx->spmv_variant != 20) return DFB_OK;
+  return dfb_bsr_ensure_packed(m);
+}
+
 DFB_API dfb_status dfb_bsr_set_zero(dfb_bsr *m) {
   DFB_REQUIRE(m, "dfb_bsr_set_zero: NULL argument");
+  // lazily: whoever needs the values next materialises the zeros in the layout it works on
   m->packed_valid = 0;
-  const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
-  DFB_CUDA(cudaMemsetAsync(m->d_idx2val, 0, m->pat->nnz * nn * sizeof(double), m->ctx->stream));
-  if (m->d_row2val) DFB_CUDA(cudaMemsetAsync(m->d_row2val, 0, m->pat->num_blk * nn * sizeof(double), m->ctx->stream));
+  m->canon_valid = 0;
   return DFB_OK;
 }
 
 DFB_API dfb_status dfb_bsr_upload(dfb_bsr *m, const double *row2val, const double *idx2val) {
   DFB_REQUIRE(m, "dfb_bsr_upload: NULL argument");
-  m->packed_valid = 0;
+  if (row2val) DFB_REQUIRE(bsr_has_dia(m), "dfb_bsr_upload: matrix has no separate diagonal (convention 1)");
+  if (idx2val && (row2val || !bsr_has_dia(m))) DFB_TRY(dfb_bsr_canon_overwrite(m));
+  else DFB_TRY(dfb_bsr_canon_write(m));  // partial upload: the other array keeps its values
   const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
   if (idx2val) DFB_CUDA(cudaMemcpyAsync(m->d_idx2val, idx2val, m->pat->nnz * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
-  if (row2val) {
-    DFB_REQUIRE(m->d_row2val, "dfb_bsr_upload: matrix has no separate diagonal (convention 1)");
-    DFB_CUDA(cudaMemcpyAsync(m->d_row2val, row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
-  }
+  if (row2val) DFB_CUDA(cudaMemcpyAsync(m->d_row2val, row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
   DFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return DFB_OK;
 }
 
 DFB_API dfb_status dfb_bsr_download(const dfb_bsr *m, double *row2val, double *idx2val) {
   DFB_REQUIRE(m, "dfb_bsr_download: NULL argument");
+  if (row2val) DFB_REQUIRE(bsr_has_dia(m), "dfb_bsr_download: matrix has no separate diagonal (convention 1)");
+  DFB_TRY(dfb_bsr_canon_read(m));
   const uint64_t nn = (uint64_t)m->blk_dim * m->blk_dim;
   if (idx2val) DFB_CUDA(cudaMemcpyAsync(idx2val, m->d_idx2val, m->pat->nnz * nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
-  if (row2val) {
-    DFB_REQUIRE(m->d_row2val, "dfb_bsr_download: matrix has no separate diagonal (convention 1)");
-    DFB_CUDA(cudaMemcpyAsync(row2val, m->d_row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
-  }
+  if (row2val) DFB_CUDA(cudaMemcpyAsync(row2val, m->d_row2val, m->pat->num_blk * nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   DFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
   return DFB_OK;
 }
@@ -153,10 +335,82 @@ __global__ void k_set_fixed_bc(double val_dia, const int32_t *__restrict__ flag,
   }
 }
 
+// the same pass over the packed records (native layout of spmv_variant 20): thread per block-row
+template <int N>
+__global__ void k_set_fixed_bc_packed(double val_dia, const int32_t *__restrict__ flag, const PackedView pv, uint64_t num_blk) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
+    int fi[N];
+    bool any_i = false;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      fi[d] = flag[i * N + d];
+      any_i |= (fi[d] != 0);
+    }
+    if (pv.has_dia && any_i) {
+      double *D = pk_diag(pv, i);
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        if (fi[d] == 0) continue;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          D[d + N * j] = 0.0;
+          D[j + N * d] = 0.0;
+        }
+        D[d + N * d] = val_dia;
+      }
+    }
+    const uint32_t *cols;
+    uint32_t n;
+    double *vals = pk_row(pv, i, &cols, &n);
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t c = cols[k];
+      double *V = vals + (uint64_t)k * (N * N);
+      if (!pv.has_dia && c == (uint32_t)i) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          if (fi[d] == 0) continue;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            V[d + N * j] = 0.0;
+            V[j + N * d] = 0.0;
+          }
+          V[d + N * d] = val_dia;
+        }
+        continue;
+      }
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        if (fi[d] != 0) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) V[d + N * j] = 0.0;
+        }
+        if (flag[(uint64_t)c * N + d] != 0) {
+#pragma unroll
+          for (int a = 0; a < N; ++a) V[a + N * d] = 0.0;
+        }
+      }
+    }
+  }
+}
+
 static dfb_status launch_set_fixed_bc(dfb_bsr *m, double val_dia, const int32_t *d_flag) {
   dfb_ctx *c = m->ctx;
-  m->packed_valid = 0;
   const int grid = c->sm_count * 8;
+  if ((m->packed_valid || !m->canon_valid) && dfb_bsr_packed_native(m)) {
+    DFB_TRY(dfb_bsr_packed_modify(m));
+    const PackedView pv = dfb_bsr_packed_view(m);
+    dfb_phase_begin(c, DFB_PH_BC);
+    switch (m->blk_dim) {
+      case 1: DFB_LAUNCH(c, k_set_fixed_bc_packed<1>, grid, 128, 0, val_dia, d_flag, pv, m->pat->num_blk); break;
+      case 2: DFB_LAUNCH(c, k_set_fixed_bc_packed<2>, grid, 128, 0, val_dia, d_flag, pv, m->pat->num_blk); break;
+      case 3: DFB_LAUNCH(c, k_set_fixed_bc_packed<3>, grid, 128, 0, val_dia, d_flag, pv, m->pat->num_blk); break;
+      case 4: DFB_LAUNCH(c, k_set_fixed_bc_packed<4>, grid, 128, 0, val_dia, d_flag, pv, m->pat->num_blk); break;
+    }
+    dfb_phase_end(c);
+    DFB_CHECK_LAUNCH();
+    return DFB_OK;
+  }
+  DFB_TRY(dfb_bsr_canon_write(m));
   dfb_phase_begin(c, DFB_PH_BC);
   switch (m->blk_dim) {
     case 1: DFB_LAUNCH(c, k_set_fixed_bc<1>, grid, 128, 0, val_dia, d_flag, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, m->pat->num_blk, m->pat->convention); break;
@@ -203,13 +457,25 @@ __global__ void k_add_to_diagonal(double *__restrict__ row2val, int N, double sc
     row2val[i * N * N + d + N * d] += scale * v[q];
   }
 }
+__global__ void k_add_to_diagonal_packed(const PackedView pv, int N, double scale, const double *__restrict__ v, uint64_t n_dof) {
+  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_dof; q += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = q / N;
+    const int d = (int)(q - i * N);
+    pk_diag(pv, i)[d + N * d] += scale * v[q];
+  }
+}
 
 DFB_API dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_vec *v) {
   DFB_REQUIRE(m && v, "dfb_bsr_add_to_diagonal: NULL argument");
-  DFB_REQUIRE(m->d_row2val, "dfb_bsr_add_to_diagonal: convention 1 matrices have no separate diagonal");
-  m->packed_valid = 0;
+  DFB_REQUIRE(bsr_has_dia(m), "dfb_bsr_add_to_diagonal: convention 1 matrices have no separate diagonal");
   DFB_REQUIRE(v->n_blk == m->pat->num_blk && v->blk_dim == m->blk_dim, "dfb_bsr_add_to_diagonal: shape mismatch");
-  DFB_LAUNCH(m->ctx, k_add_to_diagonal, m->ctx->sm_count * 8, 256, 0, m->d_row2val, m->blk_dim, scale, v->d, v->len());
+  if ((m->packed_valid || !m->canon_valid) && dfb_bsr_packed_native(m)) {
+    DFB_TRY(dfb_bsr_packed_modify(m));
+    DFB_LAUNCH(m->ctx, k_add_to_diagonal_packed, m->ctx->sm_count * 8, 256, 0, dfb_bsr_packed_view(m), m->blk_dim, scale, v->d, v->len());
+  } else {
+    DFB_TRY(dfb_bsr_canon_write(m));
+    DFB_LAUNCH(m->ctx, k_add_to_diagonal, m->ctx->sm_count * 8, 256, 0, m->d_row2val, m->blk_dim, scale, v->d, v->len());
+  }
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -218,15 +484,34 @@ DFB_API dfb_status dfb_bsr_add_to_diagonal(dfb_bsr *m, double scale, const dfb_v
 __global__ void k_axpy_values(double *__restrict__ y, double alpha, const double *__restrict__ x, uint64_t n) {
   for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (uint64_t)gridDim.x * blockDim.x) y[q] += alpha * x[q];
 }
+// packed form: the two matrices share the pattern, hence the record layout; one warp per tile walks the value part of the record
+__global__ void __launch_bounds__(256) k_axpy_packed(const PackedView y, const PackedView x, double alpha, uint64_t n_tiles) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = warp; t < n_tiles; t += nwarp) {
+    const uint32_t nb = reinterpret_cast<const uint32_t *>(pk_record(y, t))[DFB_PK_RPT];
+    const uint32_t n = ((y.has_dia ? DFB_PK_RPT : 0) + nb) * y.NN;
+    double *yv = pk_tile_values(y, t);
+    const double *xv = pk_tile_values(x, t);
+    for (uint32_t q = lane; q < n; q += 32) yv[q] += alpha * xv[q];
+  }
+}
 
 DFB_API dfb_status dfb_bsr_add_scaled(dfb_bsr *m, double alpha, const dfb_bsr *other) {
   DFB_REQUIRE(m && other, "dfb_bsr_add_scaled: NULL argument");
   DFB_REQUIRE(m->pat == other->pat && m->blk_dim == other->blk_dim, "dfb_bsr_add_scaled: matrices must share pattern and block size");
-  m->packed_valid = 0;
   const uint64_t NN = (uint64_t)m->blk_dim * m->blk_dim;
+  if (other->packed_valid && (m->packed_valid || !m->canon_valid) && dfb_bsr_packed_native(m)) {
+    DFB_TRY(dfb_bsr_packed_modify(m));
+    if (m->n_tiles) DFB_LAUNCH(m->ctx, k_axpy_packed, m->ctx->sm_count * 8, 256, 0, dfb_bsr_packed_view(m), dfb_bsr_packed_view(other), alpha, m->n_tiles);
+    DFB_CHECK_LAUNCH();
+    return DFB_OK;
+  }
+  DFB_TRY(dfb_bsr_canon_write(m));
+  DFB_TRY(dfb_bsr_canon_read(other));
   const uint64_t n_off = m->pat->nnz * NN;
   if (n_off) DFB_LAUNCH(m->ctx, k_axpy_values, m->ctx->sm_count * 8, 256, 0, m->d_idx2val, alpha, other->d_idx2val, n_off);
-  if (m->d_row2val) DFB_LAUNCH(m->ctx, k_axpy_values, m->ctx->sm_count * 8, 256, 0, m->d_row2val, alpha, other->d_row2val, m->pat->num_blk * NN);
+  if (bsr_has_dia(m)) DFB_LAUNCH(m->ctx, k_axpy_values, m->ctx->sm_count * 8, 256, 0, m->d_row2val, alpha, other->d_row2val, m->pat->num_blk * NN);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -264,7 +549,7 @@ __global__ void k_merge_one(const double *__restrict__ emat, const uint32_t *__r
 DFB_API dfb_status dfb_bsr_merge_one(dfb_bsr *m, const double *emat, const uint64_t *node2vtx, int32_t n_node, int32_t flavour) {
   DFB_REQUIRE(m && emat && node2vtx, "dfb_bsr_merge_one: NULL argument");
   DFB_REQUIRE(n_node >= 1 && n_node <= 8, "dfb_bsr_merge_one: n_node %d not in 1..8", n_node);
-  m->packed_valid = 0;
+  DFB_TRY(dfb_bsr_canon_write(m));
   dfb_ctx *c = m->ctx;
   const int NN = m->blk_dim * m->blk_dim;
   double *d_e = nullptr;
@@ -614,9 +899,9 @@ static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t s
 // per tile of 8 block-rows, one contiguous 16-byte-aligned record
 //     [ u32 rowptr_rel[9] + pad : 48 B | u32 cols[nb] (pad 16) | diag 8 x NN f64 | vals nb x NN f64 (pad 16) ]
 // so a tile is fetched by a single cp.async.bulk and everything the compute phase needs (relative row pointers included)
-// arrives with it. The canonical arrays (the reference's AoS layout) stay the storage every other entry point works on;
-// the mirror is rebuilt lazily (one streaming pass, ~2 SpMV-equivalents) after the values change and lives for a whole solve.
-static const int PK_RPT = 8, PK_LPR = 4, PK_HDR = 48;
+// arrives with it. With this variant the packed records are the matrix's native storage (dfb_internal.h): assembly, BC and the
+// Jacobi preconditioners write / read them directly, the canonical arrays are only materialised for entry points that need them.
+static const int PK_LPR = 4;
 
 template <int N>
 struct PackedCfg {
@@ -628,46 +913,12 @@ struct PackedCfg {
   static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
 };
 
-__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia) {
-  const uint32_t bytes = PK_HDR + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
-  return bytes >> 4;
-}
-
-__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia,
-                             uint32_t *__restrict__ tile_units) {
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
-    tile_units[t] = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia);
-  }
-}
-
-// one warp per tile: streams the tile's pieces out of the canonical arrays into its packed record
-__global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
-                                                    const double *__restrict__ idx2val, const double *__restrict__ row2val,
-                                                    uint64_t n_rows, uint64_t n_tiles, int NN, const uint32_t *__restrict__ tile_off,
-                                                    unsigned char *__restrict__ packed) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const int has_dia = row2val != nullptr;
-  for (uint64_t t = warp; t < n_tiles; t += nwarp) {
-    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
-    const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
-    unsigned char *rec = packed + (uint64_t)tile_off[t] * 16;
-    uint32_t *hdr = reinterpret_cast<uint32_t *>(rec);
-    if (lane <= PK_RPT) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
-    if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = 0u;
-    uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
-    const uint32_t ncol_pad = ((nb * 4u + 15u) & ~15u) / 4u;
-    for (uint32_t k = lane; k < ncol_pad; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
-    double *dia = reinterpret_cast<double *>(rec + PK_HDR + ncol_pad * 4u);
-    if (has_dia) {
-      const uint32_t nd = (uint32_t)(r1 - r0) * NN;
-      for (uint32_t q = lane; q < (uint32_t)(PK_RPT * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
-    }
-    double *vals = dia + (has_dia ? PK_RPT * NN : 0);
-    const uint32_t nv = nb * NN, nv_pad = (((nb * NN * 8u) + 15u) & ~15u) / 8u;
-    const double *src = idx2val + (uint64_t)k0 * NN;
-    for (uint32_t q = lane; q < nv_pad; q += 32) vals[q] = (q < nv) ? src[q] : 0.0;
+static uint32_t packed_buf_bytes(int N) {
+  switch (N) {
+    case 1: return PackedCfg<1>::BUF_BYTES;
+    case 2: return PackedCfg<2>::BUF_BYTES;
+    case 3: return PackedCfg<3>::BUF_BYTES;
+    default: return PackedCfg<4>::BUF_BYTES;
   }
 }
 
@@ -801,35 +1052,6 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-// (re)build the packed mirror of m on the stream
-static dfb_status bsr_pack(dfb_bsr *m, cudaStream_t strm) {
-  dfb_ctx *c = m->ctx;
-  const uint64_t n = m->pat->num_blk;
-  const int NN = m->blk_dim * m->blk_dim;
-  const int has_dia = m->d_row2val != nullptr;
-  const uint64_t n_tiles = (n + PK_RPT - 1) / PK_RPT;
-  if (!m->d_tile_off) {
-    // the layout only depends on the pattern: sizes -> scan once
-    DFB_TRY(dfb_dev_alloc_t(&m->d_tile_off, n_tiles + 2));
-    DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, m->d_tile_off);
-    DFB_CHECK_LAUNCH();
-    uint64_t total_units = 0;
-    DFB_TRY(dfb_exclusive_scan_u32(c, m->d_tile_off, n_tiles, &total_units));
-    m->n_tiles = n_tiles;
-    m->packed_cap = total_units * 16 + 256;
-    DFB_TRY(dfb_dev_alloc((void **)&m->d_packed, m->packed_cap));
-  }
-  if (n_tiles > 0) {
-    dfb_phase_begin(c, DFB_PH_PACK, strm);
-    DFB_LAUNCH_ON(c, strm, k_pack_tiles, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val, n,
-                  n_tiles, NN, m->d_tile_off, m->d_packed);
-    dfb_phase_end(c, strm);
-    DFB_CHECK_LAUNCH();
-  }
-  m->packed_valid = 1;
-  return DFB_OK;
-}
-
 template <int N>
 static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bsr *m, cudaStream_t strm) {
   using S = PackedCfg<N>;
@@ -841,10 +1063,10 @@ static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bs
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
   if (a.hw.xg[0] != nullptr) {
     DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
   } else {
     DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, m->d_row2val != nullptr);
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
   }
   DFB_CHECK_LAUNCH();
   return DFB_OK;
@@ -873,8 +1095,11 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
   SpmvArgs a;
   a.row2idx = m->pat->d_row2idx;
   a.idx2col = m->pat->d_idx2col;
+  if (c->spmv_variant == 20) DFB_TRY(dfb_bsr_ensure_packed(m));
+  // variants 0 / 4, and the oversized tiles of variant 20, multiply straight from the canonical arrays
+  if (c->spmv_variant != 20 || m->packed_ok != 1) DFB_TRY(dfb_bsr_canon_read(m));
   a.idx2val = m->d_idx2val;
-  a.row2val = m->d_row2val;
+  a.row2val = bsr_has_dia(m) ? m->d_row2val : nullptr;
   a.x = x;
   a.y = y;
   a.alpha = alpha;
@@ -898,8 +1123,6 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
     a.hw.tile_hi_begin = 0xFFFFFFFFu;
   }
   if (c->spmv_variant == 20) {
-    dfb_bsr *mm = const_cast<dfb_bsr *>(m);
-    if (!mm->packed_valid) DFB_TRY(bsr_pack(mm, strm));
     switch (m->blk_dim) {
       case 1: return spmv_launch_packed<1>(c, a, m, strm);
       case 2: return spmv_launch_packed<2>(c, a, m, strm);
@@ -914,18 +1137,6 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
     case 4: return spmv_dispatch<4>(c, a, strm);
   }
   return dfb_fail(DFB_ERR_UNSUPPORTED, "spmv: blk_dim %d", m->blk_dim);
-}
-
-// the packed mirror must exist before a chunk of iterations is captured into a CUDA graph (the pack allocates on first use)
-dfb_status dfb_bsr_ensure_packed(const dfb_bsr *m) {
-  dfb_bsr *mm = const_cast<dfb_bsr *>(m);
-  if (m->ctx->spmv_variant == 20 && !mm->packed_valid) DFB_TRY(bsr_pack(mm, m->ctx->stream));
-  return DFB_OK;
-}
-
-DFB_API dfb_status dfb_bsr_pack(dfb_bsr *m) {
-  DFB_REQUIRE(m, "dfb_bsr_pack: NULL argument");
-  return dfb_bsr_ensure_packed(m);
 }
 
 static uint64_t halo_recv_total(const dfb_bsr *m) { return (m->halo && !m->halo->recv_ptr.empty()) ? m->halo->recv_ptr.back() : 0; }
@@ -1012,6 +1223,7 @@ DFB_API dfb_status dfb_bsr_mult_mat(const dfb_bsr *m, dfb_vec *y, double beta, d
               "dfb_bsr_mult_mat: assert_eq!(y_mat.len(), x_mat.len()) / num_dim * num_row");
   DFB_REQUIRE(x->d != y->d, "dfb_bsr_mult_mat: x and y alias");
   DFB_REQUIRE(!m->halo, "dfb_bsr_mult_mat: not available for distributed matrices");
+  DFB_TRY(dfb_bsr_canon_read(m));
   dfb_ctx *c = m->ctx;
   const uint64_t total = m->pat->num_blk * (uint64_t)x->blk_dim;
   uint64_t g = (total + 255) / 256;

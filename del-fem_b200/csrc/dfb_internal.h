@@ -220,23 +220,71 @@ struct DfbHaloPush {   // kernel argument of the pack-and-push launch
   unsigned long long *flag[DFB_MAX_RANKS];    // &peer_mbox[peer]->halo_flag[rank]
 };
 
+// Matrix values live in ONE of two layouts (or both, when both are current):
+//   canonical  idx2val[nnz*NN] + row2val[num_blk*NN]: exactly the reference's Vec<[T;NN]> arrays (upload/download, per-element merge,
+//              ILU, sparse product, SpMV variants 0/4 work on these)
+//   packed     the tile-packed SpMV mirror (bsr.cu): per 8 block-rows one record [rowptr_rel | cols | 8 diagonal blocks | value blocks]
+// With spmv_variant 20 the packed layout is the NATIVE one: assembly, Dirichlet BC, add_to_diagonal, add_scaled, the Jacobi
+// preconditioners and the SpMV all work on it directly, and the canonical arrays are only materialised (unpack kernel) when an entry
+// point that needs them is called. Nothing is allocated until the values are first needed (a new matrix is "all zero").
 struct dfb_bsr {
   dfb_ctx *ctx;
   dfb_pattern *pat;
   int blk_dim;
-  double *d_idx2val;  // [nnz * NN] (+pad)
-  double *d_row2val;  // [num_blk * NN] (convention 0)
-  int32_t *d_flag;    // uploaded BC flags (scratch, lazily allocated)
-  uint64_t flag_cap;
-  dfb_halo *halo;
-  uint64_t int_begin, int_end;
-  // tile-packed mirror for the SpMV (built lazily, invalidated by every mutation of the values)
+  double *d_idx2val = nullptr;  // [nnz * NN] (+pad)   canonical, lazily allocated
+  double *d_row2val = nullptr;  // [num_blk * NN] (convention 0)
+  int canon_valid = 0;          // canonical arrays hold the current values
+  int32_t *d_flag = nullptr;    // uploaded BC flags (scratch, lazily allocated)
+  uint64_t flag_cap = 0;
+  dfb_halo *halo = nullptr;
+  uint64_t int_begin = 0, int_end = 0;
   unsigned char *d_packed = nullptr;
   uint32_t *d_tile_off = nullptr;   // [n_tiles + 1], in 16-byte units
   uint64_t packed_cap = 0;          // bytes allocated
   uint64_t n_tiles = 0;
-  int packed_valid = 0;
+  int packed_valid = 0;             // the packed records hold the current values
+  int packed_ok = -1;               // -1 layout not built yet, 1 every tile fits the SpMV's shared-memory buffer, 0 some tile is oversized
+                                    //  (its rows are multiplied straight from the canonical arrays, which then stay the native layout)
 };
+
+// device-side view of the packed layout
+struct PackedView {
+  unsigned char *base;
+  const uint32_t *tile_off;
+  int NN, has_dia;
+};
+static const int DFB_PK_RPT = 8, DFB_PK_HDR = 48;
+__device__ __forceinline__ unsigned char *pk_record(const PackedView &v, uint64_t tile) { return v.base + ((uint64_t)v.tile_off[tile] << 4); }
+// diagonal block of row r
+__device__ __forceinline__ double *pk_diag(const PackedView &v, uint64_t r) {
+  unsigned char *rec = pk_record(v, r / DFB_PK_RPT);
+  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[DFB_PK_RPT];
+  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u)) + (r % DFB_PK_RPT) * v.NN;
+}
+// off-diagonal blocks of row r: values, column indices, count
+__device__ __forceinline__ double *pk_row(const PackedView &v, uint64_t r, const uint32_t **cols, uint32_t *n) {
+  unsigned char *rec = pk_record(v, r / DFB_PK_RPT);
+  const uint32_t *hdr = reinterpret_cast<const uint32_t *>(rec);
+  const uint32_t nb = hdr[DFB_PK_RPT], kb = hdr[r % DFB_PK_RPT], ke = hdr[r % DFB_PK_RPT + 1];
+  *cols = reinterpret_cast<const uint32_t *>(rec + DFB_PK_HDR) + kb;
+  *n = ke - kb;
+  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u)) + (v.has_dia ? DFB_PK_RPT * v.NN : 0) + (uint64_t)kb * v.NN;
+}
+// first value (the tile's diagonal blocks, then its off-diagonal blocks, contiguous) of tile t
+__device__ __forceinline__ double *pk_tile_values(const PackedView &v, uint64_t tile) {
+  unsigned char *rec = pk_record(v, tile);
+  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[DFB_PK_RPT];
+  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u));
+}
+
+// ---- layout management (bsr.cu)
+bool dfb_bsr_packed_native(const dfb_bsr *m);        // spmv_variant 20 and every tile fits: the packed layout is the one entry points write
+dfb_status dfb_bsr_canon_read(const dfb_bsr *m);     // canonical arrays allocated and current (zero-filled or unpacked on demand)
+dfb_status dfb_bsr_canon_write(dfb_bsr *m);          // ... and about to be modified in place: the packed records become stale
+dfb_status dfb_bsr_canon_overwrite(dfb_bsr *m);      // ... about to be overwritten completely (no unpack needed)
+dfb_status dfb_bsr_packed_overwrite(dfb_bsr *m);     // packed layout built, every value about to be overwritten: canonical arrays become stale
+dfb_status dfb_bsr_packed_modify(dfb_bsr *m);        // packed records current and about to be modified in place: canonical arrays become stale
+PackedView dfb_bsr_packed_view(const dfb_bsr *m);
 
 struct dfb_plan {
   dfb_ctx *ctx;

@@ -378,6 +378,7 @@ dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia
   const uint64_t n = m->pat->num_blk, nnz = m->pat->nnz;
   const int N = m->blk_dim, NN = N * N;
   if (s->nnz != nnz) DFB_CUDA(cudaMemsetAsync(s->d_val, 0, s->nnz * NN * sizeof(double), c->stream));  // fill entries start at zero
+  DFB_TRY(dfb_bsr_canon_read(m));
   DFB_LAUNCH(c, k_ilu_copy, c->sm_count * 8, 256, 0, m->d_idx2val, m->d_row2val, s->d_a2ilu, nnz, n, NN, s->d_val, d_dia_out);
   const uint32_t nlev = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1;
   for (uint32_t l = 0; l < nlev; ++l) {

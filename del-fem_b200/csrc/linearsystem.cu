@@ -175,6 +175,8 @@ DFB_API dfb_status dfb_solver_clone(const dfb_solver *s, dfb_solver **out) {
     t->pat = s->pat;
     t->pat->refcount += 1;
     st = dfb_bsr_create(t->ctx, t->pat, t->blk_dim, &t->sparse);
+    if (st == DFB_OK) st = dfb_bsr_canon_read(s->sparse);
+    if (st == DFB_OK) st = dfb_bsr_canon_overwrite(t->sparse);
     if (st == DFB_OK) {
       const uint64_t nn = (uint64_t)s->blk_dim * s->blk_dim;
       cudaError_t e = cudaMemcpyAsync(t->sparse->d_idx2val, s->sparse->d_idx2val, s->pat->nnz * nn * sizeof(double), cudaMemcpyDeviceToDevice, s->ctx->stream);

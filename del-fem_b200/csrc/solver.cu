@@ -84,11 +84,12 @@ __device__ __forceinline__ const double *find_diag(uint64_t i, int NN, const dou
 
 template <int N>
 __global__ void k_precond_update(int kind, uint64_t num_blk, const double *__restrict__ row2val, const double *__restrict__ idx2val,
-                                 const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
+                                 const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col, const PackedView pv,
                                  double *__restrict__ inv, int *err) {
   constexpr int NN = N * N;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num_blk; i += (uint64_t)gridDim.x * blockDim.x) {
-    const double *D = find_diag(i, NN, row2val, idx2val, row2idx, idx2col);
+    // diagonal block: from the packed records when they are the matrix's current layout (pv.base != nullptr), else canonical
+    const double *D = pv.base ? pk_diag(pv, i) : find_diag(i, NN, row2val, idx2val, row2idx, idx2col);
     if (!D) {
       atomicExch(err, 1);
       continue;
@@ -163,11 +164,18 @@ DFB_API dfb_status dfb_precond_update(dfb_precond *pc, const dfb_bsr *m) {
     return dfb_ilu_update(c, pc->ilu, m, pc->d_inv);
   }
   const int grid = c->sm_count * 8;
+  PackedView pv = dfb_bsr_packed_view(m);
+  if (m->packed_valid && !m->canon_valid && pv.has_dia) {
+    // the packed records are the current layout: read the diagonal blocks from them
+  } else {
+    DFB_TRY(dfb_bsr_canon_read(m));
+    pv.base = nullptr;
+  }
   dfb_phase_begin(c, DFB_PH_PRECOND);
 #define PC_CASE(NV)                                                                                                       \
   case NV:                                                                                                                \
-    DFB_LAUNCH(c, k_precond_update<NV>, grid, 128, 0, pc->kind, pc->num_blk, m->d_row2val, m->d_idx2val, m->pat->d_row2idx, \
-               m->pat->d_idx2col, pc->d_inv, c->d_errflag + 2);                                                           \
+    DFB_LAUNCH(c, k_precond_update<NV>, grid, 128, 0, pc->kind, pc->num_blk, m->pat->convention == 0 ? m->d_row2val : nullptr, \
+               m->d_idx2val, m->pat->d_row2idx, m->pat->d_idx2col, pv, pc->d_inv, c->d_errflag + 2);                       \
     break;
   switch (pc->blk_dim) {
     PC_CASE(1)

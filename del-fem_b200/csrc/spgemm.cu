@@ -139,6 +139,9 @@ DFB_API dfb_status dfb_bsr_mult_square_matrices(const dfb_bsr *m0, const dfb_bsr
   }
   dfb_bsr *cm = nullptr;
   if (st == DFB_OK) st = dfb_bsr_create(c, pat, 1, &cm);
+  if (st == DFB_OK) st = dfb_bsr_canon_overwrite(cm);
+  if (st == DFB_OK) st = dfb_bsr_canon_read(m0);
+  if (st == DFB_OK) st = dfb_bsr_canon_read(m1);
   if (st == DFB_OK) {
     DFB_LAUNCH(c, k_spgemm_numeric, G, 128, 0, n, m0->pat->d_row2idx, m0->pat->d_idx2col, m0->d_idx2val, m0->d_row2val, m1->pat->d_row2idx,
                m1->pat->d_idx2col, m1->d_idx2val, m1->d_row2val, d_ub, d_scratch, pat->d_row2idx, pat->d_idx2col, cm->d_idx2val,
