@@ -302,7 +302,20 @@ struct dfb_plan {
   // row-tile assembly (variant 3): for every (row, element-node) pair the tile-relative slots of its n_node blocks, one byte each
   uint32_t *d_pair_slots = nullptr;
   int pairs_state = 0;     // 0 not built yet, 1 usable, -1 not applicable (convention/flavour, oversized tile, degenerate element)
+  // fused row-tile assembly (assemble_tile.cu, the default): per tile of 16 rows the sorted unique incident elements, and the
+  // contribution lists recoded to 16 bits (tile-local element << 4 | i << 2 | j), parallel to d_contrib
+  uint32_t *d_tile_elem = nullptr;   // tile t's list starts at nz2ptr[nnz + 16 t] - pair_base
+  uint32_t *d_tile_nelem = nullptr;  // [n_atiles]
+  uint16_t *d_code16 = nullptr;      // [num_contrib]
+  uint64_t n_atiles = 0;
+  uint32_t pair_base = 0, tile_max_elem = 0, tile_max_slots = 0;
+  int tile_state = 0;      // 0 not built yet, 1 usable, -1 not applicable
 };
+// assemble_tile.cu: DFB_ERR_UNSUPPORTED (no error string, matrix untouched) = the tile path does not apply, use the gather of assemble.cu
+dfb_status dfb_plan_build_tiles(dfb_plan *plan);
+dfb_status dfb_assemble_tile_linear(dfb_plan *plan, int kind, const dfb_mesh *mesh, double p0, double p1, dfb_bsr *m);
+dfb_status dfb_assemble_tile_energy(dfb_plan *plan, int kind, const dfb_mesh *mesh, const dfb_vec *disp, double p0, double p1, dfb_bsr *m,
+                                    double *dw, double *w_elem);
 
 struct DfbIlu;
 struct dfb_precond {
