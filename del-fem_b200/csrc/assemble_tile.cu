@@ -16,8 +16,9 @@
 #include "elements.cuh"
 #include "reduce.cuh"
 
-static const int AT_ROWS = 16;        // block-rows per assembly tile (= 2 packed SpMV tiles)
-static const int AT_THREADS = 256;
+static const int AT_THREADS = 320;    // assembly kernel: ~7-8 warps of off-diagonal slots + 2 warps of diagonal-slot quads at 16 rows/tile
+static const int AT_BUILD_THREADS = 256;
+static const int AT_DIA_LANES = 4;    // lanes that share one diagonal slot (its list is ~4x longer than an off-diagonal one)
 static const int AT_PAIR_CAP = 2048;  // (row, element) pairs per tile the builder can sort in shared memory
 static const int AT_ELEM_CAP = 4095;  // tile-local element index must fit 12 bits of the 16-bit contribution code
 
@@ -42,10 +43,12 @@ __device__ __forceinline__ void bitonic_sort_smem(uint32_t *keys, uint32_t P) {
 }
 
 // one CTA per tile: unique incident elements (sorted) and the 16-bit recoding of the tile's contribution lists
-__global__ void __launch_bounds__(AT_THREADS) k_tile_build(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
-                                                           uint64_t nnz, uint64_t num_rows, int nn, const uint32_t *__restrict__ row2idx,
-                                                           uint32_t *__restrict__ tile_elem, uint32_t *__restrict__ tile_nelem,
-                                                           uint16_t *__restrict__ code16, uint32_t *stats, uint64_t n_tiles) {
+__global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
+                                                                 uint64_t nnz, uint64_t num_rows, int nn, const uint32_t *__restrict__ row2idx,
+                                                                 uint32_t *__restrict__ tile_elem, uint32_t *__restrict__ tile_nelem,
+                                                                 uint16_t *__restrict__ code16, uint32_t *stats, uint64_t n_tiles,
+                                                                 uint32_t AT_ROWS) {
+  constexpr int AT_THREADS = AT_BUILD_THREADS;
   __shared__ uint32_t keys[AT_PAIR_CAP];
   __shared__ uint32_t uniq[AT_PAIR_CAP];
   __shared__ uint32_t cnt[AT_THREADS];
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_tile_build(const uint32_t *__res
       tile_nelem[tile] = n_le;
       atomicMax(&stats[0], n_le);
       atomicMax(&stats[1], (k1 - k0) + (uint32_t)(r1 - r0));
+      atomicMax(&stats[3], (nz2ptr[k1] - nz2ptr[k0]) + np);
       if (n_le > (uint32_t)AT_ELEM_CAP) atomicExch(&stats[2], 1u);
     }
     // recode the contributions of the tile's slots: off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)
@@ -129,6 +133,11 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   DFB_CUDA(cudaMemcpyAsync(&ends[1], plan->d_nz2ptr + nnz + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaStreamSynchronize(c->stream));
   const uint64_t npairs = ends[1] - ends[0];
+  // rows per tile: about 224 off-diagonal slots (7 warps of slot threads), a multiple of the SpMV's 8-row tiles
+  const double off_per_row = (double)nnz / (double)nr;
+  uint32_t AT_ROWS = (uint32_t)(224.0 / (off_per_row > 1.0 ? off_per_row : 1.0) / 8.0 + 0.5) * 8u;
+  if (AT_ROWS < 8) AT_ROWS = 8;
+  if (AT_ROWS > 64) AT_ROWS = 64;
   const uint64_t n_tiles = (nr + AT_ROWS - 1) / AT_ROWS;
   uint32_t *d_stats = nullptr;
   dfb_status st = dfb_dev_alloc_t(&plan->d_tile_elem, npairs + 2);
@@ -139,8 +148,8 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   if (st == DFB_OK) {
     cudaMemsetAsync(d_stats, 0, 4 * sizeof(uint32_t), c->stream);
     uint64_t g = n_tiles < (uint64_t)c->sm_count * 8 ? n_tiles : (uint64_t)c->sm_count * 8;
-    DFB_LAUNCH(c, k_tile_build, (unsigned)g, AT_THREADS, 0, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node, plan->pat->d_row2idx,
-               plan->d_tile_elem, plan->d_tile_nelem, plan->d_code16, d_stats, n_tiles);
+    DFB_LAUNCH(c, k_tile_build, (unsigned)g, AT_BUILD_THREADS, 0, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node, plan->pat->d_row2idx,
+               plan->d_tile_elem, plan->d_tile_nelem, plan->d_code16, d_stats, n_tiles, AT_ROWS);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -159,6 +168,8 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   }
   plan->tile_max_elem = h_stats[0];
   plan->tile_max_slots = h_stats[1];
+  plan->tile_max_codes = h_stats[3];
+  plan->tile_rows = AT_ROWS;
   plan->n_atiles = n_tiles;
   plan->pair_base = ends[0];
   plan->tile_state = 1;
@@ -382,18 +393,27 @@ __global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Mod
                                                               const uint16_t *__restrict__ code16, const uint32_t *__restrict__ tile_elem,
                                                               const uint32_t *__restrict__ tile_nelem, uint32_t pair_base,
                                                               const uint32_t *__restrict__ row2idx, uint64_t nnz, uint64_t num_rows,
-                                                              uint64_t n_tiles, uint32_t max_elem, const TileOut out,
-                                                              double *__restrict__ dw, double *__restrict__ w_elem) {
+                                                              uint64_t n_tiles, uint32_t AT_ROWS, uint32_t max_elem, uint32_t max_slots,
+                                                              const TileOut out, double *__restrict__ dw, double *__restrict__ w_elem) {
   constexpr int NN = Model::N * Model::N, N = Model::N, NNODE = Model::NNODE, REC = Model::REC;
   extern __shared__ __align__(16) double at_smem[];
-  double *srec = at_smem;
-  double *sout = at_smem + (size_t)max_elem * REC;
-  const unsigned tid = threadIdx.x;
+  double *srec = at_smem;                                              // [n_le][REC]
+  double *sout = srec + (size_t)max_elem * REC;                        // [n_off + n_rows][NN]
+  uint32_t *sptr = reinterpret_cast<uint32_t *>(sout + (size_t)max_slots * NN);   // list offsets of the tile's slots (+1)
+  uint16_t *scode = reinterpret_cast<uint16_t *>(sptr + max_slots + 2);           // the tile's contribution codes
+  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t r0 = tile * AT_ROWS, r1 = min(r0 + (uint64_t)AT_ROWS, num_rows);
     const uint32_t k0 = row2idx[r0], k1 = row2idx[r1], n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0);
     const uint32_t n_le = tile_nelem[tile];
-    const uint32_t *elems = tile_elem + (nz2ptr[nnz + r0] - pair_base);
+    const uint32_t ob = nz2ptr[k0], oe = nz2ptr[k1], pb = nz2ptr[nnz + r0], pe = nz2ptr[nnz + r1];
+    const uint32_t n_oc = oe - ob;                                     // codes of the off-diagonal slots; the pairs follow
+    const uint32_t *elems = tile_elem + (pb - pair_base);
+    // ---- stage the tile's lists: after this no phase-2 instruction waits for global memory
+    for (uint32_t q = tid; q <= n_off; q += AT_THREADS) sptr[q] = nz2ptr[k0 + q] - ob;
+    for (uint32_t q = tid; q <= n_rows; q += AT_THREADS) sptr[n_off + 1 + q] = n_oc + (nz2ptr[nnz + r0 + q] - pb);
+    for (uint32_t q = tid; q < n_oc; q += AT_THREADS) scode[q] = code16[ob + q];
+    for (uint32_t q = tid; q < pe - pb; q += AT_THREADS) scode[n_oc + q] = code16[pb + q];
     // ---- phase 1: per-element records into shared memory (one thread per listed element)
     for (uint32_t le = tid; le < n_le; le += AT_THREADS) {
       const uint32_t e = elems[le];
@@ -407,38 +427,84 @@ __global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Mod
       }
     }
     __syncthreads();
-    // ---- phase 2: one thread per slot: off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)
-    for (uint32_t s = tid; s < n_off + n_rows; s += AT_THREADS) {
-      const bool is_dia = s >= n_off;
-      const uint64_t slot = is_dia ? nnz + r0 + (s - n_off) : (uint64_t)k0 + s;
-      double acc[NN];
+    // ---- phase 2a: off-diagonal slots, one thread each (lists of ~4-6 contributions)
+    const uint32_t n_off_warps = (n_off + 31) >> 5;
+    const uint32_t n_dia_warps = (n_rows * AT_DIA_LANES + 31) >> 5;
+    for (uint32_t w = wid; w < n_off_warps + n_dia_warps; w += nwarp) {
+      if (w < n_off_warps) {
+        const uint32_t s = (w << 5) + lane;
+        if (s < n_off) {
+          double acc[NN];
 #pragma unroll
-      for (int q = 0; q < NN; ++q) acc[q] = 0.0;
-      double gacc[N];
+          for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+          const uint32_t cb = sptr[s], ce = sptr[s + 1];
+          for (uint32_t c = cb; c < ce; ++c) {
+            const uint32_t code = scode[c];
+            double blk[NN];
+            Model::block(srec + (size_t)(code >> 4) * REC, (int)((code >> 2) & 3u), (int)(code & 3u), args, blk);
 #pragma unroll
-      for (int d = 0; d < N; ++d) gacc[d] = 0.0;
-      const uint32_t cb = nz2ptr[slot], ce = nz2ptr[slot + 1];
-      for (uint32_t c = cb; c < ce; ++c) {
-        const uint32_t code = code16[c];
-        const double *rec = srec + (size_t)(code >> 4) * REC;
-        const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
-        double blk[NN];
-        Model::block(rec, i, j, args, blk);
+            for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+          }
+          double *dst = sout + (size_t)s * NN;
 #pragma unroll
-        for (int q = 0; q < NN; ++q) acc[q] += blk[q];
-        if (Model::HAS_GRAD && is_dia && dw) {
-          double g[N];
-          Model::grad(rec, i, args, g);
-#pragma unroll
-          for (int d = 0; d < N; ++d) gacc[d] += g[d];
+          for (int q = 0; q < NN; ++q) dst[q] = acc[q];
         }
-      }
-      double *dst = sout + (size_t)s * NN;
+      } else {
+        // ---- phase 2b: diagonal slots, AT_DIA_LANES lanes each: the lanes form the blocks of consecutive contributions in
+        // parallel, the group's first lane adds them in list order (ascending element = the serial loop's order, same bits)
+        const uint32_t v = ((w - n_off_warps) << 5) + lane;
+        const uint32_t row = v / AT_DIA_LANES, t = v % AT_DIA_LANES;
+        const bool live = row < n_rows;
+        const uint32_t cb = live ? sptr[n_off + 1 + row] : 0u, ce = live ? sptr[n_off + 1 + row + 1] : 0u;
+        uint32_t n = ce - cb, nmax = n;
 #pragma unroll
-      for (int q = 0; q < NN; ++q) dst[q] = acc[q];
-      if (Model::HAS_GRAD && is_dia && dw) {
+        for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
+        double acc[NN], gacc[N];
 #pragma unroll
-        for (int d = 0; d < N; ++d) dw[(r0 + (s - n_off)) * N + d] = gacc[d];
+        for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) gacc[d] = 0.0;
+        const int base_lane = (int)(lane - t);
+        for (uint32_t k = 0; k < nmax; k += AT_DIA_LANES) {
+          const uint32_t c = cb + k + t;
+          double blk[NN], g[N];
+#pragma unroll
+          for (int q = 0; q < NN; ++q) blk[q] = 0.0;
+#pragma unroll
+          for (int d = 0; d < N; ++d) g[d] = 0.0;
+          if (k + t < n) {
+            const uint32_t code = scode[c];
+            const double *rec = srec + (size_t)(code >> 4) * REC;
+            const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
+            Model::block(rec, i, j, args, blk);
+            if (Model::HAS_GRAD && dw) Model::grad(rec, i, args, g);
+          }
+#pragma unroll
+          for (int u = 0; u < AT_DIA_LANES; ++u) {
+            const bool on = k + u < n;  // (evaluated for the group's first lane: n is the same on the 4 lanes)
+#pragma unroll
+            for (int q = 0; q < NN; ++q) {
+              const double x = __shfl_sync(0xffffffffu, blk[q], base_lane + u);
+              if (on) acc[q] += x;
+            }
+            if (Model::HAS_GRAD && dw) {
+#pragma unroll
+              for (int d = 0; d < N; ++d) {
+                const double x = __shfl_sync(0xffffffffu, g[d], base_lane + u);
+                if (on) gacc[d] += x;
+              }
+            }
+          }
+        }
+        if (live && t == 0) {
+          double *dst = sout + (size_t)(n_off + row) * NN;
+#pragma unroll
+          for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+          if (Model::HAS_GRAD && dw) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) dw[(r0 + row) * N + d] = gacc[d];
+          }
+        }
       }
     }
     __syncthreads();
@@ -470,7 +536,8 @@ template <class Model>
 static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, dfb_bsr *m, double *dw, double *w_elem) {
   dfb_ctx *c = plan->ctx;
   constexpr int NN = Model::N * Model::N;
-  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double);
+  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double) +
+                      ((size_t)plan->tile_max_slots + 2) * sizeof(uint32_t) + (((size_t)plan->tile_max_codes + 7) & ~(size_t)7) * sizeof(uint16_t);
   if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
   TileOut out;
   if (dfb_bsr_packed_native(m)) {
@@ -495,7 +562,7 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
   dfb_phase_begin(c, DFB_PH_TILE);
   DFB_LAUNCH(c, k_assemble_tile<Model>, (unsigned)g, AT_THREADS, smem, args, plan->d_nz2ptr, plan->d_code16, plan->d_tile_elem,
              plan->d_tile_nelem, plan->pair_base, plan->pat->d_row2idx, plan->pat->nnz, plan->pat->num_blk, plan->n_atiles,
-             plan->tile_max_elem, out, dw, w_elem);
+             plan->tile_rows, plan->tile_max_elem, plan->tile_max_slots, out, dw, w_elem);
   dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
@@ -539,7 +606,7 @@ dfb_status dfb_assemble_tile_energy(dfb_plan *plan, int kind, const dfb_mesh *me
     a.stiffness = p0;
     return launch_tile<ModelSpring3>(plan, a, m, dw, w_elem);
   }
-  if (kind == DFB_ELEM_NEOHOOKEAN_TET) {
+  if (kind == DFB_ELEM_NEOHOOKEAN_TET && plan->ctx->assemble_tile_neo) {
     ModelNeoHookeanTet::Args a;
     a.e2v = mesh->d_elem2vtx;
     a.xyz = mesh->d_xyz;

@@ -122,6 +122,7 @@ struct dfb_ctx {
   int64_t use_graph = 1;          // (P)CG: replay chunks of iterations as a CUDA graph (0: plain launches)
   struct DfbGraphCache *graph = nullptr;
   int64_t assemble_variant = 0;
+  int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
   // SpMV profiling (events on the launching stream)
@@ -308,7 +309,7 @@ struct dfb_plan {
   uint32_t *d_tile_nelem = nullptr;  // [n_atiles]
   uint16_t *d_code16 = nullptr;      // [num_contrib]
   uint64_t n_atiles = 0;
-  uint32_t pair_base = 0, tile_max_elem = 0, tile_max_slots = 0;
+  uint32_t pair_base = 0, tile_max_elem = 0, tile_max_slots = 0, tile_max_codes = 0, tile_rows = 16;
   int tile_state = 0;      // 0 not built yet, 1 usable, -1 not applicable
 };
 // assemble_tile.cu: DFB_ERR_UNSUPPORTED (no error string, matrix untouched) = the tile path does not apply, use the gather of assemble.cu

@@ -10,7 +10,8 @@ import _bootstrap
 dfb = _bootstrap.load()
 from del_fem_b200 import synthetic
 
-n = synthetic.SIZES.get(sys.argv[1], None) or int(sys.argv[1])
+arg = sys.argv[1] if len(sys.argv) > 1 else "S10"
+n = synthetic.SIZES.get(arg, None) or int(arg)
 ctx = dfb.Ctx(0)
 mesh = dfb.Mesh.kuhn(ctx, n)
 ctx.timer_start()
@@ -23,7 +24,7 @@ print(f"pattern {t_pat:.2f} ms, plan {t_plan:.2f} ms, {mesh.num_elem} tets, {pla
 mat = dfb.Matrix(ctx, pat, 3)
 ref = None
 bytes_alg = 16 * mesh.num_elem + 24 * mesh.num_vtx + 72 * plan.num_slots + 64 * mesh.num_elem + 4 * (plan.num_slots + 1)
-for variant in (1, 2, 0, 3):
+for variant in (4, 0):
     ctx.set_option("assemble_variant", variant)
     mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
     best = 1e9
@@ -45,8 +46,9 @@ if n <= 110:
     d.fill_splitmix(0, 0, -1e-3, 1e-3)
     g = dfb.Vec(ctx, mesh.num_vtx, 3)
     ref = None
-    for variant in (0, 3):
+    for variant in (4, 0):
         ctx.set_option("assemble_variant", variant)
+        ctx.set_option("assemble_tile_neo", 1)
         elements.assemble_energy(plan, "neohookean_tet", mesh, d, 1.0, 10.0, mat, g)
         best = 1e9
         for _ in range(3):
@@ -55,5 +57,5 @@ if n <= 110:
             best = min(best, ctx.timer_stop())
         rv, iv = mat.download()
         same = ref is None or (np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1]))
-        ref = ref or (rv, iv)
+        ref = ref if ref is not None else (rv, iv)
         print(f"neo-Hookean energy assembly, variant {variant}: {best:.3f} ms identical_bits={same}")
