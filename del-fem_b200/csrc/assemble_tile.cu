@@ -16,11 +16,12 @@
 #include "elements.cuh"
 #include "reduce.cuh"
 
-static const int AT_THREADS = 320;    // assembly kernel: ~7-8 warps of off-diagonal slots + 2 warps of diagonal-slot quads at 16 rows/tile
+static const int AT_MAX_THREADS = 512;
 static const int AT_BUILD_THREADS = 256;
 static const int AT_DIA_LANES = 4;    // lanes that share one diagonal slot (its list is ~4x longer than an off-diagonal one)
 static const int AT_PAIR_CAP = 2048;  // (row, element) pairs per tile the builder can sort in shared memory
-static const int AT_ELEM_CAP = 4095;  // tile-local element index must fit 12 bits of the 16-bit contribution code
+static const int AT_ELEM_CAP = 1024;  // unique elements per tile (their <= 4096 vertex references are sorted in shared memory)
+static const int AT_META = 12;        // u32 per tile: k0, k1, ob, oe, pb, pe, n_le, n_lv, vtx_off, pad x 3
 
 // ------------------------------------------------------------------------------------------------ tile plan
 __device__ __forceinline__ void bitonic_sort_smem(uint32_t *keys, uint32_t P) {
@@ -42,16 +43,55 @@ __device__ __forceinline__ void bitonic_sort_smem(uint32_t *keys, uint32_t P) {
   }
 }
 
-// one CTA per tile: unique incident elements (sorted) and the 16-bit recoding of the tile's contribution lists
+// sorted keys[0..n) -> unique values in out[0..total) (block-wide; cnt = scratch of blockDim.x entries)
+__device__ __forceinline__ uint32_t unique_sorted_smem(const uint32_t *keys, uint32_t n, uint32_t P, uint32_t *out, uint32_t *cnt) {
+  const unsigned tid = threadIdx.x, T = blockDim.x;
+  const uint32_t C = (P + T - 1) / T;
+  const uint32_t cb = min(tid * C, n), ce = min(cb + C, n);
+  uint32_t local = 0;
+  for (uint32_t i = cb; i < ce; ++i) local += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+  cnt[tid] = local;
+  __syncthreads();
+  for (uint32_t off = 1; off < T; off <<= 1) {  // inclusive Hillis-Steele scan of the per-thread counts
+    const uint32_t v = (tid >= off) ? cnt[tid - off] : 0u;
+    __syncthreads();
+    cnt[tid] += v;
+    __syncthreads();
+  }
+  const uint32_t total = cnt[T - 1];
+  uint32_t w = cnt[tid] - local;
+  for (uint32_t i = cb; i < ce; ++i)
+    if (i == 0 || keys[i] != keys[i - 1]) out[w++] = keys[i];
+  __syncthreads();
+  return total;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t *a, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// one CTA per tile. FILL = false: count the tile's unique elements / vertices (sizes for the scans); FILL = true: write the
+// element list, the vertex list, the tile-local connectivity, the per-tile meta record and the 16-bit contribution codes
+template <bool FILL>
 __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
                                                                  uint64_t nnz, uint64_t num_rows, int nn, const uint32_t *__restrict__ row2idx,
-                                                                 uint32_t *__restrict__ tile_elem, uint32_t *__restrict__ tile_nelem,
-                                                                 uint16_t *__restrict__ code16, uint32_t *stats, uint64_t n_tiles,
-                                                                 uint32_t AT_ROWS) {
-  constexpr int AT_THREADS = AT_BUILD_THREADS;
-  __shared__ uint32_t keys[AT_PAIR_CAP];
-  __shared__ uint32_t uniq[AT_PAIR_CAP];
-  __shared__ uint32_t cnt[AT_THREADS];
+                                                                 const uint32_t *__restrict__ e2v, uint32_t *__restrict__ tile_nvtx,
+                                                                 const uint32_t *__restrict__ vtx_off, uint32_t *__restrict__ tile_elem,
+                                                                 uint32_t *__restrict__ tile_vtx, uint16_t *__restrict__ tile_lconn,
+                                                                 uint32_t *__restrict__ tile_meta, uint16_t *__restrict__ code16,
+                                                                 uint32_t *stats, uint64_t n_tiles, uint32_t AT_ROWS) {
+  extern __shared__ uint32_t tb_smem[];
+  uint32_t *keys = tb_smem;                       // [AT_PAIR_CAP]   pairs' elements, sorted
+  uint32_t *uniq = keys + AT_PAIR_CAP;            // [AT_ELEM_CAP]   unique elements
+  uint32_t *vkeys = uniq + AT_ELEM_CAP;           // [4 * AT_ELEM_CAP] vertex references, sorted
+  uint32_t *uvtx = vkeys + 4 * AT_ELEM_CAP;       // [4 * AT_ELEM_CAP] unique vertices
+  uint32_t *cnt = uvtx + 4 * AT_ELEM_CAP;         // [AT_BUILD_THREADS]
   const uint32_t pair_base = nz2ptr[nnz];
   const uint32_t nn2 = (uint32_t)(nn * nn);
   const unsigned tid = threadIdx.x;
@@ -60,61 +100,77 @@ __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t 
     const uint32_t pb = nz2ptr[nnz + r0], pe = nz2ptr[nnz + r1], np = pe - pb;
     const uint32_t k0 = row2idx[r0], k1 = row2idx[r1];
     if (np > (uint32_t)AT_PAIR_CAP) {
-      if (tid == 0) {
-        atomicExch(&stats[2], 1u);
-        tile_nelem[tile] = 0;
-      }
+      if (tid == 0) atomicExch(&stats[2], 1u);
       continue;
     }
     uint32_t P = 1;
     while (P < np) P <<= 1;
-    for (uint32_t i = tid; i < P; i += AT_THREADS) keys[i] = (i < np) ? contrib[pb + i] / nn2 : 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < P; i += AT_BUILD_THREADS) keys[i] = (i < np) ? contrib[pb + i] / nn2 : 0xFFFFFFFFu;
     __syncthreads();
     bitonic_sort_smem(keys, P);
-    // unique: thread t owns the chunk [t*C, (t+1)*C)
-    const uint32_t C = (P + AT_THREADS - 1) / AT_THREADS;
-    const uint32_t cb = tid * C, ce = min(cb + C, np);
-    uint32_t local = 0;
-    for (uint32_t i = cb; i < ce; ++i) local += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-    cnt[tid] = local;
-    __syncthreads();
-    for (uint32_t off = 1; off < AT_THREADS; off <<= 1) {  // inclusive Hillis-Steele scan of the per-thread counts
-      const uint32_t v = (tid >= off) ? cnt[tid - off] : 0u;
+    // the pair list may hold more distinct elements than the cap: count first, bail out before writing past `uniq`
+    uint32_t n_le = 0;
+    {
+      uint32_t local = 0;
+      for (uint32_t i = tid; i < np; i += AT_BUILD_THREADS) local += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+      cnt[tid] = local;
       __syncthreads();
-      cnt[tid] += v;
-      __syncthreads();
-    }
-    const uint32_t n_le = cnt[AT_THREADS - 1];
-    uint32_t w = cnt[tid] - local;  // exclusive offset of this chunk
-    for (uint32_t i = cb; i < ce; ++i) {
-      if (i == 0 || keys[i] != keys[i - 1]) {
-        uniq[w] = keys[i];
-        tile_elem[(pb - pair_base) + w] = keys[i];
-        ++w;
+      if (tid == 0) {
+        uint32_t t = 0;
+        for (int q = 0; q < AT_BUILD_THREADS; ++q) t += cnt[q];
+        cnt[0] = t;
       }
+      __syncthreads();
+      n_le = cnt[0];
+      __syncthreads();
     }
+    if (n_le > (uint32_t)AT_ELEM_CAP) {
+      if (tid == 0) atomicExch(&stats[2], 1u);
+      continue;
+    }
+    unique_sorted_smem(keys, np, P, uniq, cnt);
+    // vertex references of the unique elements -> sorted unique vertex list
+    const uint32_t nvr = n_le * (uint32_t)nn;
+    uint32_t PV = 1;
+    while (PV < nvr) PV <<= 1;
+    for (uint32_t i = tid; i < PV; i += AT_BUILD_THREADS) vkeys[i] = (i < nvr) ? e2v[(uint64_t)uniq[i / nn] * nn + (i % nn)] : 0xFFFFFFFFu;
     __syncthreads();
+    bitonic_sort_smem(vkeys, PV);
+    const uint32_t n_lv = unique_sorted_smem(vkeys, nvr, PV, uvtx, cnt);
+    if (!FILL) {
+      if (tid == 0) {
+        tile_nvtx[tile] = n_lv;
+        atomicMax(&stats[0], n_le);
+        atomicMax(&stats[1], (k1 - k0) + (uint32_t)(r1 - r0));
+        atomicMax(&stats[3], (nz2ptr[k1] - nz2ptr[k0]) + np);
+        atomicMax(&stats[4], n_lv);
+      }
+      __syncthreads();
+      continue;
+    }
+    const uint32_t voff = vtx_off[tile], eoff = pb - pair_base;
+    const uint32_t ob = nz2ptr[k0], oe = nz2ptr[k1];
     if (tid == 0) {
-      tile_nelem[tile] = n_le;
-      atomicMax(&stats[0], n_le);
-      atomicMax(&stats[1], (k1 - k0) + (uint32_t)(r1 - r0));
-      atomicMax(&stats[3], (nz2ptr[k1] - nz2ptr[k0]) + np);
-      if (n_le > (uint32_t)AT_ELEM_CAP) atomicExch(&stats[2], 1u);
+      uint32_t *mt = tile_meta + tile * AT_META;
+      mt[0] = k0; mt[1] = k1; mt[2] = ob; mt[3] = oe; mt[4] = pb; mt[5] = pe; mt[6] = n_le; mt[7] = n_lv; mt[8] = voff;
+      mt[9] = mt[10] = mt[11] = 0;
+    }
+    for (uint32_t i = tid; i < n_le; i += AT_BUILD_THREADS) tile_elem[eoff + i] = uniq[i];
+    for (uint32_t i = tid; i < n_lv; i += AT_BUILD_THREADS) tile_vtx[voff + i] = uvtx[i];
+    for (uint32_t i = tid; i < n_le * 4; i += AT_BUILD_THREADS) {
+      const uint32_t le = i >> 2, n = i & 3;
+      uint16_t lv = 0;
+      if (n < (uint32_t)nn) lv = (uint16_t)lower_bound_smem(uvtx, n_lv, e2v[(uint64_t)uniq[le] * nn + n]);
+      tile_lconn[(uint64_t)(eoff + le) * 4 + n] = lv;
     }
     // recode the contributions of the tile's slots: off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)
-    const uint32_t ob = nz2ptr[k0], oe = nz2ptr[k1];
     const uint32_t total = (oe - ob) + np;
-    for (uint32_t q = tid; q < total; q += AT_THREADS) {
+    for (uint32_t q = tid; q < total; q += AT_BUILD_THREADS) {
       const uint32_t c = (q < oe - ob) ? ob + q : pb + (q - (oe - ob));
       const uint32_t code = contrib[c];
       const uint32_t e = code / nn2, ij = code - e * nn2;
       const uint32_t i = ij / (uint32_t)nn, j = ij - i * (uint32_t)nn;
-      uint32_t lo = 0, hi = n_le;  // first index with uniq[idx] >= e
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (uniq[mid] < e) lo = mid + 1;
-        else hi = mid;
-      }
+      const uint32_t lo = lower_bound_smem(uniq, n_le, e);
       if (lo >= n_le || uniq[lo] != e) atomicExch(&stats[2], 1u);  // a contribution whose (element, row) is not a pair of the row
       code16[c] = (uint16_t)((lo << 4) | (i << 2) | j);
     }
@@ -122,11 +178,22 @@ __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t 
   }
 }
 
+static void plan_free_tiles(dfb_plan *plan) {
+  dfb_dev_free(plan->d_tile_elem);
+  dfb_dev_free(plan->d_tile_vtx);
+  dfb_dev_free(plan->d_tile_lconn);
+  dfb_dev_free(plan->d_tile_meta);
+  dfb_dev_free(plan->d_code16);
+  plan->d_tile_elem = plan->d_tile_vtx = plan->d_tile_meta = nullptr;
+  plan->d_tile_lconn = plan->d_code16 = nullptr;
+}
+void dfb_plan_free_tiles(dfb_plan *plan) { plan_free_tiles(plan); }
+
 dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   if (plan->tile_state != 0) return DFB_OK;
   plan->tile_state = -1;
   dfb_ctx *c = plan->ctx;
-  if (plan->pat->convention != 0 || plan->flavour != 0 || plan->num_node > 4 || plan->pat->num_blk == 0) return DFB_OK;
+  if (plan->pat->convention != 0 || plan->flavour != 0 || plan->num_node > 4 || plan->pat->num_blk == 0 || !plan->mesh) return DFB_OK;
   const uint64_t nnz = plan->pat->nnz, nr = plan->pat->num_blk;
   uint32_t ends[2] = {0, 0};
   DFB_CUDA(cudaMemcpyAsync(&ends[0], plan->d_nz2ptr + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -136,39 +203,63 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   // rows per tile: about 224 off-diagonal slots (7 warps of slot threads), a multiple of the SpMV's 8-row tiles
   const double off_per_row = (double)nnz / (double)nr;
   uint32_t AT_ROWS = (uint32_t)(224.0 / (off_per_row > 1.0 ? off_per_row : 1.0) / 8.0 + 0.5) * 8u;
+  if (c->assemble_tile_rows > 0) AT_ROWS = (uint32_t)((c->assemble_tile_rows + 7) / 8 * 8);
   if (AT_ROWS < 8) AT_ROWS = 8;
   if (AT_ROWS > 64) AT_ROWS = 64;
   const uint64_t n_tiles = (nr + AT_ROWS - 1) / AT_ROWS;
-  uint32_t *d_stats = nullptr;
-  dfb_status st = dfb_dev_alloc_t(&plan->d_tile_elem, npairs + 2);
-  if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_nelem, n_tiles + 2);
-  if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_code16, plan->num_contrib + 8);
-  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_stats, 4);
-  uint32_t h_stats[4] = {0, 0, 1, 0};
+  const size_t smem = (size_t)(AT_PAIR_CAP + AT_ELEM_CAP + 8 * AT_ELEM_CAP + AT_BUILD_THREADS) * sizeof(uint32_t);
+  DFB_CUDA(cudaFuncSetAttribute(k_tile_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DFB_CUDA(cudaFuncSetAttribute(k_tile_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  uint32_t *d_stats = nullptr, *d_voff = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&d_stats, 8);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_voff, n_tiles + 2);
+  uint32_t h_stats[8] = {0, 0, 1, 0, 0, 0, 0, 0};
+  const uint64_t g = n_tiles < (uint64_t)c->sm_count * 4 ? n_tiles : (uint64_t)c->sm_count * 4;
+  const dfb_mesh *mesh = plan->mesh;
   if (st == DFB_OK) {
-    cudaMemsetAsync(d_stats, 0, 4 * sizeof(uint32_t), c->stream);
-    uint64_t g = n_tiles < (uint64_t)c->sm_count * 8 ? n_tiles : (uint64_t)c->sm_count * 8;
-    DFB_LAUNCH(c, k_tile_build, (unsigned)g, AT_BUILD_THREADS, 0, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node, plan->pat->d_row2idx,
-               plan->d_tile_elem, plan->d_tile_nelem, plan->d_code16, d_stats, n_tiles, AT_ROWS);
+    cudaMemsetAsync(d_stats, 0, 8 * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(d_voff, 0, (n_tiles + 2) * sizeof(uint32_t), c->stream);
+    DFB_LAUNCH(c, k_tile_build<false>, (unsigned)g, AT_BUILD_THREADS, smem, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node,
+               plan->pat->d_row2idx, mesh->d_elem2vtx, d_voff, (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+               (uint16_t *)nullptr, (uint32_t *)nullptr, (uint16_t *)nullptr, d_stats, n_tiles, AT_ROWS);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_build_tiles: %s", cudaGetErrorString(e));
   }
+  uint64_t n_vtx_total = 0;
+  if (st == DFB_OK && h_stats[2] == 0) st = dfb_exclusive_scan_u32(c, d_voff, n_tiles, &n_vtx_total);
+  if (st == DFB_OK && h_stats[2] == 0) {
+    st = dfb_dev_alloc_t(&plan->d_tile_elem, npairs + 2);
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_vtx, n_vtx_total + 2);
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_lconn, (npairs + 2) * 4);
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_meta, (n_tiles + 1) * AT_META);
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_code16, plan->num_contrib + 8);
+    if (st == DFB_OK) {
+      cudaMemsetAsync(plan->d_tile_meta, 0, (n_tiles + 1) * AT_META * sizeof(uint32_t), c->stream);
+      DFB_LAUNCH(c, k_tile_build<true>, (unsigned)g, AT_BUILD_THREADS, smem, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node,
+                 plan->pat->d_row2idx, mesh->d_elem2vtx, (uint32_t *)nullptr, d_voff, plan->d_tile_elem, plan->d_tile_vtx, plan->d_tile_lconn,
+                 plan->d_tile_meta, plan->d_code16, d_stats, n_tiles, AT_ROWS);
+      cudaError_t e = cudaGetLastError();
+      uint32_t bad = 1;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_stats + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_build_tiles: %s", cudaGetErrorString(e));
+      h_stats[2] = bad;
+    }
+  }
+  cudaStreamSynchronize(c->stream);
   dfb_dev_free(d_stats);
-  if (st != DFB_OK || h_stats[2] != 0) {
+  dfb_dev_free(d_voff);
+  if (st != DFB_OK || h_stats[2] != 0 || h_stats[4] > 65535u) {
     // not applicable (very high valence / degenerate lists): the slot-centric gather of assemble.cu stays in charge
-    dfb_dev_free(plan->d_tile_elem);
-    dfb_dev_free(plan->d_tile_nelem);
-    dfb_dev_free(plan->d_code16);
-    plan->d_tile_elem = nullptr;
-    plan->d_tile_nelem = nullptr;
-    plan->d_code16 = nullptr;
+    plan_free_tiles(plan);
     return st;
   }
   plan->tile_max_elem = h_stats[0];
   plan->tile_max_slots = h_stats[1];
   plan->tile_max_codes = h_stats[3];
+  plan->tile_max_vtx = h_stats[4];
   plan->tile_rows = AT_ROWS;
   plan->n_atiles = n_tiles;
   plan->pair_base = ends[0];
@@ -177,59 +268,70 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
 }
 
 // ------------------------------------------------------------------------------------------------ models
-// A model provides: NNODE, N, REC (doubles per element record), HAS_GRAD, Args (kernel parameters),
-//   make(rec, e, args)            -> evaluates the record of element e into shared memory; returns the element's energy
-//   block(rec, i, j, args, blk)   -> block (i,j) of the element matrix, column-major N x N
-//   grad(rec, i, args, g)         -> gradient of node i (energy models)
+// A model provides: NNODE, N, NDIM, REC (doubles per element record), HAS_GRAD, NEEDS_DISP, Args (kernel parameters),
+//   make(rec, lc, sxyz, sdisp, args)  -> evaluates the record of one element into shared memory from the tile's STAGED vertex data
+//                                        (lc = the element's tile-local vertex ids); returns the element's energy
+//   block(rec, i, j, args, blk)       -> block (i,j) of the element matrix, column-major N x N
+//   grad(rec, i, args, g)             -> gradient of node i (energy models)
 
-// linear kinds: the record is ElemGeo<KIND> itself; block() IS the reference formula (ElemGeo<KIND>::block)
+// linear kinds. Record = NNODE node records of 4 doubles (two 16-byte shared-memory loads per node) where the block of (i,j) only
+// needs the two nodes' data (NodeOps<KIND>::OK), else ElemGeo<KIND> itself. block() IS the reference formula, operation for operation.
 template <int KIND>
 struct ModelLinear {
   using G = ElemGeo<KIND>;
-  static constexpr int NNODE = G::NNODE, N = G::N, NDIM = G::NDIM, REC = (int)((sizeof(G) + 7) / 8), HAS_GRAD = 0;
+  using NO = NodeOps<KIND>;
+  static constexpr int NNODE = G::NNODE, N = G::N, NDIM = G::NDIM, HAS_GRAD = 0, NEEDS_DISP = 0;
+  static constexpr int REC = NO::OK ? NNODE * 4 : (int)((sizeof(G) + 15) / 16) * 2;
   struct Args {
-    const uint32_t *e2v;
-    const double *xyz;
     double p0, p1;
   };
-  __device__ static double make(double *rec, uint32_t e, const Args &a) {
+  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *, const Args &a) {
     const double *p[NNODE];
-    double coords[NNODE][NDIM];
 #pragma unroll
-    for (int n = 0; n < NNODE; ++n) {
-      const uint32_t v = a.e2v[(uint64_t)e * NNODE + n];
-#pragma unroll
-      for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&a.xyz[(uint64_t)v * NDIM + d]);
-      p[n] = coords[n];
-    }
+    for (int n = 0; n < NNODE; ++n) p[n] = sxyz + (size_t)lc[n] * NDIM;
     G g;
     g.init(p, a.p0, a.p1);
-    *reinterpret_cast<G *>(rec) = g;
+    if constexpr (NO::OK) {
+#pragma unroll
+      for (int n = 0; n < NNODE; ++n) {
+        const NodeRec r = NO::make(g, n);
+        double2 *dst = reinterpret_cast<double2 *>(rec + n * 4);
+        dst[0] = make_double2(r.v[0], r.v[1]);
+        dst[1] = make_double2(r.v[2], r.v[3]);
+      }
+    } else {
+      *reinterpret_cast<G *>(rec) = g;
+    }
     return 0.0;
   }
   __device__ static void block(const double *rec, int i, int j, const Args &a, double *blk) {
-    reinterpret_cast<const G *>(rec)->block(i, j, a.p0, a.p1, blk);
+    if constexpr (NO::OK) {
+      const double2 *pa = reinterpret_cast<const double2 *>(rec + i * 4), *pb = reinterpret_cast<const double2 *>(rec + j * 4);
+      const double2 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+      const NodeRec ra = {{a0.x, a0.y, a1.x, a1.y}}, rb = {{b0.x, b0.y, b1.x, b1.y}};
+      NO::block(ra, rb, a.p0, a.p1, blk);
+    } else {
+      reinterpret_cast<const G *>(rec)->block(i, j, a.p0, a.p1, blk);
+    }
   }
   __device__ static void grad(const double *, int, const Args &, double *) {}
 };
 
 // spring3::wdwddw_squared_length_difference (del-fem-cpu/src/spring3.rs:1-28): same operations as k_spring3 (assemble.cu)
 struct ModelSpring3 {
-  static constexpr int NNODE = 2, N = 3, REC = 8, HAS_GRAD = 1;
+  static constexpr int NNODE = 2, N = 3, NDIM = 3, REC = 6, HAS_GRAD = 1, NEEDS_DISP = 1;
   struct Args {
-    const uint32_t *e2v;
-    const double *xyz, *disp;
     double stiffness;
   };
-  // rec: v[3], t0, t1, gp (= c k / l), pad
-  __device__ static double make(double *rec, uint32_t e, const Args &a) {
-    const uint32_t v0 = a.e2v[(uint64_t)e * 2 + 0], v1 = a.e2v[(uint64_t)e * 2 + 1];
+  // rec: v[3], t0, t1, gp (= c k / l)
+  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *sdisp, const Args &a) {
+    const double *x0 = sxyz + (size_t)lc[0] * 3, *x1 = sxyz + (size_t)lc[1] * 3;
+    const double *u0 = sdisp + (size_t)lc[0] * 3, *u1 = sdisp + (size_t)lc[1] * 3;
     double r[3], v[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double a0 = a.xyz[(uint64_t)v0 * 3 + k], a1 = a.xyz[(uint64_t)v1 * 3 + k];
-      r[k] = a0 - a1;
-      v[k] = (a0 + a.disp[(uint64_t)v0 * 3 + k]) - (a1 + a.disp[(uint64_t)v1 * 3 + k]);
+      r[k] = x0[k] - x1[k];
+      v[k] = (x0[k] + u0[k]) - (x1[k] + u1[k]);
     }
     const double l0 = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
     const double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
@@ -262,22 +364,18 @@ struct ModelSpring3 {
 // DERIVED tet neo-Hookean: the reference's chain rule (solid_incompressive_hex.rs:86-148) with 4 nodes; the same
 // operations as k_neohookean_tet (assemble.cu). Record: g[4][3], z = F [3][3], dwrdc[6], ddwrddc[6][6], detwei.
 struct ModelNeoHookeanTet {
-  static constexpr int NNODE = 4, N = 3, REC = 64, HAS_GRAD = 1;
+  static constexpr int NNODE = 4, N = 3, NDIM = 3, REC = 64, HAS_GRAD = 1, NEEDS_DISP = 1;
   struct Args {
-    const uint32_t *e2v;
-    const double *xyz, *disp;
     double myu, lambda;
   };
-  __device__ static double make(double *rec, uint32_t e, const Args &a) {
+  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *sdisp, const Args &a) {
     const int IJ[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {1, 2}, {2, 0}};  // dudx.rs:36
     double X[4][3], U[4][3];
-    for (int n = 0; n < 4; ++n) {
-      const uint32_t v = a.e2v[(uint64_t)e * 4 + n];
+    for (int n = 0; n < 4; ++n)
       for (int d = 0; d < 3; ++d) {
-        X[n][d] = a.xyz[(uint64_t)v * 3 + d];
-        U[n][d] = a.disp[(uint64_t)v * 3 + d];
+        X[n][d] = sxyz[(size_t)lc[n] * 3 + d];
+        U[n][d] = sdisp[(size_t)lc[n] * 3 + d];
       }
-    }
     double g[4][3];
     const double vol = tet_vol_grad(g, X[0], X[1], X[2], X[3]);
     double dudx[3][3];
@@ -387,43 +485,74 @@ struct TileOut {      // where the tile's values go
   double *row2val;
   PackedView packed;  // the SpMV's native records
 };
+struct TilePlanView {
+  const uint32_t *nz2ptr;
+  const uint16_t *code16;
+  const uint32_t *tile_elem, *tile_vtx, *tile_meta;
+  const uint16_t *tile_lconn;
+  const uint32_t *row2idx;
+  uint32_t pair_base, rows, max_elem, max_slots, max_vtx, max_codes;
+  uint64_t nnz, num_rows, n_tiles;
+};
 
 template <class Model>
-__global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Model::Args args, const uint32_t *__restrict__ nz2ptr,
-                                                              const uint16_t *__restrict__ code16, const uint32_t *__restrict__ tile_elem,
-                                                              const uint32_t *__restrict__ tile_nelem, uint32_t pair_base,
-                                                              const uint32_t *__restrict__ row2idx, uint64_t nnz, uint64_t num_rows,
-                                                              uint64_t n_tiles, uint32_t AT_ROWS, uint32_t max_elem, uint32_t max_slots,
-                                                              const TileOut out, double *__restrict__ dw, double *__restrict__ w_elem) {
-  constexpr int NN = Model::N * Model::N, N = Model::N, NNODE = Model::NNODE, REC = Model::REC;
+__global__ void __launch_bounds__(AT_MAX_THREADS, 2) k_assemble_tile(const typename Model::Args args, const TilePlanView P,
+                                                                  const double *__restrict__ xyz, const double *__restrict__ disp,
+                                                                  const TileOut out, double *__restrict__ dw, double *__restrict__ w_elem) {
+  constexpr int NN = Model::N * Model::N, N = Model::N, NDIM = Model::NDIM, REC = Model::REC;
   extern __shared__ __align__(16) double at_smem[];
-  double *srec = at_smem;                                              // [n_le][REC]
-  double *sout = srec + (size_t)max_elem * REC;                        // [n_off + n_rows][NN]
-  uint32_t *sptr = reinterpret_cast<uint32_t *>(sout + (size_t)max_slots * NN);   // list offsets of the tile's slots (+1)
-  uint16_t *scode = reinterpret_cast<uint16_t *>(sptr + max_slots + 2);           // the tile's contribution codes
-  const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint64_t r0 = tile * AT_ROWS, r1 = min(r0 + (uint64_t)AT_ROWS, num_rows);
-    const uint32_t k0 = row2idx[r0], k1 = row2idx[r1], n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0);
-    const uint32_t n_le = tile_nelem[tile];
-    const uint32_t ob = nz2ptr[k0], oe = nz2ptr[k1], pb = nz2ptr[nnz + r0], pe = nz2ptr[nnz + r1];
-    const uint32_t n_oc = oe - ob;                                     // codes of the off-diagonal slots; the pairs follow
-    const uint32_t *elems = tile_elem + (pb - pair_base);
-    // ---- stage the tile's lists: after this no phase-2 instruction waits for global memory
-    for (uint32_t q = tid; q <= n_off; q += AT_THREADS) sptr[q] = nz2ptr[k0 + q] - ob;
-    for (uint32_t q = tid; q <= n_rows; q += AT_THREADS) sptr[n_off + 1 + q] = n_oc + (nz2ptr[nnz + r0 + q] - pb);
-    for (uint32_t q = tid; q < n_oc; q += AT_THREADS) scode[q] = code16[ob + q];
-    for (uint32_t q = tid; q < pe - pb; q += AT_THREADS) scode[n_oc + q] = code16[pb + q];
-    // ---- phase 1: per-element records into shared memory (one thread per listed element)
-    for (uint32_t le = tid; le < n_le; le += AT_THREADS) {
-      const uint32_t e = elems[le];
-      const double w = Model::make(srec + (size_t)le * REC, e, args);
-      if (Model::HAS_GRAD && w_elem) {
-        // the element's energy is recorded once: by the tile that holds its lowest-numbered row
-        uint32_t vmin = 0xFFFFFFFFu;
+  double *srec = at_smem;                                                   // [n_le][REC]
+  double *sout = srec + (size_t)P.max_elem * REC;                           // [n_off + n_rows][NN]
+  double *sxyz = sout + (size_t)P.max_slots * NN;                           // [n_lv][NDIM]
+  double *sdisp = sxyz + (size_t)P.max_vtx * NDIM;                          // [n_lv][NDIM] (energy models)
+  uint32_t *sptr = reinterpret_cast<uint32_t *>(sdisp + (Model::NEEDS_DISP ? (size_t)P.max_vtx * NDIM : 0));  // list offsets (+2)
+  uint32_t *smeta = sptr + P.max_slots + 2;                                 // [AT_META]
+  uint16_t *slc = reinterpret_cast<uint16_t *>(smeta + AT_META);            // [n_le][4] tile-local connectivity
+  uint16_t *scode = slc + (size_t)P.max_elem * 4;                           // the tile's contribution codes
+  const unsigned tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = T >> 5;
+  uint64_t tile = blockIdx.x;
+  uint32_t meta_next = (tile < P.n_tiles && tid < AT_META) ? P.tile_meta[tile * AT_META + tid] : 0u;
+  for (; tile < P.n_tiles; tile += gridDim.x) {
+    if (tid < AT_META) smeta[tid] = meta_next;
+    __syncthreads();
+    {  // prefetch the next tile's meta record (consumed at the top of the next iteration)
+      const uint64_t nt = tile + gridDim.x;
+      if (nt < P.n_tiles && tid < AT_META) meta_next = P.tile_meta[nt * AT_META + tid];
+    }
+    const uint64_t r0 = tile * P.rows, r1 = min(r0 + (uint64_t)P.rows, P.num_rows);
+    const uint32_t k0 = smeta[0], k1 = smeta[1], ob = smeta[2], oe = smeta[3], pb = smeta[4], pe = smeta[5];
+    const uint32_t n_le = smeta[6], n_lv = smeta[7], voff = smeta[8];
+    const uint32_t n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0), n_oc = oe - ob, eoff = pb - P.pair_base;
+    // ---- stage everything the tile needs: vertex data, local connectivity, list offsets, codes (all coalesced)
+    for (uint32_t q = tid; q < n_lv; q += T) {
+      const uint64_t v = P.tile_vtx[voff + q];
 #pragma unroll
-        for (int n = 0; n < NNODE; ++n) vmin = min(vmin, args.e2v[(uint64_t)e * NNODE + n]);
-        if (vmin / AT_ROWS == tile) w_elem[e] = w;
+      for (int d = 0; d < NDIM; ++d) sxyz[q * NDIM + d] = __ldg(xyz + v * NDIM + d);
+      if (Model::NEEDS_DISP) {
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) sdisp[q * NDIM + d] = __ldg(disp + v * NDIM + d);
+      }
+    }
+    {
+      const uint2 *src = reinterpret_cast<const uint2 *>(P.tile_lconn + (uint64_t)eoff * 4);
+      uint2 *dst = reinterpret_cast<uint2 *>(slc);
+      for (uint32_t q = tid; q < n_le; q += T) dst[q] = src[q];
+    }
+    for (uint32_t q = tid; q <= n_off; q += T) sptr[q] = P.nz2ptr[k0 + q] - ob;
+    for (uint32_t q = tid; q <= n_rows; q += T) sptr[n_off + 1 + q] = n_oc + (P.nz2ptr[P.nnz + r0 + q] - pb);
+    for (uint32_t q = tid; q < n_oc; q += T) scode[q] = P.code16[ob + q];
+    for (uint32_t q = tid; q < pe - pb; q += T) scode[n_oc + q] = P.code16[pb + q];
+    __syncthreads();
+    // ---- phase 1: per-element records (one thread per listed element), from shared memory only
+    for (uint32_t le = tid; le < n_le; le += T) {
+      const double w = Model::make(srec + (size_t)le * REC, slc + (size_t)le * 4, sxyz, sdisp, args);
+      if (Model::HAS_GRAD && w_elem) {
+        // the element's energy is recorded once: by the tile that holds its lowest-numbered vertex (the vertex list is sorted,
+        // so that is the smallest local id)
+        uint32_t lmin = slc[le * 4];
+#pragma unroll
+        for (int n = 1; n < Model::NNODE; ++n) lmin = min(lmin, (uint32_t)slc[le * 4 + n]);
+        if (P.tile_vtx[voff + lmin] / P.rows == tile) w_elem[P.tile_elem[eoff + le]] = w;
       }
     }
     __syncthreads();
@@ -466,14 +595,13 @@ __global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Mod
         for (int d = 0; d < N; ++d) gacc[d] = 0.0;
         const int base_lane = (int)(lane - t);
         for (uint32_t k = 0; k < nmax; k += AT_DIA_LANES) {
-          const uint32_t c = cb + k + t;
           double blk[NN], g[N];
 #pragma unroll
           for (int q = 0; q < NN; ++q) blk[q] = 0.0;
 #pragma unroll
           for (int d = 0; d < N; ++d) g[d] = 0.0;
           if (k + t < n) {
-            const uint32_t code = scode[c];
+            const uint32_t code = scode[cb + k + t];
             const double *rec = srec + (size_t)(code >> 4) * REC;
             const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
             Model::block(rec, i, j, args, blk);
@@ -481,7 +609,7 @@ __global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Mod
           }
 #pragma unroll
           for (int u = 0; u < AT_DIA_LANES; ++u) {
-            const bool on = k + u < n;  // (evaluated for the group's first lane: n is the same on the 4 lanes)
+            const bool on = k + u < n;  // n is the same on the lanes of a group
 #pragma unroll
             for (int q = 0; q < NN; ++q) {
               const double x = __shfl_sync(0xffffffffu, blk[q], base_lane + u);
@@ -511,33 +639,36 @@ __global__ void __launch_bounds__(AT_THREADS) k_assemble_tile(const typename Mod
     // ---- phase 3: contiguous, coalesced stores
     if (out.packed.base) {
       for (uint64_t pt = r0 / DFB_PK_RPT; pt * DFB_PK_RPT < r1; ++pt) {
-        const uint64_t pr0 = pt * DFB_PK_RPT, pr1 = min(pr0 + (uint64_t)DFB_PK_RPT, num_rows);
+        const uint64_t pr0 = pt * DFB_PK_RPT, pr1 = min(pr0 + (uint64_t)DFB_PK_RPT, P.num_rows);
         double *vals = pk_tile_values(out.packed, pt);                 // [8 diagonal blocks | the tile's off-diagonal blocks]
         const uint32_t nd = (uint32_t)(pr1 - pr0) * NN;
         const double *sd = sout + (size_t)(n_off + (pr0 - r0)) * NN;
-        for (uint32_t q = tid; q < nd; q += AT_THREADS) vals[q] = sd[q];
-        const uint32_t pk0 = row2idx[pr0], nb = row2idx[pr1] - pk0;
+        for (uint32_t q = tid; q < nd; q += T) vals[q] = sd[q];
+        const uint32_t pk0 = P.row2idx[pr0], nb = P.row2idx[pr1] - pk0;
         const double *sv = sout + (size_t)(pk0 - k0) * NN;
         double *ov = vals + DFB_PK_RPT * NN;
-        for (uint32_t q = tid; q < nb * NN; q += AT_THREADS) ov[q] = sv[q];
+        for (uint32_t q = tid; q < nb * NN; q += T) ov[q] = sv[q];
       }
     } else {
       double *ov = out.idx2val + (uint64_t)k0 * NN;
-      for (uint32_t q = tid; q < n_off * NN; q += AT_THREADS) ov[q] = sout[q];
+      for (uint32_t q = tid; q < n_off * NN; q += T) ov[q] = sout[q];
       double *od = out.row2val + r0 * NN;
       const double *sd = sout + (size_t)n_off * NN;
-      for (uint32_t q = tid; q < n_rows * NN; q += AT_THREADS) od[q] = sd[q];
+      for (uint32_t q = tid; q < n_rows * NN; q += T) od[q] = sd[q];
     }
-    __syncthreads();
+    // (the __syncthreads at the top of the next iteration orders these reads of sout / smeta before the next tile's writes)
   }
 }
 
 template <class Model>
-static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, dfb_bsr *m, double *dw, double *w_elem) {
+static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, const dfb_mesh *mesh, const dfb_vec *disp, dfb_bsr *m,
+                              double *dw, double *w_elem) {
   dfb_ctx *c = plan->ctx;
   constexpr int NN = Model::N * Model::N;
-  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double) +
-                      ((size_t)plan->tile_max_slots + 2) * sizeof(uint32_t) + (((size_t)plan->tile_max_codes + 7) & ~(size_t)7) * sizeof(uint16_t);
+  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN +
+                       (size_t)plan->tile_max_vtx * Model::NDIM * (Model::NEEDS_DISP ? 2 : 1)) * sizeof(double) +
+                      ((size_t)plan->tile_max_slots + 2 + AT_META) * sizeof(uint32_t) +
+                      ((size_t)plan->tile_max_elem * 4 + (((size_t)plan->tile_max_codes + 7) & ~(size_t)7)) * sizeof(uint16_t) + 16;
   if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
   TileOut out;
   if (dfb_bsr_packed_native(m)) {
@@ -553,16 +684,37 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
     out.idx2val = m->d_idx2val;
     out.row2val = m->d_row2val;
   }
+  TilePlanView P;
+  P.nz2ptr = plan->d_nz2ptr;
+  P.code16 = plan->d_code16;
+  P.tile_elem = plan->d_tile_elem;
+  P.tile_vtx = plan->d_tile_vtx;
+  P.tile_meta = plan->d_tile_meta;
+  P.tile_lconn = plan->d_tile_lconn;
+  P.row2idx = plan->pat->d_row2idx;
+  P.pair_base = plan->pair_base;
+  P.rows = plan->tile_rows;
+  P.max_elem = plan->tile_max_elem;
+  P.max_slots = plan->tile_max_slots;
+  P.max_vtx = plan->tile_max_vtx;
+  P.max_codes = plan->tile_max_codes;
+  P.nnz = plan->pat->nnz;
+  P.num_rows = plan->pat->num_blk;
+  P.n_tiles = plan->n_atiles;
+  // one thread per off-diagonal slot + AT_DIA_LANES per diagonal slot of the largest tile
+  const uint32_t max_off = plan->tile_max_slots > plan->tile_rows ? plan->tile_max_slots - plan->tile_rows : plan->tile_max_slots;
+  int threads = (int)(((max_off + 31) / 32 + (plan->tile_rows * AT_DIA_LANES + 31) / 32) * 32);
+  if (c->assemble_tile_threads > 0) threads = (int)c->assemble_tile_threads;
+  if (threads < 64) threads = 64;
+  if (threads > AT_MAX_THREADS) threads = AT_MAX_THREADS;
   DFB_CUDA(cudaFuncSetAttribute(k_assemble_tile<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  int per_sm = 1;
+  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tile<Model>, threads, smem));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 6) per_sm = 6;
   uint64_t g = plan->n_atiles;
   if (g > (uint64_t)c->sm_count * per_sm) g = (uint64_t)c->sm_count * per_sm;
   dfb_phase_begin(c, DFB_PH_TILE);
-  DFB_LAUNCH(c, k_assemble_tile<Model>, (unsigned)g, AT_THREADS, smem, args, plan->d_nz2ptr, plan->d_code16, plan->d_tile_elem,
-             plan->d_tile_nelem, plan->pair_base, plan->pat->d_row2idx, plan->pat->nnz, plan->pat->num_blk, plan->n_atiles,
-             plan->tile_rows, plan->tile_max_elem, plan->tile_max_slots, out, dw, w_elem);
+  DFB_LAUNCH(c, k_assemble_tile<Model>, (unsigned)g, threads, smem, args, P, mesh->d_xyz, disp ? disp->d : nullptr, out, dw, w_elem);
   dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
@@ -575,11 +727,9 @@ dfb_status dfb_assemble_tile_linear(dfb_plan *plan, int kind, const dfb_mesh *me
 #define LIN_CASE(K)                                    \
   case K: {                                            \
     ModelLinear<K>::Args a;                            \
-    a.e2v = mesh->d_elem2vtx;                          \
-    a.xyz = mesh->d_xyz;                               \
     a.p0 = p0;                                         \
     a.p1 = p1;                                         \
-    return launch_tile<ModelLinear<K>>(plan, a, m, nullptr, nullptr); \
+    return launch_tile<ModelLinear<K>>(plan, a, mesh, nullptr, m, nullptr, nullptr); \
   }
   switch (kind) {
     LIN_CASE(DFB_ELEM_LAPLACE_TRI2)
@@ -600,20 +750,14 @@ dfb_status dfb_assemble_tile_energy(dfb_plan *plan, int kind, const dfb_mesh *me
   if (plan->tile_state != 1) return DFB_ERR_UNSUPPORTED;
   if (kind == DFB_ELEM_SPRING3) {
     ModelSpring3::Args a;
-    a.e2v = mesh->d_elem2vtx;
-    a.xyz = mesh->d_xyz;
-    a.disp = disp->d;
     a.stiffness = p0;
-    return launch_tile<ModelSpring3>(plan, a, m, dw, w_elem);
+    return launch_tile<ModelSpring3>(plan, a, mesh, disp, m, dw, w_elem);
   }
   if (kind == DFB_ELEM_NEOHOOKEAN_TET && plan->ctx->assemble_tile_neo) {
     ModelNeoHookeanTet::Args a;
-    a.e2v = mesh->d_elem2vtx;
-    a.xyz = mesh->d_xyz;
-    a.disp = disp->d;
     a.myu = p0;
     a.lambda = p1;
-    return launch_tile<ModelNeoHookeanTet>(plan, a, m, dw, w_elem);
+    return launch_tile<ModelNeoHookeanTet>(plan, a, mesh, disp, m, dw, w_elem);
   }
   return DFB_ERR_UNSUPPORTED;
 }

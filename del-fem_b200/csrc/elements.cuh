@@ -161,3 +161,72 @@ template <> struct ElemGeo<DFB_ELEM_MASS_TET> {  // DERIVED (SURVEY A9'): consis
   }
 };
 
+// ---- node records: the per-(element, node) quarter of the element geometry, one aligned 32-byte sector each, so that a
+// contribution (e,i,j) needs exactly two sectors (two pairs of 128-bit loads). The block formulas repeat ElemGeo<KIND>::block
+// operation for operation (bit-identical results).
+struct __align__(32) NodeRec {
+  double v[4];
+};
+
+template <int KIND> struct NodeOps;  // make(geo, i) -> NodeRec ; block(ri, rj, p0, p1, e)
+
+template <> struct NodeOps<DFB_ELEM_LAPLACE_TRI2> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_LAPLACE_TRI2> &g, int i) { return {{g.dldx[0][i], g.dldx[1][i], g.area, 0.0}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double alpha, double, double *e) {
+    e[0] = alpha * a.v[2] * (a.v[0] * b.v[0] + a.v[1] * b.v[1]);
+  }
+};
+template <> struct NodeOps<DFB_ELEM_SOLID_LINEAR_TRI2> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_SOLID_LINEAR_TRI2> &g, int i) { return {{g.dldx[0][i], g.dldx[1][i], g.w, 0.0}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double lambda, double myu, double *e) {
+    const double w = a.v[2];
+    e[0] = 0.0; e[1] = 0.0; e[2] = 0.0; e[3] = 0.0;
+    e[0] += w * (lambda + myu) * a.v[0] * b.v[0];
+    e[2] += w * (lambda * a.v[0] * b.v[1] + myu * b.v[0] * a.v[1]);
+    e[1] += w * (lambda * a.v[1] * b.v[0] + myu * b.v[1] * a.v[0]);
+    e[3] += w * (lambda + myu) * a.v[1] * b.v[1];
+    const double dtmp1 = w * myu * (a.v[1] * b.v[1] + a.v[0] * b.v[0]);
+    e[0] += dtmp1;
+    e[3] += dtmp1;
+  }
+};
+template <> struct NodeOps<DFB_ELEM_LAPLACE_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_LAPLACE_TET> &g, int i) { return {{g.g[i][0], g.g[i][1], g.g[i][2], g.vol}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double alpha, double, double *e) {
+    e[0] = alpha * a.v[3] * (a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]);
+  }
+};
+template <> struct NodeOps<DFB_ELEM_SOLID_LINEAR_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_SOLID_LINEAR_TET> &g, int i) { return {{g.g[i][0], g.g[i][1], g.g[i][2], g.vol}}; }
+  __device__ static void block(const NodeRec &ri, const NodeRec &rj, double lambda, double myu, double *e) {
+    const double vol = ri.v[3];
+    double dtmp1 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) e[a + 3 * b] = vol * (lambda * ri.v[a] * rj.v[b] + myu * rj.v[a] * ri.v[b]);
+      dtmp1 += ri.v[a] * rj.v[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) e[a + 3 * a] += vol * myu * dtmp1;
+  }
+};
+template <> struct NodeOps<DFB_ELEM_MASS_TET> {
+  static constexpr bool OK = true;
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_MASS_TET> &g, int i) { return {{(double)i, 0.0, 0.0, g.vol}}; }
+  __device__ static void block(const NodeRec &a, const NodeRec &b, double rho, double, double *e) {
+    const double v = rho * a.v[3] / 20.0 * (a.v[0] == b.v[0] ? 2.0 : 1.0);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) e[q] = (q == 0 || q == 4 || q == 8) ? v : 0.0;
+  }
+};
+template <> struct NodeOps<DFB_ELEM_COT_LAPLACE_TRI3> {
+  static constexpr bool OK = false;  // the cotangent block of (i,j) needs the angle at the THIRD corner: stays on the ElemGeo path
+  __device__ static NodeRec make(const ElemGeo<DFB_ELEM_COT_LAPLACE_TRI3> &, int) { return {{0, 0, 0, 0}}; }
+  __device__ static void block(const NodeRec &, const NodeRec &, double, double, double *) {}
+};
+
