@@ -269,8 +269,8 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
 
 // ------------------------------------------------------------------------------------------------ models
 // A model provides: NNODE, N, NDIM, REC (doubles per element record), HAS_GRAD, NEEDS_DISP, Args (kernel parameters),
-//   make(rec, lc, sxyz, sdisp, args)  -> evaluates the record of one element into shared memory from the tile's STAGED vertex data
-//                                        (lc = the element's tile-local vertex ids); returns the element's energy
+//   make(rec, px, pu, args)           -> evaluates the record of one element into shared memory; px / pu = per-node pointers to the
+//                                        coordinates / displacements (staged in shared memory, or global); returns the element's energy
 //   block(rec, i, j, args, blk)       -> block (i,j) of the element matrix, column-major N x N
 //   grad(rec, i, args, g)             -> gradient of node i (energy models)
 
@@ -285,10 +285,7 @@ struct ModelLinear {
   struct Args {
     double p0, p1;
   };
-  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *, const Args &a) {
-    const double *p[NNODE];
-#pragma unroll
-    for (int n = 0; n < NNODE; ++n) p[n] = sxyz + (size_t)lc[n] * NDIM;
+  __device__ static double make(double *rec, const double *const *p, const double *const *, const Args &a) {
     G g;
     g.init(p, a.p0, a.p1);
     if constexpr (NO::OK) {
@@ -324,9 +321,8 @@ struct ModelSpring3 {
     double stiffness;
   };
   // rec: v[3], t0, t1, gp (= c k / l)
-  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *sdisp, const Args &a) {
-    const double *x0 = sxyz + (size_t)lc[0] * 3, *x1 = sxyz + (size_t)lc[1] * 3;
-    const double *u0 = sdisp + (size_t)lc[0] * 3, *u1 = sdisp + (size_t)lc[1] * 3;
+  __device__ static double make(double *rec, const double *const *px, const double *const *pu, const Args &a) {
+    const double *x0 = px[0], *x1 = px[1], *u0 = pu[0], *u1 = pu[1];
     double r[3], v[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -368,13 +364,13 @@ struct ModelNeoHookeanTet {
   struct Args {
     double myu, lambda;
   };
-  __device__ static double make(double *rec, const uint16_t *lc, const double *sxyz, const double *sdisp, const Args &a) {
+  __device__ static double make(double *rec, const double *const *px, const double *const *pu, const Args &a) {
     const int IJ[6][2] = {{0, 0}, {1, 1}, {2, 2}, {0, 1}, {1, 2}, {2, 0}};  // dudx.rs:36
     double X[4][3], U[4][3];
     for (int n = 0; n < 4; ++n)
       for (int d = 0; d < 3; ++d) {
-        X[n][d] = sxyz[(size_t)lc[n] * 3 + d];
-        U[n][d] = sdisp[(size_t)lc[n] * 3 + d];
+        X[n][d] = px[n][d];
+        U[n][d] = pu[n][d];
       }
     double g[4][3];
     const double vol = tet_vol_grad(g, X[0], X[1], X[2], X[3]);
@@ -495,20 +491,25 @@ struct TilePlanView {
   uint64_t nnz, num_rows, n_tiles;
 };
 
-template <class Model>
+// Experiment flags (ctx option "assemble_tile_flags", measured in profiles/): STAGE_LISTS = the tile's list offsets and codes are
+// copied to shared memory first (else read from global memory inside the slot loop); DIA_QUADS = 4 lanes share a diagonal slot
+// (else one thread per slot); STAGE_VTX = the tile's vertex coordinates are staged in shared memory through the tile's unique vertex
+// list and local connectivity (else every listed element reads connectivity + coordinates from global memory).
+template <class Model, bool STAGE_LISTS, bool DIA_QUADS, bool STAGE_VTX>
 __global__ void __launch_bounds__(AT_MAX_THREADS, 2) k_assemble_tile(const typename Model::Args args, const TilePlanView P,
-                                                                  const double *__restrict__ xyz, const double *__restrict__ disp,
-                                                                  const TileOut out, double *__restrict__ dw, double *__restrict__ w_elem) {
-  constexpr int NN = Model::N * Model::N, N = Model::N, NDIM = Model::NDIM, REC = Model::REC;
+                                                                     const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                                     const double *__restrict__ disp, const TileOut out,
+                                                                     double *__restrict__ dw, double *__restrict__ w_elem) {
+  constexpr int NN = Model::N * Model::N, N = Model::N, NDIM = Model::NDIM, REC = Model::REC, NNODE = Model::NNODE;
   extern __shared__ __align__(16) double at_smem[];
   double *srec = at_smem;                                                   // [n_le][REC]
   double *sout = srec + (size_t)P.max_elem * REC;                           // [n_off + n_rows][NN]
   double *sxyz = sout + (size_t)P.max_slots * NN;                           // [n_lv][NDIM]
-  double *sdisp = sxyz + (size_t)P.max_vtx * NDIM;                          // [n_lv][NDIM] (energy models)
-  uint32_t *sptr = reinterpret_cast<uint32_t *>(sdisp + (Model::NEEDS_DISP ? (size_t)P.max_vtx * NDIM : 0));  // list offsets (+2)
-  uint32_t *smeta = sptr + P.max_slots + 2;                                 // [AT_META]
+  double *sdisp = sxyz + (STAGE_VTX ? (size_t)P.max_vtx * NDIM : 0);        // [n_lv][NDIM] (energy models)
+  uint32_t *sptr = reinterpret_cast<uint32_t *>(sdisp + ((STAGE_VTX && Model::NEEDS_DISP) ? (size_t)P.max_vtx * NDIM : 0));
+  uint32_t *smeta = sptr + (STAGE_LISTS ? P.max_slots + 2 : 0);             // [AT_META]
   uint16_t *slc = reinterpret_cast<uint16_t *>(smeta + AT_META);            // [n_le][4] tile-local connectivity
-  uint16_t *scode = slc + (size_t)P.max_elem * 4;                           // the tile's contribution codes
+  uint16_t *scode = slc + (STAGE_VTX ? (size_t)P.max_elem * 4 : 0);         // the tile's contribution codes
   const unsigned tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = T >> 5;
   uint64_t tile = blockIdx.x;
   uint32_t meta_next = (tile < P.n_tiles && tid < AT_META) ? P.tile_meta[tile * AT_META + tid] : 0u;
@@ -523,68 +524,123 @@ __global__ void __launch_bounds__(AT_MAX_THREADS, 2) k_assemble_tile(const typen
     const uint32_t k0 = smeta[0], k1 = smeta[1], ob = smeta[2], oe = smeta[3], pb = smeta[4], pe = smeta[5];
     const uint32_t n_le = smeta[6], n_lv = smeta[7], voff = smeta[8];
     const uint32_t n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0), n_oc = oe - ob, eoff = pb - P.pair_base;
-    // ---- stage everything the tile needs: vertex data, local connectivity, list offsets, codes (all coalesced)
-    for (uint32_t q = tid; q < n_lv; q += T) {
-      const uint64_t v = P.tile_vtx[voff + q];
+    if (STAGE_VTX) {
+      for (uint32_t q = tid; q < n_lv; q += T) {
+        const uint64_t v = P.tile_vtx[voff + q];
 #pragma unroll
-      for (int d = 0; d < NDIM; ++d) sxyz[q * NDIM + d] = __ldg(xyz + v * NDIM + d);
-      if (Model::NEEDS_DISP) {
+        for (int d = 0; d < NDIM; ++d) sxyz[q * NDIM + d] = __ldg(xyz + v * NDIM + d);
+        if (Model::NEEDS_DISP) {
 #pragma unroll
-        for (int d = 0; d < NDIM; ++d) sdisp[q * NDIM + d] = __ldg(disp + v * NDIM + d);
+          for (int d = 0; d < NDIM; ++d) sdisp[q * NDIM + d] = __ldg(disp + v * NDIM + d);
+        }
       }
-    }
-    {
       const uint2 *src = reinterpret_cast<const uint2 *>(P.tile_lconn + (uint64_t)eoff * 4);
       uint2 *dst = reinterpret_cast<uint2 *>(slc);
       for (uint32_t q = tid; q < n_le; q += T) dst[q] = src[q];
     }
-    for (uint32_t q = tid; q <= n_off; q += T) sptr[q] = P.nz2ptr[k0 + q] - ob;
-    for (uint32_t q = tid; q <= n_rows; q += T) sptr[n_off + 1 + q] = n_oc + (P.nz2ptr[P.nnz + r0 + q] - pb);
-    for (uint32_t q = tid; q < n_oc; q += T) scode[q] = P.code16[ob + q];
-    for (uint32_t q = tid; q < pe - pb; q += T) scode[n_oc + q] = P.code16[pb + q];
-    __syncthreads();
-    // ---- phase 1: per-element records (one thread per listed element), from shared memory only
+    if (STAGE_LISTS) {
+      for (uint32_t q = tid; q <= n_off; q += T) sptr[q] = P.nz2ptr[k0 + q] - ob;
+      for (uint32_t q = tid; q <= n_rows; q += T) sptr[n_off + 1 + q] = n_oc + (P.nz2ptr[P.nnz + r0 + q] - pb);
+      for (uint32_t q = tid; q < n_oc; q += T) scode[q] = P.code16[ob + q];
+      for (uint32_t q = tid; q < pe - pb; q += T) scode[n_oc + q] = P.code16[pb + q];
+    }
+    if (STAGE_VTX) __syncthreads();
+    // ---- phase 1: per-element records (one thread per listed element)
     for (uint32_t le = tid; le < n_le; le += T) {
-      const double w = Model::make(srec + (size_t)le * REC, slc + (size_t)le * 4, sxyz, sdisp, args);
-      if (Model::HAS_GRAD && w_elem) {
-        // the element's energy is recorded once: by the tile that holds its lowest-numbered vertex (the vertex list is sorted,
-        // so that is the smallest local id)
-        uint32_t lmin = slc[le * 4];
+      const double *px[NNODE], *pu[NNODE];
+      uint32_t vmin = 0xFFFFFFFFu;
+      if (STAGE_VTX) {
+        uint32_t lmin = 0xFFFFu;
 #pragma unroll
-        for (int n = 1; n < Model::NNODE; ++n) lmin = min(lmin, (uint32_t)slc[le * 4 + n]);
-        if (P.tile_vtx[voff + lmin] / P.rows == tile) w_elem[P.tile_elem[eoff + le]] = w;
+        for (int n = 0; n < NNODE; ++n) {
+          const uint32_t lv = slc[le * 4 + n];
+          px[n] = sxyz + (size_t)lv * NDIM;
+          pu[n] = sdisp + (size_t)lv * NDIM;
+          lmin = min(lmin, lv);
+        }
+        if (Model::HAS_GRAD && w_elem) vmin = P.tile_vtx[voff + lmin];  // the vertex list is sorted: smallest local id = smallest vertex
+      } else {
+        const uint32_t e = P.tile_elem[eoff + le];
+#pragma unroll
+        for (int n = 0; n < NNODE; ++n) {
+          const uint32_t v = e2v[(uint64_t)e * NNODE + n];
+          px[n] = xyz + (uint64_t)v * NDIM;
+          pu[n] = Model::NEEDS_DISP ? disp + (uint64_t)v * NDIM : nullptr;
+          vmin = min(vmin, v);
+        }
       }
+      const double w = Model::make(srec + (size_t)le * REC, px, pu, args);
+      // the element's energy is recorded once: by the tile that holds its lowest-numbered vertex
+      if (Model::HAS_GRAD && w_elem && vmin / P.rows == tile) w_elem[P.tile_elem[eoff + le]] = w;
     }
     __syncthreads();
-    // ---- phase 2a: off-diagonal slots, one thread each (lists of ~4-6 contributions)
-    const uint32_t n_off_warps = (n_off + 31) >> 5;
-    const uint32_t n_dia_warps = (n_rows * AT_DIA_LANES + 31) >> 5;
-    for (uint32_t w = wid; w < n_off_warps + n_dia_warps; w += nwarp) {
-      if (w < n_off_warps) {
+    // ---- phase 2: slots. Off-diagonal slots: one thread each (lists of ~4-6 contributions). Diagonal slots: one thread each, or
+    // (DIA_QUADS) AT_DIA_LANES lanes each: the lanes form the blocks of consecutive contributions in parallel, the group's first
+    // lane adds them in list order (ascending element = the serial loop's order, same bits)
+    const uint32_t n_plain = DIA_QUADS ? n_off : n_off + n_rows;
+    const uint32_t n_plain_warps = (n_plain + 31) >> 5;
+    const uint32_t n_dia_warps = DIA_QUADS ? (n_rows * AT_DIA_LANES + 31) >> 5 : 0u;
+    for (uint32_t w = wid; w < n_plain_warps + n_dia_warps; w += nwarp) {
+      if (w < n_plain_warps) {
         const uint32_t s = (w << 5) + lane;
-        if (s < n_off) {
-          double acc[NN];
+        if (s < n_plain) {
+          const bool is_dia = s >= n_off;
+          double acc[NN], gacc[N];
 #pragma unroll
           for (int q = 0; q < NN; ++q) acc[q] = 0.0;
-          const uint32_t cb = sptr[s], ce = sptr[s + 1];
+#pragma unroll
+          for (int d = 0; d < N; ++d) gacc[d] = 0.0;
+          uint32_t cb, ce;
+          const uint16_t *codes;
+          if (STAGE_LISTS) {
+            const uint32_t si = is_dia ? s + 1 : s;
+            cb = sptr[si];
+            ce = sptr[si + 1];
+            codes = scode;
+          } else {
+            const uint64_t slot = is_dia ? P.nnz + r0 + (s - n_off) : (uint64_t)k0 + s;
+            cb = P.nz2ptr[slot];
+            ce = P.nz2ptr[slot + 1];
+            codes = P.code16;
+          }
           for (uint32_t c = cb; c < ce; ++c) {
-            const uint32_t code = scode[c];
+            const uint32_t code = codes[c];
+            const double *rec = srec + (size_t)(code >> 4) * REC;
+            const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
             double blk[NN];
-            Model::block(srec + (size_t)(code >> 4) * REC, (int)((code >> 2) & 3u), (int)(code & 3u), args, blk);
+            Model::block(rec, i, j, args, blk);
 #pragma unroll
             for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+            if (Model::HAS_GRAD && dw && is_dia) {
+              double g[N];
+              Model::grad(rec, i, args, g);
+#pragma unroll
+              for (int d = 0; d < N; ++d) gacc[d] += g[d];
+            }
           }
           double *dst = sout + (size_t)s * NN;
 #pragma unroll
           for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+          if (Model::HAS_GRAD && dw && is_dia) {
+#pragma unroll
+            for (int d = 0; d < N; ++d) dw[(r0 + (s - n_off)) * N + d] = gacc[d];
+          }
         }
       } else {
-        // ---- phase 2b: diagonal slots, AT_DIA_LANES lanes each: the lanes form the blocks of consecutive contributions in
-        // parallel, the group's first lane adds them in list order (ascending element = the serial loop's order, same bits)
-        const uint32_t v = ((w - n_off_warps) << 5) + lane;
+        const uint32_t v = ((w - n_plain_warps) << 5) + lane;
         const uint32_t row = v / AT_DIA_LANES, t = v % AT_DIA_LANES;
         const bool live = row < n_rows;
-        const uint32_t cb = live ? sptr[n_off + 1 + row] : 0u, ce = live ? sptr[n_off + 1 + row + 1] : 0u;
+        uint32_t cb = 0, ce = 0;
+        const uint16_t *codes = STAGE_LISTS ? scode : P.code16;
+        if (live) {
+          if (STAGE_LISTS) {
+            cb = sptr[n_off + 1 + row];
+            ce = sptr[n_off + 1 + row + 1];
+          } else {
+            cb = P.nz2ptr[P.nnz + r0 + row];
+            ce = P.nz2ptr[P.nnz + r0 + row + 1];
+          }
+        }
         uint32_t n = ce - cb, nmax = n;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
@@ -601,7 +657,7 @@ __global__ void __launch_bounds__(AT_MAX_THREADS, 2) k_assemble_tile(const typen
 #pragma unroll
           for (int d = 0; d < N; ++d) g[d] = 0.0;
           if (k + t < n) {
-            const uint32_t code = scode[cb + k + t];
+            const uint32_t code = codes[cb + k + t];
             const double *rec = srec + (size_t)(code >> 4) * REC;
             const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
             Model::block(rec, i, j, args, blk);
@@ -665,25 +721,6 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
                               double *dw, double *w_elem) {
   dfb_ctx *c = plan->ctx;
   constexpr int NN = Model::N * Model::N;
-  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN +
-                       (size_t)plan->tile_max_vtx * Model::NDIM * (Model::NEEDS_DISP ? 2 : 1)) * sizeof(double) +
-                      ((size_t)plan->tile_max_slots + 2 + AT_META) * sizeof(uint32_t) +
-                      ((size_t)plan->tile_max_elem * 4 + (((size_t)plan->tile_max_codes + 7) & ~(size_t)7)) * sizeof(uint16_t) + 16;
-  if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
-  TileOut out;
-  if (dfb_bsr_packed_native(m)) {
-    DFB_TRY(dfb_bsr_packed_overwrite(m));
-    out.packed = dfb_bsr_packed_view(m);
-    out.idx2val = out.row2val = nullptr;
-  } else {
-    DFB_TRY(dfb_bsr_canon_overwrite(m));
-    out.packed.base = nullptr;
-    out.packed.tile_off = nullptr;
-    out.packed.NN = NN;
-    out.packed.has_dia = 1;
-    out.idx2val = m->d_idx2val;
-    out.row2val = m->d_row2val;
-  }
   TilePlanView P;
   P.nz2ptr = plan->d_nz2ptr;
   P.code16 = plan->d_code16;
@@ -701,20 +738,53 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
   P.nnz = plan->pat->nnz;
   P.num_rows = plan->pat->num_blk;
   P.n_tiles = plan->n_atiles;
-  // one thread per off-diagonal slot + AT_DIA_LANES per diagonal slot of the largest tile
+  const int flags = (int)(c->assemble_tile_flags & 7);
+  const bool stage_lists = flags & 1, dia_quads = flags & 2, stage_vtx = flags & 4;
+  // one thread per off-diagonal slot + (quads: AT_DIA_LANES, else 1) per diagonal slot of the largest tile
   const uint32_t max_off = plan->tile_max_slots > plan->tile_rows ? plan->tile_max_slots - plan->tile_rows : plan->tile_max_slots;
-  int threads = (int)(((max_off + 31) / 32 + (plan->tile_rows * AT_DIA_LANES + 31) / 32) * 32);
+  int threads = dia_quads ? (int)(((max_off + 31) / 32 + (plan->tile_rows * AT_DIA_LANES + 31) / 32) * 32) : (int)((plan->tile_max_slots + 31) / 32 * 32);
   if (c->assemble_tile_threads > 0) threads = (int)c->assemble_tile_threads;
   if (threads < 64) threads = 64;
   if (threads > AT_MAX_THREADS) threads = AT_MAX_THREADS;
-  DFB_CUDA(cudaFuncSetAttribute(k_assemble_tile<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN +
+                       (stage_vtx ? (size_t)plan->tile_max_vtx * Model::NDIM * (Model::NEEDS_DISP ? 2 : 1) : 0)) * sizeof(double) +
+                      ((stage_lists ? (size_t)plan->tile_max_slots + 2 : 0) + AT_META) * sizeof(uint32_t) +
+                      ((stage_vtx ? (size_t)plan->tile_max_elem * 4 : 0) + (stage_lists ? (((size_t)plan->tile_max_codes + 7) & ~(size_t)7) : 0)) * sizeof(uint16_t) + 16;
+  if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
+  TileOut out;
+  if (dfb_bsr_packed_native(m)) {
+    DFB_TRY(dfb_bsr_packed_overwrite(m));
+    out.packed = dfb_bsr_packed_view(m);
+    out.idx2val = out.row2val = nullptr;
+  } else {
+    DFB_TRY(dfb_bsr_canon_overwrite(m));
+    out.packed.base = nullptr;
+    out.packed.tile_off = nullptr;
+    out.packed.NN = NN;
+    out.packed.has_dia = 1;
+    out.idx2val = m->d_idx2val;
+    out.row2val = m->d_row2val;
+  }
+  void (*kern)(const typename Model::Args, const TilePlanView, const uint32_t *, const double *, const double *, const TileOut, double *, double *) = nullptr;
+  switch (flags) {
+    case 0: kern = k_assemble_tile<Model, false, false, false>; break;
+    case 1: kern = k_assemble_tile<Model, true, false, false>; break;
+    case 2: kern = k_assemble_tile<Model, false, true, false>; break;
+    case 3: kern = k_assemble_tile<Model, true, true, false>; break;
+    case 4: kern = k_assemble_tile<Model, false, false, true>; break;
+    case 5: kern = k_assemble_tile<Model, true, false, true>; break;
+    case 6: kern = k_assemble_tile<Model, false, true, true>; break;
+    default: kern = k_assemble_tile<Model, true, true, true>; break;
+  }
+  DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tile<Model>, threads, smem));
+  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) per_sm = 1;
   uint64_t g = plan->n_atiles;
   if (g > (uint64_t)c->sm_count * per_sm) g = (uint64_t)c->sm_count * per_sm;
   dfb_phase_begin(c, DFB_PH_TILE);
-  DFB_LAUNCH(c, k_assemble_tile<Model>, (unsigned)g, threads, smem, args, P, mesh->d_xyz, disp ? disp->d : nullptr, out, dw, w_elem);
+  kern<<<(unsigned)g, threads, smem, c->stream>>>(args, P, mesh->d_elem2vtx, mesh->d_xyz, disp ? disp->d : nullptr, out, dw, w_elem);
+  c->launches += 1;
   dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return DFB_OK;

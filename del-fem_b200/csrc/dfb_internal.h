@@ -124,6 +124,7 @@ struct dfb_ctx {
   int64_t assemble_variant = 0;
   int64_t assemble_tile_rows = 0;     // 0: chosen per mesh (about 224 off-diagonal slots per tile)
   int64_t assemble_tile_threads = 0;  // 0: one thread per off-diagonal slot + 4 per diagonal slot of the largest tile
+  int64_t assemble_tile_flags = 0;    // experiment switches of the tile kernel: 1 stage lists, 2 diagonal quads, 4 stage vertex data
   int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
