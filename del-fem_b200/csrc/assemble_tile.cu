@@ -16,7 +16,7 @@
 #include "elements.cuh"
 #include "reduce.cuh"
 
-static const int AT_MAX_THREADS = 512;
+static const int AT_MAX_THREADS = 384;
 static const int AT_BUILD_THREADS = 256;
 static const int AT_DIA_LANES = 4;    // lanes that share one diagonal slot (its list is ~4x longer than an off-diagonal one)
 static const int AT_PAIR_CAP = 2048;  // (row, element) pairs per tile the builder can sort in shared memory
@@ -274,49 +274,33 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
 //   block(rec, i, j, args, blk)       -> block (i,j) of the element matrix, column-major N x N
 //   grad(rec, i, args, g)             -> gradient of node i (energy models)
 
-// linear kinds. Record = NNODE node records of 4 doubles (two 16-byte shared-memory loads per node) where the block of (i,j) only
-// needs the two nodes' data (NodeOps<KIND>::OK), else ElemGeo<KIND> itself. block() IS the reference formula, operation for operation.
+// linear kinds: the record is ElemGeo<KIND> itself and block() IS the reference formula (ElemGeo<KIND>::block). The record stride
+// is an ODD number of doubles (tet: 13): threads of a warp read the records of different elements at the same offset, and an odd
+// stride spreads those reads over the shared-memory banks. (ncu: 16-double node records — two 16-byte loads per node — put every
+// lane on the same bank: 1.33 G shared-memory wavefronts, L1 81 % busy, 6.6 ms; the 13-double records: 0.75 G.)
 template <int KIND>
 struct ModelLinear {
   using G = ElemGeo<KIND>;
-  using NO = NodeOps<KIND>;
   static constexpr int NNODE = G::NNODE, N = G::N, NDIM = G::NDIM, HAS_GRAD = 0, NEEDS_DISP = 0;
-  static constexpr int REC = NO::OK ? NNODE * 4 : (int)((sizeof(G) + 15) / 16) * 2;
+  static constexpr int REC = (int)((sizeof(G) + 7) / 8) | 1;
   struct Args {
     double p0, p1;
   };
   __device__ static double make(double *rec, const double *const *p, const double *const *, const Args &a) {
     G g;
     g.init(p, a.p0, a.p1);
-    if constexpr (NO::OK) {
-#pragma unroll
-      for (int n = 0; n < NNODE; ++n) {
-        const NodeRec r = NO::make(g, n);
-        double2 *dst = reinterpret_cast<double2 *>(rec + n * 4);
-        dst[0] = make_double2(r.v[0], r.v[1]);
-        dst[1] = make_double2(r.v[2], r.v[3]);
-      }
-    } else {
-      *reinterpret_cast<G *>(rec) = g;
-    }
+    *reinterpret_cast<G *>(rec) = g;
     return 0.0;
   }
   __device__ static void block(const double *rec, int i, int j, const Args &a, double *blk) {
-    if constexpr (NO::OK) {
-      const double2 *pa = reinterpret_cast<const double2 *>(rec + i * 4), *pb = reinterpret_cast<const double2 *>(rec + j * 4);
-      const double2 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
-      const NodeRec ra = {{a0.x, a0.y, a1.x, a1.y}}, rb = {{b0.x, b0.y, b1.x, b1.y}};
-      NO::block(ra, rb, a.p0, a.p1, blk);
-    } else {
-      reinterpret_cast<const G *>(rec)->block(i, j, a.p0, a.p1, blk);
-    }
+    reinterpret_cast<const G *>(rec)->block(i, j, a.p0, a.p1, blk);
   }
   __device__ static void grad(const double *, int, const Args &, double *) {}
 };
 
 // spring3::wdwddw_squared_length_difference (del-fem-cpu/src/spring3.rs:1-28): same operations as k_spring3 (assemble.cu)
 struct ModelSpring3 {
-  static constexpr int NNODE = 2, N = 3, NDIM = 3, REC = 6, HAS_GRAD = 1, NEEDS_DISP = 1;
+  static constexpr int NNODE = 2, N = 3, NDIM = 3, REC = 7, HAS_GRAD = 1, NEEDS_DISP = 1;
   struct Args {
     double stiffness;
   };
@@ -360,7 +344,7 @@ struct ModelSpring3 {
 // DERIVED tet neo-Hookean: the reference's chain rule (solid_incompressive_hex.rs:86-148) with 4 nodes; the same
 // operations as k_neohookean_tet (assemble.cu). Record: g[4][3], z = F [3][3], dwrdc[6], ddwrddc[6][6], detwei.
 struct ModelNeoHookeanTet {
-  static constexpr int NNODE = 4, N = 3, NDIM = 3, REC = 64, HAS_GRAD = 1, NEEDS_DISP = 1;
+  static constexpr int NNODE = 4, N = 3, NDIM = 3, REC = 65, HAS_GRAD = 1, NEEDS_DISP = 1;
   struct Args {
     double myu, lambda;
   };
@@ -496,7 +480,7 @@ struct TilePlanView {
 // (else one thread per slot); STAGE_VTX = the tile's vertex coordinates are staged in shared memory through the tile's unique vertex
 // list and local connectivity (else every listed element reads connectivity + coordinates from global memory).
 template <class Model, bool STAGE_LISTS, bool DIA_QUADS, bool STAGE_VTX>
-__global__ void __launch_bounds__(AT_MAX_THREADS, 2) k_assemble_tile(const typename Model::Args args, const TilePlanView P,
+__global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename Model::Args args, const TilePlanView P,
                                                                      const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
                                                                      const double *__restrict__ disp, const TileOut out,
                                                                      double *__restrict__ dw, double *__restrict__ w_elem) {
