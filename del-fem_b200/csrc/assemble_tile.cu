@@ -12,16 +12,21 @@
 //     order => same bits as the serial loop; the thread of a row's diagonal slot also gathers the row's gradient (energy models);
 //   * phase 3: the tile's values leave through shared memory as contiguous, coalesced stores — straight into the tile-packed SpMV
 //     records when those are the matrix's native layout (no pack pass, no second copy), else into the canonical arrays.
+// Measured on S10 (19.8 M tets, profiles/r2_assemble_tile_*): 4.5 ms (1.2 TB/s algorithmic), DRAM traffic == algorithmic bytes;
+// bound by shared-memory wavefronts of the record reads (random element per lane) with the fp64 pipe at ~30 %: the bit-exact
+// formulas cost ~74 non-fused fp64 instructions per contribution, 1.6 ms of fp64 issue alone. Variants that were built, measured
+// SLOWER and removed (gpurun_out logs summarised in profiles/README.md): staging the tile's lists in shared memory (+2..12 %),
+// 4 lanes per diagonal slot with ordered shuffles (+27..50 %), staging vertex coordinates through a per-tile vertex list (+0..7 %),
+// 16-double node records read with 16-byte loads (every lane on one bank: +45 %), tiles of 24 / 32 rows (+29 % / +70 %).
 #include "dfb_internal.h"
 #include "elements.cuh"
 #include "reduce.cuh"
 
 static const int AT_MAX_THREADS = 384;
 static const int AT_BUILD_THREADS = 256;
-static const int AT_DIA_LANES = 4;    // lanes that share one diagonal slot (its list is ~4x longer than an off-diagonal one)
 static const int AT_PAIR_CAP = 2048;  // (row, element) pairs per tile the builder can sort in shared memory
-static const int AT_ELEM_CAP = 1024;  // unique elements per tile (their <= 4096 vertex references are sorted in shared memory)
-static const int AT_META = 12;        // u32 per tile: k0, k1, ob, oe, pb, pe, n_le, n_lv, vtx_off, pad x 3
+static const int AT_ELEM_CAP = 4095;  // tile-local element index must fit 12 bits of the 16-bit contribution code
+static const int AT_META = 8;         // u32 per tile: k0, k1, ob, oe, pb, pe, n_elem, pad
 
 // ------------------------------------------------------------------------------------------------ tile plan
 __device__ __forceinline__ void bitonic_sort_smem(uint32_t *keys, uint32_t P) {
@@ -76,22 +81,15 @@ __device__ __forceinline__ uint32_t lower_bound_smem(const uint32_t *a, uint32_t
   return lo;
 }
 
-// one CTA per tile. FILL = false: count the tile's unique elements / vertices (sizes for the scans); FILL = true: write the
-// element list, the vertex list, the tile-local connectivity, the per-tile meta record and the 16-bit contribution codes
-template <bool FILL>
+// one CTA per tile: the tile's sorted unique element list, its meta record and the 16-bit recoding of its contribution lists
 __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
                                                                  uint64_t nnz, uint64_t num_rows, int nn, const uint32_t *__restrict__ row2idx,
-                                                                 const uint32_t *__restrict__ e2v, uint32_t *__restrict__ tile_nvtx,
-                                                                 const uint32_t *__restrict__ vtx_off, uint32_t *__restrict__ tile_elem,
-                                                                 uint32_t *__restrict__ tile_vtx, uint16_t *__restrict__ tile_lconn,
-                                                                 uint32_t *__restrict__ tile_meta, uint16_t *__restrict__ code16,
-                                                                 uint32_t *stats, uint64_t n_tiles, uint32_t AT_ROWS) {
-  extern __shared__ uint32_t tb_smem[];
-  uint32_t *keys = tb_smem;                       // [AT_PAIR_CAP]   pairs' elements, sorted
-  uint32_t *uniq = keys + AT_PAIR_CAP;            // [AT_ELEM_CAP]   unique elements
-  uint32_t *vkeys = uniq + AT_ELEM_CAP;           // [4 * AT_ELEM_CAP] vertex references, sorted
-  uint32_t *uvtx = vkeys + 4 * AT_ELEM_CAP;       // [4 * AT_ELEM_CAP] unique vertices
-  uint32_t *cnt = uvtx + 4 * AT_ELEM_CAP;         // [AT_BUILD_THREADS]
+                                                                 uint32_t *__restrict__ tile_elem, uint32_t *__restrict__ tile_meta,
+                                                                 uint16_t *__restrict__ code16, uint32_t *stats, uint64_t n_tiles,
+                                                                 uint32_t AT_ROWS) {
+  __shared__ uint32_t keys[AT_PAIR_CAP];
+  __shared__ uint32_t uniq[AT_PAIR_CAP];
+  __shared__ uint32_t cnt[AT_BUILD_THREADS];
   const uint32_t pair_base = nz2ptr[nnz];
   const uint32_t nn2 = (uint32_t)(nn * nn);
   const unsigned tid = threadIdx.x;
@@ -108,61 +106,16 @@ __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t 
     for (uint32_t i = tid; i < P; i += AT_BUILD_THREADS) keys[i] = (i < np) ? contrib[pb + i] / nn2 : 0xFFFFFFFFu;
     __syncthreads();
     bitonic_sort_smem(keys, P);
-    // the pair list may hold more distinct elements than the cap: count first, bail out before writing past `uniq`
-    uint32_t n_le = 0;
-    {
-      uint32_t local = 0;
-      for (uint32_t i = tid; i < np; i += AT_BUILD_THREADS) local += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-      cnt[tid] = local;
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t t = 0;
-        for (int q = 0; q < AT_BUILD_THREADS; ++q) t += cnt[q];
-        cnt[0] = t;
-      }
-      __syncthreads();
-      n_le = cnt[0];
-      __syncthreads();
-    }
-    if (n_le > (uint32_t)AT_ELEM_CAP) {
-      if (tid == 0) atomicExch(&stats[2], 1u);
-      continue;
-    }
-    unique_sorted_smem(keys, np, P, uniq, cnt);
-    // vertex references of the unique elements -> sorted unique vertex list
-    const uint32_t nvr = n_le * (uint32_t)nn;
-    uint32_t PV = 1;
-    while (PV < nvr) PV <<= 1;
-    for (uint32_t i = tid; i < PV; i += AT_BUILD_THREADS) vkeys[i] = (i < nvr) ? e2v[(uint64_t)uniq[i / nn] * nn + (i % nn)] : 0xFFFFFFFFu;
-    __syncthreads();
-    bitonic_sort_smem(vkeys, PV);
-    const uint32_t n_lv = unique_sorted_smem(vkeys, nvr, PV, uvtx, cnt);
-    if (!FILL) {
-      if (tid == 0) {
-        tile_nvtx[tile] = n_lv;
-        atomicMax(&stats[0], n_le);
-        atomicMax(&stats[1], (k1 - k0) + (uint32_t)(r1 - r0));
-        atomicMax(&stats[3], (nz2ptr[k1] - nz2ptr[k0]) + np);
-        atomicMax(&stats[4], n_lv);
-      }
-      __syncthreads();
-      continue;
-    }
-    const uint32_t voff = vtx_off[tile], eoff = pb - pair_base;
-    const uint32_t ob = nz2ptr[k0], oe = nz2ptr[k1];
+    const uint32_t n_le = unique_sorted_smem(keys, np, P, uniq, cnt);
+    const uint32_t eoff = pb - pair_base, ob = nz2ptr[k0], oe = nz2ptr[k1];
     if (tid == 0) {
       uint32_t *mt = tile_meta + tile * AT_META;
-      mt[0] = k0; mt[1] = k1; mt[2] = ob; mt[3] = oe; mt[4] = pb; mt[5] = pe; mt[6] = n_le; mt[7] = n_lv; mt[8] = voff;
-      mt[9] = mt[10] = mt[11] = 0;
+      mt[0] = k0; mt[1] = k1; mt[2] = ob; mt[3] = oe; mt[4] = pb; mt[5] = pe; mt[6] = n_le; mt[7] = 0;
+      atomicMax(&stats[0], n_le);
+      atomicMax(&stats[1], (k1 - k0) + (uint32_t)(r1 - r0));
+      if (n_le > (uint32_t)AT_ELEM_CAP) atomicExch(&stats[2], 1u);
     }
     for (uint32_t i = tid; i < n_le; i += AT_BUILD_THREADS) tile_elem[eoff + i] = uniq[i];
-    for (uint32_t i = tid; i < n_lv; i += AT_BUILD_THREADS) tile_vtx[voff + i] = uvtx[i];
-    for (uint32_t i = tid; i < n_le * 4; i += AT_BUILD_THREADS) {
-      const uint32_t le = i >> 2, n = i & 3;
-      uint16_t lv = 0;
-      if (n < (uint32_t)nn) lv = (uint16_t)lower_bound_smem(uvtx, n_lv, e2v[(uint64_t)uniq[le] * nn + n]);
-      tile_lconn[(uint64_t)(eoff + le) * 4 + n] = lv;
-    }
     // recode the contributions of the tile's slots: off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)
     const uint32_t total = (oe - ob) + np;
     for (uint32_t q = tid; q < total; q += AT_BUILD_THREADS) {
@@ -180,12 +133,10 @@ __global__ void __launch_bounds__(AT_BUILD_THREADS) k_tile_build(const uint32_t 
 
 static void plan_free_tiles(dfb_plan *plan) {
   dfb_dev_free(plan->d_tile_elem);
-  dfb_dev_free(plan->d_tile_vtx);
-  dfb_dev_free(plan->d_tile_lconn);
   dfb_dev_free(plan->d_tile_meta);
   dfb_dev_free(plan->d_code16);
-  plan->d_tile_elem = plan->d_tile_vtx = plan->d_tile_meta = nullptr;
-  plan->d_tile_lconn = plan->d_code16 = nullptr;
+  plan->d_tile_elem = plan->d_tile_meta = nullptr;
+  plan->d_code16 = nullptr;
 }
 void dfb_plan_free_tiles(dfb_plan *plan) { plan_free_tiles(plan); }
 
@@ -193,73 +144,45 @@ dfb_status dfb_plan_build_tiles(dfb_plan *plan) {
   if (plan->tile_state != 0) return DFB_OK;
   plan->tile_state = -1;
   dfb_ctx *c = plan->ctx;
-  if (plan->pat->convention != 0 || plan->flavour != 0 || plan->num_node > 4 || plan->pat->num_blk == 0 || !plan->mesh) return DFB_OK;
+  if (plan->pat->convention != 0 || plan->flavour != 0 || plan->num_node > 4 || plan->pat->num_blk == 0) return DFB_OK;
   const uint64_t nnz = plan->pat->nnz, nr = plan->pat->num_blk;
   uint32_t ends[2] = {0, 0};
   DFB_CUDA(cudaMemcpyAsync(&ends[0], plan->d_nz2ptr + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaMemcpyAsync(&ends[1], plan->d_nz2ptr + nnz + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   DFB_CUDA(cudaStreamSynchronize(c->stream));
   const uint64_t npairs = ends[1] - ends[0];
-  // rows per tile: about 224 off-diagonal slots (7 warps of slot threads), a multiple of the SpMV's 8-row tiles
-  const double off_per_row = (double)nnz / (double)nr;
-  uint32_t AT_ROWS = (uint32_t)(224.0 / (off_per_row > 1.0 ? off_per_row : 1.0) / 8.0 + 0.5) * 8u;
+  // 16 rows per tile (two of the SpMV's 8-row tiles): measured best for tets (~240 slots) and for spring edges (~112 slots);
+  // 8 for very dense rows so that a tile's slots still fit one CTA
+  uint32_t AT_ROWS = ((double)nnz / (double)nr > 28.0) ? 8 : 16;
   if (c->assemble_tile_rows > 0) AT_ROWS = (uint32_t)((c->assemble_tile_rows + 7) / 8 * 8);
-  if (AT_ROWS < 8) AT_ROWS = 8;
   if (AT_ROWS > 64) AT_ROWS = 64;
   const uint64_t n_tiles = (nr + AT_ROWS - 1) / AT_ROWS;
-  const size_t smem = (size_t)(AT_PAIR_CAP + AT_ELEM_CAP + 8 * AT_ELEM_CAP + AT_BUILD_THREADS) * sizeof(uint32_t);
-  DFB_CUDA(cudaFuncSetAttribute(k_tile_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DFB_CUDA(cudaFuncSetAttribute(k_tile_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  uint32_t *d_stats = nullptr, *d_voff = nullptr;
-  dfb_status st = dfb_dev_alloc_t(&d_stats, 8);
-  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_voff, n_tiles + 2);
-  uint32_t h_stats[8] = {0, 0, 1, 0, 0, 0, 0, 0};
-  const uint64_t g = n_tiles < (uint64_t)c->sm_count * 4 ? n_tiles : (uint64_t)c->sm_count * 4;
-  const dfb_mesh *mesh = plan->mesh;
+  uint32_t *d_stats = nullptr;
+  dfb_status st = dfb_dev_alloc_t(&plan->d_tile_elem, npairs + 2);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_meta, (n_tiles + 1) * AT_META);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_code16, plan->num_contrib + 8);
+  if (st == DFB_OK) st = dfb_dev_alloc_t(&d_stats, 4);
+  uint32_t h_stats[4] = {0, 0, 1, 0};
   if (st == DFB_OK) {
-    cudaMemsetAsync(d_stats, 0, 8 * sizeof(uint32_t), c->stream);
-    cudaMemsetAsync(d_voff, 0, (n_tiles + 2) * sizeof(uint32_t), c->stream);
-    DFB_LAUNCH(c, k_tile_build<false>, (unsigned)g, AT_BUILD_THREADS, smem, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node,
-               plan->pat->d_row2idx, mesh->d_elem2vtx, d_voff, (const uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-               (uint16_t *)nullptr, (uint32_t *)nullptr, (uint16_t *)nullptr, d_stats, n_tiles, AT_ROWS);
+    cudaMemsetAsync(d_stats, 0, 4 * sizeof(uint32_t), c->stream);
+    cudaMemsetAsync(plan->d_tile_meta, 0, (n_tiles + 1) * AT_META * sizeof(uint32_t), c->stream);
+    const uint64_t g = n_tiles < (uint64_t)c->sm_count * 8 ? n_tiles : (uint64_t)c->sm_count * 8;
+    DFB_LAUNCH(c, k_tile_build, (unsigned)g, AT_BUILD_THREADS, 0, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node, plan->pat->d_row2idx,
+               plan->d_tile_elem, plan->d_tile_meta, plan->d_code16, d_stats, n_tiles, AT_ROWS);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof(h_stats), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_build_tiles: %s", cudaGetErrorString(e));
   }
-  uint64_t n_vtx_total = 0;
-  if (st == DFB_OK && h_stats[2] == 0) st = dfb_exclusive_scan_u32(c, d_voff, n_tiles, &n_vtx_total);
-  if (st == DFB_OK && h_stats[2] == 0) {
-    st = dfb_dev_alloc_t(&plan->d_tile_elem, npairs + 2);
-    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_vtx, n_vtx_total + 2);
-    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_lconn, (npairs + 2) * 4);
-    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_tile_meta, (n_tiles + 1) * AT_META);
-    if (st == DFB_OK) st = dfb_dev_alloc_t(&plan->d_code16, plan->num_contrib + 8);
-    if (st == DFB_OK) {
-      cudaMemsetAsync(plan->d_tile_meta, 0, (n_tiles + 1) * AT_META * sizeof(uint32_t), c->stream);
-      DFB_LAUNCH(c, k_tile_build<true>, (unsigned)g, AT_BUILD_THREADS, smem, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->num_node,
-                 plan->pat->d_row2idx, mesh->d_elem2vtx, (uint32_t *)nullptr, d_voff, plan->d_tile_elem, plan->d_tile_vtx, plan->d_tile_lconn,
-                 plan->d_tile_meta, plan->d_code16, d_stats, n_tiles, AT_ROWS);
-      cudaError_t e = cudaGetLastError();
-      uint32_t bad = 1;
-      if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_stats + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "dfb_plan_build_tiles: %s", cudaGetErrorString(e));
-      h_stats[2] = bad;
-    }
-  }
   cudaStreamSynchronize(c->stream);
   dfb_dev_free(d_stats);
-  dfb_dev_free(d_voff);
-  if (st != DFB_OK || h_stats[2] != 0 || h_stats[4] > 65535u) {
+  if (st != DFB_OK || h_stats[2] != 0) {
     // not applicable (very high valence / degenerate lists): the slot-centric gather of assemble.cu stays in charge
     plan_free_tiles(plan);
     return st;
   }
   plan->tile_max_elem = h_stats[0];
   plan->tile_max_slots = h_stats[1];
-  plan->tile_max_codes = h_stats[3];
-  plan->tile_max_vtx = h_stats[4];
   plan->tile_rows = AT_ROWS;
   plan->n_atiles = n_tiles;
   plan->pair_base = ends[0];
@@ -468,33 +391,23 @@ struct TileOut {      // where the tile's values go
 struct TilePlanView {
   const uint32_t *nz2ptr;
   const uint16_t *code16;
-  const uint32_t *tile_elem, *tile_vtx, *tile_meta;
-  const uint16_t *tile_lconn;
+  const uint32_t *tile_elem, *tile_meta;
   const uint32_t *row2idx;
-  uint32_t pair_base, rows, max_elem, max_slots, max_vtx, max_codes;
+  uint32_t pair_base, rows, max_elem, max_slots;
   uint64_t nnz, num_rows, n_tiles;
 };
 
-// Experiment flags (ctx option "assemble_tile_flags", measured in profiles/): STAGE_LISTS = the tile's list offsets and codes are
-// copied to shared memory first (else read from global memory inside the slot loop); DIA_QUADS = 4 lanes share a diagonal slot
-// (else one thread per slot); STAGE_VTX = the tile's vertex coordinates are staged in shared memory through the tile's unique vertex
-// list and local connectivity (else every listed element reads connectivity + coordinates from global memory).
-template <class Model, bool STAGE_LISTS, bool DIA_QUADS, bool STAGE_VTX>
+template <class Model>
 __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename Model::Args args, const TilePlanView P,
-                                                                     const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
-                                                                     const double *__restrict__ disp, const TileOut out,
-                                                                     double *__restrict__ dw, double *__restrict__ w_elem) {
+                                                                  const uint32_t *__restrict__ e2v, const double *__restrict__ xyz,
+                                                                  const double *__restrict__ disp, const TileOut out,
+                                                                  double *__restrict__ dw, double *__restrict__ w_elem) {
   constexpr int NN = Model::N * Model::N, N = Model::N, NDIM = Model::NDIM, REC = Model::REC, NNODE = Model::NNODE;
   extern __shared__ __align__(16) double at_smem[];
   double *srec = at_smem;                                                   // [n_le][REC]
   double *sout = srec + (size_t)P.max_elem * REC;                           // [n_off + n_rows][NN]
-  double *sxyz = sout + (size_t)P.max_slots * NN;                           // [n_lv][NDIM]
-  double *sdisp = sxyz + (STAGE_VTX ? (size_t)P.max_vtx * NDIM : 0);        // [n_lv][NDIM] (energy models)
-  uint32_t *sptr = reinterpret_cast<uint32_t *>(sdisp + ((STAGE_VTX && Model::NEEDS_DISP) ? (size_t)P.max_vtx * NDIM : 0));
-  uint32_t *smeta = sptr + (STAGE_LISTS ? P.max_slots + 2 : 0);             // [AT_META]
-  uint16_t *slc = reinterpret_cast<uint16_t *>(smeta + AT_META);            // [n_le][4] tile-local connectivity
-  uint16_t *scode = slc + (STAGE_VTX ? (size_t)P.max_elem * 4 : 0);         // the tile's contribution codes
-  const unsigned tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = T >> 5;
+  uint32_t *smeta = reinterpret_cast<uint32_t *>(sout + (size_t)P.max_slots * NN);   // [AT_META]
+  const unsigned tid = threadIdx.x, T = blockDim.x;
   uint64_t tile = blockIdx.x;
   uint32_t meta_next = (tile < P.n_tiles && tid < AT_META) ? P.tile_meta[tile * AT_META + tid] : 0u;
   for (; tile < P.n_tiles; tile += gridDim.x) {
@@ -505,174 +418,57 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
       if (nt < P.n_tiles && tid < AT_META) meta_next = P.tile_meta[nt * AT_META + tid];
     }
     const uint64_t r0 = tile * P.rows, r1 = min(r0 + (uint64_t)P.rows, P.num_rows);
-    const uint32_t k0 = smeta[0], k1 = smeta[1], ob = smeta[2], oe = smeta[3], pb = smeta[4], pe = smeta[5];
-    const uint32_t n_le = smeta[6], n_lv = smeta[7], voff = smeta[8];
-    const uint32_t n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0), n_oc = oe - ob, eoff = pb - P.pair_base;
-    if (STAGE_VTX) {
-      for (uint32_t q = tid; q < n_lv; q += T) {
-        const uint64_t v = P.tile_vtx[voff + q];
-#pragma unroll
-        for (int d = 0; d < NDIM; ++d) sxyz[q * NDIM + d] = __ldg(xyz + v * NDIM + d);
-        if (Model::NEEDS_DISP) {
-#pragma unroll
-          for (int d = 0; d < NDIM; ++d) sdisp[q * NDIM + d] = __ldg(disp + v * NDIM + d);
-        }
-      }
-      const uint2 *src = reinterpret_cast<const uint2 *>(P.tile_lconn + (uint64_t)eoff * 4);
-      uint2 *dst = reinterpret_cast<uint2 *>(slc);
-      for (uint32_t q = tid; q < n_le; q += T) dst[q] = src[q];
-    }
-    if (STAGE_LISTS) {
-      for (uint32_t q = tid; q <= n_off; q += T) sptr[q] = P.nz2ptr[k0 + q] - ob;
-      for (uint32_t q = tid; q <= n_rows; q += T) sptr[n_off + 1 + q] = n_oc + (P.nz2ptr[P.nnz + r0 + q] - pb);
-      for (uint32_t q = tid; q < n_oc; q += T) scode[q] = P.code16[ob + q];
-      for (uint32_t q = tid; q < pe - pb; q += T) scode[n_oc + q] = P.code16[pb + q];
-    }
-    if (STAGE_VTX) __syncthreads();
-    // ---- phase 1: per-element records (one thread per listed element)
+    const uint32_t k0 = smeta[0], k1 = smeta[1], pb = smeta[4], n_le = smeta[6];
+    const uint32_t n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0), eoff = pb - P.pair_base;
+    // ---- phase 1: per-element records into shared memory (one thread per listed element)
     for (uint32_t le = tid; le < n_le; le += T) {
+      const uint32_t e = P.tile_elem[eoff + le];
       const double *px[NNODE], *pu[NNODE];
       uint32_t vmin = 0xFFFFFFFFu;
-      if (STAGE_VTX) {
-        uint32_t lmin = 0xFFFFu;
 #pragma unroll
-        for (int n = 0; n < NNODE; ++n) {
-          const uint32_t lv = slc[le * 4 + n];
-          px[n] = sxyz + (size_t)lv * NDIM;
-          pu[n] = sdisp + (size_t)lv * NDIM;
-          lmin = min(lmin, lv);
-        }
-        if (Model::HAS_GRAD && w_elem) vmin = P.tile_vtx[voff + lmin];  // the vertex list is sorted: smallest local id = smallest vertex
-      } else {
-        const uint32_t e = P.tile_elem[eoff + le];
-#pragma unroll
-        for (int n = 0; n < NNODE; ++n) {
-          const uint32_t v = e2v[(uint64_t)e * NNODE + n];
-          px[n] = xyz + (uint64_t)v * NDIM;
-          pu[n] = Model::NEEDS_DISP ? disp + (uint64_t)v * NDIM : nullptr;
-          vmin = min(vmin, v);
-        }
+      for (int n = 0; n < NNODE; ++n) {
+        const uint32_t v = e2v[(uint64_t)e * NNODE + n];
+        px[n] = xyz + (uint64_t)v * NDIM;
+        pu[n] = Model::NEEDS_DISP ? disp + (uint64_t)v * NDIM : nullptr;
+        vmin = min(vmin, v);
       }
       const double w = Model::make(srec + (size_t)le * REC, px, pu, args);
       // the element's energy is recorded once: by the tile that holds its lowest-numbered vertex
-      if (Model::HAS_GRAD && w_elem && vmin / P.rows == tile) w_elem[P.tile_elem[eoff + le]] = w;
+      if (Model::HAS_GRAD && w_elem && vmin / P.rows == tile) w_elem[e] = w;
     }
     __syncthreads();
-    // ---- phase 2: slots. Off-diagonal slots: one thread each (lists of ~4-6 contributions). Diagonal slots: one thread each, or
-    // (DIA_QUADS) AT_DIA_LANES lanes each: the lanes form the blocks of consecutive contributions in parallel, the group's first
-    // lane adds them in list order (ascending element = the serial loop's order, same bits)
-    const uint32_t n_plain = DIA_QUADS ? n_off : n_off + n_rows;
-    const uint32_t n_plain_warps = (n_plain + 31) >> 5;
-    const uint32_t n_dia_warps = DIA_QUADS ? (n_rows * AT_DIA_LANES + 31) >> 5 : 0u;
-    for (uint32_t w = wid; w < n_plain_warps + n_dia_warps; w += nwarp) {
-      if (w < n_plain_warps) {
-        const uint32_t s = (w << 5) + lane;
-        if (s < n_plain) {
-          const bool is_dia = s >= n_off;
-          double acc[NN], gacc[N];
+    // ---- phase 2: one thread per slot (off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)): walk the list in
+    // ascending element order (= the serial loop's accumulation order, same bits), accumulate in registers
+    for (uint32_t s = tid; s < n_off + n_rows; s += T) {
+      const bool is_dia = s >= n_off;
+      const uint64_t slot = is_dia ? P.nnz + r0 + (s - n_off) : (uint64_t)k0 + s;
+      double acc[NN], gacc[N];
 #pragma unroll
-          for (int q = 0; q < NN; ++q) acc[q] = 0.0;
+      for (int q = 0; q < NN; ++q) acc[q] = 0.0;
 #pragma unroll
-          for (int d = 0; d < N; ++d) gacc[d] = 0.0;
-          uint32_t cb, ce;
-          const uint16_t *codes;
-          if (STAGE_LISTS) {
-            const uint32_t si = is_dia ? s + 1 : s;
-            cb = sptr[si];
-            ce = sptr[si + 1];
-            codes = scode;
-          } else {
-            const uint64_t slot = is_dia ? P.nnz + r0 + (s - n_off) : (uint64_t)k0 + s;
-            cb = P.nz2ptr[slot];
-            ce = P.nz2ptr[slot + 1];
-            codes = P.code16;
-          }
-          for (uint32_t c = cb; c < ce; ++c) {
-            const uint32_t code = codes[c];
-            const double *rec = srec + (size_t)(code >> 4) * REC;
-            const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
-            double blk[NN];
-            Model::block(rec, i, j, args, blk);
+      for (int d = 0; d < N; ++d) gacc[d] = 0.0;
+      const uint32_t cb = P.nz2ptr[slot], ce = P.nz2ptr[slot + 1];
+      for (uint32_t c = cb; c < ce; ++c) {
+        const uint32_t code = P.code16[c];
+        const double *rec = srec + (size_t)(code >> 4) * REC;
+        const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
+        double blk[NN];
+        Model::block(rec, i, j, args, blk);
 #pragma unroll
-            for (int q = 0; q < NN; ++q) acc[q] += blk[q];
-            if (Model::HAS_GRAD && dw && is_dia) {
-              double g[N];
-              Model::grad(rec, i, args, g);
+        for (int q = 0; q < NN; ++q) acc[q] += blk[q];
+        if (Model::HAS_GRAD && dw && is_dia) {
+          double g[N];
+          Model::grad(rec, i, args, g);
 #pragma unroll
-              for (int d = 0; d < N; ++d) gacc[d] += g[d];
-            }
-          }
-          double *dst = sout + (size_t)s * NN;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) dst[q] = acc[q];
-          if (Model::HAS_GRAD && dw && is_dia) {
-#pragma unroll
-            for (int d = 0; d < N; ++d) dw[(r0 + (s - n_off)) * N + d] = gacc[d];
-          }
+          for (int d = 0; d < N; ++d) gacc[d] += g[d];
         }
-      } else {
-        const uint32_t v = ((w - n_plain_warps) << 5) + lane;
-        const uint32_t row = v / AT_DIA_LANES, t = v % AT_DIA_LANES;
-        const bool live = row < n_rows;
-        uint32_t cb = 0, ce = 0;
-        const uint16_t *codes = STAGE_LISTS ? scode : P.code16;
-        if (live) {
-          if (STAGE_LISTS) {
-            cb = sptr[n_off + 1 + row];
-            ce = sptr[n_off + 1 + row + 1];
-          } else {
-            cb = P.nz2ptr[P.nnz + r0 + row];
-            ce = P.nz2ptr[P.nnz + r0 + row + 1];
-          }
-        }
-        uint32_t n = ce - cb, nmax = n;
+      }
+      double *dst = sout + (size_t)s * NN;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
-        double acc[NN], gacc[N];
+      for (int q = 0; q < NN; ++q) dst[q] = acc[q];
+      if (Model::HAS_GRAD && dw && is_dia) {
 #pragma unroll
-        for (int q = 0; q < NN; ++q) acc[q] = 0.0;
-#pragma unroll
-        for (int d = 0; d < N; ++d) gacc[d] = 0.0;
-        const int base_lane = (int)(lane - t);
-        for (uint32_t k = 0; k < nmax; k += AT_DIA_LANES) {
-          double blk[NN], g[N];
-#pragma unroll
-          for (int q = 0; q < NN; ++q) blk[q] = 0.0;
-#pragma unroll
-          for (int d = 0; d < N; ++d) g[d] = 0.0;
-          if (k + t < n) {
-            const uint32_t code = codes[cb + k + t];
-            const double *rec = srec + (size_t)(code >> 4) * REC;
-            const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
-            Model::block(rec, i, j, args, blk);
-            if (Model::HAS_GRAD && dw) Model::grad(rec, i, args, g);
-          }
-#pragma unroll
-          for (int u = 0; u < AT_DIA_LANES; ++u) {
-            const bool on = k + u < n;  // n is the same on the lanes of a group
-#pragma unroll
-            for (int q = 0; q < NN; ++q) {
-              const double x = __shfl_sync(0xffffffffu, blk[q], base_lane + u);
-              if (on) acc[q] += x;
-            }
-            if (Model::HAS_GRAD && dw) {
-#pragma unroll
-              for (int d = 0; d < N; ++d) {
-                const double x = __shfl_sync(0xffffffffu, g[d], base_lane + u);
-                if (on) gacc[d] += x;
-              }
-            }
-          }
-        }
-        if (live && t == 0) {
-          double *dst = sout + (size_t)(n_off + row) * NN;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) dst[q] = acc[q];
-          if (Model::HAS_GRAD && dw) {
-#pragma unroll
-            for (int d = 0; d < N; ++d) dw[(r0 + row) * N + d] = gacc[d];
-          }
-        }
+        for (int d = 0; d < N; ++d) dw[(r0 + (s - n_off)) * N + d] = gacc[d];
       }
     }
     __syncthreads();
@@ -705,35 +501,11 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
                               double *dw, double *w_elem) {
   dfb_ctx *c = plan->ctx;
   constexpr int NN = Model::N * Model::N;
-  TilePlanView P;
-  P.nz2ptr = plan->d_nz2ptr;
-  P.code16 = plan->d_code16;
-  P.tile_elem = plan->d_tile_elem;
-  P.tile_vtx = plan->d_tile_vtx;
-  P.tile_meta = plan->d_tile_meta;
-  P.tile_lconn = plan->d_tile_lconn;
-  P.row2idx = plan->pat->d_row2idx;
-  P.pair_base = plan->pair_base;
-  P.rows = plan->tile_rows;
-  P.max_elem = plan->tile_max_elem;
-  P.max_slots = plan->tile_max_slots;
-  P.max_vtx = plan->tile_max_vtx;
-  P.max_codes = plan->tile_max_codes;
-  P.nnz = plan->pat->nnz;
-  P.num_rows = plan->pat->num_blk;
-  P.n_tiles = plan->n_atiles;
-  const int flags = (int)(c->assemble_tile_flags & 7);
-  const bool stage_lists = flags & 1, dia_quads = flags & 2, stage_vtx = flags & 4;
-  // one thread per off-diagonal slot + (quads: AT_DIA_LANES, else 1) per diagonal slot of the largest tile
-  const uint32_t max_off = plan->tile_max_slots > plan->tile_rows ? plan->tile_max_slots - plan->tile_rows : plan->tile_max_slots;
-  int threads = dia_quads ? (int)(((max_off + 31) / 32 + (plan->tile_rows * AT_DIA_LANES + 31) / 32) * 32) : (int)((plan->tile_max_slots + 31) / 32 * 32);
+  int threads = (int)((plan->tile_max_slots + 31) / 32 * 32);  // one thread per slot of the largest tile
   if (c->assemble_tile_threads > 0) threads = (int)c->assemble_tile_threads;
   if (threads < 64) threads = 64;
   if (threads > AT_MAX_THREADS) threads = AT_MAX_THREADS;
-  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN +
-                       (stage_vtx ? (size_t)plan->tile_max_vtx * Model::NDIM * (Model::NEEDS_DISP ? 2 : 1) : 0)) * sizeof(double) +
-                      ((stage_lists ? (size_t)plan->tile_max_slots + 2 : 0) + AT_META) * sizeof(uint32_t) +
-                      ((stage_vtx ? (size_t)plan->tile_max_elem * 4 : 0) + (stage_lists ? (((size_t)plan->tile_max_codes + 7) & ~(size_t)7) : 0)) * sizeof(uint16_t) + 16;
+  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double) + AT_META * sizeof(uint32_t) + 16;
   if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
   TileOut out;
   if (dfb_bsr_packed_native(m)) {
@@ -749,26 +521,28 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
     out.idx2val = m->d_idx2val;
     out.row2val = m->d_row2val;
   }
-  void (*kern)(const typename Model::Args, const TilePlanView, const uint32_t *, const double *, const double *, const TileOut, double *, double *) = nullptr;
-  switch (flags) {
-    case 0: kern = k_assemble_tile<Model, false, false, false>; break;
-    case 1: kern = k_assemble_tile<Model, true, false, false>; break;
-    case 2: kern = k_assemble_tile<Model, false, true, false>; break;
-    case 3: kern = k_assemble_tile<Model, true, true, false>; break;
-    case 4: kern = k_assemble_tile<Model, false, false, true>; break;
-    case 5: kern = k_assemble_tile<Model, true, false, true>; break;
-    case 6: kern = k_assemble_tile<Model, false, true, true>; break;
-    default: kern = k_assemble_tile<Model, true, true, true>; break;
-  }
-  DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TilePlanView P;
+  P.nz2ptr = plan->d_nz2ptr;
+  P.code16 = plan->d_code16;
+  P.tile_elem = plan->d_tile_elem;
+  P.tile_meta = plan->d_tile_meta;
+  P.row2idx = plan->pat->d_row2idx;
+  P.pair_base = plan->pair_base;
+  P.rows = plan->tile_rows;
+  P.max_elem = plan->tile_max_elem;
+  P.max_slots = plan->tile_max_slots;
+  P.nnz = plan->pat->nnz;
+  P.num_rows = plan->pat->num_blk;
+  P.n_tiles = plan->n_atiles;
+  DFB_CUDA(cudaFuncSetAttribute(k_assemble_tile<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_assemble_tile<Model>, threads, smem));
   if (per_sm < 1) per_sm = 1;
   uint64_t g = plan->n_atiles;
   if (g > (uint64_t)c->sm_count * per_sm) g = (uint64_t)c->sm_count * per_sm;
   dfb_phase_begin(c, DFB_PH_TILE);
-  kern<<<(unsigned)g, threads, smem, c->stream>>>(args, P, mesh->d_elem2vtx, mesh->d_xyz, disp ? disp->d : nullptr, out, dw, w_elem);
-  c->launches += 1;
+  DFB_LAUNCH(c, k_assemble_tile<Model>, (unsigned)g, threads, smem, args, P, mesh->d_elem2vtx, mesh->d_xyz, disp ? disp->d : nullptr, out, dw,
+             w_elem);
   dfb_phase_end(c);
   DFB_CHECK_LAUNCH();
   return DFB_OK;

@@ -161,7 +161,6 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "assemble_variant")) return &c->assemble_variant;
   if (!strcmp(key, "assemble_tile_neo")) return &c->assemble_tile_neo;
   if (!strcmp(key, "assemble_tile_rows")) return &c->assemble_tile_rows;
-  if (!strcmp(key, "assemble_tile_flags")) return &c->assemble_tile_flags;
   if (!strcmp(key, "assemble_tile_threads")) return &c->assemble_tile_threads;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;

@@ -124,7 +124,6 @@ struct dfb_ctx {
   int64_t assemble_variant = 0;
   int64_t assemble_tile_rows = 0;     // 0: chosen per mesh (about 224 off-diagonal slots per tile)
   int64_t assemble_tile_threads = 0;  // 0: one thread per off-diagonal slot + 4 per diagonal slot of the largest tile
-  int64_t assemble_tile_flags = 0;    // experiment switches of the tile kernel: 1 stage lists, 2 diagonal quads, 4 stage vertex data
   int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t profile_spmv = 0;
@@ -308,13 +307,11 @@ struct dfb_plan {
   int pairs_state = 0;     // 0 not built yet, 1 usable, -1 not applicable (convention/flavour, oversized tile, degenerate element)
   // fused row-tile assembly (assemble_tile.cu, the default): per tile of 16 rows the sorted unique incident elements, and the
   // contribution lists recoded to 16 bits (tile-local element << 4 | i << 2 | j), parallel to d_contrib
-  uint32_t *d_tile_elem = nullptr;   // tile t's unique elements, at offset (first pair of the tile) - pair_base
-  uint16_t *d_tile_lconn = nullptr;  // 4 tile-local vertex ids per listed element (same offsets x 4)
-  uint32_t *d_tile_vtx = nullptr;    // tile t's unique vertices (sorted), at offset meta[8]
-  uint32_t *d_tile_meta = nullptr;   // [n_atiles][12]: k0, k1, ob, oe, pb, pe, n_elem, n_vtx, vtx_off
+  uint32_t *d_tile_elem = nullptr;   // tile t's unique elements (sorted), at offset (first pair of the tile) - pair_base
+  uint32_t *d_tile_meta = nullptr;   // [n_atiles][8]: k0, k1, ob, oe, pb, pe, n_elem, pad
   uint16_t *d_code16 = nullptr;      // [num_contrib]
   uint64_t n_atiles = 0;
-  uint32_t pair_base = 0, tile_max_elem = 0, tile_max_slots = 0, tile_max_codes = 0, tile_max_vtx = 0, tile_rows = 16;
+  uint32_t pair_base = 0, tile_max_elem = 0, tile_max_slots = 0, tile_rows = 16;
   int tile_state = 0;      // 0 not built yet, 1 usable, -1 not applicable
 };
 // assemble_tile.cu: DFB_ERR_UNSUPPORTED (no error string, matrix untouched) = the tile path does not apply, use the gather of assemble.cu

@@ -39,17 +39,15 @@ ref = mat.download()
 print(f"variant 4 (node records + slot gather): {t:.3f} ms  {bytes_alg / t / 1e6:.0f} GB/s algorithmic")
 del plan
 ctx.set_option("assemble_variant", 0)
-for flags in (0, 4, 1, 2):
-    for rows in (8, 16, 24):
-        ctx.set_option("assemble_tile_flags", flags)
-        ctx.set_option("assemble_tile_rows", rows)
-        plan = dfb.Plan(ctx, pat, mesh, 0)
-        t = time_assemble(plan, 3)
-        rv, iv = mat.download()
-        same = np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1])
-        print(f"tile flags {flags} (lists {flags & 1}, quads {(flags >> 1) & 1}, vtx {(flags >> 2) & 1}) rows {rows}: {t:.3f} ms  {bytes_alg / t / 1e6:.0f} GB/s algorithmic  identical_bits={same}", flush=True)
-        del plan
-ctx.set_option("assemble_tile_flags", 0)
+for rows, threads in ((8, 0), (16, 0), (16, 128), (16, 384), (24, 0)):
+    ctx.set_option("assemble_tile_rows", rows)
+    ctx.set_option("assemble_tile_threads", threads)
+    plan = dfb.Plan(ctx, pat, mesh, 0)
+    t = time_assemble(plan, 3)
+    rv, iv = mat.download()
+    same = np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1])
+    print(f"tile rows {rows} threads {threads or 'auto'}: {t:.3f} ms  {bytes_alg / t / 1e6:.0f} GB/s algorithmic  identical_bits={same}", flush=True)
+    del plan
 ctx.set_option("assemble_tile_rows", 0)
 ctx.set_option("assemble_tile_threads", 0)
 del mat, pat, mesh
@@ -67,10 +65,9 @@ d = dfb.Vec(ctx, mesh.num_vtx, 3)
 d.fill_splitmix(0, 0, -1e-5, 1e-5)
 gv = dfb.Vec(ctx, mesh.num_vtx, 3)
 ref = None
-for variant, rows, flags in ((4, 0, 0), (0, 16, 0), (0, 32, 0), (0, 16, 1), (0, 16, 2), (0, 16, 4), (0, 16, 7), (0, 32, 4)):
+for variant, rows in ((4, 0), (0, 8), (0, 16), (0, 32)):
     ctx.set_option("assemble_variant", variant)
     ctx.set_option("assemble_tile_rows", rows)
-    ctx.set_option("assemble_tile_flags", flags)
     plan = dfb.Plan(ctx, pat, mesh, 0)
     w = elements.assemble_energy(plan, "spring3", mesh, d, 1.0, 0.0, mat, gv)
     best = 1e9
@@ -83,5 +80,5 @@ for variant, rows, flags in ((4, 0, 0), (0, 16, 0), (0, 32, 0), (0, 16, 1), (0, 
     same = ref is None or (np.array_equal(rv, ref[0]) and np.array_equal(iv, ref[1]) and np.array_equal(gh, ref[2]))
     if ref is None:
         ref = (rv, iv, gh, w)
-    print(f"spring3 {cn}^2 variant {variant} rows {rows or 'auto'} flags {flags}: {best:.3f} ms  identical_bits={same}  |w - w_ref|/w = {abs(w - ref[3]) / abs(ref[3]):.2e}")
+    print(f"spring3 {cn}^2 variant {variant} rows {rows or 'auto'}: {best:.3f} ms  identical_bits={same}  |w - w_ref|/w = {abs(w - ref[3]) / abs(ref[3]):.2e}")
     del plan
