@@ -554,7 +554,7 @@ struct IterPlan {
   double *zbuf;
   uint64_t nb, nflat;
   int n, kind, G, GF;
-  int peer, nccl_red, peer_halo;
+  int peer, nccl_red, peer_halo, ilu_levels;
   int64_t spmv_variant, chunk;
   uint64_t hist_ring;
   const void *packed;  // the packed mirror the SpMV nodes were captured with
@@ -711,6 +711,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   P.nccl_red = (c->nranks > 1 && !P.peer) ? 1 : 0;
   P.peer_halo = (P.peer && dfb_spmv_uses_peer_halo(m)) ? 1 : 0;
   P.spmv_variant = c->spmv_variant;
+  P.ilu_levels = (int)c->ilu_level_launches;
   P.chunk = c->iters_per_sync > 0 ? c->iters_per_sync : 16;
   if (P.chunk > 256) P.chunk = 256;
   // ring of ||r_k||^2: the host drains it after every chunk, so 2 chunks + the plain head iteration always fit
@@ -760,7 +761,8 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   // ---- chunks: [one plain iteration (bracketed with events when profiling)] + [graph replay of `chunk` iterations]
   std::vector<double> &rr = c->last_hist;
   rr.assign(1, 0.0);
-  const bool use_graph = c->use_graph != 0 && !ilu;  // an ILU sweep is ~900 launches: far too many nodes per iteration
+  // (with one launch per level an ILU application is ~900 launches: far too many nodes per iteration)
+  const bool use_graph = c->use_graph != 0 && !(ilu && c->ilu_level_launches);
   DfbGraphCache *gc = nullptr;
   bool graph_tried = false;
   DfbSolverState last;

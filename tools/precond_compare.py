@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _bootstrap
 dfb = _bootstrap.load()
 from del_fem_b200 import sparse_ilu, synthetic
-n = synthetic.SIZES.get(sys.argv[1], None) or int(sys.argv[1])
+n = synthetic.SIZES.get(sys.argv[1], None) or int(sys.argv[1])  # usage: precond_compare.py S1 jacobi,block_jacobi,ilu0,ilu0_levels
 ctx = dfb.Ctx(0)
 mesh = dfb.Mesh.kuhn(ctx, n)
 pat = dfb.Pattern.from_uniform_mesh(ctx, mesh, False)
@@ -18,7 +18,9 @@ u0, rhs, r, x, q, p = (dfb.Vec(ctx, nv, 3) for _ in range(6))
 u0.fill_splitmix(0, 0, -0.1, 0.1); u0.set_fixed_dof_zero_dev(flag)
 mat.mult_vec(rhs, 0.0, -1.0, u0); rhs.set_fixed_dof_zero_dev(flag); mat.set_fixed_dof_dev(1.0, flag)
 for kind in sys.argv[2].split(","):
-    pc = sparse_ilu.Preconditioner(kind)
+    # "ilu0_levels" = ILU(0) with one launch per level (the round-1 schedule), "ilu0" = dependency-driven sweeps (one launch per sweep)
+    ctx.set_option("ilu_level_launches", 1 if kind.endswith("_levels") else 0)
+    pc = sparse_ilu.Preconditioner(kind.replace("_levels", ""))
     ctx.timer_start(); pc.initialize(mat); t_sym = ctx.timer_stop()
     sparse_ilu.copy_value(pc, mat)
     ctx.timer_start(); sparse_ilu.decompose(pc); t_num = ctx.timer_stop()
