@@ -126,6 +126,7 @@ struct dfb_ctx {
   int64_t assemble_tile_threads = 0;  // 0: one thread per off-diagonal slot + 4 per diagonal slot of the largest tile
   int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
+  int64_t ilu_sweep_ctas_per_sm = 1;  // resident CTAs (256 threads) per SM of a persistent ILU sweep
   int64_t ilu_level_launches = 0;  // 1: ILU sweeps as one launch per level (reference point) instead of the dependency-driven sweeps
   int64_t profile_spmv = 0;
   // SpMV profiling (events on the launching stream)

@@ -29,11 +29,8 @@ struct DfbIlu {
   std::vector<uint32_t> lev_f, lev_b;  // level pointers into d_rows_f / d_rows_b (host)
   double *d_val = nullptr;        // factor values [nnz*NN]
   double *d_z = nullptr;          // explicit preconditioned residual for PCG [n*N]
-  // dependency-driven sweeps (one launch per sweep): rows in level order, every level padded to whole warps (0xFFFFFFFF = idle lane)
-  uint32_t *d_slots_f = nullptr, *d_slots_b = nullptr;
-  uint64_t n_slots_f = 0, n_slots_b = 0;
-  uint32_t *d_done = nullptr;     // [n] epoch of the sweep that last finished the row
-  uint32_t *d_epoch = nullptr;    // [1] epochs used so far (device-side so that a captured graph can be replayed)
+  uint32_t *d_lev_f = nullptr, *d_lev_b = nullptr;   // level pointers on the device (persistent sweeps)
+  uint32_t *d_epoch = nullptr;    // [8] grid-barrier counter of the persistent sweeps at [4]
 };
 
 template <int N>
@@ -212,41 +209,78 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
   }
 }
 
-// ---- dependency-driven sweeps: ONE launch per sweep instead of one per level (S10: 448 + 448 launches per application).
-// Rows are laid out in level order, each level padded to whole warps, and a persistent grid walks the slots in increasing order; a
-// row spins (acquire loads of a per-row epoch flag in L2) until the rows it depends on have published their result, then does exactly
-// the reference's row arithmetic (sparse_ilu.rs:183-219) and publishes its own. Every wait points to a smaller slot index, the grid
-// is fully resident, and the lanes of a warp always hold rows of ONE level (no intra-warp dependency): the smallest unfinished
-// slot can always run, so the sweep cannot deadlock. Results are bit-identical to the level-per-launch kernels above.
-__device__ __forceinline__ void ilu_wait_row(const uint32_t *done, uint32_t j, uint32_t epoch) {
-  uint32_t v;
-  do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + j) : "memory");
-  } while (v != epoch);
+// ---- level sweeps inside ONE persistent launch with a grid-wide barrier between levels (default; S10: 2 launches per application
+// instead of 448 + 448). All CTAs are resident (one per SM); a level's rows are strided over the whole grid; barrier = one atomic
+// per CTA + one polling thread per CTA. Same row arithmetic as the per-level kernels => same bits.
+// Measured (tools/precond_compare.py, profiles/r2_precond_compare.txt): S1 4.5 ms per PCG iteration (6.4 with one launch per level),
+// S10 11.5 (41.7): ~10 us per level remain, so ILU(0)-PCG is still slower than Jacobi-PCG in time (S1 1.07 s vs 0.08 s).
+// A sync-free variant (per-row epoch flags polled by the dependent rows, Liu et al.) was built and measured SLOWER (11-13 ms per
+// iteration at S1 for every window size / back-off tried: 0.78 G L2 requests of polling per sweep) and removed.
+__device__ __forceinline__ void ilu_grid_barrier(unsigned int *ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
 }
-__device__ __forceinline__ void ilu_publish_row(uint32_t *done, uint32_t i, uint32_t epoch) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done + i), "r"(epoch) : "memory");
-}
+__global__ void k_ilu_barrier_reset(unsigned int *ctr) { *ctr = 0u; }
 
 template <int N, bool FORWARD>
-__global__ void __launch_bounds__(128) k_ilu_sweep(const uint32_t *__restrict__ slots, uint64_t n_slots, const uint32_t *__restrict__ r2i,
-                                                   const uint32_t *__restrict__ col, const uint32_t *__restrict__ diap,
-                                                   const double *__restrict__ val, const double *__restrict__ dia, double *vec,
-                                                   uint32_t *done, const uint32_t *epoch_base) {
-  constexpr int NN = N * N;
-  const uint32_t epoch = *epoch_base + (FORWARD ? 1u : 2u);
-  for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_slots; q += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t i = slots[q];
-    if (i == 0xFFFFFFFFu) continue;
+__global__ void __launch_bounds__(256) k_ilu_sweep_levels(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ lev_ptr, uint32_t n_lev,
+                                                          const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ col,
+                                                          const uint32_t *__restrict__ diap, const double *__restrict__ val,
+                                                          const double *__restrict__ dia, double *vec, unsigned int *bar) {
+  constexpr int NN = N * N, KPRE = 16;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  // Software pipeline across levels: while level l is being computed (and during its barrier) every thread already fetches what
+  // its FIRST row of level l+1 needs and does not depend on other rows — row id, row pointers, column indices (registers) and the
+  // factor blocks (L2 prefetch) — so that after the barrier only the neighbours' values (L2) are on the critical path.
+  struct Pre {
+    uint32_t i, kb, ke;
+    uint32_t cols[KPRE];
+  };
+  auto prefetch_row = [&](uint32_t q, uint32_t b) -> Pre {
+    Pre p;
+    p.i = 0xFFFFFFFFu;
+    p.kb = p.ke = 0;
+#pragma unroll
+    for (int k = 0; k < KPRE; ++k) p.cols[k] = 0u;
+    if (q < b) {
+      p.i = rows[q];
+      p.kb = FORWARD ? r2i[p.i] : diap[p.i];
+      p.ke = FORWARD ? diap[p.i] : r2i[p.i + 1];
+#pragma unroll
+      for (int k = 0; k < KPRE; ++k)
+        if (p.kb + k < p.ke) p.cols[k] = col[p.kb + k];
+      const char *pb = reinterpret_cast<const char *>(val + (uint64_t)p.kb * NN), *pe = reinterpret_cast<const char *>(val + (uint64_t)p.ke * NN);
+      for (const char *c = pb; c < pe; c += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
+      if (FORWARD) asm volatile("prefetch.global.L2 [%0];" ::"l"(dia + (uint64_t)p.i * NN));
+    }
+    return p;
+  };
+  auto do_row = [&](const Pre &p) {
+    const uint32_t i = p.i;
     double t[N], v[N], x[N];
 #pragma unroll
     for (int d = 0; d < N; ++d) t[d] = __ldcg(vec + (uint64_t)i * N + d);
-    const uint32_t kb = FORWARD ? r2i[i] : diap[i], ke = FORWARD ? diap[i] : r2i[i + 1];
-    for (uint32_t k = kb; k < ke; ++k) {
-      const uint32_t j = col[k];
-      ilu_wait_row(done, j, epoch);
 #pragma unroll
-      for (int d = 0; d < N; ++d) x[d] = __ldcg(vec + (uint64_t)j * N + d);  // written by another SM during this launch: read from L2
+    for (int k = 0; k < KPRE; ++k) {
+      if (p.kb + k < p.ke) {
+#pragma unroll
+        for (int d = 0; d < N; ++d) x[d] = __ldcg(vec + (uint64_t)p.cols[k] * N + d);  // written by other SMs in earlier levels: L2
+        mat_vec<N>(v, val + (uint64_t)(p.kb + k) * NN, x);
+#pragma unroll
+        for (int d = 0; d < N; ++d) t[d] -= v[d];
+      }
+    }
+    for (uint32_t k = p.kb + KPRE; k < p.ke; ++k) {
+#pragma unroll
+      for (int d = 0; d < N; ++d) x[d] = __ldcg(vec + (uint64_t)col[k] * N + d);
       mat_vec<N>(v, val + (uint64_t)k * NN, x);
 #pragma unroll
       for (int d = 0; d < N; ++d) t[d] -= v[d];
@@ -259,10 +293,22 @@ __global__ void __launch_bounds__(128) k_ilu_sweep(const uint32_t *__restrict__ 
 #pragma unroll
       for (int d = 0; d < N; ++d) vec[(uint64_t)i * N + d] = t[d];
     }
-    ilu_publish_row(done, i, epoch);
+  };
+  Pre cur = prefetch_row(lev_ptr[0] + gtid, lev_ptr[1]);
+  for (uint32_t l = 0; l < n_lev; ++l) {
+    const uint32_t a = lev_ptr[l], b = lev_ptr[l + 1];
+    Pre nxt;
+    nxt.i = 0xFFFFFFFFu;
+    if (l + 1 < n_lev) nxt = prefetch_row(lev_ptr[l + 1] + gtid, lev_ptr[l + 2]);   // lev_ptr has n_lev + 1 entries
+    if (cur.i != 0xFFFFFFFFu) do_row(cur);
+    for (uint32_t q = a + gtid + gsz; q < b; q += gsz) {   // levels wider than the grid: the remaining rows, unpipelined
+      const Pre p = prefetch_row(q, b);
+      do_row(p);
+    }
+    if (l + 1 < n_lev) ilu_grid_barrier(bar, (l + 1) * gridDim.x);
+    cur = nxt;
   }
 }
-__global__ void k_ilu_epoch_bump(uint32_t *epoch) { *epoch += 2u; }
 
 // red_out[0] = a . b  (deterministic)
 __global__ void __launch_bounds__(256) k_ilu_dot(const double *__restrict__ a, const double *__restrict__ b, uint64_t n, double *partials,
@@ -284,10 +330,9 @@ void dfb_ilu_destroy(DfbIlu *s) {
   dfb_dev_free(s->d_rows_b);
   dfb_dev_free(s->d_val);
   dfb_dev_free(s->d_z);
-  dfb_dev_free(s->d_slots_f);
-  dfb_dev_free(s->d_slots_b);
-  dfb_dev_free(s->d_done);
   dfb_dev_free(s->d_epoch);
+  dfb_dev_free(s->d_lev_f);
+  dfb_dev_free(s->d_lev_b);
   delete s;
 }
 
@@ -418,27 +463,10 @@ dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIl
   up(&s->d_dia, dia);
   up(&s->d_rows_f, rows_f);
   up(&s->d_rows_b, rows_b);
-  // level order padded to whole warps for the dependency-driven sweeps
-  auto padded = [&](const std::vector<uint32_t> &ptr, const std::vector<uint32_t> &rows) {
-    std::vector<uint32_t> out;
-    out.reserve(rows.size() + 32 * ptr.size());
-    for (size_t l = 0; l + 1 < ptr.size(); ++l) {
-      for (uint32_t q = ptr[l]; q < ptr[l + 1]; ++q) out.push_back(rows[q]);
-      while (out.size() % 32) out.push_back(0xFFFFFFFFu);
-    }
-    return out;
-  };
-  const std::vector<uint32_t> slots_f = padded(s->lev_f, rows_f), slots_b = padded(s->lev_b, rows_b);
-  s->n_slots_f = slots_f.size();
-  s->n_slots_b = slots_b.size();
-  up(&s->d_slots_f, slots_f);
-  up(&s->d_slots_b, slots_b);
-  if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_done, n + 8);
+  up(&s->d_lev_f, s->lev_f);
+  up(&s->d_lev_b, s->lev_b);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_epoch, 8);
-  if (st == DFB_OK) {
-    cudaMemsetAsync(s->d_done, 0, (n + 8) * sizeof(uint32_t), c->stream);
-    cudaMemsetAsync(s->d_epoch, 0, 8 * sizeof(uint32_t), c->stream);
-  }
+  if (st == DFB_OK) cudaMemsetAsync(s->d_epoch, 0, 8 * sizeof(uint32_t), c->stream);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_val, nnz * NN + 8);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_z, n * N + 8);
   if (st == DFB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu0: upload failed");
@@ -482,20 +510,21 @@ dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia
 
 // solve_preconditioning_vec, in place
 template <int N>
-static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, const double *d_dia, double *d_vec) {
-  // persistent, fully resident grid (the spin-waits need every slot's owner to be running)
-  int per_sm_f = 1, per_sm_b = 1;
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, k_ilu_sweep<N, true>, 128, 0));
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_ilu_sweep<N, false>, 128, 0));
-  auto grid = [&](uint64_t n_slots, int per_sm) {
-    uint64_t g = (n_slots + 127) / 128;
-    const uint64_t cap = (uint64_t)c->sm_count * (uint64_t)(per_sm < 1 ? 1 : per_sm);
-    if (g > cap) g = cap;
-    return (unsigned)(g < 1 ? 1 : g);
-  };
-  if (s->n_slots_f) DFB_LAUNCH(c, (k_ilu_sweep<N, true>), grid(s->n_slots_f, per_sm_f), 128, 0, s->d_slots_f, s->n_slots_f, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, s->d_done, s->d_epoch);
-  if (s->n_slots_b) DFB_LAUNCH(c, (k_ilu_sweep<N, false>), grid(s->n_slots_b, per_sm_b), 128, 0, s->d_slots_b, s->n_slots_b, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, s->d_done, s->d_epoch);
-  DFB_LAUNCH(c, k_ilu_epoch_bump, 1, 1, 0, s->d_epoch);
+static dfb_status ilu_sweeps_barrier(dfb_ctx *c, const DfbIlu *s, const double *d_dia, double *d_vec) {
+  int per_sm = 1;
+  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_sweep_levels<N, true>, 256, 0));
+  int per_sm_b = 1;
+  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_ilu_sweep_levels<N, false>, 256, 0));
+  if (per_sm_b < per_sm) per_sm = per_sm_b;
+  if (c->ilu_sweep_ctas_per_sm > 0 && c->ilu_sweep_ctas_per_sm < per_sm) per_sm = (int)c->ilu_sweep_ctas_per_sm;
+  if (per_sm < 1) per_sm = 1;
+  const unsigned g = (unsigned)(c->sm_count * per_sm);
+  const uint32_t nf = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1, nb = s->lev_b.empty() ? 0 : (uint32_t)s->lev_b.size() - 1;
+  unsigned int *bar = s->d_epoch + 4;
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
+  if (nf) DFB_LAUNCH(c, (k_ilu_sweep_levels<N, true>), g, 256, 0, s->d_rows_f, s->d_lev_f, nf, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, bar);
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
+  if (nb) DFB_LAUNCH(c, (k_ilu_sweep_levels<N, false>), g, 256, 0, s->d_rows_b, s->d_lev_b, nb, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, bar);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -503,10 +532,10 @@ static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, const double *d_dia, d
 dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec) {
   if (c->ilu_level_launches == 0) {
     switch (N) {
-      case 1: return ilu_sweeps<1>(c, s, d_dia, d_vec);
-      case 2: return ilu_sweeps<2>(c, s, d_dia, d_vec);
-      case 3: return ilu_sweeps<3>(c, s, d_dia, d_vec);
-      case 4: return ilu_sweeps<4>(c, s, d_dia, d_vec);
+      case 1: return ilu_sweeps_barrier<1>(c, s, d_dia, d_vec);
+      case 2: return ilu_sweeps_barrier<2>(c, s, d_dia, d_vec);
+      case 3: return ilu_sweeps_barrier<3>(c, s, d_dia, d_vec);
+      case 4: return ilu_sweeps_barrier<4>(c, s, d_dia, d_vec);
     }
   }
   // one launch per level (option "ilu_level_launches" = 1): the reference point the sweeps are checked against

@@ -455,13 +455,13 @@ def test_ilu0_matches_oracle(dfb, ctx, orc, case):
     vd = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vd, pc)
     assert rel_err(vd.download(), want) < 1e-13
-    # the dependency-driven sweeps (default, one launch per sweep) and the level-per-launch sweeps give the same bits
+    # the persistent sweeps (default: one launch per sweep, grid barrier per level) and the level-per-launch sweeps give the same bits
     ctx.set_option("ilu_level_launches", 1)
     vl = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vl, pc)
     ctx.set_option("ilu_level_launches", 0)
     assert np.array_equal(vl.download(), vd.download())
-    for _ in range(3):  # repeated applications reuse the epoch flags
+    for _ in range(3):  # repeated applications reuse the barrier counter
         vr = dfb.Vec.from_numpy(ctx, v)
         sparse_ilu.solve_preconditioning_vec(vr, pc)
         assert np.array_equal(vr.download(), vd.download())

@@ -17,6 +17,9 @@ flag = dfb.BcFlag(ctx, synthetic.clamp_flags_z0(n, n, n))
 u0, rhs, r, x, q, p = (dfb.Vec(ctx, nv, 3) for _ in range(6))
 u0.fill_splitmix(0, 0, -0.1, 0.1); u0.set_fixed_dof_zero_dev(flag)
 mat.mult_vec(rhs, 0.0, -1.0, u0); rhs.set_fixed_dof_zero_dev(flag); mat.set_fixed_dof_dev(1.0, flag)
+for kv in sys.argv[3:]:
+    k, v = kv.split("=")
+    ctx.set_option(k, int(v))
 for kind in sys.argv[2].split(","):
     # "ilu0_levels" = ILU(0) with one launch per level (the round-1 schedule), "ilu0" = dependency-driven sweeps (one launch per sweep)
     ctx.set_option("ilu_level_launches", 1 if kind.endswith("_levels") else 0)
