@@ -7,9 +7,10 @@
 // whose floating-point accumulation order into a given nonzero is "ascending element index".
 //
 // Here: dfb_plan_create inverts the element->nonzero map once per (pattern, mesh): for every nonzero slot (off-diagonal
-// idx, or nnz+row for the separate diagonal) the list of contributions (e,i,j), sorted ascending.  dfb_assemble then runs
-// one thread per slot that walks its list in that order, recomputes the (i,j) block of each element matrix from the
-// vertex coordinates (no 1152 B/tet scratch) and writes the sum once: no atomics, no set_zero pass, bit-reproducible.
+// idx, or nnz+row for the separate diagonal) the list of contributions (e,i,j), sorted ascending.  The default assembly is the
+// fused row-tile kernel of assemble_tile.cu; this file holds the plan, the batched element kernels of the two-phase path (energy
+// models, user-supplied element matrices), and the slot-centric gathers (one thread per slot walks its list in that order and
+// writes the sum once: no atomics, no set_zero pass, bit-reproducible) that serve as fallback and reference point.
 // This translation unit is compiled with --fmad=false and the element formulas are written operation-for-operation like
 // the reference's (no contraction in rustc either), so linear kernels reproduce the serial result bit-for-bit.
 #include "dfb_internal.h"
@@ -150,7 +151,6 @@ DFB_API dfb_status dfb_plan_destroy(dfb_plan *p) {
   dfb_dev_free(p->d_nz2ptr);
   dfb_dev_free(p->d_contrib);
   dfb_dev_free(p->d_geo);
-  dfb_dev_free(p->d_pair_slots);
   dfb_plan_free_tiles(p);
   dfb_pattern_destroy(p->pat);
   delete p;
@@ -280,292 +280,6 @@ __global__ void __launch_bounds__(128) k_assemble_recs(const uint32_t *__restric
   }
 }
 
-// ------------------------------------------------------------------------------------------------ row-tile assembly (variant 3)
-// The slot-centric gather above re-reads every node record once per contribution through scattered 32-byte sectors (ncu: L1
-// sector throughput 86 %, DRAM reads 2.8x the algorithmic bytes).  Here a warp owns a tile of 8 consecutive block-rows and keeps
-// the tile's off-diagonal blocks (contiguous in idx2val) plus its 8 diagonal blocks in shared memory.  4 lanes serve one row and
-// walk the row's (element, node i) pairs in ascending order — exactly the contribution list of the row's diagonal slot — lane j
-// loading node record j of the element (one coalesced 128-byte line per pair), taking record i by shuffle, forming block (i, j)
-// and adding it to the slot named by the pair's byte map.  Per slot the additions happen in ascending (e, i, j) order, i.e. the
-// reference's element loop order: results are bit-identical to the other variants.  The tile is then stored with coalesced writes.
-static const int AR_RPT = 8, AR_TILE_CAP = 128, AR_WARPS = 7;
-
-// pair byte map: for pair q = (e, i) of row r (tile base r0 = r - r % 8): byte j = slot of (r, elem2vtx[e][j]) relative to
-// row2idx[r0]; 0xFF = the diagonal block of r; 0xFE = unused node. Sets *bad when the layout does not fit (caller falls back).
-__global__ void k_build_pairs(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib, uint64_t nnz, uint64_t num_rows,
-                              const uint32_t *__restrict__ e2v, int n_node, const uint32_t *__restrict__ row2idx,
-                              const uint32_t *__restrict__ idx2col, uint32_t *__restrict__ pair_slots, int *bad) {
-  const uint32_t pair_base = nz2ptr[nnz];
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < num_rows; r += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r0 = r - (r % AR_RPT), r1 = min(r0 + (uint64_t)AR_RPT, num_rows);
-    const uint32_t base = row2idx[r0];
-    if (row2idx[r1] - base > (uint32_t)AR_TILE_CAP) *bad = 1;
-    for (uint32_t c = nz2ptr[nnz + r]; c < nz2ptr[nnz + r + 1]; ++c) {
-      const uint32_t code = contrib[c];
-      const uint32_t ei = code / n_node, i = ei % n_node, e = ei / n_node;
-      if (code % n_node != i) *bad = 1;  // only (e, i, i) belongs in a diagonal list
-      uint32_t packed = 0;
-      for (int j = 0; j < 4; ++j) {
-        uint32_t rel = 0xFEu;
-        if (j < n_node) {
-          if ((uint32_t)j == i) {
-            rel = 0xFFu;
-          } else {
-            const uint32_t k = find_slot(row2idx, idx2col, (uint32_t)r, e2v[(uint64_t)e * n_node + j]);
-            if (k == NO_SLOT || k - base >= 0xFEu) {
-              *bad = 1;
-            } else {
-              rel = k - base;
-              for (int jj = 0; jj < j; ++jj)
-                if (((packed >> (8 * jj)) & 0xFFu) == rel) *bad = 1;  // degenerate element: two nodes on one slot
-            }
-          }
-        }
-        packed |= rel << (8 * j);
-      }
-      pair_slots[c - pair_base] = packed;
-    }
-  }
-}
-
-static dfb_status plan_build_pairs(dfb_plan *plan) {
-  if (plan->pairs_state != 0) return DFB_OK;
-  dfb_ctx *c = plan->ctx;
-  plan->pairs_state = -1;
-  if (plan->pat->convention != 0 || plan->flavour != 0 || plan->num_node > 4 || !plan->mesh) return DFB_OK;
-  const uint64_t nnz = plan->pat->nnz, nr = plan->pat->num_blk;
-  uint32_t ends[2] = {0, 0};
-  DFB_CUDA(cudaMemcpyAsync(&ends[0], plan->d_nz2ptr + nnz, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  DFB_CUDA(cudaMemcpyAsync(&ends[1], plan->d_nz2ptr + nnz + nr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  DFB_CUDA(cudaStreamSynchronize(c->stream));
-  const uint64_t npairs = ends[1] - ends[0];
-  DFB_TRY(dfb_dev_alloc_t(&plan->d_pair_slots, npairs + 2));
-  DFB_CUDA(cudaMemsetAsync(c->d_errflag + 3, 0, sizeof(int), c->stream));
-  DFB_LAUNCH(c, k_build_pairs, c->sm_count * 8, 128, 0, plan->d_nz2ptr, plan->d_contrib, nnz, nr, plan->mesh->d_elem2vtx, plan->num_node,
-             plan->pat->d_row2idx, plan->pat->d_idx2col, plan->d_pair_slots, c->d_errflag + 3);
-  DFB_CHECK_LAUNCH();
-  int bad = 0;
-  DFB_CUDA(cudaMemcpyAsync(&bad, c->d_errflag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  DFB_CUDA(cudaStreamSynchronize(c->stream));
-  if (bad) {
-    dfb_dev_free(plan->d_pair_slots);
-    plan->d_pair_slots = nullptr;
-    return DFB_OK;
-  }
-  plan->pairs_state = 1;
-  return DFB_OK;
-}
-
-// block sources for k_assemble_rows. load() fetches what lane j contributes to pair (e, i) — issued U pairs ahead of its use —
-// and block() turns it into block (i, j); block() is called by the 4 lanes of a row group together (SrcRecs shuffles record i).
-template <int KIND>
-struct SrcRecs {
-  static constexpr int NNODE = ElemGeo<KIND>::NNODE, N = ElemGeo<KIND>::N, U = 2;
-  struct Pre {
-    double v[4];
-  };
-  const NodeRec *recs;
-  double p0, p1;
-  __device__ __forceinline__ Pre load(uint32_t e, uint32_t, unsigned j, bool on) const {
-    Pre r = {{0.0, 0.0, 0.0, 0.0}};
-    if (on) {
-      const double2 *pb = reinterpret_cast<const double2 *>(&recs[(uint64_t)e * NNODE + j]);
-      const double2 b0 = __ldg(pb), b1 = __ldg(pb + 1);
-      r = {{b0.x, b0.y, b1.x, b1.y}};
-    }
-    return r;
-  }
-  __device__ __forceinline__ void block(const Pre &pre, uint32_t i, bool on, double *blk) const {
-    const int src = (int)((threadIdx.x & 31u & ~3u) + i);
-    NodeRec ra, rb;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      rb.v[k] = pre.v[k];
-      ra.v[k] = __shfl_sync(0xffffffffu, pre.v[k], src);
-    }
-    if (on) NodeOps<KIND>::block(ra, rb, p0, p1, blk);
-  }
-};
-template <int NNODE_, int N_>
-struct SrcEmat {  // precomputed element matrices [e][i][j][N*N] (two-phase path: energy models, user-supplied emat)
-  static constexpr int NNODE = NNODE_, N = N_, U = 1;
-  struct Pre {
-    double v[N_ * N_];
-  };
-  const double *emat;
-  __device__ __forceinline__ Pre load(uint32_t e, uint32_t i, unsigned j, bool on) const {
-    Pre r;
-#pragma unroll
-    for (int q = 0; q < N * N; ++q) r.v[q] = 0.0;
-    if (on) {
-      const double *b = emat + (((uint64_t)e * NNODE + i) * NNODE + j) * (N * N);
-#pragma unroll
-      for (int q = 0; q < N * N; ++q) r.v[q] = __ldg(b + q);
-    }
-    return r;
-  }
-  __device__ __forceinline__ void block(const Pre &pre, uint32_t, bool, double *blk) const {
-#pragma unroll
-    for (int q = 0; q < N * N; ++q) blk[q] = pre.v[q];
-  }
-};
-
-template <class Src>
-__global__ void __launch_bounds__(AR_WARPS * 32) k_assemble_rows(const Src src, const uint32_t *__restrict__ nz2ptr,
-                                                                 const uint32_t *__restrict__ contrib,
-                                                                 const uint32_t *__restrict__ pair_slots,
-                                                                 const uint32_t *__restrict__ row2idx, uint64_t nnz, uint64_t num_rows,
-                                                                 double *__restrict__ idx2val, double *__restrict__ row2val) {
-  constexpr int NN = Src::N * Src::N, NNODE = Src::NNODE, U = Src::U;
-  using Pre = typename Src::Pre;
-  extern __shared__ double ar_smem[];
-  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned g = lane >> 2, j = lane & 3;
-  const bool jon = j < (unsigned)NNODE;
-  double *acc = ar_smem + (size_t)wid * (AR_TILE_CAP + AR_RPT) * NN;
-  double *dia = acc + (size_t)AR_TILE_CAP * NN;
-  const uint32_t pair_base = nz2ptr[nnz];
-  const uint64_t n_tiles = (num_rows + AR_RPT - 1) / AR_RPT;
-  for (uint64_t tile = (uint64_t)blockIdx.x * AR_WARPS + wid; tile < n_tiles; tile += (uint64_t)gridDim.x * AR_WARPS) {
-    const uint64_t r0 = tile * AR_RPT, r1 = min(r0 + (uint64_t)AR_RPT, num_rows), r = r0 + g;
-    const bool valid = r < r1;
-    const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
-    const uint32_t cb = valid ? nz2ptr[nnz + r] : 0u, n = valid ? nz2ptr[nnz + r + 1] - cb : 0u;
-    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-    // software pipeline over chunks of U pairs: indices two chunks ahead, records one chunk ahead of the accumulation
-    uint32_t codeA[U], psA[U], codeB[U], psB[U];
-    Pre preA[U];
-    auto load_idx = [&](uint32_t t, uint32_t &code, uint32_t &ps) {
-      code = 0u;
-      ps = 0u;
-      if (t < n) {
-        code = __ldg(contrib + cb + t);
-        ps = __ldg(pair_slots + (cb + t - pair_base));
-      }
-    };
-    auto load_pre = [&](uint32_t t, uint32_t code) -> Pre {
-      const uint32_t ei = code / NNODE, e = ei / NNODE, i = ei - e * NNODE;
-      return src.load(e, i, j, jon && t < n);
-    };
-#pragma unroll
-    for (int u = 0; u < U; ++u) load_idx(u, codeA[u], psA[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) load_idx(U + u, codeB[u], psB[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) preA[u] = load_pre(u, codeA[u]);
-    for (uint32_t q = lane; q < nb * NN; q += 32) acc[q] = 0.0;
-    for (uint32_t q = lane; q < AR_RPT * NN; q += 32) dia[q] = 0.0;
-    __syncwarp();
-    for (uint32_t t0 = 0; t0 < nmax; t0 += U) {
-      Pre preB[U];
-      uint32_t codeC[U], psC[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) preB[u] = load_pre(t0 + U + u, codeB[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) load_idx(t0 + 2 * U + u, codeC[u], psC[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t ei = codeA[u] / NNODE, i = ei % NNODE;
-        const bool on = jon && (t0 + u) < n;
-        double blk[NN];
-        src.block(preA[u], i, on, blk);
-        if (on) {
-          const uint32_t rel = (psA[u] >> (8 * j)) & 0xFFu;
-          double *dst = (rel == 0xFFu) ? dia + g * NN : acc + (size_t)rel * NN;
-#pragma unroll
-          for (int q = 0; q < NN; ++q) dst[q] += blk[q];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        preA[u] = preB[u];
-        codeA[u] = codeB[u];
-        psA[u] = psB[u];
-        codeB[u] = codeC[u];
-        psB[u] = psC[u];
-      }
-    }
-    __syncwarp();
-    double *out = idx2val + (uint64_t)k0 * NN;
-    for (uint32_t q = lane; q < nb * NN; q += 32) out[q] = acc[q];
-    double *outd = row2val + r0 * NN;
-    for (uint32_t q = lane; q < (uint32_t)(r1 - r0) * NN; q += 32) outd[q] = dia[q];
-    __syncwarp();
-  }
-}
-
-template <class Src>
-static dfb_status launch_assemble_rows(dfb_plan *plan, const Src &src, dfb_bsr *m) {
-  dfb_ctx *c = plan->ctx;
-  constexpr int NN = Src::N * Src::N;
-  const size_t smem = (size_t)AR_WARPS * (AR_TILE_CAP + AR_RPT) * NN * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    DFB_CUDA(cudaFuncSetAttribute(k_assemble_rows<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  const uint64_t nr = plan->pat->num_blk, n_tiles = (nr + AR_RPT - 1) / AR_RPT;
-  uint64_t g = (n_tiles + AR_WARPS - 1) / AR_WARPS;
-  if (g < 1) g = 1;
-  if (g > (uint64_t)c->sm_count * 6) g = (uint64_t)c->sm_count * 6;
-  DFB_LAUNCH(c, k_assemble_rows<Src>, (unsigned)g, AR_WARPS * 32, smem, src, plan->d_nz2ptr, plan->d_contrib, plan->d_pair_slots,
-             plan->pat->d_row2idx, plan->pat->nnz, nr, m->d_idx2val, m->d_row2val);
-  DFB_CHECK_LAUNCH();
-  return DFB_OK;
-}
-
-// ---- default fused path in two kernels: (1) one thread per element evaluates the element geometry ONCE (tet: volume + 4 barycentric
-// gradients = 104 B) into a scratch array; (2) one thread per nonzero slot walks its contribution list and forms only the (i,j)
-// block from that record. Same arithmetic, same order => same bits as the single-kernel variant, but the per-contribution cost
-// drops from (16 B connectivity + 96 B coordinates + ~110 flop geometry) to (56 B + ~45 flop).
-template <int KIND>
-__global__ void __launch_bounds__(128) k_elem_geo(const uint32_t *__restrict__ e2v, const double *__restrict__ xyz, uint64_t num_elem,
-                                                  double p0, double p1, ElemGeo<KIND> *__restrict__ geo) {
-  using G = ElemGeo<KIND>;
-  constexpr int NNODE = G::NNODE, NDIM = G::NDIM;
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < num_elem; e += (uint64_t)gridDim.x * blockDim.x) {
-    const double *p[NNODE];
-    double coords[NNODE][NDIM];
-#pragma unroll
-    for (int n = 0; n < NNODE; ++n) {
-      const uint32_t v = e2v[e * NNODE + n];
-#pragma unroll
-      for (int d = 0; d < NDIM; ++d) coords[n][d] = __ldg(&xyz[(uint64_t)v * NDIM + d]);
-      p[n] = coords[n];
-    }
-    G g;
-    g.init(p, p0, p1);
-    geo[e] = g;
-  }
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(128) k_assemble_geo(const uint32_t *__restrict__ nz2ptr, const uint32_t *__restrict__ contrib,
-                                                      uint64_t num_slots, uint64_t nnz, const ElemGeo<KIND> *__restrict__ geo, double p0,
-                                                      double p1, double *__restrict__ idx2val, double *__restrict__ row2val) {
-  using G = ElemGeo<KIND>;
-  constexpr int NN = G::N * G::N, NNODE = G::NNODE;
-  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < num_slots; s += (uint64_t)gridDim.x * blockDim.x) {
-    double acc[NN];
-#pragma unroll
-    for (int q = 0; q < NN; ++q) acc[q] = 0.0;
-    const uint32_t cb = nz2ptr[s], ce = nz2ptr[s + 1];
-    for (uint32_t c = cb; c < ce; ++c) {
-      const uint32_t code = contrib[c];
-      const uint32_t e = code / (NNODE * NNODE);
-      const int ij = (int)(code - e * (NNODE * NNODE));
-      const int i = ij / NNODE, j = ij - i * NNODE;
-      double blk[NN];
-      geo[e].block(i, j, p0, p1, blk);
-#pragma unroll
-      for (int q = 0; q < NN; ++q) acc[q] += blk[q];
-    }
-    double *dst = (s < nnz) ? (idx2val + s * NN) : (row2val + (s - nnz) * NN);
-#pragma unroll
-    for (int q = 0; q < NN; ++q) dst[q] = acc[q];
-  }
-}
-
 DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *mesh, double p0, double p1, dfb_bsr *m) {
   DFB_REQUIRE(plan && mesh && m, "dfb_assemble: NULL argument");
   const ElemInfo info = elem_info(kind);
@@ -581,14 +295,15 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     const dfb_status ts = dfb_assemble_tile_linear(plan, kind, mesh, p0, p1, m);
     if (ts != DFB_ERR_UNSUPPORTED) return ts;
   }
+  // fallbacks / reference points, all bit-identical to the tile path: "assemble_variant" 4 (also where the tile path does not apply:
+  // convention 1, flavour 1, very high valence) = node records + slot-centric gather; 1 = single kernel, geometry recomputed per
+  // contribution (no scratch memory)
   DFB_TRY(dfb_bsr_canon_overwrite(m));  // every value is about to be rewritten in the canonical arrays
   const uint64_t ns = plan->num_slots;
   uint64_t g = (ns + 127) / 128;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
-  if (c->assemble_variant == 3 && kind != DFB_ELEM_COT_LAPLACE_TRI3) DFB_TRY(plan_build_pairs(plan));
-  const bool rows_path = c->assemble_variant == 3 && plan->pairs_state == 1;
-  if ((c->assemble_variant == 0 || c->assemble_variant == 3 || c->assemble_variant == 4) && kind != DFB_ELEM_COT_LAPLACE_TRI3) {
+  if (c->assemble_variant != 1 && kind != DFB_ELEM_COT_LAPLACE_TRI3) {
     // node-record path: 32-byte record per (element, node), two aligned sectors per contribution
     uint64_t ge = (mesh->num_elem + 127) / 128;
     if (ge < 1) ge = 1;
@@ -607,16 +322,8 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     DFB_LAUNCH(c, k_node_recs<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (NodeRec *)plan->d_geo); \
     dfb_phase_end(c);                                                                                                                 \
     dfb_phase_begin(c, DFB_PH_GATHER);                                                                                                \
-    if (rows_path) {                                                                                                                  \
-      SrcRecs<K> src;                                                                                                                 \
-      src.recs = (const NodeRec *)plan->d_geo;                                                                                        \
-      src.p0 = p0;                                                                                                                    \
-      src.p1 = p1;                                                                        \
-      DFB_TRY(launch_assemble_rows(plan, src, m));                                                                                    \
-    } else {                                                                                                                          \
-      DFB_LAUNCH(c, k_assemble_recs<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                     \
-                 (const NodeRec *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                                   \
-    }                                                                                                                                 \
+    DFB_LAUNCH(c, k_assemble_recs<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                       \
+               (const NodeRec *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                                     \
     dfb_phase_end(c);                                                                                                                 \
     break;
     switch (kind) {
@@ -632,43 +339,12 @@ DFB_API dfb_status dfb_assemble(dfb_plan *plan, int32_t kind, const dfb_mesh *me
     DFB_CHECK_LAUNCH();
     return DFB_OK;
   }
-  if (c->assemble_variant == 0 || c->assemble_variant == 2 || c->assemble_variant == 3 || c->assemble_variant == 4) {
-    uint64_t ge = (mesh->num_elem + 127) / 128;
-    if (ge < 1) ge = 1;
-    if (ge > (uint64_t)c->sm_count * 16) ge = (uint64_t)c->sm_count * 16;
-#define GEO_CASE(K)                                                                                                            \
-  case K: {                                                                                                                    \
-    const uint64_t need = mesh->num_elem * sizeof(ElemGeo<K>) + 256;                                                           \
-    if (plan->geo_cap < need) {                                                                                                \
-      dfb_dev_free(plan->d_geo);                                                                                                   \
-      plan->d_geo = nullptr;                                                                                                   \
-      plan->geo_cap = 0;                                                                                                       \
-      DFB_TRY(dfb_dev_alloc(&plan->d_geo, need));                                                                              \
-      plan->geo_cap = need;                                                                                                    \
-    }                                                                                                                          \
-    DFB_LAUNCH(c, k_elem_geo<K>, (unsigned)ge, 128, 0, mesh->d_elem2vtx, mesh->d_xyz, mesh->num_elem, p0, p1, (ElemGeo<K> *)plan->d_geo); \
-    DFB_LAUNCH(c, k_assemble_geo<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz,                \
-               (const ElemGeo<K> *)plan->d_geo, p0, p1, m->d_idx2val, m->d_row2val);                                           \
-    break;                                                                                                                     \
-  }
-    switch (kind) {
-      GEO_CASE(DFB_ELEM_LAPLACE_TRI2)
-      GEO_CASE(DFB_ELEM_COT_LAPLACE_TRI3)
-      GEO_CASE(DFB_ELEM_SOLID_LINEAR_TRI2)
-      GEO_CASE(DFB_ELEM_LAPLACE_TET)
-      GEO_CASE(DFB_ELEM_SOLID_LINEAR_TET)
-      GEO_CASE(DFB_ELEM_MASS_TET)
-      default:
-        return dfb_fail(DFB_ERR_UNSUPPORTED, "dfb_assemble: kind %d has no fused path (use dfb_emat_batch + dfb_assemble_from_emat)", kind);
-    }
-#undef GEO_CASE
-    DFB_CHECK_LAUNCH();
-    return DFB_OK;
-  }
 #define ASM_CASE(K)                                                                                                          \
   case K:                                                                                                                    \
+    dfb_phase_begin(c, DFB_PH_GATHER);                                                                                       \
     DFB_LAUNCH(c, k_assemble_fused<K>, (unsigned)g, 128, 0, plan->d_nz2ptr, plan->d_contrib, ns, plan->pat->nnz, mesh->d_elem2vtx, \
                mesh->d_xyz, p0, p1, m->d_idx2val, m->d_row2val);                                                             \
+    dfb_phase_end(c);                                                                                                        \
     break;
   switch (kind) {
     ASM_CASE(DFB_ELEM_LAPLACE_TRI2)
@@ -1158,20 +834,6 @@ DFB_API dfb_status dfb_assemble_from_emat(dfb_plan *plan, const double *emat_dev
   DFB_REQUIRE(m->pat == plan->pat, "dfb_assemble_from_emat: matrix and plan use different patterns");
   DFB_TRY(dfb_bsr_canon_overwrite(m));  // every value is about to be rewritten in the canonical arrays
   dfb_ctx *c = plan->ctx;
-  if (c->assemble_variant == 3) {
-    // row-tile gather: each (row, element-node) pair reads n_node consecutive blocks of the element matrix
-    DFB_TRY(plan_build_pairs(plan));
-    if (plan->pairs_state == 1) {
-#define FE_ROWS(NNODE, NV)                                     \
-  if (plan->num_node == NNODE && m->blk_dim == NV) {           \
-    SrcEmat<NNODE, NV> src;                                    \
-    src.emat = emat_dev;                                       \
-    return launch_assemble_rows(plan, src, m);                 \
-  }
-      FE_ROWS(2, 1) FE_ROWS(2, 2) FE_ROWS(2, 3) FE_ROWS(3, 1) FE_ROWS(3, 2) FE_ROWS(3, 3) FE_ROWS(4, 1) FE_ROWS(4, 2) FE_ROWS(4, 3)
-#undef FE_ROWS
-    }
-  }
   const uint64_t ns = plan->num_slots;
   uint64_t g = (ns + 127) / 128;
   if (g < 1) g = 1;

@@ -302,11 +302,8 @@ struct dfb_plan {
   uint32_t *d_nz2ptr;    // [num_slots+1]
   uint32_t *d_contrib;   // [num_contrib] code = e*nn2 + i*num_node + j
   const dfb_mesh *mesh;  // borrowed (elem2vtx used to rebuild elem2nz on demand)
-  void *d_geo = nullptr;   // per-element geometry scratch of the two-kernel fused assembly (lazily allocated)
+  void *d_geo = nullptr;   // node-record scratch of the slot-centric gather (variant 4 / fallback; lazily allocated)
   uint64_t geo_cap = 0;
-  // row-tile assembly (variant 3): for every (row, element-node) pair the tile-relative slots of its n_node blocks, one byte each
-  uint32_t *d_pair_slots = nullptr;
-  int pairs_state = 0;     // 0 not built yet, 1 usable, -1 not applicable (convention/flavour, oversized tile, degenerate element)
   // fused row-tile assembly (assemble_tile.cu, the default): per tile of 16 rows the sorted unique incident elements, and the
   // contribution lists recoded to 16 bits (tile-local element << 4 | i << 2 | j), parallel to d_contrib
   uint32_t *d_tile_elem = nullptr;   // tile t's unique elements (sorted), at offset (first pair of the tile) - pair_base

@@ -122,13 +122,12 @@ def _mesh_for(orc, kind, rng):
     return t2v, np.ascontiguousarray(xy), 3
 
 
-@pytest.mark.parametrize("asm_variant", [0, 3, 4])
+@pytest.mark.parametrize("asm_variant", [0, 1, 4])
 @pytest.mark.parametrize("convention", [0, 1])
 @pytest.mark.parametrize("kind,p0,p1", KINDS)
 def test_fused_assembly_matches_oracle(dfb, ctx, orc, kind, p0, p1, convention, asm_variant):
-    """asm_variant 0: fused row-tile assembly (default; writes the SpMV's packed records directly); 4: slot-centric gather over node
-    records; 3: warp row-tile gather with shared-memory accumulators (falls back to 4 where it does
-    not apply: convention 1, the cotangent kernel)"""
+    """asm_variant 0: fused row-tile assembly (default; writes the SpMV's packed records directly; falls back to 4 where it does not
+    apply: convention 1); 4: node records + slot-centric gather; 1: single kernel, geometry recomputed per contribution"""
     ctx.set_option("assemble_variant", asm_variant)
     rng = np.random.default_rng(3)
     e2v, xyz, n_node = _mesh_for(orc, kind, rng)

@@ -329,7 +329,7 @@ def test_mass_matches_oracle(dfb, ctx, orc):
     pat = dfb.Pattern(ctx, r2i, i2c, 0)
     plan = dfb.Plan(ctx, pat, mesh, 0)
     mat = dfb.Matrix(ctx, pat, 3)
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1, 4):
         ctx.set_option("assemble_variant", variant)
         mat.set_zero()
         mat.assemble(plan, "mass_tet", mesh, 2.5, 0.0)
