@@ -150,7 +150,7 @@ struct dfb_ctx {
   int peer_enabled = 0;
   int64_t use_peer_allreduce = 1;               // option: 0 forces NCCL all-reduce even when mailboxes are mapped
   // peer halo push (ghost values stored straight into the neighbours' landing zones over NVLink; PCG only)
-  int64_t use_peer_halo = 0;                    // option: 1 = ghost exchange by peer push inside (P)CG (measured slower than NCCL, see profiles/README.md)
+  int64_t use_peer_halo = 1;                    // option: ghost exchange by NVLink peer push inside (P)CG when the peers are mapped and dfb_halo_set_remote was called (0: NCCL send/recv)
   int64_t peer_halo_bytes = 8ll << 20;          // option (before dfb_ctx_peer_export): landing-zone bytes per parity buffer
   uint64_t landing_bytes = 0;                   // what the exported allocation actually holds per parity buffer
 };

@@ -301,10 +301,10 @@ dfb_status dfb_halo_destroy(dfb_halo *h);
 dfb_status dfb_halo_exchange(dfb_halo *h, dfb_vec *v);
 /* Optional (needs dfb_ctx_peer_import): remote_off[p] = recv_ptr entry, on rank peers[p], of the range that receives THIS rank's
    packet (in blocks). With it (P)CG pushes the boundary entries of its direction vector straight into the neighbours' landing zones
-   over NVLink (one small launch; the SpMV's boundary tiles wait for the neighbours' flags) instead of ncclSend/ncclRecv on a second
-   stream. The landing zone is sized by the ctx option "peer_halo_bytes" (default 8 MiB per buffer, set before dfb_ctx_peer_export).
-   Opt-in: ctx option "use_peer_halo" = 1 (default 0 = NCCL, which measured faster). Standalone dfb_bsr_mult_vec / dfb_halo_exchange
-   always use NCCL. */
+   over NVLink right after the direction kernel, and the SpMV becomes ONE launch whose boundary tiles wait for the neighbours' flags —
+   instead of pack kernel + ncclSend/ncclRecv on a second stream and three SpMV launches. The landing zone is sized by the ctx option
+   "peer_halo_bytes" (default 8 MiB per buffer, set before dfb_ctx_peer_export). Default on (ctx option "use_peer_halo" = 0 selects the
+   NCCL halo). Standalone dfb_bsr_mult_vec / dfb_halo_exchange always use NCCL. */
 dfb_status dfb_halo_set_remote(dfb_halo *h, const uint64_t *remote_off);
 /* attach a halo to a matrix: mult_vec / cg / pcg then exchange x's ghosts (overlapped with interior rows) and
    all-reduce their dot products.  interior rows = rows [int_begin, int_end) reference no ghost column. */
