@@ -345,6 +345,9 @@ class Env:
         ctx.set_option("iters_per_sync", args.iters_per_sync)
         ctx.set_option("use_graph", 0 if args.no_graph else 1)
         ctx.set_option("profile_spmv", args.profile_every)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            ctx.set_option(k, int(v))
         self.peak, self.peak_src = peak_hbm()
 
     def barrier(self):
@@ -919,6 +922,7 @@ def main():
     ap.add_argument("--no-peer", action="store_true", help="multi-GPU: NCCL for everything (all-reduce + halo) instead of the NVLink peer paths")
     ap.add_argument("--nccl-halo", action="store_true", help="multi-GPU: ncclSend/ncclRecv halo on a second stream (peer mailboxes still carry the scalars)")
     ap.add_argument("--profile-every", type=int, default=1, help="> 0: bracket the plain-launched SpMV at the head of every PCG chunk with CUDA events (roofline.achieved); 0 = off")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT", help="extra dfb_ctx option (A/B runs), e.g. --opt spmv_tile_rows=8")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip strong_S50 / dist_parity / configs")

@@ -474,15 +474,16 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
     __syncthreads();
     // ---- phase 3: contiguous, coalesced stores
     if (out.packed.base) {
-      for (uint64_t pt = r0 / DFB_PK_RPT; pt * DFB_PK_RPT < r1; ++pt) {
-        const uint64_t pr0 = pt * DFB_PK_RPT, pr1 = min(pr0 + (uint64_t)DFB_PK_RPT, P.num_rows);
+      const uint64_t prt = (uint64_t)out.packed.rpt;   // 8 or 16: the assembly tile (16 rows) is a whole number of packed tiles
+      for (uint64_t pt = r0 / prt; pt * prt < r1; ++pt) {
+        const uint64_t pr0 = pt * prt, pr1 = min(pr0 + prt, P.num_rows);
         double *vals = pk_tile_values(out.packed, pt);                 // [8 diagonal blocks | the tile's off-diagonal blocks]
         const uint32_t nd = (uint32_t)(pr1 - pr0) * NN;
         const double *sd = sout + (size_t)(n_off + (pr0 - r0)) * NN;
         for (uint32_t q = tid; q < nd; q += T) vals[q] = sd[q];
         const uint32_t pk0 = P.row2idx[pr0], nb = P.row2idx[pr1] - pk0;
         const double *sv = sout + (size_t)(pk0 - k0) * NN;
-        double *ov = vals + DFB_PK_RPT * NN;
+        double *ov = vals + prt * NN;
         for (uint32_t q = tid; q < nb * NN; q += T) ov[q] = sv[q];
       }
     } else {
@@ -518,6 +519,8 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
     out.packed.tile_off = nullptr;
     out.packed.NN = NN;
     out.packed.has_dia = 1;
+    out.packed.rpt = 8;
+    out.packed.hdr = 48;
     out.idx2val = m->d_idx2val;
     out.row2val = m->d_row2val;
   }

@@ -49,19 +49,17 @@ DFB_API dfb_pattern *dfb_bsr_pattern(const dfb_bsr *m) { return m ? m->pat : nul
 // ---- the tile-packed layout: per tile of 8 block-rows one contiguous 16-byte-aligned record
 //     [ u32 rowptr_rel[9] + pad : 48 B | u32 cols[nb] (pad 16) | diag 8 x NN f64 | vals nb x NN f64 (pad 16) ]
 // so the SpMV fetches a tile with a single cp.async.bulk and everything its compute phase needs arrives with it.
-static const int PK_RPT = DFB_PK_RPT, PK_HDR = DFB_PK_HDR;
-
-__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia) {
-  const uint32_t bytes = PK_HDR + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(PK_RPT * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
+__host__ __device__ inline uint32_t pk_tile_units(uint32_t nb, int NN, int has_dia, int rpt) {
+  const uint32_t bytes = (uint32_t)dfb_pk_hdr_bytes(rpt) + ((nb * 4u + 15u) & ~15u) + (has_dia ? (uint32_t)(rpt * NN * 8) : 0u) + ((nb * NN * 8u + 15u) & ~15u);
   return bytes >> 4;
 }
 
-__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia,
+__global__ void k_pack_sizes(const uint32_t *__restrict__ row2idx, uint64_t n_rows, uint64_t n_tiles, int NN, int has_dia, int rpt,
                              uint32_t *__restrict__ tile_units, unsigned int *max_units) {
   unsigned int mx = 0;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
-    const uint32_t u = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia);
+    const uint64_t r0 = t * rpt, r1 = min(r0 + (uint64_t)rpt, n_rows);
+    const uint32_t u = pk_tile_units(row2idx[r1] - row2idx[r0], NN, has_dia, rpt);
     tile_units[t] = u;
     mx = max(mx, u);
   }
@@ -75,29 +73,30 @@ enum { PK_STRUCT = 1, PK_VALUES = 2, PK_UNPACK = 4 };
 template <int MODE>
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__ row2idx, const uint32_t *__restrict__ idx2col,
                                                     double *__restrict__ idx2val, double *__restrict__ row2val, uint64_t n_rows,
-                                                    uint64_t n_tiles, int NN, int has_dia, const uint32_t *__restrict__ tile_off,
+                                                    uint64_t n_tiles, int NN, int has_dia, int rpt, const uint32_t *__restrict__ tile_off,
                                                     unsigned char *__restrict__ packed) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t hdr_bytes = (uint32_t)dfb_pk_hdr_bytes(rpt);
   for (uint64_t t = warp; t < n_tiles; t += nwarp) {
-    const uint64_t r0 = t * PK_RPT, r1 = min(r0 + (uint64_t)PK_RPT, n_rows);
+    const uint64_t r0 = t * rpt, r1 = min(r0 + (uint64_t)rpt, n_rows);
     const uint32_t k0 = row2idx[r0], nb = row2idx[r1] - k0;
     unsigned char *rec = packed + (uint64_t)tile_off[t] * 16;
     const uint32_t ncol_pad = ((nb * 4u + 15u) & ~15u) / 4u;
     if (MODE & PK_STRUCT) {
       uint32_t *hdr = reinterpret_cast<uint32_t *>(rec);
-      if (lane <= PK_RPT) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
-      if (lane > PK_RPT && lane < PK_HDR / 4) hdr[lane] = 0u;
-      uint32_t *cols = reinterpret_cast<uint32_t *>(rec + PK_HDR);
+      if (lane <= (unsigned)rpt) hdr[lane] = (r0 + lane <= r1) ? row2idx[r0 + lane] - k0 : nb;
+      if (lane > (unsigned)rpt && lane < hdr_bytes / 4) hdr[lane] = 0u;
+      uint32_t *cols = reinterpret_cast<uint32_t *>(rec + hdr_bytes);
       for (uint32_t k = lane; k < ncol_pad; k += 32) cols[k] = (k < nb) ? idx2col[k0 + k] : 0u;
     }
-    double *dia = reinterpret_cast<double *>(rec + PK_HDR + ncol_pad * 4u);
-    double *vals = dia + (has_dia ? PK_RPT * NN : 0);
+    double *dia = reinterpret_cast<double *>(rec + hdr_bytes + ncol_pad * 4u);
+    double *vals = dia + (has_dia ? rpt * NN : 0);
     const uint32_t nv = nb * NN, nv_pad = (((nb * NN * 8u) + 15u) & ~15u) / 8u;
     const uint32_t nd = (uint32_t)(r1 - r0) * NN;
     if (MODE & PK_VALUES) {
       if (has_dia)
-        for (uint32_t q = lane; q < (uint32_t)(PK_RPT * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
+        for (uint32_t q = lane; q < (uint32_t)(rpt * NN); q += 32) dia[q] = (q < nd) ? row2val[r0 * NN + q] : 0.0;
       const double *src = idx2val + (uint64_t)k0 * NN;
       for (uint32_t q = lane; q < nv_pad; q += 32) vals[q] = (q < nv) ? src[q] : 0.0;
     }
@@ -110,8 +109,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t *__restrict__
   }
 }
 
-template <int N> struct PackedCfg;
-static uint32_t packed_buf_bytes(int N);  // the SpMV's per-stage shared-memory buffer (defined with the kernel)
+static uint32_t packed_buf_bytes(int N, int rpt);  // the SpMV's per-stage shared-memory buffer (defined with the kernel)
 
 // allocate the packed records and write their pattern-only part (once per matrix); all value bytes start as zero
 static dfb_status bsr_packed_structure(dfb_bsr *m) {
@@ -119,11 +117,15 @@ static dfb_status bsr_packed_structure(dfb_bsr *m) {
   dfb_ctx *c = m->ctx;
   const uint64_t n = m->pat->num_blk;
   const int NN = m->blk_dim * m->blk_dim, has_dia = bsr_has_dia(m);
-  const uint64_t n_tiles = (n + PK_RPT - 1) / PK_RPT;
+  // sparse rows (spring networks: 6 blocks per row) get 16-row tiles: the SpMV is bound by bulk-copy operations per SM, not bytes,
+  // when a tile is only ~4 KB (measured: 2048^2 cloth 3.96 TB/s with 8-row tiles)
+  m->pk_rpt = (c->spmv_tile_rows == 8 || c->spmv_tile_rows == 16) ? (int)c->spmv_tile_rows : ((n > 0 && m->pat->nnz <= 8 * n) ? 16 : 8);
+  const int rpt = m->pk_rpt;
+  const uint64_t n_tiles = (n + rpt - 1) / rpt;
   DFB_TRY(dfb_dev_alloc_t(&m->d_tile_off, n_tiles + 2));
   unsigned int *d_max = (unsigned int *)(c->d_scratch + 18);
   DFB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), c->stream));
-  DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, m->d_tile_off, d_max);
+  DFB_LAUNCH(c, k_pack_sizes, c->sm_count * 8, 256, 0, m->pat->d_row2idx, n, n_tiles, NN, has_dia, rpt, m->d_tile_off, d_max);
   DFB_CHECK_LAUNCH();
   unsigned int h_max = 0;
   DFB_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
@@ -135,10 +137,10 @@ static dfb_status bsr_packed_structure(dfb_bsr *m) {
   DFB_CUDA(cudaMemsetAsync(m->d_packed, 0, m->packed_cap, c->stream));
   if (n_tiles > 0) {
     DFB_LAUNCH(c, k_pack_tiles<PK_STRUCT>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, (double *)nullptr, (double *)nullptr, n,
-               n_tiles, NN, has_dia, m->d_tile_off, m->d_packed);
+               n_tiles, NN, has_dia, rpt, m->d_tile_off, m->d_packed);
     DFB_CHECK_LAUNCH();
   }
-  m->packed_ok = ((uint64_t)h_max * 16 <= packed_buf_bytes(m->blk_dim)) ? 1 : 0;
+  m->packed_ok = ((uint64_t)h_max * 16 <= packed_buf_bytes(m->blk_dim, rpt)) ? 1 : 0;
   return DFB_OK;
 }
 
@@ -167,6 +169,8 @@ PackedView dfb_bsr_packed_view(const dfb_bsr *m) {
   v.tile_off = m->d_tile_off;
   v.NN = m->blk_dim * m->blk_dim;
   v.has_dia = bsr_has_dia(m) ? 1 : 0;
+  v.rpt = m->pk_rpt;
+  v.hdr = dfb_pk_hdr_bytes(m->pk_rpt);
   return v;
 }
 
@@ -180,7 +184,7 @@ dfb_status dfb_bsr_canon_read(const dfb_bsr *cm) {
     DFB_TRY(bsr_canon_alloc(m, false));
     if (m->n_tiles > 0) {
       DFB_LAUNCH(c, k_pack_tiles<PK_UNPACK>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val,
-                 m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->d_tile_off, m->d_packed);
+                 m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->pk_rpt, m->d_tile_off, m->d_packed);
       DFB_CHECK_LAUNCH();
     }
   }
@@ -222,7 +226,7 @@ dfb_status dfb_bsr_ensure_packed(const dfb_bsr *cm) {
   if (m->n_tiles > 0) {
     dfb_phase_begin(c, DFB_PH_PACK);
     DFB_LAUNCH(c, k_pack_tiles<PK_VALUES>, c->sm_count * 8, 256, 0, m->pat->d_row2idx, m->pat->d_idx2col, m->d_idx2val, m->d_row2val,
-               m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->d_tile_off, m->d_packed);
+               m->pat->num_blk, m->n_tiles, m->blk_dim * m->blk_dim, bsr_has_dia(m) ? 1 : 0, m->pk_rpt, m->d_tile_off, m->d_packed);
     dfb_phase_end(c);
     DFB_CHECK_LAUNCH();
   }
@@ -489,8 +493,8 @@ __global__ void __launch_bounds__(256) k_axpy_packed(const PackedView y, const P
   const unsigned lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t t = warp; t < n_tiles; t += nwarp) {
-    const uint32_t nb = reinterpret_cast<const uint32_t *>(pk_record(y, t))[DFB_PK_RPT];
-    const uint32_t n = ((y.has_dia ? DFB_PK_RPT : 0) + nb) * y.NN;
+    const uint32_t nb = reinterpret_cast<const uint32_t *>(pk_record(y, t))[y.rpt];
+    const uint32_t n = ((y.has_dia ? y.rpt : 0) + nb) * y.NN;
     double *yv = pk_tile_values(y, t);
     const double *xv = pk_tile_values(x, t);
     for (uint32_t q = lane; q < n; q += 32) yv[q] += alpha * xv[q];
@@ -901,35 +905,43 @@ static dfb_status spmv_launch_ring(dfb_ctx *c, const SpmvArgs &a, cudaStream_t s
 // so a tile is fetched by a single cp.async.bulk and everything the compute phase needs (relative row pointers included)
 // arrives with it. With this variant the packed records are the matrix's native storage (dfb_internal.h): assembly, BC and the
 // Jacobi preconditioners write / read them directly, the canonical arrays are only materialised for entry points that need them.
-static const int PK_LPR = 4;
-
-template <int N>
+template <int N, int RPT>
 struct PackedCfg {
   static constexpr int NN = N * N;
-  static constexpr int CAP = PK_RPT * 16;
-  static constexpr int BUF_BYTES = PK_HDR + ((CAP * 4 + 15) / 16) * 16 + PK_RPT * NN * 8 + ((CAP * NN * 8 + 15) / 16) * 16;
+  static constexpr int LPR = 32 / RPT;   // lanes per row: 4 (8-row tiles) or 2 (16-row tiles)
+  static constexpr int HDR = ((RPT + 1) * 4 + 15) / 16 * 16;
+  static constexpr int CAP = 128;        // blocks per tile held in shared memory (longer tiles take the direct path)
+  static constexpr int BUF_BYTES = HDR + ((CAP * 4 + 15) / 16) * 16 + RPT * NN * 8 + ((CAP * NN * 8 + 15) / 16) * 16;
   static constexpr int WARP_BYTES = 2 * BUF_BYTES + 16;
   static constexpr int WARPS_RAW = (220 * 1024) / WARP_BYTES;
   static constexpr int WARPS = WARPS_RAW > 24 ? 24 : (WARPS_RAW < 1 ? 1 : WARPS_RAW);
 };
 
-static uint32_t packed_buf_bytes(int N) {
+static uint32_t packed_buf_bytes(int N, int rpt) {
+  if (rpt == 16) {
+    switch (N) {
+      case 1: return PackedCfg<1, 16>::BUF_BYTES;
+      case 2: return PackedCfg<2, 16>::BUF_BYTES;
+      case 3: return PackedCfg<3, 16>::BUF_BYTES;
+      default: return PackedCfg<4, 16>::BUF_BYTES;
+    }
+  }
   switch (N) {
-    case 1: return PackedCfg<1>::BUF_BYTES;
-    case 2: return PackedCfg<2>::BUF_BYTES;
-    case 3: return PackedCfg<3>::BUF_BYTES;
-    default: return PackedCfg<4>::BUF_BYTES;
+    case 1: return PackedCfg<1, 8>::BUF_BYTES;
+    case 2: return PackedCfg<2, 8>::BUF_BYTES;
+    case 3: return PackedCfg<3, 8>::BUF_BYTES;
+    default: return PackedCfg<4, 8>::BUF_BYTES;
   }
 }
 
 // HALO = false is the single-domain kernel; HALO = true adds the peer-halo logic (ghost columns from the landing zone, interior
 // tiles first, bounded wait before the first boundary tile; only inside the solvers: needs a.st). The two are separate
 // instantiations because the tile mapping in the hot loop cost the single-domain kernel when it was compiled in unconditionally.
-template <int N, bool HALO>
-__global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const SpmvArgs a, const unsigned char *__restrict__ packed,
-                                                                         const uint32_t *__restrict__ tile_off, int has_dia) {
-  using S = PackedCfg<N>;
-  constexpr int NN = N * N, RPT = PK_RPT, LPR = PK_LPR;
+template <int N, bool HALO, int RPT>
+__global__ void __launch_bounds__(PackedCfg<N, RPT>::WARPS * 32) k_spmv_packed(const SpmvArgs a, const unsigned char *__restrict__ packed,
+                                                                              const uint32_t *__restrict__ tile_off, int has_dia) {
+  using S = PackedCfg<N, RPT>;
+  constexpr int NN = N * N, LPR = S::LPR, PK_HDR = S::HDR;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_buf[32];
   if (a.st && a.st->done[a.st->iter & 1]) return;
@@ -1052,21 +1064,22 @@ __global__ void __launch_bounds__(PackedCfg<N>::WARPS * 32) k_spmv_packed(const 
   if (a.fuse_dot) spmv_publish_dot(a, dot, s_buf);
 }
 
-template <int N>
+template <int N, int RPT>
 static dfb_status spmv_launch_packed(dfb_ctx *c, const SpmvArgs &a, const dfb_bsr *m, cudaStream_t strm) {
-  using S = PackedCfg<N>;
+  using S = PackedCfg<N, RPT>;
   const int warps = S::WARPS;
   const size_t smem = (size_t)warps * S::WARP_BYTES;
-  const uint64_t t_begin = a.row_begin / PK_RPT, t_end = ((uint64_t)a.row_end + PK_RPT - 1) / PK_RPT;
+  const uint64_t t_begin = a.row_begin / RPT, t_end = ((uint64_t)a.row_end + RPT - 1) / RPT;
   uint64_t g = (t_end - t_begin + warps - 1) / warps;
   if (g < 1) g = 1;
   if (g > (uint64_t)c->sm_count) g = (uint64_t)c->sm_count;
+  // (the dynamic shared-memory opt-in is a per-device function attribute: set on every launch, cheap)
   if (a.hw.xg[0] != nullptr) {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, true, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, true, RPT>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
   } else {
-    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
+    DFB_CUDA(cudaFuncSetAttribute(k_spmv_packed<N, false, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DFB_LAUNCH_ON(c, strm, (k_spmv_packed<N, false, RPT>), (unsigned)g, warps * 32, smem, a, m->d_packed, m->d_tile_off, bsr_has_dia(m) ? 1 : 0);
   }
   DFB_CHECK_LAUNCH();
   return DFB_OK;
@@ -1123,11 +1136,19 @@ dfb_status dfb_spmv_launch(const dfb_bsr *m, double *y, double beta, double alph
     a.hw.tile_hi_begin = 0xFFFFFFFFu;
   }
   if (c->spmv_variant == 20) {
+    if (m->pk_rpt == 16) {
+      switch (m->blk_dim) {
+        case 1: return spmv_launch_packed<1, 16>(c, a, m, strm);
+        case 2: return spmv_launch_packed<2, 16>(c, a, m, strm);
+        case 3: return spmv_launch_packed<3, 16>(c, a, m, strm);
+        case 4: return spmv_launch_packed<4, 16>(c, a, m, strm);
+      }
+    }
     switch (m->blk_dim) {
-      case 1: return spmv_launch_packed<1>(c, a, m, strm);
-      case 2: return spmv_launch_packed<2>(c, a, m, strm);
-      case 3: return spmv_launch_packed<3>(c, a, m, strm);
-      case 4: return spmv_launch_packed<4>(c, a, m, strm);
+      case 1: return spmv_launch_packed<1, 8>(c, a, m, strm);
+      case 2: return spmv_launch_packed<2, 8>(c, a, m, strm);
+      case 3: return spmv_launch_packed<3, 8>(c, a, m, strm);
+      case 4: return spmv_launch_packed<4, 8>(c, a, m, strm);
     }
   }
   switch (m->blk_dim) {
@@ -1159,8 +1180,8 @@ dfb_status dfb_spmv_full(const dfb_bsr *m, double *y, double beta, double alpha,
   if (in_solver && dfb_spmv_uses_peer_halo(m)) {
     DfbHaloWait hw;
     dfb_halo_wait_view(m->halo, m->blk_dim, n, &hw);
-    hw.tile_lo_end = (uint32_t)((m->int_begin + PK_RPT - 1) / PK_RPT);
-    hw.tile_hi_begin = (uint32_t)(m->int_end / PK_RPT);
+    hw.tile_lo_end = (uint32_t)((m->int_begin + m->pk_rpt - 1) / m->pk_rpt);
+    hw.tile_hi_begin = (uint32_t)(m->int_end / m->pk_rpt);
     return dfb_spmv_launch(m, y, beta, alpha, x, 0, n, fuse_dot, in_solver, c->stream, post, &hw);
   }
   // comm stream: wait until x is final, exchange ghosts

@@ -163,6 +163,7 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "assemble_tile_rows")) return &c->assemble_tile_rows;
   if (!strcmp(key, "assemble_tile_threads")) return &c->assemble_tile_threads;
   if (!strcmp(key, "spmv_ctas_per_sm")) return &c->spmv_ctas_per_sm;
+  if (!strcmp(key, "spmv_tile_rows")) return &c->spmv_tile_rows;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
   if (!strcmp(key, "ilu_level_launches")) return &c->ilu_level_launches;
   if (!strcmp(key, "ilu_sweep_ctas_per_sm")) return &c->ilu_sweep_ctas_per_sm;

@@ -126,6 +126,7 @@ struct dfb_ctx {
   int64_t assemble_tile_threads = 0;  // 0: one thread per off-diagonal slot + 4 per diagonal slot of the largest tile
   int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
+  int64_t spmv_tile_rows = 0;    // block-rows per packed tile: 0 = by row density (8, or 16 for <= 8 blocks per row), else 8 / 16
   int64_t ilu_sweep_ctas_per_sm = 1;  // resident CTAs (256 threads) per SM of a persistent ILU sweep
   int64_t ilu_level_launches = 0;  // 1: ILU sweeps as one launch per level (reference point) instead of the dependency-driven sweeps
   int64_t profile_spmv = 0;
@@ -228,7 +229,7 @@ struct DfbHaloPush {   // kernel argument of the pack-and-push launch
 // Matrix values live in ONE of two layouts (or both, when both are current):
 //   canonical  idx2val[nnz*NN] + row2val[num_blk*NN]: exactly the reference's Vec<[T;NN]> arrays (upload/download, per-element merge,
 //              ILU, sparse product, SpMV variants 0/4 work on these)
-//   packed     the tile-packed SpMV mirror (bsr.cu): per 8 block-rows one record [rowptr_rel | cols | 8 diagonal blocks | value blocks]
+//   packed     the tile-packed SpMV mirror (bsr.cu): per 8 (or 16) block-rows one record [rowptr_rel | cols | diagonal blocks | value blocks]
 // With spmv_variant 20 the packed layout is the NATIVE one: assembly, Dirichlet BC, add_to_diagonal, add_scaled, the Jacobi
 // preconditioners and the SpMV all work on it directly, and the canonical arrays are only materialised (unpack kernel) when an entry
 // point that needs them is called. Nothing is allocated until the values are first needed (a new matrix is "all zero").
@@ -247,39 +248,41 @@ struct dfb_bsr {
   uint32_t *d_tile_off = nullptr;   // [n_tiles + 1], in 16-byte units
   uint64_t packed_cap = 0;          // bytes allocated
   uint64_t n_tiles = 0;
+  int pk_rpt = 8;                   // block-rows per packed tile (8 or 16), fixed when the layout is built
   int packed_valid = 0;             // the packed records hold the current values
   int packed_ok = -1;               // -1 layout not built yet, 1 every tile fits the SpMV's shared-memory buffer, 0 some tile is oversized
                                     //  (its rows are multiplied straight from the canonical arrays, which then stay the native layout)
 };
 
-// device-side view of the packed layout
+// device-side view of the packed layout. rpt = block-rows per tile: 8 (4 lanes per row in the SpMV) or, for sparse rows (<= 8 blocks per
+// row on average, e.g. spring networks), 16 (2 lanes per row) so that a tile's single bulk copy stays ~8 KB
 struct PackedView {
   unsigned char *base;
   const uint32_t *tile_off;
-  int NN, has_dia;
+  int NN, has_dia, rpt, hdr;   // hdr = bytes of the record header: rpt + 1 relative row pointers, padded to 16
 };
-static const int DFB_PK_RPT = 8, DFB_PK_HDR = 48;
+__host__ __device__ inline int dfb_pk_hdr_bytes(int rpt) { return ((rpt + 1) * 4 + 15) / 16 * 16; }
 __device__ __forceinline__ unsigned char *pk_record(const PackedView &v, uint64_t tile) { return v.base + ((uint64_t)v.tile_off[tile] << 4); }
 // diagonal block of row r
 __device__ __forceinline__ double *pk_diag(const PackedView &v, uint64_t r) {
-  unsigned char *rec = pk_record(v, r / DFB_PK_RPT);
-  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[DFB_PK_RPT];
-  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u)) + (r % DFB_PK_RPT) * v.NN;
+  unsigned char *rec = pk_record(v, r / v.rpt);
+  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[v.rpt];
+  return reinterpret_cast<double *>(rec + v.hdr + ((nb * 4u + 15u) & ~15u)) + (r % v.rpt) * v.NN;
 }
 // off-diagonal blocks of row r: values, column indices, count
 __device__ __forceinline__ double *pk_row(const PackedView &v, uint64_t r, const uint32_t **cols, uint32_t *n) {
-  unsigned char *rec = pk_record(v, r / DFB_PK_RPT);
+  unsigned char *rec = pk_record(v, r / v.rpt);
   const uint32_t *hdr = reinterpret_cast<const uint32_t *>(rec);
-  const uint32_t nb = hdr[DFB_PK_RPT], kb = hdr[r % DFB_PK_RPT], ke = hdr[r % DFB_PK_RPT + 1];
-  *cols = reinterpret_cast<const uint32_t *>(rec + DFB_PK_HDR) + kb;
+  const uint32_t nb = hdr[v.rpt], kb = hdr[r % v.rpt], ke = hdr[r % v.rpt + 1];
+  *cols = reinterpret_cast<const uint32_t *>(rec + v.hdr) + kb;
   *n = ke - kb;
-  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u)) + (v.has_dia ? DFB_PK_RPT * v.NN : 0) + (uint64_t)kb * v.NN;
+  return reinterpret_cast<double *>(rec + v.hdr + ((nb * 4u + 15u) & ~15u)) + (v.has_dia ? v.rpt * v.NN : 0) + (uint64_t)kb * v.NN;
 }
 // first value (the tile's diagonal blocks, then its off-diagonal blocks, contiguous) of tile t
 __device__ __forceinline__ double *pk_tile_values(const PackedView &v, uint64_t tile) {
   unsigned char *rec = pk_record(v, tile);
-  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[DFB_PK_RPT];
-  return reinterpret_cast<double *>(rec + DFB_PK_HDR + ((nb * 4u + 15u) & ~15u));
+  const uint32_t nb = reinterpret_cast<const uint32_t *>(rec)[v.rpt];
+  return reinterpret_cast<double *>(rec + v.hdr + ((nb * 4u + 15u) & ~15u));
 }
 
 // ---- layout management (bsr.cu)

@@ -75,13 +75,13 @@ def test_sass_contains_tma_bulk_copies(dfb):
     funcs = out.split("Function : ")
     # the shipped default k_spmv_packed<3, false> (variant 20): exactly one bulk-copy site per tile buffer stage + the prologue,
     # no halo logic (the separate <3, true> instantiation carries the flag loads), and the ring kernel of variant 4
-    for prefix in ("_Z13k_spmv_packedILi3ELb0EE", "_Z13k_spmv_packedILi3ELb1EE", "_Z11k_spmv_ringILi3EE"):
+    for prefix in ("_Z13k_spmv_packedILi3ELb0ELi8EE", "_Z13k_spmv_packedILi3ELb1ELi8EE", "_Z11k_spmv_ringILi3EE"):
         k = [f for f in funcs if f.startswith(prefix)]
         assert k, f"{prefix} not found in the library"
         assert "UBLKCP" in k[0], prefix
         assert "SYNCS" in k[0], prefix  # mbarrier
-    plain = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb0EE")][0]
-    halo = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb1EE")][0]
+    plain = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb0ELi8EE")][0]
+    halo = [f for f in funcs if f.startswith("_Z13k_spmv_packedILi3ELb1ELi8EE")][0]
     assert "LDG.E.64.STRONG.SYS" not in plain and "LDG.E.64.STRONG.SYS" in halo  # only the halo kernel polls peer flags
     # the halo kernel carries the row code twice: interior tiles run the single-domain instruction stream, boundary tiles a copy
     # whose ghost gathers are L2-coherent loads (the neighbours write the landing zone while the kernel runs)
