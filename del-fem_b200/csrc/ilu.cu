@@ -29,8 +29,11 @@ struct DfbIlu {
   std::vector<uint32_t> lev_f, lev_b;  // level pointers into d_rows_f / d_rows_b (host)
   double *d_val = nullptr;        // factor values [nnz*NN]
   double *d_z = nullptr;          // explicit preconditioned residual for PCG [n*N]
-  uint32_t *d_lev_f = nullptr, *d_lev_b = nullptr;   // level pointers on the device (persistent sweeps)
-  uint32_t *d_epoch = nullptr;    // [8] grid-barrier counter of the persistent sweeps at [4]
+  uint32_t *d_epoch = nullptr;    // [8] grid-barrier counters of the persistent sweeps at [4..7]
+  struct Items {                  // work items of a persistent sweep for one launch shape (ilu_items)
+    uint2 *d = nullptr;
+    uint32_t n = 0, pass = 0;
+  } items_f, items_b;
 };
 
 template <int N>
@@ -209,104 +212,185 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
   }
 }
 
-// ---- level sweeps inside ONE persistent launch with a grid-wide barrier between levels (default; S10: 2 launches per application
-// instead of 448 + 448). All CTAs are resident (one per SM); a level's rows are strided over the whole grid; barrier = one atomic
-// per CTA + one polling thread per CTA. Same row arithmetic as the per-level kernels => same bits.
-// Measured (tools/precond_compare.py, profiles/r2_precond_compare.txt): S1 4.5 ms per PCG iteration (6.4 with one launch per level),
-// S10 11.5 (41.7): ~10 us per level remain, so ILU(0)-PCG is still slower than Jacobi-PCG in time (S1 1.07 s vs 0.08 s).
+// ---- level sweeps inside ONE persistent launch (default; S10: 2 launches per application instead of 448 + 448), two flavours of
+// the same kernel:
+//   CLUSTER = false  one CTA per SM, a grid-wide barrier between levels (one atomic per CTA on one of four counters + one
+//                    polling thread per CTA)
+//   CLUSTER = true   ONE thread-block cluster (16 CTAs), the hardware cluster barrier (barrier.cluster, release/acquire at cluster
+//                    scope) between levels
+// A block-row is shared by N lanes — lane a carries component a of t = v_i - sum_j L_ij v_j through the reference's loop
+// (sparse_ilu.rs:183-219: ascending entries, mult_vec's left fold over the block's columns), the D^-1 product takes the other
+// lanes' t by shuffle — so every rounding is the one of the one-thread-per-row kernels above (bit-identical, tested).
+// The work items (one pass of the whole grid over part of a level; built on the host for the launch shape, staged in shared
+// memory) are software-pipelined FOUR deep so that no load issued in an iteration is consumed in the same iteration (a warp
+// issues in order: a dependent chain row id -> row pointers -> columns inside one iteration would stall the row arithmetic):
+//   item k+3: row id      item k+2: row pointers      item k+1: columns (registers) + factor blocks (L2 prefetch)      item k: the row
+// After a barrier only the neighbours' values (L2) and the prefetched blocks are read. THREADS is chosen by the mean level
+// width: narrow levels are latency-bound and every resident warp costs issue slots per level, wide levels want the warps.
 // A sync-free variant (per-row epoch flags polled by the dependent rows, Liu et al.) was built and measured SLOWER (11-13 ms per
 // iteration at S1 for every window size / back-off tried: 0.78 G L2 requests of polling per sweep) and removed.
-__device__ __forceinline__ void ilu_grid_barrier(unsigned int *ctr, unsigned int target) {
+static const int ILU_BAR_WAYS = 4;   // arrival counters of the grid barrier (CTA b arrives on counter b % 4)
+__device__ __forceinline__ void ilu_grid_barrier(unsigned int *ctr, unsigned int epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();   // the CTA's stores (ordered before by the barrier above) are performed before the arrival
+    atomicAdd(ctr + (blockIdx.x % ILU_BAR_WAYS), 1u);
+    // counter w receives one arrival per epoch from each CTA with id % 4 == w
+    unsigned int want[ILU_BAR_WAYS];
+#pragma unroll
+    for (int w = 0; w < ILU_BAR_WAYS; ++w) want[w] = epoch * ((gridDim.x + ILU_BAR_WAYS - 1 - w) / ILU_BAR_WAYS);
+    for (;;) {
+      unsigned int v0, v1, v2, v3;
+      asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "l"(ctr) : "memory");
+      if (v0 >= want[0] && v1 >= want[1] && v2 >= want[2] && v3 >= want[3]) break;
+    }
     __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
   }
   __syncthreads();
 }
-__global__ void k_ilu_barrier_reset(unsigned int *ctr) { *ctr = 0u; }
+__global__ void k_ilu_barrier_reset(unsigned int *ctr) {
+  if (threadIdx.x < ILU_BAR_WAYS) ctr[threadIdx.x] = 0u;
+}
 
-template <int N, bool FORWARD>
-__global__ void __launch_bounds__(256) k_ilu_sweep_levels(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ lev_ptr, uint32_t n_lev,
-                                                          const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ col,
-                                                          const uint32_t *__restrict__ diap, const double *__restrict__ val,
-                                                          const double *__restrict__ dia, double *vec, unsigned int *bar) {
-  constexpr int NN = N * N, KPRE = 16;
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  // Software pipeline across levels: while level l is being computed (and during its barrier) every thread already fetches what
-  // its FIRST row of level l+1 needs and does not depend on other rows — row id, row pointers, column indices (registers) and the
-  // factor blocks (L2 prefetch) — so that after the barrier only the neighbours' values (L2) are on the critical path.
-  struct Pre {
-    uint32_t i, kb, ke;
-    uint32_t cols[KPRE];
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int N> struct IluLanes { static constexpr int LPR = (N == 3) ? 4 : N; };   // lanes per row (N = 3: the 4th lane of a quad idles)
+static const int ILU_ITEM_SMEM = 4096;          // work items staged in shared memory (longer lists: read from global)
+static const uint32_t ILU_ITEM_BARRIER = 0x80000000u;   // flag in an item's end: a level boundary precedes the item
+
+template <int N, bool FORWARD, bool CLUSTER, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_ilu_sweep(const uint32_t *__restrict__ rows, const uint2 *__restrict__ items, uint32_t n_items,
+                                                       const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ col,
+                                                       const uint32_t *__restrict__ diap, const double *__restrict__ val,
+                                                       const double *__restrict__ dia, double *vec, unsigned int *bar) {
+  constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = 32 / LPR, KPRE = 8;
+  constexpr int B = THREADS <= 128 ? 8 : 4;   // entries whose loads are issued together before their arithmetic (registers)
+  __shared__ uint2 s_item[ILU_ITEM_SMEM];
+  const unsigned n_cta = CLUSTER ? cluster_nctarank() : gridDim.x, cta = CLUSTER ? cluster_ctarank() : blockIdx.x;
+  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const unsigned sub = lane % LPR, base = lane - sub;
+  const bool act = sub < (unsigned)N;
+  const unsigned a_ = act ? sub : 0u;                            // component of the row this lane carries
+  const uint32_t slot = (wid * n_cta + cta) * RPW + lane / LPR;  // consecutive row groups of a level go to different CTAs
+  const bool in_smem = n_items <= (uint32_t)ILU_ITEM_SMEM;
+  if (in_smem)
+    for (uint32_t k = threadIdx.x; k < n_items; k += THREADS) s_item[k] = items[k];
+  __syncthreads();
+  const uint32_t NONE = 0xFFFFFFFFu;
+  // item k: rows [x, y & ~flag) of the level-ordered row list, of which this lane group takes x + slot
+  auto item = [&](uint32_t k) -> uint2 {
+    if (k >= n_items) return make_uint2(0u, 0u);
+    return in_smem ? s_item[k] : items[k];
   };
-  auto prefetch_row = [&](uint32_t q, uint32_t b) -> Pre {
-    Pre p;
-    p.i = 0xFFFFFFFFu;
-    p.kb = p.ke = 0;
-#pragma unroll
-    for (int k = 0; k < KPRE; ++k) p.cols[k] = 0u;
-    if (q < b) {
-      p.i = rows[q];
-      p.kb = FORWARD ? r2i[p.i] : diap[p.i];
-      p.ke = FORWARD ? diap[p.i] : r2i[p.i + 1];
-#pragma unroll
-      for (int k = 0; k < KPRE; ++k)
-        if (p.kb + k < p.ke) p.cols[k] = col[p.kb + k];
-      const char *pb = reinterpret_cast<const char *>(val + (uint64_t)p.kb * NN), *pe = reinterpret_cast<const char *>(val + (uint64_t)p.ke * NN);
-      for (const char *c = pb; c < pe; c += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
-      if (FORWARD) asm volatile("prefetch.global.L2 [%0];" ::"l"(dia + (uint64_t)p.i * NN));
+  // the three load stages (each consumes only what an EARLIER iteration loaded)
+  auto load_row_id = [&](uint32_t k) -> uint32_t {
+    const uint2 it = item(k);
+    const uint32_t q = it.x + slot;
+    return q < (it.y & ~ILU_ITEM_BARRIER) ? rows[q] : NONE;
+  };
+  auto load_row_ptrs = [&](uint32_t i, uint32_t &kb, uint32_t &ke) {
+    kb = ke = 0;
+    if (i != NONE) {
+      kb = FORWARD ? r2i[i] : diap[i];
+      ke = FORWARD ? diap[i] : r2i[i + 1];
     }
-    return p;
   };
-  auto do_row = [&](const Pre &p) {
-    const uint32_t i = p.i;
-    double t[N], v[N], x[N];
+  auto load_cols = [&](uint32_t i, uint32_t kb, uint32_t ke, uint32_t (&cols)[KPRE]) {
 #pragma unroll
-    for (int d = 0; d < N; ++d) t[d] = __ldcg(vec + (uint64_t)i * N + d);
+    for (int k = 0; k < KPRE; ++k) cols[k] = (kb + k < ke) ? col[kb + k] : 0u;
+    if (i != NONE) {   // the lanes of a row split the row's 128-byte lines between them
+      const char *pb = reinterpret_cast<const char *>(val + (uint64_t)kb * NN), *pe = reinterpret_cast<const char *>(val + (uint64_t)ke * NN);
+      for (const char *c = pb + 128 * sub; c < pe; c += 128 * LPR) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
+      if (FORWARD && sub == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(dia + (uint64_t)i * NN));
+    }
+  };
+  // the row itself; executed by whole warps (shuffles): rows beyond the level (i = NONE) only take part in those
+  auto do_row = [&](uint32_t ri, uint32_t kb, uint32_t ke, const uint32_t (&cols)[KPRE]) {
+    const bool live = ri != NONE;
+    const uint32_t i = live ? ri : 0u;
+    double t = live ? __ldcg(vec + (uint64_t)i * N + a_) : 0.0;
+    double dw[N];
+    if (FORWARD) {
 #pragma unroll
-    for (int k = 0; k < KPRE; ++k) {
-      if (p.kb + k < p.ke) {
+      for (int d = 0; d < N; ++d) dw[d] = live ? dia[(uint64_t)i * NN + a_ + N * d] : 0.0;
+    }
 #pragma unroll
-        for (int d = 0; d < N; ++d) x[d] = __ldcg(vec + (uint64_t)p.cols[k] * N + d);  // written by other SMs in earlier levels: L2
-        mat_vec<N>(v, val + (uint64_t)(p.kb + k) * NN, x);
+    for (int k0 = 0; k0 < KPRE; k0 += B) {
+      double x[B][N], w[B][N];
 #pragma unroll
-        for (int d = 0; d < N; ++d) t[d] -= v[d];
+      for (int k = 0; k < B; ++k) {
+        const bool on = kb + k0 + k < ke;
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+          x[k][d] = on ? __ldcg(vec + (uint64_t)cols[k0 + k] * N + d) : 0.0;   // written by other SMs in earlier levels: L2
+          w[k][d] = on ? val[(uint64_t)(kb + k0 + k) * NN + a_ + N * d] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        if (kb + k0 + k < ke) {
+          double s = 0.0;
+#pragma unroll
+          for (int d = 0; d < N; ++d) s = s + w[k][d] * x[k][d];
+          t -= s;
+        }
       }
     }
-    for (uint32_t k = p.kb + KPRE; k < p.ke; ++k) {
+    for (uint32_t k = kb + KPRE; k < ke; ++k) {   // rows longer than the pipelined columns (ILU(k) fill)
+      const uint32_t c = col[k];
+      double s = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) x[d] = __ldcg(vec + (uint64_t)col[k] * N + d);
-      mat_vec<N>(v, val + (uint64_t)k * NN, x);
-#pragma unroll
-      for (int d = 0; d < N; ++d) t[d] -= v[d];
+      for (int d = 0; d < N; ++d) s = s + val[(uint64_t)k * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
+      t -= s;
     }
     if (FORWARD) {
-      mat_vec<N>(v, dia + (uint64_t)i * NN, t);
+      double s = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) vec[(uint64_t)i * N + d] = v[d];
-    } else {
-#pragma unroll
-      for (int d = 0; d < N; ++d) vec[(uint64_t)i * N + d] = t[d];
+      for (int d = 0; d < N; ++d) s = s + dw[d] * __shfl_sync(0xFFFFFFFFu, t, base + d);
+      t = s;
     }
+    if (live && act) vec[(uint64_t)i * N + a_] = t;
   };
-  Pre cur = prefetch_row(lev_ptr[0] + gtid, lev_ptr[1]);
-  for (uint32_t l = 0; l < n_lev; ++l) {
-    const uint32_t a = lev_ptr[l], b = lev_ptr[l + 1];
-    Pre nxt;
-    nxt.i = 0xFFFFFFFFu;
-    if (l + 1 < n_lev) nxt = prefetch_row(lev_ptr[l + 1] + gtid, lev_ptr[l + 2]);   // lev_ptr has n_lev + 1 entries
-    if (cur.i != 0xFFFFFFFFu) do_row(cur);
-    for (uint32_t q = a + gtid + gsz; q < b; q += gsz) {   // levels wider than the grid: the remaining rows, unpipelined
-      const Pre p = prefetch_row(q, b);
-      do_row(p);
+
+  if (n_items == 0) return;
+  // prologue: fill the pipeline (the only place where the dependent chain is waited for)
+  uint32_t i0 = load_row_id(0), i1 = load_row_id(1), i2 = load_row_id(2);
+  uint32_t kb0, ke0, kb1, ke1;
+  load_row_ptrs(i0, kb0, ke0);
+  load_row_ptrs(i1, kb1, ke1);
+  uint32_t cols0[KPRE];
+  load_cols(i0, kb0, ke0, cols0);
+  uint32_t n_bar = 0;
+  for (uint32_t k = 0;; ++k) {
+    // stage loads for the items ahead (addresses come from registers filled in earlier iterations)
+    const uint32_t i3 = load_row_id(k + 3);
+    uint32_t kb2, ke2;
+    load_row_ptrs(i2, kb2, ke2);
+    uint32_t cols1[KPRE];
+    load_cols(i1, kb1, ke1, cols1);
+    do_row(i0, kb0, ke0, cols0);
+    if (k + 1 >= n_items) break;
+    if (item(k + 1).y & ILU_ITEM_BARRIER) {
+      if (CLUSTER) cluster_barrier();
+      else ilu_grid_barrier(bar, ++n_bar);
     }
-    if (l + 1 < n_lev) ilu_grid_barrier(bar, (l + 1) * gridDim.x);
-    cur = nxt;
+    i0 = i1; kb0 = kb1; ke0 = ke1;
+#pragma unroll
+    for (int q = 0; q < KPRE; ++q) cols0[q] = cols1[q];
+    i1 = i2; kb1 = kb2; ke1 = ke2;
+    i2 = i3;
   }
 }
 
@@ -331,8 +415,8 @@ void dfb_ilu_destroy(DfbIlu *s) {
   dfb_dev_free(s->d_val);
   dfb_dev_free(s->d_z);
   dfb_dev_free(s->d_epoch);
-  dfb_dev_free(s->d_lev_f);
-  dfb_dev_free(s->d_lev_b);
+  dfb_dev_free(s->items_f.d);
+  dfb_dev_free(s->items_b.d);
   delete s;
 }
 
@@ -463,8 +547,6 @@ dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIl
   up(&s->d_dia, dia);
   up(&s->d_rows_f, rows_f);
   up(&s->d_rows_b, rows_b);
-  up(&s->d_lev_f, s->lev_f);
-  up(&s->d_lev_b, s->lev_b);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_epoch, 8);
   if (st == DFB_OK) cudaMemsetAsync(s->d_epoch, 0, 8 * sizeof(uint32_t), c->stream);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_val, nnz * NN + 8);
@@ -508,34 +590,141 @@ dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia
   return dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "ilu0 decompose: singular pivot block (try_inverse().unwrap())");
 }
 
-// solve_preconditioning_vec, in place
-template <int N>
-static dfb_status ilu_sweeps_barrier(dfb_ctx *c, const DfbIlu *s, const double *d_dia, double *d_vec) {
-  int per_sm = 1;
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ilu_sweep_levels<N, true>, 256, 0));
-  int per_sm_b = 1;
-  DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_ilu_sweep_levels<N, false>, 256, 0));
-  if (per_sm_b < per_sm) per_sm = per_sm_b;
-  if (c->ilu_sweep_ctas_per_sm > 0 && c->ilu_sweep_ctas_per_sm < per_sm) per_sm = (int)c->ilu_sweep_ctas_per_sm;
-  if (per_sm < 1) per_sm = 1;
-  const unsigned g = (unsigned)(c->sm_count * per_sm);
-  const uint32_t nf = s->lev_f.empty() ? 0 : (uint32_t)s->lev_f.size() - 1, nb = s->lev_b.empty() ? 0 : (uint32_t)s->lev_b.size() - 1;
+// work items of a sweep for a launch shape: every non-empty level is cut into passes of `pass` rows; the first pass of every
+// level but the first carries the barrier flag. Cached per direction until the shape changes.
+static dfb_status ilu_items(dfb_ctx *c, const DfbIlu *cs, bool forward, uint32_t pass, const uint2 **d_items, uint32_t *n_items) {
+  DfbIlu *s = const_cast<DfbIlu *>(cs);
+  DfbIlu::Items &I = forward ? s->items_f : s->items_b;
+  if (I.pass != pass || !I.d) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    DFB_CUDA(cudaStreamIsCapturing(c->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return dfb_fail(DFB_ERR_BAD_ARG, "ilu: the sweep shape changed inside a stream capture");
+    const std::vector<uint32_t> &lev = forward ? s->lev_f : s->lev_b;
+    std::vector<uint2> h;
+    bool first = true;
+    for (size_t l = 0; l + 1 < lev.size(); ++l) {
+      const uint32_t a = lev[l], b = lev[l + 1];
+      for (uint32_t q = a; q < b; q += pass) {
+        h.push_back(make_uint2(q, b | ((q == a && !first) ? ILU_ITEM_BARRIER : 0u)));
+        first = false;
+      }
+    }
+    DFB_CUDA(cudaStreamSynchronize(c->stream));   // a sweep with the old list may be in flight
+    dfb_dev_free(I.d);
+    I.d = nullptr;
+    DFB_TRY(dfb_dev_alloc_t(&I.d, h.size() + 1));
+    if (!h.empty()) DFB_CUDA(cudaMemcpy(I.d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    I.n = (uint32_t)h.size();
+    I.pass = pass;
+  }
+  *d_items = I.d;
+  *n_items = I.n;
+  return DFB_OK;
+}
+
+static void ilu_cluster_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *at, int cs, int threads, cudaStream_t strm) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(cs);
+  cfg->blockDim = dim3(threads);
+  cfg->stream = strm;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
+  cfg->attrs = at;
+  cfg->numAttrs = 1;
+}
+
+// one cluster of 16 CTAs (8 where the non-portable size cannot be scheduled); 0 = clusters unavailable for this kernel
+template <int N, int THREADS>
+static int ilu_cluster_size(dfb_ctx *c) {
+  static int cached = -1, cached_want = -1;
+  const int want = c->ilu_cluster_ctas > 0 ? (int)c->ilu_cluster_ctas : 16;
+  if (cached >= 0 && cached_want == want) return cached;
+  int best = 0;
+  for (int cs = want; cs >= 1 && !best; cs /= 2) {
+    bool ok = true;
+    for (int f = 0; f < 2 && ok; ++f) {
+      const void *fn = f ? (const void *)k_ilu_sweep<N, true, true, THREADS> : (const void *)k_ilu_sweep<N, false, true, THREADS>;
+      if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute at[1];
+      ilu_cluster_config(&cfg, at, cs, THREADS, c->stream);
+      int nclusters = 0;
+      if (ok && (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1)) ok = false;
+    }
+    if (ok) best = cs;
+  }
+  (void)cudaGetLastError();
+  cached = best;
+  cached_want = want;
+  return best;
+}
+
+// solve_preconditioning_vec, in place: forward then backward sweep, one launch each
+template <int N, int THREADS>
+static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, const double *d_dia, double *d_vec, bool cluster) {
+  constexpr int RPW = 32 / IluLanes<N>::LPR;
+  int n_cta = c->sm_count;   // grid barrier: one resident CTA per SM (<= 512 threads, 32 KB of shared memory: always co-resident)
+  if (cluster) {
+    n_cta = ilu_cluster_size<N, THREADS>(c);
+    if (n_cta < 1) {
+      cluster = false;
+      n_cta = c->sm_count;
+    }
+  }
+  const uint32_t pass = (uint32_t)n_cta * (THREADS / 32) * RPW;
+  const uint2 *it_f = nullptr, *it_b = nullptr;
+  uint32_t nf = 0, nb = 0;
+  DFB_TRY(ilu_items(c, s, true, pass, &it_f, &nf));
+  DFB_TRY(ilu_items(c, s, false, pass, &it_b, &nb));
+  const uint32_t *rows_f = s->d_rows_f, *rows_b = s->d_rows_b, *r2i = s->d_r2i, *col = s->d_col, *dp = s->d_dia;
+  const double *val = s->d_val;
   unsigned int *bar = s->d_epoch + 4;
-  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nf) DFB_LAUNCH(c, (k_ilu_sweep_levels<N, true>), g, 256, 0, s->d_rows_f, s->d_lev_f, nf, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, bar);
-  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nb) DFB_LAUNCH(c, (k_ilu_sweep_levels<N, false>), g, 256, 0, s->d_rows_b, s->d_lev_b, nb, s->d_r2i, s->d_col, s->d_dia, s->d_val, d_dia, d_vec, bar);
+  if (cluster) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    ilu_cluster_config(&cfg, at, n_cta, THREADS, c->stream);
+    if (nf) {
+      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, true, true, THREADS>, rows_f, it_f, nf, r2i, col, dp, val, d_dia, d_vec, bar));
+      c->launches += 1;
+    }
+    if (nb) {
+      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, false, true, THREADS>, rows_b, it_b, nb, r2i, col, dp, val, d_dia, d_vec, bar));
+      c->launches += 1;
+    }
+    return DFB_OK;
+  }
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 32, 0, bar);
+  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, false, THREADS>), n_cta, THREADS, 0, rows_f, it_f, nf, r2i, col, dp, val, d_dia, d_vec, bar);
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 32, 0, bar);
+  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, false, THREADS>), n_cta, THREADS, 0, rows_b, it_b, nb, r2i, col, dp, val, d_dia, d_vec, bar);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
+}
+
+// which sweep runs: option "ilu_sweep_mode" 1 = grid barrier, 2 = one cluster, 0 = grid barrier (the cluster measured slower at
+// every size: 16 SMs' load pipes carry ~100 rows each per level); "ilu_sweep_threads" 128 / 512 per CTA, 0 = by the mean level
+// width (narrow levels are latency-bound and every resident warp costs issue slots per level; wide levels want the warps)
+template <int N>
+static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, uint64_t n_rows, const double *d_dia, double *d_vec) {
+  const bool cluster = c->ilu_sweep_mode == 2;
+  int threads = (int)c->ilu_sweep_threads;
+  if (threads != 128 && threads != 512) {
+    const uint64_t nlev = s->lev_f.size() > 1 ? s->lev_f.size() - 1 : 1;
+    const uint64_t lanes = n_rows / nlev * IluLanes<N>::LPR;   // lanes a mean level keeps busy
+    threads = (!cluster && lanes <= (uint64_t)c->sm_count * 128) ? 128 : 512;
+  }
+  if (threads == 128) return ilu_sweeps_launch<N, 128>(c, s, d_dia, d_vec, cluster);
+  return ilu_sweeps_launch<N, 512>(c, s, d_dia, d_vec, cluster);
 }
 
 dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec) {
   if (c->ilu_level_launches == 0) {
     switch (N) {
-      case 1: return ilu_sweeps_barrier<1>(c, s, d_dia, d_vec);
-      case 2: return ilu_sweeps_barrier<2>(c, s, d_dia, d_vec);
-      case 3: return ilu_sweeps_barrier<3>(c, s, d_dia, d_vec);
-      case 4: return ilu_sweeps_barrier<4>(c, s, d_dia, d_vec);
+      case 1: return ilu_sweeps<1>(c, s, pat->num_blk, d_dia, d_vec);
+      case 2: return ilu_sweeps<2>(c, s, pat->num_blk, d_dia, d_vec);
+      case 3: return ilu_sweeps<3>(c, s, pat->num_blk, d_dia, d_vec);
+      case 4: return ilu_sweeps<4>(c, s, pat->num_blk, d_dia, d_vec);
     }
   }
   // one launch per level (option "ilu_level_launches" = 1): the reference point the sweeps are checked against

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, out_dir, variant, use_peer):
+def _worker(rank, world, port, shape, out_dir, variant, use_peer, tile_rows=0):
     # use_peer: 0 = NCCL all-reduce + NCCL halo, 1 = peer mailbox all-reduce + NCCL halo, 2 = peer mailbox + peer halo push
     import sys
     sys.path.insert(0, ROOT)
@@ -42,6 +42,8 @@ def _worker(rank, world, port, shape, out_dir, variant, use_peer):
         ctx.peer_import(handles)
     ctx.set_option("spmv_variant", variant)
     ctx.set_option("use_peer_halo", 1 if use_peer == 2 else 0)
+    if tile_rows:
+        ctx.set_option("spmv_tile_rows", tile_rows)
     nx, ny, nz = shape
     prob = Problem(dfb, ctx, nx, ny, nz, rank, world, "jacobi")
     asm_ms, tot_ms, iters = prob.step(max_it=5000)
@@ -62,13 +64,24 @@ def _worker(rank, world, port, shape, out_dir, variant, use_peer):
 @pytest.mark.parametrize("world,shape", [(2, (9, 8, 20)), (4, (9, 8, 23))])
 def test_multi_gpu_pcg_equals_single_gpu(tmp_path, dfb, world, shape, variant, use_peer):
     """world = 4 has middle ranks with two neighbours (both landing ranges, two flags to wait for)"""
+    _run_multi_gpu_pcg(tmp_path, dfb, world, shape, variant, use_peer, 0)
+
+
+@pytest.mark.parametrize("use_peer", [0, 2])
+def test_multi_gpu_pcg_16_row_tiles(tmp_path, dfb, use_peer):
+    """the packed records of sparse-row matrices use 16-row tiles (2 lanes per row); forced here on the tet matrix so that the
+    halo instantiation of that tile height (staged tiles at the mesh boundary, direct-path tiles inside) is covered too"""
+    _run_multi_gpu_pcg(tmp_path, dfb, 2, (9, 8, 20), 20, use_peer, 16)
+
+
+def _run_multi_gpu_pcg(tmp_path, dfb, world, shape, variant, use_peer, tile_rows):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     if world > 2 and variant != 20:
         pytest.skip("the 4-GPU case only runs the default SpMV variant")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path), variant, use_peer), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, str(tmp_path), variant, use_peer, tile_rows), nprocs=world, join=True)
     from del_fem_b200.workload import Problem
     ctx = dfb.Ctx(0)
     ctx.set_option("spmv_variant", variant)

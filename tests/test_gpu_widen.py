@@ -455,16 +455,19 @@ def test_ilu0_matches_oracle(dfb, ctx, orc, case):
     vd = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vd, pc)
     assert rel_err(vd.download(), want) < 1e-13
-    # the persistent sweeps (default: one launch per sweep, grid barrier per level) and the level-per-launch sweeps give the same bits
+    # the persistent sweeps (one launch per sweep: grid barrier per level, or one thread-block cluster with N lanes per row) and
+    # the level-per-launch sweeps give the same bits
     ctx.set_option("ilu_level_launches", 1)
     vl = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vl, pc)
     ctx.set_option("ilu_level_launches", 0)
     assert np.array_equal(vl.download(), vd.download())
-    for _ in range(3):  # repeated applications reuse the barrier counter
-        vr = dfb.Vec.from_numpy(ctx, v)
-        sparse_ilu.solve_preconditioning_vec(vr, pc)
-        assert np.array_equal(vr.download(), vd.download())
+    for mode in (1, 2, 0):
+        ctx.set_option("ilu_sweep_mode", mode)
+        for _ in range(3):  # repeated applications reuse the barrier counter
+            vr = dfb.Vec.from_numpy(ctx, v)
+            sparse_ilu.solve_preconditioning_vec(vr, pc)
+            assert np.array_equal(vr.download(), vl.download()), mode
     ro = rhs_h.copy()
     xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
     hist_o = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, tol, max_it, r2i, i2c, iv, rv, ilu_o)
