@@ -29,11 +29,16 @@ struct DfbIlu {
   std::vector<uint32_t> lev_f, lev_b;  // level pointers into d_rows_f / d_rows_b (host)
   double *d_val = nullptr;        // factor values [nnz*NN]
   double *d_z = nullptr;          // explicit preconditioned residual for PCG [n*N]
-  uint32_t *d_epoch = nullptr;    // [8] grid-barrier counters of the persistent sweeps at [4..7]
-  struct Items {                  // work items of a persistent sweep for one launch shape (ilu_items)
-    uint2 *d = nullptr;
-    uint32_t n = 0, pass = 0;
-  } items_f, items_b;
+  uint32_t *d_epoch = nullptr;    // [8] grid-barrier counter of the persistent sweeps at [4]
+  struct Sweep {                  // persistent sweep of one direction
+    std::vector<uint32_t> lev_rec;   // records of level l: [lev_rec[l], lev_rec[l+1])
+    uint2 *d_groups = nullptr;       // per record {first position in the level-ordered row list, rows}
+    uint32_t n_rec = 0;
+    unsigned char *d_rec = nullptr;  // sweep-ordered factor copy (IluRec), rebuilt by every update
+    uint64_t rec_bytes = 0;
+    uint2 *d_items = nullptr;        // work items for one launch shape (ilu_items)
+    uint32_t n_items = 0, pass = 0;
+  } fwd, bwd;
 };
 
 template <int N>
@@ -212,45 +217,101 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
   }
 }
 
-// ---- level sweeps inside ONE persistent launch (default; S10: 2 launches per application instead of 448 + 448), two flavours of
-// the same kernel:
-//   CLUSTER = false  one CTA per SM, a grid-wide barrier between levels (one atomic per CTA on one of four counters + one
-//                    polling thread per CTA)
-//   CLUSTER = true   ONE thread-block cluster (16 CTAs), the hardware cluster barrier (barrier.cluster, release/acquire at cluster
-//                    scope) between levels
+// ---- level sweeps inside ONE persistent launch (default; S10: 2 launches per application instead of 448 + 448).
+// Sweep-ordered factor copy: after every decompose the rows' strictly-lower (forward) / strictly-upper (backward) entries are
+// re-laid in the order the sweep visits them, in records of RPW rows (= the rows one warp handles at a time, cut at level
+// boundaries):   [ uint4 {row, entries here, first / end of the entries beyond KS in the canonical arrays} x RPW
+//                | columns [KS][RPW] | blocks [KS][N][RPW*N] (component a of row r at r*N + a) | D^-1 [N][RPW*N] (forward) ]
+// so that every load of a warp is contiguous (the canonical row-major blocks cost 8 memory wavefronts per load instruction
+// — one per row — and the sweeps were bound by exactly that: 330 + 200 wavefronts per warp and level, ncu + in-kernel clocks).
 // A block-row is shared by N lanes — lane a carries component a of t = v_i - sum_j L_ij v_j through the reference's loop
-// (sparse_ilu.rs:183-219: ascending entries, mult_vec's left fold over the block's columns), the D^-1 product takes the other
-// lanes' t by shuffle — so every rounding is the one of the one-thread-per-row kernels above (bit-identical, tested).
-// The work items (one pass of the whole grid over part of a level; built on the host for the launch shape, staged in shared
-// memory) are software-pipelined FOUR deep so that no load issued in an iteration is consumed in the same iteration (a warp
-// issues in order: a dependent chain row id -> row pointers -> columns inside one iteration would stall the row arithmetic):
-//   item k+3: row id      item k+2: row pointers      item k+1: columns (registers) + factor blocks (L2 prefetch)      item k: the row
-// After a barrier only the neighbours' values (L2) and the prefetched blocks are read. THREADS is chosen by the mean level
-// width: narrow levels are latency-bound and every resident warp costs issue slots per level, wide levels want the warps.
+// (sparse_ilu.rs:183-219: ascending entries, mult_vec's left fold over the block's columns), the neighbours' values and the
+// D^-1 product move between the lanes by shuffle — so every rounding is the one of the one-thread-per-row kernels above
+// (bit-identical, tested).  Two flavours of the same kernel:
+//   CLUSTER = false  one CTA per SM, a grid-wide barrier between levels (one atomic per CTA + one polling thread per CTA)
+//   CLUSTER = true   ONE thread-block cluster (16 CTAs), the hardware cluster barrier between levels
+// Work items (one pass of the grid over part of a level; built on the host for the launch shape, staged in shared memory) are
+// software-pipelined: the record of item k+1 is loaded into registers (THREADS = 128: narrow, latency-bound levels) or
+// prefetched to L2 (THREADS = 512: wide levels) while item k is computed, so that behind a barrier only the neighbours' values
+// are a dependent read.
 // A sync-free variant (per-row epoch flags polled by the dependent rows, Liu et al.) was built and measured SLOWER (11-13 ms per
 // iteration at S1 for every window size / back-off tried: 0.78 G L2 requests of polling per sweep) and removed.
-static const int ILU_BAR_WAYS = 4;   // arrival counters of the grid barrier (CTA b arrives on counter b % 4)
+template <int N> struct IluLanes {   // lanes per row (N = 3: the 4th lane of a quad idles) and rows per warp
+  static constexpr int LPR = (N == 3) ? 4 : N, RPW = 32 / LPR;
+};
+static const int ILU_KS = 8;                   // entries per row held in the sweep-ordered records
+static const uint32_t ILU_NONE = 0xFFFFFFFFu;
+template <int N, bool FORWARD> struct IluRec {
+  static constexpr int RPW = IluLanes<N>::RPW, RN = RPW * N;
+  static constexpr int OFF_COL = RPW * 16;
+  static constexpr int OFF_W = OFF_COL + ILU_KS * RPW * 4;
+  static constexpr int OFF_DIA = OFF_W + ILU_KS * N * RN * 8;
+  static constexpr int BYTES = (OFF_DIA + (FORWARD ? N * RN * 8 : 0) + 127) / 128 * 128;
+};
+static uint64_t ilu_rec_bytes(int N, bool forward) {
+  switch (N) {
+    case 1: return forward ? IluRec<1, true>::BYTES : IluRec<1, false>::BYTES;
+    case 2: return forward ? IluRec<2, true>::BYTES : IluRec<2, false>::BYTES;
+    case 3: return forward ? IluRec<3, true>::BYTES : IluRec<3, false>::BYTES;
+    default: return forward ? IluRec<4, true>::BYTES : IluRec<4, false>::BYTES;
+  }
+}
+
+// one warp per record: gathers the rows' entries from the canonical factor arrays
+template <int N, bool FORWARD>
+__global__ void __launch_bounds__(256) k_ilu_slice(const uint2 *__restrict__ groups, uint32_t n_groups, const uint32_t *__restrict__ rows,
+                                                   const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ diap,
+                                                   const uint32_t *__restrict__ col, const double *__restrict__ val,
+                                                   const double *__restrict__ dia, unsigned char *__restrict__ rec) {
+  using R = IluRec<N, FORWARD>;
+  constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = R::RPW, RN = R::RN, KS = ILU_KS;
+  const unsigned lane = threadIdx.x & 31u, sub = lane % LPR, r = lane / LPR;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t g = warp; g < n_groups; g += n_warps) {
+    const uint2 gr = groups[g];   // {first position in the level-ordered row list, rows}
+    unsigned char *p = rec + (uint64_t)g * R::BYTES;
+    const bool live = r < gr.y;
+    const uint32_t i = live ? rows[gr.x + r] : ILU_NONE;
+    uint32_t kb = 0, ke = 0;
+    if (live) {
+      kb = FORWARD ? r2i[i] : diap[i];
+      ke = FORWARD ? diap[i] : r2i[i + 1];
+    }
+    const uint32_t cnt = min(ke - kb, (uint32_t)KS);
+    if (sub == 0) reinterpret_cast<uint4 *>(p)[r] = make_uint4(i, cnt, kb + cnt, ke);
+    uint32_t *pc = reinterpret_cast<uint32_t *>(p + R::OFF_COL);
+    for (uint32_t k = sub; k < (uint32_t)KS; k += LPR) pc[k * RPW + r] = k < cnt ? col[kb + k] : 0u;
+    if (sub < (unsigned)N) {
+      double *pw = reinterpret_cast<double *>(p + R::OFF_W);
+      for (uint32_t k = 0; k < (uint32_t)KS; ++k)
+#pragma unroll
+        for (int d = 0; d < N; ++d) pw[(k * N + d) * RN + r * N + sub] = k < cnt ? val[(uint64_t)(kb + k) * NN + sub + N * d] : 0.0;
+      if (FORWARD) {
+        double *pd = reinterpret_cast<double *>(p + R::OFF_DIA);
+#pragma unroll
+        for (int d = 0; d < N; ++d) pd[d * RN + r * N + sub] = live ? dia[(uint64_t)i * NN + sub + N * d] : 0.0;
+      }
+    }
+  }
+}
+
+// grid barrier: arrival = red.release (the CTA's stores, ordered before it by bar.sync, are performed first), one polling thread
+// per CTA with ld.acquire. tools/micro/gridbar.cu (profiles/r2_gridbar.txt): 1.52 us per barrier incl. one dependent store/load
+// pair on 148 CTAs; fence + atomicAdd + relaxed poll + fence 1.87, a flag per CTA polled by a warp 3.0-3.9, grid.sync() 1.47;
+// spreading the arrivals over several counters changes nothing.
 __device__ __forceinline__ void ilu_grid_barrier(unsigned int *ctr, unsigned int epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();   // the CTA's stores (ordered before by the barrier above) are performed before the arrival
-    atomicAdd(ctr + (blockIdx.x % ILU_BAR_WAYS), 1u);
-    // counter w receives one arrival per epoch from each CTA with id % 4 == w
-    unsigned int want[ILU_BAR_WAYS];
-#pragma unroll
-    for (int w = 0; w < ILU_BAR_WAYS; ++w) want[w] = epoch * ((gridDim.x + ILU_BAR_WAYS - 1 - w) / ILU_BAR_WAYS);
-    for (;;) {
-      unsigned int v0, v1, v2, v3;
-      asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "l"(ctr) : "memory");
-      if (v0 >= want[0] && v1 >= want[1] && v2 >= want[2] && v3 >= want[3]) break;
-    }
-    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    const unsigned int want = epoch * gridDim.x;
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < want);
   }
   __syncthreads();
 }
-__global__ void k_ilu_barrier_reset(unsigned int *ctr) {
-  if (threadIdx.x < ILU_BAR_WAYS) ctr[threadIdx.x] = 0u;
-}
+__global__ void k_ilu_barrier_reset(unsigned int *ctr) { *ctr = 0u; }
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
   unsigned r;
@@ -266,131 +327,129 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int N> struct IluLanes { static constexpr int LPR = (N == 3) ? 4 : N; };   // lanes per row (N = 3: the 4th lane of a quad idles)
-static const int ILU_ITEM_SMEM = 4096;          // work items staged in shared memory (longer lists: read from global)
-static const uint32_t ILU_ITEM_BARRIER = 0x80000000u;   // flag in an item's end: a level boundary precedes the item
+static const int ILU_ITEM_SMEM = 4096;                  // work items staged in shared memory (longer lists: read from global)
+static const uint32_t ILU_ITEM_BARRIER = 0x80000000u;   // flag in an item's record count: a level boundary precedes the item
 
 template <int N, bool FORWARD, bool CLUSTER, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_ilu_sweep(const uint32_t *__restrict__ rows, const uint2 *__restrict__ items, uint32_t n_items,
-                                                       const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ col,
-                                                       const uint32_t *__restrict__ diap, const double *__restrict__ val,
-                                                       const double *__restrict__ dia, double *vec, unsigned int *bar) {
-  constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = 32 / LPR, KPRE = 8;
-  constexpr int B = THREADS <= 128 ? 8 : 4;   // entries whose loads are issued together before their arithmetic (registers)
+__global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__restrict__ rec, const uint2 *__restrict__ items, uint32_t n_items,
+                                                       const uint32_t *__restrict__ col, const double *__restrict__ val, double *vec,
+                                                       unsigned int *bar) {
+  using R = IluRec<N, FORWARD>;
+  constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = R::RPW, RN = R::RN, KS = ILU_KS;
+  constexpr bool WPRE = THREADS <= 128 && N <= 3;   // registers to spare: the next record's blocks are loaded one item ahead
+  constexpr int B = WPRE ? KS : 4;                  // entries whose loads are issued together before their arithmetic
   __shared__ uint2 s_item[ILU_ITEM_SMEM];
   const unsigned n_cta = CLUSTER ? cluster_nctarank() : gridDim.x, cta = CLUSTER ? cluster_ctarank() : blockIdx.x;
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  const unsigned sub = lane % LPR, base = lane - sub;
+  const unsigned sub = lane % LPR, base = lane - sub, r = lane / LPR;
   const bool act = sub < (unsigned)N;
-  const unsigned a_ = act ? sub : 0u;                            // component of the row this lane carries
-  const uint32_t slot = (wid * n_cta + cta) * RPW + lane / LPR;  // consecutive row groups of a level go to different CTAs
+  const unsigned a_ = act ? sub : 0u;           // component of the row this lane carries
+  const uint32_t wslot = wid * n_cta + cta;     // consecutive records of a level go to different CTAs
   const bool in_smem = n_items <= (uint32_t)ILU_ITEM_SMEM;
   if (in_smem)
     for (uint32_t k = threadIdx.x; k < n_items; k += THREADS) s_item[k] = items[k];
   __syncthreads();
-  const uint32_t NONE = 0xFFFFFFFFu;
-  // item k: rows [x, y & ~flag) of the level-ordered row list, of which this lane group takes x + slot
-  auto item = [&](uint32_t k) -> uint2 {
+  auto item = [&](uint32_t k) -> uint2 {   // {first record, records | barrier flag}
     if (k >= n_items) return make_uint2(0u, 0u);
     return in_smem ? s_item[k] : items[k];
   };
-  // the three load stages (each consumes only what an EARLIER iteration loaded)
-  auto load_row_id = [&](uint32_t k) -> uint32_t {
+  auto record = [&](uint32_t k) -> const unsigned char * {   // this warp's record of item k (warp-uniform), or null
     const uint2 it = item(k);
-    const uint32_t q = it.x + slot;
-    return q < (it.y & ~ILU_ITEM_BARRIER) ? rows[q] : NONE;
+    return wslot < (it.y & ~ILU_ITEM_BARRIER) ? rec + (uint64_t)(it.x + wslot) * R::BYTES : nullptr;
   };
-  auto load_row_ptrs = [&](uint32_t i, uint32_t &kb, uint32_t &ke) {
-    kb = ke = 0;
-    if (i != NONE) {
-      kb = FORWARD ? r2i[i] : diap[i];
-      ke = FORWARD ? diap[i] : r2i[i + 1];
-    }
+  struct Stage {
+    const unsigned char *p;
+    uint4 h;
+    uint32_t cols[KS];
+    double w[WPRE ? KS : 1][N], dw[N];
   };
-  auto load_cols = [&](uint32_t i, uint32_t kb, uint32_t ke, uint32_t (&cols)[KPRE]) {
+  auto stage = [&](const unsigned char *p, Stage &s) {
+    s.p = p;
+    if (!p) return;
+    s.h = reinterpret_cast<const uint4 *>(p)[r];
+    const uint32_t *pc = reinterpret_cast<const uint32_t *>(p + R::OFF_COL);
 #pragma unroll
-    for (int k = 0; k < KPRE; ++k) cols[k] = (kb + k < ke) ? col[kb + k] : 0u;
-    if (i != NONE) {   // the lanes of a row split the row's 128-byte lines between them
-      const char *pb = reinterpret_cast<const char *>(val + (uint64_t)kb * NN), *pe = reinterpret_cast<const char *>(val + (uint64_t)ke * NN);
-      for (const char *c = pb + 128 * sub; c < pe; c += 128 * LPR) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
-      if (FORWARD && sub == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(dia + (uint64_t)i * NN));
+    for (int k = 0; k < KS; ++k) s.cols[k] = pc[k * RPW + r];
+    if (WPRE) {
+      const double *pw = reinterpret_cast<const double *>(p + R::OFF_W);
+#pragma unroll
+      for (int k = 0; k < KS; ++k)
+#pragma unroll
+        for (int d = 0; d < N; ++d) s.w[WPRE ? k : 0][d] = pw[(k * N + d) * RN + r * N + a_];
+      if (FORWARD) {
+        const double *pd = reinterpret_cast<const double *>(p + R::OFF_DIA);
+#pragma unroll
+        for (int d = 0; d < N; ++d) s.dw[d] = pd[d * RN + r * N + a_];
+      }
     }
   };
-  // the row itself; executed by whole warps (shuffles): rows beyond the level (i = NONE) only take part in those
-  auto do_row = [&](uint32_t ri, uint32_t kb, uint32_t ke, const uint32_t (&cols)[KPRE]) {
-    const bool live = ri != NONE;
-    const uint32_t i = live ? ri : 0u;
+  auto prefetch_record = [&](const unsigned char *p) {
+    if (!p) return;
+    for (int off = lane * 128; off < R::BYTES; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+  };
+  // the rows of one record; executed by whole warps (shuffles)
+  auto do_rows = [&](const Stage &s) {
+    const bool live = s.h.x != ILU_NONE;
+    const uint32_t i = live ? s.h.x : 0u, cnt = s.h.y;
     double t = live ? __ldcg(vec + (uint64_t)i * N + a_) : 0.0;
+    const double *pw = reinterpret_cast<const double *>(s.p + R::OFF_W);
     double dw[N];
     if (FORWARD) {
+      const double *pd = reinterpret_cast<const double *>(s.p + R::OFF_DIA);
 #pragma unroll
-      for (int d = 0; d < N; ++d) dw[d] = live ? dia[(uint64_t)i * NN + a_ + N * d] : 0.0;
+      for (int d = 0; d < N; ++d) dw[d] = WPRE ? s.dw[d] : pd[d * RN + r * N + a_];
     }
 #pragma unroll
-    for (int k0 = 0; k0 < KPRE; k0 += B) {
-      double x[B][N], w[B][N];
+    for (int k0 = 0; k0 < KS; k0 += B) {
+      double xv[B], w[B][N];
 #pragma unroll
       for (int k = 0; k < B; ++k) {
-        const bool on = kb + k0 + k < ke;
+        // lane a reads component a of the neighbour (written by other SMs in earlier levels: L2); the row's lanes exchange below
+        xv[k] = ((uint32_t)(k0 + k) < cnt && act) ? __ldcg(vec + (uint64_t)s.cols[k0 + k] * N + a_) : 0.0;
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-          x[k][d] = on ? __ldcg(vec + (uint64_t)cols[k0 + k] * N + d) : 0.0;   // written by other SMs in earlier levels: L2
-          w[k][d] = on ? val[(uint64_t)(kb + k0 + k) * NN + a_ + N * d] : 0.0;
-        }
+        for (int d = 0; d < N; ++d) w[k][d] = WPRE ? s.w[WPRE ? k0 + k : 0][d] : pw[((k0 + k) * N + d) * RN + r * N + a_];
       }
 #pragma unroll
       for (int k = 0; k < B; ++k) {
-        if (kb + k0 + k < ke) {
-          double s = 0.0;
+        double acc = 0.0;
 #pragma unroll
-          for (int d = 0; d < N; ++d) s = s + w[k][d] * x[k][d];
-          t -= s;
-        }
+        for (int d = 0; d < N; ++d) acc = acc + w[k][d] * __shfl_sync(0xFFFFFFFFu, xv[k], base + d);
+        if ((uint32_t)(k0 + k) < cnt) t -= acc;
       }
     }
-    for (uint32_t k = kb + KPRE; k < ke; ++k) {   // rows longer than the pipelined columns (ILU(k) fill)
+    for (uint32_t k = s.h.z; k < s.h.w; ++k) {   // rows longer than the record (ILU(k) fill): the canonical arrays
       const uint32_t c = col[k];
-      double s = 0.0;
+      double acc = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) s = s + val[(uint64_t)k * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
-      t -= s;
+      for (int d = 0; d < N; ++d) acc = acc + val[(uint64_t)k * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
+      t -= acc;
     }
+    __syncwarp();
     if (FORWARD) {
-      double s = 0.0;
+      double acc = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) s = s + dw[d] * __shfl_sync(0xFFFFFFFFu, t, base + d);
-      t = s;
+      for (int d = 0; d < N; ++d) acc = acc + dw[d] * __shfl_sync(0xFFFFFFFFu, t, base + d);
+      t = acc;
     }
     if (live && act) vec[(uint64_t)i * N + a_] = t;
   };
 
   if (n_items == 0) return;
-  // prologue: fill the pipeline (the only place where the dependent chain is waited for)
-  uint32_t i0 = load_row_id(0), i1 = load_row_id(1), i2 = load_row_id(2);
-  uint32_t kb0, ke0, kb1, ke1;
-  load_row_ptrs(i0, kb0, ke0);
-  load_row_ptrs(i1, kb1, ke1);
-  uint32_t cols0[KPRE];
-  load_cols(i0, kb0, ke0, cols0);
-  uint32_t n_bar = 0;
+  Stage cur;
+  stage(record(0), cur);
+  if (!WPRE) prefetch_record(record(1));
+  unsigned int n_bar = 0;
   for (uint32_t k = 0;; ++k) {
-    // stage loads for the items ahead (addresses come from registers filled in earlier iterations)
-    const uint32_t i3 = load_row_id(k + 3);
-    uint32_t kb2, ke2;
-    load_row_ptrs(i2, kb2, ke2);
-    uint32_t cols1[KPRE];
-    load_cols(i1, kb1, ke1, cols1);
-    do_row(i0, kb0, ke0, cols0);
+    Stage nxt;
+    stage(record(k + 1), nxt);
+    if (!WPRE) prefetch_record(record(k + 2));
+    if (cur.p) do_rows(cur);
     if (k + 1 >= n_items) break;
     if (item(k + 1).y & ILU_ITEM_BARRIER) {
       if (CLUSTER) cluster_barrier();
       else ilu_grid_barrier(bar, ++n_bar);
     }
-    i0 = i1; kb0 = kb1; ke0 = ke1;
-#pragma unroll
-    for (int q = 0; q < KPRE; ++q) cols0[q] = cols1[q];
-    i1 = i2; kb1 = kb2; ke1 = ke2;
-    i2 = i3;
+    cur = nxt;
   }
 }
 
@@ -415,8 +474,11 @@ void dfb_ilu_destroy(DfbIlu *s) {
   dfb_dev_free(s->d_val);
   dfb_dev_free(s->d_z);
   dfb_dev_free(s->d_epoch);
-  dfb_dev_free(s->items_f.d);
-  dfb_dev_free(s->items_b.d);
+  for (DfbIlu::Sweep *w : {&s->fwd, &s->bwd}) {
+    dfb_dev_free(w->d_groups);
+    dfb_dev_free(w->d_rec);
+    dfb_dev_free(w->d_items);
+  }
   delete s;
 }
 
@@ -547,6 +609,27 @@ dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIl
   up(&s->d_dia, dia);
   up(&s->d_rows_f, rows_f);
   up(&s->d_rows_b, rows_b);
+  // records of the sweep-ordered factor copy: RPW consecutive rows of a level
+  auto records = [&](const std::vector<uint32_t> &lev, bool forward, DfbIlu::Sweep &w) {
+    if (st != DFB_OK) return;
+    const uint32_t rpw = N == 1 ? 32u : N == 2 ? 16u : 8u;
+    std::vector<uint2> g;
+    w.lev_rec.assign(1, 0u);
+    for (size_t l = 0; l + 1 < lev.size(); ++l) {
+      for (uint32_t q = lev[l]; q < lev[l + 1]; q += rpw) g.push_back(make_uint2(q, std::min(rpw, lev[l + 1] - q)));
+      w.lev_rec.push_back((uint32_t)g.size());
+    }
+    w.n_rec = (uint32_t)g.size();
+    w.rec_bytes = (uint64_t)g.size() * ilu_rec_bytes(N, forward);
+    st = dfb_dev_alloc_t(&w.d_groups, g.size() + 1);
+    if (st == DFB_OK && !g.empty()) {
+      cudaError_t e = cudaMemcpy(w.d_groups, g.data(), g.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu: %s", cudaGetErrorString(e));
+    }
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&w.d_rec, w.rec_bytes + 128);
+  };
+  records(s->lev_f, true, s->fwd);
+  records(s->lev_b, false, s->bwd);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_epoch, 8);
   if (st == DFB_OK) cudaMemsetAsync(s->d_epoch, 0, 8 * sizeof(uint32_t), c->stream);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_val, nnz * NN + 8);
@@ -564,6 +647,8 @@ static int level_grid(uint32_t count) {
   int g = (int)((count + 127) / 128);
   return g < 1 ? 1 : (g > 1184 ? 1184 : g);
 }
+
+static dfb_status dfb_ilu_reslice(dfb_ctx *c, DfbIlu *s, int N, const double *d_dia);
 
 // copy_value + decompose
 dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia_out) {
@@ -587,39 +672,61 @@ dfb_status dfb_ilu_update(dfb_ctx *c, DfbIlu *s, const dfb_bsr *m, double *d_dia
 #undef DEC
   }
   DFB_CHECK_LAUNCH();
-  return dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "ilu0 decompose: singular pivot block (try_inverse().unwrap())");
+  DFB_TRY(dfb_check_error_flag(c, 2, DFB_ERR_SINGULAR_DIAG, "ilu0 decompose: singular pivot block (try_inverse().unwrap())"));
+  return dfb_ilu_reslice(c, s, N, d_dia_out);
 }
 
-// work items of a sweep for a launch shape: every non-empty level is cut into passes of `pass` rows; the first pass of every
-// level but the first carries the barrier flag. Cached per direction until the shape changes.
+// work items of a sweep for a launch shape: the records of every non-empty level are cut into passes of `pass` records (one per
+// warp of the grid); the first pass of every level but the first carries the barrier flag. Cached per direction.
 static dfb_status ilu_items(dfb_ctx *c, const DfbIlu *cs, bool forward, uint32_t pass, const uint2 **d_items, uint32_t *n_items) {
   DfbIlu *s = const_cast<DfbIlu *>(cs);
-  DfbIlu::Items &I = forward ? s->items_f : s->items_b;
-  if (I.pass != pass || !I.d) {
+  DfbIlu::Sweep &W = forward ? s->fwd : s->bwd;
+  if (W.pass != pass || !W.d_items) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     DFB_CUDA(cudaStreamIsCapturing(c->stream, &cap));
     if (cap != cudaStreamCaptureStatusNone) return dfb_fail(DFB_ERR_BAD_ARG, "ilu: the sweep shape changed inside a stream capture");
-    const std::vector<uint32_t> &lev = forward ? s->lev_f : s->lev_b;
     std::vector<uint2> h;
     bool first = true;
-    for (size_t l = 0; l + 1 < lev.size(); ++l) {
-      const uint32_t a = lev[l], b = lev[l + 1];
-      for (uint32_t q = a; q < b; q += pass) {
-        h.push_back(make_uint2(q, b | ((q == a && !first) ? ILU_ITEM_BARRIER : 0u)));
+    for (size_t l = 0; l + 1 < W.lev_rec.size(); ++l) {
+      const uint32_t a = W.lev_rec[l], b = W.lev_rec[l + 1];
+      for (uint32_t g = a; g < b; g += pass) {
+        h.push_back(make_uint2(g, std::min(pass, b - g) | ((g == a && !first) ? ILU_ITEM_BARRIER : 0u)));
         first = false;
       }
     }
     DFB_CUDA(cudaStreamSynchronize(c->stream));   // a sweep with the old list may be in flight
-    dfb_dev_free(I.d);
-    I.d = nullptr;
-    DFB_TRY(dfb_dev_alloc_t(&I.d, h.size() + 1));
-    if (!h.empty()) DFB_CUDA(cudaMemcpy(I.d, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    I.n = (uint32_t)h.size();
-    I.pass = pass;
+    dfb_dev_free(W.d_items);
+    W.d_items = nullptr;
+    DFB_TRY(dfb_dev_alloc_t(&W.d_items, h.size() + 1));
+    if (!h.empty()) DFB_CUDA(cudaMemcpy(W.d_items, h.data(), h.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    W.n_items = (uint32_t)h.size();
+    W.pass = pass;
   }
-  *d_items = I.d;
-  *n_items = I.n;
+  *d_items = W.d_items;
+  *n_items = W.n_items;
   return DFB_OK;
+}
+
+// the sweep-ordered records of both directions from the canonical factor (after decompose)
+template <int N>
+static dfb_status ilu_slice(dfb_ctx *c, DfbIlu *s, const double *d_dia) {
+  const int g = c->sm_count * 8;
+  if (s->fwd.n_rec)
+    DFB_LAUNCH(c, (k_ilu_slice<N, true>), g, 256, 0, s->fwd.d_groups, s->fwd.n_rec, s->d_rows_f, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->fwd.d_rec);
+  if (s->bwd.n_rec)
+    DFB_LAUNCH(c, (k_ilu_slice<N, false>), g, 256, 0, s->bwd.d_groups, s->bwd.n_rec, s->d_rows_b, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->bwd.d_rec);
+  DFB_CHECK_LAUNCH();
+  return DFB_OK;
+}
+
+static dfb_status dfb_ilu_reslice(dfb_ctx *c, DfbIlu *s, int N, const double *d_dia) {
+  switch (N) {
+    case 1: return ilu_slice<1>(c, s, d_dia);
+    case 2: return ilu_slice<2>(c, s, d_dia);
+    case 3: return ilu_slice<3>(c, s, d_dia);
+    case 4: return ilu_slice<4>(c, s, d_dia);
+  }
+  return dfb_fail(DFB_ERR_UNSUPPORTED, "ilu: blk_dim %d", N);
 }
 
 static void ilu_cluster_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *at, int cs, int threads, cudaStream_t strm) {
@@ -662,8 +769,7 @@ static int ilu_cluster_size(dfb_ctx *c) {
 
 // solve_preconditioning_vec, in place: forward then backward sweep, one launch each
 template <int N, int THREADS>
-static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, const double *d_dia, double *d_vec, bool cluster) {
-  constexpr int RPW = 32 / IluLanes<N>::LPR;
+static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, double *d_vec, bool cluster) {
   int n_cta = c->sm_count;   // grid barrier: one resident CTA per SM (<= 512 threads, 32 KB of shared memory: always co-resident)
   if (cluster) {
     n_cta = ilu_cluster_size<N, THREADS>(c);
@@ -672,12 +778,13 @@ static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, const double *d
       n_cta = c->sm_count;
     }
   }
-  const uint32_t pass = (uint32_t)n_cta * (THREADS / 32) * RPW;
+  const uint32_t pass = (uint32_t)n_cta * (THREADS / 32);
   const uint2 *it_f = nullptr, *it_b = nullptr;
   uint32_t nf = 0, nb = 0;
   DFB_TRY(ilu_items(c, s, true, pass, &it_f, &nf));
   DFB_TRY(ilu_items(c, s, false, pass, &it_b, &nb));
-  const uint32_t *rows_f = s->d_rows_f, *rows_b = s->d_rows_b, *r2i = s->d_r2i, *col = s->d_col, *dp = s->d_dia;
+  const unsigned char *rec_f = s->fwd.d_rec, *rec_b = s->bwd.d_rec;
+  const uint32_t *col = s->d_col;
   const double *val = s->d_val;
   unsigned int *bar = s->d_epoch + 4;
   if (cluster) {
@@ -685,28 +792,28 @@ static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, const double *d
     cudaLaunchAttribute at[1];
     ilu_cluster_config(&cfg, at, n_cta, THREADS, c->stream);
     if (nf) {
-      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, true, true, THREADS>, rows_f, it_f, nf, r2i, col, dp, val, d_dia, d_vec, bar));
+      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, true, true, THREADS>, rec_f, it_f, nf, col, val, d_vec, bar));
       c->launches += 1;
     }
     if (nb) {
-      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, false, true, THREADS>, rows_b, it_b, nb, r2i, col, dp, val, d_dia, d_vec, bar));
+      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, false, true, THREADS>, rec_b, it_b, nb, col, val, d_vec, bar));
       c->launches += 1;
     }
     return DFB_OK;
   }
-  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 32, 0, bar);
-  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, false, THREADS>), n_cta, THREADS, 0, rows_f, it_f, nf, r2i, col, dp, val, d_dia, d_vec, bar);
-  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 32, 0, bar);
-  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, false, THREADS>), n_cta, THREADS, 0, rows_b, it_b, nb, r2i, col, dp, val, d_dia, d_vec, bar);
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
+  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, false, THREADS>), n_cta, THREADS, 0, rec_f, it_f, nf, col, val, d_vec, bar);
+  DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
+  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, false, THREADS>), n_cta, THREADS, 0, rec_b, it_b, nb, col, val, d_vec, bar);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
 
-// which sweep runs: option "ilu_sweep_mode" 1 = grid barrier, 2 = one cluster, 0 = grid barrier (the cluster measured slower at
-// every size: 16 SMs' load pipes carry ~100 rows each per level); "ilu_sweep_threads" 128 / 512 per CTA, 0 = by the mean level
-// width (narrow levels are latency-bound and every resident warp costs issue slots per level; wide levels want the warps)
+// which sweep runs: option "ilu_sweep_mode" 2 = one cluster, else the grid barrier; "ilu_sweep_threads" 128 / 512 per CTA,
+// 0 = by the mean level width (narrow levels are latency-bound and every resident warp costs issue slots per level; wide levels
+// want the warps)
 template <int N>
-static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, uint64_t n_rows, const double *d_dia, double *d_vec) {
+static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, uint64_t n_rows, double *d_vec) {
   const bool cluster = c->ilu_sweep_mode == 2;
   int threads = (int)c->ilu_sweep_threads;
   if (threads != 128 && threads != 512) {
@@ -714,17 +821,17 @@ static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, uint64_t n_rows, const
     const uint64_t lanes = n_rows / nlev * IluLanes<N>::LPR;   // lanes a mean level keeps busy
     threads = (!cluster && lanes <= (uint64_t)c->sm_count * 128) ? 128 : 512;
   }
-  if (threads == 128) return ilu_sweeps_launch<N, 128>(c, s, d_dia, d_vec, cluster);
-  return ilu_sweeps_launch<N, 512>(c, s, d_dia, d_vec, cluster);
+  if (threads == 128) return ilu_sweeps_launch<N, 128>(c, s, d_vec, cluster);
+  return ilu_sweeps_launch<N, 512>(c, s, d_vec, cluster);
 }
 
 dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec) {
   if (c->ilu_level_launches == 0) {
     switch (N) {
-      case 1: return ilu_sweeps<1>(c, s, pat->num_blk, d_dia, d_vec);
-      case 2: return ilu_sweeps<2>(c, s, pat->num_blk, d_dia, d_vec);
-      case 3: return ilu_sweeps<3>(c, s, pat->num_blk, d_dia, d_vec);
-      case 4: return ilu_sweeps<4>(c, s, pat->num_blk, d_dia, d_vec);
+      case 1: return ilu_sweeps<1>(c, s, pat->num_blk, d_vec);
+      case 2: return ilu_sweeps<2>(c, s, pat->num_blk, d_vec);
+      case 3: return ilu_sweeps<3>(c, s, pat->num_blk, d_vec);
+      case 4: return ilu_sweeps<4>(c, s, pat->num_blk, d_vec);
     }
   }
   // one launch per level (option "ilu_level_launches" = 1): the reference point the sweeps are checked against
@@ -764,6 +871,9 @@ double *dfb_ilu_z(DfbIlu *s) { return s->d_z; }
 dfb_status dfb_ilu_copy_values(dfb_ctx *c, DfbIlu *dst, const DfbIlu *src, int NN) {
   DFB_REQUIRE(dst && src && dst->nnz == src->nnz, "ilu copy: the two factorisations have different patterns");
   DFB_CUDA(cudaMemcpyAsync(dst->d_val, src->d_val, src->nnz * (uint64_t)NN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  DFB_REQUIRE(dst->fwd.rec_bytes == src->fwd.rec_bytes && dst->bwd.rec_bytes == src->bwd.rec_bytes, "ilu copy: different sweep records");
+  if (src->fwd.rec_bytes) DFB_CUDA(cudaMemcpyAsync(dst->fwd.d_rec, src->fwd.d_rec, src->fwd.rec_bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if (src->bwd.rec_bytes) DFB_CUDA(cudaMemcpyAsync(dst->bwd.d_rec, src->bwd.d_rec, src->bwd.rec_bytes, cudaMemcpyDeviceToDevice, c->stream));
   return DFB_OK;
 }
 
