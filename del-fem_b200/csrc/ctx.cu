@@ -166,9 +166,6 @@ static int64_t *option_slot(dfb_ctx *c, const char *key) {
   if (!strcmp(key, "spmv_tile_rows")) return &c->spmv_tile_rows;
   if (!strcmp(key, "profile_spmv")) return &c->profile_spmv;
   if (!strcmp(key, "ilu_level_launches")) return &c->ilu_level_launches;
-  if (!strcmp(key, "ilu_sweep_mode")) return &c->ilu_sweep_mode;
-  if (!strcmp(key, "ilu_sweep_threads")) return &c->ilu_sweep_threads;
-  if (!strcmp(key, "ilu_cluster_ctas")) return &c->ilu_cluster_ctas;
   if (!strcmp(key, "profile_phases")) return &c->profile_phases;
   if (!strcmp(key, "use_peer_allreduce")) return &c->use_peer_allreduce;
   if (!strcmp(key, "use_peer_halo")) return &c->use_peer_halo;

@@ -127,9 +127,6 @@ struct dfb_ctx {
   int64_t assemble_tile_neo = 0;  // 1: the neo-Hookean tet also takes the fused row-tile path (measured slower than element kernel + gather: 255 registers)
   int64_t spmv_ctas_per_sm = 0;  // 0 = auto
   int64_t spmv_tile_rows = 0;    // block-rows per packed tile: 0 = by row density (8, or 16 for <= 8 blocks per row), else 8 / 16
-  int64_t ilu_cluster_ctas = 16;   // CTAs of the single-cluster ILU sweep (halved until the device can schedule it)
-  int64_t ilu_sweep_mode = 0;      // persistent ILU sweeps: 0 / 1 = grid barrier over one CTA per SM, 2 = one thread-block cluster
-  int64_t ilu_sweep_threads = 0;   // threads per CTA of a persistent sweep: 128 or 512, 0 = by the mean level width
   int64_t ilu_level_launches = 0;  // 1: ILU sweeps as one launch per level (reference point) instead of the dependency-driven sweeps
   int64_t profile_spmv = 0;
   // SpMV profiling (events on the launching stream)

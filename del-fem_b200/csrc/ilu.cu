@@ -217,25 +217,28 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
   }
 }
 
-// ---- level sweeps inside ONE persistent launch (default; S10: 2 launches per application instead of 448 + 448).
+// ---- level sweeps inside ONE persistent launch (S10: 2 launches per application instead of 448 + 448): one CTA per SM, a
+// grid-wide barrier between levels.
 // Sweep-ordered factor copy: after every decompose the rows' strictly-lower (forward) / strictly-upper (backward) entries are
 // re-laid in the order the sweep visits them, in records of RPW rows (= the rows one warp handles at a time, cut at level
 // boundaries):   [ uint4 {row, entries here, first / end of the entries beyond KS in the canonical arrays} x RPW
 //                | columns [KS][RPW] | blocks [KS][N][RPW*N] (component a of row r at r*N + a) | D^-1 [N][RPW*N] (forward) ]
-// so that every load of a warp is contiguous (the canonical row-major blocks cost 8 memory wavefronts per load instruction
-// — one per row — and the sweeps were bound by exactly that: 330 + 200 wavefronts per warp and level, ncu + in-kernel clocks).
+// A warp fetches its record with ONE bulk copy (TMA, evict-first: the factor streams through L2 once per sweep and must not
+// push out the vector the levels exchange through L2), two items ahead, into its own double buffer in shared memory. The
+// canonical row-major blocks cost 8 memory wavefronts per load instruction — one per row — and the sweeps were bound by
+// exactly that (330 + 200 wavefronts per warp and level: ncu + in-kernel clocks, DFB_ILU_TRACE).
 // A block-row is shared by N lanes — lane a carries component a of t = v_i - sum_j L_ij v_j through the reference's loop
 // (sparse_ilu.rs:183-219: ascending entries, mult_vec's left fold over the block's columns), the neighbours' values and the
 // D^-1 product move between the lanes by shuffle — so every rounding is the one of the one-thread-per-row kernels above
-// (bit-identical, tested).  Two flavours of the same kernel:
-//   CLUSTER = false  one CTA per SM, a grid-wide barrier between levels (one atomic per CTA + one polling thread per CTA)
-//   CLUSTER = true   ONE thread-block cluster (16 CTAs), the hardware cluster barrier between levels
-// Work items (one pass of the grid over part of a level; built on the host for the launch shape, staged in shared memory) are
-// software-pipelined: the record of item k+1 is loaded into registers (THREADS = 128: narrow, latency-bound levels) or
-// prefetched to L2 (THREADS = 512: wide levels) while item k is computed, so that behind a barrier only the neighbours' values
-// are a dependent read.
-// A sync-free variant (per-row epoch flags polled by the dependent rows, Liu et al.) was built and measured SLOWER (11-13 ms per
-// iteration at S1 for every window size / back-off tried: 0.78 G L2 requests of polling per sweep) and removed.
+// (bit-identical, tested).
+// Work items (one pass of the grid over part of a level) are built on the host for the launch shape and staged in shared memory.
+// Measured (tools/precond_compare.py, profiles/r2_precond_compare.txt): S1 1.27 ms per PCG iteration (round 1, one launch per
+// level: 6.4), S10 4.3 (41.7). What remains per level at S1 (in-kernel clocks): ~1.5 us grid barrier (tools/micro/gridbar.cu) +
+// ~0.5 us until the neighbours' values arrive + ~0.3 us arithmetic.
+// Built, measured slower and removed: per-row epoch flags polled by the dependent rows (sync-free, Liu et al.: 11-13 ms per
+// iteration at S1, 0.78 G L2 requests of polling per sweep); one thread per row with register prefetch of the canonical
+// entries (3.8 ms); the whole sweep on ONE 16-CTA thread-block cluster with the hardware cluster barrier (1.6 ms at S1, 29 ms
+// at S10: 16 SMs' load pipes carry ~100 rows each per level); tree barriers (group counters -> root -> release flags: 3.7-8.3 us).
 template <int N> struct IluLanes {   // lanes per row (N = 3: the 4th lane of a quad idles) and rows per warp
   static constexpr int LPR = (N == 3) ? 4 : N, RPW = 32 / LPR;
 };
@@ -313,38 +316,45 @@ __device__ __forceinline__ void ilu_grid_barrier(unsigned int *ctr, unsigned int
 }
 __global__ void k_ilu_barrier_reset(unsigned int *ctr) { *ctr = 0u; }
 
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ unsigned cluster_nctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-static const int ILU_ITEM_SMEM = 4096;                  // work items staged in shared memory (longer lists: read from global)
+static const int ILU_ITEM_SMEM = 2048;                  // work items staged in shared memory (longer lists: read from global)
 static const uint32_t ILU_ITEM_BARRIER = 0x80000000u;   // flag in an item's record count: a level boundary precedes the item
 
-template <int N, bool FORWARD, bool CLUSTER, int THREADS>
+#ifdef DFB_ILU_TRACE   // debugging aid (make EXTRA=-DDFB_ILU_TRACE): SM clocks of CTA 0 / warp 0 around the phases of every item
+__device__ long long g_ilu_trace[8 * 1024];
+#define ILU_TRACE(slot) if (FORWARD && cta == 0 && threadIdx.x == 0 && k < 1024) g_ilu_trace[k * 8 + (slot)] = clock64()
+#else
+#define ILU_TRACE(slot)
+#endif
+
+template <int N, bool FORWARD> struct IluSweepSmem {   // dynamic shared memory per warp: two record buffers + their mbarriers
+  static constexpr int WARP_BYTES = 2 * IluRec<N, FORWARD>::BYTES + 128;
+};
+
+template <int N, bool FORWARD, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__restrict__ rec, const uint2 *__restrict__ items, uint32_t n_items,
                                                        const uint32_t *__restrict__ col, const double *__restrict__ val, double *vec,
                                                        unsigned int *bar) {
   using R = IluRec<N, FORWARD>;
   constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = R::RPW, RN = R::RN, KS = ILU_KS;
-  constexpr bool WPRE = THREADS <= 128 && N <= 3;   // registers to spare: the next record's blocks are loaded one item ahead
-  constexpr int B = WPRE ? KS : 4;                  // entries whose loads are issued together before their arithmetic
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint2 s_item[ILU_ITEM_SMEM];
-  const unsigned n_cta = CLUSTER ? cluster_nctarank() : gridDim.x, cta = CLUSTER ? cluster_ctarank() : blockIdx.x;
+  const unsigned n_cta = gridDim.x, cta = blockIdx.x;
   const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const unsigned sub = lane % LPR, base = lane - sub, r = lane / LPR;
   const bool act = sub < (unsigned)N;
   const unsigned a_ = act ? sub : 0u;           // component of the row this lane carries
   const uint32_t wslot = wid * n_cta + cta;     // consecutive records of a level go to different CTAs
+  unsigned char *wbase = smem_raw + (size_t)wid * IluSweepSmem<N, FORWARD>::WARP_BYTES;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(wbase + 2 * R::BYTES);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the factor records stream through L2 once per sweep: evict-first, so that they do not push out the vector the levels
+  // exchange through L2 (its lines are touched at one level only and would be gone by the time they are needed)
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   const bool in_smem = n_items <= (uint32_t)ILU_ITEM_SMEM;
   if (in_smem)
     for (uint32_t k = threadIdx.x; k < n_items; k += THREADS) s_item[k] = items[k];
@@ -357,99 +367,91 @@ __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__re
     const uint2 it = item(k);
     return wslot < (it.y & ~ILU_ITEM_BARRIER) ? rec + (uint64_t)(it.x + wslot) * R::BYTES : nullptr;
   };
-  struct Stage {
-    const unsigned char *p;
-    uint4 h;
-    uint32_t cols[KS];
-    double w[WPRE ? KS : 1][N], dw[N];
+  // the record of item k into buffer b: ONE bulk copy (TMA) per warp, no registers and no load-pipe slots spent on the stream
+  auto issue = [&](uint32_t k, uint32_t b) {
+    const unsigned char *p = record(k);
+    if (lane != 0 || !p) return;
+    const uint32_t mb = bar0 + 8 * b;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)R::BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(wbase + (size_t)b * R::BYTES)),
+                 "l"(p), "r"((uint32_t)R::BYTES), "r"(mb), "l"(pol)
+                 : "memory");
   };
-  auto stage = [&](const unsigned char *p, Stage &s) {
-    s.p = p;
-    if (!p) return;
-    s.h = reinterpret_cast<const uint4 *>(p)[r];
-    const uint32_t *pc = reinterpret_cast<const uint32_t *>(p + R::OFF_COL);
-#pragma unroll
-    for (int k = 0; k < KS; ++k) s.cols[k] = pc[k * RPW + r];
-    if (WPRE) {
-      const double *pw = reinterpret_cast<const double *>(p + R::OFF_W);
-#pragma unroll
-      for (int k = 0; k < KS; ++k)
-#pragma unroll
-        for (int d = 0; d < N; ++d) s.w[WPRE ? k : 0][d] = pw[(k * N + d) * RN + r * N + a_];
-      if (FORWARD) {
-        const double *pd = reinterpret_cast<const double *>(p + R::OFF_DIA);
-#pragma unroll
-        for (int d = 0; d < N; ++d) s.dw[d] = pd[d * RN + r * N + a_];
-      }
-    }
-  };
-  auto prefetch_record = [&](const unsigned char *p) {
-    if (!p) return;
-    for (int off = lane * 128; off < R::BYTES; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-  };
-  // the rows of one record; executed by whole warps (shuffles)
-  auto do_rows = [&](const Stage &s) {
-    const bool live = s.h.x != ILU_NONE;
-    const uint32_t i = live ? s.h.x : 0u, cnt = s.h.y;
+  // the rows of one record (in shared memory); executed by whole warps (shuffles)
+  auto do_rows = [&](const unsigned char *buf, uint32_t k) {
+    (void)k;
+    const uint4 h = reinterpret_cast<const uint4 *>(buf)[r];   // {row, entries here, first / end of the entries beyond KS}
+    const bool live = h.x != ILU_NONE;
+    const uint32_t i = live ? h.x : 0u, cnt = h.y;
+    const uint32_t *pc = reinterpret_cast<const uint32_t *>(buf + R::OFF_COL);
     double t = live ? __ldcg(vec + (uint64_t)i * N + a_) : 0.0;
-    const double *pw = reinterpret_cast<const double *>(s.p + R::OFF_W);
-    double dw[N];
-    if (FORWARD) {
-      const double *pd = reinterpret_cast<const double *>(s.p + R::OFF_DIA);
+    double xv[KS];
 #pragma unroll
-      for (int d = 0; d < N; ++d) dw[d] = WPRE ? s.dw[d] : pd[d * RN + r * N + a_];
-    }
+    for (int q = 0; q < KS; ++q)   // lane a reads component a of the neighbour (written by other SMs in earlier levels: L2)
+      xv[q] = ((uint32_t)q < cnt && act) ? __ldcg(vec + (uint64_t)pc[q * RPW + r] * N + a_) : 0.0;
+    ILU_TRACE(1);
+    const double *pw = reinterpret_cast<const double *>(buf + R::OFF_W);
 #pragma unroll
-    for (int k0 = 0; k0 < KS; k0 += B) {
-      double xv[B], w[B][N];
-#pragma unroll
-      for (int k = 0; k < B; ++k) {
-        // lane a reads component a of the neighbour (written by other SMs in earlier levels: L2); the row's lanes exchange below
-        xv[k] = ((uint32_t)(k0 + k) < cnt && act) ? __ldcg(vec + (uint64_t)s.cols[k0 + k] * N + a_) : 0.0;
-#pragma unroll
-        for (int d = 0; d < N; ++d) w[k][d] = WPRE ? s.w[WPRE ? k0 + k : 0][d] : pw[((k0 + k) * N + d) * RN + r * N + a_];
-      }
-#pragma unroll
-      for (int k = 0; k < B; ++k) {
-        double acc = 0.0;
-#pragma unroll
-        for (int d = 0; d < N; ++d) acc = acc + w[k][d] * __shfl_sync(0xFFFFFFFFu, xv[k], base + d);
-        if ((uint32_t)(k0 + k) < cnt) t -= acc;
-      }
-    }
-    for (uint32_t k = s.h.z; k < s.h.w; ++k) {   // rows longer than the record (ILU(k) fill): the canonical arrays
-      const uint32_t c = col[k];
+    for (int q = 0; q < KS; ++q) {
       double acc = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) acc = acc + val[(uint64_t)k * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
+      for (int d = 0; d < N; ++d) acc = acc + pw[(q * N + d) * RN + r * N + a_] * __shfl_sync(0xFFFFFFFFu, xv[q], base + d);   // the row's lanes exchange
+      if ((uint32_t)q < cnt) t -= acc;
+    }
+    for (uint32_t q = h.z; q < h.w; ++q) {   // rows longer than the record (ILU(k) fill): the canonical arrays
+      const uint32_t c = col[q];
+      double acc = 0.0;
+#pragma unroll
+      for (int d = 0; d < N; ++d) acc = acc + val[(uint64_t)q * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
       t -= acc;
     }
     __syncwarp();
     if (FORWARD) {
+      const double *pd = reinterpret_cast<const double *>(buf + R::OFF_DIA);
       double acc = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) acc = acc + dw[d] * __shfl_sync(0xFFFFFFFFu, t, base + d);
+      for (int d = 0; d < N; ++d) acc = acc + pd[d * RN + r * N + a_] * __shfl_sync(0xFFFFFFFFu, t, base + d);
       t = acc;
     }
     if (live && act) vec[(uint64_t)i * N + a_] = t;
+#ifdef DFB_ILU_TRACE
+    if (t == 1.2345e300) g_ilu_trace[8191] = 1;   // the clock read behind the rows must wait for their result
+#endif
   };
 
   if (n_items == 0) return;
-  Stage cur;
-  stage(record(0), cur);
-  if (!WPRE) prefetch_record(record(1));
+  __syncwarp();
+  issue(0, 0);
+  issue(1, 1);
+  uint32_t phase[2] = {0u, 0u};
   unsigned int n_bar = 0;
   for (uint32_t k = 0;; ++k) {
-    Stage nxt;
-    stage(record(k + 1), nxt);
-    if (!WPRE) prefetch_record(record(k + 2));
-    if (cur.p) do_rows(cur);
-    if (k + 1 >= n_items) break;
-    if (item(k + 1).y & ILU_ITEM_BARRIER) {
-      if (CLUSTER) cluster_barrier();
-      else ilu_grid_barrier(bar, ++n_bar);
+    const uint32_t b = k & 1u;
+    ILU_TRACE(0);
+    if (record(k)) {
+      const uint32_t mb = bar0 + 8 * b;
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "ILU_WAIT:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra ILU_DONE;\n"
+          "bra ILU_WAIT;\n"
+          "ILU_DONE:\n"
+          "}\n" ::"r"(mb),
+          "r"(phase[b])
+          : "memory");
+      phase[b] ^= 1u;
+      ILU_TRACE(4);
+      do_rows(wbase + (size_t)b * R::BYTES, k);
+      __syncwarp();   // every lane has read the buffer before the next copy into it is issued
     }
-    cur = nxt;
+    ILU_TRACE(2);
+    issue(k + 2, b);
+    if (k + 1 >= n_items) break;
+    if (item(k + 1).y & ILU_ITEM_BARRIER) ilu_grid_barrier(bar, ++n_bar);
+    ILU_TRACE(3);
   }
 }
 
@@ -729,55 +731,11 @@ static dfb_status dfb_ilu_reslice(dfb_ctx *c, DfbIlu *s, int N, const double *d_
   return dfb_fail(DFB_ERR_UNSUPPORTED, "ilu: blk_dim %d", N);
 }
 
-static void ilu_cluster_config(cudaLaunchConfig_t *cfg, cudaLaunchAttribute *at, int cs, int threads, cudaStream_t strm) {
-  *cfg = cudaLaunchConfig_t{};
-  cfg->gridDim = dim3(cs);
-  cfg->blockDim = dim3(threads);
-  cfg->stream = strm;
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cs;
-  at[0].val.clusterDim.y = at[0].val.clusterDim.z = 1;
-  cfg->attrs = at;
-  cfg->numAttrs = 1;
-}
-
-// one cluster of 16 CTAs (8 where the non-portable size cannot be scheduled); 0 = clusters unavailable for this kernel
-template <int N, int THREADS>
-static int ilu_cluster_size(dfb_ctx *c) {
-  static int cached = -1, cached_want = -1;
-  const int want = c->ilu_cluster_ctas > 0 ? (int)c->ilu_cluster_ctas : 16;
-  if (cached >= 0 && cached_want == want) return cached;
-  int best = 0;
-  for (int cs = want; cs >= 1 && !best; cs /= 2) {
-    bool ok = true;
-    for (int f = 0; f < 2 && ok; ++f) {
-      const void *fn = f ? (const void *)k_ilu_sweep<N, true, true, THREADS> : (const void *)k_ilu_sweep<N, false, true, THREADS>;
-      if (cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
-      cudaLaunchConfig_t cfg;
-      cudaLaunchAttribute at[1];
-      ilu_cluster_config(&cfg, at, cs, THREADS, c->stream);
-      int nclusters = 0;
-      if (ok && (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1)) ok = false;
-    }
-    if (ok) best = cs;
-  }
-  (void)cudaGetLastError();
-  cached = best;
-  cached_want = want;
-  return best;
-}
-
 // solve_preconditioning_vec, in place: forward then backward sweep, one launch each
-template <int N, int THREADS>
-static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, double *d_vec, bool cluster) {
-  int n_cta = c->sm_count;   // grid barrier: one resident CTA per SM (<= 512 threads, 32 KB of shared memory: always co-resident)
-  if (cluster) {
-    n_cta = ilu_cluster_size<N, THREADS>(c);
-    if (n_cta < 1) {
-      cluster = false;
-      n_cta = c->sm_count;
-    }
-  }
+template <int N>
+static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, double *d_vec) {
+  constexpr int THREADS = N == 4 ? 256 : 512;   // two record buffers per warp: 180 KB of shared memory (N = 4: 9.6 KB records)
+  const int n_cta = c->sm_count;                // one resident CTA per SM: the grid barrier needs all of them running
   const uint32_t pass = (uint32_t)n_cta * (THREADS / 32);
   const uint2 *it_f = nullptr, *it_b = nullptr;
   uint32_t nf = 0, nb = 0;
@@ -787,51 +745,48 @@ static dfb_status ilu_sweeps_launch(dfb_ctx *c, const DfbIlu *s, double *d_vec, 
   const uint32_t *col = s->d_col;
   const double *val = s->d_val;
   unsigned int *bar = s->d_epoch + 4;
-  if (cluster) {
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[1];
-    ilu_cluster_config(&cfg, at, n_cta, THREADS, c->stream);
-    if (nf) {
-      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, true, true, THREADS>, rec_f, it_f, nf, col, val, d_vec, bar));
-      c->launches += 1;
-    }
-    if (nb) {
-      DFB_CUDA(cudaLaunchKernelEx(&cfg, k_ilu_sweep<N, false, true, THREADS>, rec_b, it_b, nb, col, val, d_vec, bar));
-      c->launches += 1;
-    }
-    return DFB_OK;
-  }
+  const size_t smem_f = (size_t)(THREADS / 32) * IluSweepSmem<N, true>::WARP_BYTES, smem_b = (size_t)(THREADS / 32) * IluSweepSmem<N, false>::WARP_BYTES;
+  // (the dynamic shared-memory opt-in is a per-device function attribute: set on every launch, cheap)
+  DFB_CUDA(cudaFuncSetAttribute(k_ilu_sweep<N, true, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+  DFB_CUDA(cudaFuncSetAttribute(k_ilu_sweep<N, false, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, false, THREADS>), n_cta, THREADS, 0, rec_f, it_f, nf, col, val, d_vec, bar);
+  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, THREADS>), n_cta, THREADS, smem_f, rec_f, it_f, nf, col, val, d_vec, bar);
   DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, false, THREADS>), n_cta, THREADS, 0, rec_b, it_b, nb, col, val, d_vec, bar);
+  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, THREADS>), n_cta, THREADS, smem_b, rec_b, it_b, nb, col, val, d_vec, bar);
   DFB_CHECK_LAUNCH();
-  return DFB_OK;
-}
-
-// which sweep runs: option "ilu_sweep_mode" 2 = one cluster, else the grid barrier; "ilu_sweep_threads" 128 / 512 per CTA,
-// 0 = by the mean level width (narrow levels are latency-bound and every resident warp costs issue slots per level; wide levels
-// want the warps)
-template <int N>
-static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, uint64_t n_rows, double *d_vec) {
-  const bool cluster = c->ilu_sweep_mode == 2;
-  int threads = (int)c->ilu_sweep_threads;
-  if (threads != 128 && threads != 512) {
-    const uint64_t nlev = s->lev_f.size() > 1 ? s->lev_f.size() - 1 : 1;
-    const uint64_t lanes = n_rows / nlev * IluLanes<N>::LPR;   // lanes a mean level keeps busy
-    threads = (!cluster && lanes <= (uint64_t)c->sm_count * 128) ? 128 : 512;
+#ifdef DFB_ILU_TRACE
+  {
+    static int calls = 0;
+    if (++calls == 5) {
+      cudaStreamSynchronize(c->stream);
+      static long long h[8 * 1024];
+      cudaMemcpyFromSymbol(h, g_ilu_trace, sizeof(h));
+      const int lo = (int)nf / 4, hi = std::min((int)nf - 1, 1023) * 3 / 4;
+      double d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k = lo; k < hi; ++k) {
+        const long long *q = h + k * 8;
+        d[0] += q[4] - q[0];   // wait for the record (TMA)
+        d[1] += q[1] - q[4];   // header + gather loads issued
+        d[2] += q[2] - q[1];   // wait for the values + arithmetic + store
+        d[3] += q[3] - q[2];   // next copy issued + barrier
+        d[4] += q[8] - q[3];   // loop
+      }
+      const double n = hi - lo;
+      fprintf(stderr, "[ilu trace] forward items %d..%d, SM cycles: record wait %.0f | gather issue %.0f | values + arithmetic + store %.0f | barrier %.0f | loop %.0f\n",
+              lo, hi, d[0] / n, d[1] / n, d[2] / n, d[3] / n, d[4] / n);
+    }
   }
-  if (threads == 128) return ilu_sweeps_launch<N, 128>(c, s, d_vec, cluster);
-  return ilu_sweeps_launch<N, 512>(c, s, d_vec, cluster);
+#endif
+  return DFB_OK;
 }
 
 dfb_status dfb_ilu_apply(dfb_ctx *c, const DfbIlu *s, const dfb_pattern *pat, int N, const double *d_dia, double *d_vec) {
   if (c->ilu_level_launches == 0) {
     switch (N) {
-      case 1: return ilu_sweeps<1>(c, s, pat->num_blk, d_vec);
-      case 2: return ilu_sweeps<2>(c, s, pat->num_blk, d_vec);
-      case 3: return ilu_sweeps<3>(c, s, pat->num_blk, d_vec);
-      case 4: return ilu_sweeps<4>(c, s, pat->num_blk, d_vec);
+      case 1: return ilu_sweeps<1>(c, s, d_vec);
+      case 2: return ilu_sweeps<2>(c, s, d_vec);
+      case 3: return ilu_sweeps<3>(c, s, d_vec);
+      case 4: return ilu_sweeps<4>(c, s, d_vec);
     }
   }
   // one launch per level (option "ilu_level_launches" = 1): the reference point the sweeps are checked against

@@ -711,7 +711,7 @@ static dfb_status run_pcg(const dfb_bsr *m, const dfb_precond *pc, dfb_vec *r, d
   P.nccl_red = (c->nranks > 1 && !P.peer) ? 1 : 0;
   P.peer_halo = (P.peer && dfb_spmv_uses_peer_halo(m)) ? 1 : 0;
   P.spmv_variant = c->spmv_variant;
-  P.ilu_levels = (int)(c->ilu_level_launches | (c->ilu_sweep_mode << 1) | (c->ilu_sweep_threads << 4));
+  P.ilu_levels = (int)c->ilu_level_launches;
   P.chunk = c->iters_per_sync > 0 ? c->iters_per_sync : 16;
   if (P.chunk > 256) P.chunk = 256;
   // ring of ||r_k||^2: the host drains it after every chunk, so 2 chunks + the plain head iteration always fit

@@ -455,19 +455,17 @@ def test_ilu0_matches_oracle(dfb, ctx, orc, case):
     vd = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vd, pc)
     assert rel_err(vd.download(), want) < 1e-13
-    # the persistent sweeps (one launch per sweep: grid barrier per level, or one thread-block cluster with N lanes per row) and
-    # the level-per-launch sweeps give the same bits
+    # the persistent sweeps (default: one launch per sweep over the sweep-ordered factor copy, N lanes per row, grid barrier per
+    # level) and the level-per-launch sweeps (one thread per row, canonical arrays) give the same bits
     ctx.set_option("ilu_level_launches", 1)
     vl = dfb.Vec.from_numpy(ctx, v)
     sparse_ilu.solve_preconditioning_vec(vl, pc)
     ctx.set_option("ilu_level_launches", 0)
     assert np.array_equal(vl.download(), vd.download())
-    for mode in (1, 2, 0):
-        ctx.set_option("ilu_sweep_mode", mode)
-        for _ in range(3):  # repeated applications reuse the barrier counter
-            vr = dfb.Vec.from_numpy(ctx, v)
-            sparse_ilu.solve_preconditioning_vec(vr, pc)
-            assert np.array_equal(vr.download(), vl.download()), mode
+    for _ in range(3):  # repeated applications reuse the barrier counter
+        vr = dfb.Vec.from_numpy(ctx, v)
+        sparse_ilu.solve_preconditioning_vec(vr, pc)
+        assert np.array_equal(vr.download(), vl.download())
     ro = rhs_h.copy()
     xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
     hist_o = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, tol, max_it, r2i, i2c, iv, rv, ilu_o)
@@ -522,6 +520,42 @@ def test_general_problem_single_rank_matches_oracle(dfb, ctx, orc):
     ho = orc.preconditioned_conjugate_gradient(b, xo, pr, p, 1e-8, 5000, r2i, i2c, iv, rv, ilu)
     assert abs(len(prob.hist) - len(ho)) <= 1
     assert rel_err(x, xo) < 1e-7
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_ilu0_sweeps_every_block_size(dfb, ctx, orc, n):
+    """ILU(0) of a block-diagonally-dominant random matrix on a tet-mesh pattern for every block size the ABI accepts: factor +
+    sweeps match the oracle's serial ones, and the persistent sweeps (N lanes per row over the sweep-ordered factor copy; rows
+    of up to 14 entries, i.e. more than the 8 a record holds) give the bits of the level-per-launch sweeps"""
+    from del_fem_b200 import sparse_ilu
+    e2v, xyz = orc.kuhn_tet_mesh(6, 5, 7)
+    nv = xyz.shape[0]
+    r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+    rng = np.random.default_rng(10 + n)
+    nnz = len(i2c)
+    iv = 0.1 * rng.standard_normal((nnz, n * n))
+    rv = 0.1 * rng.standard_normal((nv, n * n))
+    rv[:, :: n + 1] += 4.0   # dominant block diagonals (col-major n x n: entries 0, n+1, ...)
+    mat = dfb.Matrix.from_vtx2vtx(r2i, i2c, n, ctx=ctx)
+    mat.upload(rv, iv)
+    ilu_o = orc.Ilu("ilu0", n, r2i, i2c)
+    ilu_o.copy_value(r2i, i2c, iv, rv)
+    ilu_o.decompose()
+    pc = sparse_ilu.Preconditioner("ilu0")
+    pc.initialize(mat)
+    sparse_ilu.copy_value(pc, mat)
+    sparse_ilu.decompose(pc)
+    v = rng.standard_normal((nv, n))
+    want = v.copy()
+    ilu_o.solve(want)
+    vd = dfb.Vec.from_numpy(ctx, v)
+    sparse_ilu.solve_preconditioning_vec(vd, pc)
+    assert rel_err(vd.download(), want) < 1e-13
+    ctx.set_option("ilu_level_launches", 1)
+    vl = dfb.Vec.from_numpy(ctx, v)
+    sparse_ilu.solve_preconditioning_vec(vl, pc)
+    ctx.set_option("ilu_level_launches", 0)
+    assert np.array_equal(vl.download(), vd.download())
 
 
 @pytest.mark.parametrize("lev_fill", [0, 1, 3, 10000])

@@ -65,6 +65,57 @@ __device__ __forceinline__ void barrier(unsigned *ctr, unsigned *flags, unsigned
       }
     }
     __syncthreads();
+  } else if (V >= 7 && V <= 9) {   // two-level tree: G group counters on separate 128-byte lines -> root -> G release flags
+    constexpr unsigned G = V == 7 ? 4u : V == 8 ? 8u : 16u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned g = blockIdx.x % G, members = (gridDim.x + G - 1 - g) / G;
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr + 32 * (1 + g)) : "memory");
+      if (old + 1 == epoch * members) {   // last of the group
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+        if (old + 1 == epoch * G) {       // last group: release everybody
+          for (unsigned q = 0; q < G; ++q) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + 32 * q), "r"(epoch) : "memory");
+        }
+      }
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + 32 * g) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+  } else if (V == 10) {   // one counter, but the release is a separate flag line written by the last arriver
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+      if (old + 1 == epoch * gridDim.x) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags), "r"(epoch) : "memory");
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+  } else if (V == 11) {   // like 8, relaxed polling + one fence
+    constexpr unsigned G = 8u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned g = blockIdx.x % G, members = (gridDim.x + G - 1 - g) / G;
+      unsigned old;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr + 32 * (1 + g)) : "memory");
+      if (old + 1 == epoch * members) {
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+        if (old + 1 == epoch * G) {
+          for (unsigned q = 0; q < G; ++q) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + 32 * q), "r"(epoch) : "memory");
+        }
+      }
+      unsigned v;
+      do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + 32 * g) : "memory");
+      } while (v < epoch);
+      __threadfence();
+    }
+    __syncthreads();
   } else if (V == 6) {   // every warp's lane 0 polls (no second __syncthreads)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -103,7 +154,7 @@ template <int V>
 void run(const char *name, int threads, int grid) {
   unsigned *ctr, *flags, *err;
   double *vec;
-  cudaMalloc(&ctr, 64);
+  cudaMalloc(&ctr, 128 * 40);
   cudaMalloc(&flags, 4096);
   cudaMalloc(&err, 4);
   cudaMalloc(&vec, 4096 * 16 * 8);
@@ -111,7 +162,7 @@ void run(const char *name, int threads, int grid) {
   float best = 1e30f;
   unsigned herr = 0;
   for (int rep = 0; rep < 3; ++rep) {
-    cudaMemset(ctr, 0, 64);
+    cudaMemset(ctr, 0, 128 * 40);
     cudaMemset(flags, 0, 4096);
     cudaMemset(err, 0, 4);
     cudaEvent_t a, b;
@@ -152,6 +203,11 @@ int main() {
     run<4>("cooperative groups grid.sync()", threads, g);
     run<5>("atomicAdd + poll, NO fences (signalling only)", threads, g);
     run<6>("4 counters, every warp polls", threads, g);
+    run<7>("tree: 4 group lines -> root -> 4 flag lines", threads, g);
+    run<8>("tree: 8 group lines -> root -> 8 flag lines", threads, g);
+    run<9>("tree: 16 group lines -> root -> 16 flag lines", threads, g);
+    run<10>("one counter, separate release flag line", threads, g);
+    run<11>("tree 8, relaxed flags + fence", threads, g);
   }
   run<0>("fence + atomicAdd (4 counters), 74 CTAs", 128, g / 2);
   run<0>("fence + atomicAdd (4 counters), 37 CTAs", 128, g / 4);

@@ -21,11 +21,9 @@ for kv in sys.argv[3:]:
     k, v = kv.split("=")
     ctx.set_option(k, int(v))
 for kind in sys.argv[2].split(","):
-    # "ilu0_levels" = ILU(0) with one launch per level (the round-1 schedule), "ilu0" = dependency-driven sweeps (one launch per sweep)
-    # "ilu0_grid" / "ilu0_cluster" force the grid-barrier / single-cluster sweep (plain "ilu0" chooses by level width)
+    # "ilu0_levels" = ILU(0) with one launch per level (the round-1 schedule), "ilu0" = persistent sweeps (one launch per sweep, grid barrier per level)
     ctx.set_option("ilu_level_launches", 1 if kind.endswith("_levels") else 0)
-    ctx.set_option("ilu_sweep_mode", 1 if kind.endswith("_grid") else 2 if kind.endswith("_cluster") else 0)
-    pc = sparse_ilu.Preconditioner(kind.split("_levels")[0].split("_grid")[0].split("_cluster")[0])
+    pc = sparse_ilu.Preconditioner(kind.replace("_levels", ""))
     ctx.timer_start(); pc.initialize(mat); t_sym = ctx.timer_stop()
     sparse_ilu.copy_value(pc, mat)
     ctx.timer_start(); sparse_ilu.decompose(pc); t_num = ctx.timer_stop()
