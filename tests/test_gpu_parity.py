@@ -423,6 +423,63 @@ def test_pcg_matches_oracle(dfb, ctx, orc, n_mesh, kind):
     assert np.array_equal(xd.download(), xs)
 
 
+def test_degenerate_sizes(dfb, ctx, orc):
+    """the smallest inputs the path accepts: ONE tet (4 vertices, a single partial tile everywhere), a 2 x 2 x 2-vertex cube, and
+    a matrix with zero rows — pattern, fused assembly, BC, SpMV and PCG against the oracle"""
+    from del_fem_b200 import sparse_ilu
+    for shape in [(2, 2, 2), None]:
+        if shape is None:   # one tet
+            e2v = np.array([[0, 1, 2, 3]], dtype=np.uint64)
+            xyz = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+        else:
+            e2v, xyz = orc.kuhn_tet_mesh(*shape)
+        nv = xyz.shape[0]
+        r2i, i2c = orc.vtx2vtx_from_uniform_mesh(e2v, 4, nv, False)
+        rv, iv = orc.assemble("solid_linear_tet", 0, e2v, xyz, 1.0, 1.0, r2i, i2c)
+        mesh = dfb.Mesh(ctx, e2v, xyz)
+        pat = dfb.Pattern.from_uniform_mesh(ctx, mesh, False)
+        r2i_d, i2c_d = pat.download()
+        assert np.array_equal(r2i_d, r2i) and np.array_equal(i2c_d, i2c)
+        plan = dfb.Plan(ctx, pat, mesh, 0)
+        mat = dfb.Matrix(ctx, pat, 3)
+        mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
+        rv_d, iv_d = mat.download()
+        assert np.array_equal(rv_d, rv) and np.array_equal(iv_d, iv)
+        flag = flags_z0(xyz)
+        x = np.random.default_rng(0).standard_normal((nv, 3))
+        y = np.zeros((nv, 3))
+        orc.mult_vec(y, 0.0, 1.0, x, r2i, i2c, iv, rv)
+        xd, yd = dfb.Vec.from_numpy(ctx, x), dfb.Vec(ctx, nv, 3)
+        mat.mult_vec(yd, 0.0, 1.0, xd)
+        assert rel_err(yd.download(), y) < 1e-13
+        orc.set_fixed_bc(1.0, flag, rv, iv, r2i, i2c)
+        mat.set_fixed_dof(1.0, flag)
+        rv_d, iv_d = mat.download()
+        assert np.array_equal(rv_d, rv) and np.array_equal(iv_d, iv)
+        b = np.zeros((nv, 3))
+        b[flag == 0] = 1e-2
+        pc = sparse_ilu.Preconditioner("jacobi")
+        pc.initialize(mat)
+        sparse_ilu.copy_value(pc, mat)
+        sparse_ilu.decompose(pc)
+        rd = dfb.Vec.from_numpy(ctx, b)
+        ud, qd, pd = dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3), dfb.Vec(ctx, nv, 3)
+        h = dfb.preconditioned_conjugate_gradient(rd, ud, qd, pd, 1e-10, 100, mat, pc)
+        ilu_o = orc.Ilu("jacobi", 3, r2i, i2c)
+        ilu_o.copy_value(r2i, i2c, iv, rv)
+        ilu_o.decompose()
+        ro = b.copy()
+        xo, pro, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+        ho = orc.preconditioned_conjugate_gradient(ro, xo, pro, po, 1e-10, 100, r2i, i2c, iv, rv, ilu_o)
+        assert abs(len(h) - len(ho)) <= 1
+        assert rel_err(ud.download(), xo) < 1e-8
+    # zero rows: every entry point is a no-op
+    m0 = dfb.Matrix.from_vtx2vtx(np.array([0], dtype=np.uint64), np.array([], dtype=np.uint64), 3, ctx=ctx)
+    v0, w0 = dfb.Vec(ctx, 0, 3), dfb.Vec(ctx, 0, 3)
+    m0.mult_vec(w0, 0.0, 1.0, v0)
+    assert w0.download().shape == (0, 3)
+
+
 def test_solver_history_semantics(dfb, ctx, orc):
     """A11/A12 quirks: CG early-out returns an empty history; PCG history has k=0 and a trailing entry when max_it
     is exhausted; CG hits max_it with exactly max_it entries."""
