@@ -19,7 +19,8 @@ Beside the headline the same JSON line carries (so that one driver run sees them
   dist_parity   (N > 1) a small slab problem and a shuffled-then-RCM general mesh solved distributed and on rank 0 alone: owned rows
                 bit-identical, iteration count +-1, |x - x1| / |x1| < 1e-7.  A failure makes the run exit non-zero.
   configs       (N = 1) compact records of BASELINE configs 3 (2048^2 mass-spring cloth: 10 steps x (reassembly + CG 1e-5)) and
-                4 (16 x 16 x 256-cell neo-Hookean beam: Newton ramp, reassembly + Jacobi-PCG per iteration) with their phase split.
+                4 (16 x 16 x 256-cell neo-Hookean beam: Newton ramp, reassembly + Jacobi-PCG per iteration) with their phase split,
+                and c2_ilu0: config 2 (S1) solved with the reference's own default preconditioner ILU(0) beside Jacobi.
   true_rel_residual   ||b - A x|| / ||b|| of the last headline solve, recomputed with one (distributed) SpMV after the timed region.
 """
 import argparse
@@ -716,6 +717,49 @@ def run_ours(args):
     return rc
 
 
+def ilu_record(env, n=70):
+    """BASELINE config 2 (S1) solved with the reference's OWN default preconditioner, ILU(0) (del-fem-ls/src/linearsystem.rs:53),
+    beside Jacobi on the same system: setup (symbolic + numeric), iterations, ms per iteration, time to solution"""
+    from del_fem_b200 import sparse_ilu, synthetic
+    dfb, ctx = env.dfb, env.ctx
+    mesh = dfb.Mesh.kuhn(ctx, n)
+    pat = dfb.Pattern.from_uniform_mesh(ctx, mesh, False)
+    plan = dfb.Plan(ctx, pat, mesh, 0)
+    mat = dfb.Matrix(ctx, pat, 3)
+    mat.assemble(plan, "solid_linear_tet", mesh, 1.0, 1.0)
+    nv = mesh.num_vtx
+    flag = dfb.BcFlag(ctx, synthetic.clamp_flags_z0(n, n, n))
+    u0, rhs, r, x, q, p = (dfb.Vec(ctx, nv, 3) for _ in range(6))
+    u0.fill_splitmix(0, 0, -0.1, 0.1)
+    u0.set_fixed_dof_zero_dev(flag)
+    mat.mult_vec(rhs, 0.0, -1.0, u0)
+    rhs.set_fixed_dof_zero_dev(flag)
+    mat.set_fixed_dof_dev(1.0, flag)
+    rec = {"workload": f"S1 ({n}^3 vertices, {3 * nv} DoF), (P)CG to 1e-8"}
+    for kind in ("jacobi", "ilu0"):
+        pc = sparse_ilu.Preconditioner(kind)
+        ctx.timer_start()
+        pc.initialize(mat)
+        t_sym = ctx.timer_stop()
+        sparse_ilu.copy_value(pc, mat)
+        ctx.timer_start()
+        sparse_ilu.decompose(pc)
+        t_num = ctx.timer_stop()
+        best = None
+        for _ in range(2):   # the second solve replays the cached graph
+            r.copy_from(rhs)
+            ctx.timer_start()
+            hist = dfb.preconditioned_conjugate_gradient(r, x, q, p, 1e-8, 20000, mat, pc)
+            t = ctx.timer_stop()
+            best = t if best is None else min(best, t)
+        its = len(hist) - 1
+        rec[kind] = {"symbolic_ms": t_sym, "numeric_ms": t_num, "pcg_iters": its, "pcg_ms": best, "ms_per_iteration": best / max(its, 1),
+                     "rel_residual": hist[-1] / hist[0]}
+        del pc
+    rec["ilu0_over_jacobi_time"] = rec["ilu0"]["pcg_ms"] / rec["jacobi"]["pcg_ms"]
+    return rec
+
+
 def run_ours_config34(env):
     """BASELINE config 3 or 4 as the measured workload; N > 1 runs N independent replicas (the path shards by problem here)"""
     args = env.args
@@ -836,7 +880,8 @@ def run_ours_headline(env):
             if not dist_par["ok"]:
                 rc = 3
         elif rank == 0:
-            configs = {"c3": cloth_record(env, with_cpu=not args.no_cpu), "c4": beam_record(env, with_cpu=not args.no_cpu)}
+            configs = {"c3": cloth_record(env, with_cpu=not args.no_cpu), "c4": beam_record(env, with_cpu=not args.no_cpu),
+                       "c2_ilu0": ilu_record(env)}
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
         cpu = cpu_elasticity_record(n, EXPECTED_ITERS.get(n, iters[0]))
