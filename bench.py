@@ -18,7 +18,8 @@ Beside the headline the same JSON line carries (so that one driver run sees them
                 ms/iteration, in-loop SpMV GB/s, true residual.  The 1 -> 8 ratio of its ms_per_step is the >= 6x target.
   dist_parity   (N > 1) a small slab problem and a shuffled-then-RCM general mesh solved distributed and on rank 0 alone: owned rows
                 bit-identical, iteration count +-1, |x - x1| / |x1| < 1e-7.  A failure makes the run exit non-zero.
-  configs       (N = 1) compact records of BASELINE configs 3 (2048^2 mass-spring cloth: 10 steps x (reassembly + CG 1e-5)) and
+  configs       (N = 1) compact records of BASELINE configs 1 (2-D Poisson disk, ~10 k vertices: assembly + CG), 2 (S1: the headline
+                step at 1.03 M DoF), 3 (2048^2 mass-spring cloth: 10 steps x (reassembly + CG 1e-5)) and
                 4 (16 x 16 x 256-cell neo-Hookean beam: Newton ramp, reassembly + Jacobi-PCG per iteration) with their phase split,
                 and c2_ilu0: config 2 (S1) solved with the reference's own default preconditioner ILU(0) beside Jacobi.
   true_rel_residual   ||b - A x|| / ||b|| of the last headline solve, recomputed with one (distributed) SpMV after the timed region.
@@ -717,6 +718,94 @@ def run_ours(args):
     return rc
 
 
+def c1_record(env, n=100, with_cpu=False):
+    """BASELINE config 1: scalar Laplacian on a ~10 k-vertex triangulated disk, assembly (CSR + separate diagonal) + CG to 1e-8
+    through the same entry points the reference's own test uses (laplace_tri2::ddw_ -> merge -> set_fixed_bc -> conjugate_gradient)"""
+    from del_fem_b200 import synthetic
+    dfb, ctx = env.dfb, env.ctx
+    t2v, xy = synthetic.grid_tri_mesh(n, disk=True)
+    nv = xy.shape[0]
+    idx = np.arange(nv)
+    i, j = idx % (n + 1), idx // (n + 1)
+    flag_h = ((i == 0) | (i == n) | (j == 0) | (j == n)).astype(np.int32).reshape(nv, 1)
+    p = xy[t2v.astype(np.int64)]
+    area = 0.5 * ((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 2, 0] - p[:, 0, 0]) * (p[:, 1, 1] - p[:, 0, 1]))
+    rhs_h = np.zeros((nv, 1))
+    np.add.at(rhs_h[:, 0], t2v.astype(np.int64).reshape(-1), np.repeat(area / 3.0, 3))   # -lap u = 1
+    rhs_h[flag_h != 0] = 0.0
+    mesh = dfb.Mesh(ctx, t2v, xy)
+    pat = dfb.Pattern.from_uniform_mesh(ctx, mesh, False)
+    plan = dfb.Plan(ctx, pat, mesh, 1)
+    mat = dfb.Matrix(ctx, pat, 1)
+    flag = dfb.BcFlag(ctx, flag_h)
+    rhs = dfb.Vec.from_numpy(ctx, rhs_h)
+    r, u, ap, pv = (dfb.Vec(ctx, nv, 1) for _ in range(4))
+    best, its = None, 0
+    for _ in range(4):
+        ctx.timer_start()
+        mat.assemble(plan, "laplace_tri2", mesh, 1.0)
+        mat.set_fixed_dof_dev(1.0, flag)
+        t_asm = ctx.timer_stop()
+        r.copy_from(rhs)
+        ctx.timer_start()
+        hist = dfb.conjugate_gradient(r, u, ap, pv, 1e-8, 3000, mat)
+        t_cg = ctx.timer_stop()
+        its = len(hist)
+        if best is None or t_asm + t_cg < best[0] + best[1]:
+            best = (t_asm, t_cg)
+    rec = {"workload": f"2-D Poisson on a {nv}-vertex triangulated disk ({t2v.shape[0]} triangles), assembly + BC + CG to 1e-8",
+           "assembly_bc_ms": best[0], "cg_ms": best[1], "cg_iters": its, "us_per_iteration": 1e3 * best[1] / max(its, 1),
+           "value": nv * its / ((best[0] + best[1]) * 1e-3) / 1e6, "unit": UNIT,
+           "u_center": float(u.download()[n // 2 + (n + 1) * (n // 2), 0]), "u_center_exact": 0.25,
+           "note": "10 k unknowns: three launches of a few microseconds per iteration, launch-latency-bound by construction"}
+    if with_cpu:
+        import oracle as orc
+        orc.build()
+        t2v64 = t2v.astype(np.uint64)
+        t0 = time.perf_counter()
+        r2i, i2c = orc.vtx2vtx_from_uniform_mesh(t2v64, 3, nv, False)
+        rv, iv = orc.assemble("laplace_tri2", 0, t2v64, xy, 1.0, 0.0, r2i, i2c)
+        orc.set_fixed_bc(1.0, flag_h, rv, iv, r2i, i2c)
+        t_a = time.perf_counter() - t0
+        ro = rhs_h.copy()
+        uo, apo, po = np.zeros_like(ro), np.zeros_like(ro), np.zeros_like(ro)
+        t0 = time.perf_counter()
+        ho = orc.conjugate_gradient(ro, uo, apo, po, 1e-8, 3000, r2i, i2c, iv, rv)
+        t_c = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": nv * len(ho) / (t_a + t_c) / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"the whole config on one host core: pattern + assembly + BC {t_a * 1e3:.1f} ms, CG {len(ho)} iterations {t_c * 1e3:.1f} ms",
+                               "cg_iters": len(ho)}
+    return rec
+
+
+def c2_record(env, n=70, steps=3, with_cpu=False):
+    """BASELINE config 2 at its own size (S1, 1.03 M DoF): the headline step (fused assembly + rhs + BC + Jacobi-PCG to 1e-8)"""
+    from del_fem_b200.workload import Problem
+    ctx = env.ctx
+    prob = Problem(env.dfb, ctx, n, n, n, 0, 1, "jacobi")
+    prob.step(max_it=20000)
+    ctx.profile_spmv(reset=True)
+    asm, tot, its = 0.0, 0.0, 0
+    for _ in range(steps):
+        a, t, its = prob.step(max_it=20000)
+        asm += a
+        tot += t
+    sp_ms, sp_n = ctx.profile_spmv(reset=True)
+    nnz, nb = prob.pat.nnz, prob.slab.n_own
+    b_spmv = 76 * nnz + 124 * nb
+    rec = {"workload": f"S1: {n}^3-vertex Kuhn tet cube, {3 * n ** 3} DoF, linear elasticity, z=0 clamped, jacobi-PCG to 1e-8",
+           "ms_per_step": tot / steps, "assembly_ms": asm / steps, "pcg_iters": its, "ms_per_iteration": (tot - asm) / steps / max(its, 1),
+           "value": 3 * n ** 3 * its / (tot / steps * 1e-3) / 1e6, "unit": UNIT, "true_rel_residual": prob.true_rel_residual()}
+    if sp_n:
+        rec["spmv_in_loop_ms"] = sp_ms / sp_n
+        rec["spmv_in_loop_gbs"] = b_spmv / (sp_ms / sp_n * 1e-3) / 1e9
+        rec["spmv_frac_of_peak"] = rec["spmv_in_loop_gbs"] / env.peak
+    del prob
+    if with_cpu:
+        rec["cpu_baseline"] = cpu_elasticity_record(n, EXPECTED_ITERS.get(n, its), k=10, reps=2)
+    return rec
+
+
 def ilu_record(env, n=70):
     """BASELINE config 2 (S1) solved with the reference's OWN default preconditioner, ILU(0) (del-fem-ls/src/linearsystem.rs:53),
     beside Jacobi on the same system: setup (symbolic + numeric), iterations, ms per iteration, time to solution"""
@@ -880,7 +969,8 @@ def run_ours_headline(env):
             if not dist_par["ok"]:
                 rc = 3
         elif rank == 0:
-            configs = {"c3": cloth_record(env, with_cpu=not args.no_cpu), "c4": beam_record(env, with_cpu=not args.no_cpu),
+            configs = {"c1": c1_record(env, with_cpu=not args.no_cpu), "c2": c2_record(env, with_cpu=not args.no_cpu),
+                       "c3": cloth_record(env, with_cpu=not args.no_cpu), "c4": beam_record(env, with_cpu=not args.no_cpu),
                        "c2_ilu0": ilu_record(env)}
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:

@@ -37,6 +37,24 @@ def kuhn_tet_mesh(nx, ny=None, nz=None, h=None, k_begin=0, k_end=None, index_dty
     return e2v.reshape(-1, 4), xyz
 
 
+def grid_tri_mesh(n, disk=False, index_dtype=np.uint32):
+    """n x n cells of [-1,1]^2 split into 2 n^2 triangles, optionally mapped onto the unit disk (the config-1 stand-in
+    for the reference's Delaunay disk). -> (tri2vtx [2 n^2, 3], vtx2xy [(n+1)^2, 2])"""
+    m = n + 1
+    g = -1.0 + 2.0 * np.arange(m) / float(n)
+    s, t = np.meshgrid(g, g)   # s varies fastest (i), t = rows (j)
+    x, y = (s * np.sqrt(1.0 - 0.5 * t * t), t * np.sqrt(1.0 - 0.5 * s * s)) if disk else (s, t)
+    xy = np.ascontiguousarray(np.stack([x.ravel(), y.ravel()], 1))
+    i, j = np.meshgrid(np.arange(n, dtype=np.int64), np.arange(n, dtype=np.int64))
+    v00 = (i + m * j).ravel()
+    v10, v01 = v00 + 1, v00 + m
+    v11 = v01 + 1
+    t2v = np.empty((v00.size, 2, 3), dtype=index_dtype)
+    t2v[:, 0, 0], t2v[:, 0, 1], t2v[:, 0, 2] = v00, v10, v11
+    t2v[:, 1, 0], t2v[:, 1, 1], t2v[:, 1, 2] = v00, v11, v01
+    return t2v.reshape(-1, 3), xy
+
+
 def splitmix_uniform(seed, first_idx, n, lo, hi):
     """same hash as dfb_vec_fill_splitmix (uniform in [lo,hi), indexed by first_idx + i)"""
     with np.errstate(over="ignore"):

@@ -25,6 +25,16 @@ def test_numpy_kuhn_slab_is_a_window_of_the_global_mesh(orc):
     assert np.array_equal(e_w.astype(np.int64) + kb * nx * ny, e_g[inside].astype(np.int64))
 
 
+def test_numpy_tri_grid_equals_oracle_mesh(orc):
+    """bench.py's config-1 workload generator (numpy) against the oracle's serial generator: connectivity equal, coordinates bit-exact"""
+    from del_fem_b200 import synthetic
+    for disk in (False, True):
+        t2v, xy = synthetic.grid_tri_mesh(9, disk=disk)
+        t2v_o, xy_o = orc.grid_tri_mesh(9, disk=disk)
+        assert np.array_equal(t2v.astype(np.uint64), t2v_o)
+        assert np.array_equal(xy, xy_o)
+
+
 def test_numpy_splitmix_equals_oracle_splitmix(orc):
     from del_fem_b200 import synthetic
     for seed, first, n in [(0, 0, 1000), (3, 12345, 257)]:
