@@ -30,6 +30,8 @@ struct DfbIlu {
   double *d_val = nullptr;        // factor values [nnz*NN]
   double *d_z = nullptr;          // explicit preconditioned residual for PCG [n*N]
   uint32_t *d_epoch = nullptr;    // [8] grid-barrier counter of the persistent sweeps at [4]
+  uint32_t *d_pos = nullptr;      // [n] position of a row in the forward level order (inverse of d_rows_f)
+  double *d_yp = nullptr;         // [n*N] the vector the persistent sweeps exchange, stored in forward level order
   struct Sweep {                  // persistent sweep of one direction
     std::vector<uint32_t> lev_rec;   // records of level l: [lev_rec[l], lev_rec[l+1])
     uint2 *d_groups = nullptr;       // per record {first position in the level-ordered row list, rows}
@@ -221,8 +223,12 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
 // grid-wide barrier between levels.
 // Sweep-ordered factor copy: after every decompose the rows' strictly-lower (forward) / strictly-upper (backward) entries are
 // re-laid in the order the sweep visits them, in records of RPW rows (= the rows one warp handles at a time, cut at level
-// boundaries):   [ uint4 {row, entries here, first / end of the entries beyond KS in the canonical arrays} x RPW
-//                | columns [KS][RPW] | blocks [KS][N][RPW*N] (component a of row r at r*N + a) | D^-1 [N][RPW*N] (forward) ]
+// boundaries):   [ uint4 {row, entries here, first / end of the entries beyond KS in the canonical arrays} x RPW | position [RPW]
+//                | neighbour positions [KS][RPW] | blocks [KS][N][RPW*N] (component a of row r at r*N + a) | D^-1 [N][RPW*N] (forward) ]
+// and the vector the levels exchange (yp) is stored in the same FORWARD LEVEL ORDER ("position"): the rows of a record are
+// consecutive there, and so — on a structured mesh — are their k-th neighbours in the earlier levels, so a warp's gather of a
+// neighbour touches 2-3 memory lines instead of 8-16. The forward sweep reads the right-hand side from the row-ordered vector
+// and writes yp; the backward sweep works on yp and writes the result back in row order.
 // A warp fetches its record with ONE bulk copy (TMA, evict-first: the factor streams through L2 once per sweep and must not
 // push out the vector the levels exchange through L2), two items ahead, into its own double buffer in shared memory. The
 // canonical row-major blocks cost 8 memory wavefronts per load instruction — one per row — and the sweeps were bound by
@@ -246,7 +252,8 @@ static const int ILU_KS = 8;                   // entries per row held in the sw
 static const uint32_t ILU_NONE = 0xFFFFFFFFu;
 template <int N, bool FORWARD> struct IluRec {
   static constexpr int RPW = IluLanes<N>::RPW, RN = RPW * N;
-  static constexpr int OFF_COL = RPW * 16;
+  static constexpr int OFF_POS = RPW * 16;
+  static constexpr int OFF_COL = OFF_POS + RPW * 4;
   static constexpr int OFF_W = OFF_COL + ILU_KS * RPW * 4;
   static constexpr int OFF_DIA = OFF_W + ILU_KS * N * RN * 8;
   static constexpr int BYTES = (OFF_DIA + (FORWARD ? N * RN * 8 : 0) + 127) / 128 * 128;
@@ -265,7 +272,8 @@ template <int N, bool FORWARD>
 __global__ void __launch_bounds__(256) k_ilu_slice(const uint2 *__restrict__ groups, uint32_t n_groups, const uint32_t *__restrict__ rows,
                                                    const uint32_t *__restrict__ r2i, const uint32_t *__restrict__ diap,
                                                    const uint32_t *__restrict__ col, const double *__restrict__ val,
-                                                   const double *__restrict__ dia, unsigned char *__restrict__ rec) {
+                                                   const double *__restrict__ dia, const uint32_t *__restrict__ pos,
+                                                   unsigned char *__restrict__ rec) {
   using R = IluRec<N, FORWARD>;
   constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = R::RPW, RN = R::RN, KS = ILU_KS;
   const unsigned lane = threadIdx.x & 31u, sub = lane % LPR, r = lane / LPR;
@@ -281,9 +289,13 @@ __global__ void __launch_bounds__(256) k_ilu_slice(const uint2 *__restrict__ gro
       ke = FORWARD ? diap[i] : r2i[i + 1];
     }
     const uint32_t cnt = min(ke - kb, (uint32_t)KS);
-    if (sub == 0) reinterpret_cast<uint4 *>(p)[r] = make_uint4(i, cnt, kb + cnt, ke);
+    if (sub == 0) {
+      reinterpret_cast<uint4 *>(p)[r] = make_uint4(i, cnt, kb + cnt, ke);
+      reinterpret_cast<uint32_t *>(p + R::OFF_POS)[r] = live ? pos[i] : 0u;
+    }
+    // neighbours are addressed by their POSITION in the forward level order: the sweeps exchange a vector stored in that order
     uint32_t *pc = reinterpret_cast<uint32_t *>(p + R::OFF_COL);
-    for (uint32_t k = sub; k < (uint32_t)KS; k += LPR) pc[k * RPW + r] = k < cnt ? col[kb + k] : 0u;
+    for (uint32_t k = sub; k < (uint32_t)KS; k += LPR) pc[k * RPW + r] = k < cnt ? pos[col[kb + k]] : 0u;
     if (sub < (unsigned)N) {
       double *pw = reinterpret_cast<double *>(p + R::OFF_W);
       for (uint32_t k = 0; k < (uint32_t)KS; ++k)
@@ -332,8 +344,8 @@ template <int N, bool FORWARD> struct IluSweepSmem {   // dynamic shared memory 
 
 template <int N, bool FORWARD, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__restrict__ rec, const uint2 *__restrict__ items, uint32_t n_items,
-                                                       const uint32_t *__restrict__ col, const double *__restrict__ val, double *vec,
-                                                       unsigned int *bar) {
+                                                       const uint32_t *__restrict__ col, const double *__restrict__ val,
+                                                       const uint32_t *__restrict__ pos, double *vec, double *yp, unsigned int *bar) {
   using R = IluRec<N, FORWARD>;
   constexpr int NN = N * N, LPR = IluLanes<N>::LPR, RPW = R::RPW, RN = R::RN, KS = ILU_KS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -384,12 +396,14 @@ __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__re
     const uint4 h = reinterpret_cast<const uint4 *>(buf)[r];   // {row, entries here, first / end of the entries beyond KS}
     const bool live = h.x != ILU_NONE;
     const uint32_t i = live ? h.x : 0u, cnt = h.y;
+    const uint32_t own = reinterpret_cast<const uint32_t *>(buf + R::OFF_POS)[r];   // the row's position in the forward level order
     const uint32_t *pc = reinterpret_cast<const uint32_t *>(buf + R::OFF_COL);
-    double t = live ? __ldcg(vec + (uint64_t)i * N + a_) : 0.0;
+    // forward: the right-hand side comes from vec (row order); backward: the forward result from yp (level order)
+    double t = !live ? 0.0 : FORWARD ? __ldcg(vec + (uint64_t)i * N + a_) : __ldcg(yp + (uint64_t)own * N + a_);
     double xv[KS];
 #pragma unroll
     for (int q = 0; q < KS; ++q)   // lane a reads component a of the neighbour (written by other SMs in earlier levels: L2)
-      xv[q] = ((uint32_t)q < cnt && act) ? __ldcg(vec + (uint64_t)pc[q * RPW + r] * N + a_) : 0.0;
+      xv[q] = ((uint32_t)q < cnt && act) ? __ldcg(yp + (uint64_t)pc[q * RPW + r] * N + a_) : 0.0;
     ILU_TRACE(1);
     const double *pw = reinterpret_cast<const double *>(buf + R::OFF_W);
 #pragma unroll
@@ -400,10 +414,10 @@ __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__re
       if ((uint32_t)q < cnt) t -= acc;
     }
     for (uint32_t q = h.z; q < h.w; ++q) {   // rows longer than the record (ILU(k) fill): the canonical arrays
-      const uint32_t c = col[q];
+      const uint32_t c = pos[col[q]];
       double acc = 0.0;
 #pragma unroll
-      for (int d = 0; d < N; ++d) acc = acc + val[(uint64_t)q * NN + a_ + N * d] * __ldcg(vec + (uint64_t)c * N + d);
+      for (int d = 0; d < N; ++d) acc = acc + val[(uint64_t)q * NN + a_ + N * d] * __ldcg(yp + (uint64_t)c * N + d);
       t -= acc;
     }
     __syncwarp();
@@ -414,7 +428,10 @@ __global__ void __launch_bounds__(THREADS) k_ilu_sweep(const unsigned char *__re
       for (int d = 0; d < N; ++d) acc = acc + pd[d * RN + r * N + a_] * __shfl_sync(0xFFFFFFFFu, t, base + d);
       t = acc;
     }
-    if (live && act) vec[(uint64_t)i * N + a_] = t;
+    if (live && act) {
+      yp[(uint64_t)own * N + a_] = t;
+      if (!FORWARD) vec[(uint64_t)i * N + a_] = t;   // the result, back in row order
+    }
 #ifdef DFB_ILU_TRACE
     if (t == 1.2345e300) g_ilu_trace[8191] = 1;   // the clock read behind the rows must wait for their result
 #endif
@@ -476,6 +493,8 @@ void dfb_ilu_destroy(DfbIlu *s) {
   dfb_dev_free(s->d_val);
   dfb_dev_free(s->d_z);
   dfb_dev_free(s->d_epoch);
+  dfb_dev_free(s->d_pos);
+  dfb_dev_free(s->d_yp);
   for (DfbIlu::Sweep *w : {&s->fwd, &s->bwd}) {
     dfb_dev_free(w->d_groups);
     dfb_dev_free(w->d_rec);
@@ -632,6 +651,13 @@ dfb_status dfb_ilu_create(dfb_ctx *c, const dfb_bsr *m, uint64_t lev_fill, DfbIl
   };
   records(s->lev_f, true, s->fwd);
   records(s->lev_b, false, s->bwd);
+  {
+    std::vector<uint32_t> pos(n);
+    for (uint64_t q = 0; q < n; ++q) pos[rows_f[q]] = (uint32_t)q;
+    up(&s->d_pos, pos);
+    if (st == DFB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = dfb_fail(DFB_ERR_CUDA, "ilu0: upload failed");   // pos is a local
+    if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_yp, n * N + 8);
+  }
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_epoch, 8);
   if (st == DFB_OK) cudaMemsetAsync(s->d_epoch, 0, 8 * sizeof(uint32_t), c->stream);
   if (st == DFB_OK) st = dfb_dev_alloc_t(&s->d_val, nnz * NN + 8);
@@ -714,9 +740,9 @@ template <int N>
 static dfb_status ilu_slice(dfb_ctx *c, DfbIlu *s, const double *d_dia) {
   const int g = c->sm_count * 8;
   if (s->fwd.n_rec)
-    DFB_LAUNCH(c, (k_ilu_slice<N, true>), g, 256, 0, s->fwd.d_groups, s->fwd.n_rec, s->d_rows_f, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->fwd.d_rec);
+    DFB_LAUNCH(c, (k_ilu_slice<N, true>), g, 256, 0, s->fwd.d_groups, s->fwd.n_rec, s->d_rows_f, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->d_pos, s->fwd.d_rec);
   if (s->bwd.n_rec)
-    DFB_LAUNCH(c, (k_ilu_slice<N, false>), g, 256, 0, s->bwd.d_groups, s->bwd.n_rec, s->d_rows_b, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->bwd.d_rec);
+    DFB_LAUNCH(c, (k_ilu_slice<N, false>), g, 256, 0, s->bwd.d_groups, s->bwd.n_rec, s->d_rows_b, s->d_r2i, s->d_dia, s->d_col, s->d_val, d_dia, s->d_pos, s->bwd.d_rec);
   DFB_CHECK_LAUNCH();
   return DFB_OK;
 }
@@ -750,9 +776,9 @@ static dfb_status ilu_sweeps(dfb_ctx *c, const DfbIlu *s, double *d_vec) {
   DFB_CUDA(cudaFuncSetAttribute(k_ilu_sweep<N, true, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
   DFB_CUDA(cudaFuncSetAttribute(k_ilu_sweep<N, false, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, THREADS>), n_cta, THREADS, smem_f, rec_f, it_f, nf, col, val, d_vec, bar);
+  if (nf) DFB_LAUNCH(c, (k_ilu_sweep<N, true, THREADS>), n_cta, THREADS, smem_f, rec_f, it_f, nf, col, val, s->d_pos, d_vec, s->d_yp, bar);
   DFB_LAUNCH(c, k_ilu_barrier_reset, 1, 1, 0, bar);
-  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, THREADS>), n_cta, THREADS, smem_b, rec_b, it_b, nb, col, val, d_vec, bar);
+  if (nb) DFB_LAUNCH(c, (k_ilu_sweep<N, false, THREADS>), n_cta, THREADS, smem_b, rec_b, it_b, nb, col, val, s->d_pos, d_vec, s->d_yp, bar);
   DFB_CHECK_LAUNCH();
 #ifdef DFB_ILU_TRACE
   {
