@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -54,3 +56,27 @@ def test_stdout_guard_keeps_stdout_to_one_line():
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     assert r.stdout.decode() == '{"ok": 1}\n'
     assert b"NCCL version" in r.stderr and b"python noise" in r.stderr
+
+
+@pytest.mark.gpu
+def test_ours_arm_json_line_on_a_small_workload():
+    """the product arm on one GPU with the S1 workload (seconds): ONE JSON line on stdout with every key of the contract, the
+    roofline / e2e / clocks objects filled in and a non-zero count of our own kernel launches"""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "S1", "--steps", "2", "--warmup", "3", "--no-cpu", "--no-extras"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "roofline", "clocks", "gpu_launches", "e2e", "true_rel_residual"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["dtype"] == "f64" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["gpu_launches"] > 0 and d["value"] > 0
+    assert d["pcg_iters"] == 861 and d["true_rel_residual"] < 1e-8
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.2 < rf["frac"] < 1.2
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.05
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"]
