@@ -448,8 +448,12 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
 #pragma unroll
       for (int d = 0; d < N; ++d) gacc[d] = 0.0;
       const uint32_t cb = P.nz2ptr[slot], ce = P.nz2ptr[slot + 1];
+      // the code of the NEXT contribution is fetched while this one is evaluated (ncu: the load sat at the head of every
+      // iteration's dependent chain, 6 % of the warp samples; -2.6 % on the S10 assembly)
+      uint32_t code_next = cb < ce ? P.code16[cb] : 0u;
       for (uint32_t c = cb; c < ce; ++c) {
-        const uint32_t code = P.code16[c];
+        const uint32_t code = code_next;
+        code_next = c + 1 < ce ? P.code16[c + 1] : 0u;
         const double *rec = srec + (size_t)(code >> 4) * REC;
         const int i = (int)((code >> 2) & 3u), j = (int)(code & 3u);
         double blk[NN];
