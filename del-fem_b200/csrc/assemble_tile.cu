@@ -27,6 +27,7 @@ static const int AT_BUILD_THREADS = 256;
 static const int AT_PAIR_CAP = 2048;  // (row, element) pairs per tile the builder can sort in shared memory
 static const int AT_ELEM_CAP = 4095;  // tile-local element index must fit 12 bits of the 16-bit contribution code
 static const int AT_META = 8;         // u32 per tile: k0, k1, ob, oe, pb, pe, n_elem, pad
+static const int AT_PKT = 10;         // packed records per assembly tile + 1 (a tile of up to 64 rows over 8-row records)
 
 // ------------------------------------------------------------------------------------------------ tile plan
 __device__ __forceinline__ void bitonic_sort_smem(uint32_t *keys, uint32_t P) {
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
   extern __shared__ __align__(16) double at_smem[];
   double *srec = at_smem;                                                   // [n_le][REC]
   double *sout = srec + (size_t)P.max_elem * REC;                           // [n_off + n_rows][NN]
-  uint32_t *smeta = reinterpret_cast<uint32_t *>(sout + (size_t)P.max_slots * NN);   // [AT_META]
+  uint32_t *smeta = reinterpret_cast<uint32_t *>(sout + (size_t)P.max_slots * NN);   // [AT_META] + packed-store info [AT_PK]
   const unsigned tid = threadIdx.x, T = blockDim.x;
   uint64_t tile = blockIdx.x;
   uint32_t meta_next = (tile < P.n_tiles && tid < AT_META) ? P.tile_meta[tile * AT_META + tid] : 0u;
@@ -418,6 +419,14 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
       if (nt < P.n_tiles && tid < AT_META) meta_next = P.tile_meta[nt * AT_META + tid];
     }
     const uint64_t r0 = tile * P.rows, r1 = min(r0 + (uint64_t)P.rows, P.num_rows);
+    // what phase 3 needs to find its packed records — record offsets and the row pointers at the packed-tile boundaries — is
+    // requested now (ncu: the dependent chain tile offset -> record header sat in front of the stores, 9 % of the warp samples)
+    if (out.packed.base && tid >= 32 && tid < 32 + 2 * AT_PKT) {
+      const uint32_t j = (tid - 32) % AT_PKT;
+      const uint64_t prt = (uint64_t)out.packed.rpt, row = r0 + j * prt;
+      if (tid < 32 + AT_PKT) smeta[AT_META + j] = row < r1 ? out.packed.tile_off[row / prt] : 0u;
+      else smeta[AT_META + AT_PKT + j] = P.row2idx[min(row, P.num_rows)];
+    }
     const uint32_t k0 = smeta[0], k1 = smeta[1], pb = smeta[4], n_le = smeta[6];
     const uint32_t n_off = k1 - k0, n_rows = (uint32_t)(r1 - r0), eoff = pb - P.pair_base;
     // ---- phase 1: per-element records into shared memory (one thread per listed element)
@@ -479,13 +488,15 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
     // ---- phase 3: contiguous, coalesced stores
     if (out.packed.base) {
       const uint64_t prt = (uint64_t)out.packed.rpt;   // 8 or 16: the assembly tile (16 rows) is a whole number of packed tiles
-      for (uint64_t pt = r0 / prt; pt * prt < r1; ++pt) {
+      uint32_t j = 0;
+      for (uint64_t pt = r0 / prt; pt * prt < r1; ++pt, ++j) {
         const uint64_t pr0 = pt * prt, pr1 = min(pr0 + prt, P.num_rows);
-        double *vals = pk_tile_values(out.packed, pt);                 // [8 diagonal blocks | the tile's off-diagonal blocks]
+        const uint32_t pk0 = smeta[AT_META + AT_PKT + j], nb = smeta[AT_META + AT_PKT + j + 1] - pk0;
+        // [diagonal blocks | the tile's off-diagonal blocks] of packed record pt (the header and the columns precede them)
+        double *vals = reinterpret_cast<double *>(out.packed.base + ((uint64_t)smeta[AT_META + j] << 4) + out.packed.hdr + ((nb * 4u + 15u) & ~15u));
         const uint32_t nd = (uint32_t)(pr1 - pr0) * NN;
         const double *sd = sout + (size_t)(n_off + (pr0 - r0)) * NN;
         for (uint32_t q = tid; q < nd; q += T) vals[q] = sd[q];
-        const uint32_t pk0 = P.row2idx[pr0], nb = P.row2idx[pr1] - pk0;
         const double *sv = sout + (size_t)(pk0 - k0) * NN;
         double *ov = vals + prt * NN;
         for (uint32_t q = tid; q < nb * NN; q += T) ov[q] = sv[q];
@@ -510,7 +521,7 @@ static dfb_status launch_tile(dfb_plan *plan, const typename Model::Args &args, 
   if (c->assemble_tile_threads > 0) threads = (int)c->assemble_tile_threads;
   if (threads < 64) threads = 64;
   if (threads > AT_MAX_THREADS) threads = AT_MAX_THREADS;
-  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double) + AT_META * sizeof(uint32_t) + 16;
+  const size_t smem = ((size_t)plan->tile_max_elem * Model::REC + (size_t)plan->tile_max_slots * NN) * sizeof(double) + (AT_META + 2 * AT_PKT) * sizeof(uint32_t) + 16;
   if (smem > 200 * 1024) return DFB_ERR_UNSUPPORTED;  // caller falls back (no error string: not a failure)
   TileOut out;
   if (dfb_bsr_packed_native(m)) {
