@@ -445,6 +445,14 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
       // the element's energy is recorded once: by the tile that holds its lowest-numbered vertex
       if (Model::HAS_GRAD && w_elem && vmin / P.rows == tile) w_elem[e] = w;
     }
+    // the first slot's list bounds and first code do not depend on the records: requested before the barrier
+    uint32_t pre_cb = 0, pre_ce = 0, pre_code = 0;
+    if (tid < n_off + n_rows) {
+      const uint64_t slot0 = tid >= n_off ? P.nnz + r0 + (tid - n_off) : (uint64_t)k0 + tid;
+      pre_cb = P.nz2ptr[slot0];
+      pre_ce = P.nz2ptr[slot0 + 1];
+      pre_code = pre_cb < pre_ce ? P.code16[pre_cb] : 0u;
+    }
     __syncthreads();
     // ---- phase 2: one thread per slot (off-diagonal slots [k0, k1), then the diagonal slots of rows [r0, r1)): walk the list in
     // ascending element order (= the serial loop's accumulation order, same bits), accumulate in registers
@@ -456,10 +464,11 @@ __global__ void __launch_bounds__(AT_MAX_THREADS) k_assemble_tile(const typename
       for (int q = 0; q < NN; ++q) acc[q] = 0.0;
 #pragma unroll
       for (int d = 0; d < N; ++d) gacc[d] = 0.0;
-      const uint32_t cb = P.nz2ptr[slot], ce = P.nz2ptr[slot + 1];
+      const bool first = s == tid;
+      const uint32_t cb = first ? pre_cb : P.nz2ptr[slot], ce = first ? pre_ce : P.nz2ptr[slot + 1];
       // the code of the NEXT contribution is fetched while this one is evaluated (ncu: the load sat at the head of every
       // iteration's dependent chain, 6 % of the warp samples; -2.6 % on the S10 assembly)
-      uint32_t code_next = cb < ce ? P.code16[cb] : 0u;
+      uint32_t code_next = first ? pre_code : (cb < ce ? P.code16[cb] : 0u);
       for (uint32_t c = cb; c < ce; ++c) {
         const uint32_t code = code_next;
         code_next = c + 1 < ce ? P.code16[c + 1] : 0u;
