@@ -238,13 +238,13 @@ __global__ void k_ilu_backward_level(const uint32_t *__restrict__ rows, uint32_t
 // D^-1 product move between the lanes by shuffle — so every rounding is the one of the one-thread-per-row kernels above
 // (bit-identical, tested).
 // Work items (one pass of the grid over part of a level) are built on the host for the launch shape and staged in shared memory.
-// Measured (tools/precond_compare.py, profiles/r2_precond_compare.txt): S1 1.27 ms per PCG iteration (round 1, one launch per
-// level: 6.4), S10 4.3 (41.7). What remains per level at S1 (in-kernel clocks): ~1.5 us grid barrier (tools/micro/gridbar.cu) +
+// Measured (tools/precond_compare.py, profiles/r2_precond_compare.txt): S1 1.23 ms per PCG iteration (round 1, one launch per
+// level: 6.4), S10 4.1 (41.7). What remains per level at S1 (in-kernel clocks): ~1.5 us grid barrier (tools/micro/gridbar.cu) +
 // ~0.5 us until the neighbours' values arrive + ~0.3 us arithmetic.
-// Built, measured slower and removed: per-row epoch flags polled by the dependent rows (sync-free, Liu et al.: 11-13 ms per
-// iteration at S1, 0.78 G L2 requests of polling per sweep); one thread per row with register prefetch of the canonical
-// entries (3.8 ms); the whole sweep on ONE 16-CTA thread-block cluster with the hardware cluster barrier (1.6 ms at S1, 29 ms
-// at S10: 16 SMs' load pipes carry ~100 rows each per level); tree barriers (group counters -> root -> release flags: 3.7-8.3 us).
+// Built, measured slower and removed: per-row ready flags polled by the dependent rows (sync-free, Liu et al.), also
+// with the exchanged values as their own flags on this kernel (3.2 ms at S1); one thread per row with register prefetch of the
+// canonical entries (3.8 ms); the whole sweep on ONE 16-CTA thread-block cluster with the hardware cluster barrier (1.4 ms at
+// S1, 8.6 ms at S10); tree barriers (group counters -> root -> release flags: 3.7-8.3 us).
 template <int N> struct IluLanes {   // lanes per row (N = 3: the 4th lane of a quad idles) and rows per warp
   static constexpr int LPR = (N == 3) ? 4 : N, RPW = 32 / LPR;
 };
